@@ -1,0 +1,145 @@
+/*
+ * suriko-b200 — C ABI of the B200-native bundle-adjustment engine.
+ *
+ * Drop-in boundary for suriko-engine's Kanatani BA path.  "BA.h" / "BA.cpp" below are
+ *   /root/reference/cpp_impl/suriko-engine/include/suriko/bundle-adj-kanatani.h
+ *   /root/reference/cpp_impl/suriko-engine/src/bundle-adj-kanatani.cpp
+ * Every entry point is extern "C", takes plain pointers and sizes (host memory unless the name says "dev"),
+ * never throws and never aborts: the return value is 0 on success or a negative SRK_E_* code.
+ *
+ * Threading contract (same as the reference, BA.h:136-163): one handle = one CUDA device + stream; calls on a
+ * handle are serialised by the caller; a handle may be reused across problems (work buffers are cached).
+ *
+ * There is no CPU fallback: srk_ba_create fails with SRK_E_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef SRK_BA_C_API_H
+#define SRK_BA_C_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRK_OK 0
+#define SRK_E_INVALID_ARG (-1)   /* null pointer, f0 ~ 0 (BA.cpp:420), bad unity_comp_ind (BA.cpp:628), unsorted observations */
+#define SRK_E_NO_DEVICE (-2)     /* no CUDA device / wrong architecture */
+#define SRK_E_CUDA (-3)          /* a CUDA call failed; srk_last_error() has the text */
+#define SRK_E_NOT_BOUND (-4)     /* run/fetch/debug call before srk_ba_bind */
+#define SRK_E_TOO_LARGE (-5)     /* reduced camera system does not fit the selected solver */
+
+/* Stop reasons: BA.cpp:751, :866-868, :882; 5 = NormalizeSceneInplace failed (BA.cpp:681-682, empty string in the
+ * reference); 6 = max_outer_iters reached (an extension: the reference has no iteration cap, quirk Q9). */
+#define SRK_STOP_NONE 0
+#define SRK_STOP_ABS_ERR_THRESHOLD 1      /* "abs err threshold"            -> returns true  */
+#define SRK_STOP_SMALL_ERR_CHANGE 2       /* "small relative err change"    -> returns true  */
+#define SRK_STOP_HESSIAN_OVERFLOW 3       /* "hessian overflow"             -> returns false */
+#define SRK_STOP_ERR_CONVERGED 4          /* "err converged to limit value" -> returns false */
+#define SRK_STOP_NORMALIZATION_FAILED 5
+#define SRK_STOP_MAX_ITERS 6
+
+/* Reduced-camera solver selection (north_star kernel 3). */
+#define SRK_SOLVER_AUTO 0          /* dense Cholesky when the reduced system is small/dense enough, else PCG */
+#define SRK_SOLVER_DENSE_CHOLESKY 1
+#define SRK_SOLVER_BLOCK_PCG 2
+
+/*
+ * Flat problem.  Replaces the (FragmentMap&, vector<SE3Transform>&, CornerTrackRepository&, K) argument pack of
+ * BundleAdjustmentKanatani::ComputeInplace (BA.h:179-184).  The adapter in include/suriko_compat/ builds it from the
+ * reference's containers through GetCorner/EachCorner (quirks Q10, Q11 of SURVEY.md section 8).
+ */
+typedef struct srk_ba_problem {
+    int64_t n_cams, n_points, n_obs;
+    const int32_t* obs_cam;    /* [n_obs]   frame_ind                                                              */
+    const int32_t* obs_point;  /* [n_obs]   pnt_ind = running index over tracks that own a SalientPointId (BA.cpp:1161-1171);
+                                            observations sorted by (pnt_ind, frame_ind), at most one per pair      */
+    const double* obs_xy;      /* [2*n_obs] pixels as stored in CornerData.pixel_coord (obs-geom.h:245-249)        */
+    double* points;            /* [3*n_points] in/out, indexed by pnt_ind                                          */
+    double* cams;              /* [12*n_cams] in/out: T[3] then R column-major[9] — byte-compatible with
+                                            suriko::SE3Transform (obs-geom.h:177-190); inverse (camera-from-world) poses */
+    const double* K;           /* [9] (shared) or [9*n_cams], column-major — byte-compatible with Eigen::Matrix<Scalar,3,3>;
+                                            never written (quirk Q2: BA.cpp:2026-2035 drops the intrinsic corrections) */
+    int32_t shared_K;          /* 1: K is one matrix for all frames (BA.h shared_intrinsic_cam_mat), 0: one per frame */
+    double f0;                 /* numerical-stability scale (BA.h:128-130)                                         */
+} srk_ba_problem;
+
+typedef struct srk_ba_options {
+    int32_t has_err_change;            /* BundleAdjustmentKanataniTermCriteria::AllowedReprojErrRelativeChange (BA.h:84-85) */
+    double err_change;
+    int32_t has_max_hessian_factor;    /* ...::MaxHessianFactor (BA.h:89-90)                                         */
+    double max_hessian_factor;
+    int32_t unity_comp_ind;            /* BA.h:134 unity_t1_comp_ind_, default 1                                      */
+    double unity_comp_value;           /* BA.h:133 unity_t1_comp_value_, default 1.0                                  */
+    int32_t max_outer_iters;           /* 0 = unlimited (reference behaviour)                                         */
+    int32_t solver;                    /* SRK_SOLVER_*                                                                */
+    int32_t pcg_max_iters;             /* 0 = default                                                                 */
+    double pcg_rel_tol;                /* 0 = default (1e-13)                                                         */
+} srk_ba_options;
+
+typedef struct srk_ba_report {
+    int32_t converged;                 /* return value of ComputeInplace                                             */
+    int32_t stop_reason;               /* SRK_STOP_*; srk_stop_reason_string() gives OptimizationStatusString()      */
+    int32_t outer_iters;               /* outer LM iterations started                                                */
+    int32_t attempts;                  /* solve attempts (EstimateCorrections + ApplyCorrections + ReprojError)      */
+    double err_initial, err_final;     /* sum of squared residuals in (pix/f0)^2 (BA.cpp:479-482)                     */
+    double hessian_factor_final;
+    int64_t seen_points;               /* number of observations (seen_points_count, BA.cpp:483)                      */
+    double* err_trace;                 /* optional [err_trace_cap]: accepted error after each successful outer iteration */
+    int32_t err_trace_cap, err_trace_len;
+    double* attempt_trace;             /* optional [4*attempt_trace_cap]: hessian_factor, err_new, accepted, skipped_points */
+    int32_t attempt_trace_cap, attempt_trace_len;
+    int64_t gpu_launches;              /* kernels launched by this call                                              */
+    int32_t solver_used;               /* SRK_SOLVER_DENSE_CHOLESKY or SRK_SOLVER_BLOCK_PCG                           */
+    int32_t pcg_iters_last;
+} srk_ba_report;
+
+void srk_ba_default_options(srk_ba_options* opt);
+const char* srk_stop_reason_string(int32_t stop_reason);
+const char* srk_last_error(void);
+int srk_abi_version(void);
+
+/* Handle life cycle.  device_ids may be null (device 0); n_devices must be 1 (one process per GPU; multi-GPU runs use
+ * one handle per rank plus srk_ba_set_allreduce). */
+int srk_ba_create(void** h, const int* device_ids, int n_devices);
+void srk_ba_destroy(void* h);
+
+/* One-call path == BundleAdjustmentKanatani::ComputeInplace (BA.cpp:617-718): upload, normalise, LM loop, revert,
+ * download.  points/cams are refined in place. */
+int srk_ba_solve(void* h, srk_ba_problem* problem, const srk_ba_options* opt, srk_ba_report* rep);
+
+/* == static BundleAdjustmentKanatani::ReprojError (BA.cpp:589-600): no normalisation, state untouched. */
+int srk_ba_reproj_error(void* h, const srk_ba_problem* problem, double* err, int64_t* seen_points);
+
+/* Split path (what srk_ba_solve is made of); keeps the scene resident in HBM between calls. */
+int srk_ba_bind(void* h, const srk_ba_problem* problem, const srk_ba_options* opt);  /* H2D + NormalizeSceneInplace; returns 1 if normalisation failed */
+int srk_ba_run(void* h, const srk_ba_options* opt, srk_ba_report* rep);              /* ComputeOnNormalizedWorld on the resident state */
+int srk_ba_reset(void* h);                                                           /* resident state <- state as bound (device copy) */
+int srk_ba_fetch(void* h, srk_ba_problem* problem);                                  /* RevertNormalization + D2H into points/cams */
+
+/* Multi-GPU plumbing: the host (torch.distributed / NCCL, or gloo in CPU tests) provides an in-place sum all-reduce over
+ * `count` doubles at device pointer `dev`, ordered on CUDA stream `stream`.  Each rank binds its own shard of points with
+ * all cameras replicated; the engine reduces G, g_f, S, rhs and the error partials. */
+typedef int (*srk_allreduce_fn)(void* user, double* dev, int64_t count, void* stream);
+int srk_ba_set_allreduce(void* h, srk_allreduce_fn fn, void* user, int rank, int world_size);
+
+/* Parity hooks: one derivative pass (+ one two-phase solve at damping c when c >= 0) on the resident normalised state.
+ * Any output may be null.  Layouts match oracle/srk_oracle_capi.cpp::srk_oracle_derivs_and_solve:
+ *   gradE[3N+10M]; E[9N] per point row-major 3x3; G[100M] per frame row-major 10x10; Fblk[30*n_obs] per observation
+ *   row-major 3x10; S[n_f*n_f] column-major (lower triangle valid, upper mirrored); rhs[n_f]; skipped[N];
+ *   corrections[3N+10M] (gaps re-inserted, BA.cpp:1600-1679). */
+int srk_ba_debug_derivs_and_solve(void* h, double c, double* gradE, double* E, double* G, double* Fblk, double* S, double* rhs,
+                                  unsigned char* skipped, double* corrections);
+/* Resident (normalised) state as the engine holds it. */
+int srk_ba_debug_get_state(void* h, double* points, double* cams);
+/* ApplyCorrections (BA.cpp:1997-2063) of `corrections` to the resident state, then ReprojError. */
+int srk_ba_debug_apply(void* h, const double* corrections, double* err_new);
+
+/* Kernel timing for bench.py: CUDA-event time (ms) of the last launch of each kernel family on this handle's stream,
+ * enabled with srk_ba_set_timing(h, 1).  names: "jacobian", "frame_blocks", "schur", "solve", "backsub", "update", "residual". */
+int srk_ba_set_timing(void* h, int enabled);
+int srk_ba_get_timing(void* h, const char* name, double* ms_last, double* ms_total, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRK_BA_C_API_H */

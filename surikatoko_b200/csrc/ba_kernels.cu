@@ -1,0 +1,569 @@
+// suriko-b200 — hand-written sm_100a kernels of the bundle-adjustment hot path.
+//
+//   k_cam_prep        per-camera derived record (P = K[R|T], direct pose, rot1..3)      BA.cpp:1193-1197, :1499-1520
+//   k_jacobian   (K1) per-observation residual + analytic Jacobian rows, SoA planes     BA.cpp:1160-1266 / :1268-1412 / :1450-1549
+//   k_frame_blocks    per-camera 10x10 block G and gradient g_f (the reference's "frame pass")  BA.cpp:1268-1334
+//   k_residual  (K1') per-observation squared residual + deterministic reduction         BA.cpp:410-490
+//   k_fill_reduced    S <- gauge-reduced, damped G;  rhs <- -g_f                           BA.cpp:1780-1823, :1902-1908
+//   k_schur      (K2) per-point 3x3 block, cofactor inverse, Schur accumulation          BA.cpp:1859-1900
+//   k_backsub   (K2') per-point back-substitution + point update into the trial state   BA.cpp:1919-1960, :2003-2017
+//   k_cam_update (K4) per-camera pose update (direct T += dT, R <- Rodrigues(dW) R)       BA.cpp:2021-2062, :59-92
+//   k_normalize_points / k_revert_points   gauge normalisation of the points               BA.cpp:179-199
+//
+// Data layout in HBM (all FP64 values, int32 indices): observations point-major (pnt_ind, frame_ind) — the reference's
+// own track order — as SoA arrays; Jacobian rows as 28 planes of n_obs doubles so that every warp access is one
+// contiguous 256-B segment; points as 3 planes.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srk {
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void k_cam_prep(int M, const double* __restrict__ cams, const double* __restrict__ K, int shared_K, double f0,
+                           double* __restrict__ camd) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const double* c = cams + (size_t)i * 12;  // T[3], R col-major[9]
+    const double* k = K + (shared_K ? 0 : (size_t)i * 9);
+    double* d = camd + (size_t)i * kCamStride;
+    double R[9], T[3], Km[9];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[j] = c[j];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { R[j] = c[3 + j]; Km[j] = k[j]; }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { d[CD_R + j] = R[j]; d[CD_K + j] = Km[j]; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) d[CD_T + j] = T[j];
+    // KR(r,c) = sum_m K(r,m) R(m,c)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) d[CD_KR + cc * 3 + r] = Km[0 * 3 + r] * R[cc * 3 + 0] + Km[1 * 3 + r] * R[cc * 3 + 1] + Km[2 * 3 + r] * R[cc * 3 + 2];
+    // direct pose: Rd = R^T, Td = -Rd*T   (obs-geom.cpp:117-122);  Rd(i,c) = R(c,i)
+    double Td[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) Td[r] = -(R[r * 3 + 0] * T[0] + R[r * 3 + 1] * T[1] + R[r * 3 + 2] * T[2]);
+    double fx = Km[0], fy = Km[4], u0 = Km[6], v0 = Km[7];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        double rd0 = R[t * 3 + 0], rd1 = R[t * 3 + 1], rd2 = R[t * 3 + 2];  // Rd(t,0..2) = R(0..2,t)
+        d[CD_TD + t] = Td[t];
+        d[CD_ROT1 + t] = fx * rd0 + u0 * rd2;
+        d[CD_ROT2 + t] = fy * rd1 + v0 * rd2;
+        d[CD_ROT3 + t] = f0 * rd2;
+    }
+    d[CD_FX] = fx; d[CD_FY] = fy; d[CD_U0] = u0; d[CD_V0] = v0; d[CD_F0] = f0; d[47] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1: one thread per observation.  Reads 24 B/obs of observation data + the point (gathered, L1/L2-served) + the camera
+// record (L1/L2-resident), writes 224 B/obs as 28 coalesced planes: rho[2], Jp[6], Jc[20].
+__global__ void __launch_bounds__(256) k_jacobian(int64_t O, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt,
+                                                  const double* __restrict__ obs_x, const double* __restrict__ obs_y,
+                                                  const double* __restrict__ X, int64_t N, const double* __restrict__ camd,
+                                                  double* __restrict__ J) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= O) return;
+    int cam = obs_cam[o], pt = obs_pt[o];
+    double x = obs_x[o], y = obs_y[o];
+    double X0 = X[pt], X1 = X[N + pt], X2 = X[2 * N + pt];
+    const double* cd = camd + (size_t)cam * kCamStride;
+    double rx, ry, jp[6], jc[20];
+    obs_jacobian(cd, X0, X1, X2, x, y, rx, ry, jp, jc);
+    J[o] = rx;
+    J[O + o] = ry;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) J[(int64_t)(2 + i) * O + o] = jp[i];
+#pragma unroll
+    for (int i = 0; i < 20; ++i) J[(int64_t)(8 + i) * O + o] = jc[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Frame pass: camera-major.  grid = (M, splits); each CTA walks a slice of the camera's observations (camera-major copy
+// of the observation list: point index + pixel), recomputes the 2x10 row block and accumulates the 55 unique entries of
+// 2*Jc^T*Jc and the 10 of 2*Jc^T*rho in registers; one block reduction, one store (splits == 1) or 65 atomics.
+__global__ void __launch_bounds__(128) k_frame_blocks(int M, const int64_t* __restrict__ cam_begin, const int32_t* __restrict__ c_pt,
+                                                      const double* __restrict__ c_x, const double* __restrict__ c_y,
+                                                      const double* __restrict__ X, int64_t N, const double* __restrict__ camd,
+                                                      double* __restrict__ G, double* __restrict__ gf, int splits) {
+    int cam = blockIdx.x;
+    const double* cd = camd + (size_t)cam * kCamStride;
+    int64_t b = cam_begin[cam], e = cam_begin[cam + 1];
+    int64_t len = e - b;
+    int64_t sb = b + (len * blockIdx.y) / splits, se = b + (len * (blockIdx.y + 1)) / splits;
+    double acc[65];
+#pragma unroll
+    for (int i = 0; i < 65; ++i) acc[i] = 0.0;
+    for (int64_t o = sb + threadIdx.x; o < se; o += blockDim.x) {
+        int pt = c_pt[o];
+        double rx, ry, jp[6], jc[20];
+        obs_jacobian(cd, X[pt], X[N + pt], X[2 * N + pt], c_x[o], c_y[o], rx, ry, jp, jc);
+        int idx = 0;
+#pragma unroll
+        for (int a = 0; a < 10; ++a)
+#pragma unroll
+            for (int bb = a; bb < 10; ++bb) { acc[idx] += jc[a * 2] * jc[bb * 2] + jc[a * 2 + 1] * jc[bb * 2 + 1]; ++idx; }
+#pragma unroll
+        for (int a = 0; a < 10; ++a) acc[55 + a] += jc[a * 2] * rx + jc[a * 2 + 1] * ry;
+    }
+    __shared__ double red[4][65];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 65; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        if (lane == 0) red[w][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 65) {
+        double v = 2.0 * ((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]));
+        int i = threadIdx.x;
+        if (i < 55) {
+            int a = 0, rem = i;
+            while (rem >= 10 - a) { rem -= 10 - a; ++a; }
+            int bb = a + rem;
+            double* g = G + (size_t)cam * 100;
+            if (splits == 1) { g[a * 10 + bb] = v; g[bb * 10 + a] = v; }
+            else { atomicAdd(&g[a * 10 + bb], v); if (a != bb) atomicAdd(&g[bb * 10 + a], v); }
+        } else {
+            if (splits == 1) gf[(size_t)cam * 10 + (i - 55)] = v;
+            else atomicAdd(&gf[(size_t)cam * 10 + (i - 55)], v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1': squared residuals, grid-stride, fixed grid; per-block partial then a fixed-order final sum (deterministic).
+__global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt,
+                                                  const double* __restrict__ obs_x, const double* __restrict__ obs_y,
+                                                  const double* __restrict__ X, int64_t N, const double* __restrict__ camd,
+                                                  double* __restrict__ partial) {
+    double s = 0.0;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < O; o += (int64_t)gridDim.x * blockDim.x) {
+        int cam = obs_cam[o], pt = obs_pt[o];
+        double rx, ry;
+        obs_residual(camd + (size_t)cam * kCamStride, X[pt], X[N + pt], X[2 * N + pt], obs_x[o], obs_y[o], rx, ry);
+        s += rx * rx + ry * ry;
+    }
+    __shared__ double red[8];
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void k_sum_partials(int n, const double* __restrict__ partial, double* __restrict__ out) {
+    __shared__ double sm[256];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += partial[i];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (int st = 128; st > 0; st >>= 1) { if ((int)threadIdx.x < st) sm[threadIdx.x] += sm[threadIdx.x + st]; __syncthreads(); }
+    if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// S <- gauge-reduced G with the diagonal multiplied by (1+c) (fill_matG, BA.cpp:1780-1823); rhs <- -g_f (BA.cpp:1908).
+// One CTA per camera.  S is dense column-major n_f x n_f (already zeroed).  with_G == 0 (ranks > 0 in a multi-GPU run)
+// leaves both untouched so that the all-reduced sum contains G exactly once.
+__global__ void k_fill_reduced(int M, const double* __restrict__ G, const double* __restrict__ gf, double c, int unity,
+                               double* __restrict__ S, int64_t ld, double* __restrict__ rhs) {
+    int cam = blockIdx.x;
+    int t = threadIdx.x;
+    if (t < 100) {
+        int a = t / 10, b = t % 10;
+        int ra = red_index(cam, a, unity), rb = red_index(cam, b, unity);
+        if (ra >= 0 && rb >= 0) {
+            double g = G[(size_t)cam * 100 + t];
+            if (a == b) g *= 1.0 + c;
+            S[(size_t)rb * ld + ra] = g;
+        }
+    } else if (t < 110) {
+        int a = t - 100;
+        int ra = red_index(cam, a, unity);
+        if (ra >= 0) rhs[ra] = -gf[(size_t)cam * 10 + a];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K2: one warp per point.
+//  phase 1: E = 2*sum Jp^T Jp, g_p = 2*sum Jp^T rho over the point's observations (lanes over observations, shuffle
+//           reduction), damping, cofactor inverse with the |det| > 1e-12 rule; Einv/g_p/flag are stored for K2'.
+//  phase 2: for every observation i: F_i = 2*Jp_i^T*Jc_i (3x10), W_i = Einv*F_i, staged in shared memory in chunks of
+//           CH observations; every pair (i >= l) contributes the 10x10 block  -F_i^T W_l  to S[cam_i, cam_l] (lower
+//           triangle, cam_i >= cam_l because observations are frame-sorted within a point) as 5x5 register tiles,
+//           accumulated with red.global.add.f64; rhs[cam_i] += F_i^T (Einv g_p).
+constexpr int kSchurCH = 16;
+constexpr int kSchurWarps = 4;
+
+__global__ void __launch_bounds__(kSchurWarps * 32) k_schur(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin,
+                                                            const int32_t* __restrict__ obs_cam, const double* __restrict__ J, double c,
+                                                            int unity, double* __restrict__ S, int64_t ld, double* __restrict__ rhs,
+                                                            double* __restrict__ pinv, unsigned char* __restrict__ skipped) {
+    __shared__ double sF[kSchurWarps][kSchurCH][30];   // slot 0 only: F of the row chunk
+    __shared__ double sW[kSchurWarps][2][kSchurCH][30];
+    __shared__ int sCam[kSchurWarps][2][kSchurCH];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t j = (int64_t)blockIdx.x * kSchurWarps + w;
+    if (j >= N) return;
+    const int64_t b = pt_begin[j], e = pt_begin[j + 1];
+    const int k = (int)(e - b);
+
+    // ---- phase 1
+    double a9[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a9[i] = 0.0;
+    for (int64_t o = b + lane; o < e; o += 32) {
+        double rx = J[o], ry = J[O + o];
+        double jp[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+        a9[0] += jp[0] * jp[0] + jp[1] * jp[1];
+        a9[1] += jp[0] * jp[2] + jp[1] * jp[3];
+        a9[2] += jp[0] * jp[4] + jp[1] * jp[5];
+        a9[3] += jp[2] * jp[2] + jp[3] * jp[3];
+        a9[4] += jp[2] * jp[4] + jp[3] * jp[5];
+        a9[5] += jp[4] * jp[4] + jp[5] * jp[5];
+        a9[6] += jp[0] * rx + jp[1] * ry;
+        a9[7] += jp[2] * rx + jp[3] * ry;
+        a9[8] += jp[4] * rx + jp[5] * ry;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double v = a9[i];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        a9[i] = 2.0 * v;
+    }
+    double inv[6];
+    bool ok = point_block_inverse(a9, c, inv);
+    if (lane == 0) {
+        skipped[j] = ok ? 0 : 1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pinv[(int64_t)i * N + j] = ok ? inv[i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pinv[(int64_t)(6 + i) * N + j] = a9[6 + i];
+    }
+    if (!ok) return;  // non-invertible point block: no Schur contribution (BA.cpp:1877-1881)
+    const double gp0 = a9[6], gp1 = a9[7], gp2 = a9[8];
+    const double t0 = inv[0] * gp0 + inv[1] * gp1 + inv[2] * gp2;
+    const double t1 = inv[1] * gp0 + inv[3] * gp1 + inv[4] * gp2;
+    const double t2 = inv[2] * gp0 + inv[4] * gp1 + inv[5] * gp2;
+
+    // ---- phase 2
+    const int nch = (k + kSchurCH - 1) / kSchurCH;
+    auto stage = [&](int chunk, int slot) {
+        int n = min(kSchurCH, k - chunk * kSchurCH);
+        if (lane < n) {
+            int64_t o = b + (int64_t)chunk * kSchurCH + lane;
+            double jp[6], jc[20];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+#pragma unroll
+            for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
+            sCam[w][slot][lane] = obs_cam[o];
+#pragma unroll
+            for (int a = 0; a < 10; ++a) {
+                double f0 = 2.0 * (jp[0] * jc[a * 2] + jp[1] * jc[a * 2 + 1]);
+                double f1 = 2.0 * (jp[2] * jc[a * 2] + jp[3] * jc[a * 2 + 1]);
+                double f2 = 2.0 * (jp[4] * jc[a * 2] + jp[5] * jc[a * 2 + 1]);
+                if (slot == 0) { sF[w][lane][a] = f0; sF[w][lane][10 + a] = f1; sF[w][lane][20 + a] = f2; }
+                sW[w][slot][lane][a] = inv[0] * f0 + inv[1] * f1 + inv[2] * f2;
+                sW[w][slot][lane][10 + a] = inv[1] * f0 + inv[3] * f1 + inv[4] * f2;
+                sW[w][slot][lane][20 + a] = inv[2] * f0 + inv[4] * f1 + inv[5] * f2;
+            }
+        }
+        __syncwarp();
+        return n;
+    };
+    for (int ci = 0; ci < nch; ++ci) {
+        int nA = stage(ci, 0);
+        // rhs += F_i^T (Einv g_p)
+        for (int t = lane; t < nA * 10; t += 32) {
+            int i = t / 10, a = t % 10;
+            int r = red_index(sCam[w][0][i], a, unity);
+            if (r >= 0) atomicAdd(&rhs[r], sF[w][i][a] * t0 + sF[w][i][10 + a] * t1 + sF[w][i][20 + a] * t2);
+        }
+        for (int cl = 0; cl <= ci; ++cl) {
+            int slotB = 0, nB = nA;
+            if (cl != ci) { nB = stage(cl, 1); slotB = 1; }
+            int npairs = (cl == ci) ? nA * (nA + 1) / 2 : nA * nB;
+            for (int tt = lane; tt < npairs * 4; tt += 32) {
+                int pr = tt >> 2, tile = tt & 3;
+                int i, l;
+                if (cl == ci) {
+                    i = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+                    while (i * (i + 1) / 2 > pr) --i;
+                    while ((i + 1) * (i + 2) / 2 <= pr) ++i;
+                    l = pr - i * (i + 1) / 2;
+                } else { i = pr / nB; l = pr % nB; }
+                const int tr = (tile >> 1) * 5, tc = (tile & 1) * 5;
+                const double* Fi = sF[w][i];
+                const double* Wl = sW[w][slotB][l];
+                const int cam_i = sCam[w][0][i], cam_l = sCam[w][slotB][l];
+                double f[3][5], ww[3][5];
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+#pragma unroll
+                    for (int x = 0; x < 5; ++x) { f[v][x] = Fi[v * 10 + tr + x]; ww[v][x] = Wl[v * 10 + tc + x]; }
+#pragma unroll
+                for (int x = 0; x < 5; ++x) {
+                    int row = red_index(cam_i, tr + x, unity);
+                    if (row < 0) continue;
+#pragma unroll
+                    for (int y = 0; y < 5; ++y) {
+                        int col = red_index(cam_l, tc + y, unity);
+                        if (col < 0) continue;
+                        double v = f[0][x] * ww[0][y] + f[1][x] * ww[1][y] + f[2][x] * ww[2][y];
+                        atomicAdd(&S[(size_t)col * ld + row], -v);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K2': LPP lanes per point.  t = sum_i F_i * df[cam_i] + g_p ;  dp = -Einv t ;  X_try = X + dp  (skipped points: dp = 0).
+template <int LPP>
+__global__ void __launch_bounds__(256) k_backsub(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam,
+                                                 const double* __restrict__ J, const double* __restrict__ df /*[10M] with gaps*/,
+                                                 const double* __restrict__ pinv, const unsigned char* __restrict__ skipped,
+                                                 const double* __restrict__ X, double* __restrict__ Xtry, double* __restrict__ dp_out) {
+    int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t j = gid / LPP;
+    int sub = (int)(gid % LPP);
+    bool active = j < N;
+    double t[3] = {0.0, 0.0, 0.0};
+    bool skip = true;
+    if (active) {
+        skip = skipped[j] != 0;
+        if (!skip) {
+            int64_t b = pt_begin[j], e = pt_begin[j + 1];
+            for (int64_t o = b + sub; o < e; o += LPP) {
+                const double* d = df + (size_t)obs_cam[o] * 10;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int a = 0; a < 10; ++a) {
+                    double da = d[a];
+                    s0 += J[(int64_t)(8 + a * 2) * O + o] * da;
+                    s1 += J[(int64_t)(9 + a * 2) * O + o] * da;
+                }
+#pragma unroll
+                for (int v = 0; v < 3; ++v)
+                    t[v] += 2.0 * (J[(int64_t)(2 + v * 2) * O + o] * s0 + J[(int64_t)(3 + v * 2) * O + o] * s1);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int s = LPP / 2; s > 0; s >>= 1) t[v] += __shfl_xor_sync(0xffffffffu, t[v], s);
+    if (active && sub == 0) {
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+        if (!skip) {
+            double i0 = pinv[j], i1 = pinv[N + j], i2 = pinv[2 * N + j], i3 = pinv[3 * N + j], i4 = pinv[4 * N + j], i5 = pinv[5 * N + j];
+            double u0 = t[0] + pinv[6 * N + j], u1 = t[1] + pinv[7 * N + j], u2 = t[2] + pinv[8 * N + j];
+            d0 = -(i0 * u0 + i1 * u1 + i2 * u2);
+            d1 = -(i1 * u0 + i3 * u1 + i4 * u2);
+            d2 = -(i2 * u0 + i4 * u1 + i5 * u2);
+        }
+        Xtry[j] = X[j] + d0; Xtry[N + j] = X[N + j] + d1; Xtry[2 * N + j] = X[2 * N + j] + d2;
+        if (dp_out != nullptr) { dp_out[3 * j] = d0; dp_out[3 * j + 1] = d1; dp_out[3 * j + 2] = d2; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K4: per-camera update (ApplyCorrections, BA.cpp:2021-2062): direct = SE3Inv(inverse); T_d += dT;
+// R_d <- Rodrigues(dW)*R_d unless |dW| is ~0 (IsClose(0, ang), quirk Q6); inverse = SE3Inv(direct).
+__global__ void k_cam_update(int M, const double* __restrict__ cams, const double* __restrict__ df, double* __restrict__ cams_try) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const double* c = cams + (size_t)i * 12;
+    const double* d = df + (size_t)i * 10;
+    double T[3] = {c[0], c[1], c[2]};
+    double R[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) R[j] = c[3 + j];
+    // direct pose
+    double Rd[9], Td[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Rd[cc * 3 + r] = R[r * 3 + cc];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) Td[r] = -(Rd[0 * 3 + r] * T[0] + Rd[1 * 3 + r] * T[1] + Rd[2 * 3 + r] * T[2]);
+    Td[0] += d[4]; Td[1] += d[5]; Td[2] += d[6];
+    double w0 = d[7], w1 = d[8], w2 = d[9];
+    double ang = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    // IsClose(0, ang): |0 - ang| <= 1e-8 + 1e-5*|max(0, ang)|   (approx-alg.h:7-16)
+    bool skip_rot = fabs(ang) <= (1e-8 + 1e-5 * fabs(fmax(0.0, ang)));
+    double Rn[9];
+    if (!skip_rot) {
+        double n0 = w0 / ang, n1 = w1 / ang, n2 = w2 / ang;
+        double s = sin(ang), co = cos(ang);
+        double Sk[9] = {0.0, n2, -n1, -n2, 0.0, n0, n1, -n0, 0.0};  // column-major skew
+        double A[9];                                                  // (1-c)*Sk
+#pragma unroll
+        for (int j = 0; j < 9; ++j) A[j] = (1.0 - co) * Sk[j];
+        double rot[9];
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double a2 = A[0 * 3 + r] * Sk[cc * 3 + 0] + A[1 * 3 + r] * Sk[cc * 3 + 1] + A[2 * 3 + r] * Sk[cc * 3 + 2];
+                rot[cc * 3 + r] = ((r == cc ? 1.0 : 0.0) + s * Sk[cc * 3 + r]) + a2;
+            }
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) Rn[cc * 3 + r] = rot[0 * 3 + r] * Rd[cc * 3 + 0] + rot[1 * 3 + r] * Rd[cc * 3 + 1] + rot[2 * 3 + r] * Rd[cc * 3 + 2];
+    } else {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) Rn[j] = Rd[j];
+    }
+    // back to inverse pose
+    double* o = cams_try + (size_t)i * 12;
+    double Ri[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) Ri[cc * 3 + r] = Rn[r * 3 + cc];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o[r] = -(Ri[0 * 3 + r] * Td[0] + Ri[1 * 3 + r] * Td[1] + Ri[2 * 3 + r] * Td[2]);
+#pragma unroll
+    for (int j = 0; j < 9; ++j) o[3 + j] = Ri[j];
+}
+
+// df (with gaps, [10M]) from the reduced solution (FillCorrectionsGapsFromNormalized, BA.cpp:1600-1679).
+__global__ void k_expand_df(int M, const double* __restrict__ dfr, int unity, double* __restrict__ df) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M * 10) return;
+    int r = red_index(t / 10, t % 10, unity);
+    df[t] = r >= 0 ? dfr[r] : 0.0;
+}
+
+// Points: X' = (R0*X + T0)*s (BA.cpp:179-186) or the inverse X = R0^T (X'*(1/s) - T0) (BA.cpp:187-191).
+__global__ void k_normalize_points(int64_t N, double* __restrict__ X, const double* __restrict__ cam0 /*T[3],R[9]*/, double s, int revert) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const double* T = cam0; const double* R = cam0 + 3;
+    double x0 = X[j], x1 = X[N + j], x2 = X[2 * N + j];
+    if (!revert) {
+        double y0 = R[0] * x0 + R[3] * x1 + R[6] * x2 + T[0];
+        double y1 = R[1] * x0 + R[4] * x1 + R[7] * x2 + T[1];
+        double y2 = R[2] * x0 + R[5] * x1 + R[8] * x2 + T[2];
+        X[j] = y0 * s; X[N + j] = y1 * s; X[2 * N + j] = y2 * s;
+    } else {
+        double is = 1.0 / s;
+        double t0 = x0 * is - T[0], t1 = x1 * is - T[1], t2 = x2 * is - T[2];
+        X[j] = R[0] * t0 + R[1] * t1 + R[2] * t2;
+        X[N + j] = R[3] * t0 + R[4] * t1 + R[5] * t2;
+        X[2 * N + j] = R[6] * t0 + R[7] * t1 + R[8] * t2;
+    }
+}
+
+// AoS [3N] <-> planes [3][N]
+__global__ void k_points_to_planes(int64_t N, const double* __restrict__ aos, double* __restrict__ planes) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    planes[j] = aos[3 * j]; planes[N + j] = aos[3 * j + 1]; planes[2 * N + j] = aos[3 * j + 2];
+}
+__global__ void k_planes_to_points(int64_t N, const double* __restrict__ planes, double* __restrict__ aos) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    aos[3 * j] = planes[j]; aos[3 * j + 1] = planes[N + j]; aos[3 * j + 2] = planes[2 * N + j];
+}
+
+// Parity hooks: E (from the stored point data is damped/inverted, so recompute the raw blocks) and F blocks from J.
+__global__ void k_debug_point_blocks(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin, const double* __restrict__ J,
+                                     double* __restrict__ E /*[9N]*/, double* __restrict__ gp /*[3N]*/) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    double a[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int64_t o = pt_begin[j]; o < pt_begin[j + 1]; ++o) {
+        double rx = J[o], ry = J[O + o], jp[6];
+        for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+        a[0] += jp[0] * jp[0] + jp[1] * jp[1]; a[1] += jp[0] * jp[2] + jp[1] * jp[3]; a[2] += jp[0] * jp[4] + jp[1] * jp[5];
+        a[3] += jp[2] * jp[2] + jp[3] * jp[3]; a[4] += jp[2] * jp[4] + jp[3] * jp[5]; a[5] += jp[4] * jp[4] + jp[5] * jp[5];
+        a[6] += jp[0] * rx + jp[1] * ry; a[7] += jp[2] * rx + jp[3] * ry; a[8] += jp[4] * rx + jp[5] * ry;
+    }
+    double* e = E + 9 * j;
+    e[0] = 2 * a[0]; e[1] = 2 * a[1]; e[2] = 2 * a[2]; e[3] = 2 * a[1]; e[4] = 2 * a[3]; e[5] = 2 * a[4]; e[6] = 2 * a[2]; e[7] = 2 * a[4]; e[8] = 2 * a[5];
+    gp[3 * j] = 2 * a[6]; gp[3 * j + 1] = 2 * a[7]; gp[3 * j + 2] = 2 * a[8];
+}
+__global__ void k_debug_F_blocks(int64_t O, const double* __restrict__ J, double* __restrict__ F /*[30*O]*/) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= O) return;
+    for (int v = 0; v < 3; ++v)
+        for (int a = 0; a < 10; ++a)
+            F[o * 30 + v * 10 + a] = 2.0 * (J[(int64_t)(2 + v * 2) * O + o] * J[(int64_t)(8 + a * 2) * O + o] + J[(int64_t)(3 + v * 2) * O + o] * J[(int64_t)(9 + a * 2) * O + o]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Launch wrappers
+
+static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+void launch_cam_prep(cudaStream_t st, int M, const double* cams, const double* K, int shared_K, double f0, double* camd) {
+    k_cam_prep<<<cdiv(M, 128), 128, 0, st>>>(M, cams, K, shared_K, f0, camd);
+}
+void launch_jacobian(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
+                     const double* X, int64_t N, const double* camd, double* J) {
+    if (O > 0) k_jacobian<<<cdiv(O, 256), 256, 0, st>>>(O, obs_cam, obs_pt, x, y, X, N, camd, J);
+}
+void launch_frame_blocks(cudaStream_t st, int M, const int64_t* cam_begin, const int32_t* c_pt, const double* c_x, const double* c_y,
+                         const double* X, int64_t N, const double* camd, double* G, double* gf, int splits) {
+    if (splits > 1) { cudaMemsetAsync(G, 0, sizeof(double) * 100 * (size_t)M, st); cudaMemsetAsync(gf, 0, sizeof(double) * 10 * (size_t)M, st); }
+    k_frame_blocks<<<dim3(M, splits), 128, 0, st>>>(M, cam_begin, c_pt, c_x, c_y, X, N, camd, G, gf, splits);
+}
+void launch_residual(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
+                     const double* X, int64_t N, const double* camd, double* partial, int nblocks, double* out) {
+    k_residual<<<nblocks, 256, 0, st>>>(O, obs_cam, obs_pt, x, y, X, N, camd, partial);
+    k_sum_partials<<<1, 256, 0, st>>>(nblocks, partial, out);
+}
+void launch_fill_reduced(cudaStream_t st, int M, const double* G, const double* gf, double c, int unity, double* S, int64_t ld, double* rhs) {
+    k_fill_reduced<<<M, 128, 0, st>>>(M, G, gf, c, unity, S, ld, rhs);
+}
+void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, int unity,
+                  double* S, int64_t ld, double* rhs, double* pinv, unsigned char* skipped) {
+    if (N > 0) k_schur<<<cdiv(N, kSchurWarps), kSchurWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, unity, S, ld, rhs, pinv, skipped);
+}
+void launch_backsub(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, const double* df,
+                    const double* pinv, const unsigned char* skipped, const double* X, double* Xtry, double* dp_out, int lanes_per_point) {
+    if (N <= 0) return;
+    if (lanes_per_point <= 4) k_backsub<4><<<cdiv(N * 4, 256), 256, 0, st>>>(N, O, pt_begin, obs_cam, J, df, pinv, skipped, X, Xtry, dp_out);
+    else if (lanes_per_point <= 8) k_backsub<8><<<cdiv(N * 8, 256), 256, 0, st>>>(N, O, pt_begin, obs_cam, J, df, pinv, skipped, X, Xtry, dp_out);
+    else if (lanes_per_point <= 16) k_backsub<16><<<cdiv(N * 16, 256), 256, 0, st>>>(N, O, pt_begin, obs_cam, J, df, pinv, skipped, X, Xtry, dp_out);
+    else k_backsub<32><<<cdiv(N * 32, 256), 256, 0, st>>>(N, O, pt_begin, obs_cam, J, df, pinv, skipped, X, Xtry, dp_out);
+}
+void launch_cam_update(cudaStream_t st, int M, const double* cams, const double* df, double* cams_try) {
+    k_cam_update<<<cdiv(M, 128), 128, 0, st>>>(M, cams, df, cams_try);
+}
+void launch_expand_df(cudaStream_t st, int M, const double* dfr, int unity, double* df) {
+    k_expand_df<<<cdiv((int64_t)M * 10, 256), 256, 0, st>>>(M, dfr, unity, df);
+}
+void launch_normalize_points(cudaStream_t st, int64_t N, double* X, const double* cam0_dev, double s, int revert) {
+    if (N > 0) k_normalize_points<<<cdiv(N, 256), 256, 0, st>>>(N, X, cam0_dev, s, revert);
+}
+void launch_points_to_planes(cudaStream_t st, int64_t N, const double* aos, double* planes) {
+    if (N > 0) k_points_to_planes<<<cdiv(N, 256), 256, 0, st>>>(N, aos, planes);
+}
+void launch_planes_to_points(cudaStream_t st, int64_t N, const double* planes, double* aos) {
+    if (N > 0) k_planes_to_points<<<cdiv(N, 256), 256, 0, st>>>(N, planes, aos);
+}
+void launch_debug_point_blocks(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const double* J, double* E, double* gp) {
+    if (N > 0) k_debug_point_blocks<<<cdiv(N, 128), 128, 0, st>>>(N, O, pt_begin, J, E, gp);
+}
+void launch_debug_F_blocks(cudaStream_t st, int64_t O, const double* J, double* F) {
+    if (O > 0) k_debug_F_blocks<<<cdiv(O, 128), 128, 0, st>>>(O, J, F);
+}
+
+}  // namespace srk

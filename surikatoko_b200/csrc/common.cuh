@@ -1,0 +1,116 @@
+// suriko-b200 — shared device helpers for the BA kernels (sm_100a).
+// Per-observation formulas follow /root/reference/cpp_impl/suriko-engine/src/bundle-adj-kanatani.cpp ("BA.cpp").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace srk {
+
+constexpr int kV = 10;           // frame variables [fx fy u0 v0 | Tx Ty Tz | Wx Wy Wz]   (BA.h:102-118)
+constexpr int kCamStride = 48;   // doubles per derived-camera record (384 B, 128-B aligned)
+
+// Derived camera record, rebuilt whenever a pose changes (k_cam_prep).  All 3x3 are column-major (r,c)->[c*3+r].
+//  [0..8] R  [9..11] T  [12..20] K  [21..29] KR=K*R  [30..32] Td=-R^T*T  [33..35] rot1  [36..38] rot2  [39..41] rot3
+//  [42] fx [43] fy [44] u0 [45] v0 [46] f0 [47] pad
+enum { CD_R = 0, CD_T = 9, CD_K = 12, CD_KR = 21, CD_TD = 30, CD_ROT1 = 33, CD_ROT2 = 36, CD_ROT3 = 39, CD_FX = 42, CD_FY = 43, CD_U0 = 44, CD_V0 = 45, CD_F0 = 46 };
+
+// Gauge-reduced index of frame variable (cam, a): frame 0 keeps [fx fy u0 v0], frame 1 drops T[unity], frames >= 2 keep
+// all 10 (quirk Q13; BA.cpp:539-563, :1780-1823).  Returns -1 for the 7 removed variables.
+__host__ __device__ __forceinline__ int red_index(int cam, int a, int unity) {
+    if (cam == 0) return a < 4 ? a : -1;
+    if (cam == 1) {
+        if (a < 4) return 4 + a;
+        int t = a - 4;
+        if (t == unity) return -1;
+        return 4 + a - (t > unity ? 1 : 0);
+    }
+    return cam * kV - 7 + a;
+}
+
+// pqr = K * (R*X + T)   (BA.cpp:469-470), natural left-to-right coefficient order.
+__device__ __forceinline__ void project_pqr(const double* __restrict__ cd, double X0, double X1, double X2, double& p, double& q, double& r) {
+    const double* R = cd + CD_R; const double* T = cd + CD_T; const double* K = cd + CD_K;
+    double c0 = R[0] * X0 + R[3] * X1 + R[6] * X2 + T[0];
+    double c1 = R[1] * X0 + R[4] * X1 + R[7] * X2 + T[1];
+    double c2 = R[2] * X0 + R[5] * X1 + R[8] * X2 + T[2];
+    p = K[0] * c0 + K[3] * c1 + K[6] * c2;
+    q = K[1] * c0 + K[4] * c1 + K[7] * c2;
+    r = K[2] * c0 + K[5] * c1 + K[8] * c2;
+}
+
+// One observation: residual rho = (p/r - x/f0, q/r - y/f0) (BA.cpp:475-479).
+__device__ __forceinline__ void obs_residual(const double* __restrict__ cd, double X0, double X1, double X2, double x, double y,
+                                             double& rx, double& ry) {
+    double p, q, r;
+    project_pqr(cd, X0, X1, X2, p, q, r);
+    double f0 = cd[CD_F0];
+    rx = p / r - x / f0;
+    ry = q / r - y / f0;
+}
+
+// One observation: residual + Jacobian rows J_a = (r*p_a - p*r_a, r*q_a - q*r_a) / r^2 for the 3 point variables
+// (BA.cpp:1450-1455) and the 10 frame variables (BA.cpp:1457-1525, quirk Q3: f0 verbatim).  With these,
+// formula 8 (BA.cpp:1528-1537) is 2*rho.J_a and formula 9 (BA.cpp:1540-1549) is 2*J_a.J_b.
+// jp[v*2+comp], jc[a*2+comp].
+__device__ __forceinline__ void obs_jacobian(const double* __restrict__ cd, double X0, double X1, double X2, double x, double y,
+                                             double& rx, double& ry, double* __restrict__ jp, double* __restrict__ jc) {
+    double p, q, r;
+    project_pqr(cd, X0, X1, X2, p, q, r);
+    const double f0 = cd[CD_F0];
+    rx = p / r - x / f0;
+    ry = q / r - y / f0;
+    const double ir2 = 1.0 / (r * r);
+    const double* KR = cd + CD_KR;
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {  // column v of P = K*[R|T]
+        double pa = KR[v * 3 + 0], qa = KR[v * 3 + 1], ra = KR[v * 3 + 2];
+        jp[v * 2 + 0] = (r * pa - p * ra) * ir2;
+        jp[v * 2 + 1] = (r * qa - q * ra) * ir2;
+    }
+    const double fx = cd[CD_FX], fy = cd[CD_FY], u0 = cd[CD_U0], v0 = cd[CD_V0];
+    // intrinsics: only one of (p_a, q_a) is non-zero and r_a = 0
+    double pfx = (1.0 / fx) * p - u0 / (f0 * fx) * r;
+    double qfy = (1.0 / fy) * q - v0 / (f0 * fy) * r;
+    double pu0 = (1.0 / f0) * r;
+    jc[0] = (r * pfx) * ir2; jc[1] = 0.0;
+    jc[2] = 0.0;             jc[3] = (r * qfy) * ir2;
+    jc[4] = (r * pu0) * ir2; jc[5] = 0.0;
+    jc[6] = 0.0;             jc[7] = (r * pu0) * ir2;
+    const double* rot1 = cd + CD_ROT1; const double* rot2 = cd + CD_ROT2; const double* rot3 = cd + CD_ROT3;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {  // direct translation
+        double pa = -rot1[t], qa = -rot2[t], ra = -rot3[t];
+        jc[(4 + t) * 2 + 0] = (r * pa - p * ra) * ir2;
+        jc[(4 + t) * 2 + 1] = (r * qa - q * ra) * ir2;
+    }
+    const double* Td = cd + CD_TD;
+    double d0 = X0 - Td[0], d1 = X1 - Td[1], d2 = X2 - Td[2];
+    double wp[3] = {rot1[1] * d2 - rot1[2] * d1, rot1[2] * d0 - rot1[0] * d2, rot1[0] * d1 - rot1[1] * d0};
+    double wq[3] = {rot2[1] * d2 - rot2[2] * d1, rot2[2] * d0 - rot2[0] * d2, rot2[0] * d1 - rot2[1] * d0};
+    double wr[3] = {rot3[1] * d2 - rot3[2] * d1, rot3[2] * d0 - rot3[0] * d2, rot3[0] * d1 - rot3[1] * d0};
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {  // direct axis-angle
+        jc[(7 + t) * 2 + 0] = (r * wp[t] - p * wr[t]) * ir2;
+        jc[(7 + t) * 2 + 1] = (r * wq[t] - q * wr[t]) * ir2;
+    }
+}
+
+// Damped 3x3 point block -> cofactor inverse with Eigen's computeInverseAndDetWithCheck rule |det| > 1e-12
+// (BA.cpp:1873-1881, quirk Q5).  e = {E00,E01,E02,E11,E12,E22} (undamped, symmetric); inv gets the same packing.
+__device__ __forceinline__ bool point_block_inverse(const double* e, double c, double* inv) {
+    double m00 = e[0] * (1.0 + c), m11 = e[3] * (1.0 + c), m22 = e[5] * (1.0 + c);
+    double m01 = e[1], m02 = e[2], m12 = e[4];
+    double c00 = m11 * m22 - m12 * m12;
+    double c10 = m12 * m02 - m01 * m22;   // cofactor(1,0) = m(2,1)*m(0,2) - m(2,2)*m(0,1)
+    double c20 = m01 * m12 - m02 * m11;   // cofactor(2,0) = m(0,1)*m(1,2) - m(0,2)*m(1,1)
+    double det = (c00 * m00 + c10 * m01) + c20 * m02;
+    if (!(fabs(det) > 1e-12)) return false;
+    double id = 1.0 / det;
+    inv[0] = c00 * id; inv[1] = c10 * id; inv[2] = c20 * id;
+    inv[3] = (m22 * m00 - m02 * m02) * id;
+    inv[4] = (m02 * m01 - m00 * m12) * id;
+    inv[5] = (m00 * m11 - m01 * m01) * id;
+    return true;
+}
+
+}  // namespace srk
