@@ -17,6 +17,12 @@
 
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define SRK_API __attribute__((visibility("default")))
+#else
+#define SRK_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -74,6 +80,7 @@ typedef struct srk_ba_options {
     int32_t solver;                    /* SRK_SOLVER_*                                                                */
     int32_t pcg_max_iters;             /* 0 = default                                                                 */
     double pcg_rel_tol;                /* 0 = default (1e-13)                                                         */
+    int32_t refine_steps;              /* dense solve: iterative-refinement steps with a double-double residual (default 1) */
 } srk_ba_options;
 
 typedef struct srk_ba_report {
@@ -93,51 +100,54 @@ typedef struct srk_ba_report {
     int32_t pcg_iters_last;
 } srk_ba_report;
 
-void srk_ba_default_options(srk_ba_options* opt);
-const char* srk_stop_reason_string(int32_t stop_reason);
-const char* srk_last_error(void);
-int srk_abi_version(void);
+SRK_API void srk_ba_default_options(srk_ba_options* opt);
+SRK_API const char* srk_stop_reason_string(int32_t stop_reason);
+SRK_API const char* srk_last_error(void);
+SRK_API int srk_abi_version(void);
 
 /* Handle life cycle.  device_ids may be null (device 0); n_devices must be 1 (one process per GPU; multi-GPU runs use
  * one handle per rank plus srk_ba_set_allreduce). */
-int srk_ba_create(void** h, const int* device_ids, int n_devices);
-void srk_ba_destroy(void* h);
+SRK_API int srk_ba_create(void** h, const int* device_ids, int n_devices);
+SRK_API void srk_ba_destroy(void* h);
+/* Run every kernel of this handle on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
+ * instead of the handle's own stream; null restores the own stream.  Needed when the all-reduce callback is stream-ordered. */
+SRK_API int srk_ba_set_stream(void* h, void* cuda_stream);
 
 /* One-call path == BundleAdjustmentKanatani::ComputeInplace (BA.cpp:617-718): upload, normalise, LM loop, revert,
  * download.  points/cams are refined in place. */
-int srk_ba_solve(void* h, srk_ba_problem* problem, const srk_ba_options* opt, srk_ba_report* rep);
+SRK_API int srk_ba_solve(void* h, srk_ba_problem* problem, const srk_ba_options* opt, srk_ba_report* rep);
 
 /* == static BundleAdjustmentKanatani::ReprojError (BA.cpp:589-600): no normalisation, state untouched. */
-int srk_ba_reproj_error(void* h, const srk_ba_problem* problem, double* err, int64_t* seen_points);
+SRK_API int srk_ba_reproj_error(void* h, const srk_ba_problem* problem, double* err, int64_t* seen_points);
 
 /* Split path (what srk_ba_solve is made of); keeps the scene resident in HBM between calls. */
-int srk_ba_bind(void* h, const srk_ba_problem* problem, const srk_ba_options* opt);  /* H2D + NormalizeSceneInplace; returns 1 if normalisation failed */
-int srk_ba_run(void* h, const srk_ba_options* opt, srk_ba_report* rep);              /* ComputeOnNormalizedWorld on the resident state */
-int srk_ba_reset(void* h);                                                           /* resident state <- state as bound (device copy) */
-int srk_ba_fetch(void* h, srk_ba_problem* problem);                                  /* RevertNormalization + D2H into points/cams */
+SRK_API int srk_ba_bind(void* h, const srk_ba_problem* problem, const srk_ba_options* opt);  /* H2D + NormalizeSceneInplace; returns 1 if normalisation failed */
+SRK_API int srk_ba_run(void* h, const srk_ba_options* opt, srk_ba_report* rep);              /* ComputeOnNormalizedWorld on the resident state */
+SRK_API int srk_ba_reset(void* h);                                                           /* resident state <- state as bound (device copy) */
+SRK_API int srk_ba_fetch(void* h, srk_ba_problem* problem);                                  /* RevertNormalization + D2H into points/cams */
 
 /* Multi-GPU plumbing: the host (torch.distributed / NCCL, or gloo in CPU tests) provides an in-place sum all-reduce over
  * `count` doubles at device pointer `dev`, ordered on CUDA stream `stream`.  Each rank binds its own shard of points with
  * all cameras replicated; the engine reduces G, g_f, S, rhs and the error partials. */
 typedef int (*srk_allreduce_fn)(void* user, double* dev, int64_t count, void* stream);
-int srk_ba_set_allreduce(void* h, srk_allreduce_fn fn, void* user, int rank, int world_size);
+SRK_API int srk_ba_set_allreduce(void* h, srk_allreduce_fn fn, void* user, int rank, int world_size);
 
 /* Parity hooks: one derivative pass (+ one two-phase solve at damping c when c >= 0) on the resident normalised state.
  * Any output may be null.  Layouts match oracle/srk_oracle_capi.cpp::srk_oracle_derivs_and_solve:
  *   gradE[3N+10M]; E[9N] per point row-major 3x3; G[100M] per frame row-major 10x10; Fblk[30*n_obs] per observation
  *   row-major 3x10; S[n_f*n_f] column-major (lower triangle valid, upper mirrored); rhs[n_f]; skipped[N];
  *   corrections[3N+10M] (gaps re-inserted, BA.cpp:1600-1679). */
-int srk_ba_debug_derivs_and_solve(void* h, double c, double* gradE, double* E, double* G, double* Fblk, double* S, double* rhs,
+SRK_API int srk_ba_debug_derivs_and_solve(void* h, double c, double* gradE, double* E, double* G, double* Fblk, double* S, double* rhs,
                                   unsigned char* skipped, double* corrections);
 /* Resident (normalised) state as the engine holds it. */
-int srk_ba_debug_get_state(void* h, double* points, double* cams);
+SRK_API int srk_ba_debug_get_state(void* h, double* points, double* cams);
 /* ApplyCorrections (BA.cpp:1997-2063) of `corrections` to the resident state, then ReprojError. */
-int srk_ba_debug_apply(void* h, const double* corrections, double* err_new);
+SRK_API int srk_ba_debug_apply(void* h, const double* corrections, double* err_new);
 
 /* Kernel timing for bench.py: CUDA-event time (ms) of the last launch of each kernel family on this handle's stream,
  * enabled with srk_ba_set_timing(h, 1).  names: "jacobian", "frame_blocks", "schur", "solve", "backsub", "update", "residual". */
-int srk_ba_set_timing(void* h, int enabled);
-int srk_ba_get_timing(void* h, const char* name, double* ms_last, double* ms_total, int64_t* launches);
+SRK_API int srk_ba_set_timing(void* h, int enabled);
+SRK_API int srk_ba_get_timing(void* h, const char* name, double* ms_last, double* ms_total, int64_t* launches);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) k_potrf64(int n, int k0, double* __restri
         int c = e / NB, r = e % NB;
         T[c][r] = (r < nb && c < nb && r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : 0.0;
     }
-    if (tid < NB) y[tid] = tid < nb ? b[k0 + tid] : 0.0;
+    if (tid < NB) y[tid] = (b != nullptr && tid < nb) ? b[k0 + tid] : 0.0;
     __syncthreads();
     for (int j = 0; j < nb; ++j) {
         double d = T[j][j];
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) k_potrf64(int n, int k0, double* __restri
         int c = e / NB, r = e % NB;
         if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = T[c][r];
     }
-    if (tid < nb) b[k0 + tid] = y[tid];
+    if (b != nullptr && tid < nb) b[k0 + tid] = y[tid];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(TR) k_trsm64(int n, int k0, double* __restrict
         int c = e / NB, r = e % NB;
         L[e] = (r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : 0.0;
     }
-    if (tid < NB) y[tid] = b[k0 + tid];
+    if (tid < NB) y[tid] = b != nullptr ? b[k0 + tid] : 0.0;
     for (int c = 0; c < NB; ++c) Xt[c * TR + tid] = tid < rows ? A[(size_t)(k0 + c) * ld + r0 + tid] : 0.0;
     __syncthreads();
     double acc = 0.0;
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(TR) k_trsm64(int n, int k0, double* __restrict
     }
     if (tid < rows) {
         for (int c = 0; c < NB; ++c) A[(size_t)(k0 + c) * ld + r0 + tid] = Xt[c * TR + tid];
-        b[r0 + tid] -= acc;
+        if (b != nullptr) b[r0 + tid] -= acc;
     }
 }
 
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256, 1) k_syrk(int n, int k0, double* __restri
 //   ... except that x_kb itself must first be produced: launch order is  solve_diag(kb) ; update(j<kb) — two tiny
 //   kernels would double the launch count, so CTA j == kb-1 of launch kb also solves the diagonal block kb-1 after its
 //   own update, and launch kb == last block starts with a diagonal-only launch.
-__global__ void __launch_bounds__(128) k_back64(int n, int kb, int first, double* __restrict__ A, int64_t ld, double* __restrict__ b) {
+__global__ void __launch_bounds__(128) k_back64(int n, int kb, int first, const double* __restrict__ A, int64_t ld, double* __restrict__ b) {
     __shared__ double xk[NB];
     __shared__ double yj[NB];
     __shared__ double T[NB][NB + 1];
@@ -215,32 +215,125 @@ __global__ void __launch_bounds__(128) k_back64(int n, int kb, int first, double
     if (tid < NB) b[j0 + tid] = yj[tid];
 }
 
-__global__ void k_symv_lower(int n, const double* __restrict__ A, int64_t ld, const double* __restrict__ x, double* __restrict__ y) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward substitution L y = b with an existing factor (used by the refinement steps), block column kb ascending:
+//   first launch: diagonal solve of block 0.  Launch kb: CTA j (j = kb+1 .. nblk-1) applies  b_j -= L(j,kb) * y_kb ;
+//   the CTA of block kb+1 then owns a complete right-hand side and solves its diagonal block.
+__global__ void __launch_bounds__(128) k_fwd64(int n, int kb, int first, const double* __restrict__ A, int64_t ld, double* __restrict__ b) {
+    __shared__ double yk[NB];
+    __shared__ double yj[NB];
+    __shared__ double part[2][NB];
+    __shared__ double T[NB][NB + 1];
+    const int tid = threadIdx.x;
+    auto diag_solve = [&](int j0) {
+        const int nb = min(NB, n - j0);
+        for (int e = tid; e < NB * NB; e += 128) { int c = e / NB, r = e % NB; T[c][r] = (r < nb && c < nb && r >= c) ? A[(size_t)(j0 + c) * ld + j0 + r] : 0.0; }
+        __syncthreads();
+        for (int c = 0; c < nb; ++c) {
+            if (tid == 0) yj[c] = yj[c] / T[c][c];
+            __syncthreads();
+            if (tid > c && tid < nb) yj[tid] -= T[c][tid] * yj[c];
+            __syncthreads();
+        }
+        if (tid < nb) b[j0 + tid] = yj[tid];
+    };
+    if (first) {
+        if (tid < NB) yj[tid] = tid < n ? b[tid] : 0.0;
+        __syncthreads();
+        diag_solve(0);
+        return;
+    }
+    const int k0 = kb * NB;
+    const int j = kb + 1 + blockIdx.x;
+    const int j0 = j * NB;
+    const int nbj = min(NB, n - j0);
+    if (tid < NB) { yk[tid] = b[k0 + tid]; yj[tid] = tid < nbj ? b[j0 + tid] : 0.0; }
+    __syncthreads();
+    {
+        const int r = tid & (NB - 1), half = tid >> 6;
+        double s = 0.0;
+        if (r < nbj)
+            for (int c = half; c < NB; c += 2) s += A[(size_t)(k0 + c) * ld + j0 + r] * yk[c];
+        part[half][r] = s;
+    }
+    __syncthreads();
+    if (tid < NB) yj[tid] -= part[0][tid] + part[1][tid];
+    __syncthreads();
+    if (j == kb + 1) diag_solve(j0);
+    else if (tid < nbj) b[j0 + tid] = yj[tid];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Mirror the lower triangle into the upper one, 32x32 tiles through shared memory (both sides coalesced).
+__global__ void __launch_bounds__(256) k_mirror_lower(int n, double* __restrict__ A, int64_t ld) {
+    __shared__ double t[32][33];
+    const int ti = blockIdx.y, tj = blockIdx.x;   // tile row / tile col; only ti >= tj does work
+    if (ti < tj) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int cc = ty; cc < 32; cc += 8) {
+        int r = ti * 32 + tx, c = tj * 32 + cc;
+        t[cc][tx] = (r < n && c < n) ? A[(size_t)c * ld + r] : 0.0;
+    }
+    __syncthreads();
+    for (int cc = ty; cc < 32; cc += 8) {
+        // destination element (row = tj*32 + tx, col = ti*32 + cc) = source (row = ti*32 + cc, col = tj*32 + tx)
+        int r = tj * 32 + tx, c = ti * 32 + cc;
+        if (r < n && c < n && c > r) A[(size_t)c * ld + r] = t[tx][cc];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// r = b - A*x for symmetric A with BOTH triangles stored (row i is read as the contiguous column i), accumulated in
+// double-double (two-prod / two-sum), one warp per row.  This is the extended-precision residual of the refinement.
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double bh, double bl) {
+    double s = __dadd_rn(hi, bh);
+    double bb = __dadd_rn(s, -hi);
+    double e = __dadd_rn(__dadd_rn(hi, -__dadd_rn(s, -bb)), __dadd_rn(bh, -bb));
+    e = __dadd_rn(e, __dadd_rn(lo, bl));
+    hi = __dadd_rn(s, e);
+    lo = __dadd_rn(e, -__dadd_rn(hi, -s));
+}
+__global__ void __launch_bounds__(256) k_residual_dd(int n, const double* __restrict__ A, int64_t ld, const double* __restrict__ x,
+                                                     const double* __restrict__ b, double* __restrict__ r) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
-    double s = 0.0;
-    for (int j = 0; j <= i; ++j) s += A[(size_t)j * ld + i] * x[j];
-    for (int j = i + 1; j < n; ++j) s += A[(size_t)i * ld + j] * x[j];
-    y[i] = s;
+    const double* col = A + (size_t)i * ld;
+    double hi = 0.0, lo = 0.0;
+    for (int j = lane; j < n; j += 32) {
+        double a = col[j], xv = x[j];
+        double p = __dmul_rn(a, xv);
+        double e = __fma_rn(a, xv, -p);
+        dd_add(hi, lo, p, e);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        double oh = __shfl_xor_sync(0xffffffffu, hi, s), ol = __shfl_xor_sync(0xffffffffu, lo, s);
+        dd_add(hi, lo, oh, ol);
+    }
+    if (lane == 0) {
+        double rh = b[i], rl = 0.0;
+        dd_add(rh, rl, -hi, -lo);
+        r[i] = rh;
+    }
 }
-__global__ void k_mirror_lower(int n, double* __restrict__ A, int64_t ld) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (int64_t)n * n) return;
-    int c = (int)(e / n), r = (int)(e % n);
-    if (r > c) A[(size_t)r * ld + c] = A[(size_t)c * ld + r];
+__global__ void k_axpy1(int n, const double* __restrict__ d, double* __restrict__ x) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += d[i];
 }
 
-size_t dense_cholesky_work_doubles(int) { return 0; }
-
-int64_t dense_cholesky_solve(cudaStream_t st, int n, double* A, int64_t ld, double* b, int* info_dev, double*) {
+static void set_attrs_once() {
     static bool attr_set = false;
+    if (attr_set) return;
+    cudaFuncSetAttribute(k_trsm64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (NB * NB + NB * TR + NB)));
+    cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * NB * SLD)));
+    attr_set = true;
+}
+
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* b, int* info_dev) {
+    set_attrs_once();
     const size_t trsm_smem = sizeof(double) * (NB * NB + NB * TR + NB);
     const size_t syrk_smem = sizeof(double) * (2 * NB * SLD);
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_trsm64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem);
-        cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem);
-        attr_set = true;
-    }
     int64_t launches = 0;
     cudaMemsetAsync(info_dev, 0, sizeof(int), st);
     const int nblk = (n + NB - 1) / NB;
@@ -254,18 +347,29 @@ int64_t dense_cholesky_solve(cudaStream_t st, int n, double* A, int64_t ld, doub
             k_syrk<<<T * (T + 1) / 2, 256, syrk_smem, st>>>(n, k0, A, ld); ++launches;
         }
     }
-    // backward: L^T x = y
-    k_back64<<<1, 128, 0, st>>>(n, nblk - 1, 1, A, ld, b); ++launches;
-    for (int kb = nblk - 1; kb >= 1; --kb) { k_back64<<<kb, 128, 0, st>>>(n, kb, 0, A, ld, b); ++launches; }
     return launches;
 }
-
-void launch_symv_lower(cudaStream_t st, int n, const double* A, int64_t ld, const double* x, double* y) {
-    k_symv_lower<<<(n + 127) / 128, 128, 0, st>>>(n, A, ld, x, y);
+int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* b) {
+    const int nblk = (n + NB - 1) / NB;
+    int64_t launches = 0;
+    k_fwd64<<<1, 128, 0, st>>>(n, 0, 1, L, ld, b); ++launches;
+    for (int kb = 0; kb + 1 < nblk; ++kb) { k_fwd64<<<nblk - kb - 1, 128, 0, st>>>(n, kb, 0, L, ld, b); ++launches; }
+    return launches;
+}
+int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* b) {
+    const int nblk = (n + NB - 1) / NB;
+    int64_t launches = 0;
+    k_back64<<<1, 128, 0, st>>>(n, nblk - 1, 1, L, ld, b); ++launches;
+    for (int kb = nblk - 1; kb >= 1; --kb) { k_back64<<<kb, 128, 0, st>>>(n, kb, 0, L, ld, b); ++launches; }
+    return launches;
 }
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld) {
-    int64_t tot = (int64_t)n * n;
-    k_mirror_lower<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(n, A, ld);
+    int T = (n + 31) / 32;
+    k_mirror_lower<<<dim3(T, T), 256, 0, st>>>(n, A, ld);
 }
+void launch_residual_dd(cudaStream_t st, int n, const double* A, int64_t ld, const double* x, const double* b, double* r) {
+    k_residual_dd<<<(n + 7) / 8, 256, 0, st>>>(n, A, ld, x, b, r);
+}
+void launch_axpy1(cudaStream_t st, int n, const double* d, double* x) { k_axpy1<<<(n + 255) / 256, 256, 0, st>>>(n, d, x); }
 
 }  // namespace srk

@@ -26,13 +26,21 @@ void launch_debug_point_blocks(cudaStream_t st, int64_t N, int64_t O, const int6
 void launch_debug_F_blocks(cudaStream_t st, int64_t O, const double* J, double* F);
 
 // Dense reduced-camera solve (chol_kernels.cu).  A is column-major n x n with leading dimension ld, lower triangle
-// referenced; b[n] is overwritten by the solution.  Returns the number of kernels launched; *info (device int) is set
-// to the 1-based index of the first non-positive pivot (0 = success).
-int64_t dense_cholesky_solve(cudaStream_t st, int n, double* A, int64_t ld, double* b, int* info_dev, double* work);
-size_t dense_cholesky_work_doubles(int n);
-// y = A*x using only the lower triangle of symmetric A (for parity hooks / refinement).
-void launch_symv_lower(cudaStream_t st, int n, const double* A, int64_t ld, const double* x, double* y);
-// mirror the lower triangle into the upper one (parity hook output)
+// referenced and overwritten by L.  b (optional) gets the forward substitution fused into the factorisation.
+// *info_dev is set to the 1-based index of the first non-positive pivot (0 = success).  All return launch counts.
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* b, int* info_dev);
+int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* b);
+int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* b);
+// mirror the lower triangle into the upper one
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld);
+// r = b - A*x, symmetric A with both triangles stored, double-double accumulation
+void launch_residual_dd(cudaStream_t st, int n, const double* A, int64_t ld, const double* x, const double* b, double* r);
+void launch_axpy1(cudaStream_t st, int n, const double* d, double* x);
+
+// aux_kernels.cu
+void launch_pack_attempt(cudaStream_t st, const double* err_sum, const int* finite_flag, const unsigned long long* skipped_cnt, int rank, int world,
+                         double* slots);
+void launch_add_points_aos(cudaStream_t st, int64_t N, const double* X, const double* corr_aos, double* Xtry);
+
 
 }  // namespace srk
