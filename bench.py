@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the BA hot path (BASELINE.json metric: BA LM iterations/s and reprojection residuals/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5|tiny]
+
+A step = one Levenberg-Marquardt outer iteration (one derivative pass, then solve attempts + trial-state error
+evaluations until the error decreases) from the same resident initial state (srk_ba_reset between steps).
+`value` = reprojection residuals carried through full LM iterations per second, summed over all ranks, inputs resident
+in HBM.  `e2e` = the same through srk_ba_solve with HOST buffers (H2D of the scene and D2H of the refined state inside
+the timed region).  Weak scaling: every rank owns its own 1M points / 10M observations of one shared 1000-camera world;
+the reduced camera system is all-reduced over NCCL and solved redundantly on every rank.
+
+--impl reference times the CPU oracle (the reference's algorithm restated in plain C++, single-threaded like the
+reference) on a bounded sample of the same workload shape.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_cams, n_points, obs_per_point, description)
+    "c3": (1000, 1_000_000, 10, "synthetic large-scale BA: 1,000 cameras x 1M points x 10M observations (BASELINE.json configs[2])"),
+    "c2": (50, 10_000, 50, "synthetic circle-grid-shaped BA: 50 cameras x 10k points, every point in every frame (configs[1])"),
+    "c5": (10_000, 5_000_000, 10, "synthetic city-scale BA: 10,000 cameras x 5M points x 50M observations, PCG solve (configs[4])"),
+    "tiny": (40, 4000, 8, "tiny ring scene (smoke)"),
+}
+# bounded CPU sample of each workload (same generator, fewer cameras/points so the oracle finishes in ~10-30 s)
+CPU_SAMPLES = {"c3": (100, 100_000, 10), "c2": (50, 2_000, 50), "c5": (100, 100_000, 10), "tiny": (40, 4000, 8)}
+METRIC = "BA reprojection residuals/sec through full LM iterations"
+UNIT = "residuals/s"
+
+
+def make_scene(name, rank=0, sample=False):
+    from surikatoko_b200 import scenes
+    M, N, k = CPU_SAMPLES[name] if sample else WORKLOADS[name][:3]
+    return scenes.ring_scene(M, N, k, seed=1234, point_offset=rank)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_run(name, steps, warmup):
+    """Oracle (the reference's algorithm, plain C++17, 1 thread) on the bounded sample: residuals/s through LM iterations."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib as ol
+    ol.build()
+    pr = make_scene(name, sample=True)
+    op = ol.Problem(pr.obs_cam, pr.obs_point, pr.obs_xy, pr.points, pr.cams, pr.K, False, pr.f0)
+    times, iters = [], []
+    for i in range(warmup + steps):
+        if i < warmup and i > 0:
+            continue  # one warm-up pass is enough to page the library and the scene in
+        r = ol.ba_solve(op, max_outer_iters=1, flow="sparse", solve="qr", acc="double")
+        if i >= warmup:
+            times.append(r.seconds); iters.append(max(1, r.outer_iters))
+    t = float(np.sum(times))
+    M, N, k = CPU_SAMPLES[name]
+    return {"value": pr.n_obs * len(times) / t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "ring scene %d cameras x %d points x %d observations (same generator and seed as the GPU workload), %d LM iteration(s), "
+                      "oracle sparse-equivalent flow + Householder QR, single thread like the reference" % (M, N, pr.n_obs, len(times)),
+            "seconds_per_iteration": t / len(times), "n_obs": pr.n_obs}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3)); warmup = 1 if args.warmup > 0 else 0
+    cb = cpu_oracle_run(args.workload, steps, warmup)
+    out = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+           "ms_per_step": cb["seconds_per_iteration"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": WORKLOADS[args.workload][3], "sample": cb["sample"]},
+           "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def fp64_gemm_peak(torch, dev):
+    """cuBLAS DGEMM 8192^3, best of 5 -- the denominator for the FP64 tensor-pipe (DMMA) kernels; MEASURED_PEAKS.json has no FP64 entry."""
+    n = 8192
+    a = torch.randn(n, n, device=dev, dtype=torch.float64); b = torch.randn(n, n, device=dev, dtype=torch.float64)
+    torch.matmul(a, b); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import surikatoko_b200 as sb
+
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    name = args.workload
+    M, N, k, desc = WORKLOADS[name]
+
+    prob = make_scene(name, rank=rank)
+    O = prob.n_obs
+    # pinned host copies (the e2e leg copies from these)
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t, t.numpy()
+    keep = []
+    for attr in ("obs_cam", "obs_point", "obs_xy", "points", "cams", "K"):
+        t, v = pin(getattr(prob, attr)); keep.append(t); setattr(prob, attr, v)
+    pts0, cams0 = prob.points.copy(), prob.cams.copy()
+
+    stream = torch.cuda.Stream(device=dev)
+    eng = sb.Engine(local)
+    eng.set_stream(stream.cuda_stream)
+    views = {}
+    if world > 1:
+        class _Dev:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+
+        def allreduce(ptr, count, st):
+            key = (ptr, count)
+            t = views.get(key)
+            if t is None:
+                t = torch.as_tensor(_Dev(ptr, count), device=dev); views[key] = t
+            with torch.cuda.stream(stream):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        eng.set_allreduce(allreduce, rank, world)
+
+    solver = {"c5": sb.SOLVER_BLOCK_PCG}.get(name, sb.SOLVER_AUTO)
+    opt1 = sb.BAOptions(max_outer_iters=1, solver=solver)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        assert eng.bind(prob, opt1), "gauge normalisation failed on the synthetic scene"
+        # ---------------- device-resident steps
+        launches = 0
+        for _ in range(args.warmup):
+            eng.reset(); rep = eng.run(opt1)
+        barrier()
+        eng.set_timing(True)
+        clocks = ClockSampler(local); clocks.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        attempts = 0
+        for _ in range(args.steps):
+            eng.reset(); rep = eng.run(opt1)
+            launches += rep.gpu_launches + 1; attempts += rep.attempts_count
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop()
+        timing = eng.get_timing()
+        eng.set_timing(False)
+        # ---------------- end to end through srk_ba_solve with host buffers
+        e2e_steps = max(1, min(args.steps, 5))
+        for i in range(1 + e2e_steps):
+            prob.points[:] = pts0; prob.cams[:] = cams0
+            if i == 1:
+                barrier(); t0 = time.perf_counter(); g0 = torch.cuda.Event(enable_timing=True); g0.record(stream)
+            rep_e = eng.solve(prob, opt1)
+        g1 = torch.cuda.Event(enable_timing=True); g1.record(stream)
+        barrier()
+        ms_e2e = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    tot_obs = torch.tensor([float(O)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(tot_obs, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = float(t[0]), float(t[1]); total_obs = float(tot_obs[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    f64_peak = fp64_gemm_peak(torch, dev)
+    nf = 10 * M - 7
+    # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
+    alg = {"jacobian": ("hbm", 248.0 * O + 24.0 * N + 200.0 * M), "schur": ("hbm", 232.0 * O + 72.0 * N + 8.0 * nf * nf + 80.0 * M),
+           "backsub": ("hbm", 232.0 * O + 72.0 * N + 80.0 * M + 24.0 * N), "residual": ("hbm", 24.0 * O + 24.0 * N + 200.0 * M),
+           "frame_blocks": ("hbm", 20.0 * O + 24.0 * N + 200.0 * M + 880.0 * M), "solve": ("tensor", nf ** 3 / 3.0 + 2.0 * nf * nf)}
+    kernels = {}
+    for fam, (bound, work) in alg.items():
+        tm = timing[fam]
+        if tm["count"] == 0:
+            continue
+        avg_ms = tm["ms_total"] / tm["count"]
+        if bound == "hbm":
+            ach = work / (avg_ms * 1e-3) / 1e9
+            kernels[fam] = {"bound": "hbm", "avg_ms": avg_ms, "launch_groups": tm["count"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": ach / hbm_peak, "share_of_step": tm["ms_total"] / ms}
+        else:
+            ach = work / (avg_ms * 1e-3) / 1e12
+            kernels[fam] = {"bound": "tensor", "avg_ms": avg_ms, "launch_groups": tm["count"], "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s",
+                            "frac": ach / f64_peak, "share_of_step": tm["ms_total"] / ms}
+    for fam in ("update", "allreduce"):
+        if timing[fam]["count"]:
+            kernels[fam] = {"avg_ms": timing[fam]["ms_total"] / timing[fam]["count"], "launch_groups": timing[fam]["count"],
+                            "share_of_step": timing[fam]["ms_total"] / ms}
+    dominant = max((f for f in kernels if "frac" in kernels[f]), key=lambda f: kernels[f]["share_of_step"])
+    dk = kernels[dominant]
+    roofline = {"kernel": dominant, "bound": dk["bound"], "achieved": dk["achieved"], "peak": dk["peak"], "unit": dk["unit"], "frac": dk["frac"],
+                "traffic": None,
+                "peak_source": hbm_src if dk["bound"] == "hbm" else "cuBLAS DGEMM 8192^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json)"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_oracle_run(name, 1, 0)
+
+    h2d = 24 * O + 24 * N + 96 * M + 72 * M
+    d2h = 24 * N + 96 * M
+    steps_per_s = args.steps / (ms * 1e-3)
+    out = {"metric": METRIC, "value": total_obs * steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "lm_iters_per_sec": steps_per_s, "attempts_per_step": attempts / args.steps,
+           "config": {"workload": desc, "per_rank": {"n_cams": M, "n_points": N, "n_obs": int(O)}, "solver": "dense_cholesky" if rep.solver_used == 1 else "block_pcg",
+                      "l2": "inputs larger than L2 (Jacobian store %.2f GB per rank)" % (224.0 * O / 1e9), "parallelism": "points sharded, dp%d" % world},
+           "clocks": clk,
+           "e2e": {"value": total_obs * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+           "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "fp64_gemm_peak_tflops": f64_peak,
+           "err_initial": rep.err_initial, "err_after_step": rep.err_final}
+    if cpu is not None:
+        out["cpu_baseline"] = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
