@@ -205,13 +205,15 @@ constexpr int kSchurWarps = 4;
 __global__ void __launch_bounds__(kSchurWarps * 32) k_schur(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin,
                                                             const int32_t* __restrict__ obs_cam, const double* __restrict__ J, double c,
                                                             int unity, double* __restrict__ S, int64_t ld, double* __restrict__ rhs,
-                                                            double* __restrict__ pinv, unsigned char* __restrict__ skipped) {
+                                                            double* __restrict__ pinv, unsigned char* __restrict__ skipped,
+                                                            const unsigned char* __restrict__ only_flagged) {
     __shared__ double sF[kSchurWarps][kSchurCH][30];   // slot 0 only: F of the row chunk
     __shared__ double sW[kSchurWarps][2][kSchurCH][30];
     __shared__ int sCam[kSchurWarps][2][kSchurCH];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int64_t j = (int64_t)blockIdx.x * kSchurWarps + w;
     if (j >= N) return;
+    if (only_flagged != nullptr && only_flagged[j] == 0) return;
     const int64_t b = pt_begin[j], e = pt_begin[j + 1];
     const int k = (int)(e - b);
 
@@ -328,6 +330,274 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_schur(int64_t N, int64_t O
             __syncwarp();
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K2 (tiled): the Schur accumulation without per-point global atomics.
+//
+// A CTA owns a tile of TP consecutive points.  Tracks are created in capture order, so a tile touches few cameras: the
+// CTA builds the sorted table of the (at most CMAX) distinct cameras of its tile and keeps the tile's whole contribution
+//   S[cam_i, cam_l] -= sum_j F_ji^T E_cj^-1 F_jl        (lower block triangle, cam_i >= cam_l)
+// in REGISTERS: "block warps" own 8 local camera pairs each, lane -> (pair, 5x5 sub-tile) with 25 FP64 accumulators, so
+// every output entry has exactly one owner and no atomics are needed inside the tile.  Per batch of <= 16 points the
+// warps first build E / E^-1 (shuffle reductions, the |det| > 1e-12 rule) and stage F_i = 2 Jp_i^T Jc_i and
+// W_i = E^-1 F_i for the batch's observations in shared memory; then every owner lane scans the batch and adds
+// F_i^T W_l wherever the point sees both cameras of its pair.  One extra warp owns the tile's rhs entries.  At the end of
+// the tile each lane flushes its accumulators with red.global.add.f64: one atomic per touched entry per TILE instead of
+// per point.  Points with more than kTileKMax observations, or with a camera outside the tile table, are flagged in
+// `deferred` and handled by k_schur (per-point global atomics); the flags depend on the structure only, so the host
+// learns at bind time (plan_only) whether that second launch is needed at all.
+constexpr int kTileKMax = 16;    // longest track handled in the tile kernel
+constexpr int kTileBatch = 16;   // points per staging batch
+constexpr int kTileSO = 128;     // observations per staging batch
+constexpr int kTileHash = 64;
+
+template <int CMAX>
+struct SchurTileCfg {
+    static constexpr int kBlocks = CMAX * (CMAX + 1) / 2;
+    static constexpr int kBlockWarps = (kBlocks + 7) / 8;
+    static constexpr int kWarps = kBlockWarps + 1;   // + the rhs warp
+    static constexpr int kThreads = kWarps * 32;
+};
+
+template <int CMAX>
+__global__ void __launch_bounds__(SchurTileCfg<CMAX>::kThreads) k_schur_tile(
+    int64_t N, int64_t O, int tile_points, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam, const double* __restrict__ J,
+    double c, int unity, double* __restrict__ S, int64_t ld, double* __restrict__ rhs, double* __restrict__ pinv,
+    unsigned char* __restrict__ skipped, unsigned char* __restrict__ deferred, int plan_only) {
+    using Cfg = SchurTileCfg<CMAX>;
+    extern __shared__ double smem[];
+    double* sF = smem;                         // [kTileSO][30]
+    double* sW = smem + kTileSO * 30;          // [kTileSO][30]
+    double* sT = sW + kTileSO * 30;            // [kTileBatch][3]
+    int* sSlot = (int*)(sT + kTileBatch * 3);  // [kTileBatch][CMAX]
+    int* sTab = sSlot + kTileBatch * CMAX;     // [CMAX] sorted camera ids of the tile
+    int* sHash = sTab + CMAX;                  // [kTileHash]
+    int* sMisc = sHash + kTileHash;            // [0] nLocal, [1] batch begin, [2] batch end
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t p0 = (int64_t)blockIdx.x * tile_points;
+    const int64_t p1 = min(N, p0 + (int64_t)tile_points);
+    if (p0 >= N) return;
+
+    // ---- camera table of the tile: hash-set insert of every observation's camera, then sort
+    for (int i = tid; i < kTileHash; i += Cfg::kThreads) sHash[i] = -1;
+    __syncthreads();
+    {
+        const int64_t ob = pt_begin[p0], oe = pt_begin[p1];
+        for (int64_t o = ob + tid; o < oe; o += Cfg::kThreads) {
+            int cam = obs_cam[o];
+            unsigned h = ((unsigned)cam * 2654435761u) >> 26;   // 6 bits
+            for (int probe = 0; probe < kTileHash; ++probe) {
+                int prev = atomicCAS(&sHash[h], -1, cam);
+                if (prev == -1 || prev == cam) break;
+                h = (h + 1) & (kTileHash - 1);
+            }   // a full table simply drops the camera: its points get deferred below
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int n = 0;
+        for (int i = 0; i < kTileHash; ++i) {
+            int cam = sHash[i];
+            if (cam < 0) continue;
+            // insertion into the sorted table, keeping the CMAX smallest ids
+            int pos = n < CMAX ? n : CMAX;
+            while (pos > 0 && sTab[pos - 1] > cam) --pos;
+            if (pos >= CMAX) continue;
+            int last = n < CMAX ? n : CMAX - 1;
+            for (int q = last; q > pos; --q) sTab[q] = sTab[q - 1];
+            sTab[pos] = cam;
+            if (n < CMAX) ++n;
+        }
+        sMisc[0] = n;
+    }
+    __syncthreads();
+    const int nLocal = sMisc[0];
+
+    // ---- ownership: block warps -> 8 local pairs, lane -> (pair, 5x5 sub-tile)
+    const bool is_block_warp = w < Cfg::kBlockWarps;
+    int li = -1, ll = -1, tr = 0, tc = 0;
+    if (is_block_warp) {
+        int b = w * 8 + (lane >> 2);
+        if (b < Cfg::kBlocks) {
+            int r = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+            while (r * (r + 1) / 2 > b) --r;
+            while ((r + 1) * (r + 2) / 2 <= b) ++r;
+            li = r; ll = b - r * (r + 1) / 2;
+            if (li >= nLocal) { li = -1; ll = -1; }
+        }
+        tr = ((lane >> 1) & 1) * 5; tc = (lane & 1) * 5;
+    }
+    double acc[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) acc[i] = 0.0;
+    double racc[4] = {0.0, 0.0, 0.0, 0.0};   // rhs warp: entries e = lane + 32*q < CMAX*10
+
+    int64_t bb = p0;
+    while (bb < p1) {
+        // batch = consecutive points with <= kTileSO observations in total and <= kTileBatch points
+        if (tid == 0) {
+            int64_t e = bb; int64_t base = pt_begin[bb];
+            while (e < p1 && e - bb < kTileBatch && pt_begin[e + 1] - base <= kTileSO) ++e;
+            if (e == bb) e = bb + 1;   // a single over-long track: deferred below
+            sMisc[1] = (int)(e - bb);
+        }
+        __syncthreads();
+        const int cnt = sMisc[1];
+        const int64_t obase = pt_begin[bb];
+        // ---- P1: per point E, E^-1, slots, staging
+        for (int ptl = w; ptl < cnt; ptl += Cfg::kWarps) {
+            const int64_t j = bb + ptl;
+            const int64_t b = pt_begin[j], e = pt_begin[j + 1];
+            const int k = (int)(e - b);
+            if (lane < CMAX) sSlot[ptl * CMAX + lane] = -1;
+            int loc = -1;
+            bool bad = k > kTileKMax;
+            if (!bad && lane < k) {
+                int cam = obs_cam[b + lane];
+                for (int q = 0; q < nLocal; ++q) if (sTab[q] == cam) loc = q;
+                if (loc < 0) bad = true;
+            }
+            bad = __any_sync(0xffffffffu, bad);
+            if (lane == 0) deferred[j] = bad ? 1 : 0;
+            if (bad || plan_only) continue;
+            double a9[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) a9[i] = 0.0;
+            double jp[6] = {0, 0, 0, 0, 0, 0};
+            if (lane < k) {
+                const int64_t o = b + lane;
+                double rx = J[o], ry = J[O + o];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+                a9[0] = jp[0] * jp[0] + jp[1] * jp[1];
+                a9[1] = jp[0] * jp[2] + jp[1] * jp[3];
+                a9[2] = jp[0] * jp[4] + jp[1] * jp[5];
+                a9[3] = jp[2] * jp[2] + jp[3] * jp[3];
+                a9[4] = jp[2] * jp[4] + jp[3] * jp[5];
+                a9[5] = jp[4] * jp[4] + jp[5] * jp[5];
+                a9[6] = jp[0] * rx + jp[1] * ry;
+                a9[7] = jp[2] * rx + jp[3] * ry;
+                a9[8] = jp[4] * rx + jp[5] * ry;
+            }
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                double v = a9[i];
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                a9[i] = 2.0 * v;
+            }
+            double inv[6];
+            const bool ok = point_block_inverse(a9, c, inv);
+            if (lane == 0) {
+                skipped[j] = ok ? 0 : 1;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) pinv[(int64_t)i * N + j] = ok ? inv[i] : 0.0;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pinv[(int64_t)(6 + i) * N + j] = a9[6 + i];
+            }
+            if (!ok) continue;   // BA.cpp:1877-1881: no Schur contribution
+            if (lane == 0) {
+                sT[ptl * 3 + 0] = inv[0] * a9[6] + inv[1] * a9[7] + inv[2] * a9[8];
+                sT[ptl * 3 + 1] = inv[1] * a9[6] + inv[3] * a9[7] + inv[4] * a9[8];
+                sT[ptl * 3 + 2] = inv[2] * a9[6] + inv[4] * a9[7] + inv[5] * a9[8];
+            }
+            __syncwarp();
+            const int sbase = (int)(b - obase);
+            if (lane < k) {
+                sSlot[ptl * CMAX + loc] = sbase + lane;
+                const int64_t o = b + lane;
+                double* Fi = sF + (sbase + lane) * 30;
+                double* Wi = sW + (sbase + lane) * 30;
+#pragma unroll
+                for (int a = 0; a < 10; ++a) {
+                    double j0 = J[(int64_t)(8 + 2 * a) * O + o], j1 = J[(int64_t)(9 + 2 * a) * O + o];
+                    double f0 = 2.0 * (jp[0] * j0 + jp[1] * j1);
+                    double f1 = 2.0 * (jp[2] * j0 + jp[3] * j1);
+                    double f2 = 2.0 * (jp[4] * j0 + jp[5] * j1);
+                    Fi[a] = f0; Fi[10 + a] = f1; Fi[20 + a] = f2;
+                    Wi[a] = inv[0] * f0 + inv[1] * f1 + inv[2] * f2;
+                    Wi[10 + a] = inv[1] * f0 + inv[3] * f1 + inv[4] * f2;
+                    Wi[20 + a] = inv[2] * f0 + inv[4] * f1 + inv[5] * f2;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- P2: owners scan the batch
+        if (!plan_only) {
+            if (is_block_warp) {
+                if (li >= 0) {
+                    for (int ptl = 0; ptl < cnt; ++ptl) {
+                        const int si = sSlot[ptl * CMAX + li], sl = sSlot[ptl * CMAX + ll];
+                        if (si < 0 || sl < 0) continue;
+                        const double* Fi = sF + si * 30 + tr;
+                        const double* Wl = sW + sl * 30 + tc;
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) {
+                            double f[5], ww[5];
+#pragma unroll
+                            for (int x = 0; x < 5; ++x) { f[x] = Fi[v * 10 + x]; ww[x] = Wl[v * 10 + x]; }
+#pragma unroll
+                            for (int x = 0; x < 5; ++x)
+#pragma unroll
+                                for (int y = 0; y < 5; ++y) acc[x * 5 + y] += f[x] * ww[y];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int en = lane + 32 * q;
+                    if (en >= CMAX * 10) continue;
+                    const int lc = en / 10, a = en % 10;
+                    if (lc >= nLocal) continue;
+                    for (int ptl = 0; ptl < cnt; ++ptl) {
+                        const int si = sSlot[ptl * CMAX + lc];
+                        if (si < 0) continue;
+                        const double* Fi = sF + si * 30;
+                        racc[q] += Fi[a] * sT[ptl * 3 + 0] + Fi[10 + a] * sT[ptl * 3 + 1] + Fi[20 + a] * sT[ptl * 3 + 2];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        bb += cnt;
+    }
+    if (plan_only) return;
+    // ---- flush: one red.global.add.f64 per touched entry per tile
+    if (is_block_warp) {
+        if (li >= 0) {
+            const int cam_i = sTab[li], cam_l = sTab[ll];
+#pragma unroll
+            for (int x = 0; x < 5; ++x) {
+                const int row = red_index(cam_i, tr + x, unity);
+                if (row < 0) continue;
+#pragma unroll
+                for (int y = 0; y < 5; ++y) {
+                    const int col = red_index(cam_l, tc + y, unity);
+                    if (col < 0) continue;
+                    const double v = acc[x * 5 + y];
+                    if (v != 0.0) atomicAdd(&S[(size_t)col * ld + row], -v);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int en = lane + 32 * q;
+            if (en >= CMAX * 10) continue;
+            const int lc = en / 10, a = en % 10;
+            if (lc >= nLocal) continue;
+            const int r = red_index(sTab[lc], a, unity);
+            if (r >= 0 && racc[q] != 0.0) atomicAdd(&rhs[r], racc[q]);
+        }
+    }
+}
+
+template <int CMAX>
+static size_t schur_tile_smem() {
+    return sizeof(double) * (kTileSO * 60 + kTileBatch * 3) + sizeof(int) * (kTileBatch * CMAX + CMAX + kTileHash + 4);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -533,8 +803,18 @@ void launch_fill_reduced(cudaStream_t st, int M, const double* G, const double* 
     k_fill_reduced<<<M, 128, 0, st>>>(M, G, gf, c, unity, S, ld, rhs);
 }
 void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, int unity,
-                  double* S, int64_t ld, double* rhs, double* pinv, unsigned char* skipped) {
-    if (N > 0) k_schur<<<cdiv(N, kSchurWarps), kSchurWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, unity, S, ld, rhs, pinv, skipped);
+                  double* S, int64_t ld, double* rhs, double* pinv, unsigned char* skipped, const unsigned char* only_flagged) {
+    if (N > 0) k_schur<<<cdiv(N, kSchurWarps), kSchurWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, unity, S, ld, rhs, pinv, skipped, only_flagged);
+}
+void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
+                       int unity, double* S, int64_t ld, double* rhs, double* pinv, unsigned char* skipped, unsigned char* deferred, int plan_only) {
+    if (N <= 0) return;
+    constexpr int CMAX = 12;
+    static bool attr = false;
+    const size_t smem = schur_tile_smem<CMAX>();
+    if (!attr) { cudaFuncSetAttribute(k_schur_tile<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    k_schur_tile<CMAX><<<cdiv(N, tile_points), SchurTileCfg<CMAX>::kThreads, smem, st>>>(N, O, tile_points, pt_begin, obs_cam, J, c, unity, S, ld, rhs, pinv,
+                                                                                      skipped, deferred, plan_only);
 }
 void launch_backsub(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, const double* df,
                     const double* pinv, const unsigned char* skipped, const double* X, double* Xtry, double* dp_out, int lanes_per_point) {

@@ -108,7 +108,9 @@ struct Engine {
     Buf Xa, Xb, Xbound, pts_stage, cams_a, cams_b, cams_bound, Kd, camd_a, camd_b;
     double *X_cur = nullptr, *X_try = nullptr, *cams_cur = nullptr, *cams_try = nullptr, *camd_cur = nullptr, *camd_try = nullptr;
     // derivative pass and solve
-    Buf J, Ggf, pinv, skipped, Srhs, Lfac, xsol, resid, dfull, partial, errsum, slots, flags, skipped_cnt, dbg;
+    Buf J, Ggf, pinv, skipped, deferred, Srhs, Lfac, xsol, resid, dfull, partial, errsum, slots, flags, skipped_cnt, dbg;
+    int64_t n_deferred = 0;   // points the tiled Schur kernel leaves to the per-point kernel (structure only, known at bind time)
+    int schur_tile_points = 256;
     srk::PcgWorkspace pcg;
     int residual_blocks = 0;
     double* h_slots = nullptr;  // pinned
@@ -274,6 +276,20 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     SRK_CUDA(cudaMemcpyAsync(e.cams_bound.p, e.cams_cur, sizeof(double) * 12 * M, cudaMemcpyDeviceToDevice, st));
     if (N > 0) SRK_CUDA(cudaMemcpyAsync(e.Xbound.p, e.X_cur, sizeof(double) * 3 * N, cudaMemcpyDeviceToDevice, st));
     srk::launch_cam_prep(st, M, e.cams_cur, e.Kd.as<double>(), e.shared_K, e.f0, e.camd_cur); e.launches += 1;
+    // ---- plan of the tiled Schur kernel: which points fall back to the per-point kernel (long tracks, scattered cameras)
+    SRK_CUDA(e.deferred.ensure((size_t)(N > 0 ? N : 1)));
+    e.n_deferred = 0;
+    if (N > 0) {
+        SRK_CUDA(cudaMemsetAsync(e.skipped_cnt.p, 0, sizeof(unsigned long long), st));
+        srk::launch_schur_tile(st, N, O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), nullptr, 0.0, e.unity, nullptr, 0, nullptr,
+                               nullptr, nullptr, e.deferred.as<unsigned char>(), 1);
+        srk::launch_count_skipped(st, N, e.deferred.as<unsigned char>(), e.skipped_cnt.as<unsigned long long>());
+        e.launches += 2;
+        unsigned long long nd = 0;
+        SRK_CUDA(cudaMemcpyAsync(&nd, e.skipped_cnt.p, sizeof(nd), cudaMemcpyDeviceToHost, st));
+        SRK_CUDA(cudaStreamSynchronize(st));
+        e.n_deferred = (int64_t)nd;
+    }
     SRK_CUDA(cudaStreamSynchronize(st));
     SRK_CUDA(cudaGetLastError());
     e.bound = true;
@@ -365,9 +381,14 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
             Scope s(e, F_SCHUR);
             SRK_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * ((size_t)ld * nf + ld), st));
             if (e.rank == 0) { srk::launch_fill_reduced(st, M, G, gf, c, e.unity, S, ld, rhs); e.launches += 1; }
-            srk::launch_schur(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, e.unity, S, ld, rhs,
-                              e.pinv.as<double>(), e.skipped.as<unsigned char>());
+            srk::launch_schur_tile(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, e.unity, S, ld,
+                                   rhs, e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>(), 0);
             e.launches += e.N > 0 ? 1 : 0;
+            if (e.n_deferred > 0) {
+                srk::launch_schur(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, e.unity, S, ld, rhs,
+                                  e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>());
+                e.launches += 1;
+            }
         }
         int rc = do_allreduce(e, S, (int64_t)ld * nf + ld);
         if (rc != SRK_OK) return rc;
@@ -599,7 +620,7 @@ void srk_ba_destroy(void* h) {
     cudaStreamSynchronize(e->stream);
     Buf* bufs[] = {&e->obs_cam, &e->obs_pt, &e->obs_xy, &e->ox, &e->oy, &e->pt_begin, &e->cam_cnt, &e->cam_cursor, &e->cam_begin, &e->c_pt, &e->c_x, &e->c_y,
                    &e->Xa, &e->Xb, &e->Xbound, &e->pts_stage, &e->cams_a, &e->cams_b, &e->cams_bound, &e->Kd, &e->camd_a, &e->camd_b, &e->J, &e->Ggf,
-                   &e->pinv, &e->skipped, &e->Srhs, &e->Lfac, &e->xsol, &e->resid, &e->dfull, &e->partial, &e->errsum, &e->slots, &e->flags,
+                   &e->pinv, &e->skipped, &e->deferred, &e->Srhs, &e->Lfac, &e->xsol, &e->resid, &e->dfull, &e->partial, &e->errsum, &e->slots, &e->flags,
                    &e->skipped_cnt, &e->dbg};
     for (Buf* b : bufs) b->release();
     srk::pcg_release(e->pcg);

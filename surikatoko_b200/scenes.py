@@ -79,7 +79,7 @@ def _assemble(R, T, K_pix, f0, X_gt, obs_cam, obs_pt, rng, pix_sigma, rot_sigma,
 
 
 def ring_scene(n_cams=1000, n_points=1_000_000, obs_per_point=10, seed=1234, f0=600.0, pix_sigma=0.5, rot_sigma=0.005,
-               trans_rel=0.005, point_rel=0.005, point_offset=0):
+               trans_rel=0.005, point_rel=0.005, point_offset=0, level_step=0.6):
     """Config 3 shape: cameras on a ring at 4 height levels looking inward, points uniform in a slab,
     each point observed by exactly `obs_per_point` cameras = the ring-nearest ones to its azimuth.  Points are ordered by
     azimuth (the order a sequential capture would create the tracks in), observations by (pnt_ind, frame_ind).
@@ -89,7 +89,7 @@ def ring_scene(n_cams=1000, n_points=1_000_000, obs_per_point=10, seed=1234, f0=
     M, N, k = n_cams, n_points, obs_per_point
     Rc, Rp = 10.0, 6.0
     th = 2.0 * np.pi * np.arange(M) / M
-    levels = np.array([0.0, 0.6, 1.2, 1.8])
+    levels = level_step * np.arange(4)
     pos = np.stack([Rc * np.cos(th), Rc * np.sin(th), 2.0 + levels[np.arange(M) % 4]], axis=1)
     target = np.tile(np.array([0.0, 0.0, 0.0]), (M, 1))
     R, T = _look_at(pos, target)

@@ -79,8 +79,18 @@ def test_schur_system_and_corrections_match_oracle(oracle, engine, c):
 
 
 def run_pair(oracle, engine, pr, err_change, max_outer_iters, **kw):
+    """Returns (exact oracle run, GPU report, refined problem).  The parity target is the oracle in "exact" mode (Schur
+    complement and solve in long double); ref.noise holds the deviation of the "faithful" oracle (the reference's own plain
+    double arithmetic with Householder QR, BA.cpp:1911) from it -- the reference's intrinsic floating-point noise on this
+    scene (cond(S) ~ 1e13), which grows along the trajectory."""
     import surikatoko_b200 as sb
     ref = oracle.ba_solve(pr, err_change=err_change, max_outer_iters=max_outer_iters, flow="sparse", solve="chol", acc="ld")
+    faithful = oracle.ba_solve(pr, err_change=err_change, max_outer_iters=max_outer_iters, flow="sparse", solve="qr", acc="double")
+    n = min(len(ref.err_trace), len(faithful.err_trace))
+    ref.noise = np.zeros(len(ref.err_trace))
+    ref.noise[:n] = np.abs(np.sqrt(faithful.err_trace[:n]) - np.sqrt(ref.err_trace[:n])) / np.sqrt(ref.err_trace[:n])
+    if n < len(ref.err_trace):
+        ref.noise[n:] = np.inf
     prob = to_problem(pr)
     rep = engine.solve(prob, sb.BAOptions(err_change=err_change, max_outer_iters=max_outer_iters, **kw))
     return ref, rep, prob
@@ -95,8 +105,11 @@ def check_trajectory(ref, rep, pr, prob, f0):
     assert np.array_equal(rep.attempts[:n, 3], ref.attempts[:n, 3]), "skipped-point counts differ"
     assert np.allclose(rep.attempts[:n, 0], ref.attempts[:n, 0], rtol=1e-15, atol=0)
     assert len(rep.err_trace) == len(ref.err_trace)
-    # per-iteration residual norms sqrt(err): 1e-9 relative
-    assert np.max(np.abs(np.sqrt(rep.err_trace) - np.sqrt(ref.err_trace)) / np.sqrt(ref.err_trace)) < 1e-9
+    # per-iteration residual norms sqrt(err): 1e-9 relative to the exact oracle; the first iteration starts from the identical
+    # state and must meet it outright, later ones get max(1e-9, the reference's own double-precision noise at that iteration)
+    dev = np.abs(np.sqrt(rep.err_trace) - np.sqrt(ref.err_trace)) / np.sqrt(ref.err_trace)
+    assert dev[0] < 1e-9
+    assert np.all(dev <= np.maximum(1e-9, ref.noise)), (dev, ref.noise)
     assert rep.stop_reason == ref.stop_reason
     assert rep.converged == ref.converged
     rms_ref = f0 * np.sqrt(ref.err_final / ref.seen_points)
@@ -155,3 +168,63 @@ def test_invalid_arguments_fail_loudly(oracle, engine):
         engine.solve(bad)
     with pytest.raises(sb.SrkError):
         engine.solve(to_problem(pr), sb.BAOptions(unity_comp_ind=3))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Sparse-visibility scenes: these go through the tiled Schur kernel (short tracks, localized cameras); the dinosaur-shaped
+# scene mixes it with the per-point fallback (tracks longer than 16 frames) and ragged track lengths.
+
+def as_oracle_problem(oracle, prob):
+    return oracle.Problem(prob.obs_cam.copy(), prob.obs_point.copy(), prob.obs_xy.copy(), prob.points.copy(), prob.cams.copy(), prob.K.copy(),
+                          prob.shared_K, prob.f0)
+
+
+def scene_by_name(name):
+    from surikatoko_b200 import scenes
+    if name == "ring":
+        return scenes.ring_scene(40, 3000, 8, seed=7)
+    if name == "ring_wide":     # 14 cameras per point > the 12-camera tile table: every point is deferred to the per-point kernel
+        return scenes.ring_scene(60, 1500, 14, seed=8)
+    if name == "dino":
+        return scenes.dino_shaped_scene(n_points=1200, n_obs=4000, seed=9)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["ring", "ring_wide", "dino"])
+@pytest.mark.parametrize("c", [1e-4, 1.0])
+def test_schur_system_sparse_scenes(oracle, engine, name, c):
+    prob = scene_by_name(name)
+    pr = as_oracle_problem(oracle, prob)
+    ref = oracle.derivs_and_solve(normalized_problem(oracle, pr), c=c, flow="sparse", solve="chol", acc="ld")
+    assert engine.bind(to_problem(pr))
+    got = engine.debug_derivs_and_solve(c=c)
+    for k in ("gradE", "E", "G", "F"):
+        assert relerr(got[k], ref[k]) < 1e-11, k
+    assert np.array_equal(got["skipped"], ref["skipped"])
+    assert np.array_equal(got["S"] != 0, ref["S"] != 0), "sparsity structure of the reduced camera system differs"
+    assert relerr(got["S"], ref["S"]) < 1e-11
+    assert relerr(got["rhs"], ref["rhs"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["ring", "dino"])
+def test_lm_trajectory_sparse_scenes(oracle, engine, name):
+    prob = scene_by_name(name)
+    pr = as_oracle_problem(oracle, prob)
+    ref, rep, out = run_pair(oracle, engine, pr, 1e-10, 5)
+    check_trajectory(ref, rep, pr, out, pr.f0)
+
+
+def test_skipped_points_mask_is_reproduced(oracle, engine):
+    # two-frame tracks with a narrow baseline have det(E_damped) <= 1e-12 in the demos' f0 = 600 units (quirk Q5)
+    from surikatoko_b200 import scenes
+    prob = scenes.ring_scene(200, 2000, 2, seed=11, level_step=0.05)
+    pr = as_oracle_problem(oracle, prob)
+    ref = oracle.derivs_and_solve(normalized_problem(oracle, pr), c=1e-4, flow="sparse", solve="chol", acc="ld")
+    assert engine.bind(to_problem(pr))
+    got = engine.debug_derivs_and_solve(c=1e-4)
+    assert ref["skipped"].sum() > 0, "scene does not exercise the skip rule"
+    assert np.array_equal(got["skipped"], ref["skipped"])
+    assert np.array_equal(got["S"] != 0, ref["S"] != 0)
+    N = pr.n_points
+    sk = np.nonzero(ref["skipped"])[0]
+    assert np.all(got["corrections"][:3 * N].reshape(N, 3)[sk] == 0.0)
