@@ -32,9 +32,10 @@ WORKLOADS = {
     "c2": (50, 10_000, 50, "synthetic circle-grid-shaped BA: 50 cameras x 10k points, every point in every frame (configs[1])"),
     "c5": (10_000, 5_000_000, 10, "synthetic city-scale BA: 10,000 cameras x 5M points x 50M observations, PCG solve (configs[4])"),
     "tiny": (40, 4000, 8, "tiny ring scene (smoke)"),
+    "c3s": (1000, 50_000, 10, "profiling aid: the 1,000-camera reduced system of configs[2] with 50k points"),
 }
 # bounded CPU sample of each workload (same generator, fewer cameras/points so the oracle finishes in ~10-30 s)
-CPU_SAMPLES = {"c3": (100, 100_000, 10), "c2": (50, 2_000, 50), "c5": (100, 100_000, 10), "tiny": (40, 4000, 8)}
+CPU_SAMPLES = {"c3": (100, 100_000, 10), "c2": (50, 2_000, 50), "c5": (100, 100_000, 10), "tiny": (40, 4000, 8), "c3s": (100, 100_000, 10)}
 METRIC = "BA reprojection residuals/sec through full LM iterations"
 UNIT = "residuals/s"
 

@@ -4,263 +4,400 @@
 // damped Gauss-Newton Hessian), so LL^T is the appropriate factorisation.  FP64 tensor work on Blackwell is DMMA:
 // mma.sync.aligned.m8n8k4.f64 (tcgen05.mma has no f64 kind, TMEM accumulators are not available for doubles).
 //
-// Right-looking blocked algorithm, panel width NB = 64, column-major lower triangle, leading dimension ld (multiple of 2):
-//   k_potrf64 : diagonal 64x64 tile in shared memory (one CTA) + forward substitution of the matching rhs slice
-//   k_trsm64  : panel rows below the tile,  P <- P * L_kk^-T  in shared memory, fused rhs update  b_rows -= P*y_k
-//   k_syrk    : trailing update  C -= P*P^T  on 128x128 lower tiles, K = 64, DMMA with register tiles of 32x64 per warp
-//   k_back64  : backward substitution L^T x = y, one launch per block column (right-looking on row panels)
+// Right-looking blocked algorithm on the column-major lower triangle (leading dimension ld, a multiple of 8):
+//   panel width PB = 256, factored as four 64-column sub-panels:
+//     k_potrf64_inv : 64x64 diagonal block -> L_kk in place and L_kk^-1 into dinv[kb] (kept for the substitutions)
+//     k_panel_solve : rows below, X = A * L_kk^-T as a small GEMM against the inverted block (no serial TRSM)
+//     k_syrk_dmma   : C -= X*X^T restricted to the rest of the current 256-panel (K = 64)
+//   then ONE trailing update per panel with K = 256:
+//     k_syrk_dmma   : 128x128 tiles, 3-stage cp.async pipeline over K chunks of 16, DMMA m8n8k4 with 32x64 register
+//                     tiles per warp.  4x less trailing-matrix traffic than a 64-wide right-looking sweep.
+//   k_trsv_coop     : forward / backward substitution as ONE cooperative kernel: per 64-block a GEMV with the stored
+//                     L_kk^-1, a grid-wide panel GEMV for the rows below / above, one grid.sync per block.
+#include <cooperative_groups.h>
 #include <math.h>
 #include "kernels.h"
 
+namespace cg = cooperative_groups;
+
 namespace srk {
 
-constexpr int NB = 64;
+constexpr int NB = 64;     // diagonal block / sub-panel width
+constexpr int PB = 256;    // panel width of the trailing update
 
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_potrf64(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ b, int* __restrict__ info) {
-    __shared__ double T[NB][NB + 1];  // T[c][r]
-    __shared__ double y[NB];
+// 64x64 diagonal block, register resident.  Thread (r = tid & 63, grp = tid >> 6) keeps row r of the block for the columns
+// c == grp (mod 4) in 16 registers, and the same slice of row r of W, which starts as the identity and receives the same
+// row operations: after the 64 elimination steps T holds L and W holds L^-1 (the row operations multiply by L^-1).
+// Per step the owners publish column j of T and row j of W through shared memory (double buffered, one barrier).
+// info: 1-based index of the first non-positive pivot.
+__global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ dinv, int* __restrict__ info,
+                                                     unsigned char* __restrict__ F, int nblk) {
+    __shared__ double col[2][NB];    // column j of T (unscaled), indexed by row
+    __shared__ double wrow[2][NB];   // row j of W (unscaled), indexed by column
     const int nb = min(NB, n - k0);
     const int tid = threadIdx.x;
-    for (int e = tid; e < NB * NB; e += 256) {
-        int c = e / NB, r = e % NB;
-        T[c][r] = (r < nb && c < nb && r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : 0.0;
+    const int r = tid & 63, grp = tid >> 6;
+    double t[16], w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = grp + 4 * i;
+        t[i] = (r < nb && c < nb && r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : ((r == c) ? 1.0 : 0.0);
+        w[i] = (r == c) ? 1.0 : 0.0;
     }
-    if (tid < NB) y[tid] = (b != nullptr && tid < nb) ? b[k0 + tid] : 0.0;
-    __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-        double d = T[j][j];
-        if (tid == 0 && !(d > 0.0) && atomicCAS(info, 0, k0 + j + 1) == 0) {}
-        double sd = sqrt(d);
-        __syncthreads();
-        // scale column j
-        if (tid >= j && tid < nb) T[j][tid] = (tid == j) ? sd : T[j][tid] / sd;
-        __syncthreads();
-        // rank-1 update of the trailing lower part: T[c][r] -= T[j][r]*T[j][c], j < c <= r
-        int m = nb - j - 1;
-        for (int e = tid; e < m * m; e += 256) {
-            int c = j + 1 + e / m, r = j + 1 + e % m;
-            if (r >= c) T[c][r] -= T[j][r] * T[j][c];
+    if (tid == 0) F[(size_t)(k0 / NB) * nblk + k0 / NB] = 1;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+        const int buf = j & 1;
+        if (grp == (j & 3)) col[buf][r] = t[j >> 2];             // T(r, j): column j lives in the threads of group j mod 4
+        if (r == j) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) wrow[buf][grp + 4 * i] = w[i];   // W(j, :)
         }
-        // no barrier needed here: the next iteration's first barrier orders these writes before they are read
         __syncthreads();
+        const double d = col[buf][j];
+        if (tid == 0 && !(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1);
+        const double rs = rsqrt(d);
+        const double lr = col[buf][r] * rs;                       // L(r, j) for r > j
+        if (r > j) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int c = grp + 4 * i;
+                if (c > j) { if (c <= r) t[i] -= lr * (col[buf][c] * rs); }
+                else w[i] -= lr * (wrow[buf][c] * rs);
+            }
+            if (grp == (j & 3)) t[j >> 2] = lr;
+        } else if (r == j) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] *= rs;
+            if (grp == (j & 3)) t[j >> 2] = d * rs;               // sqrt(d)
+        }
     }
-    // forward substitution  L y = b_k  (column oriented)
-    for (int j = 0; j < nb; ++j) {
-        if (tid == 0) y[j] = y[j] / T[j][j];
-        __syncthreads();
-        if (tid > j && tid < nb) y[tid] -= T[j][tid] * y[j];
-        __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = grp + 4 * i;
+        if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = t[i];
+        dinv[(size_t)c * NB + r] = (r >= c) ? w[i] : 0.0;         // column-major 64x64: Linv(r, c)
     }
-    for (int e = tid; e < NB * NB; e += 256) {
-        int c = e / NB, r = e % NB;
-        if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = T[c][r];
-    }
-    if (b != nullptr && tid < nb) b[k0 + tid] = y[tid];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Rows [k0+NB, n) of the panel: 128 rows per CTA, one thread per row.  smem: L_kk (64x64) and the row tile (64 x 128).
-constexpr int TR = 128;
-__global__ void __launch_bounds__(TR) k_trsm64(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ b) {
+// Rows below the diagonal block: X = A * L_kk^-T, i.e. X(r,c) = sum_{m<=c} A(r,m) * Linv(c,m).  128 rows per CTA.
+constexpr int PS_ROWS = 128;
+__global__ void __launch_bounds__(256) k_panel_solve(int n, int k0, double* __restrict__ A, int64_t ld, const double* __restrict__ dinv,
+                                                     unsigned char* __restrict__ F, int nblk) {
     extern __shared__ double sm[];
-    double* L = sm;                 // L[c*NB + r]  (column-major tile)
-    double* Xt = sm + NB * NB;      // Xt[c*TR + row]
-    double* y = Xt + NB * TR;       // y[NB]
+    double* sLi = sm;                    // sLi[m*NB + c] = Linv(c, m): for a fixed m the 32 columns of a thread are contiguous
+    double* sA = sm + NB * NB;           // sA[m*PS_ROWS + r]
     const int tid = threadIdx.x;
-    const int r0 = k0 + NB + blockIdx.x * TR;
-    const int rows = min(TR, n - r0);
-    for (int e = tid; e < NB * NB; e += TR) {
-        int c = e / NB, r = e % NB;
-        L[e] = (r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : 0.0;
+    const int r0 = k0 + NB + blockIdx.x * PS_ROWS;
+    for (int e = tid; e < NB * NB; e += 256) { int m = e >> 6, cc = e & 63; sLi[m * NB + cc] = dinv[(size_t)m * NB + cc]; }
+    // 64x64 block structure of L: F[kb][rb] != 0 iff the block (rows rb, columns kb) holds a non-zero.  An all-zero input tile
+    // stays zero (X = 0 * Linv^T), so the CTA records that and leaves; the trailing update and the substitutions skip it.
+    int nz_lo = 0, nz_hi = 0;
+    for (int e = tid; e < NB * PS_ROWS; e += 256) {
+        int m = e / PS_ROWS, r = e % PS_ROWS;
+        double v = (r0 + r < n) ? A[(size_t)(k0 + m) * ld + r0 + r] : 0.0;
+        sA[e] = v;
+        if (v != 0.0) { if (r < NB) nz_lo = 1; else nz_hi = 1; }
     }
-    if (tid < NB) y[tid] = b != nullptr ? b[k0 + tid] : 0.0;
-    for (int c = 0; c < NB; ++c) Xt[c * TR + tid] = tid < rows ? A[(size_t)(k0 + c) * ld + r0 + tid] : 0.0;
-    __syncthreads();
-    double acc = 0.0;
-    for (int c = 0; c < NB; ++c) {
-        double s = Xt[c * TR + tid];
-#pragma unroll 8
-        for (int m = 0; m < c; ++m) s -= Xt[m * TR + tid] * L[m * NB + c];   // L(c,m)
-        s = s / L[c * NB + c];
-        Xt[c * TR + tid] = s;
-        acc += s * y[c];
+    nz_lo = __syncthreads_or(nz_lo);
+    nz_hi = __syncthreads_or(nz_hi);
+    if (tid == 0) {
+        const int rb = r0 / NB;
+        F[(size_t)(k0 / NB) * nblk + rb] = (unsigned char)nz_lo;
+        if (rb + 1 < nblk) F[(size_t)(k0 / NB) * nblk + rb + 1] = (unsigned char)nz_hi;
     }
-    if (tid < rows) {
-        for (int c = 0; c < NB; ++c) A[(size_t)(k0 + c) * ld + r0 + tid] = Xt[c * TR + tid];
-        if (b != nullptr) b[r0 + tid] -= acc;
+    if (!(nz_lo | nz_hi)) return;
+    const int r = tid & (PS_ROWS - 1), cbase = (tid >> 7) * 32;
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    for (int m = 0; m < cbase + 32; ++m) {
+        const double a = sA[m * PS_ROWS + r];
+        const double* li = sLi + m * NB + cbase;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += a * li[i];   // Linv(c, m) is zero for m > c
+    }
+    if (r0 + r < n) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) A[(size_t)(k0 + cbase + i) * ld + r0 + r] = acc[i];
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Trailing update C -= P*P^T on lower 128x128 tiles; P = A[k0+NB.., k0..k0+63] (already solved by k_trsm64).
-constexpr int TM = 128;
-constexpr int SLD = TM + 4;  // padded row stride of the [k][row] shared tiles: conflict-free DMMA fragment loads
+// C(origin.., origin..col_end) -= P * P^T on the lower triangle, P = A[:, kcol0 .. kcol0+K).
+// Persistent CTAs over a work list that every CTA derives from F (the 64x64 block structure of the panel): only pairs of
+// NON-ZERO row tiles are visited, so a banded / block-sparse reduced camera system costs what its fill costs while a dense
+// one runs every tile.  Two instantiations share the code: 128x128 tiles (8 warps of 32x64, best DMMA efficiency) when there
+// are at least kHeavyPairs tile pairs, 64x64 tiles (4 warps of 32x32, four times the CTAs per unit of work) otherwise, so
+// that a short work list is not bound by the DMMA throughput of a handful of SMs.  Both are launched; the one whose regime
+// does not apply returns at once.
+constexpr int KC = 16;           // K chunk per pipeline stage
+constexpr int STAGES = 3;
+constexpr int kHeavyPairs = 148;
+constexpr int kMaxRowBlocks = 512;   // n <= 32768
 
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__global__ void __launch_bounds__(256, 1) k_syrk(int n, int k0, double* __restrict__ A, int64_t ld) {
+template <int TILE>
+struct SyrkCfg {
+    static constexpr int kWarpsR = TILE / 32;                    // warps along rows (32 rows each)
+    static constexpr int kNJ = TILE == 128 ? 8 : 4;              // 8-column fragments per warp
+    static constexpr int kWarpsC = TILE / (kNJ * 8);
+    static constexpr int kThreads = kWarpsR * kWarpsC * 32;
+    static constexpr int kSLD = TILE + 4;                        // padded [k][row] stride: conflict-free fragment loads, 16-B aligned rows
+    static constexpr size_t kSmem = sizeof(double) * (2 * STAGES * KC * kSLD) + sizeof(short) * kMaxRowBlocks;
+};
+
+template <int TILE>
+__global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads) k_syrk_dmma(int n, double* __restrict__ A, int64_t ld, int kcol0, int K, int origin, int col_end,
+                                                                      const unsigned char* __restrict__ F, int nblk) {
+    using Cfg = SyrkCfg<TILE>;
+    constexpr int SLD = Cfg::kSLD, NT = Cfg::kThreads, NJ = Cfg::kNJ;
     extern __shared__ double sm[];
-    double* sA = sm;               // [NB][SLD]  rows of the tile-row block
-    double* sB = sm + NB * SLD;    // [NB][SLD]  rows of the tile-column block
-    // decode lower-triangular tile index
-    const int t0 = k0 + NB;
-    int bt = blockIdx.x;
-    int ti = (int)((sqrtf(8.0f * (float)bt + 1.0f) - 1.0f) * 0.5f);
-    while (ti * (ti + 1) / 2 > bt) --ti;
-    while ((ti + 1) * (ti + 2) / 2 <= bt) ++ti;
-    const int tj = bt - ti * (ti + 1) / 2;
-    const int i0 = t0 + ti * TM, j0 = t0 + tj * TM;
+    double* sA = sm;                              // [STAGES][KC][SLD]
+    double* sB = sm + STAGES * KC * SLD;          // [STAGES][KC][SLD]
+    short* nzt = (short*)(sm + 2 * STAGES * KC * SLD);
+    __shared__ int s_m, s_m128;
     const int tid = threadIdx.x;
-    // load the two 128x64 panel tiles (coalesced along rows)
-    for (int e = tid; e < NB * TM; e += 256) {
-        int k = e / TM, r = e % TM;
-        int gi = i0 + r, gj = j0 + r;
-        sA[k * SLD + r] = gi < n ? A[(size_t)(k0 + k) * ld + gi] : 0.0;
-        sB[k * SLD + r] = gj < n ? A[(size_t)(k0 + k) * ld + gj] : 0.0;
+    const int warp = tid >> 5, lane = tid & 31;
+
+    // ---- work list: non-zero row tiles of this panel (tile index relative to origin), identical in every CTA
+    if (warp == 0) {
+        const int kb0 = kcol0 / NB, kb1 = (kcol0 + K) / NB;
+        const int ntile = (n - origin + TILE - 1) / TILE;
+        const int ntile128 = (n - origin + 127) / 128;
+        int m = 0, m128 = 0;
+        for (int base = 0; base < max(ntile, ntile128); base += 32) {
+            const int t = base + lane;
+            int nz = 0, nz128 = 0;
+            if (t < ntile) {
+                const int rb0 = (origin + t * TILE) / NB;
+                for (int rb = rb0; rb < rb0 + TILE / NB && rb < nblk; ++rb)
+                    for (int kb = kb0; kb < kb1; ++kb) nz |= F[(size_t)kb * nblk + rb];
+            }
+            if (TILE == 128) nz128 = nz;
+            else if (t < ntile128) {
+                const int rb0 = (origin + t * 128) / NB;
+                for (int rb = rb0; rb < rb0 + 2 && rb < nblk; ++rb)
+                    for (int kb = kb0; kb < kb1; ++kb) nz128 |= F[(size_t)kb * nblk + rb];
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, nz != 0);
+            if (nz) nzt[m + __popc(bal & ((1u << lane) - 1))] = (short)t;
+            m += __popc(bal);
+            m128 += __popc(__ballot_sync(0xffffffffu, nz128 != 0));
+        }
+        if (lane == 0) { s_m = m; s_m128 = m128; }
     }
     __syncthreads();
-    const int warp = tid >> 5, lane = tid & 31;
-    const int wr = (warp & 3) * 32;   // warp row offset in the tile (4 warps along rows)
-    const int wc = (warp >> 2) * 64;  // warp col offset (2 warps along cols)
+    const int m = s_m;
+    const bool heavy = s_m128 * (s_m128 + 1) / 2 >= kHeavyPairs;
+    if (heavy != (TILE == 128)) return;
+    const int npairs = m * (m + 1) / 2;
+    const int nk = K / KC;
+    const int wr = (warp % Cfg::kWarpsR) * 32;
+    const int wc = (warp / Cfg::kWarpsR) * (NJ * 8);
     const int g = lane >> 2, tg = lane & 3;
-    double acc[4][8][2];
+
+    for (int p = blockIdx.x; p < npairs; p += gridDim.x) {
+        int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+        while (a * (a + 1) / 2 > p) --a;
+        while ((a + 1) * (a + 2) / 2 <= p) ++a;
+        const int bb = p - a * (a + 1) / 2;
+        const int i0 = origin + (int)nzt[a] * TILE, j0 = origin + (int)nzt[bb] * TILE;
+        if (j0 >= col_end) continue;
+
+        auto load_chunk = [&](int stage, int kc) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-#pragma unroll 2
-    for (int ks = 0; ks < NB; ks += 4) {
-        double a[4], bfr[8];
-        const double* pa = sA + (ks + tg) * SLD + wr + g;
-        const double* pb = sB + (ks + tg) * SLD + wc + g;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = pa[i * 8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bfr[j] = pb[j * 8];
+            for (int q = 0; q < 4; ++q) {
+                const int v = tid + NT * q;            // KC * TILE / 2 16-byte vectors per operand tile
+                const int k = v / (TILE / 2), rp = (v % (TILE / 2)) * 2;
+                const size_t colo = (size_t)(kcol0 + kc * KC + k) * ld;
+                {
+                    const int row = i0 + rp;
+                    int bytes = (n - row) * 8; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+                    cp_async16(sA + (stage * KC + k) * SLD + rp, A + colo + (bytes > 0 ? row : 0), bytes);
+                }
+                {
+                    const int row = j0 + rp;
+                    int bytes = (n - row) * 8; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+                    cp_async16(sB + (stage * KC + k) * SLD + rp, A + colo + (bytes > 0 ? row : 0), bytes);
+                }
+            }
+        };
+        load_chunk(0, 0); cp_async_commit();
+        if (nk > 1) load_chunk(1, 1);
+        cp_async_commit();
+
+        double acc[4][NJ][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], bfr[j]);
-    }
-    // epilogue: C(row, col) -= acc, lower part only
+            for (int j = 0; j < NJ; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+        for (int kc = 0; kc < nk; ++kc) {
+            cp_async_wait<1>();
+            __syncthreads();
+            if (kc + 2 < nk) load_chunk((kc + 2) % STAGES, kc + 2);
+            cp_async_commit();
+            const double* cA = sA + (kc % STAGES) * KC * SLD;
+            const double* cB = sB + (kc % STAGES) * KC * SLD;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+            for (int ks = 0; ks < KC; ks += 4) {
+                double af[4], bf[NJ];
+                const double* pa = cA + (ks + tg) * SLD + wr + g;
+                const double* pb = cB + (ks + tg) * SLD + wc + g;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int row = i0 + wr + i * 8 + g;
-            int col = j0 + wc + j * 8 + tg * 2;
-            if (row < n) {
-                if (col < n && row >= col) A[(size_t)col * ld + row] -= acc[i][j][0];
-                if (col + 1 < n && row >= col + 1) A[(size_t)(col + 1) * ld + row] -= acc[i][j][1];
+                for (int i = 0; i < 4; ++i) af[i] = pa[i * 8];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) bf[j] = pb[j * 8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
         }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Backward substitution, block column kb (descending).  x lives in b.  grid.x = kb+1 CTAs:
-//   CTA j < kb : b_j -= L(kb-block rows, j-block cols)^T * x_kb         (x_kb final from the previous launch)
-//   ... except that x_kb itself must first be produced: launch order is  solve_diag(kb) ; update(j<kb) — two tiny
-//   kernels would double the launch count, so CTA j == kb-1 of launch kb also solves the diagonal block kb-1 after its
-//   own update, and launch kb == last block starts with a diagonal-only launch.
-__global__ void __launch_bounds__(128) k_back64(int n, int kb, int first, const double* __restrict__ A, int64_t ld, double* __restrict__ b) {
-    __shared__ double xk[NB];
-    __shared__ double yj[NB];
-    __shared__ double T[NB][NB + 1];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int j = blockIdx.x;  // target block column
-    const int k0 = kb * NB;
-    if (first) {
-        // diagonal solve of the last block only
-        const int nb = min(NB, n - k0);
-        for (int e = tid; e < NB * NB; e += 128) { int c = e / NB, r = e % NB; T[c][r] = (r < nb && c < nb && r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : 0.0; }
-        if (tid < NB) yj[tid] = tid < nb ? b[k0 + tid] : 0.0;
-        __syncthreads();
-        for (int c = nb - 1; c >= 0; --c) {   // L^T x = y : x_c = (y_c - sum_{r>c} L(r,c) x_r) / L(c,c)
-            if (tid == 0) yj[c] = yj[c] / T[c][c];
-            __syncthreads();
-            if (tid < c) yj[tid] -= T[tid][c] * yj[c];
-            __syncthreads();
-        }
-        if (tid < nb) b[k0 + tid] = yj[tid];
-        return;
-    }
-    const int nbk = min(NB, n - k0);
-    const int j0 = j * NB;
-    if (tid < NB) { xk[tid] = tid < nbk ? b[k0 + tid] : 0.0; yj[tid] = b[j0 + tid]; }
-    __syncthreads();
-    // y_j[c] -= sum_r L(k0+r, j0+c) * x_k[r] : each warp handles 16 columns, lanes over rows
-    for (int cc = 0; cc < 16; ++cc) {
-        int c = warp * 16 + cc;
-        const double* col = A + (size_t)(j0 + c) * ld + k0;
-        double s = 0.0;
-        for (int r = lane; r < nbk; r += 32) s += col[r] * xk[r];
+        cp_async_wait<0>();
+        __syncthreads();   // the stage buffers are free for the next tile
+        // epilogue: C(row, col) -= acc on the lower triangle inside [origin, col_end)
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) s += __shfl_xor_sync(0xffffffffu, s, sft);
-        if (lane == 0) yj[c] -= s;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int row = i0 + wr + i * 8 + g;
+                const int col = j0 + wc + j * 8 + tg * 2;
+                if (row < n) {
+                    if (col < col_end && row >= col) A[(size_t)col * ld + row] -= acc[i][j][0];
+                    if (col + 1 < col_end && row >= col + 1) A[(size_t)(col + 1) * ld + row] -= acc[i][j][1];
+                }
+            }
     }
-    __syncthreads();
-    if (j == kb - 1) {
-        for (int e = tid; e < NB * NB; e += 128) { int c = e / NB, r = e % NB; T[c][r] = (r >= c) ? A[(size_t)(j0 + c) * ld + j0 + r] : 0.0; }
-        __syncthreads();
-        for (int c = NB - 1; c >= 0; --c) {
-            if (tid == 0) yj[c] = yj[c] / T[c][c];
-            __syncthreads();
-            if (tid < c) yj[tid] -= T[tid][c] * yj[c];
-            __syncthreads();
-        }
-    }
-    if (tid < NB) b[j0 + tid] = yj[tid];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Forward substitution L y = b with an existing factor (used by the refinement steps), block column kb ascending:
-//   first launch: diagonal solve of block 0.  Launch kb: CTA j (j = kb+1 .. nblk-1) applies  b_j -= L(j,kb) * y_kb ;
-//   the CTA of block kb+1 then owns a complete right-hand side and solves its diagonal block.
-__global__ void __launch_bounds__(128) k_fwd64(int n, int kb, int first, const double* __restrict__ A, int64_t ld, double* __restrict__ b) {
+// Triangular solves with the stored inverses of the diagonal blocks, ONE cooperative launch and no grid-wide barrier.
+//   forward  (L y = b):   blocks in ascending order:  y_k = Linv_k b_k ;   b_j -= L(j,k) y_k   for j > k
+//   backward (L^T x = y): blocks in descending order: x_k = Linv_k^T b_k ; b_j -= L(k,j)^T x_k for j < k
+// Row block j of the right-hand side is owned by CTA (order(j) mod G): every update of b_j happens inside one CTA in
+// program order.  The owner of block k turns b_k into the solved y_k, publishes it (ybuf + release flag = epoch) and the
+// other CTAs pick it up with an acquire spin only when they own a non-zero tile in that block column (F, the 64x64 block
+// structure of L).  All CTAs are co-resident (cooperative launch), so the spins cannot deadlock.
+__device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+
+constexpr int kTrsvOwn = 2;          // owned row blocks per CTA whose operands are kept in shared memory
+constexpr int kTrsvFCacheMax = 65536;  // bytes of F cached in shared memory (n <= 16384)
+
+__global__ void __launch_bounds__(256) k_trsv_flags(int n, const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv, double* b,
+                                                    double* ybuf, int* flags, const unsigned char* __restrict__ F, int epoch, int backward, int cacheF) {
+    extern __shared__ double smt[];
+    double* sDi = smt;                          // [kTrsvOwn][64*64]  Linv of my blocks, column-major
+    double* sLt = smt + kTrsvOwn * NB * NB;     // [kTrsvOwn][64*64]  the sub-diagonal tile next to each of my blocks, column-major
+    unsigned char* sF = (unsigned char*)(smt + 2 * kTrsvOwn * NB * NB);
+    __shared__ double bown[kTrsvOwn][NB];
     __shared__ double yk[NB];
-    __shared__ double yj[NB];
-    __shared__ double part[2][NB];
-    __shared__ double T[NB][NB + 1];
+    __shared__ double part[4][NB];
     const int tid = threadIdx.x;
-    auto diag_solve = [&](int j0) {
-        const int nb = min(NB, n - j0);
-        for (int e = tid; e < NB * NB; e += 128) { int c = e / NB, r = e % NB; T[c][r] = (r < nb && c < nb && r >= c) ? A[(size_t)(j0 + c) * ld + j0 + r] : 0.0; }
-        __syncthreads();
-        for (int c = 0; c < nb; ++c) {
-            if (tid == 0) yj[c] = yj[c] / T[c][c];
+    const int nblk = (n + NB - 1) / NB;
+    const int G = gridDim.x, me = blockIdx.x;
+    const int r = tid & 63, q = tid >> 6;
+    const unsigned char* Fp = F;
+    if (cacheF) {
+        for (int e = tid; e < nblk * nblk; e += 256) sF[e] = F[e];
+        Fp = sF;
+    }
+    // ---- prefetch: everything on the critical path of my blocks lives in shared memory before the chain reaches me
+    for (int o = 0; o < kTrsvOwn; ++o) {
+        const int so = me + o * G;
+        if (so >= nblk) break;
+        const int kb = backward ? nblk - 1 - so : so;
+        const double* Di = dinv + (size_t)kb * NB * NB;
+        for (int e = tid; e < NB * NB; e += 256) sDi[o * NB * NB + e] = Di[e];
+        if (tid < NB) bown[o][tid] = (kb * NB + tid < n) ? b[kb * NB + tid] : 0.0;
+        if (so >= 1) {
+            const int lo = backward ? kb : kb - 1;          // the tile L(rows lo+1, cols lo)
+            for (int e = tid; e < NB * NB; e += 256) {
+                const int c = e >> 6, rr = e & 63;
+                const int row = (lo + 1) * NB + rr, colg = lo * NB + c;
+                sLt[o * NB * NB + e] = (row < n) ? L[(size_t)colg * ld + row] : 0.0;
+            }
+        }
+    }
+    __syncthreads();
+
+    for (int s = 0; s < nblk; ++s) {
+        const int kb = backward ? nblk - 1 - s : s;
+        const int k0 = kb * NB;
+        const int nbk = min(NB, n - k0);
+        const bool owner = (s % G) == me;
+        int s2_first = s + ((me - s) % G + G) % G;
+        if (s2_first == s) s2_first += G;
+        bool any_tile = false;
+        for (int s2 = s2_first; s2 < nblk; s2 += G) {
+            const int jb = backward ? nblk - 1 - s2 : s2;
+            any_tile |= (backward ? Fp[(size_t)jb * nblk + kb] : Fp[(size_t)kb * nblk + jb]) != 0;
+        }
+        if (owner) {
+            const int o = (s - me) / G;
+            const double* Di = o < kTrsvOwn ? sDi + o * NB * NB : dinv + (size_t)kb * NB * NB;   // Di[c*NB + r] = Linv(r, c)
+            if (o >= kTrsvOwn) {
+                if (tid < NB) yk[tid] = tid < nbk ? __ldcg(b + k0 + tid) : 0.0;
+                __syncthreads();
+            }
+            const double* bk = o < kTrsvOwn ? bown[o] : yk;
+            double sacc = 0.0;
+            if (!backward) { for (int c = q; c <= r; c += 4) sacc += Di[(size_t)c * NB + r] * bk[c]; }                  // y_r = sum_c Linv(r,c) b_c
+            else { for (int c = r + ((q - r) & 3); c < NB; c += 4) sacc += Di[(size_t)r * NB + c] * bk[c]; }           // x_r = sum_c Linv(c,r) b_c
+            part[q][r] = sacc;
             __syncthreads();
-            if (tid > c && tid < nb) yj[tid] -= T[c][tid] * yj[c];
+            if (tid < NB) {
+                const double v = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+                yk[tid] = v;
+                if (tid < nbk) { __stcg(ybuf + k0 + tid, v); __stcg(b + k0 + tid, v); }
+            }
+            __syncthreads();                       // orders the 64 stores before the release below (cumulativity through the barrier)
+            if (tid == 0) st_release(flags + s, epoch);
+        } else {
+            if (!any_tile) continue;   // uniform across the CTA
+            if (tid == 0) { while (ld_acquire(flags + s) != epoch) {} }
+            __syncthreads();
+            if (tid < NB) yk[tid] = tid < nbk ? __ldcg(ybuf + k0 + tid) : 0.0;
             __syncthreads();
         }
-        if (tid < nb) b[j0 + tid] = yj[tid];
-    };
-    if (first) {
-        if (tid < NB) yj[tid] = tid < n ? b[tid] : 0.0;
-        __syncthreads();
-        diag_solve(0);
-        return;
+        for (int s2 = s2_first; s2 < nblk; s2 += G) {
+            const int jb = backward ? nblk - 1 - s2 : s2;
+            if ((backward ? Fp[(size_t)jb * nblk + kb] : Fp[(size_t)kb * nblk + jb]) == 0) continue;
+            const int o2 = (s2 - me) / G;
+            const int j0 = jb * NB;
+            const int nbj = min(NB, n - j0);
+            double sacc = 0.0;
+            if (s2 == s + 1 && o2 < kTrsvOwn) {    // the sub-diagonal tile, prefetched: sLt[c*64 + rr] = L(lo+1 rows, lo cols)
+                const double* T = sLt + o2 * NB * NB;
+                if (!backward) { for (int c = q; c < NB; c += 4) sacc += T[c * NB + r] * yk[c]; }        // b_j[r] -= sum_c L(j0+r, k0+c) y_c
+                else { for (int c = q; c < NB; c += 4) sacc += T[r * NB + c] * yk[c]; }                  // b_j[r] -= sum_c L(k0+c, j0+r) x_c
+            } else if (r < nbj) {
+                if (!backward) { for (int c = q; c < nbk; c += 4) sacc += L[(size_t)(k0 + c) * ld + j0 + r] * yk[c]; }
+                else { for (int c = q; c < nbk; c += 4) sacc += L[(size_t)(j0 + r) * ld + k0 + c] * yk[c]; }
+            }
+            part[q][r] = sacc;
+            __syncthreads();
+            if (tid < nbj) {
+                const double dlt = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+                if (o2 < kTrsvOwn) bown[o2][tid] -= dlt;
+                else __stcg(b + j0 + tid, __ldcg(b + j0 + tid) - dlt);
+            }
+            __syncthreads();
+        }
     }
-    const int k0 = kb * NB;
-    const int j = kb + 1 + blockIdx.x;
-    const int j0 = j * NB;
-    const int nbj = min(NB, n - j0);
-    if (tid < NB) { yk[tid] = b[k0 + tid]; yj[tid] = tid < nbj ? b[j0 + tid] : 0.0; }
-    __syncthreads();
-    {
-        const int r = tid & (NB - 1), half = tid >> 6;
-        double s = 0.0;
-        if (r < nbj)
-            for (int c = half; c < NB; c += 2) s += A[(size_t)(k0 + c) * ld + j0 + r] * yk[c];
-        part[half][r] = s;
-    }
-    __syncthreads();
-    if (tid < NB) yj[tid] -= part[0][tid] + part[1][tid];
-    __syncthreads();
-    if (j == kb + 1) diag_solve(j0);
-    else if (tid < nbj) b[j0 + tid] = yj[tid];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -322,47 +459,92 @@ __global__ void k_axpy1(int n, const double* __restrict__ d, double* __restrict_
     if (i < n) x[i] += d[i];
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr size_t kPanelSolveSmem = sizeof(double) * (NB * NB + NB * PS_ROWS);
+
+static int g_coop_blocks = 0;
+static int g_sms = 148;
+static void launch_syrk(cudaStream_t st, int n, double* A, int64_t ld, int kcol0, int K, int origin, int col_end, const unsigned char* F, int nblk);
+static int g_epoch = 0;
 static void set_attrs_once() {
     static bool attr_set = false;
     if (attr_set) return;
-    cudaFuncSetAttribute(k_trsm64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (NB * NB + NB * TR + NB)));
-    cudaFuncSetAttribute(k_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * (2 * NB * SLD)));
+    cudaFuncSetAttribute(k_panel_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSolveSmem);
+    cudaFuncSetAttribute(k_syrk_dmma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<128>::kSmem);
+    cudaFuncSetAttribute(k_syrk_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<64>::kSmem);
+    g_sms = 148; { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, d); }
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_trsv_flags, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * kTrsvOwn * NB * NB + kTrsvFCacheMax));
+    g_coop_blocks = sms * (per_sm < 1 ? 1 : 1);   // one CTA per SM: fewer spinners, same bandwidth
     attr_set = true;
 }
 
-int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* b, int* info_dev) {
+// Workspace layout (doubles): [dinv: nblk*64*64][ybuf: nblk*64][flags: nblk ints, padded][F: nblk*nblk bytes, padded]
+static inline int chol_nblk(int n) { return (n + NB - 1) / NB; }
+size_t dense_cholesky_dinv_doubles(int n) {
+    const size_t nblk = (size_t)chol_nblk(n);
+    return nblk * NB * NB + nblk * NB + (nblk + 1) / 2 + 8 + (nblk * nblk + 7) / 8 + 8;
+}
+static inline double* ws_ybuf(double* ws, int n) { return ws + (size_t)chol_nblk(n) * NB * NB; }
+static inline int* ws_flags(double* ws, int n) { return (int*)(ws_ybuf(ws, n) + (size_t)chol_nblk(n) * NB); }
+static inline unsigned char* ws_F(double* ws, int n) { return (unsigned char*)(ws_ybuf(ws, n) + (size_t)chol_nblk(n) * NB + (chol_nblk(n) + 1) / 2 + 8); }
+
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
     set_attrs_once();
-    const size_t trsm_smem = sizeof(double) * (NB * NB + NB * TR + NB);
-    const size_t syrk_smem = sizeof(double) * (2 * NB * SLD);
     int64_t launches = 0;
+    const int nblk = chol_nblk(n);
+    unsigned char* F = ws_F(ws, n);
     cudaMemsetAsync(info_dev, 0, sizeof(int), st);
-    const int nblk = (n + NB - 1) / NB;
-    for (int kb = 0; kb < nblk; ++kb) {
-        const int k0 = kb * NB;
-        k_potrf64<<<1, 256, 0, st>>>(n, k0, A, ld, b, info_dev); ++launches;
-        const int below = n - (k0 + NB);
-        if (below > 0) {
-            k_trsm64<<<(below + TR - 1) / TR, TR, trsm_smem, st>>>(n, k0, A, ld, b); ++launches;
-            const int T = (below + TM - 1) / TM;
-            k_syrk<<<T * (T + 1) / 2, 256, syrk_smem, st>>>(n, k0, A, ld); ++launches;
+    cudaMemsetAsync(ws_flags(ws, n), 0, sizeof(int) * nblk, st);
+    cudaMemsetAsync(F, 0, (size_t)nblk * nblk, st);
+    g_epoch = 0;
+    for (int p0 = 0; p0 < n; p0 += PB) {
+        const int pend = min(n, p0 + PB);
+        for (int k0 = p0; k0 < pend; k0 += NB) {
+            double* di = ws + (size_t)(k0 / NB) * NB * NB;
+            k_potrf64_inv<<<1, 256, 0, st>>>(n, k0, A, ld, di, info_dev, F, nblk); ++launches;
+            const int below = n - (k0 + NB);
+            if (below <= 0) continue;
+            k_panel_solve<<<(below + PS_ROWS - 1) / PS_ROWS, 256, kPanelSolveSmem, st>>>(n, k0, A, ld, di, F, nblk); ++launches;
+            const int origin = k0 + NB;
+            if (origin < pend) {   // rest of the current panel, K = 64
+                launch_syrk(st, n, A, ld, k0, NB, origin, pend, F, nblk); launches += 2;
+            }
+        }
+        if (pend < n) {            // trailing matrix, K = panel width (pend - p0 == PB whenever pend < n)
+            launch_syrk(st, n, A, ld, p0, pend - p0, pend, n, F, nblk); launches += 2;
         }
     }
     return launches;
 }
-int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* b) {
-    const int nblk = (n + NB - 1) / NB;
-    int64_t launches = 0;
-    k_fwd64<<<1, 128, 0, st>>>(n, 0, 1, L, ld, b); ++launches;
-    for (int kb = 0; kb + 1 < nblk; ++kb) { k_fwd64<<<nblk - kb - 1, 128, 0, st>>>(n, kb, 0, L, ld, b); ++launches; }
-    return launches;
+
+static void launch_syrk(cudaStream_t st, int n, double* A, int64_t ld, int kcol0, int K, int origin, int col_end, const unsigned char* F, int nblk) {
+    k_syrk_dmma<128><<<g_sms, SyrkCfg<128>::kThreads, SyrkCfg<128>::kSmem, st>>>(n, A, ld, kcol0, K, origin, col_end, F, nblk);
+    k_syrk_dmma<64><<<g_sms * 3, SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmem, st>>>(n, A, ld, kcol0, K, origin, col_end, F, nblk);
 }
-int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* b) {
-    const int nblk = (n + NB - 1) / NB;
-    int64_t launches = 0;
-    k_back64<<<1, 128, 0, st>>>(n, nblk - 1, 1, L, ld, b); ++launches;
-    for (int kb = nblk - 1; kb >= 1; --kb) { k_back64<<<kb, 128, 0, st>>>(n, kb, 0, L, ld, b); ++launches; }
-    return launches;
+
+static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, int backward) {
+    set_attrs_once();
+    const int nblk = chol_nblk(n);
+    int blocks = g_coop_blocks < nblk ? g_coop_blocks : nblk;
+    if (blocks < 1) blocks = 1;
+    const double* dinv = ws;
+    double* ybuf = ws_ybuf(ws, n);
+    int* flags = ws_flags(ws, n);
+    const unsigned char* F = ws_F(ws, n);
+    int epoch = ++g_epoch;
+    int cacheF = nblk * nblk <= kTrsvFCacheMax ? 1 : 0;
+    size_t smem = sizeof(double) * 2 * kTrsvOwn * NB * NB + (cacheF ? (size_t)((nblk * nblk + 15) & ~15) : 0);
+    void* args[] = {(void*)&n, (void*)&L, (void*)&ld, (void*)&dinv, (void*)&b, (void*)&ybuf, (void*)&flags, (void*)&F, (void*)&epoch, (void*)&backward,
+                    (void*)&cacheF};
+    cudaLaunchCooperativeKernel((void*)k_trsv_flags, dim3(blocks), dim3(256), args, smem, st);
+    return 1;
 }
+int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 0); }
+int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 1); }
+
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld) {
     int T = (n + 31) / 32;
     k_mirror_lower<<<dim3(T, T), 256, 0, st>>>(n, A, ld);

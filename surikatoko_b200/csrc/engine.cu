@@ -108,7 +108,7 @@ struct Engine {
     Buf Xa, Xb, Xbound, pts_stage, cams_a, cams_b, cams_bound, Kd, camd_a, camd_b;
     double *X_cur = nullptr, *X_try = nullptr, *cams_cur = nullptr, *cams_try = nullptr, *camd_cur = nullptr, *camd_try = nullptr;
     // derivative pass and solve
-    Buf J, Ggf, pinv, skipped, deferred, Srhs, Lfac, xsol, resid, dfull, partial, errsum, slots, flags, skipped_cnt, dbg;
+    Buf J, Ggf, pinv, skipped, deferred, Srhs, Lfac, dinv, xsol, resid, dfull, partial, errsum, slots, flags, skipped_cnt, dbg;
     int64_t n_deferred = 0;   // points the tiled Schur kernel leaves to the per-point kernel (structure only, known at bind time)
     int schur_tile_points = 256;
     srk::PcgWorkspace pcg;
@@ -308,6 +308,7 @@ int ensure_solver_buffers(Engine& e, int solver) {
         size_t sbytes = sizeof(double) * ((size_t)e.ld * (size_t)e.nf + (size_t)e.ld);
         SRK_CUDA(e.Srhs.ensure(sbytes));
         SRK_CUDA(e.Lfac.ensure(sizeof(double) * (size_t)e.ld * (size_t)e.nf));
+        SRK_CUDA(e.dinv.ensure(sizeof(double) * srk::dense_cholesky_dinv_doubles(e.nf)));
     }
     return SRK_OK;
 }
@@ -399,14 +400,16 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
             if (refine > 0) { srk::launch_mirror_lower(st, nf, S, ld); e.launches += 1; }
             SRK_CUDA(cudaMemcpyAsync(L, S, sizeof(double) * (size_t)ld * nf, cudaMemcpyDeviceToDevice, st));
             SRK_CUDA(cudaMemcpyAsync(x, rhs, sizeof(double) * nf, cudaMemcpyDeviceToDevice, st));
-            e.launches += srk::dense_cholesky_factor(st, nf, L, ld, x, e.flags.as<int>() + 2);
-            e.launches += srk::dense_cholesky_backward(st, nf, L, ld, x);
+            double* di = e.dinv.as<double>();
+            e.launches += srk::dense_cholesky_factor(st, nf, L, ld, e.dinv.as<double>(), e.flags.as<int>() + 2);
+            e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, x);
+            e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, x);
             double* r = e.resid.as<double>();
             for (int it = 0; it < refine; ++it) {
                 srk::launch_residual_dd(st, nf, S, ld, x, rhs, r);
                 e.launches += 1;
-                e.launches += srk::dense_cholesky_forward(st, nf, L, ld, r);
-                e.launches += srk::dense_cholesky_backward(st, nf, L, ld, r);
+                e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, r);
+                e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, r);
                 srk::launch_axpy1(st, nf, r, x); e.launches += 1;
             }
         }
@@ -620,7 +623,7 @@ void srk_ba_destroy(void* h) {
     cudaStreamSynchronize(e->stream);
     Buf* bufs[] = {&e->obs_cam, &e->obs_pt, &e->obs_xy, &e->ox, &e->oy, &e->pt_begin, &e->cam_cnt, &e->cam_cursor, &e->cam_begin, &e->c_pt, &e->c_x, &e->c_y,
                    &e->Xa, &e->Xb, &e->Xbound, &e->pts_stage, &e->cams_a, &e->cams_b, &e->cams_bound, &e->Kd, &e->camd_a, &e->camd_b, &e->J, &e->Ggf,
-                   &e->pinv, &e->skipped, &e->deferred, &e->Srhs, &e->Lfac, &e->xsol, &e->resid, &e->dfull, &e->partial, &e->errsum, &e->slots, &e->flags,
+                   &e->pinv, &e->skipped, &e->deferred, &e->Srhs, &e->Lfac, &e->dinv, &e->xsol, &e->resid, &e->dfull, &e->partial, &e->errsum, &e->slots, &e->flags,
                    &e->skipped_cnt, &e->dbg};
     for (Buf* b : bufs) b->release();
     srk::pcg_release(e->pcg);

@@ -28,12 +28,14 @@ void launch_planes_to_points(cudaStream_t st, int64_t N, const double* planes, d
 void launch_debug_point_blocks(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const double* J, double* E, double* gp);
 void launch_debug_F_blocks(cudaStream_t st, int64_t O, const double* J, double* F);
 
-// Dense reduced-camera solve (chol_kernels.cu).  A is column-major n x n with leading dimension ld, lower triangle
-// referenced and overwritten by L.  b (optional) gets the forward substitution fused into the factorisation.
-// *info_dev is set to the 1-based index of the first non-positive pivot (0 = success).  All return launch counts.
-int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* b, int* info_dev);
-int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* b);
-int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* b);
+// Dense reduced-camera solve (chol_kernels.cu).  A is column-major n x n with leading dimension ld (multiple of 8), lower
+// triangle referenced and overwritten by L; ws (dense_cholesky_dinv_doubles(n) doubles) receives the inverses of the 64x64
+// diagonal blocks of L, the 64x64 block structure of L (zero tiles are skipped everywhere) and the substitution flags.  *info_dev is set to the 1-based index of the
+// first non-positive pivot (0 = success).  All return launch counts.
+size_t dense_cholesky_dinv_doubles(int n);
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev);
+int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
+int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
 // mirror the lower triangle into the upper one
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld);
 // r = b - A*x, symmetric A with both triangles stored, double-double accumulation
