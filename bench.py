@@ -264,7 +264,7 @@ def run_ours(args):
             ach = work / (avg_ms * 1e-3) / 1e12
             kernels[fam] = {"bound": "tensor", "avg_ms": avg_ms, "launch_groups": tm["count"], "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s",
                             "frac": ach / f64_peak, "share_of_step": tm["ms_total"] / ms}
-    for fam in ("update", "allreduce"):
+    for fam in ("update", "allreduce", "solve_factor", "solve_trsv"):
         if timing[fam]["count"]:
             kernels[fam] = {"avg_ms": timing[fam]["ms_total"] / timing[fam]["count"], "launch_groups": timing[fam]["count"],
                             "share_of_step": timing[fam]["ms_total"] / ms}

@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libsrk_ba.so")
 SOLVER_AUTO, SOLVER_DENSE_CHOLESKY, SOLVER_BLOCK_PCG = 0, 1, 2
 STOP_REASONS = {0: "", 1: "abs err threshold", 2: "small relative err change", 3: "hessian overflow",
                 4: "err converged to limit value", 5: "", 6: "max iterations"}
-TIMING_FAMILIES = ("jacobian", "frame_blocks", "schur", "solve", "backsub", "update", "residual", "allreduce")
+TIMING_FAMILIES = ("jacobian", "frame_blocks", "schur", "solve", "backsub", "update", "residual", "allreduce", "solve_factor", "solve_trsv")
 
 
 class SrkError(RuntimeError):

@@ -16,6 +16,8 @@
 //                     L_kk^-1, a grid-wide panel GEMV for the rows below / above, one grid.sync per block.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "kernels.h"
 
 namespace cg = cooperative_groups;
@@ -26,15 +28,18 @@ constexpr int NB = 64;     // diagonal block / sub-panel width
 constexpr int PB = 256;    // panel width of the trailing update
 
 // ---------------------------------------------------------------------------------------------------------------------
-// 64x64 diagonal block, register resident.  Thread (r = tid & 63, grp = tid >> 6) keeps row r of the block for the columns
-// c == grp (mod 4) in 16 registers, and the same slice of row r of W, which starts as the identity and receives the same
-// row operations: after the 64 elimination steps T holds L and W holds L^-1 (the row operations multiply by L^-1).
-// Per step the owners publish column j of T and row j of W through shared memory (double buffered, one barrier).
-// info: 1-based index of the first non-positive pivot.
+// 64x64 diagonal block.  Thread (r = tid & 63, grp = tid >> 6) keeps row r of the block, columns c == grp (mod 4), in 16
+// registers, and the same slice of row r of W, which starts as the identity and receives the same row operations: after the
+// 64 elimination steps T holds L D^(1/2)-unscaled and W the matching L^-1 factor; the 1/sqrt(d_j) scalings are deferred to the
+// output (L(r,c) = T(r,c) rs_c, Linv(r,c) = W(r,c) rs_r), so a step is: publish column j of T and row j of W through shared
+// memory (double buffered, ONE barrier), then one DFMA per owned element.  The step loop stays rolled: the column to publish
+// is picked with a predicated sweep instead of a dynamic register index, so the body is ~150 instructions and stays in the
+// instruction cache (a fully unrolled version is fetch bound).  info: 1-based index of the first non-positive pivot.
 __global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ dinv, int* __restrict__ info,
                                                      unsigned char* __restrict__ F, int nblk) {
-    __shared__ double col[2][NB];    // column j of T (unscaled), indexed by row
-    __shared__ double wrow[2][NB];   // row j of W (unscaled), indexed by column
+    __shared__ double col[2][NB];
+    __shared__ double wrow[2][NB];
+    __shared__ double rsv[NB];
     const int nb = min(NB, n - k0);
     const int tid = threadIdx.x;
     const int r = tid & 63, grp = tid >> 6;
@@ -46,38 +51,38 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __re
         w[i] = (r == c) ? 1.0 : 0.0;
     }
     if (tid == 0) F[(size_t)(k0 / NB) * nblk + k0 / NB] = 1;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < NB; ++j) {
         const int buf = j & 1;
-        if (grp == (j & 3)) col[buf][r] = t[j >> 2];             // T(r, j): column j lives in the threads of group j mod 4
+#pragma unroll
+        for (int i = 0; i < 16; ++i) if (grp + 4 * i == j) col[buf][r] = t[i];   // T(r, j), unscaled
         if (r == j) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) wrow[buf][grp + 4 * i] = w[i];   // W(j, :)
+            for (int i = 0; i < 16; ++i) wrow[buf][grp + 4 * i] = w[i];          // W(j, :), unscaled
         }
         __syncthreads();
         const double d = col[buf][j];
-        if (tid == 0 && !(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1);
-        const double rs = rsqrt(d);
-        const double lr = col[buf][r] * rs;                       // L(r, j) for r > j
+        if (tid == j) {
+            if (!(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1);
+            rsv[j] = rsqrt(d);
+        }
         if (r > j) {
+            const double a = col[buf][r] * (1.0 / d);         // L(r,j) L(c,j) = T(r,j) T(c,j) / d
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int c = grp + 4 * i;
-                if (c > j) { if (c <= r) t[i] -= lr * (col[buf][c] * rs); }
-                else w[i] -= lr * (wrow[buf][c] * rs);
+                if (c > j) { if (c <= r) t[i] -= a * col[buf][c]; }
+                else w[i] -= a * wrow[buf][c];
             }
-            if (grp == (j & 3)) t[j >> 2] = lr;
-        } else if (r == j) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) w[i] *= rs;
-            if (grp == (j & 3)) t[j >> 2] = d * rs;               // sqrt(d)
         }
     }
+    __syncthreads();
+    const double rsr = rsv[r];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int c = grp + 4 * i;
-        if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = t[i];
-        dinv[(size_t)c * NB + r] = (r >= c) ? w[i] : 0.0;         // column-major 64x64: Linv(r, c)
+        if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = t[i] * rsv[c];
+        dinv[(size_t)c * NB + r] = (r >= c) ? w[i] * rsr : 0.0;   // column-major 64x64: Linv(r, c)
     }
 }
 
@@ -491,33 +496,81 @@ static inline double* ws_ybuf(double* ws, int n) { return ws + (size_t)chol_nblk
 static inline int* ws_flags(double* ws, int n) { return (int*)(ws_ybuf(ws, n) + (size_t)chol_nblk(n) * NB); }
 static inline unsigned char* ws_F(double* ws, int n) { return (unsigned char*)(ws_ybuf(ws, n) + (size_t)chol_nblk(n) * NB + (chol_nblk(n) + 1) / 2 + 8); }
 
-int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
-    set_attrs_once();
+// Development aid: SRK_CHOL_PROFILE=1 times every kernel type of the factorisation with events (serialised, no graph).
+static bool g_prof = false;
+static double g_prof_ms[4] = {0, 0, 0, 0};
+static int g_prof_n[4] = {0, 0, 0, 0};
+struct ProfScope {
+    int k; cudaStream_t st; cudaEvent_t a, b;
+    ProfScope(int kind, cudaStream_t s) : k(kind), st(s) { if (g_prof) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); } }
+    ~ProfScope() { if (g_prof) { cudaEventRecord(b, st); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); g_prof_ms[k] += ms; g_prof_n[k]++; cudaEventDestroy(a); cudaEventDestroy(b); } }
+};
+void dense_cholesky_profile_report() {
+    const char* names[4] = {"potrf64_inv", "panel_solve", "syrk_inpanel", "syrk_trailing"};
+    for (int i = 0; i < 4; ++i) if (g_prof_n[i]) printf("  %-14s n=%4d total %8.3f ms avg %7.1f us\n", names[i], g_prof_n[i], g_prof_ms[i], 1e3 * g_prof_ms[i] / g_prof_n[i]);
+    for (int i = 0; i < 4; ++i) { g_prof_ms[i] = 0; g_prof_n[i] = 0; }
+}
+
+static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
     int64_t launches = 0;
     const int nblk = chol_nblk(n);
     unsigned char* F = ws_F(ws, n);
     cudaMemsetAsync(info_dev, 0, sizeof(int), st);
     cudaMemsetAsync(ws_flags(ws, n), 0, sizeof(int) * nblk, st);
     cudaMemsetAsync(F, 0, (size_t)nblk * nblk, st);
-    g_epoch = 0;
     for (int p0 = 0; p0 < n; p0 += PB) {
         const int pend = min(n, p0 + PB);
         for (int k0 = p0; k0 < pend; k0 += NB) {
             double* di = ws + (size_t)(k0 / NB) * NB * NB;
-            k_potrf64_inv<<<1, 256, 0, st>>>(n, k0, A, ld, di, info_dev, F, nblk); ++launches;
+            { ProfScope ps(0, st); k_potrf64_inv<<<1, 256, 0, st>>>(n, k0, A, ld, di, info_dev, F, nblk); } ++launches;
             const int below = n - (k0 + NB);
             if (below <= 0) continue;
-            k_panel_solve<<<(below + PS_ROWS - 1) / PS_ROWS, 256, kPanelSolveSmem, st>>>(n, k0, A, ld, di, F, nblk); ++launches;
+            { ProfScope ps(1, st); k_panel_solve<<<(below + PS_ROWS - 1) / PS_ROWS, 256, kPanelSolveSmem, st>>>(n, k0, A, ld, di, F, nblk); } ++launches;
             const int origin = k0 + NB;
             if (origin < pend) {   // rest of the current panel, K = 64
-                launch_syrk(st, n, A, ld, k0, NB, origin, pend, F, nblk); launches += 2;
+                { ProfScope ps(2, st); launch_syrk(st, n, A, ld, k0, NB, origin, pend, F, nblk); } launches += 2;
             }
         }
         if (pend < n) {            // trailing matrix, K = panel width (pend - p0 == PB whenever pend < n)
-            launch_syrk(st, n, A, ld, p0, pend - p0, pend, n, F, nblk); launches += 2;
+            { ProfScope ps(3, st); launch_syrk(st, n, A, ld, p0, pend - p0, pend, n, F, nblk); } launches += 2;
         }
     }
     return launches;
+}
+
+// The launch sequence of a factorisation is static for given (n, buffers): it is captured once into a CUDA graph and
+// replayed, which removes ~800 host launch calls per solve from the critical path.
+struct FactorGraph { int n = 0; double* A = nullptr; int64_t ld = 0; double* ws = nullptr; int* info = nullptr; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
+static FactorGraph g_fg;
+
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
+    set_attrs_once();
+    g_epoch = 0;
+    static int prof_env = -1;
+    if (prof_env < 0) { const char* e = getenv("SRK_CHOL_PROFILE"); prof_env = (e != nullptr && e[0] == '1') ? 1 : 0; }
+    g_prof = prof_env == 1;
+    if (g_prof) return enqueue_factor(st, n, A, ld, ws, info_dev);
+    if (g_fg.exec != nullptr && g_fg.n == n && g_fg.A == A && g_fg.ld == ld && g_fg.ws == ws && g_fg.info == info_dev) {
+        if (cudaGraphLaunch(g_fg.exec, st) == cudaSuccess) return g_fg.launches;
+        cudaGetLastError();
+    }
+    if (g_fg.exec != nullptr) { cudaGraphExecDestroy(g_fg.exec); g_fg.exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    if (chol_nblk(n) >= 8 && cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int64_t launches = enqueue_factor(st, n, A, ld, ws, info_dev);
+        if (cudaStreamEndCapture(st, &graph) == cudaSuccess && graph != nullptr) {
+            cudaGraphExec_t exec = nullptr;
+            if (cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                cudaGraphDestroy(graph);
+                g_fg.n = n; g_fg.A = A; g_fg.ld = ld; g_fg.ws = ws; g_fg.info = info_dev; g_fg.exec = exec; g_fg.launches = launches;
+                if (cudaGraphLaunch(exec, st) == cudaSuccess) return launches;
+            } else {
+                cudaGraphDestroy(graph);
+            }
+        }
+        cudaGetLastError();
+    }
+    return enqueue_factor(st, n, A, ld, ws, info_dev);
 }
 
 static void launch_syrk(cudaStream_t st, int n, double* A, int64_t ld, int kcol0, int K, int origin, int col_end, const unsigned char* F, int nblk) {

@@ -48,8 +48,8 @@ struct Buf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-enum Family { F_JACOBIAN = 0, F_FRAME, F_SCHUR, F_SOLVE, F_BACKSUB, F_UPDATE, F_RESIDUAL, F_ALLREDUCE, F_COUNT };
-const char* kFamilyNames[F_COUNT] = {"jacobian", "frame_blocks", "schur", "solve", "backsub", "update", "residual", "allreduce"};
+enum Family { F_JACOBIAN = 0, F_FRAME, F_SCHUR, F_SOLVE, F_BACKSUB, F_UPDATE, F_RESIDUAL, F_ALLREDUCE, F_FACTOR, F_TRSV, F_COUNT };
+const char* kFamilyNames[F_COUNT] = {"jacobian", "frame_blocks", "schur", "solve", "backsub", "update", "residual", "allreduce", "solve_factor", "solve_trsv"};
 
 struct FamilyTimer {
     std::vector<cudaEvent_t> pending;  // start, stop, start, stop, ...
@@ -401,15 +401,17 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
             SRK_CUDA(cudaMemcpyAsync(L, S, sizeof(double) * (size_t)ld * nf, cudaMemcpyDeviceToDevice, st));
             SRK_CUDA(cudaMemcpyAsync(x, rhs, sizeof(double) * nf, cudaMemcpyDeviceToDevice, st));
             double* di = e.dinv.as<double>();
-            e.launches += srk::dense_cholesky_factor(st, nf, L, ld, e.dinv.as<double>(), e.flags.as<int>() + 2);
-            e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, x);
-            e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, x);
+            { Scope s2(e, F_FACTOR); e.launches += srk::dense_cholesky_factor(st, nf, L, ld, e.dinv.as<double>(), e.flags.as<int>() + 2); }
+            { Scope s2(e, F_TRSV);
+              e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, x);
+              e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, x); }
             double* r = e.resid.as<double>();
             for (int it = 0; it < refine; ++it) {
                 srk::launch_residual_dd(st, nf, S, ld, x, rhs, r);
                 e.launches += 1;
-                e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, r);
-                e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, r);
+                { Scope s2(e, F_TRSV);
+                  e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, r);
+                  e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, r); }
                 srk::launch_axpy1(st, nf, r, x); e.launches += 1;
             }
         }

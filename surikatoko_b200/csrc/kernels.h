@@ -33,6 +33,7 @@ void launch_debug_F_blocks(cudaStream_t st, int64_t O, const double* J, double* 
 // diagonal blocks of L, the 64x64 block structure of L (zero tiles are skipped everywhere) and the substitution flags.  *info_dev is set to the 1-based index of the
 // first non-positive pivot (0 = success).  All return launch counts.
 size_t dense_cholesky_dinv_doubles(int n);
+void dense_cholesky_profile_report();
 int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev);
 int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
 int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
