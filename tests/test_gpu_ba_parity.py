@@ -228,3 +228,70 @@ def test_skipped_points_mask_is_reproduced(oracle, engine):
     N = pr.n_points
     sk = np.nonzero(ref["skipped"])[0]
     assert np.all(got["corrections"][:3 * N].reshape(N, 3)[sk] == 0.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_gpu_matches_reference_python_prototype_fixture(engine):
+    """The committed outputs of the reference's own Python prototype (tests/golden/pyproto_derivs.json, f0 = K22 = 1)."""
+    import json, os
+    import surikatoko_b200 as sb
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pyproto_derivs.json")))
+    M, N = g["n_cams"], g["n_points"]
+    prob = sb.BAProblem(g["obs_cam"], g["obs_point"], g["obs_xy"], g["points"], g["cams"], np.tile(np.array(g["K"]), (M, 1)), False, g["f0"])
+    err, seen = engine.reproj_error(prob.copy())
+    assert seen == len(g["obs_cam"]) and abs(err - g["err_initial"]) <= 1e-12 * g["err_initial"]
+    assert engine.bind(prob)       # the fixture state is already normalised: normalising again is the identity up to rounding
+    got = engine.debug_derivs_and_solve(c=g["hessian_factor"])
+    assert relerr(got["gradE"], np.array(g["gradE"])) < 1e-11
+    assert relerr(got["E"].reshape(3 * N, 3), np.array(g["E"])) < 1e-11
+    assert relerr(got["G"].reshape(10 * M, 10), np.array(g["G"])) < 1e-11
+    Fd = np.array(g["F"]); mine = np.zeros_like(Fd)
+    for o in range(len(g["obs_cam"])):
+        p, f = g["obs_point"][o], g["obs_cam"][o]
+        mine[3 * p:3 * p + 3, 10 * f:10 * f + 10] = got["F"][o]
+    assert relerr(mine, Fd) < 1e-11 and np.array_equal(mine != 0, Fd != 0)
+    assert relerr(got["S"], np.array(g["S"])) < 1e-10
+    assert relerr(got["rhs"], np.array(g["rhs"])) < 1e-9
+    assert relerr(got["corrections"], np.array(g["corrections"])) < 1e-4    # cond(S) ~ 1e11: LA.solve vs refined Cholesky
+
+
+def test_cpp_drop_in_adapter_builds_and_runs(tmp_path):
+    """include/suriko_compat (C++17, the reference's container API) -> C ABI -> GPU."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "surikatoko_b200", "_lib")
+    exe = str(tmp_path / "compat_demo")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(root, "tests", "cpp", "compat_demo.cpp"), "-L" + lib, "-lsrk_ba",
+                           "-Wl,-rpath," + lib, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout
+    f = out.stdout.split()
+    e0, e1 = float(f[0]), float(f[1])
+    assert e1 < 0.5 * e0 and int(f[-3]) > 0 and int(f[-2]) == 12 * 64
+
+
+def test_python_mirror_of_reference_interface(oracle, engine):
+    """BundleAdjustmentKanatani.ComputeInplace on FragmentMap / CornerTrackRepository containers == flat path."""
+    import surikatoko_b200 as sb
+    from surikatoko_b200 import ba
+    pr = small_scene(oracle, cell=0.5)
+    m = ba.FragmentMap(); rep = ba.CornerTrackRepository()
+    for p in range(pr.n_points):
+        _, sp_id = m.AddSalientPointTempl(pr.points[p])
+        rep.AddCornerTrackObj().SalientPointId = sp_id
+    for o in range(pr.n_obs):
+        rep.GetPointTrackById(int(pr.obs_point[o])).AddCorner(int(pr.obs_cam[o]), pr.obs_xy[o])
+    cams = [ba.SE3Transform.from_flat(c) for c in pr.cams]
+    Ks = [k.reshape(3, 3).T for k in pr.K]
+    bak = sb.BundleAdjustmentKanatani(engine=engine)
+    bak.max_outer_iters = 4
+    tc = sb.BundleAdjustmentKanataniTermCriteria(); tc.AllowedReprojErrRelativeChange(1e-10)
+    e0 = sb.BundleAdjustmentKanatani.ReprojError(pr.f0, m, cams, rep, None, Ks, engine=engine)
+    ok = bak.ComputeInplace(pr.f0, m, cams, rep, None, Ks, tc)
+    flat = engine.solve(to_problem(pr), sb.BAOptions(err_change=1e-10, max_outer_iters=4))
+    assert abs(e0 - flat.err_initial) <= 1e-14 * e0
+    assert ok == flat.converged and bak.OptimizationStatusString() == flat.stop_reason
+    assert np.allclose(bak.last_report.err_trace, flat.err_trace, rtol=1e-9)
+    assert bak.PointsCount() == pr.n_points and bak.FramesCount() == pr.n_cams and bak.NormalizedVarsCount() == 3 * pr.n_points + 10 * pr.n_cams - 7
+    rms = bak.ReprojErrorPixPerPoint(bak.last_report.err_final, bak.last_report.seen_points)
+    assert abs(rms - pr.f0 * np.sqrt(flat.err_final / flat.seen_points)) < 1e-9
