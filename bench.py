@@ -173,20 +173,9 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     eng = sb.Engine(local)
     eng.set_stream(stream.cuda_stream)
-    views = {}
     if world > 1:
-        class _Dev:
-            def __init__(self, ptr, n):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
-
-        def allreduce(ptr, count, st):
-            key = (ptr, count)
-            t = views.get(key)
-            if t is None:
-                t = torch.as_tensor(_Dev(ptr, count), device=dev); views[key] = t
-            with torch.cuda.stream(stream):
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        eng.set_allreduce(allreduce, rank, world)
+        from surikatoko_b200.dist import attach_allreduce
+        attach_allreduce(eng, stream, dev)
 
     solver = {"c5": sb.SOLVER_BLOCK_PCG}.get(name, sb.SOLVER_AUTO)
     opt1 = sb.BAOptions(max_outer_iters=1, solver=solver)
