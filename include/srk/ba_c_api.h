@@ -139,6 +139,10 @@ SRK_API int srk_ba_set_allreduce(void* h, srk_allreduce_fn fn, void* user, int r
  *   corrections[3N+10M] (gaps re-inserted, BA.cpp:1600-1679). */
 SRK_API int srk_ba_debug_derivs_and_solve(void* h, double c, double* gradE, double* E, double* G, double* Fblk, double* S, double* rhs,
                                   unsigned char* skipped, double* corrections);
+/* Same with the reduced-camera solver chosen explicitly (SRK_SOLVER_DENSE_CHOLESKY / SRK_SOLVER_BLOCK_PCG); with the PCG solver
+ * S / rhs are the block-sparse system scattered into the same dense layout, *pcg_iters the iterations it took. */
+SRK_API int srk_ba_debug_derivs_and_solve_ex(void* h, double c, int32_t solver, double* gradE, double* E, double* G, double* Fblk, double* S, double* rhs,
+                                             unsigned char* skipped, double* corrections, int32_t* pcg_iters);
 /* Resident (normalised) state as the engine holds it. */
 SRK_API int srk_ba_debug_get_state(void* h, double* points, double* cams);
 /* ApplyCorrections (BA.cpp:1997-2063) of `corrections` to the resident state, then ReprojError. */

@@ -69,6 +69,7 @@ def load_library():
     L.srk_ba_fetch.argtypes = [C.c_void_p, C.POINTER(_Problem)]
     L.srk_ba_set_allreduce.argtypes = [C.c_void_p, ALLREDUCE_FN, C.c_void_p, C.c_int, C.c_int]
     L.srk_ba_debug_derivs_and_solve.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 8
+    L.srk_ba_debug_derivs_and_solve_ex.argtypes = [C.c_void_p, C.c_double, C.c_int32] + [C.c_void_p] * 8 + [C.POINTER(C.c_int32)]
     L.srk_ba_debug_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.srk_ba_debug_apply.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
     L.srk_ba_set_timing.argtypes = [C.c_void_p, C.c_int]
@@ -239,16 +240,18 @@ class Engine:
         _check(self._lib.srk_ba_fetch(self._h, C.byref(ps)))
         return problem
 
-    def debug_derivs_and_solve(self, c=None):
+    def debug_derivs_and_solve(self, c=None, solver=SOLVER_DENSE_CHOLESKY):
         pr = self._bound
         N, M, O = pr.n_points, pr.n_cams, pr.n_obs
         nf = 10 * M - 7
         out = dict(gradE=np.zeros(3 * N + 10 * M), E=np.zeros((N, 3, 3)), G=np.zeros((M, 10, 10)), F=np.zeros((O, 3, 10)))
         if c is not None:
             out.update(S=np.zeros((nf, nf)), rhs=np.zeros(nf), skipped=np.zeros(N, dtype=np.uint8), corrections=np.zeros(3 * N + 10 * M))
-        _check(self._lib.srk_ba_debug_derivs_and_solve(self._h, -1.0 if c is None else float(c), _ptr(out["gradE"]), _ptr(out["E"]), _ptr(out["G"]),
-                                                       _ptr(out["F"]), _ptr(out.get("S")), _ptr(out.get("rhs")), _ptr(out.get("skipped")),
-                                                       _ptr(out.get("corrections"))))
+        iters = C.c_int32(0)
+        _check(self._lib.srk_ba_debug_derivs_and_solve_ex(self._h, -1.0 if c is None else float(c), solver, _ptr(out["gradE"]), _ptr(out["E"]),
+                                                          _ptr(out["G"]), _ptr(out["F"]), _ptr(out.get("S")), _ptr(out.get("rhs")),
+                                                          _ptr(out.get("skipped")), _ptr(out.get("corrections")), C.byref(iters)))
+        out["pcg_iters"] = iters.value
         if "S" in out:
             out["S"] = out["S"].T.copy()  # column-major -> [row, col]
         return out

@@ -204,8 +204,7 @@ constexpr int kSchurWarps = 4;
 
 __global__ void __launch_bounds__(kSchurWarps * 32) k_schur(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin,
                                                             const int32_t* __restrict__ obs_cam, const double* __restrict__ J, double c,
-                                                            int unity, double* __restrict__ S, int64_t ld, double* __restrict__ rhs,
-                                                            double* __restrict__ pinv, unsigned char* __restrict__ skipped,
+                                                            SchurSink sink, double* __restrict__ pinv, unsigned char* __restrict__ skipped,
                                                             const unsigned char* __restrict__ only_flagged) {
     __shared__ double sF[kSchurWarps][kSchurCH][30];   // slot 0 only: F of the row chunk
     __shared__ double sW[kSchurWarps][2][kSchurCH][30];
@@ -289,8 +288,7 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_schur(int64_t N, int64_t O
         // rhs += F_i^T (Einv g_p)
         for (int t = lane; t < nA * 10; t += 32) {
             int i = t / 10, a = t % 10;
-            int r = red_index(sCam[w][0][i], a, unity);
-            if (r >= 0) atomicAdd(&rhs[r], sF[w][i][a] * t0 + sF[w][i][10 + a] * t1 + sF[w][i][20 + a] * t2);
+            sink_add_rhs(sink, sCam[w][0][i], a, sF[w][i][a] * t0 + sF[w][i][10 + a] * t1 + sF[w][i][20 + a] * t2);
         }
         for (int cl = 0; cl <= ci; ++cl) {
             int slotB = 0, nB = nA;
@@ -314,16 +312,13 @@ __global__ void __launch_bounds__(kSchurWarps * 32) k_schur(int64_t N, int64_t O
                 for (int v = 0; v < 3; ++v)
 #pragma unroll
                     for (int x = 0; x < 5; ++x) { f[v][x] = Fi[v * 10 + tr + x]; ww[v][x] = Wl[v * 10 + tc + x]; }
+                const int blk = sink_block_id(sink, cam_i, cam_l);
 #pragma unroll
                 for (int x = 0; x < 5; ++x) {
-                    int row = red_index(cam_i, tr + x, unity);
-                    if (row < 0) continue;
 #pragma unroll
                     for (int y = 0; y < 5; ++y) {
-                        int col = red_index(cam_l, tc + y, unity);
-                        if (col < 0) continue;
                         double v = f[0][x] * ww[0][y] + f[1][x] * ww[1][y] + f[2][x] * ww[2][y];
-                        atomicAdd(&S[(size_t)col * ld + row], -v);
+                        sink_add(sink, blk, cam_i, tr + x, cam_l, tc + y, -v);
                     }
                 }
             }
@@ -353,6 +348,17 @@ constexpr int kTileBatch = 16;   // points per staging batch
 constexpr int kTileSO = 128;     // observations per staging batch
 constexpr int kTileHash = 64;
 
+__device__ __forceinline__ void hash_insert_pair(unsigned long long* keys, unsigned mask, int cam_i, int cam_l, int* overflow) {
+    const unsigned long long key = ((unsigned long long)(unsigned)cam_i << 32) | (unsigned)cam_l;
+    unsigned h = hash_pair(key, mask);
+    for (unsigned probe = 0; probe <= mask; ++probe) {
+        const unsigned long long prev = atomicCAS(&keys[h], kHashEmpty, key);
+        if (prev == kHashEmpty || prev == key) return;
+        h = (h + 1) & mask;
+    }
+    atomicExch(overflow, 1);
+}
+
 template <int CMAX>
 struct SchurTileCfg {
     static constexpr int kBlocks = CMAX * (CMAX + 1) / 2;
@@ -364,8 +370,8 @@ struct SchurTileCfg {
 template <int CMAX>
 __global__ void __launch_bounds__(SchurTileCfg<CMAX>::kThreads) k_schur_tile(
     int64_t N, int64_t O, int tile_points, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam, const double* __restrict__ J,
-    double c, int unity, double* __restrict__ S, int64_t ld, double* __restrict__ rhs, double* __restrict__ pinv,
-    unsigned char* __restrict__ skipped, unsigned char* __restrict__ deferred, int plan_only) {
+    double c, SchurSink sink, double* __restrict__ pinv, unsigned char* __restrict__ skipped, unsigned char* __restrict__ deferred, int plan_only,
+    unsigned long long* __restrict__ plan_keys, unsigned plan_mask, int* __restrict__ plan_overflow) {
     using Cfg = SchurTileCfg<CMAX>;
     extern __shared__ double smem[];
     double* sF = smem;                         // [kTileSO][30]
@@ -461,6 +467,15 @@ __global__ void __launch_bounds__(SchurTileCfg<CMAX>::kThreads) k_schur_tile(
             }
             bad = __any_sync(0xffffffffu, bad);
             if (lane == 0) deferred[j] = bad ? 1 : 0;
+            if (bad && plan_only && plan_keys != nullptr) {
+                for (int pr = lane; pr < k * (k + 1) / 2; pr += 32) {
+                    int i2 = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+                    while (i2 * (i2 + 1) / 2 > pr) --i2;
+                    while ((i2 + 1) * (i2 + 2) / 2 <= pr) ++i2;
+                    const int l2 = pr - i2 * (i2 + 1) / 2;
+                    hash_insert_pair(plan_keys, plan_mask, obs_cam[b + i2], obs_cam[b + l2], plan_overflow);
+                }
+            }
             if (bad || plan_only) continue;
             double a9[9];
 #pragma unroll
@@ -564,21 +579,31 @@ __global__ void __launch_bounds__(SchurTileCfg<CMAX>::kThreads) k_schur_tile(
         __syncthreads();
         bb += cnt;
     }
-    if (plan_only) return;
+    if (plan_only) {
+        // structure of the block-sparse reduced camera system: every camera pair of the tile table (a superset of the pairs that
+        // co-observe a point of the tile; the extra blocks simply stay zero)
+        if (plan_keys != nullptr) {
+            for (int b = tid; b < Cfg::kBlocks; b += Cfg::kThreads) {
+                int r = (int)((sqrtf(8.0f * (float)b + 1.0f) - 1.0f) * 0.5f);
+                while (r * (r + 1) / 2 > b) --r;
+                while ((r + 1) * (r + 2) / 2 <= b) ++r;
+                const int l2 = b - r * (r + 1) / 2;
+                if (r < nLocal) hash_insert_pair(plan_keys, plan_mask, sTab[r], sTab[l2], plan_overflow);
+            }
+        }
+        return;
+    }
     // ---- flush: one red.global.add.f64 per touched entry per tile
     if (is_block_warp) {
         if (li >= 0) {
             const int cam_i = sTab[li], cam_l = sTab[ll];
+            const int blk = sink_block_id(sink, cam_i, cam_l);
 #pragma unroll
             for (int x = 0; x < 5; ++x) {
-                const int row = red_index(cam_i, tr + x, unity);
-                if (row < 0) continue;
 #pragma unroll
                 for (int y = 0; y < 5; ++y) {
-                    const int col = red_index(cam_l, tc + y, unity);
-                    if (col < 0) continue;
                     const double v = acc[x * 5 + y];
-                    if (v != 0.0) atomicAdd(&S[(size_t)col * ld + row], -v);
+                    if (v != 0.0) sink_add(sink, blk, cam_i, tr + x, cam_l, tc + y, -v);
                 }
             }
         }
@@ -589,8 +614,7 @@ __global__ void __launch_bounds__(SchurTileCfg<CMAX>::kThreads) k_schur_tile(
             if (en >= CMAX * 10) continue;
             const int lc = en / 10, a = en % 10;
             if (lc >= nLocal) continue;
-            const int r = red_index(sTab[lc], a, unity);
-            if (r >= 0 && racc[q] != 0.0) atomicAdd(&rhs[r], racc[q]);
+            if (racc[q] != 0.0) sink_add_rhs(sink, sTab[lc], a, racc[q]);
         }
     }
 }
@@ -802,19 +826,20 @@ void launch_residual(cudaStream_t st, int64_t O, const int32_t* obs_cam, const i
 void launch_fill_reduced(cudaStream_t st, int M, const double* G, const double* gf, double c, int unity, double* S, int64_t ld, double* rhs) {
     k_fill_reduced<<<M, 128, 0, st>>>(M, G, gf, c, unity, S, ld, rhs);
 }
-void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, int unity,
-                  double* S, int64_t ld, double* rhs, double* pinv, unsigned char* skipped, const unsigned char* only_flagged) {
-    if (N > 0) k_schur<<<cdiv(N, kSchurWarps), kSchurWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, unity, S, ld, rhs, pinv, skipped, only_flagged);
+void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
+                  double* pinv, unsigned char* skipped, const unsigned char* only_flagged) {
+    if (N > 0) k_schur<<<cdiv(N, kSchurWarps), kSchurWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, sink, pinv, skipped, only_flagged);
 }
 void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
-                       int unity, double* S, int64_t ld, double* rhs, double* pinv, unsigned char* skipped, unsigned char* deferred, int plan_only) {
+                       const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred, int plan_only,
+                       unsigned long long* plan_keys, unsigned plan_mask, int* plan_overflow) {
     if (N <= 0) return;
     constexpr int CMAX = 12;
     static bool attr = false;
     const size_t smem = schur_tile_smem<CMAX>();
     if (!attr) { cudaFuncSetAttribute(k_schur_tile<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-    k_schur_tile<CMAX><<<cdiv(N, tile_points), SchurTileCfg<CMAX>::kThreads, smem, st>>>(N, O, tile_points, pt_begin, obs_cam, J, c, unity, S, ld, rhs, pinv,
-                                                                                      skipped, deferred, plan_only);
+    k_schur_tile<CMAX><<<cdiv(N, tile_points), SchurTileCfg<CMAX>::kThreads, smem, st>>>(N, O, tile_points, pt_begin, obs_cam, J, c, sink, pinv, skipped,
+                                                                                      deferred, plan_only, plan_keys, plan_mask, plan_overflow);
 }
 void launch_backsub(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, const double* df,
                     const double* pinv, const unsigned char* skipped, const double* X, double* Xtry, double* dp_out, int lanes_per_point) {

@@ -27,6 +27,45 @@ __host__ __device__ __forceinline__ int red_index(int cam, int a, int unity) {
     return cam * kV - 7 + a;
 }
 
+// Where the Schur accumulation kernels put their results.  Dense mode (blocks == nullptr): the gauge-reduced column-major
+// matrix S (lower block triangle) and rhs of the dense Cholesky path.  Block-sparse mode: 10x10 blocks (row-major, rows = the
+// variables of the LARGER camera index) addressed through an open-addressing hash of the camera pair, and a right-hand side
+// in full frame-variable space [10M]; the 7 gauge variables are skipped (their rows / columns stay zero).
+struct SchurSink {
+    double* S; int64_t ld; double* rhs; int unity;
+    const unsigned long long* hkeys; const int* hids; unsigned hmask; double* blocks;
+};
+constexpr unsigned long long kHashEmpty = 0xffffffffffffffffull;
+__host__ __device__ __forceinline__ unsigned hash_pair(unsigned long long key, unsigned mask) {
+    key ^= key >> 33; key *= 0xff51afd7ed558ccdull; key ^= key >> 33; key *= 0xc4ceb9fe1a85ec53ull; key ^= key >> 33;
+    return (unsigned)key & mask;
+}
+// block id of the camera pair (cam_i >= cam_l), or -1 (dense mode / pair not in the structure)
+__device__ __forceinline__ int sink_block_id(const SchurSink& s, int cam_i, int cam_l) {
+    if (s.blocks == nullptr) return -1;
+    const unsigned long long key = ((unsigned long long)(unsigned)cam_i << 32) | (unsigned)cam_l;
+    unsigned h = hash_pair(key, s.hmask);
+    for (unsigned probe = 0; probe <= s.hmask; ++probe) {
+        const unsigned long long k = s.hkeys[h];
+        if (k == key) return s.hids[h];
+        if (k == kHashEmpty) return -1;
+        h = (h + 1) & s.hmask;
+    }
+    return -1;
+}
+__device__ __forceinline__ void sink_add(const SchurSink& s, int blk, int cam_i, int a, int cam_l, int b, double v) {
+    const int row = red_index(cam_i, a, s.unity), col = red_index(cam_l, b, s.unity);
+    if (row < 0 || col < 0) return;
+    if (s.blocks == nullptr) atomicAdd(&s.S[(size_t)col * s.ld + row], v);
+    else if (blk >= 0) atomicAdd(&s.blocks[(size_t)blk * 100 + a * 10 + b], v);
+}
+__device__ __forceinline__ void sink_add_rhs(const SchurSink& s, int cam, int a, double v) {
+    const int r = red_index(cam, a, s.unity);
+    if (r < 0) return;
+    if (s.blocks == nullptr) atomicAdd(&s.rhs[r], v);
+    else atomicAdd(&s.rhs[(size_t)cam * 10 + a], v);
+}
+
 // pqr = K * (R*X + T)   (BA.cpp:469-470), natural left-to-right coefficient order.
 __device__ __forceinline__ void project_pqr(const double* __restrict__ cd, double X0, double X1, double X2, double& p, double& q, double& r) {
     const double* R = cd + CD_R; const double* T = cd + CD_T; const double* K = cd + CD_K;

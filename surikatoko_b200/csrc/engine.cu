@@ -187,6 +187,7 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     }
     SRK_CUDA(cudaSetDevice(e.device));
     e.bound = false;
+    e.pcg.structure_valid = false;
     e.N = p->n_points; e.O = p->n_obs; e.M = (int)p->n_cams; e.shared_K = p->shared_K ? 1 : 0; e.f0 = p->f0;
     e.unity = unity; e.unity_val = unity_val;
     e.nf = e.M * 10 - 7;
@@ -281,8 +282,9 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     e.n_deferred = 0;
     if (N > 0) {
         SRK_CUDA(cudaMemsetAsync(e.skipped_cnt.p, 0, sizeof(unsigned long long), st));
-        srk::launch_schur_tile(st, N, O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), nullptr, 0.0, e.unity, nullptr, 0, nullptr,
-                               nullptr, nullptr, e.deferred.as<unsigned char>(), 1);
+        srk::SchurSink none{};
+        srk::launch_schur_tile(st, N, O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), nullptr, 0.0, none, nullptr, nullptr,
+                               e.deferred.as<unsigned char>(), 1, nullptr, 0, nullptr);
         srk::launch_count_skipped(st, N, e.deferred.as<unsigned char>(), e.skipped_cnt.as<unsigned long long>());
         e.launches += 2;
         unsigned long long nd = 0;
@@ -367,6 +369,19 @@ int derivative_pass(Engine& e) {
     return do_allreduce(e, e.Ggf.as<double>(), 110 * (int64_t)e.M);
 }
 
+// K2: per-point blocks + Schur accumulation into `sink` (dense S or block-sparse blocks).
+void schur_accumulate(Engine& e, const srk::SchurSink& sink, double c) {
+    cudaStream_t st = e.stream;
+    srk::launch_schur_tile(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink,
+                           e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>(), 0, nullptr, 0, nullptr);
+    e.launches += e.N > 0 ? 1 : 0;
+    if (e.n_deferred > 0) {
+        srk::launch_schur(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink, e.pinv.as<double>(),
+                          e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>());
+        e.launches += 1;
+    }
+}
+
 // EstimateCorrectionsDecomposedInTwoPhases (BA.cpp:1771-1995) + ApplyCorrections (BA.cpp:1997-2063) into the trial state,
 // then ReprojError of the trial state.  dp_out (optional) receives the point corrections [3N].
 int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* dp_out) {
@@ -382,14 +397,8 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
             Scope s(e, F_SCHUR);
             SRK_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * ((size_t)ld * nf + ld), st));
             if (e.rank == 0) { srk::launch_fill_reduced(st, M, G, gf, c, e.unity, S, ld, rhs); e.launches += 1; }
-            srk::launch_schur_tile(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, e.unity, S, ld,
-                                   rhs, e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>(), 0);
-            e.launches += e.N > 0 ? 1 : 0;
-            if (e.n_deferred > 0) {
-                srk::launch_schur(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, e.unity, S, ld, rhs,
-                                  e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>());
-                e.launches += 1;
-            }
+            srk::SchurSink sink{S, ld, rhs, e.unity, nullptr, nullptr, 0, nullptr};
+            schur_accumulate(e, sink, c);
         }
         int rc = do_allreduce(e, S, (int64_t)ld * nf + ld);
         if (rc != SRK_OK) return rc;
@@ -417,16 +426,35 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
         }
         e.solver_used = SRK_SOLVER_DENSE_CHOLESKY;
     } else {
-        int rc = srk::pcg_schur_solve(e.pcg, st, e.N, e.O, M, e.unity, c, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), G, gf,
-                                      e.pinv.as<double>(), e.skipped.as<unsigned char>(), x, opt != nullptr ? opt->pcg_max_iters : 0,
-                                      opt != nullptr ? opt->pcg_rel_tol : 0.0, e.rank, e.world, e.ar, e.ar_user, &e.launches, &e.pcg_iters_last,
-                                      e.timing ? 1 : 0);
-        if (rc != SRK_OK) { set_error("pcg solve failed: " + std::string(cudaGetErrorString(cudaGetLastError()))); return rc; }
+        int rc = SRK_OK;
+        if (!e.pcg.structure_valid) {
+            rc = srk::pcg_build_structure(e.pcg, st, e.N, e.O, M, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(),
+                                          e.deferred.as<unsigned char>(), &e.launches);
+            if (rc != SRK_OK) { set_error("block-sparse structure of the reduced camera system could not be built (hash table overflow?)"); return rc; }
+        }
+        srk::SchurSink sink{};
+        {
+            Scope s(e, F_SCHUR);
+            rc = srk::pcg_begin(e.pcg, st, M, G, gf, c, e.unity, e.rank, &sink, &e.launches);
+            if (rc != SRK_OK) { set_error("pcg_begin failed"); return rc; }
+            schur_accumulate(e, sink, c);
+        }
+        {
+            Scope s(e, F_SOLVE);
+            double rel = 0.0;
+            rc = srk::pcg_solve(e.pcg, st, M, e.dfull.as<double>(), opt != nullptr ? opt->pcg_max_iters : 0, opt != nullptr ? opt->pcg_rel_tol : 0.0, e.world,
+                                e.ar, e.ar_user, &e.launches, &e.pcg_iters_last, &rel);
+            if (rc != SRK_OK) { set_error("pcg solve failed: " + std::string(cudaGetErrorString(cudaGetLastError()))); return rc; }
+        }
         e.solver_used = SRK_SOLVER_BLOCK_PCG;
     }
-    // allFinite(corrections_frame) (BA.cpp:1912-1913)
-    srk::launch_finite_flag(st, nf, x, e.flags.as<int>() + 1); e.launches += 1;
-    srk::launch_expand_df(st, M, x, e.unity, e.dfull.as<double>()); e.launches += 1;
+    // allFinite(corrections_frame) (BA.cpp:1912-1913); the PCG path solves directly in full frame-variable space
+    if (solver == SRK_SOLVER_DENSE_CHOLESKY) {
+        srk::launch_finite_flag(st, nf, x, e.flags.as<int>() + 1); e.launches += 1;
+        srk::launch_expand_df(st, M, x, e.unity, e.dfull.as<double>()); e.launches += 1;
+    } else {
+        srk::launch_finite_flag(st, 10 * (int64_t)M, e.dfull.as<double>(), e.flags.as<int>() + 1); e.launches += 1;
+    }
     {
         Scope s(e, F_BACKSUB);
         int64_t avg = e.N > 0 ? e.O / e.N : 0;
@@ -709,13 +737,19 @@ int srk_ba_reproj_error(void* h, const srk_ba_problem* problem, double* err, int
 
 int srk_ba_debug_derivs_and_solve(void* h, double c, double* gradE, double* E, double* G, double* Fblk, double* S, double* rhs,
                                   unsigned char* skipped, double* corrections) {
+    return srk_ba_debug_derivs_and_solve_ex(h, c, SRK_SOLVER_DENSE_CHOLESKY, gradE, E, G, Fblk, S, rhs, skipped, corrections, nullptr);
+}
+
+int srk_ba_debug_derivs_and_solve_ex(void* h, double c, int32_t solver, double* gradE, double* E, double* G, double* Fblk, double* S, double* rhs,
+                                     unsigned char* skipped, double* corrections, int32_t* pcg_iters) {
     if (h == nullptr) { set_error("null handle"); return SRK_E_INVALID_ARG; }
     Engine& e = *(Engine*)h;
     if (!e.bound) { set_error("debug call before srk_ba_bind"); return SRK_E_NOT_BOUND; }
     SRK_CUDA(cudaSetDevice(e.device));
     srk_ba_options opt; srk_ba_default_options(&opt);
-    opt.solver = SRK_SOLVER_DENSE_CHOLESKY;
-    int rc = ensure_solver_buffers(e, SRK_SOLVER_DENSE_CHOLESKY);
+    if (solver != SRK_SOLVER_BLOCK_PCG) solver = SRK_SOLVER_DENSE_CHOLESKY;
+    opt.solver = solver;
+    int rc = ensure_solver_buffers(e, SRK_SOLVER_DENSE_CHOLESKY);   // the dense buffers also receive the PCG system for inspection
     if (rc != SRK_OK) return rc;
     rc = derivative_pass(e);
     if (rc != SRK_OK) return rc;
@@ -736,11 +770,15 @@ int srk_ba_debug_derivs_and_solve(void* h, double c, double* gradE, double* E, d
     if (Fblk != nullptr && O > 0) SRK_CUDA(cudaMemcpyAsync(Fblk, dF, sizeof(double) * 30 * O, cudaMemcpyDeviceToHost, st));
     SRK_CUDA(cudaStreamSynchronize(st));
     if (c >= 0) {
-        rc = attempt(e, SRK_SOLVER_DENSE_CHOLESKY, &opt, c, ddp);
+        rc = attempt(e, solver, &opt, c, ddp);
         if (rc != SRK_OK) return rc;
         const int nf = e.nf; const int64_t ld = e.ld;
         double* dS = e.Srhs.as<double>();
-        if (opt.refine_steps <= 0) { srk::launch_mirror_lower(st, nf, dS, ld); e.launches += 1; }
+        if (solver == SRK_SOLVER_BLOCK_PCG) {
+            rc = srk::pcg_debug_to_dense(e.pcg, st, M, e.unity, dS, ld, dS + (size_t)ld * nf, &e.launches);
+            if (rc != SRK_OK) { set_error("pcg_debug_to_dense failed"); return rc; }
+            if (pcg_iters != nullptr) *pcg_iters = e.pcg_iters_last;
+        } else if (opt.refine_steps <= 0) { srk::launch_mirror_lower(st, nf, dS, ld); e.launches += 1; }
         if (S != nullptr) SRK_CUDA(cudaMemcpy2DAsync(S, sizeof(double) * nf, dS, sizeof(double) * ld, sizeof(double) * nf, nf, cudaMemcpyDeviceToHost, st));
         if (rhs != nullptr) SRK_CUDA(cudaMemcpyAsync(rhs, dS + (size_t)ld * nf, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
         if (skipped != nullptr && N > 0) SRK_CUDA(cudaMemcpyAsync(skipped, e.skipped.p, (size_t)N, cudaMemcpyDeviceToHost, st));

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "common.cuh"
 
 namespace srk {
 
@@ -13,11 +14,14 @@ void launch_frame_blocks(cudaStream_t st, int M, const int64_t* cam_begin, const
 void launch_residual(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
                      const double* X, int64_t N, const double* camd, double* partial, int nblocks, double* out);
 void launch_fill_reduced(cudaStream_t st, int M, const double* G, const double* gf, double c, int unity, double* S, int64_t ld, double* rhs);
-void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, int unity,
-                  double* S, int64_t ld, double* rhs, double* pinv, unsigned char* skipped, const unsigned char* only_flagged);
+struct SchurSink;   // common.cuh
+void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
+                  double* pinv, unsigned char* skipped, const unsigned char* only_flagged);
 // Tiled Schur accumulation (register-owned camera-pair blocks per tile of points); flags the points it leaves to launch_schur.
+// plan_only: structure pass -- deferred flags and (plan_keys != nullptr) the camera-pair hash of the block-sparse system.
 void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
-                       int unity, double* S, int64_t ld, double* rhs, double* pinv, unsigned char* skipped, unsigned char* deferred, int plan_only);
+                       const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred, int plan_only,
+                       unsigned long long* plan_keys, unsigned plan_mask, int* plan_overflow);
 void launch_backsub(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, const double* df,
                     const double* pinv, const unsigned char* skipped, const double* X, double* Xtry, double* dp_out, int lanes_per_point);
 void launch_cam_update(cudaStream_t st, int M, const double* cams, const double* df, double* cams_try);

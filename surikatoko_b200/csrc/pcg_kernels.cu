@@ -1,10 +1,363 @@
-// suriko-b200 — K3b placeholder: the matrix-free block-Jacobi PCG is not built yet; the entry point fails loudly.
+// suriko-b200 — K3b: block-sparse reduced camera system + block-Jacobi PCG (see pcg.h).
+#include <math.h>
+#include <stdio.h>
+#include "kernels.h"
 #include "pcg.h"
+#include "prep.h"
 
 namespace srk {
-int pcg_schur_solve(PcgWorkspace&, cudaStream_t, int64_t, int64_t, int, int, double, const int64_t*, const int32_t*, const double*, const double*,
-                    const double*, double*, unsigned char*, double*, int, double, int, int, srk_allreduce_fn, void*, int64_t*, int32_t*, int) {
-    return SRK_E_TOO_LARGE;
+
+namespace {
+
+template <class T>
+cudaError_t ensure(T*& p, size_t& cap, size_t count) {
+    if (p != nullptr && count <= cap) return cudaSuccess;
+    if (p != nullptr) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = count < 64 ? 64 : count;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
 }
-void pcg_release(PcgWorkspace&) {}
+inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- structure ----------------------------------------------------------------------------------------------------------
+__global__ void k_insert_diagonals(int M, unsigned long long* keys, unsigned mask, int* overflow) {
+    int cam = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cam >= M) return;
+    const unsigned long long key = ((unsigned long long)(unsigned)cam << 32) | (unsigned)cam;
+    unsigned h = hash_pair(key, mask);
+    for (unsigned probe = 0; probe <= mask; ++probe) {
+        const unsigned long long prev = atomicCAS(&keys[h], kHashEmpty, key);
+        if (prev == kHashEmpty || prev == key) return;
+        h = (h + 1) & mask;
+    }
+    atomicExch(overflow, 1);
+}
+__global__ void k_count_blocks(unsigned cap, const unsigned long long* __restrict__ keys, int* __restrict__ counter) {
+    unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned v = (s < cap && keys[s] != kHashEmpty) ? 1u : 0u;
+    unsigned b = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(counter, __popc(b));
+}
+// ids in slot order (deterministic given the table): exclusive scan over the occupancy, one CTA walking the table
+__global__ void k_assign_ids(unsigned cap, const unsigned long long* __restrict__ keys, int* __restrict__ ids, int* __restrict__ blk_cams,
+                             unsigned long long* __restrict__ row_cnt) {
+    __shared__ int warp_sums[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (unsigned base = 0; base < cap; base += 1024) {
+        const unsigned s = base + threadIdx.x;
+        const unsigned long long key = s < cap ? keys[s] : kHashEmpty;
+        const int occ = key != kHashEmpty ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, occ);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) warp_sums[w] = __popc(bal);
+        __syncthreads();
+        int off = carry;
+        for (int i = 0; i < w; ++i) off += warp_sums[i];
+        if (occ) {
+            const int id = off + __popc(bal & ((1u << lane) - 1));
+            ids[s] = id;
+            const int ci = (int)(key >> 32), cl = (int)(key & 0xffffffffu);
+            blk_cams[2 * id] = ci; blk_cams[2 * id + 1] = cl;
+            atomicAdd(&row_cnt[ci], 1ULL);
+            if (ci != cl) atomicAdd(&row_cnt[cl], 1ULL);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += warp_sums[i]; carry += t; }
+        __syncthreads();
+    }
+}
+__global__ void k_fill_rows(int nnzb, const int* __restrict__ blk_cams, unsigned long long* __restrict__ cursor, int* __restrict__ row_ent, int* __restrict__ diag_id) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nnzb) return;
+    const int ci = blk_cams[2 * id], cl = blk_cams[2 * id + 1];
+    unsigned long long pos = atomicAdd(&cursor[ci], 1ULL);
+    row_ent[2 * pos] = id; row_ent[2 * pos + 1] = cl;
+    if (ci != cl) {
+        pos = atomicAdd(&cursor[cl], 1ULL);
+        row_ent[2 * pos] = id | (1 << 30); row_ent[2 * pos + 1] = ci;
+    } else {
+        diag_id[ci] = id;
+    }
+}
+// fixed summation order of the mat-vec: every row's entries sorted by column camera
+__global__ void k_sort_rows(int M, const int64_t* __restrict__ row_ptr, int* __restrict__ row_ent) {
+    int cam = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cam >= M) return;
+    const int64_t b = row_ptr[cam], e = row_ptr[cam + 1];
+    for (int64_t i = b + 1; i < e; ++i) {
+        const int id = row_ent[2 * i], col = row_ent[2 * i + 1];
+        int64_t j = i - 1;
+        while (j >= b && row_ent[2 * j + 1] > col) { row_ent[2 * j + 2] = row_ent[2 * j]; row_ent[2 * j + 3] = row_ent[2 * j + 1]; --j; }
+        row_ent[2 * j + 2] = id; row_ent[2 * j + 3] = col;
+    }
+}
+
+// ---- values -------------------------------------------------------------------------------------------------------------
+// diagonal blocks <- damped G (fill_matG, BA.cpp:1780-1823) with the gauge variables turned into identity rows; rhs <- -g_f
+__global__ void k_bsr_fill_diag(int M, const double* __restrict__ G, const double* __restrict__ gf, double c, int unity, const int* __restrict__ diag_id,
+                                double* __restrict__ blocks, double* __restrict__ rhs) {
+    const int cam = blockIdx.x, t = threadIdx.x;
+    if (t < 100) {
+        const int a = t / 10, b = t % 10;
+        const bool ka = red_index(cam, a, unity) >= 0, kb = red_index(cam, b, unity) >= 0;
+        double v;
+        if (ka && kb) { v = G[(size_t)cam * 100 + t]; if (a == b) v *= 1.0 + c; }
+        else v = (a == b) ? 1.0 : 0.0;
+        blocks[(size_t)diag_id[cam] * 100 + t] = v;
+    } else if (t < 110) {
+        const int a = t - 100;
+        rhs[(size_t)cam * 10 + a] = red_index(cam, a, unity) >= 0 ? -gf[(size_t)cam * 10 + a] : 0.0;
+    }
+}
+__global__ void k_gather_diag(int M, const int* __restrict__ diag_id, const double* __restrict__ blocks, double* __restrict__ diag) {
+    const int cam = blockIdx.x, t = threadIdx.x;
+    if (t < 100) diag[(size_t)cam * 100 + t] = blocks[(size_t)diag_id[cam] * 100 + t];
+}
+// block-Jacobi preconditioner: in-place inverse of the (symmetric positive definite) 10x10 diagonal blocks, Gauss-Jordan
+__global__ void k_invert_diag(int M, double* __restrict__ diag) {
+    const int cam = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cam >= M) return;
+    double a[10][10], inv[10][10];
+    double* d = diag + (size_t)cam * 100;
+    for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) { a[i][j] = 0.5 * (d[i * 10 + j] + d[j * 10 + i]); inv[i][j] = i == j ? 1.0 : 0.0; }
+    for (int k = 0; k < 10; ++k) {
+        const double piv = 1.0 / a[k][k];
+        for (int j = 0; j < 10; ++j) { a[k][j] *= piv; inv[k][j] *= piv; }
+        for (int i = 0; i < 10; ++i) {
+            if (i == k) continue;
+            const double f = a[i][k];
+            for (int j = 0; j < 10; ++j) { a[i][j] -= f * a[k][j]; inv[i][j] -= f * inv[k][j]; }
+        }
+    }
+    for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) d[i * 10 + j] = inv[i][j];
+}
+
+// y = S v.  Ten threads per block row (camera), three rows per warp; thread a accumulates y[a] over the row's entries in column
+// order.  A stored block is row-major [10][10] = B(rows: larger camera, cols: smaller camera); the mirrored entry reads it transposed.
+__global__ void __launch_bounds__(128) k_bsr_spmv(int M, const int64_t* __restrict__ row_ptr, const int* __restrict__ row_ent, const double* __restrict__ blocks,
+                                                  const double* __restrict__ v, double* __restrict__ y) {
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sub = lane / 10, a = lane % 10;
+    const int cam = warp * 3 + sub;
+    if (sub >= 3 || cam >= M) return;
+    double acc = 0.0;
+    for (int64_t e = row_ptr[cam]; e < row_ptr[cam + 1]; ++e) {
+        const int ent = row_ent[2 * e], col = row_ent[2 * e + 1];
+        const double* B = blocks + (size_t)(ent & 0x3fffffff) * 100;
+        const double* vc = v + (size_t)col * 10;
+        if (ent & (1 << 30)) {
+#pragma unroll
+            for (int b = 0; b < 10; ++b) acc += B[b * 10 + a] * vc[b];
+        } else {
+#pragma unroll
+            for (int b = 0; b < 10; ++b) acc += B[a * 10 + b] * vc[b];
+        }
+    }
+    y[(size_t)cam * 10 + a] = acc;
+}
+
+// ---- the vector half of a PCG iteration, one CTA (fixed reduction order, device-resident scalars) -----------------------
+__device__ double block_sum(double v, double* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    return t;
+}
+// scal: [0] rz, [1] bb, [2] rr, [3] pAp
+__global__ void __launch_bounds__(1024) k_pcg_init(int n, const double* __restrict__ b, const double* __restrict__ Minv, double* __restrict__ x, double* __restrict__ r,
+                                                   double* __restrict__ z, double* __restrict__ p, double* __restrict__ scal) {
+    __shared__ double red[32];
+    double rz = 0.0, bb = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int cam = i / 10, a = i % 10;
+        const double* Mi = Minv + (size_t)cam * 100 + a * 10;
+        const double* bc = b + (size_t)cam * 10;
+        double zi = 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) zi += Mi[k] * bc[k];
+        const double bi = b[i];
+        x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi;
+        rz += bi * zi; bb += bi * bi;
+    }
+    rz = block_sum(rz, red); bb = block_sum(bb, red);
+    if (threadIdx.x == 0) { scal[0] = rz; scal[1] = bb; scal[2] = bb; scal[3] = 0.0; }
+}
+__global__ void __launch_bounds__(1024) k_pcg_step(int n, const double* __restrict__ Minv, const double* __restrict__ y, double* __restrict__ x, double* __restrict__ r,
+                                                   double* __restrict__ z, double* __restrict__ p, double* __restrict__ scal) {
+    __shared__ double red[32];
+    double pAp = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) pAp += p[i] * y[i];
+    pAp = block_sum(pAp, red);
+    const double rz = scal[0];
+    const double alpha = (pAp != 0.0) ? rz / pAp : 0.0;
+    double rr = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * y[i];
+        r[i] = ri; rr += ri * ri;
+    }
+    rr = block_sum(rr, red);   // also orders the writes of r before the preconditioner reads them
+    double rz_new = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int cam = i / 10, a = i % 10;
+        const double* Mi = Minv + (size_t)cam * 100 + a * 10;
+        const double* rc = r + (size_t)cam * 10;
+        double zi = 0.0;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) zi += Mi[k] * rc[k];
+        z[i] = zi; rz_new += r[i] * zi;
+    }
+    rz_new = block_sum(rz_new, red);
+    const double beta = (rz != 0.0) ? rz_new / rz : 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = z[i] + beta * p[i];
+    if (threadIdx.x == 0) { scal[0] = rz_new; scal[2] = rr; scal[3] = pAp; }
+}
+
+// parity hook: scatter the block-sparse system into the dense gauge-reduced layout
+__global__ void k_bsr_to_dense(int nnzb, const int* __restrict__ blk_cams, const double* __restrict__ blocks, int unity, double* __restrict__ S, int64_t ld) {
+    const int id = blockIdx.x, t = threadIdx.x;
+    if (id >= nnzb || t >= 100) return;
+    const int ci = blk_cams[2 * id], cl = blk_cams[2 * id + 1];
+    const int a = t / 10, b = t % 10;
+    const int row = red_index(ci, a, unity), col = red_index(cl, b, unity);
+    if (row < 0 || col < 0) return;
+    const double v = blocks[(size_t)id * 100 + t];
+    S[(size_t)col * ld + row] = v;
+    S[(size_t)row * ld + col] = v;
+}
+__global__ void k_full_to_reduced(int M, int unity, const double* __restrict__ full, double* __restrict__ red) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= M * 10) return;
+    const int r = red_index(t / 10, t % 10, unity);
+    if (r >= 0) red[r] = full[t];
+}
+
+}  // namespace
+
+#define PCG_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return SRK_E_CUDA; } while (0)
+
+int pcg_build_structure(PcgWorkspace& ws, cudaStream_t st, int64_t N, int64_t O, int M, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam,
+                        unsigned char* deferred, int64_t* launches) {
+    // capacity: a camera couples with at most a few dozen others in a localized scene; 64 slots per camera, power of two
+    size_t cap = 1024;
+    while (cap < (size_t)M * 64) cap <<= 1;
+    if (cap > ((size_t)1 << 30)) return SRK_E_TOO_LARGE;
+    PCG_CUDA(ensure(ws.hkeys, ws.hkeys_cap, cap)); PCG_CUDA(ensure(ws.hids, ws.hids_cap, cap));
+    PCG_CUDA(ensure(ws.cnt, ws.cnt_cap, (size_t)M + 2)); PCG_CUDA(ensure(ws.row_ptr, ws.row_ptr_cap, (size_t)M + 1));
+    PCG_CUDA(ensure(ws.diag_id, ws.diag_id_cap, (size_t)M));
+    if (ws.misc == nullptr) PCG_CUDA(cudaMalloc((void**)&ws.misc, sizeof(int) * 4));
+    if (ws.scal == nullptr) PCG_CUDA(cudaMalloc((void**)&ws.scal, sizeof(double) * 8));
+    if (ws.h_scal == nullptr) PCG_CUDA(cudaMallocHost((void**)&ws.h_scal, sizeof(double) * 8));
+    ws.hmask = (unsigned)(cap - 1);
+    PCG_CUDA(cudaMemsetAsync(ws.hkeys, 0xff, sizeof(unsigned long long) * cap, st));
+    PCG_CUDA(cudaMemsetAsync(ws.misc, 0, sizeof(int) * 4, st));
+    PCG_CUDA(cudaMemsetAsync(ws.cnt, 0, sizeof(unsigned long long) * ((size_t)M + 2), st));
+    k_insert_diagonals<<<cdiv(M, 256), 256, 0, st>>>(M, ws.hkeys, ws.hmask, ws.misc);
+    SchurSink none{};
+    launch_schur_tile(st, N, O, tile_points, pt_begin, obs_cam, nullptr, 0.0, none, nullptr, nullptr, deferred, 1, ws.hkeys, ws.hmask, ws.misc);
+    k_count_blocks<<<cdiv((int64_t)cap, 256), 256, 0, st>>>((unsigned)cap, ws.hkeys, ws.misc + 1);
+    *launches += 3;
+    int h[2] = {0, 0};
+    PCG_CUDA(cudaMemcpyAsync(h, ws.misc, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    PCG_CUDA(cudaStreamSynchronize(st));
+    if (h[0] != 0 || (size_t)h[1] * 10 > cap * 7) return SRK_E_TOO_LARGE;   // table overflow / load factor above 0.7
+    ws.nnzb = h[1];
+    PCG_CUDA(ensure(ws.blk_cams, ws.blk_cams_cap, (size_t)2 * ws.nnzb));
+    PCG_CUDA(ensure(ws.row_ent, ws.row_ent_cap, (size_t)4 * ws.nnzb));
+    PCG_CUDA(ensure(ws.blocks, ws.blocks_cap, (size_t)100 * ws.nnzb));
+    k_assign_ids<<<1, 1024, 0, st>>>((unsigned)cap, ws.hkeys, ws.hids, ws.blk_cams, ws.cnt);
+    launch_scan_counts(st, M, ws.cnt, ws.row_ptr, ws.cnt);   // cnt becomes the per-row cursor
+    k_fill_rows<<<cdiv(ws.nnzb, 256), 256, 0, st>>>(ws.nnzb, ws.blk_cams, ws.cnt, ws.row_ent, ws.diag_id);
+    k_sort_rows<<<cdiv(M, 128), 128, 0, st>>>(M, ws.row_ptr, ws.row_ent);
+    *launches += 4;
+    size_t nv = (size_t)M * 10;
+    if (ws.rhs == nullptr || ws.vec_cap < nv) {
+        if (ws.rhs != nullptr) cudaFree(ws.rhs);
+        ws.rhs = nullptr; ws.vec_cap = 0;
+        PCG_CUDA(cudaMalloc((void**)&ws.rhs, sizeof(double) * nv * 5));
+        ws.vec_cap = nv;
+    }
+    ws.r = ws.rhs + nv; ws.z = ws.r + nv; ws.p = ws.z + nv; ws.y = ws.p + nv;
+    PCG_CUDA(ensure(ws.diag, ws.diag_cap, (size_t)100 * M));
+    PCG_CUDA(cudaStreamSynchronize(st));
+    PCG_CUDA(cudaGetLastError());
+    ws.structure_valid = true;
+    return SRK_OK;
+}
+
+int pcg_begin(PcgWorkspace& ws, cudaStream_t st, int M, const double* G, const double* gf, double c, int unity, int rank, SchurSink* sink, int64_t* launches) {
+    if (!ws.structure_valid) return SRK_E_NOT_BOUND;
+    PCG_CUDA(cudaMemsetAsync(ws.blocks, 0, sizeof(double) * 100 * (size_t)ws.nnzb, st));
+    PCG_CUDA(cudaMemsetAsync(ws.rhs, 0, sizeof(double) * 10 * (size_t)M, st));
+    if (rank == 0) { k_bsr_fill_diag<<<M, 128, 0, st>>>(M, G, gf, c, unity, ws.diag_id, ws.blocks, ws.rhs); *launches += 1; }
+    sink->S = nullptr; sink->ld = 0; sink->rhs = ws.rhs; sink->unity = unity;
+    sink->hkeys = ws.hkeys; sink->hids = ws.hids; sink->hmask = ws.hmask; sink->blocks = ws.blocks;
+    return SRK_OK;
+}
+
+int pcg_solve(PcgWorkspace& ws, cudaStream_t st, int M, double* x, int max_iters, double rel_tol, int world, srk_allreduce_fn ar, void* ar_user,
+              int64_t* launches, int32_t* iters_out, double* rel_res_out) {
+    if (!ws.structure_valid) return SRK_E_NOT_BOUND;
+    const int n = M * 10;
+    if (max_iters <= 0) max_iters = 4 * n < 20000 ? 4 * n : 20000;
+    if (rel_tol <= 0.0) rel_tol = 1e-13;
+    const bool multi = ar != nullptr && world > 1;
+    if (multi && ar(ar_user, ws.rhs, n, (void*)st) != 0) return SRK_E_CUDA;
+    k_gather_diag<<<M, 128, 0, st>>>(M, ws.diag_id, ws.blocks, ws.diag);
+    if (multi && ar(ar_user, ws.diag, (int64_t)100 * M, (void*)st) != 0) return SRK_E_CUDA;
+    k_invert_diag<<<cdiv(M, 64), 64, 0, st>>>(M, ws.diag);
+    k_pcg_init<<<1, 1024, 0, st>>>(n, ws.rhs, ws.diag, x, ws.r, ws.z, ws.p, ws.scal);
+    *launches += 3;
+    const int check_every = 16;
+    int it = 0;
+    double rel = 1.0;
+    const double tol2 = rel_tol * rel_tol;
+    while (it < max_iters) {
+        const int batch = (max_iters - it) < check_every ? (max_iters - it) : check_every;
+        for (int k = 0; k < batch; ++k) {
+            k_bsr_spmv<<<cdiv((int64_t)((M + 2) / 3) * 32, 128), 128, 0, st>>>(M, ws.row_ptr, ws.row_ent, ws.blocks, ws.p, ws.y);
+            if (multi && ar(ar_user, ws.y, n, (void*)st) != 0) return SRK_E_CUDA;
+            k_pcg_step<<<1, 1024, 0, st>>>(n, ws.diag, ws.y, x, ws.r, ws.z, ws.p, ws.scal);
+        }
+        *launches += 2 * batch;
+        it += batch;
+        PCG_CUDA(cudaMemcpyAsync(ws.h_scal, ws.scal, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+        PCG_CUDA(cudaStreamSynchronize(st));
+        const double bb = ws.h_scal[1], rr = ws.h_scal[2];
+        if (!(bb > 0.0)) { rel = 0.0; break; }
+        rel = sqrt(rr / bb);
+        if (!(rr == rr) || rr <= tol2 * bb) break;   // NaN (breakdown) or converged
+    }
+    *iters_out = it;
+    if (rel_res_out != nullptr) *rel_res_out = rel;
+    PCG_CUDA(cudaGetLastError());
+    return SRK_OK;
+}
+
+int pcg_debug_to_dense(PcgWorkspace& ws, cudaStream_t st, int M, int unity, double* S, int64_t ld, double* rhs, int64_t* launches) {
+    if (!ws.structure_valid) return SRK_E_NOT_BOUND;
+    const int nf = M * 10 - 7;
+    PCG_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * (size_t)ld * nf, st));
+    k_bsr_to_dense<<<ws.nnzb, 128, 0, st>>>(ws.nnzb, ws.blk_cams, ws.blocks, unity, S, ld);
+    k_full_to_reduced<<<cdiv((int64_t)M * 10, 256), 256, 0, st>>>(M, unity, ws.rhs, rhs);
+    *launches += 2;
+    return SRK_OK;
+}
+
+void pcg_release(PcgWorkspace& ws) {
+    void* ptrs[] = {ws.hkeys, ws.hids, ws.blk_cams, ws.row_ptr, ws.row_ent, ws.diag_id, ws.cnt, ws.misc, ws.blocks, ws.rhs, ws.diag, ws.scal};
+    for (void* p : ptrs) if (p != nullptr) cudaFree(p);
+    if (ws.h_scal != nullptr) cudaFreeHost(ws.h_scal);
+    ws = PcgWorkspace();
+}
+
 }  // namespace srk

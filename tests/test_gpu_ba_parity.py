@@ -295,3 +295,39 @@ def test_python_mirror_of_reference_interface(oracle, engine):
     assert bak.PointsCount() == pr.n_points and bak.FramesCount() == pr.n_cams and bak.NormalizedVarsCount() == 3 * pr.n_points + 10 * pr.n_cams - 7
     rms = bak.ReprojErrorPixPerPoint(bak.last_report.err_final, bak.last_report.seen_points)
     assert abs(rms - pr.f0 * np.sqrt(flat.err_final / flat.seen_points)) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K3b: block-sparse reduced camera system + block-Jacobi PCG
+
+@pytest.mark.parametrize("name", ["ring", "dino", "ring_wide"])
+def test_pcg_system_and_solution_match_dense_path(oracle, engine, name):
+    import surikatoko_b200 as sb
+    prob = scene_by_name(name)
+    pr = as_oracle_problem(oracle, prob)
+    ref = oracle.derivs_and_solve(normalized_problem(oracle, pr), c=1e-2, flow="sparse", solve="chol", acc="ld")
+    assert engine.bind(to_problem(pr))
+    got = engine.debug_derivs_and_solve(c=1e-2, solver=sb.SOLVER_BLOCK_PCG)
+    assert got["pcg_iters"] > 0
+    assert np.array_equal(got["skipped"], ref["skipped"])
+    assert np.array_equal(got["S"] != 0, ref["S"] != 0), "sparsity structure of the block-sparse system differs"
+    assert relerr(got["S"], ref["S"]) < 1e-11
+    assert relerr(got["rhs"], ref["rhs"]) < 1e-10
+    N = pr.n_points
+    fixed = [3 * N + i for i in (4, 5, 6, 7, 8, 9, 15)]
+    assert np.all(got["corrections"][fixed] == 0.0)
+    q = normalized_problem(oracle, pr)
+    p2, c2 = oracle.apply_corrections(q.points, q.cams, ref["corrections"])
+    z = q.copy(); z.points = p2; z.cams = c2
+    e_ref, _ = oracle.reproj_error(z)
+    e_gpu = engine.debug_apply(got["corrections"])
+    assert abs(e_gpu - e_ref) <= 1e-7 * abs(e_ref)
+
+
+def test_pcg_lm_trajectory(oracle, engine):
+    import surikatoko_b200 as sb
+    prob = scene_by_name("ring")
+    pr = as_oracle_problem(oracle, prob)
+    ref, rep, out = run_pair(oracle, engine, pr, 1e-10, 4, solver=sb.SOLVER_BLOCK_PCG)
+    assert rep.solver_used == sb.SOLVER_BLOCK_PCG and rep.pcg_iters_last > 0
+    check_trajectory(ref, rep, pr, out, pr.f0)
