@@ -1,0 +1,60 @@
+/*
+ * suriko-b200 — C ABI of the MonoSLAM EKF dense covariance chain (north_star kernel 4, second half).
+ *
+ * Replaces the Eigen dense algebra of suriko-engine's Davison/Civera MonoSLAM ("EKF.cpp" =
+ * /root/reference/cpp_impl/suriko-engine/src/davison-mono-slam.cpp):
+ *   srk_ekf_predict*  : PredictEstimVars, covariance part                             EKF.cpp:669-693
+ *   srk_ekf_update*   : ProcessFrame_StackedObservationsPerUpdateCore                 EKF.cpp:977-1125
+ *                       (+ NormalizeCameraOrientationQuaternionAndCovariances :1652-1711, FixSymmetricMat :4308,
+ *                          EnsureNonnegativeStateVariance :1739-1750)
+ * The measurement Jacobian arrives in its sparse form: every observation row touches the 13 camera-state columns and the s
+ * columns of its own salient point (EKF.cpp:3115-3159); the reference multiplies the dense [2m x n] matrix instead.
+ * State layout (EKF.h): x = [cam pos 3 | cam quaternion 4 | velocity 3 | angular velocity 3 | s components per salient point ...],
+ * P is n x n column-major (Eigen default), n = 13 + s * salient points.
+ *
+ * Algebra used on the device (equal to the reference's in exact arithmetic):
+ *   PHt = P*H^T (sparse H) ; S = H*PHt + meas_var*I ; S = L*L^T ; Z = PHt*L^-T ; x += Z*(L^-1 (z - h)) ; P -= Z*Z^T.
+ * All functions return 0 on success or a negative SRK_E_* code (ba_c_api.h); srk_last_error() has the text.
+ */
+#ifndef SRK_EKF_C_API_H
+#define SRK_EKF_C_API_H
+
+#include <stdint.h>
+#include "ba_c_api.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+SRK_API int srk_ekf_create(void** h, int device);
+SRK_API void srk_ekf_destroy(void* h);
+SRK_API int srk_ekf_set_stream(void* h, void* cuda_stream);
+
+/* Resident state: covariance P [n*n] column-major and state x [n] live in HBM between calls. */
+SRK_API int srk_ekf_set_state(void* h, int64_t n, const double* P, const double* x);
+SRK_API int srk_ekf_get_state(void* h, double* P, double* x);
+
+/* Predict on the resident state: Pvv <- F*Pvv*F^T + GQGt, Pvm <- F*Pvm, Pmv <- Pvm^T (EKF.cpp:669-690); x[0..13) <- cam_state_new
+ * (the kinematic model itself, EKF.cpp:583-637, is 13 scalars of host code and stays with the caller).  F13, GQGt13: 13x13 column-major. */
+SRK_API int srk_ekf_predict_resident(void* h, const double* F13, const double* GQGt13, const double* cam_state_new);
+
+/* Stacked update on the resident state.  Hcam [2m x 13] and Hpt [2m x s] row-major per observation row, pt_off[m] = state index of
+ * the observed salient point, z / h_pred [2m] measured and projected pixels, R = meas_var * I (EKF.cpp:563-581).
+ * info (optional): 0 ok, >0 = 1-based index of the first non-positive pivot of the innovation covariance. */
+SRK_API int srk_ekf_update_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z,
+                                    const double* h_pred, double meas_var, int32_t* info);
+
+/* One-shot forms with host buffers (upload, operate, download). */
+SRK_API int srk_ekf_update(void* h, int64_t n, int64_t m, double* P, double* x, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s,
+                           const double* z, const double* h_pred, double meas_var);
+SRK_API int srk_ekf_predict(void* h, int64_t n, double* P, const double* F13, const double* GQGt13);
+
+/* Kernel-family timing (CUDA events on the handle's stream): "pht", "innov", "chol", "trsm", "syrk", "state", "predict". */
+SRK_API int srk_ekf_set_timing(void* h, int enabled);
+SRK_API int srk_ekf_get_timing(void* h, const char* name, double* ms_total, int64_t* count);
+SRK_API int64_t srk_ekf_launches(void* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRK_EKF_C_API_H */

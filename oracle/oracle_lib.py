@@ -235,3 +235,26 @@ def track_pushback_probe(frames, xy, n_frames):
     lib().srk_oracle_track_pushback_probe(_p(f, C.c_int32), _p(p, C.c_double), C.c_int(len(f)), C.c_int(n_frames), _p(has, C.c_int32),
                                           _p(out, C.c_double))
     return has, out
+
+
+# ---- MonoSLAM EKF dense chain (EKF.cpp:639-694, :977-1125) -------------------------------------------------------------
+def ekf_update(P, x, Hcam, Hpt, pt_off, z, hpred, meas_var, fix_symmetry=True):
+    """Reference-style dense stacked update on copies.  Returns (ok, P_new, x_new, seconds)."""
+    Pn = np.asfortranarray(np.array(P, dtype=np.float64)); xn = np.array(x, dtype=np.float64)
+    n = xn.shape[0]; m = len(pt_off); s = Hpt.shape[1]
+    Hc = np.ascontiguousarray(Hcam, dtype=np.float64); Hp = np.ascontiguousarray(Hpt, dtype=np.float64)
+    off = np.ascontiguousarray(pt_off, dtype=np.int64)
+    zz = np.ascontiguousarray(z, dtype=np.float64); hh = np.ascontiguousarray(hpred, dtype=np.float64)
+    sec = C.c_double()
+    rc = lib().srk_oracle_ekf_update(C.c_int64(n), C.c_int64(m), Pn.ctypes.data_as(C.POINTER(C.c_double)), _p(xn, C.c_double), _p(Hc, C.c_double),
+                                     _p(Hp, C.c_double), _p(off, C.c_int64), C.c_int(s), _p(zz, C.c_double), _p(hh, C.c_double), C.c_double(meas_var),
+                                     C.c_int(1 if fix_symmetry else 0), C.byref(sec))
+    return rc == 0, np.array(Pn), xn, sec.value
+
+
+def ekf_predict(P, F13, GQGt13, fix_symmetry=True):
+    Pn = np.asfortranarray(np.array(P, dtype=np.float64))
+    F = np.asfortranarray(np.array(F13, dtype=np.float64)); Q = np.asfortranarray(np.array(GQGt13, dtype=np.float64))
+    lib().srk_oracle_ekf_predict(C.c_int64(Pn.shape[0]), Pn.ctypes.data_as(C.POINTER(C.c_double)), F.ctypes.data_as(C.POINTER(C.c_double)),
+                                 Q.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(1 if fix_symmetry else 0))
+    return np.array(Pn)

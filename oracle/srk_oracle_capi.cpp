@@ -8,6 +8,7 @@
 #include <cstring>
 #include "srk_oracle_ba.hpp"
 #include "srk_oracle_scene.hpp"
+#include "srk_oracle_ekf.hpp"
 
 using namespace srk_oracle;
 
@@ -293,6 +294,37 @@ int srk_oracle_track_pushback_probe(const int32_t* frames, const double* xy, int
         has[f] = c.has_value() ? 1 : 0;
         if (c.has_value()) { out_xy[2 * f] = c.value()[0]; out_xy[2 * f + 1] = c.value()[1]; }
     }
+    return 0;
+}
+
+// MonoSLAM EKF dense chain.  H is given in the sparse form of the C ABI (Hcam [2m x 13] and Hpt [2m x s], both row-major per
+// observation row, pt_off[m] = first state index of the observed point) and expanded into the dense [2m x n] matrix the reference
+// multiplies.  P [n x n] column-major and x [n] are updated in place.  Returns 0, or 1 if S is singular.
+int srk_oracle_ekf_update(int64_t n, int64_t m, double* P, double* x, const double* Hcam, const double* Hpt, const int64_t* pt_off, int s,
+                          const double* z, const double* hpred, double meas_var, int fix_symmetry, double* seconds) {
+    EkfMat Pm((size_t)n, (size_t)n);
+    std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);
+    std::vector<double> xs(x, x + n), zs(z, z + 2 * m), hs(hpred, hpred + 2 * m);
+    EkfMat H((size_t)(2 * m), (size_t)n);
+    for (int64_t i = 0; i < m; ++i)
+        for (int k = 0; k < 2; ++k) {
+            size_t row = (size_t)(2 * i + k);
+            for (int c = 0; c < 13; ++c) H(row, (size_t)c) = Hcam[row * 13 + c];
+            for (int c = 0; c < s; ++c) H(row, (size_t)(pt_off[i] + c)) = Hpt[row * s + c];
+        }
+    auto t0 = std::chrono::steady_clock::now();
+    bool ok = EkfStackedUpdate(&xs, &Pm, H, zs, hs, meas_var, fix_symmetry != 0);
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    std::memcpy(P, Pm.d.data(), sizeof(double) * (size_t)n * (size_t)n);
+    std::memcpy(x, xs.data(), sizeof(double) * (size_t)n);
+    return ok ? 0 : 1;
+}
+int srk_oracle_ekf_predict(int64_t n, double* P, const double* F13, const double* GQGt13, int fix_symmetry) {
+    EkfMat Pm((size_t)n, (size_t)n);
+    std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);
+    EkfPredictCovariance(&Pm, F13, GQGt13, fix_symmetry != 0);
+    std::memcpy(P, Pm.d.data(), sizeof(double) * (size_t)n * (size_t)n);
     return 0;
 }
 

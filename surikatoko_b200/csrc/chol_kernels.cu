@@ -598,6 +598,134 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
 int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 0); }
 int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 1); }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// General C -= A * B^T on DMMA (the TRSM and covariance updates of the EKF chain).  Same pipeline as k_syrk_dmma: operands are
+// read in [k][row] order straight from the column-major matrices, 128x128 tiles, persistent CTAs over the tile list.
+__global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int K, const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                                                         double* __restrict__ C, int64_t ldc, int lower_only) {
+    constexpr int TILE = 128, SLD = TILE + 4, NJ = 8;
+    extern __shared__ double sm[];
+    double* sA = sm;
+    double* sB = sm + STAGES * KC * SLD;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tm = (m + TILE - 1) / TILE, tn = (n + TILE - 1) / TILE;
+    const int nk = (K + KC - 1) / KC;
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 64;
+    const int g = lane >> 2, tg = lane & 3;
+    for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
+        const int ti = t % tm, tj = t / tm;
+        const int i0 = ti * TILE, j0 = tj * TILE;
+        if (lower_only && i0 + TILE - 1 < j0) continue;
+        auto load_chunk = [&](int stage, int kc) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int v = tid + 256 * q;
+                const int k = v >> 6, rp = (v & 63) * 2;
+                const int kk = kc * KC + k;
+                {
+                    const int row = i0 + rp;
+                    int bytes = (kk < K) ? (m - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+                    cp_async16(sA + (stage * KC + k) * SLD + rp, A + (bytes > 0 ? (size_t)kk * lda + row : 0), bytes);
+                }
+                {
+                    const int row = j0 + rp;
+                    int bytes = (kk < K) ? (n - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+                    cp_async16(sB + (stage * KC + k) * SLD + rp, B + (bytes > 0 ? (size_t)kk * ldb + row : 0), bytes);
+                }
+            }
+        };
+        load_chunk(0, 0); cp_async_commit();
+        if (nk > 1) load_chunk(1, 1);
+        cp_async_commit();
+        double acc[4][NJ][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int kc = 0; kc < nk; ++kc) {
+            cp_async_wait<1>();
+            __syncthreads();
+            if (kc + 2 < nk) load_chunk((kc + 2) % STAGES, kc + 2);
+            cp_async_commit();
+            const double* cA = sA + (kc % STAGES) * KC * SLD;
+            const double* cB = sB + (kc % STAGES) * KC * SLD;
+#pragma unroll
+            for (int ks = 0; ks < KC; ks += 4) {
+                double af[4], bf[NJ];
+                const double* pa = cA + (ks + tg) * SLD + wr + g;
+                const double* pb = cB + (ks + tg) * SLD + wc + g;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] = pa[i * 8];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) bf[j] = pb[j * 8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int row = i0 + wr + i * 8 + g;
+                const int col = j0 + wc + j * 8 + tg * 2;
+                if (row < m) {
+                    if (col < n && (!lower_only || row >= col)) C[(size_t)col * ldc + row] -= acc[i][j][0];
+                    if (col + 1 < n && (!lower_only || row >= col + 1)) C[(size_t)(col + 1) * ldc + row] -= acc[i][j][1];
+                }
+            }
+    }
+}
+// the operands need 16-byte aligned columns: lda, ldb even and base pointers 16-byte aligned (the callers guarantee it)
+void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only) {
+    set_attrs_once();
+    static bool attr = false;
+    const size_t smem = sizeof(double) * (2 * STAGES * KC * (128 + 4));
+    if (!attr) { cudaFuncSetAttribute(k_gemm_nt_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    if (m <= 0 || n <= 0 || K <= 0) return;
+    const int tiles = ((m + 127) / 128) * ((n + 127) / 128);
+    k_gemm_nt_dmma<<<tiles < g_sms ? tiles : g_sms, 256, smem, st>>>(m, n, K, A, lda, B, ldb, C, ldc, lower_only);
+}
+
+// X <- X * Linv^T on an (rows x 64) block column: X(r,c) = sum_{q<=c} X(r,q) * Linv(c,q).
+__global__ void __launch_bounds__(256) k_block_right_solve(int rows, double* __restrict__ A, int64_t lda, const double* __restrict__ dinv) {
+    extern __shared__ double sm[];
+    double* sLi = sm;                    // sLi[q*NB + c] = Linv(c, q)
+    double* sA = sm + NB * NB;           // sA[q*PS_ROWS + r]
+    const int tid = threadIdx.x;
+    const int r0 = blockIdx.x * PS_ROWS;
+    for (int e = tid; e < NB * NB; e += 256) sLi[e] = dinv[e];   // dinv[q*NB + c] = Linv(c, q) (column q)
+    for (int e = tid; e < NB * PS_ROWS; e += 256) {
+        const int q = e / PS_ROWS, r = e % PS_ROWS;
+        sA[e] = (r0 + r < rows) ? A[(size_t)q * lda + r0 + r] : 0.0;
+    }
+    __syncthreads();
+    const int r = tid & (PS_ROWS - 1), cbase = (tid >> 7) * 32;
+    double acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+    for (int q = 0; q < cbase + 32; ++q) {
+        const double a = sA[q * PS_ROWS + r];
+        const double* li = sLi + q * NB + cbase;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] += a * li[i];
+    }
+    if (r0 + r < rows) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) A[(size_t)(cbase + i) * lda + r0 + r] = acc[i];
+    }
+}
+void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block) {
+    set_attrs_once();
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_block_right_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSolveSmem); attr = true; }
+    if (rows > 0) k_block_right_solve<<<(rows + PS_ROWS - 1) / PS_ROWS, 256, kPanelSolveSmem, st>>>(rows, A, lda, dinv_block);
+}
+
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld) {
     int T = (n + 31) / 32;
     k_mirror_lower<<<dim3(T, T), 256, 0, st>>>(n, A, ld);

@@ -1,0 +1,459 @@
+// suriko-b200 — MonoSLAM EKF dense covariance chain on sm_100a behind include/srk/ekf_c_api.h.
+//
+// Replaces the Eigen algebra of ProcessFrame_StackedObservationsPerUpdateCore (EKF.cpp:977-1125) and PredictEstimVars
+// (EKF.cpp:669-693), EKF.cpp = /root/reference/cpp_impl/suriko-engine/src/davison-mono-slam.cpp.  Device algorithm:
+//   k_ekf_pht      PHt = P * H^T with the SPARSE H (13 camera columns + s point columns per observation row)        [n x 2m]
+//   k_ekf_innov    S = H * PHt + meas_var * I, lower triangle                                                       [2m x 2m]
+//   chol_kernels   S = L L^T (DMMA blocked Cholesky, inverted 64x64 diagonal blocks)
+//   TRSM           Z = PHt * L^-T, block column by block column: 64-wide right solve + DMMA update of the columns to the right
+//   k_ekf_state    x += Z * (L^-1 (z - h))
+//   k_gemm_nt_dmma P -= Z * Z^T on the lower triangle (n x n x 2m DMMA), then mirrored
+//   k_ekf_quat_*   quaternion renormalisation of x and of the 4 rows / columns of P (EKF.cpp:1652-1711)
+//   k_ekf_nonneg_* rows / columns with a negative variance are zeroed (EKF.cpp:1739-1750)
+//   k_ekf_predict* Pvv <- F Pvv F^T + G Q G^T, Pvm <- F Pvm, Pmv <- Pvm^T
+// K = PHt S^-1 is never formed: K S K^T = Z Z^T and K (z - h) = Z L^-1 (z - h).
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/srk/ekf_c_api.h"
+#include "kernels.h"
+
+extern "C" void srk_internal_set_error(const char* s);   // engine.cu: the string behind srk_last_error()
+
+namespace {
+
+constexpr int kCam = 13;   // camera-state components (EKF.h kCamStateComps)
+
+// PHt(r, j) = sum_c P(r, c) Hcam(j, c) + sum_c P(r, off_j + c) Hpt(j, c).  Threads along r (coalesced columns of P), 8 observation
+// rows per CTA share the 13 camera columns through registers.
+template <int S>
+__global__ void __launch_bounds__(256) k_ekf_pht(int n, int m2, const double* __restrict__ P, const double* __restrict__ Hcam, const double* __restrict__ Hpt,
+                                                 const int64_t* __restrict__ pt_off, double* __restrict__ PHt, int64_t ldz) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j0 = blockIdx.y * 8;
+    if (r >= n) return;
+    double pc[kCam];
+#pragma unroll
+    for (int c = 0; c < kCam; ++c) pc[c] = P[(size_t)c * n + r];
+    for (int j = j0; j < j0 + 8 && j < m2; ++j) {
+        const double* hc = Hcam + (size_t)j * kCam;
+        const double* hp = Hpt + (size_t)j * S;
+        const int64_t off = pt_off[j >> 1];
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < kCam; ++c) acc += pc[c] * hc[c];
+#pragma unroll
+        for (int c = 0; c < S; ++c) acc += P[(size_t)(off + c) * n + r] * hp[c];
+        PHt[(size_t)j * ldz + r] = acc;
+    }
+}
+// S(i, j) = sum_c Hcam(i, c) PHt(c, j) + sum_c Hpt(i, c) PHt(off_i + c, j) + meas_var [i == j], lower triangle (i >= j), ld = lds
+template <int S>
+__global__ void __launch_bounds__(256) k_ekf_innov(int n, int m2, const double* __restrict__ PHt, const double* __restrict__ Hcam, const double* __restrict__ Hpt,
+                                                   const int64_t* __restrict__ pt_off, double meas_var, double* __restrict__ Sm, int64_t lds, int64_t ldz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (i >= m2 || i < j) return;
+    const double* col = PHt + (size_t)j * ldz;
+    const double* hc = Hcam + (size_t)i * kCam;
+    const double* hp = Hpt + (size_t)i * S;
+    const int64_t off = pt_off[i >> 1];
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < kCam; ++c) acc += hc[c] * col[c];
+#pragma unroll
+    for (int c = 0; c < S; ++c) acc += hp[c] * col[off + c];
+    if (i == j) acc += meas_var;
+    Sm[(size_t)j * lds + i] = acc;
+}
+__global__ void k_ekf_innovation_vec(int m2, const double* __restrict__ z, const double* __restrict__ h, double* __restrict__ w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m2) w[i] = z[i] - h[i];
+}
+// x += Z w  (Z: n x m2 column-major); one warp per 32 rows, columns strided over the CTA's warps, fixed combination order
+__global__ void __launch_bounds__(256) k_ekf_state(int n, int m2, const double* __restrict__ Z, int64_t ldz, const double* __restrict__ w, double* __restrict__ x) {
+    __shared__ double part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * 32 + lane;
+    double acc = 0.0;
+    if (r < n) for (int j = warp; j < m2; j += 8) acc += Z[(size_t)j * ldz + r] * w[j];
+    part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && r < n) {
+        double s = 0.0;
+        for (int k = 0; k < 8; ++k) s += part[k][lane];
+        x[r] += s;
+    }
+}
+
+// Quaternion renormalisation (EKF.cpp:1652-1711).  Step 1 (one CTA): decide (IsClose(1, |q|)), normalise x[3..7), build dq (4x4) into
+// aux[0..16), flag into aux[16]; step 2: new column block  Cnew(r, j) = sum_k P(r, 3+k) dq(j, k)  for r outside 3..6 and the centre
+// dq P44 dq^T, into tmp [n x 4]; step 3: write the four columns and rows back.
+__global__ void k_ekf_quat_prepare(double* __restrict__ x, double* __restrict__ aux) {
+    if (threadIdx.x != 0) return;
+    const double q[4] = {x[3], x[4], x[5], x[6]};
+    const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const double len = sqrt(n2);
+    const bool close = fabs(1.0 - len) <= (1.0e-8 + 1.0e-5 * fabs(fmax(1.0, len)));   // approx-alg.h:7-16
+    aux[16] = close ? 0.0 : 1.0;
+    if (close) return;
+    for (int i = 0; i < 4; ++i) x[3 + i] = q[i] / len;
+    const double mult = pow(n2, (double)-1.5f);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double v;
+            if (i == j) { v = 0.0; for (int k = 0; k < 4; ++k) if (k != i) v += q[k] * q[k]; }
+            else v = -q[i] * q[j];
+            aux[i * 4 + j] = v * mult;
+        }
+}
+__global__ void k_ekf_quat_columns(int n, const double* __restrict__ P, const double* __restrict__ aux, double* __restrict__ tmp) {
+    if (aux[16] == 0.0) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double p[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) p[k] = P[(size_t)(3 + k) * n + r];
+    if (r >= 3 && r < 7) {   // centre: dq * P44 * dq^T, row r-3
+        double t[4];
+        for (int c = 0; c < 4; ++c) { double s = 0.0; for (int k = 0; k < 4; ++k) s += aux[(r - 3) * 4 + k] * P[(size_t)(3 + c) * n + 3 + k]; t[c] = s; }
+        for (int j = 0; j < 4; ++j) { double s = 0.0; for (int k = 0; k < 4; ++k) s += t[k] * aux[j * 4 + k]; tmp[(size_t)j * n + r] = s; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmp[(size_t)j * n + r] = (p[0] * aux[j * 4 + 0] + p[1] * aux[j * 4 + 1]) + (p[2] * aux[j * 4 + 2] + p[3] * aux[j * 4 + 3]);
+    }
+}
+__global__ void k_ekf_quat_write(int n, double* __restrict__ P, const double* __restrict__ aux, const double* __restrict__ tmp) {
+    if (aux[16] == 0.0) return;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double v = tmp[(size_t)j * n + r];
+        P[(size_t)(3 + j) * n + r] = v;           // column 3+j
+        if (r < 3 || r >= 7) P[(size_t)r * n + 3 + j] = v;   // row 3+j (mirror); the centre block is written once, as columns
+    }
+}
+// EnsureNonnegativeStateVariance (EKF.cpp:1739-1750)
+__global__ void k_ekf_nonneg_flag(int n, const double* __restrict__ P, unsigned char* __restrict__ neg, int* __restrict__ any) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const bool bad = !(P[(size_t)i * n + i] >= 0.0);
+    neg[i] = bad ? 1 : 0;
+    if (bad) atomicOr(any, 1);
+}
+__global__ void k_ekf_nonneg_zero(int n, double* __restrict__ P, const unsigned char* __restrict__ neg, const int* __restrict__ any) {
+    if (*any == 0) return;
+    const int c = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (neg[c] || neg[r]) P[(size_t)c * n + r] = 0.0;
+}
+// Predict: one CTA computes Pvv_new (13x13) into aux; a grid computes Pvm_new = F * Pvm column by column and mirrors it.
+__global__ void k_ekf_predict_vv(int n, const double* __restrict__ P, const double* __restrict__ F, const double* __restrict__ Q, double* __restrict__ out) {
+    __shared__ double FP[kCam][kCam];
+    const int t = threadIdx.x;
+    if (t < kCam * kCam) {
+        const int i = t % kCam, j = t / kCam;
+        double s = 0.0;
+        for (int k = 0; k < kCam; ++k) s += F[(size_t)k * kCam + i] * P[(size_t)j * n + k];   // (F Pvv)(i, j)
+        FP[i][j] = s;
+    }
+    __syncthreads();
+    if (t < kCam * kCam) {
+        const int i = t % kCam, j = t / kCam;
+        double s = 0.0;
+        for (int k = 0; k < kCam; ++k) s += FP[i][k] * F[(size_t)k * kCam + j];               // (F Pvv F^T)(i, j) = sum_k FP(i,k) F(j,k)
+        out[(size_t)j * kCam + i] = s + Q[(size_t)j * kCam + i];
+    }
+}
+__global__ void k_ekf_predict_vm(int n, double* __restrict__ P, const double* __restrict__ F, const double* __restrict__ vv_new, const double* __restrict__ cam_new,
+                                 double* __restrict__ x) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;   // column of P
+    if (c >= n) return;
+    if (c < kCam) {
+        for (int i = 0; i < kCam; ++i) P[(size_t)c * n + i] = vv_new[(size_t)c * kCam + i];
+        if (cam_new != nullptr) x[c] = cam_new[c];
+        return;
+    }
+    double col[kCam], res[kCam];
+#pragma unroll
+    for (int k = 0; k < kCam; ++k) col[k] = P[(size_t)c * n + k];
+#pragma unroll
+    for (int i = 0; i < kCam; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < kCam; ++k) s += F[(size_t)k * kCam + i] * col[k];
+        res[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < kCam; ++i) { P[(size_t)c * n + i] = res[i]; P[(size_t)i * n + c] = res[i]; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct ErrSink { ErrSink& operator=(const std::string& s) { srk_internal_set_error(s.c_str()); return *this; } ErrSink& operator=(const char* s) { srk_internal_set_error(s); return *this; } };
+ErrSink g_ekf_error;
+#define EKF_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { g_ekf_error = std::string(#call) + ": " + cudaGetErrorString(e__); return SRK_E_CUDA; } } while (0)
+
+struct DBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (p != nullptr && bytes <= cap) return cudaSuccess;
+        if (p != nullptr) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes < 256 ? 256 : bytes;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+const char* kEkfFam[] = {"pht", "innov", "chol", "trsm", "syrk", "state", "predict"};
+enum { E_PHT = 0, E_INNOV, E_CHOL, E_TRSM, E_SYRK, E_STATE, E_PREDICT, E_COUNT };
+
+struct Ekf {
+    int device = 0;
+    cudaStream_t own = nullptr, st = nullptr;
+    int64_t n = 0;
+    DBuf P, x, PHt, S, ws, w, Hcam, Hpt, off, z, h, aux, tmp, neg, info, small;
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<cudaEvent_t> pend[E_COUNT];
+    double total[E_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    int64_t count[E_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+};
+struct EScope {
+    Ekf& e; int f; cudaEvent_t b = nullptr;
+    EScope(Ekf& ek, int fam) : e(ek), f(fam) {
+        if (!e.timing) return;
+        cudaEvent_t a; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, e.st);
+        e.pend[f].push_back(a); e.pend[f].push_back(b);
+    }
+    ~EScope() { if (b != nullptr) cudaEventRecord(b, e.st); }
+};
+void ekf_resolve(Ekf& e) {
+    cudaStreamSynchronize(e.st);
+    for (int f = 0; f < E_COUNT; ++f) {
+        for (size_t i = 0; i + 1 < e.pend[f].size(); i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, e.pend[f][i], e.pend[f][i + 1]) == cudaSuccess) { e.total[f] += ms; e.count[f] += 1; }
+            cudaEventDestroy(e.pend[f][i]); cudaEventDestroy(e.pend[f][i + 1]);
+        }
+        e.pend[f].clear();
+    }
+}
+
+int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int s, const double* z, const double* hpred, double meas_var,
+                    int32_t* info_out) {
+    if (e.n <= 0) { g_ekf_error = "srk_ekf_update_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
+    if (m <= 0 || Hcam == nullptr || Hpt == nullptr || pt_off == nullptr || z == nullptr || hpred == nullptr || (s != 3 && s != 6)) {
+        g_ekf_error = "bad update arguments (s must be 3 or 6)"; return SRK_E_INVALID_ARG;
+    }
+    for (int64_t i = 0; i < m; ++i) if (pt_off[i] < kCam || pt_off[i] + s > e.n) { g_ekf_error = "salient point offset out of range"; return SRK_E_INVALID_ARG; }
+    EKF_CUDA(cudaSetDevice(e.device));
+    const int n = (int)e.n, m2 = (int)(2 * m);
+    const int64_t lds = ((int64_t)m2 + 7) & ~(int64_t)7;
+    const int64_t ldz = ((int64_t)n + 7) & ~(int64_t)7;   // 16-byte aligned columns for the cp.async operand loads
+    cudaStream_t st = e.st;
+    EKF_CUDA(e.PHt.ensure(sizeof(double) * (size_t)ldz * m2 + 64)); EKF_CUDA(e.S.ensure(sizeof(double) * (size_t)lds * m2));
+    EKF_CUDA(e.ws.ensure(sizeof(double) * srk::dense_cholesky_dinv_doubles(m2))); EKF_CUDA(e.w.ensure(sizeof(double) * (size_t)lds));
+    EKF_CUDA(e.Hcam.ensure(sizeof(double) * (size_t)m2 * kCam)); EKF_CUDA(e.Hpt.ensure(sizeof(double) * (size_t)m2 * s));
+    EKF_CUDA(e.off.ensure(sizeof(int64_t) * (size_t)m)); EKF_CUDA(e.z.ensure(sizeof(double) * m2)); EKF_CUDA(e.h.ensure(sizeof(double) * m2));
+    EKF_CUDA(e.aux.ensure(sizeof(double) * 32)); EKF_CUDA(e.tmp.ensure(sizeof(double) * 4 * (size_t)n)); EKF_CUDA(e.neg.ensure((size_t)n));
+    EKF_CUDA(e.info.ensure(sizeof(int) * 4));
+    EKF_CUDA(cudaMemcpyAsync(e.Hcam.p, Hcam, sizeof(double) * (size_t)m2 * kCam, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.Hpt.p, Hpt, sizeof(double) * (size_t)m2 * s, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.off.p, pt_off, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.z.p, z, sizeof(double) * m2, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.h.p, hpred, sizeof(double) * m2, cudaMemcpyHostToDevice, st));
+    double* P = e.P.as<double>(); double* PHt = e.PHt.as<double>(); double* S = e.S.as<double>(); double* ws = e.ws.as<double>();
+    {
+        EScope sc(e, E_PHT);
+        dim3 grid((n + 255) / 256, (m2 + 7) / 8);
+        if (s == 3) k_ekf_pht<3><<<grid, 256, 0, st>>>(n, m2, P, e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(), PHt, ldz);
+        else k_ekf_pht<6><<<grid, 256, 0, st>>>(n, m2, P, e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(), PHt, ldz);
+        e.launches += 1;
+    }
+    {
+        EScope sc(e, E_INNOV);
+        EKF_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * (size_t)lds * m2, st));
+        dim3 grid((m2 + 255) / 256, m2);
+        if (s == 3) k_ekf_innov<3><<<grid, 256, 0, st>>>(n, m2, PHt, e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(), meas_var, S, lds, ldz);
+        else k_ekf_innov<6><<<grid, 256, 0, st>>>(n, m2, PHt, e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(), meas_var, S, lds, ldz);
+        e.launches += 1;
+    }
+    {
+        EScope sc(e, E_CHOL);
+        e.launches += srk::dense_cholesky_factor(st, m2, S, lds, ws, e.info.as<int>());
+    }
+    {   // Z = PHt * L^-T, right-looking over 64-column blocks; Z overwrites PHt
+        EScope sc(e, E_TRSM);
+        const int nblk = (m2 + 63) / 64;
+        for (int kb = 0; kb < nblk; ++kb) {
+            const int k0 = kb * 64;
+            srk::launch_block_right_solve(st, n, PHt + (size_t)k0 * ldz, ldz, srk::dense_cholesky_dinv_block(ws, kb));
+            e.launches += 1;
+            const int rest = m2 - (k0 + 64);
+            if (rest > 0) {
+                const int kw = m2 - k0 < 64 ? m2 - k0 : 64;
+                // PHt[:, k0+64:] -= Z_k (n x 64) * L[k0+64:, k0:k0+64]^T
+                srk::launch_gemm_nt_dmma(st, n, rest, kw, PHt + (size_t)k0 * ldz, ldz, S + (size_t)k0 * lds + k0 + 64, lds, PHt + (size_t)(k0 + 64) * ldz, ldz, 0);
+                e.launches += 1;
+            }
+        }
+    }
+    {
+        EScope sc(e, E_STATE);
+        k_ekf_innovation_vec<<<(m2 + 255) / 256, 256, 0, st>>>(m2, e.z.as<double>(), e.h.as<double>(), e.w.as<double>());
+        e.launches += 1;
+        e.launches += srk::dense_cholesky_forward(st, m2, S, lds, ws, e.w.as<double>());
+        k_ekf_state<<<(n + 31) / 32, 256, 0, st>>>(n, m2, PHt, ldz, e.w.as<double>(), e.x.as<double>());
+        e.launches += 1;
+    }
+    {
+        EScope sc(e, E_SYRK);
+        srk::launch_gemm_nt_dmma(st, n, n, m2, PHt, ldz, PHt, ldz, P, n, 1);
+        srk::launch_mirror_lower(st, n, P, n);
+        e.launches += 2;
+    }
+    {
+        EScope sc(e, E_STATE);
+        k_ekf_quat_prepare<<<1, 32, 0, st>>>(e.x.as<double>(), e.aux.as<double>());
+        k_ekf_quat_columns<<<(n + 255) / 256, 256, 0, st>>>(n, P, e.aux.as<double>(), e.tmp.as<double>());
+        k_ekf_quat_write<<<(n + 255) / 256, 256, 0, st>>>(n, P, e.aux.as<double>(), e.tmp.as<double>());
+        EKF_CUDA(cudaMemsetAsync(e.info.as<int>() + 1, 0, sizeof(int), st));
+        k_ekf_nonneg_flag<<<(n + 255) / 256, 256, 0, st>>>(n, P, e.neg.as<unsigned char>(), e.info.as<int>() + 1);
+        k_ekf_nonneg_zero<<<dim3((n + 255) / 256, n), 256, 0, st>>>(n, P, e.neg.as<unsigned char>(), e.info.as<int>() + 1);
+        e.launches += 5;
+    }
+    int hinfo = 0;
+    EKF_CUDA(cudaMemcpyAsync(&hinfo, e.info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    EKF_CUDA(cudaStreamSynchronize(st));
+    EKF_CUDA(cudaGetLastError());
+    if (info_out != nullptr) *info_out = hinfo;
+    return SRK_OK;
+}
+
+int predict_resident(Ekf& e, const double* F13, const double* GQGt13, const double* cam_new) {
+    if (e.n <= 0) { g_ekf_error = "srk_ekf_predict_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
+    if (F13 == nullptr || GQGt13 == nullptr) { g_ekf_error = "null F / GQGt"; return SRK_E_INVALID_ARG; }
+    EKF_CUDA(cudaSetDevice(e.device));
+    const int n = (int)e.n;
+    EKF_CUDA(e.small.ensure(sizeof(double) * (3 * kCam * kCam + kCam)));
+    double* dF = e.small.as<double>(); double* dQ = dF + kCam * kCam; double* dVV = dQ + kCam * kCam; double* dCam = dVV + kCam * kCam;
+    EKF_CUDA(cudaMemcpyAsync(dF, F13, sizeof(double) * kCam * kCam, cudaMemcpyHostToDevice, e.st));
+    EKF_CUDA(cudaMemcpyAsync(dQ, GQGt13, sizeof(double) * kCam * kCam, cudaMemcpyHostToDevice, e.st));
+    if (cam_new != nullptr) EKF_CUDA(cudaMemcpyAsync(dCam, cam_new, sizeof(double) * kCam, cudaMemcpyHostToDevice, e.st));
+    EScope sc(e, E_PREDICT);
+    k_ekf_predict_vv<<<1, 192, 0, e.st>>>(n, e.P.as<double>(), dF, dQ, dVV);
+    k_ekf_predict_vm<<<(n + 127) / 128, 128, 0, e.st>>>(n, e.P.as<double>(), dF, dVV, cam_new != nullptr ? dCam : nullptr, e.x.as<double>());
+    e.launches += 2;
+    return SRK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int srk_ekf_create(void** h, int device) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    *h = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) { cudaGetLastError(); g_ekf_error = "no CUDA device (there is no CPU fallback)"; return SRK_E_NO_DEVICE; }
+    if (device < 0 || device >= count) { g_ekf_error = "device id out of range"; return SRK_E_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) { g_ekf_error = "this library holds sm_100a code only"; return SRK_E_NO_DEVICE; }
+    cudaSetDevice(device);
+    Ekf* e = new Ekf();
+    e->device = device;
+    if (cudaStreamCreateWithFlags(&e->own, cudaStreamNonBlocking) != cudaSuccess) { delete e; return SRK_E_CUDA; }
+    e->st = e->own;
+    *h = e;
+    return SRK_OK;
+}
+void srk_ekf_destroy(void* h) {
+    if (h == nullptr) return;
+    Ekf* e = (Ekf*)h;
+    cudaSetDevice(e->device);
+    ekf_resolve(*e);
+    DBuf* bufs[] = {&e->P, &e->x, &e->PHt, &e->S, &e->ws, &e->w, &e->Hcam, &e->Hpt, &e->off, &e->z, &e->h, &e->aux, &e->tmp, &e->neg, &e->info, &e->small};
+    for (DBuf* b : bufs) if (b->p != nullptr) cudaFree(b->p);
+    if (e->own != nullptr) cudaStreamDestroy(e->own);
+    delete e;
+}
+int srk_ekf_set_stream(void* h, void* cuda_stream) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    Ekf* e = (Ekf*)h;
+    cudaStreamSynchronize(e->st);
+    e->st = cuda_stream != nullptr ? (cudaStream_t)cuda_stream : e->own;
+    return SRK_OK;
+}
+int srk_ekf_set_state(void* h, int64_t n, const double* P, const double* x) {
+    if (h == nullptr || P == nullptr || x == nullptr || n < kCam || n > 60000) { g_ekf_error = "bad state arguments"; return SRK_E_INVALID_ARG; }
+    Ekf& e = *(Ekf*)h;
+    EKF_CUDA(cudaSetDevice(e.device));
+    EKF_CUDA(e.P.ensure(sizeof(double) * (size_t)n * n + 64)); EKF_CUDA(e.x.ensure(sizeof(double) * (size_t)n));
+    EKF_CUDA(cudaMemcpyAsync(e.P.p, P, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice, e.st));
+    EKF_CUDA(cudaMemcpyAsync(e.x.p, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, e.st));
+    EKF_CUDA(cudaStreamSynchronize(e.st));
+    e.n = n;
+    return SRK_OK;
+}
+int srk_ekf_get_state(void* h, double* P, double* x) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    Ekf& e = *(Ekf*)h;
+    if (e.n <= 0) { g_ekf_error = "no resident state"; return SRK_E_NOT_BOUND; }
+    EKF_CUDA(cudaSetDevice(e.device));
+    if (P != nullptr) EKF_CUDA(cudaMemcpyAsync(P, e.P.p, sizeof(double) * (size_t)e.n * e.n, cudaMemcpyDeviceToHost, e.st));
+    if (x != nullptr) EKF_CUDA(cudaMemcpyAsync(x, e.x.p, sizeof(double) * (size_t)e.n, cudaMemcpyDeviceToHost, e.st));
+    EKF_CUDA(cudaStreamSynchronize(e.st));
+    return SRK_OK;
+}
+int srk_ekf_predict_resident(void* h, const double* F13, const double* GQGt13, const double* cam_state_new) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    return predict_resident(*(Ekf*)h, F13, GQGt13, cam_state_new);
+}
+int srk_ekf_update_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z, const double* h_pred,
+                            double meas_var, int32_t* info) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    return update_resident(*(Ekf*)h, m, Hcam, Hpt, pt_off, s, z, h_pred, meas_var, info);
+}
+int srk_ekf_update(void* h, int64_t n, int64_t m, double* P, double* x, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z,
+                   const double* h_pred, double meas_var) {
+    int rc = srk_ekf_set_state(h, n, P, x);
+    if (rc != SRK_OK) return rc;
+    int32_t info = 0;
+    rc = srk_ekf_update_resident(h, m, Hcam, Hpt, pt_off, s, z, h_pred, meas_var, &info);
+    if (rc != SRK_OK) return rc;
+    return srk_ekf_get_state(h, P, x);
+}
+int srk_ekf_predict(void* h, int64_t n, double* P, const double* F13, const double* GQGt13) {
+    if (h == nullptr || P == nullptr) return SRK_E_INVALID_ARG;
+    std::vector<double> x((size_t)n, 0.0);
+    int rc = srk_ekf_set_state(h, n, P, x.data());
+    if (rc != SRK_OK) return rc;
+    rc = srk_ekf_predict_resident(h, F13, GQGt13, nullptr);
+    if (rc != SRK_OK) return rc;
+    return srk_ekf_get_state(h, P, nullptr);
+}
+int srk_ekf_set_timing(void* h, int enabled) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    Ekf& e = *(Ekf*)h;
+    ekf_resolve(e);
+    e.timing = enabled != 0;
+    for (int f = 0; f < E_COUNT; ++f) { e.total[f] = 0; e.count[f] = 0; }
+    return SRK_OK;
+}
+int srk_ekf_get_timing(void* h, const char* name, double* ms_total, int64_t* count) {
+    if (h == nullptr || name == nullptr) return SRK_E_INVALID_ARG;
+    Ekf& e = *(Ekf*)h;
+    ekf_resolve(e);
+    for (int f = 0; f < E_COUNT; ++f)
+        if (std::strcmp(name, kEkfFam[f]) == 0) { if (ms_total) *ms_total = e.total[f]; if (count) *count = e.count[f]; return SRK_OK; }
+    return SRK_E_INVALID_ARG;
+}
+int64_t srk_ekf_launches(void* h) { return h == nullptr ? 0 : ((Ekf*)h)->launches; }
+
+}  // extern "C"

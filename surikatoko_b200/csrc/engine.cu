@@ -604,6 +604,7 @@ int fetch_impl(Engine& e, srk_ba_problem* p) {
 extern "C" {
 
 int srk_abi_version(void) { return 1; }
+void srk_internal_set_error(const char* s) { g_last_error = s != nullptr ? s : ""; }
 const char* srk_last_error(void) { return g_last_error.c_str(); }
 
 void srk_ba_default_options(srk_ba_options* o) {

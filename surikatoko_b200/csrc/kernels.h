@@ -38,6 +38,12 @@ void launch_debug_F_blocks(cudaStream_t st, int64_t O, const double* J, double* 
 // first non-positive pivot (0 = success).  All return launch counts.
 size_t dense_cholesky_dinv_doubles(int n);
 void dense_cholesky_profile_report();
+// column-major 64x64 inverse of the kb-th diagonal block of L inside the workspace
+inline const double* dense_cholesky_dinv_block(const double* ws, int kb) { return ws + (size_t)kb * 64 * 64; }
+// C (m x n, ldc) -= A (m x K, lda) * B (n x K, ldb)^T, all column-major, DMMA 128x128 tiles; lower_only: only tiles / entries with row >= col.
+void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only);
+// X (rows x 64 at A, lda) <- X * Linv^T with Linv a column-major 64x64 lower-triangular inverse (right-side triangular solve of one block column)
+void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block);
 int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev);
 int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
 int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);

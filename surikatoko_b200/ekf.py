@@ -1,0 +1,168 @@
+"""ctypes binding of the MonoSLAM EKF dense covariance chain (include/srk/ekf_c_api.h) and a synthetic scenario generator.
+
+Mirrors the reference's DavisonMonoSlam members on this path: PredictEstimVars (covariance part, EKF.cpp:669-693) and
+ProcessFrame_StackedObservationsPerUpdateCore (EKF.cpp:977-1125).  No CPU fallback.
+"""
+import ctypes as C
+
+import numpy as np
+
+from .capi import SrkError, load_library
+
+CAM = 13
+EKF_FAMILIES = ("pht", "innov", "chol", "trsm", "syrk", "state", "predict")
+
+
+def _lib():
+    L = load_library()
+    if not getattr(L, "_ekf_ready", False):
+        L.srk_ekf_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.srk_ekf_destroy.argtypes = [C.c_void_p]; L.srk_ekf_destroy.restype = None
+        L.srk_ekf_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.srk_ekf_set_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.srk_ekf_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.srk_ekf_predict_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.srk_ekf_update_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double,
+                                              C.POINTER(C.c_int32)]
+        L.srk_ekf_update.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                     C.c_void_p, C.c_double]
+        L.srk_ekf_predict.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.srk_ekf_set_timing.argtypes = [C.c_void_p, C.c_int]
+        L.srk_ekf_get_timing.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        L.srk_ekf_launches.argtypes = [C.c_void_p]; L.srk_ekf_launches.restype = C.c_int64
+        L._ekf_ready = True
+    return L
+
+
+def _chk(rc):
+    if rc < 0:
+        raise SrkError(rc, load_library().srk_last_error().decode())
+    return rc
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class EkfEngine:
+    def __init__(self, device=0):
+        self._L = _lib()
+        self._h = C.c_void_p()
+        _chk(self._L.srk_ekf_create(C.byref(self._h), device))
+        self.n = 0
+
+    def close(self):
+        if self._h:
+            self._L.srk_ekf_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        _chk(self._L.srk_ekf_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def set_state(self, P, x):
+        P = np.asfortranarray(P, dtype=np.float64); x = np.ascontiguousarray(x, dtype=np.float64)
+        self.n = x.shape[0]
+        _chk(self._L.srk_ekf_set_state(self._h, self.n, C.c_void_p(P.ctypes.data), _p(x)))
+
+    def get_state(self):
+        P = np.zeros((self.n, self.n), order="F"); x = np.zeros(self.n)
+        _chk(self._L.srk_ekf_get_state(self._h, C.c_void_p(P.ctypes.data), _p(x)))
+        return P, x
+
+    def predict(self, F13, GQGt13, cam_state_new=None):
+        F = np.asfortranarray(F13, dtype=np.float64); Q = np.asfortranarray(GQGt13, dtype=np.float64)
+        cs = None if cam_state_new is None else np.ascontiguousarray(cam_state_new, dtype=np.float64)
+        _chk(self._L.srk_ekf_predict_resident(self._h, C.c_void_p(F.ctypes.data), C.c_void_p(Q.ctypes.data), _p(cs)))
+
+    def update(self, Hcam, Hpt, pt_off, z, h_pred, meas_var):
+        Hc = np.ascontiguousarray(Hcam, dtype=np.float64); Hp = np.ascontiguousarray(Hpt, dtype=np.float64)
+        off = np.ascontiguousarray(pt_off, dtype=np.int64)
+        zz = np.ascontiguousarray(z, dtype=np.float64); hh = np.ascontiguousarray(h_pred, dtype=np.float64)
+        info = C.c_int32(0)
+        _chk(self._L.srk_ekf_update_resident(self._h, off.shape[0], _p(Hc), _p(Hp), _p(off), Hp.shape[1], _p(zz), _p(hh), float(meas_var), C.byref(info)))
+        return info.value
+
+    def update_host(self, P, x, Hcam, Hpt, pt_off, z, h_pred, meas_var):
+        """One-shot srk_ekf_update with host buffers; P (Fortran order) and x are updated in place."""
+        off = np.ascontiguousarray(pt_off, dtype=np.int64)
+        _chk(self._L.srk_ekf_update(self._h, x.shape[0], off.shape[0], C.c_void_p(P.ctypes.data), _p(x), _p(Hcam), _p(Hpt), _p(off), Hpt.shape[1], _p(z),
+                                    _p(h_pred), float(meas_var)))
+
+    def set_timing(self, on):
+        _chk(self._L.srk_ekf_set_timing(self._h, 1 if on else 0))
+
+    def get_timing(self):
+        out = {}
+        for f in EKF_FAMILIES:
+            t, c = C.c_double(), C.c_int64()
+            _chk(self._L.srk_ekf_get_timing(self._h, f.encode(), C.byref(t), C.byref(c)))
+            out[f] = dict(ms_total=t.value, count=c.value)
+        return out
+
+    def launches(self):
+        return int(self._L.srk_ekf_launches(self._h))
+
+
+def _quat_to_R(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def synthetic_ekf_frame(n_points=2000, s=3, seed=1234, cov_rank=24, pix_sigma=1.0):
+    """One MonoSLAM frame of the configs[3] shape: a camera (pos, quaternion, velocities) in front of a wall of
+    `n_points` XYZ salient points (s = 3) or 6-component inverse-depth points (s = 6, the extra components enter H with the same
+    sparsity), all observed; H = d(pinhole projection)/d(state) with the velocity columns structurally zero (EKF.cpp:2755-2816).
+    Returns dict(P, x, Hcam, Hpt, pt_off, z, h, meas_var, F, GQGt)."""
+    rng = np.random.default_rng(seed)
+    n = CAM + s * n_points
+    x = np.zeros(n)
+    x[0:3] = [0.1, -0.05, 0.0]
+    q = np.array([0.995, 0.02, -0.03, 0.01]); x[3:7] = q / np.linalg.norm(q) * 1.0004   # slightly off unit: the normalisation branch runs
+    x[7:13] = rng.normal(0, 0.01, 6)
+    g = int(np.ceil(np.sqrt(n_points)))
+    gx, gy = np.meshgrid(np.linspace(-1.5, 1.5, g), np.linspace(-1.5, -0.4 + 1.1, g))
+    pts = np.stack([gx.ravel()[:n_points], gy.ravel()[:n_points], 7.0 + 0.3 * rng.normal(size=n_points)], axis=1)
+    off = CAM + s * np.arange(n_points, dtype=np.int64)
+    for c in range(3):
+        x[off + c] = pts[:, c]
+    if s == 6:
+        x[off[:, None] + np.arange(3, 6)] = rng.normal(0, 0.1, (n_points, 3))
+    fpx = np.array([195.0, 195.0]); c0 = np.array([160.0, 120.0])
+
+    def project(xs):
+        R = _quat_to_R(xs[3:7] / np.linalg.norm(xs[3:7]))
+        X = np.stack([xs[off], xs[off + 1], xs[off + 2]], axis=1)
+        if s == 6:
+            X = X + 0.05 * np.stack([xs[off + 3], xs[off + 4], xs[off + 5]], axis=1)
+        Xc = (X - xs[0:3]) @ R       # R^T (X - pos)
+        return (fpx * Xc[:, :2] / Xc[:, 2:3] + c0)
+
+    h = project(x)
+    eps = 1e-6
+    Hcam = np.zeros((2 * n_points, CAM)); Hpt = np.zeros((2 * n_points, s))
+    for c in range(7):                # velocity / angular-velocity columns stay zero
+        d = np.zeros(n); d[c] = eps
+        Hcam[:, c] = ((project(x + d) - project(x - d)) / (2 * eps)).reshape(-1)
+    for c in range(s):
+        d = np.zeros(n); d[off + c] = eps
+        Hpt[:, c] = ((project(x + d) - project(x - d)) / (2 * eps)).reshape(-1)
+    z = (h + rng.normal(0, pix_sigma, h.shape)).reshape(-1)
+    # covariance: point-wise variances + a low-rank camera/point coupling, symmetric positive definite
+    U = rng.normal(0, 0.02, (n, cov_rank)); U[:CAM] *= 3.0
+    P = np.asfortranarray(U @ U.T)
+    P[np.diag_indices(n)] += np.concatenate([np.full(CAM, 1e-3), np.full(n - CAM, 2.5e-3)])
+    dt = 1.0 / 30
+    F = np.eye(CAM); F[0:3, 7:10] = dt * np.eye(3)
+    F[3:7, 10:13] = 0.5 * dt * rng.normal(0, 1, (4, 3)); F[3:7, 3:7] += 0.01 * rng.normal(0, 1, (4, 4))
+    Gm = np.zeros((CAM, 6)); Gm[0:3, 0:3] = dt * np.eye(3); Gm[7:10, 0:3] = np.eye(3); Gm[10:13, 3:6] = np.eye(3); Gm[3:7, 3:6] = 0.5 * dt * rng.normal(0, 1, (4, 3))
+    Q = np.diag([0.15 ** 2] * 3 + [0.01 ** 2] * 3)
+    return dict(P=P, x=x, Hcam=Hcam, Hpt=Hpt, pt_off=off, z=z, h=h.reshape(-1), meas_var=pix_sigma ** 2, F=np.asfortranarray(F),
+                GQGt=np.asfortranarray(Gm @ Q @ Gm.T), n=n, m=n_points, s=s)

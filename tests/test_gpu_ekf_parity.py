@@ -1,0 +1,86 @@
+"""GPU parity of the MonoSLAM EKF dense covariance chain against the CPU oracle's reference-style dense update
+(oracle/srk_oracle_ekf.hpp: H*P, S, partial-pivot LU inverse, K, P - K S K^T).  Tolerance: 1e-9 relative to the largest entry
+(FP64; the two paths differ algebraically: Cholesky / TRSM / SYRK here, explicit inverse there)."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ekf():
+    from surikatoko_b200.ekf import EkfEngine
+    e = EkfEngine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("npts,s", [(40, 3), (150, 3), (70, 6), (333, 3)])
+def test_stacked_update_matches_reference_algebra(oracle, ekf, npts, s):
+    from surikatoko_b200.ekf import synthetic_ekf_frame
+    fr = synthetic_ekf_frame(npts, s, seed=3 + npts)
+    ok, P_ref, x_ref, _ = oracle.ekf_update(fr["P"], fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+    assert ok
+    ekf.set_state(fr["P"], fr["x"])
+    info = ekf.update(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+    assert info == 0
+    P, x = ekf.get_state()
+    assert relerr(x, x_ref) < 1e-9
+    assert relerr(P, P_ref) < 1e-9
+    assert np.array_equal(P, P.T), "the updated covariance must be exactly symmetric"
+    assert abs(np.linalg.norm(x[3:7]) - 1.0) < 1e-12          # quaternion renormalised (EKF.cpp:1652-1711)
+    assert np.all(np.diag(P) >= 0)
+    assert ekf.launches() > 0
+
+
+def test_update_subset_of_points_and_one_shot_host_form(oracle, ekf):
+    from surikatoko_b200.ekf import synthetic_ekf_frame
+    fr = synthetic_ekf_frame(120, 3, seed=8)
+    sel = np.arange(0, 120, 3)                                  # only a third of the salient points are matched in this frame
+    rows = np.stack([2 * sel, 2 * sel + 1], axis=1).reshape(-1)
+    args = (fr["Hcam"][rows], fr["Hpt"][rows], fr["pt_off"][sel], fr["z"][rows], fr["h"][rows], fr["meas_var"])
+    ok, P_ref, x_ref, _ = oracle.ekf_update(fr["P"], fr["x"], *args)
+    P = np.asfortranarray(fr["P"].copy()); x = fr["x"].copy()
+    ekf.update_host(P, x, *[np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a for a in args])
+    assert relerr(x, x_ref) < 1e-9 and relerr(P, P_ref) < 1e-9
+
+
+def test_predict_matches_reference(oracle, ekf):
+    from surikatoko_b200.ekf import synthetic_ekf_frame
+    fr = synthetic_ekf_frame(90, 3, seed=5)
+    P_ref = oracle.ekf_predict(fr["P"], fr["F"], fr["GQGt"])
+    ekf.set_state(fr["P"], fr["x"])
+    cam_new = fr["x"][:13] + 0.01
+    ekf.predict(fr["F"], fr["GQGt"], cam_new)
+    P, x = ekf.get_state()
+    assert relerr(P, P_ref) < 1e-13
+    assert np.array_equal(P, P.T)
+    assert np.array_equal(x[:13], cam_new) and np.array_equal(x[13:], fr["x"][13:])
+    assert np.array_equal(P[13:, 13:], fr["P"][13:, 13:]), "Pmm is unchanged by the prediction"
+
+
+def test_negative_variance_rows_are_zeroed(oracle, ekf):
+    from surikatoko_b200.ekf import synthetic_ekf_frame
+    fr = synthetic_ekf_frame(30, 3, seed=6)
+    P0 = fr["P"].copy()
+    k = 13 + 3 * 7 + 1
+    P0[k, k] = -1e-3                                            # EnsureNonnegativeStateVariance (EKF.cpp:1739-1750)
+    ok, P_ref, x_ref, _ = oracle.ekf_update(P0, fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+    ekf.set_state(P0, fr["x"])
+    ekf.update(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+    P, x = ekf.get_state()
+    if P_ref[k, k] == 0.0:
+        assert np.all(P[k, :] == 0) and np.all(P[:, k] == 0)
+    assert relerr(P, P_ref) < 1e-8
+
+
+def test_bad_arguments_fail_loudly(ekf):
+    import surikatoko_b200 as sb
+    from surikatoko_b200.ekf import synthetic_ekf_frame
+    fr = synthetic_ekf_frame(10, 3, seed=1)
+    ekf.set_state(fr["P"], fr["x"])
+    bad = fr["pt_off"].copy(); bad[0] = 5                       # inside the camera block
+    with pytest.raises(sb.SrkError):
+        ekf.update(fr["Hcam"], fr["Hpt"], bad, fr["z"], fr["h"], fr["meas_var"])
