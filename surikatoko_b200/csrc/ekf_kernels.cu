@@ -131,7 +131,8 @@ __global__ void k_ekf_quat_write(int n, double* __restrict__ P, const double* __
     if (r >= n) return;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const double v = tmp[(size_t)j * n + r];
+        double v = tmp[(size_t)j * n + r];
+        if (r >= 3 && r < 7) v = 0.5 * (v + tmp[(size_t)(r - 3) * n + 3 + j]);   // centre block: (M + M^T)/2 as FixSymmetricMat does (EKF.cpp:4308)
         P[(size_t)(3 + j) * n + r] = v;           // column 3+j
         if (r < 3 || r >= 7) P[(size_t)r * n + 3 + j] = v;   // row 3+j (mirror); the centre block is written once, as columns
     }
@@ -154,6 +155,7 @@ __global__ void k_ekf_nonneg_zero(int n, double* __restrict__ P, const unsigned 
 // Predict: one CTA computes Pvv_new (13x13) into aux; a grid computes Pvm_new = F * Pvm column by column and mirrors it.
 __global__ void k_ekf_predict_vv(int n, const double* __restrict__ P, const double* __restrict__ F, const double* __restrict__ Q, double* __restrict__ out) {
     __shared__ double FP[kCam][kCam];
+    __shared__ double R2[kCam][kCam];
     const int t = threadIdx.x;
     if (t < kCam * kCam) {
         const int i = t % kCam, j = t / kCam;
@@ -166,7 +168,12 @@ __global__ void k_ekf_predict_vv(int n, const double* __restrict__ P, const doub
         const int i = t % kCam, j = t / kCam;
         double s = 0.0;
         for (int k = 0; k < kCam; ++k) s += FP[i][k] * F[(size_t)k * kCam + j];               // (F Pvv F^T)(i, j) = sum_k FP(i,k) F(j,k)
-        out[(size_t)j * kCam + i] = s + Q[(size_t)j * kCam + i];
+        R2[i][j] = s + Q[(size_t)j * kCam + i];
+    }
+    __syncthreads();
+    if (t < kCam * kCam) {   // exactly symmetric result, as FixSymmetricMat leaves it (EKF.cpp:692-693)
+        const int i = t % kCam, j = t / kCam;
+        out[(size_t)j * kCam + i] = 0.5 * (R2[i][j] + R2[j][i]);
     }
 }
 __global__ void k_ekf_predict_vm(int n, double* __restrict__ P, const double* __restrict__ F, const double* __restrict__ vv_new, const double* __restrict__ cam_new,
