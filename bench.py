@@ -33,9 +33,10 @@ WORKLOADS = {
     "c5": (10_000, 5_000_000, 10, "synthetic city-scale BA: 10,000 cameras x 5M points x 50M observations, PCG solve (configs[4])"),
     "tiny": (40, 4000, 8, "tiny ring scene (smoke)"),
     "c3s": (1000, 50_000, 10, "profiling aid: the 1,000-camera reduced system of configs[2] with 50k points"),
+    "c4": (0, 2000, 0, "Davison MonoSLAM EKF with 2,000 salient points: dense 6013x6013 covariance predict + stacked update per frame (configs[3])"),
 }
 # bounded CPU sample of each workload (same generator, fewer cameras/points so the oracle finishes in ~10-30 s)
-CPU_SAMPLES = {"c3": (100, 100_000, 10), "c2": (50, 2_000, 50), "c5": (100, 100_000, 10), "tiny": (40, 4000, 8), "c3s": (100, 100_000, 10)}
+CPU_SAMPLES = {"c3": (100, 100_000, 10), "c2": (50, 2_000, 50), "c5": (100, 100_000, 10), "tiny": (40, 4000, 8), "c3s": (100, 100_000, 10), "c4": (0, 250, 0)}
 METRIC = "BA reprojection residuals/sec through full LM iterations"
 UNIT = "residuals/s"
 
@@ -287,6 +288,88 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_ekf(args):
+    """configs[3]: one step = one MonoSLAM frame (covariance predict + stacked update of all 2000 observed points) on the resident state."""
+    import torch
+    from surikatoko_b200.ekf import EkfEngine, synthetic_ekf_frame
+    rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    npts = WORKLOADS["c4"][1]
+    fr = synthetic_ekf_frame(npts, 3, seed=1234 + rank)
+    n, m2 = fr["n"], 2 * fr["m"]
+    stream = torch.cuda.Stream(device=dev)
+    eng = EkfEngine(local); eng.set_stream(stream.cuda_stream)
+    args_u = (fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+    with torch.cuda.stream(stream):
+        eng.set_state(fr["P"], fr["x"])
+        for _ in range(args.warmup):
+            eng.predict(fr["F"], fr["GQGt"], fr["x"][:13]); eng.update(*args_u)
+        torch.cuda.synchronize()
+        eng.set_state(fr["P"], fr["x"])
+        eng.set_timing(True)
+        l0 = eng.launches()
+        clocks = ClockSampler(local); clocks.start()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            eng.predict(fr["F"], fr["GQGt"], fr["x"][:13]); info = eng.update(*args_u)
+        e1.record(stream); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clk = clocks.stop()
+        tm = eng.get_timing(); eng.set_timing(False)
+        launches = eng.launches() - l0
+        # e2e: one-shot host form, P travels both ways
+        P = torch.from_numpy(np.asfortranarray(fr["P"]).T.copy()).pin_memory().numpy().T   # Fortran-ordered view of pinned memory
+        x = fr["x"].copy()
+        e2e_steps = max(1, min(args.steps, 3))
+        for i in range(1 + e2e_steps):
+            P[:, :] = fr["P"]; x[:] = fr["x"]
+            if i == 1:
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+            eng.update_host(P, x, *[np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a for a in args_u])
+        torch.cuda.synchronize()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+    if rank != 0:
+        return
+    f64_peak = fp64_gemm_peak(torch, dev)
+    flops = {"chol": m2 ** 3 / 3.0, "trsm": float(n) * m2 * m2, "syrk": float(n) * n * m2}   # SURVEY.md 8d: the algorithmic minimum of the chain
+    kernels = {}
+    for fam, t in tm.items():
+        if not t["count"]:
+            continue
+        avg = t["ms_total"] / t["count"]
+        kernels[fam] = {"avg_ms": avg, "launch_groups": t["count"], "share_of_step": t["ms_total"] / ms}
+        if fam in flops:
+            ach = flops[fam] / (avg * 1e-3) / 1e12
+            kernels[fam].update({"bound": "tensor", "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s", "frac": ach / f64_peak})
+    dom = max((f for f in kernels if "frac" in kernels[f]), key=lambda f: kernels[f]["share_of_step"])
+    cpu = None
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_lib as ol
+        ol.build()
+        sm = synthetic_ekf_frame(CPU_SAMPLES["c4"][1], 3, seed=1234)
+        ok, _, _, sec = ol.ekf_update(sm["P"], sm["x"], sm["Hcam"], sm["Hpt"], sm["pt_off"], sm["z"], sm["h"], sm["meas_var"])
+        cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": "stacked update with %d salient points (n = %d, 2m = %d): the reference's dense H*P, LU inverse, K, P - K S K^T chain, one thread; "
+                         "its cost grows ~cubically with the point count" % (sm["m"], sm["n"], 2 * sm["m"])}
+    out = {"metric": "MonoSLAM EKF frames/sec (covariance predict + stacked update)", "value": args.steps / (ms * 1e-3) * world, "unit": "frames/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic",
+           "config": {"workload": WORKLOADS["c4"][3], "n_state": n, "n_observed": fr["m"], "parallelism": "replicas only (a single filter is one dense chain)",
+                      "l2": "covariance %.0f MB + P*H^T %.0f MB exceed L2" % (8.0 * n * n / 1e6, 8.0 * n * m2 / 1e6)},
+           "clocks": clk, "e2e": {"value": e2e_steps / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": int(8 * n * n + 8 * n + 8 * m2 * 18),
+                                  "d2h_bytes_per_step": int(8 * n * n + 8 * n), "ms_per_step": ms_e2e / e2e_steps},
+           "gpu_launches": int(launches),
+           "roofline": {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["achieved"], "peak": f64_peak, "unit": "TFLOP/s", "frac": kernels[dom]["frac"],
+                        "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json)"},
+           "kernels": kernels, "fp64_gemm_peak_tflops": f64_peak, "chol_info": int(info)}
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -299,6 +382,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c4":
+        run_ekf(args)
     else:
         run_ours(args)
 
