@@ -30,59 +30,70 @@ constexpr int PB = 256;    // panel width of the trailing update
 // ---------------------------------------------------------------------------------------------------------------------
 // 64x64 diagonal block.  Thread (r = tid & 63, grp = tid >> 6) keeps row r of the block, columns c == grp (mod 4), in 16
 // registers, and the same slice of row r of W, which starts as the identity and receives the same row operations: after the
-// 64 elimination steps T holds L D^(1/2)-unscaled and W the matching L^-1 factor; the 1/sqrt(d_j) scalings are deferred to the
-// output (L(r,c) = T(r,c) rs_c, Linv(r,c) = W(r,c) rs_r), so a step is: publish column j of T and row j of W through shared
-// memory (double buffered, ONE barrier), then one DFMA per owned element.  The step loop stays rolled: the column to publish
-// is picked with a predicated sweep instead of a dynamic register index, so the body is ~150 instructions and stays in the
-// instruction cache (a fully unrolled version is fetch bound).  info: 1-based index of the first non-positive pivot.
+// 64 elimination steps T holds L up to the deferred column scalings and W the matching L^-1 (L(r,c) = T(r,c) rs_c,
+// Linv(r,c) = W(r,c) rs_r, rs = 1/sqrt(pivot)).  A step publishes column j of T and row j of W through shared memory (double
+// buffered, ONE barrier) and applies one DFMA per owned element.
+// The step is bound by the ~200-instruction critical path of a single warp, not by FP64 throughput (measured with
+// tools/potrf_micro.cu: 1870 -> 667 cycles per step), hence: the loop nest is (i unrolled) x (g rolled) so that every register
+// index and almost every T-vs-W decision is static; the reciprocal of the pivot is an FP32 seed + Newton steps instead of the
+// library division; rsqrt is taken once at the end.  info: 1-based index of the first non-positive pivot.
+__device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp
+    double x = (double)__frcp_rn((float)d);
+    x = x * (2.0 - d * x);
+    x = x * (2.0 - d * x);
+    x = x + x * (1.0 - d * x);
+    return x;
+}
 __global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ dinv, int* __restrict__ info,
                                                      unsigned char* __restrict__ F, int nblk) {
+    constexpr int G = 4, E = NB / G;
     __shared__ double col[2][NB];
     __shared__ double wrow[2][NB];
-    __shared__ double rsv[NB];
+    __shared__ double dv[NB];
     const int nb = min(NB, n - k0);
     const int tid = threadIdx.x;
     const int r = tid & 63, grp = tid >> 6;
-    double t[16], w[16];
+    double t[E], w[E];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int c = grp + 4 * i;
+    for (int i = 0; i < E; ++i) {
+        const int c = grp + G * i;
         t[i] = (r < nb && c < nb && r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : ((r == c) ? 1.0 : 0.0);
         w[i] = (r == c) ? 1.0 : 0.0;
     }
     if (tid == 0) F[(size_t)(k0 / NB) * nblk + k0 / NB] = 1;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
 #pragma unroll 1
-    for (int j = 0; j < NB; ++j) {
-        const int buf = j & 1;
+        for (int g = 0; g < G; ++g) {
+            const int j = i * G + g;
+            const int buf = g & 1;
+            if (grp == g) col[buf][r] = t[i];                                     // T(r, j), unscaled
+            if (r == j) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) if (grp + 4 * i == j) col[buf][r] = t[i];   // T(r, j), unscaled
-        if (r == j) {
+                for (int i2 = 0; i2 <= i; ++i2) wrow[buf][grp + G * i2] = w[i2];  // W(j, c <= j), unscaled
+            }
+            __syncthreads();
+            const double d = col[buf][j];
+            if (tid == j) { dv[j] = d; if (!(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1); }
+            if (r > j) {
+                const double a = col[buf][r] * fast_rcp(d);                       // L(r,j) L(c,j) = T(r,j) T(c,j) / d
 #pragma unroll
-            for (int i = 0; i < 16; ++i) wrow[buf][grp + 4 * i] = w[i];          // W(j, :), unscaled
-        }
-        __syncthreads();
-        const double d = col[buf][j];
-        if (tid == j) {
-            if (!(d > 0.0) && j < nb) atomicCAS(info, 0, k0 + j + 1);
-            rsv[j] = rsqrt(d);
-        }
-        if (r > j) {
-            const double a = col[buf][r] * (1.0 / d);         // L(r,j) L(c,j) = T(r,j) T(c,j) / d
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int c = grp + 4 * i;
-                if (c > j) { if (c <= r) t[i] -= a * col[buf][c]; }
-                else w[i] -= a * wrow[buf][c];
+                for (int i2 = 0; i2 < E; ++i2) {
+                    const int c = grp + G * i2;
+                    if (i2 < i) w[i2] -= a * wrow[buf][c];                        // c < j
+                    else if (i2 > i) { if (c <= r) t[i2] -= a * col[buf][c]; }   // c > j
+                    else { if (grp > g) { if (c <= r) t[i2] -= a * col[buf][c]; } else w[i2] -= a * wrow[buf][c]; }
+                }
             }
         }
     }
     __syncthreads();
-    const double rsr = rsv[r];
+    const double rsr = rsqrt(dv[r]);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int c = grp + 4 * i;
-        if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = t[i] * rsv[c];
-        dinv[(size_t)c * NB + r] = (r >= c) ? w[i] * rsr : 0.0;   // column-major 64x64: Linv(r, c)
+    for (int i = 0; i < E; ++i) {
+        const int c = grp + G * i;
+        if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = t[i] * rsqrt(dv[c]);
+        dinv[(size_t)c * NB + r] = (r >= c) ? w[i] * rsr : 0.0;                   // column-major 64x64: Linv(r, c)
     }
 }
 
@@ -176,14 +187,16 @@ __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads) k_syrk_dmma(int n, do
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
 
-    // ---- work list: non-zero row tiles of this panel (tile index relative to origin), identical in every CTA
-    if (warp == 0) {
+    // ---- work list: non-zero row tiles of this panel (tile index relative to origin), identical in every CTA.  All threads test
+    // tiles in parallel (the F bytes of a tile are independent loads), warp ballots + a scan over the warp counts compact them.
+    {
+        __shared__ int s_wcnt[8];
         const int kb0 = kcol0 / NB, kb1 = (kcol0 + K) / NB;
         const int ntile = (n - origin + TILE - 1) / TILE;
         const int ntile128 = (n - origin + 127) / 128;
-        int m = 0, m128 = 0;
-        for (int base = 0; base < max(ntile, ntile128); base += 32) {
-            const int t = base + lane;
+        int m_run = 0, m128_run = 0;
+        for (int base = 0; base < max(ntile, ntile128); base += NT) {
+            const int t = base + tid;
             int nz = 0, nz128 = 0;
             if (t < ntile) {
                 const int rb0 = (origin + t * TILE) / NB;
@@ -197,11 +210,15 @@ __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads) k_syrk_dmma(int n, do
                     for (int kb = kb0; kb < kb1; ++kb) nz128 |= F[(size_t)kb * nblk + rb];
             }
             const unsigned bal = __ballot_sync(0xffffffffu, nz != 0);
-            if (nz) nzt[m + __popc(bal & ((1u << lane) - 1))] = (short)t;
-            m += __popc(bal);
-            m128 += __popc(__ballot_sync(0xffffffffu, nz128 != 0));
+            if (lane == 0) s_wcnt[warp] = __popc(bal);
+            const int c128 = __syncthreads_count(nz128 != 0);   // also publishes s_wcnt
+            int off = m_run, tot = 0;
+            for (int w2 = 0; w2 < NT / 32; ++w2) { if (w2 < warp) off += s_wcnt[w2]; tot += s_wcnt[w2]; }
+            if (nz) nzt[off + __popc(bal & ((1u << lane) - 1))] = (short)t;
+            m_run += tot; m128_run += c128;
+            __syncthreads();
         }
-        if (lane == 0) { s_m = m; s_m128 = m128; }
+        if (tid == 0) { s_m = m_run; s_m128 = m128_run; }
     }
     __syncthreads();
     const int m = s_m;
@@ -289,6 +306,88 @@ __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads) k_syrk_dmma(int n, do
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Right-side solve of one 64-column block against the inverted diagonal block, on the tensor pipe:
+//   X(rows, 0..63) <- X * Linv^T,  X(r, c) = sum_q X(r, q) Linv(c, q)      (in place; a CTA owns 128 full rows, so it reads its
+// operands completely before it writes).  Used by the Cholesky panel (rows below the diagonal block; F receives the 64x64
+// block structure, all-zero tiles are recorded and left alone) and by the EKF TRSM (F == nullptr).
+constexpr int RS_ROWS = 128;
+constexpr int RS_SLDA = RS_ROWS + 4;
+constexpr int RS_SLDB = NB + 4;
+constexpr size_t kRightSolveSmem = sizeof(double) * (NB * RS_SLDA + NB * RS_SLDB);
+__global__ void __launch_bounds__(256) k_right_solve_dmma(int rows, int row0, double* __restrict__ A, int64_t lda, const double* __restrict__ dinv,
+                                                          unsigned char* __restrict__ Frow, int nblk) {
+    extern __shared__ double sm[];
+    double* sA = sm;                       // [q][row]
+    double* sB = sm + NB * RS_SLDA;        // [q][c] = Linv(c, q)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = row0 + blockIdx.x * RS_ROWS;
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {      // 64 x 128 doubles = 4096 16-byte vectors
+        const int v = tid + 256 * it;
+        const int q = v >> 6, rp = (v & 63) * 2;
+        const int row = r0 + rp;
+        int bytes = (rows - row) * 8; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+        cp_async16(sA + q * RS_SLDA + rp, A + (bytes > 0 ? (size_t)q * lda + row : 0), bytes);
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {       // 64 x 64 doubles = 2048 vectors; dinv[q*64 + c] = Linv(c, q)
+        const int v = tid + 256 * it;
+        const int q = v >> 5, cp = (v & 31) * 2;
+        cp_async16(sB + q * RS_SLDB + cp, dinv + (size_t)q * NB + cp, 16);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (Frow != nullptr) {                 // block structure of L: which 64-row halves of this tile hold a non-zero
+        int nz_lo = 0, nz_hi = 0;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int v = tid + 256 * it;
+            const int q = v >> 6, rp = (v & 63) * 2;
+            const double a0 = sA[q * RS_SLDA + rp], a1 = sA[q * RS_SLDA + rp + 1];
+            if (a0 != 0.0 || a1 != 0.0) { if (rp < NB) nz_lo = 1; else nz_hi = 1; }
+        }
+        nz_lo = __syncthreads_or(nz_lo);
+        nz_hi = __syncthreads_or(nz_hi);
+        if (tid == 0) {
+            const int rb = r0 / NB;
+            Frow[rb] = (unsigned char)nz_lo;
+            if (rb + 1 < nblk) Frow[rb + 1] = (unsigned char)nz_hi;
+        }
+        if (!(nz_lo | nz_hi)) return;      // X = 0 * Linv^T stays zero
+    }
+    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 32;
+    const int g = lane >> 2, tg = lane & 3;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll 4
+    for (int ks = 0; ks < NB; ks += 4) {
+        double af[4], bf[4];
+        const double* pa = sA + (ks + tg) * RS_SLDA + wr + g;
+        const double* pb = sB + (ks + tg) * RS_SLDB + wc + g;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = pa[i * 8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = pb[j * 8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = r0 + wr + i * 8 + g;
+            const int c = wc + j * 8 + tg * 2;
+            if (row < rows) { A[(size_t)c * lda + row] = acc[i][j][0]; A[(size_t)(c + 1) * lda + row] = acc[i][j][1]; }
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Triangular solves with the stored inverses of the diagonal blocks, ONE cooperative launch and no grid-wide barrier.
 //   forward  (L y = b):   blocks in ascending order:  y_k = Linv_k b_k ;   b_j -= L(j,k) y_k   for j > k
 //   backward (L^T x = y): blocks in descending order: x_k = Linv_k^T b_k ; b_j -= L(k,j)^T x_k for j < k
@@ -299,11 +398,151 @@ __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads) k_syrk_dmma(int n, do
 __device__ __forceinline__ int ld_acquire(const int* p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory"); return v; }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
 
+// Sparse-factor path of the substitutions: when L has few non-zero 64x64 tiles (block-banded reduced camera systems) the whole solve
+// is a latency chain, and handing solved blocks from CTA to CTA through global memory (k_trsv_flags) costs ~6 us per block.
+// Here ONE CTA walks the chain with the right-hand side resident in shared memory and no inter-CTA traffic at all.
+//   * k_build_trsv_lists (once per factorisation) turns F into two flat op lists, forward and backward: per block the diagonal
+//     op (k,k) followed by one op per non-zero tile (k,j); op = (k << 16) | j.
+//   * k_trsv_single walks a list.  Every op is a 64x64 GEMV slice: lane = (row & 7, q) owns the partial sum over columns
+//     c == q (mod 4) of one row, 16 operands per thread, reduced over q with two shuffles (no shared-memory reduction).  The
+//     operands of op t+2 are loaded into registers before op t is computed, so the L2/HBM latency of the tiles is off the chain;
+//     tile ops of one block column write different row blocks and need no barrier between them: 2 barriers per BLOCK.
+// nz_tiles (device) decides which of the two kernels does the work; both are launched, the other returns at once.
+constexpr int kTrsvSparseMaxN = 24576;      // b in shared memory: 192 KB
+constexpr int kTrsvSparseMaxBlk = kTrsvSparseMaxN / NB;
+constexpr int kTrsvSparseFill = 6;          // sparse path while nz_tiles <= kTrsvSparseFill * nblk
+__host__ __device__ __forceinline__ bool trsv_use_sparse(int n, int nblk, int nz_tiles) { return n <= kTrsvSparseMaxN && nz_tiles <= kTrsvSparseFill * nblk; }
+
+// out[0] = number of non-zero 64x64 tiles of L (diagonal included), out[1] = ops per list; listF / listB: (kTrsvSparseFill+1)*nblk ints each.
+__global__ void __launch_bounds__(1024) k_build_trsv_lists(int n, int nblk, const unsigned char* __restrict__ F, int* __restrict__ out, int* __restrict__ listF,
+                                                           int* __restrict__ listB) {
+    __shared__ int cntF[kTrsvSparseMaxBlk], cntB[kTrsvSparseMaxBlk], offF[kTrsvSparseMaxBlk], offB[kTrsvSparseMaxBlk];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    if (n > kTrsvSparseMaxN) {   // dense path only: just the tile count
+        int c = 0;
+        for (int e = tid; e < nblk * nblk; e += blockDim.x) c += F[e] != 0;
+        for (int s2 = 16; s2 > 0; s2 >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s2);
+        if (tid == 0) s_total = 0;
+        __syncthreads();
+        if (lane == 0) atomicAdd(&s_total, c);
+        __syncthreads();
+        if (tid == 0) { out[0] = s_total; out[1] = 0; }
+        return;
+    }
+    for (int k = tid; k < nblk; k += blockDim.x) { cntF[k] = 0; cntB[k] = 0; }
+    __syncthreads();
+    // pass 1: off-diagonal non-zero tiles per block column (forward) / per block row (backward)
+    for (int k = warp; k < nblk; k += nwarp) {
+        int c = 0;
+        for (int j = k + 1 + lane; j < nblk; j += 32)
+            if (F[(size_t)k * nblk + j] != 0) { ++c; atomicAdd(&cntB[j], 1); }
+        for (int s2 = 16; s2 > 0; s2 >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s2);
+        if (lane == 0) cntF[k] = c;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int k = 0; k < nblk; ++k) { offF[k] = run; run += 1 + cntF[k]; }
+        const int total = run;
+        run = 0;
+        for (int k = nblk - 1; k >= 0; --k) { offB[k] = run; run += 1 + cntB[k]; }
+        s_total = total;
+        out[0] = total; out[1] = total;
+    }
+    __syncthreads();
+    if (!trsv_use_sparse(n, nblk, s_total)) return;
+    for (int k = tid; k < nblk; k += blockDim.x) {
+        listF[offF[k]] = (k << 16) | k;
+        listB[offB[k]] = (k << 16) | k;
+        cntB[k] = 0;   // reused as the fill cursor of the backward list
+    }
+    __syncthreads();
+    for (int k = warp; k < nblk; k += nwarp) {
+        int run = 0;
+        for (int j0 = k + 1; j0 < nblk; j0 += 32) {
+            const int j = j0 + lane;
+            const bool nz = j < nblk && F[(size_t)k * nblk + j] != 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, nz);
+            if (nz) {
+                listF[offF[k] + 1 + run + __popc(bal & ((1u << lane) - 1))] = (k << 16) | j;      // solved block k updates row block j > k
+                listB[offB[j] + 1 + atomicAdd(&cntB[j], 1)] = (j << 16) | k;                       // solved block j updates row block k < j
+            }
+            run += __popc(bal);
+        }
+    }
+}
+
+__device__ __forceinline__ void trsv_load_op(int op, int n, const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv, int backward, int r, int q,
+                                             double (&v)[16]) {
+    const int k = op >> 16, j = op & 0xffff;
+    if (k == j) {
+        const double* Di = dinv + (size_t)k * NB * NB;      // Di[c*NB + r] = Linv(r, c), zeros above the diagonal
+        if (!backward) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = Di[(size_t)(q + 4 * i) * NB + r];      // y_r = sum_c Linv(r,c) b_c
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = Di[(size_t)r * NB + q + 4 * i];        // x_r = sum_c Linv(c,r) b_c
+        }
+    } else {
+        const int k0 = k * NB, j0 = j * NB;
+        if (!backward) {                                    // b_j[r] -= sum_c L(j0+r, k0+c) y_c   (block k < j is full)
+            const bool ok = j0 + r < n;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = ok ? L[(size_t)(k0 + q + 4 * i) * ld + j0 + r] : 0.0;
+        } else {                                            // b_j[r] -= sum_c L(k0+c, j0+r) x_c   (block k > j may be the ragged last one)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (k0 + q + 4 * i < n) ? L[(size_t)(j0 + r) * ld + k0 + q + 4 * i] : 0.0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) k_trsv_single(int n, const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv, double* __restrict__ b,
+                                                        const int* __restrict__ stats, const int* __restrict__ list, int backward) {
+    extern __shared__ double sb[];          // the whole right-hand side, padded to full blocks
+    __shared__ double yk[NB];
+    const int nblk = (n + NB - 1) / NB;
+    if (!trsv_use_sparse(n, nblk, stats[0])) return;
+    const int nops = stats[1];
+    const int tid = threadIdx.x;
+    const int q = tid & 3, r = tid >> 2;    // 4 consecutive lanes share a row
+    for (int i = tid; i < nblk * NB; i += 256) sb[i] = i < n ? b[i] : 0.0;
+    double v0[16], v1[16], v2[16];
+    int op0 = nops > 0 ? list[0] : 0, op1 = nops > 1 ? list[1] : 0, op2 = 0;
+    if (nops > 0) trsv_load_op(op0, n, L, ld, dinv, backward, r, q, v0);
+    if (nops > 1) trsv_load_op(op1, n, L, ld, dinv, backward, r, q, v1);
+    __syncthreads();
+    for (int t = 0; t < nops; ++t) {
+        if (t + 2 < nops) { op2 = list[t + 2]; trsv_load_op(op2, n, L, ld, dinv, backward, r, q, v2); }
+        const int k = op0 >> 16, j = op0 & 0xffff;
+        const bool diag = k == j;
+        if (diag) __syncthreads();          // the pending updates of row block k are complete
+        const double* x = diag ? sb + k * NB : yk;
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s += v0[i] * x[q + 4 * i];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (diag) {
+            if (q == 0) { yk[r] = s; if (k * NB + r < n) b[k * NB + r] = s; }
+            __syncthreads();
+        } else if (q == 0) {
+            sb[j * NB + r] -= s;
+        }
+        op0 = op1; op1 = op2;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v0[i] = v1[i]; v1[i] = v2[i]; }
+    }
+}
+
 constexpr int kTrsvOwn = 2;          // owned row blocks per CTA whose operands are kept in shared memory
 constexpr int kTrsvFCacheMax = 65536;  // bytes of F cached in shared memory (n <= 16384)
 
 __global__ void __launch_bounds__(256) k_trsv_flags(int n, const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv, double* b,
-                                                    double* ybuf, int* flags, const unsigned char* __restrict__ F, int epoch, int backward, int cacheF) {
+                                                    double* ybuf, int* flags, const unsigned char* __restrict__ F, int epoch, int backward, int cacheF,
+                                                    const int* __restrict__ nz_tiles) {
+    if (trsv_use_sparse(n, (n + NB - 1) / NB, nz_tiles[0])) return;   // k_trsv_single does it
     extern __shared__ double smt[];
     double* sDi = smt;                          // [kTrsvOwn][64*64]  Linv of my blocks, column-major
     double* sLt = smt + kTrsvOwn * NB * NB;     // [kTrsvOwn][64*64]  the sub-diagonal tile next to each of my blocks, column-major
@@ -475,6 +714,7 @@ static void set_attrs_once() {
     static bool attr_set = false;
     if (attr_set) return;
     cudaFuncSetAttribute(k_panel_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSolveSmem);
+    cudaFuncSetAttribute(k_right_solve_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRightSolveSmem);
     cudaFuncSetAttribute(k_syrk_dmma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<128>::kSmem);
     cudaFuncSetAttribute(k_syrk_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<64>::kSmem);
     g_sms = 148; { int d = 0; cudaGetDevice(&d); cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, d); }
@@ -486,15 +726,21 @@ static void set_attrs_once() {
     attr_set = true;
 }
 
-// Workspace layout (doubles): [dinv: nblk*64*64][ybuf: nblk*64][flags: nblk ints, padded][F: nblk*nblk bytes, padded]
+// Workspace layout (doubles): [dinv: nblk*64*64][ybuf: nblk*64][flags: nblk ints, padded][F: nblk*nblk bytes, padded][op lists: 2 x 7*nblk ints]
 static inline int chol_nblk(int n) { return (n + NB - 1) / NB; }
 size_t dense_cholesky_dinv_doubles(int n) {
     const size_t nblk = (size_t)chol_nblk(n);
-    return nblk * NB * NB + nblk * NB + (nblk + 1) / 2 + 8 + (nblk * nblk + 7) / 8 + 8;
+    return nblk * NB * NB + nblk * NB + (nblk + 1) / 2 + 8 + (nblk * nblk + 7) / 8 + 8 + (size_t)(kTrsvSparseFill + 1) * nblk + 8;   // the +8 after the flags also holds the tile / op counters
 }
 static inline double* ws_ybuf(double* ws, int n) { return ws + (size_t)chol_nblk(n) * NB * NB; }
 static inline int* ws_flags(double* ws, int n) { return (int*)(ws_ybuf(ws, n) + (size_t)chol_nblk(n) * NB); }
+static inline int* ws_nzt(double* ws, int n) { return ws_flags(ws, n) + chol_nblk(n) + 1; }
 static inline unsigned char* ws_F(double* ws, int n) { return (unsigned char*)(ws_ybuf(ws, n) + (size_t)chol_nblk(n) * NB + (chol_nblk(n) + 1) / 2 + 8); }
+static inline int* ws_list(double* ws, int n, int backward) {
+    const size_t nblk = (size_t)chol_nblk(n);
+    int* base = (int*)(ws_ybuf(ws, n) + nblk * NB + (nblk + 1) / 2 + 8 + (nblk * nblk + 7) / 8 + 8);
+    return base + (backward ? (size_t)(kTrsvSparseFill + 1) * nblk : 0);
+}
 
 // Development aid: SRK_CHOL_PROFILE=1 times every kernel type of the factorisation with events (serialised, no graph).
 static bool g_prof = false;
@@ -525,7 +771,7 @@ static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
             { ProfScope ps(0, st); k_potrf64_inv<<<1, 256, 0, st>>>(n, k0, A, ld, di, info_dev, F, nblk); } ++launches;
             const int below = n - (k0 + NB);
             if (below <= 0) continue;
-            { ProfScope ps(1, st); k_panel_solve<<<(below + PS_ROWS - 1) / PS_ROWS, 256, kPanelSolveSmem, st>>>(n, k0, A, ld, di, F, nblk); } ++launches;
+            { ProfScope ps(1, st); k_right_solve_dmma<<<(below + RS_ROWS - 1) / RS_ROWS, 256, kRightSolveSmem, st>>>(n, k0 + NB, A + (size_t)k0 * ld, ld, di, F + (size_t)(k0 / NB) * nblk, nblk); } ++launches;
             const int origin = k0 + NB;
             if (origin < pend) {   // rest of the current panel, K = 64
                 { ProfScope ps(2, st); launch_syrk(st, n, A, ld, k0, NB, origin, pend, F, nblk); } launches += 2;
@@ -535,6 +781,7 @@ static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
             { ProfScope ps(3, st); launch_syrk(st, n, A, ld, p0, pend - p0, pend, n, F, nblk); } launches += 2;
         }
     }
+    k_build_trsv_lists<<<1, 1024, 0, st>>>(n, nblk, F, ws_nzt(ws, n), ws_list(ws, n, 0), ws_list(ws, n, 1)); ++launches;
     return launches;
 }
 
@@ -588,12 +835,18 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
     int* flags = ws_flags(ws, n);
     const unsigned char* F = ws_F(ws, n);
     int epoch = ++g_epoch;
+    const int* nzt = ws_nzt(ws, n);
+    if (n <= kTrsvSparseMaxN) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(k_trsv_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTrsvSparseMaxN)); attr = true; }
+        k_trsv_single<<<1, 256, sizeof(double) * (size_t)nblk * NB, st>>>(n, L, ld, dinv, b, nzt, ws_list(ws, n, backward), backward);
+    }
     int cacheF = nblk * nblk <= kTrsvFCacheMax ? 1 : 0;
     size_t smem = sizeof(double) * 2 * kTrsvOwn * NB * NB + (cacheF ? (size_t)((nblk * nblk + 15) & ~15) : 0);
     void* args[] = {(void*)&n, (void*)&L, (void*)&ld, (void*)&dinv, (void*)&b, (void*)&ybuf, (void*)&flags, (void*)&F, (void*)&epoch, (void*)&backward,
-                    (void*)&cacheF};
+                    (void*)&cacheF, (void*)&nzt};
     cudaLaunchCooperativeKernel((void*)k_trsv_flags, dim3(blocks), dim3(256), args, smem, st);
-    return 1;
+    return 2;
 }
 int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 0); }
 int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 1); }
@@ -721,9 +974,7 @@ __global__ void __launch_bounds__(256) k_block_right_solve(int rows, double* __r
 }
 void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block) {
     set_attrs_once();
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_block_right_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSolveSmem); attr = true; }
-    if (rows > 0) k_block_right_solve<<<(rows + PS_ROWS - 1) / PS_ROWS, 256, kPanelSolveSmem, st>>>(rows, A, lda, dinv_block);
+    if (rows > 0) k_right_solve_dmma<<<(rows + RS_ROWS - 1) / RS_ROWS, 256, kRightSolveSmem, st>>>(rows, 0, A, lda, dinv_block, nullptr, 0);
 }
 
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld) {
