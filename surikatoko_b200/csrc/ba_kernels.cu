@@ -44,7 +44,7 @@ __global__ void k_cam_prep(int M, const double* __restrict__ cams, const double*
     double Td[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) Td[r] = -(R[r * 3 + 0] * T[0] + R[r * 3 + 1] * T[1] + R[r * 3 + 2] * T[2]);
-    double fx = Km[0], fy = Km[4], u0 = Km[6], v0 = Km[7];
+    const double fx = Km[0], fy = Km[4], u0 = Km[6], v0 = Km[7];
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
         double rd0 = R[t * 3 + 0], rd1 = R[t * 3 + 1], rd2 = R[t * 3 + 2];  // Rd(t,0..2) = R(0..2,t)
@@ -53,30 +53,47 @@ __global__ void k_cam_prep(int M, const double* __restrict__ cams, const double*
         d[CD_ROT2 + t] = fy * rd1 + v0 * rd2;
         d[CD_ROT3 + t] = f0 * rd2;
     }
-    d[CD_FX] = fx; d[CD_FY] = fy; d[CD_U0] = u0; d[CD_V0] = v0; d[CD_F0] = f0; d[47] = 0.0;
+    d[CD_IFX] = 1.0 / fx; d[CD_CU] = u0 / (f0 * fx); d[CD_IFY] = 1.0 / fy; d[CD_CV] = v0 / (f0 * fy); d[CD_IF0] = 1.0 / f0; d[47] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K1: one thread per observation.  Reads 24 B/obs of observation data + the point (gathered, L1/L2-served) + the camera
-// record (L1/L2-resident), writes 224 B/obs as 28 coalesced planes: rho[2], Jp[6], Jc[20].
+// K1: a CTA of 256 threads owns a chunk of kObsRows*256 consecutive observations (thread t: observations base + t + 256*row).
+// Reads 24 B/obs of observation data + the point (gathered, L1-served: a point's observations are consecutive) + the camera
+// record through the per-CTA camera table (shared memory), writes 224 B/obs as 28 coalesced planes: rho[2], Jp[6], Jc[20].
+constexpr int kObsRows = 4;
 __global__ void __launch_bounds__(256) k_jacobian(int64_t O, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt,
-                                                  const double* __restrict__ obs_x, const double* __restrict__ obs_y,
+                                                  const double* __restrict__ obs_xs, const double* __restrict__ obs_ys,
                                                   const double* __restrict__ X, int64_t N, const double* __restrict__ camd,
                                                   double* __restrict__ J) {
-    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= O) return;
-    int cam = obs_cam[o], pt = obs_pt[o];
-    double x = obs_x[o], y = obs_y[o];
-    double X0 = X[pt], X1 = X[N + pt], X2 = X[2 * N + pt];
-    const double* cd = camd + (size_t)cam * kCamStride;
-    double rx, ry, jp[6], jc[20];
-    obs_jacobian(cd, X0, X1, X2, x, y, rx, ry, jp, jc);
-    J[o] = rx;
-    J[O + o] = ry;
+    __shared__ CamTable tab;
+    const int64_t base = (int64_t)blockIdx.x * (256 * kObsRows) + threadIdx.x;
+    cam_table_reset(tab);
+    int cam[kObsRows], hp[kObsRows];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) J[(int64_t)(2 + i) * O + o] = jp[i];
+    for (int rr = 0; rr < kObsRows; ++rr) { const int64_t o = base + 256 * rr; cam[rr] = o < O ? obs_cam[o] : -1; }
+    __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 20; ++i) J[(int64_t)(8 + i) * O + o] = jc[i];
+    for (int rr = 0; rr < kObsRows; ++rr) hp[rr] = cam[rr] >= 0 ? cam_table_insert(tab, cam[rr]) : -1;
+    __syncthreads();
+    cam_table_stage(tab, camd);
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < kObsRows; ++rr) {
+        const int64_t o = base + 256 * rr;
+        if (o >= O) continue;
+        const int pt = obs_pt[o];
+        const double xs = obs_xs[o], ys = obs_ys[o];
+        const double X0 = X[pt], X1 = X[N + pt], X2 = X[2 * N + pt];
+        const double* cd = cam_table_record(tab, hp[rr], cam[rr], camd);
+        double rx, ry, jp[6], jc[20];
+        obs_jacobian(cd, X0, X1, X2, xs, ys, rx, ry, jp, jc);
+        J[o] = rx;
+        J[O + o] = ry;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) J[(int64_t)(2 + i) * O + o] = jp[i];
+#pragma unroll
+        for (int i = 0; i < 20; ++i) J[(int64_t)(8 + i) * O + o] = jc[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -135,17 +152,40 @@ __global__ void __launch_bounds__(128) k_frame_blocks(int M, const int64_t* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// K1': squared residuals, grid-stride, fixed grid; per-block partial then a fixed-order final sum (deterministic).
+// K1': squared residuals.  Fixed grid; a CTA walks chunks of kObsRows*256 observations (camera table per chunk), keeps one
+// partial per thread, then a per-block partial and a fixed-order final sum (deterministic for a given grid).
 __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt,
-                                                  const double* __restrict__ obs_x, const double* __restrict__ obs_y,
+                                                  const double* __restrict__ obs_xs, const double* __restrict__ obs_ys,
                                                   const double* __restrict__ X, int64_t N, const double* __restrict__ camd,
                                                   double* __restrict__ partial) {
+    __shared__ CamTable tab;
     double s = 0.0;
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < O; o += (int64_t)gridDim.x * blockDim.x) {
-        int cam = obs_cam[o], pt = obs_pt[o];
-        double rx, ry;
-        obs_residual(camd + (size_t)cam * kCamStride, X[pt], X[N + pt], X[2 * N + pt], obs_x[o], obs_y[o], rx, ry);
-        s += rx * rx + ry * ry;
+    const int64_t nchunks = (O + 256 * kObsRows - 1) / (256 * kObsRows);
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int64_t base = ch * (256 * kObsRows) + threadIdx.x;
+        __syncthreads();                      // the previous chunk's records are no longer read
+        cam_table_reset(tab);
+        int cam[kObsRows], hp[kObsRows], pt[kObsRows];
+        double xs[kObsRows], ys[kObsRows];
+#pragma unroll
+        for (int rr = 0; rr < kObsRows; ++rr) {
+            const int64_t o = base + 256 * rr;
+            const bool in = o < O;
+            cam[rr] = in ? obs_cam[o] : -1; pt[rr] = in ? obs_pt[o] : 0; xs[rr] = in ? obs_xs[o] : 0.0; ys[rr] = in ? obs_ys[o] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < kObsRows; ++rr) hp[rr] = cam[rr] >= 0 ? cam_table_insert(tab, cam[rr]) : -1;
+        __syncthreads();
+        cam_table_stage(tab, camd);
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < kObsRows; ++rr) {
+            if (cam[rr] < 0) continue;
+            double rx, ry;
+            obs_residual(cam_table_record(tab, hp[rr], cam[rr], camd), X[pt[rr]], X[N + pt[rr]], X[2 * N + pt[rr]], xs[rr], ys[rr], rx, ry);
+            s += rx * rx + ry * ry;
+        }
     }
     __shared__ double red[8];
 #pragma unroll
@@ -811,7 +851,7 @@ void launch_cam_prep(cudaStream_t st, int M, const double* cams, const double* K
 }
 void launch_jacobian(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
                      const double* X, int64_t N, const double* camd, double* J) {
-    if (O > 0) k_jacobian<<<cdiv(O, 256), 256, 0, st>>>(O, obs_cam, obs_pt, x, y, X, N, camd, J);
+    if (O > 0) k_jacobian<<<cdiv(O, 256 * kObsRows), 256, 0, st>>>(O, obs_cam, obs_pt, x, y, X, N, camd, J);
 }
 void launch_frame_blocks(cudaStream_t st, int M, const int64_t* cam_begin, const int32_t* c_pt, const double* c_x, const double* c_y,
                          const double* X, int64_t N, const double* camd, double* G, double* gf, int splits) {

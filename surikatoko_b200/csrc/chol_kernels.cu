@@ -500,28 +500,33 @@ __device__ __forceinline__ void trsv_load_op(int op, int n, const double* __rest
 
 __global__ void __launch_bounds__(256, 1) k_trsv_single(int n, const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv, double* __restrict__ b,
                                                         const int* __restrict__ stats, const int* __restrict__ list, int backward) {
-    extern __shared__ double sb[];          // the whole right-hand side, padded to full blocks
+    extern __shared__ double sb[];          // [nblk*NB] the whole right-hand side, padded to full blocks; then the op list (ints)
     __shared__ double yk[NB];
     const int nblk = (n + NB - 1) / NB;
     if (!trsv_use_sparse(n, nblk, stats[0])) return;
     const int nops = stats[1];
+    int* sop = (int*)(sb + (size_t)nblk * NB);
     const int tid = threadIdx.x;
     const int q = tid & 3, r = tid >> 2;    // 4 consecutive lanes share a row
     for (int i = tid; i < nblk * NB; i += 256) sb[i] = i < n ? b[i] : 0.0;
-    double v0[16], v1[16], v2[16];
-    int op0 = nops > 0 ? list[0] : 0, op1 = nops > 1 ? list[1] : 0, op2 = 0;
-    if (nops > 0) trsv_load_op(op0, n, L, ld, dinv, backward, r, q, v0);
-    if (nops > 1) trsv_load_op(op1, n, L, ld, dinv, backward, r, q, v1);
+    for (int i = tid; i < nops; i += 256) sop[i] = list[i];
     __syncthreads();
-    for (int t = 0; t < nops; ++t) {
-        if (t + 2 < nops) { op2 = list[t + 2]; trsv_load_op(op2, n, L, ld, dinv, backward, r, q, v2); }
-        const int k = op0 >> 16, j = op0 & 0xffff;
+    double vA[16], vB[16], vC[16];
+    if (nops > 0) trsv_load_op(sop[0], n, L, ld, dinv, backward, r, q, vA);
+    if (nops > 1) trsv_load_op(sop[1], n, L, ld, dinv, backward, r, q, vB);
+    // one op: the operands of op t are in `cur` (loaded two ops ago); the operands of op t+2 go to `pre`.  The three buffers
+    // rotate by name (the loop is unrolled by 3), never by copying: a register copy would wait for the load it copies.
+    auto step = [&](int t, double (&cur)[16], double (&pre)[16]) {
+        if (t >= nops) return;
+        if (t + 2 < nops) trsv_load_op(sop[t + 2], n, L, ld, dinv, backward, r, q, pre);
+        const int op = sop[t];
+        const int k = op >> 16, j = op & 0xffff;
         const bool diag = k == j;
         if (diag) __syncthreads();          // the pending updates of row block k are complete
         const double* x = diag ? sb + k * NB : yk;
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) s += v0[i] * x[q + 4 * i];
+        for (int i = 0; i < 16; ++i) s += cur[i] * x[q + 4 * i];
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         if (diag) {
@@ -530,9 +535,11 @@ __global__ void __launch_bounds__(256, 1) k_trsv_single(int n, const double* __r
         } else if (q == 0) {
             sb[j * NB + r] -= s;
         }
-        op0 = op1; op1 = op2;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { v0[i] = v1[i]; v1[i] = v2[i]; }
+    };
+    for (int t = 0; t < nops; t += 3) {
+        step(t, vA, vC);
+        step(t + 1, vB, vA);
+        step(t + 2, vC, vB);
     }
 }
 
@@ -838,8 +845,14 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
     const int* nzt = ws_nzt(ws, n);
     if (n <= kTrsvSparseMaxN) {
         static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_trsv_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTrsvSparseMaxN)); attr = true; }
-        k_trsv_single<<<1, 256, sizeof(double) * (size_t)nblk * NB, st>>>(n, L, ld, dinv, b, nzt, ws_list(ws, n, backward), backward);
+        if (!attr) { cudaFuncSetAttribute(k_trsv_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTrsvSparseMaxN + sizeof(int) * (kTrsvSparseFill + 1) * kTrsvSparseMaxBlk)); attr = true; }
+        k_trsv_single<<<1, 256, sizeof(double) * (size_t)nblk * NB + sizeof(int) * (size_t)(kTrsvSparseFill + 1) * nblk, st>>>(n, L, ld, dinv, b, nzt, ws_list(ws, n, backward),
+                                                                                                                             backward);
+        if (g_prof) {
+            int h[2] = {0, 0};
+            cudaStreamSynchronize(st); cudaMemcpy(h, nzt, sizeof(h), cudaMemcpyDeviceToHost);
+            printf("  trsv: nblk=%d non-zero tiles=%d ops=%d sparse path=%d\n", nblk, h[0], h[1], (int)trsv_use_sparse(n, nblk, h[0]));
+        }
     }
     int cacheF = nblk * nblk <= kTrsvFCacheMax ? 1 : 0;
     size_t smem = sizeof(double) * 2 * kTrsvOwn * NB * NB + (cacheF ? (size_t)((nblk * nblk + 15) & ~15) : 0);

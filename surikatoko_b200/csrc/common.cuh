@@ -11,8 +11,9 @@ constexpr int kCamStride = 48;   // doubles per derived-camera record (384 B, 12
 
 // Derived camera record, rebuilt whenever a pose changes (k_cam_prep).  All 3x3 are column-major (r,c)->[c*3+r].
 //  [0..8] R  [9..11] T  [12..20] K  [21..29] KR=K*R  [30..32] Td=-R^T*T  [33..35] rot1  [36..38] rot2  [39..41] rot3
-//  [42] fx [43] fy [44] u0 [45] v0 [46] f0 [47] pad
-enum { CD_R = 0, CD_T = 9, CD_K = 12, CD_KR = 21, CD_TD = 30, CD_ROT1 = 33, CD_ROT2 = 36, CD_ROT3 = 39, CD_FX = 42, CD_FY = 43, CD_U0 = 44, CD_V0 = 45, CD_F0 = 46 };
+//  [42] 1/fx [43] u0/(f0*fx) [44] 1/fy [45] v0/(f0*fy) [46] 1/f0 [47] pad   -- the per-camera quotients of BA.cpp:1463-1474,
+//  evaluated once per camera instead of once per observation (same operands, same IEEE division, same bits).
+enum { CD_R = 0, CD_T = 9, CD_K = 12, CD_KR = 21, CD_TD = 30, CD_ROT1 = 33, CD_ROT2 = 36, CD_ROT3 = 39, CD_IFX = 42, CD_CU = 43, CD_IFY = 44, CD_CV = 45, CD_IF0 = 46 };
 
 // Gauge-reduced index of frame variable (cam, a): frame 0 keeps [fx fy u0 v0], frame 1 drops T[unity], frames >= 2 keep
 // all 10 (quirk Q13; BA.cpp:539-563, :1780-1823).  Returns -1 for the 7 removed variables.
@@ -67,7 +68,7 @@ __device__ __forceinline__ void sink_add_rhs(const SchurSink& s, int cam, int a,
 }
 
 // pqr = K * (R*X + T)   (BA.cpp:469-470), natural left-to-right coefficient order.
-__device__ __forceinline__ void project_pqr(const double* __restrict__ cd, double X0, double X1, double X2, double& p, double& q, double& r) {
+__device__ __forceinline__ void project_pqr(const double* cd, double X0, double X1, double X2, double& p, double& q, double& r) {
     const double* R = cd + CD_R; const double* T = cd + CD_T; const double* K = cd + CD_K;
     double c0 = R[0] * X0 + R[3] * X1 + R[6] * X2 + T[0];
     double c1 = R[1] * X0 + R[4] * X1 + R[7] * X2 + T[1];
@@ -77,27 +78,26 @@ __device__ __forceinline__ void project_pqr(const double* __restrict__ cd, doubl
     r = K[2] * c0 + K[5] * c1 + K[8] * c2;
 }
 
-// One observation: residual rho = (p/r - x/f0, q/r - y/f0) (BA.cpp:475-479).
-__device__ __forceinline__ void obs_residual(const double* __restrict__ cd, double X0, double X1, double X2, double x, double y,
+// One observation: residual rho = (p/r - x/f0, q/r - y/f0) (BA.cpp:475-479).  xs = x/f0, ys = y/f0 are formed once at bind time
+// (k_prep_obs): the pixel and f0 never change during a solve, and the quotient is the same IEEE division.
+__device__ __forceinline__ void obs_residual(const double* cd, double X0, double X1, double X2, double xs, double ys,
                                              double& rx, double& ry) {
     double p, q, r;
     project_pqr(cd, X0, X1, X2, p, q, r);
-    double f0 = cd[CD_F0];
-    rx = p / r - x / f0;
-    ry = q / r - y / f0;
+    rx = p / r - xs;
+    ry = q / r - ys;
 }
 
 // One observation: residual + Jacobian rows J_a = (r*p_a - p*r_a, r*q_a - q*r_a) / r^2 for the 3 point variables
 // (BA.cpp:1450-1455) and the 10 frame variables (BA.cpp:1457-1525, quirk Q3: f0 verbatim).  With these,
 // formula 8 (BA.cpp:1528-1537) is 2*rho.J_a and formula 9 (BA.cpp:1540-1549) is 2*J_a.J_b.
 // jp[v*2+comp], jc[a*2+comp].
-__device__ __forceinline__ void obs_jacobian(const double* __restrict__ cd, double X0, double X1, double X2, double x, double y,
+__device__ __forceinline__ void obs_jacobian(const double* cd, double X0, double X1, double X2, double xs, double ys,
                                              double& rx, double& ry, double* __restrict__ jp, double* __restrict__ jc) {
     double p, q, r;
     project_pqr(cd, X0, X1, X2, p, q, r);
-    const double f0 = cd[CD_F0];
-    rx = p / r - x / f0;
-    ry = q / r - y / f0;
+    rx = p / r - xs;
+    ry = q / r - ys;
     const double ir2 = 1.0 / (r * r);
     const double* KR = cd + CD_KR;
 #pragma unroll
@@ -106,11 +106,10 @@ __device__ __forceinline__ void obs_jacobian(const double* __restrict__ cd, doub
         jp[v * 2 + 0] = (r * pa - p * ra) * ir2;
         jp[v * 2 + 1] = (r * qa - q * ra) * ir2;
     }
-    const double fx = cd[CD_FX], fy = cd[CD_FY], u0 = cd[CD_U0], v0 = cd[CD_V0];
     // intrinsics: only one of (p_a, q_a) is non-zero and r_a = 0
-    double pfx = (1.0 / fx) * p - u0 / (f0 * fx) * r;
-    double qfy = (1.0 / fy) * q - v0 / (f0 * fy) * r;
-    double pu0 = (1.0 / f0) * r;
+    double pfx = cd[CD_IFX] * p - cd[CD_CU] * r;     // (1/fx) p - u0/(f0 fx) r
+    double qfy = cd[CD_IFY] * q - cd[CD_CV] * r;     // (1/fy) q - v0/(f0 fy) r
+    double pu0 = cd[CD_IF0] * r;                     // (1/f0) r
     jc[0] = (r * pfx) * ir2; jc[1] = 0.0;
     jc[2] = 0.0;             jc[3] = (r * qfy) * ir2;
     jc[4] = (r * pu0) * ir2; jc[5] = 0.0;
@@ -132,6 +131,55 @@ __device__ __forceinline__ void obs_jacobian(const double* __restrict__ cd, doub
         jc[(7 + t) * 2 + 0] = (r * wp[t] - p * wr[t]) * ir2;
         jc[(7 + t) * 2 + 1] = (r * wq[t] - q * wr[t]) * ir2;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Per-CTA camera table.  Observations are point-major, so the 32 lanes of a warp touch ~10 different cameras; reading the
+// 384-byte records straight from global memory costs one L1 wavefront per distinct camera per load (ncu: the LSU data pipe
+// at 96 % with HBM at 8-33 %).  A CTA therefore collects the distinct cameras of its chunk of observations in a small
+// shared-memory hash set, copies their records once (coalesced) into shared memory with an ODD stride, so that records of
+// different cameras start in different banks and same-camera lanes broadcast, and every per-observation read becomes a
+// conflict-free shared-memory load.  Cameras beyond kCamTabSlots per chunk (scattered visibility) are read from global memory.
+constexpr int kCamTabSlots = 24;
+constexpr int kCamTabHash = 64;
+constexpr int kCamRecPad = kCamStride + 1;
+struct CamTable {
+    int key[kCamTabHash];
+    int slot[kCamTabHash];
+    int cam_of_slot[kCamTabSlots];
+    int count;
+    double rec[kCamTabSlots * kCamRecPad];
+};
+__device__ __forceinline__ void cam_table_reset(CamTable& t) {
+    for (int i = threadIdx.x; i < kCamTabHash; i += blockDim.x) t.key[i] = -1;
+    if (threadIdx.x == 0) t.count = 0;
+}
+// returns the hash position of `cam` (its slot is valid after the next barrier), or -1 when the hash set is full
+__device__ __forceinline__ int cam_table_insert(CamTable& t, int cam) {
+    unsigned h = ((unsigned)cam * 2654435761u) >> 26;   // 6 bits
+    for (int probe = 0; probe < kCamTabHash; ++probe) {
+        const int prev = atomicCAS(&t.key[h], -1, cam);
+        if (prev == -1) {
+            const int s = atomicAdd(&t.count, 1);
+            if (s < kCamTabSlots) { t.slot[h] = s; t.cam_of_slot[s] = cam; } else t.slot[h] = -1;
+            return (int)h;
+        }
+        if (prev == cam) return (int)h;
+        h = (h + 1) & (kCamTabHash - 1);
+    }
+    return -1;
+}
+// after a barrier: copies the records of the collected cameras (coalesced), caller issues the next barrier
+__device__ __forceinline__ void cam_table_stage(CamTable& t, const double* __restrict__ camd) {
+    const int n = min(t.count, kCamTabSlots) * kCamStride;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int s = e / kCamStride, f = e - s * kCamStride;
+        t.rec[s * kCamRecPad + f] = camd[(size_t)t.cam_of_slot[s] * kCamStride + f];
+    }
+}
+__device__ __forceinline__ const double* cam_table_record(const CamTable& t, int hpos, int cam, const double* camd) {
+    const int s = hpos >= 0 ? t.slot[hpos] : -1;
+    return s >= 0 ? t.rec + s * kCamRecPad : camd + (size_t)cam * kCamStride;
 }
 
 // Damped 3x3 point block -> cofactor inverse with Eigen's computeInverseAndDetWithCheck rule |det| > 1e-12

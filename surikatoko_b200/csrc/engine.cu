@@ -8,6 +8,7 @@
 // There is no CPU fallback: without a CUDA device srk_ba_create fails.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -111,6 +112,7 @@ struct Engine {
     Buf J, Ggf, pinv, skipped, deferred, Srhs, Lfac, dinv, xsol, resid, dfull, partial, errsum, slots, flags, skipped_cnt, dbg;
     int64_t n_deferred = 0;   // points the tiled Schur kernel leaves to the per-point kernel (structure only, known at bind time)
     int schur_tile_points = 256;
+    int schur_impl = 0;       // 0 = DMMA tile kernel (schur_mma.cu), 1 = vector-FMA tile kernel (ba_kernels.cu)
     srk::PcgWorkspace pcg;
     int residual_blocks = 0;
     double* h_slots = nullptr;  // pinned
@@ -231,7 +233,7 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     SRK_CUDA(cudaMemsetAsync(e.flags.p, 0, sizeof(int) * 8, st));
     SRK_CUDA(cudaMemsetAsync(e.cam_cnt.p, 0, sizeof(unsigned long long) * (M + 1), st));
     if (O == 0) SRK_CUDA(cudaMemsetAsync(e.pt_begin.p, 0, sizeof(int64_t) * (N + 1), st));
-    srk::launch_prep_obs(st, O, N, M, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.obs_xy.as<double>(), e.ox.as<double>(), e.oy.as<double>(),
+    srk::launch_prep_obs(st, O, N, M, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.obs_xy.as<double>(), e.f0, e.ox.as<double>(), e.oy.as<double>(),
                          e.pt_begin.as<int64_t>(), e.cam_cnt.as<unsigned long long>(), e.flags.as<int>());
     srk::launch_scan_counts(st, M, e.cam_cnt.as<unsigned long long>(), e.cam_begin.as<int64_t>(), e.cam_cursor.as<unsigned long long>());
     srk::launch_scatter_by_cam(st, O, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.ox.as<double>(), e.oy.as<double>(),
@@ -372,8 +374,12 @@ int derivative_pass(Engine& e) {
 // K2: per-point blocks + Schur accumulation into `sink` (dense S or block-sparse blocks).
 void schur_accumulate(Engine& e, const srk::SchurSink& sink, double c) {
     cudaStream_t st = e.stream;
-    srk::launch_schur_tile(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink,
-                           e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>(), 0, nullptr, 0, nullptr);
+    if (e.schur_impl == 0)
+        srk::launch_schur_mma(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink,
+                              e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>());
+    else   // SRK_SCHUR_IMPL=1: the vector-FMA tile kernel (kept as a cross-check of the DMMA path)
+        srk::launch_schur_tile(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink,
+                               e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>(), 0, nullptr, 0, nullptr);
     e.launches += e.N > 0 ? 1 : 0;
     if (e.n_deferred > 0) {
         srk::launch_schur(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink, e.pinv.as<double>(),
@@ -641,6 +647,7 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     SRK_CUDA(cudaSetDevice(dev));
     Engine* e = new Engine();
     e->device = dev;
+    if (const char* v = std::getenv("SRK_SCHUR_IMPL")) e->schur_impl = std::atoi(v) == 1 ? 1 : 0;
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; set_error("cudaStreamCreate failed"); return SRK_E_CUDA; }
     e->stream = e->own_stream;
     *h = e;

@@ -19,6 +19,9 @@ void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin
                   double* pinv, unsigned char* skipped, const unsigned char* only_flagged);
 // Tiled Schur accumulation (register-owned camera-pair blocks per tile of points); flags the points it leaves to launch_schur.
 // plan_only: structure pass -- deferred flags and (plan_keys != nullptr) the camera-pair hash of the block-sparse system.
+// DMMA formulation of the same accumulation (schur_mma.cu); same deferral rule as the plan pass of launch_schur_tile.
+void launch_schur_mma(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
+                      const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred);
 void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
                        const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred, int plan_only,
                        unsigned long long* plan_keys, unsigned plan_mask, int* plan_overflow);

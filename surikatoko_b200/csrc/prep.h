@@ -4,7 +4,7 @@
 #include <stdint.h>
 
 namespace srk {
-void launch_prep_obs(cudaStream_t st, int64_t O, int64_t N, int M, const int32_t* obs_cam, const int32_t* obs_pt, const double* obs_xy,
+void launch_prep_obs(cudaStream_t st, int64_t O, int64_t N, int M, const int32_t* obs_cam, const int32_t* obs_pt, const double* obs_xy, double f0,
                      double* x, double* y, int64_t* pt_begin, unsigned long long* cam_count, int* err_flag);
 void launch_scan_counts(cudaStream_t st, int M, const unsigned long long* cnt, int64_t* cam_begin, unsigned long long* cursor);
 void launch_scatter_by_cam(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,

@@ -1,5 +1,5 @@
 // suriko-b200 — bind-time index construction on the device (runs once per srk_ba_bind, not per LM iteration).
-//   k_prep_obs       validate the (pnt_ind, frame_ind) ordering, split pixel pairs into planes, build the point CSR
+//   k_prep_obs       validate the (pnt_ind, frame_ind) ordering, split pixel pairs into planes of x/f0, y/f0, build the point CSR
 //                    (pt_begin) by boundary detection, histogram observations per camera
 //   k_scan_counts    exclusive scan of the per-camera histogram (M is small: one CTA)
 //   k_scatter_by_cam camera-major copy of (point index, x, y) used by the frame pass (k_frame_blocks)
@@ -10,7 +10,7 @@
 namespace srk {
 
 __global__ void k_prep_obs(int64_t O, int64_t N, int M, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt,
-                           const double* __restrict__ obs_xy, double* __restrict__ x, double* __restrict__ y, int64_t* __restrict__ pt_begin,
+                           const double* __restrict__ obs_xy, double f0, double* __restrict__ x, double* __restrict__ y, int64_t* __restrict__ pt_begin,
                            unsigned long long* __restrict__ cam_count, int* __restrict__ err_flag) {
     int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= O) return;
@@ -18,7 +18,7 @@ __global__ void k_prep_obs(int64_t O, int64_t N, int M, const int32_t* __restric
     if (p < 0 || p >= N || c < 0 || c >= M) { atomicOr(err_flag, 1); return; }
     int pp = o > 0 ? obs_pt[o - 1] : -1, pc = o > 0 ? obs_cam[o - 1] : -1;
     if (p < pp || (p == pp && c <= pc)) atomicOr(err_flag, 2);
-    x[o] = obs_xy[2 * o]; y[o] = obs_xy[2 * o + 1];
+    x[o] = obs_xy[2 * o] / f0; y[o] = obs_xy[2 * o + 1] / f0;   // x/f0, y/f0 of BA.cpp:475-479, formed once
     if (p != pp) for (int q = (pp < 0 ? 0 : pp + 1); q <= p; ++q) pt_begin[q] = o;
     if (o == O - 1) for (int64_t q = p + 1; q <= N; ++q) pt_begin[q] = O;
     atomicAdd(&cam_count[c], 1ULL);
@@ -72,9 +72,9 @@ __global__ void k_count_skipped(int64_t N, const unsigned char* __restrict__ ski
 
 static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
-void launch_prep_obs(cudaStream_t st, int64_t O, int64_t N, int M, const int32_t* obs_cam, const int32_t* obs_pt, const double* obs_xy,
+void launch_prep_obs(cudaStream_t st, int64_t O, int64_t N, int M, const int32_t* obs_cam, const int32_t* obs_pt, const double* obs_xy, double f0,
                      double* x, double* y, int64_t* pt_begin, unsigned long long* cam_count, int* err_flag) {
-    if (O > 0) k_prep_obs<<<cdiv(O, 256), 256, 0, st>>>(O, N, M, obs_cam, obs_pt, obs_xy, x, y, pt_begin, cam_count, err_flag);
+    if (O > 0) k_prep_obs<<<cdiv(O, 256), 256, 0, st>>>(O, N, M, obs_cam, obs_pt, obs_xy, f0, x, y, pt_begin, cam_count, err_flag);
 }
 void launch_scan_counts(cudaStream_t st, int M, const unsigned long long* cnt, int64_t* cam_begin, unsigned long long* cursor) {
     k_scan_counts<<<1, 1024, 0, st>>>(M, cnt, cam_begin, cursor);
