@@ -152,6 +152,10 @@ SRK_API int srk_ba_debug_apply(void* h, const double* corrections, double* err_n
  * enabled with srk_ba_set_timing(h, 1).  names: "jacobian", "frame_blocks", "schur", "solve", "backsub", "update", "residual". */
 SRK_API int srk_ba_set_timing(void* h, int enabled);
 SRK_API int srk_ba_get_timing(void* h, const char* name, double* ms_last, double* ms_total, int64_t* launches);
+/* Structure of the last dense Cholesky factor of the reduced camera system: number of 64x64 block rows, non-zero tiles of L,
+ * and the floating-point operations the factorisation executed (zero tiles are skipped, so a block-banded system costs what
+ * its fill costs).  bench.py uses it for the FP64 roofline. */
+SRK_API int srk_ba_solve_stats(void* h, int64_t* n_f, int64_t* block_rows, int64_t* nonzero_tiles, double* factor_flops);
 
 #ifdef __cplusplus
 }

@@ -861,6 +861,29 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
     cudaLaunchCooperativeKernel((void*)k_trsv_flags, dim3(blocks), dim3(256), args, smem, st);
     return 2;
 }
+// Structure of the last factor held in `ws`: non-zero 64x64 tiles of L and the flops the factorisation actually executed
+// (potrf 64^3/3 per diagonal block, 64^3 per off-diagonal tile for the right solve, 2*64^3 per pair of non-zero tiles of a
+// block column for the symmetric update) -- what a roofline may count when zero tiles are skipped.  Synchronises `st`.
+int dense_cholesky_stats(cudaStream_t st, int n, const double* ws, int64_t* nblk_out, int64_t* nz_tiles, double* factor_flops) {
+    const int nblk = chol_nblk(n);
+    const unsigned char* F = ws_F(const_cast<double*>(ws), n);
+    unsigned char* h = (unsigned char*)malloc((size_t)nblk * nblk);
+    if (h == nullptr) return -1;
+    if (cudaMemcpyAsync(h, F, (size_t)nblk * nblk, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { free(h); return -1; }
+    const double b3 = 64.0 * 64.0 * 64.0;
+    double fl = 0.0; int64_t nz = 0;
+    for (int k = 0; k < nblk; ++k) {
+        int64_t ck = 0;
+        for (int j = k + 1; j < nblk; ++j) ck += h[(size_t)k * nblk + j] != 0;
+        nz += 1 + ck;
+        fl += b3 / 3.0 + (double)ck * b3 + (double)(ck * (ck + 1) / 2) * 2.0 * b3;
+    }
+    free(h);
+    if (nblk_out) *nblk_out = nblk;
+    if (nz_tiles) *nz_tiles = nz;
+    if (factor_flops) *factor_flops = fl;
+    return 0;
+}
 int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 0); }
 int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 1); }
 

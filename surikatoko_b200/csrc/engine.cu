@@ -112,6 +112,7 @@ struct Engine {
     Buf J, Ggf, pinv, skipped, deferred, Srhs, Lfac, dinv, xsol, resid, dfull, partial, errsum, slots, flags, skipped_cnt, dbg;
     int64_t n_deferred = 0;   // points the tiled Schur kernel leaves to the per-point kernel (structure only, known at bind time)
     int schur_tile_points = 256;
+    int schur_tile_fixed = 0; // SRK_SCHUR_TILE: force the tile size (0 = choose at bind time)
     int schur_impl = 0;       // 0 = DMMA tile kernel (schur_mma.cu), 1 = vector-FMA tile kernel (ba_kernels.cu)
     srk::PcgWorkspace pcg;
     int residual_blocks = 0;
@@ -279,20 +280,40 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     SRK_CUDA(cudaMemcpyAsync(e.cams_bound.p, e.cams_cur, sizeof(double) * 12 * M, cudaMemcpyDeviceToDevice, st));
     if (N > 0) SRK_CUDA(cudaMemcpyAsync(e.Xbound.p, e.X_cur, sizeof(double) * 3 * N, cudaMemcpyDeviceToDevice, st));
     srk::launch_cam_prep(st, M, e.cams_cur, e.Kd.as<double>(), e.shared_K, e.f0, e.camd_cur); e.launches += 1;
-    // ---- plan of the tiled Schur kernel: which points fall back to the per-point kernel (long tracks, scattered cameras)
+    // ---- plan of the tiled Schur kernel: which points fall back to the per-point kernel (long tracks, scattered cameras).
+    // Larger tiles amortise the per-tile table build and the flush of the accumulators, but a tile may only touch 12 cameras:
+    // take the largest tile size that defers (almost) no more points than the smallest one.  Structure only, once per bind.
     SRK_CUDA(e.deferred.ensure((size_t)(N > 0 ? N : 1)));
     e.n_deferred = 0;
     if (N > 0) {
-        SRK_CUDA(cudaMemsetAsync(e.skipped_cnt.p, 0, sizeof(unsigned long long), st));
-        srk::SchurSink none{};
-        srk::launch_schur_tile(st, N, O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), nullptr, 0.0, none, nullptr, nullptr,
-                               e.deferred.as<unsigned char>(), 1, nullptr, 0, nullptr);
-        srk::launch_count_skipped(st, N, e.deferred.as<unsigned char>(), e.skipped_cnt.as<unsigned long long>());
-        e.launches += 2;
-        unsigned long long nd = 0;
-        SRK_CUDA(cudaMemcpyAsync(&nd, e.skipped_cnt.p, sizeof(nd), cudaMemcpyDeviceToHost, st));
-        SRK_CUDA(cudaStreamSynchronize(st));
-        e.n_deferred = (int64_t)nd;
+        auto plan = [&](int tile, int64_t* out) -> int {
+            SRK_CUDA(cudaMemsetAsync(e.skipped_cnt.p, 0, sizeof(unsigned long long), st));
+            srk::launch_schur_plan(st, N, tile, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.deferred.as<unsigned char>(),
+                                   e.skipped_cnt.as<unsigned long long>());
+            e.launches += 1;
+            unsigned long long nd = 0;
+            SRK_CUDA(cudaMemcpyAsync(&nd, e.skipped_cnt.p, sizeof(nd), cudaMemcpyDeviceToHost, st));
+            SRK_CUDA(cudaStreamSynchronize(st));
+            *out = (int64_t)nd;
+            return SRK_OK;
+        };
+        int64_t nd_small = 0;
+        int rcp = plan(256, &nd_small);
+        if (rcp != SRK_OK) return rcp;
+        e.schur_tile_points = 256; e.n_deferred = nd_small;
+        if (e.schur_tile_fixed > 0) {
+            if (e.schur_tile_fixed != 256) { rcp = plan(e.schur_tile_fixed, &e.n_deferred); if (rcp != SRK_OK) return rcp; e.schur_tile_points = e.schur_tile_fixed; }
+        } else if (N >= 148 * 4 * 1024) {   // enough tiles to keep every SM busy for several waves
+            const int cands[2] = {1024, 512};
+            bool chosen = false;
+            for (int t : cands) {
+                int64_t nd = 0;
+                rcp = plan(t, &nd);
+                if (rcp != SRK_OK) return rcp;
+                if (nd <= nd_small + N / 1000) { e.schur_tile_points = t; e.n_deferred = nd; chosen = true; break; }
+            }
+            if (!chosen) { rcp = plan(256, &e.n_deferred); if (rcp != SRK_OK) return rcp; }   // restore the flags of the small tiling
+        }
     }
     SRK_CUDA(cudaStreamSynchronize(st));
     SRK_CUDA(cudaGetLastError());
@@ -648,6 +669,7 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     Engine* e = new Engine();
     e->device = dev;
     if (const char* v = std::getenv("SRK_SCHUR_IMPL")) e->schur_impl = std::atoi(v) == 1 ? 1 : 0;
+    if (const char* v = std::getenv("SRK_SCHUR_TILE")) { const int t = std::atoi(v); if (t >= 16 && t <= 4096 && t % 16 == 0) e->schur_tile_fixed = t; }
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; set_error("cudaStreamCreate failed"); return SRK_E_CUDA; }
     e->stream = e->own_stream;
     *h = e;
@@ -835,6 +857,16 @@ int srk_ba_debug_apply(void* h, const double* corrections, double* err_new) {
     int rc = fetch_attempt_scalars(e, false, &v, nullptr, nullptr);
     if (rc != SRK_OK) return rc;
     if (err_new != nullptr) *err_new = v;
+    return SRK_OK;
+}
+
+int srk_ba_solve_stats(void* h, int64_t* n_f, int64_t* block_rows, int64_t* nonzero_tiles, double* factor_flops) {
+    if (h == nullptr) { set_error("null handle"); return SRK_E_INVALID_ARG; }
+    Engine& e = *(Engine*)h;
+    if (!e.bound || e.solver_used != SRK_SOLVER_DENSE_CHOLESKY || e.dinv.p == nullptr) { set_error("no dense factor on this handle"); return SRK_E_NOT_BOUND; }
+    SRK_CUDA(cudaSetDevice(e.device));
+    if (n_f != nullptr) *n_f = e.nf;
+    if (srk::dense_cholesky_stats(e.stream, e.nf, e.dinv.as<double>(), block_rows, nonzero_tiles, factor_flops) != 0) { set_error("could not read the factor structure"); return SRK_E_CUDA; }
     return SRK_OK;
 }
 

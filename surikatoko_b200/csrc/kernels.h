@@ -22,6 +22,8 @@ void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin
 // DMMA formulation of the same accumulation (schur_mma.cu); same deferral rule as the plan pass of launch_schur_tile.
 void launch_schur_mma(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
                       const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred);
+void launch_schur_plan(cudaStream_t st, int64_t N, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, unsigned char* deferred,
+                       unsigned long long* n_deferred);
 void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
                        const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred, int plan_only,
                        unsigned long long* plan_keys, unsigned plan_mask, int* plan_overflow);
@@ -48,6 +50,7 @@ void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, 
 // X (rows x 64 at A, lda) <- X * Linv^T with Linv a column-major 64x64 lower-triangular inverse (right-side triangular solve of one block column)
 void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block);
 int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev);
+int dense_cholesky_stats(cudaStream_t st, int n, const double* ws, int64_t* nblk, int64_t* nz_tiles, double* factor_flops);
 int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
 int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
 // mirror the lower triangle into the upper one

@@ -13,15 +13,23 @@ __global__ void k_prep_obs(int64_t O, int64_t N, int M, const int32_t* __restric
                            const double* __restrict__ obs_xy, double f0, double* __restrict__ x, double* __restrict__ y, int64_t* __restrict__ pt_begin,
                            unsigned long long* __restrict__ cam_count, int* __restrict__ err_flag) {
     int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= O) return;
-    int p = obs_pt[o], c = obs_cam[o];
-    if (p < 0 || p >= N || c < 0 || c >= M) { atomicOr(err_flag, 1); return; }
-    int pp = o > 0 ? obs_pt[o - 1] : -1, pc = o > 0 ? obs_cam[o - 1] : -1;
-    if (p < pp || (p == pp && c <= pc)) atomicOr(err_flag, 2);
-    x[o] = obs_xy[2 * o] / f0; y[o] = obs_xy[2 * o + 1] / f0;   // x/f0, y/f0 of BA.cpp:475-479, formed once
-    if (p != pp) for (int q = (pp < 0 ? 0 : pp + 1); q <= p; ++q) pt_begin[q] = o;
-    if (o == O - 1) for (int64_t q = p + 1; q <= N; ++q) pt_begin[q] = O;
-    atomicAdd(&cam_count[c], 1ULL);
+    int c = -1;
+    if (o < O) {
+        int p = obs_pt[o];
+        c = obs_cam[o];
+        if (p < 0 || p >= N || c < 0 || c >= M) { atomicOr(err_flag, 1); c = -1; }
+        else {
+            int pp = o > 0 ? obs_pt[o - 1] : -1, pc = o > 0 ? obs_cam[o - 1] : -1;
+            if (p < pp || (p == pp && c <= pc)) atomicOr(err_flag, 2);
+            const double2 xy = reinterpret_cast<const double2*>(obs_xy)[o];
+            x[o] = xy.x / f0; y[o] = xy.y / f0;   // x/f0, y/f0 of BA.cpp:475-479, formed once
+            if (p != pp) for (int q = (pp < 0 ? 0 : pp + 1); q <= p; ++q) pt_begin[q] = o;
+            if (o == O - 1) for (int64_t q = p + 1; q <= N; ++q) pt_begin[q] = O;
+        }
+    }
+    // histogram with one atomic per distinct camera of the warp (point-major order: ~10 cameras per 32 observations)
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    if (c >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cam_count[c], (unsigned long long)__popc(peers));
 }
 
 __global__ void k_scan_counts(int M, const unsigned long long* __restrict__ cnt, int64_t* __restrict__ cam_begin, unsigned long long* __restrict__ cursor) {
@@ -54,8 +62,14 @@ __global__ void k_scatter_by_cam(int64_t O, const int32_t* __restrict__ obs_cam,
                                  const double* __restrict__ y, unsigned long long* __restrict__ cursor, int32_t* __restrict__ c_pt,
                                  double* __restrict__ c_x, double* __restrict__ c_y) {
     int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= O) return;
-    unsigned long long pos = atomicAdd(&cursor[obs_cam[o]], 1ULL);
+    const int c = o < O ? obs_cam[o] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (c >= 0 && lane == leader) base = atomicAdd(&cursor[c], (unsigned long long)__popc(peers));   // one atomic per distinct camera of the warp
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (c < 0) return;
+    const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
     c_pt[pos] = obs_pt[o]; c_x[pos] = x[o]; c_y[pos] = y[o];
 }
 

@@ -44,6 +44,7 @@ struct MmaSmem {
     int hash[kMmaHash];
     int slot_obs[kMmaBP][16];
     int blk[kMmaCams * kMmaCams];
+    int gidx[kMmaRows];    // local row (slot*10 + a) -> gauge-reduced global index, -1 for a removed variable or an empty slot
     int n_local;
 };
 
@@ -79,20 +80,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        int n = 0;
+    if (tid < kMmaHash) {   // rank of every distinct camera = number of smaller ones; the table keeps the kMmaCams smallest ids, sorted
+        const int cam = sm.hash[tid];
+        int rank = 0, total = 0;
         for (int i = 0; i < kMmaHash; ++i) {
-            const int cam = sm.hash[i];
-            if (cam < 0) continue;
-            int pos = n < kMmaCams ? n : kMmaCams;
-            while (pos > 0 && sm.tab[pos - 1] > cam) --pos;
-            if (pos >= kMmaCams) continue;
-            const int last = n < kMmaCams ? n : kMmaCams - 1;
-            for (int q = last; q > pos; --q) sm.tab[q] = sm.tab[q - 1];
-            sm.tab[pos] = cam;
-            if (n < kMmaCams) ++n;
+            const int other = sm.hash[i];
+            total += other >= 0;
+            rank += (other >= 0 && other < cam);
         }
-        sm.n_local = n;
+        if (cam >= 0 && rank < kMmaCams) sm.tab[rank] = cam;
+        if (tid == 0) sm.n_local = total < kMmaCams ? total : kMmaCams;
     }
     __syncthreads();
     const int nLocal = sm.n_local;
@@ -103,21 +100,45 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t
         }
     }
 
+    for (int m = tid; m < kMmaRows; m += kMmaThreads) {
+        const int slot = m / 10, a = m - 10 * slot;
+        sm.gidx[m] = slot < nLocal ? red_index(sm.tab[slot], a, sink.unity) : -1;
+    }
+
     const int nbatch = (int)((p1 - p0 + kMmaBP - 1) / kMmaBP);
     const bool producer = w >= 8;
 
-    // ---- producer: stage one batch (16 points, half-warp per point) into buffer `buf`
-    auto stage = [&](int b, int buf) {
-        const int h = lane >> 4, hl = lane & 15;
+    // ---- producer: stage one batch (16 points, half-warp per point) into buffer `buf`.  (kb, k) = first observation and track
+    // length of this half-warp's point, loaded one batch ahead; every global load of the batch is issued before the first use.
+    const int h = lane >> 4, hl = lane & 15;
+    auto load_track = [&](int b, int64_t& kb, int& k) {
+        const int64_t j = p0 + (int64_t)b * kMmaBP + 2 * (w - 8) + h;
+        kb = 0; k = 0;
+        if (b < nbatch && j < p1) { kb = pt_begin[j]; k = (int)(pt_begin[j + 1] - kb); }
+    };
+    auto load_cam = [&](int64_t kb, int k) { return (k <= 16 && hl < k) ? obs_cam[kb + hl] : -1; };
+    auto stage = [&](int b, int buf, int64_t kb, int k, int cam) {
         const int pl = 2 * (w - 8) + h;                    // point of the batch
         const int64_t j = p0 + (int64_t)b * kMmaBP + pl;
         const bool valid = j < p1;
-        int64_t kb = 0; int k = 0;
-        if (valid) { kb = pt_begin[j]; k = (int)(pt_begin[j + 1] - kb); }
         bool bad = k > 16;
+        const bool active = valid && !bad && hl < k;       // this lane carries one observation of the point
+        double rx = 0.0, ry = 0.0, jp[6], jc[20];
+        if (active) {
+            const int64_t o = kb + hl;
+            rx = J[o]; ry = J[O + o];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+#pragma unroll
+            for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) jp[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 20; ++i) jc[i] = 0.0;
+        }
         int loc = -1;
-        if (valid && !bad && hl < k) {
-            const int cam = obs_cam[kb + hl];
+        if (active) {
             for (int q = 0; q < nLocal; ++q) if (sm.tab[q] == cam) loc = q;
             if (loc < 0) bad = true;
         }
@@ -128,12 +149,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t
         double a9[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) a9[i] = 0.0;
-        if (use && hl < k) {
-            const int64_t o = kb + hl;
-            const double rx = J[o], ry = J[O + o];
-            double jp[6];
-#pragma unroll
-            for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+        if (use && active) {
             a9[0] = jp[0] * jp[0] + jp[1] * jp[1];
             a9[1] = jp[0] * jp[2] + jp[1] * jp[3];
             a9[2] = jp[0] * jp[4] + jp[1] * jp[5];
@@ -148,7 +164,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t
         for (int i = 0; i < 9; ++i) {
             double v = a9[i];
 #pragma unroll
-            for (int s = 8; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);   // stays inside the half-warp
+            for (int s2 = 8; s2 > 0; s2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s2);   // stays inside the half-warp
             a9[i] = 2.0 * v;
         }
         double inv[6];
@@ -170,67 +186,63 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t
             }
             sm.T[buf][3 * pl + hl] = t;
         }
-        // slot -> observation of this point
-        sm.slot_obs[pl][hl] = -1;
+        // which table slots does this point fill?
+        sm.slot_obs[pl][hl] = 0;
         __syncwarp();
-        if (contrib && hl < k) sm.slot_obs[pl][loc] = hl;
+        if (contrib && active) sm.slot_obs[pl][loc] = 1;
         __syncwarp();
-        if (hl < kMmaCams) {
-            const int oi = sm.slot_obs[pl][hl];
+        if (contrib && active) {
+            double* Fr = sm.F[buf] + (3 * pl) * kMmaSLD + 10 * loc;
+            double* Wr = sm.W[buf] + (3 * pl) * kMmaSLD + 10 * loc;
+#pragma unroll
+            for (int a = 0; a < 10; a += 2) {
+                double f[3][2], ww[3][2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const double j0 = jc[(a + u) * 2], j1 = jc[(a + u) * 2 + 1];
+                    f[0][u] = 2.0 * (jp[0] * j0 + jp[1] * j1);
+                    f[1][u] = 2.0 * (jp[2] * j0 + jp[3] * j1);
+                    f[2][u] = 2.0 * (jp[4] * j0 + jp[5] * j1);
+                    ww[0][u] = inv[0] * f[0][u] + inv[1] * f[1][u] + inv[2] * f[2][u];
+                    ww[1][u] = inv[1] * f[0][u] + inv[3] * f[1][u] + inv[4] * f[2][u];
+                    ww[2][u] = inv[2] * f[0][u] + inv[4] * f[1][u] + inv[5] * f[2][u];
+                }
+#pragma unroll
+                for (int v = 0; v < 3; ++v) {
+                    *reinterpret_cast<double2*>(Fr + v * kMmaSLD + a) = make_double2(f[v][0], f[v][1]);
+                    *reinterpret_cast<double2*>(Wr + v * kMmaSLD + a) = make_double2(ww[v][0], ww[v][1]);
+                }
+            }
+        }
+        if (hl < kMmaCams && sm.slot_obs[pl][hl] == 0) {   // slots the point does not see (all of them for an absent / skipped / deferred point)
             double* Fr = sm.F[buf] + (3 * pl) * kMmaSLD + 10 * hl;
             double* Wr = sm.W[buf] + (3 * pl) * kMmaSLD + 10 * hl;
-            if (oi >= 0) {
-                const int64_t o = kb + oi;
-                double jp[6];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+            for (int v = 0; v < 3; ++v)
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    double jc[10];
-#pragma unroll
-                    for (int i = 0; i < 10; ++i) jc[i] = J[(int64_t)(8 + 10 * half + i) * O + o];
-#pragma unroll
-                    for (int a2 = 0; a2 < 5; a2 += 2) {
-                        // variables a = 5*half + a2 (and a + 1 when it stays inside this half)
-                        const int a = 5 * half + a2;
-                        const int na = (a2 + 1 < 5) ? 2 : 1;
-                        double f[3][2], ww[3][2];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            const double j0 = u < na ? jc[(a2 + u) * 2] : 0.0, j1 = u < na ? jc[(a2 + u) * 2 + 1] : 0.0;
-                            f[0][u] = 2.0 * (jp[0] * j0 + jp[1] * j1);
-                            f[1][u] = 2.0 * (jp[2] * j0 + jp[3] * j1);
-                            f[2][u] = 2.0 * (jp[4] * j0 + jp[5] * j1);
-                            ww[0][u] = inv[0] * f[0][u] + inv[1] * f[1][u] + inv[2] * f[2][u];
-                            ww[1][u] = inv[1] * f[0][u] + inv[3] * f[1][u] + inv[4] * f[2][u];
-                            ww[2][u] = inv[2] * f[0][u] + inv[4] * f[1][u] + inv[5] * f[2][u];
-                        }
-#pragma unroll
-                        for (int v = 0; v < 3; ++v)
-#pragma unroll
-                            for (int u = 0; u < 2; ++u)
-                                if (u < na) { Fr[v * kMmaSLD + a + u] = f[v][u]; Wr[v * kMmaSLD + a + u] = ww[v][u]; }
-                    }
+                for (int a = 0; a < 10; a += 2) {
+                    *reinterpret_cast<double2*>(Fr + v * kMmaSLD + a) = make_double2(0.0, 0.0);
+                    *reinterpret_cast<double2*>(Wr + v * kMmaSLD + a) = make_double2(0.0, 0.0);
                 }
-            } else {
-#pragma unroll
-                for (int v = 0; v < 3; ++v)
-#pragma unroll
-                    for (int a = 0; a < 10; a += 2) {
-                        *reinterpret_cast<double2*>(Fr + v * kMmaSLD + a) = make_double2(0.0, 0.0);
-                        *reinterpret_cast<double2*>(Wr + v * kMmaSLD + a) = make_double2(0.0, 0.0);
-                    }
-            }
         }
     };
 
     // Producers and consumers run separate loops with the same number of CTA-wide barriers (bar.sync 0 counts arrivals, it
     // does not care from which instruction they come), so the consumers' accumulators are not live in the producer code.
     if (producer) {
-        stage(0, 0);
+        // software pipeline over batches: track extents two batches ahead, camera ids one batch ahead, Jacobian rows in the batch itself
+        int64_t kb0, kb1; int k0, k1, cam0, cam1;
+        load_track(0, kb0, k0);
+        load_track(1, kb1, k1);
+        cam0 = load_cam(kb0, k0);
+        cam1 = load_cam(kb1, k1);
+        stage(0, 0, kb0, k0, cam0);
         cta_barrier();
-        for (int b = 0; b < nbatch; ++b) {
-            if (b + 1 < nbatch) stage(b + 1, (b & 1) ^ 1);
+        for (int b = 0; b < nbatch; ++b) {   // consumers work on batch b while batch b+1 is staged
+            kb0 = kb1; k0 = k1; cam0 = cam1;
+            load_track(b + 2, kb1, k1);
+            if (b + 1 < nbatch) stage(b + 1, (b & 1) ^ 1, kb0, k0, cam0);
+            cam1 = load_cam(kb1, k1);
             cta_barrier();
         }
         return;
@@ -301,40 +313,108 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t
         cta_barrier();
     }
 
-    // ---- flush: one red.global.add.f64 per touched entry per tile
+    // ---- flush: one red.global.add.f64 per touched entry per tile.  Index work comes from the per-tile tables (gidx, blk); the
+    // loops stay unrolled (register accumulators) but the body is a handful of instructions.
+    const bool dense = sink.blocks == nullptr;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         if (q >= nsb) break;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) {
+            const int row = 24 * sbI[q] + 8 * i + g;
+            const int ri = sm.gidx[row], si = row / 10;
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const double v = acc[q][i][jj][e];
-                    if (v == 0.0) continue;
-                    const int row = 24 * sbI[q] + 8 * i + g, col = 24 * sbJ[q] + 8 * jj + 2 * tg + e;
-                    const int si = row / 10, a = row - 10 * si, sl = col / 10, bq = col - 10 * sl;
-                    if (si >= nLocal || sl > si) continue;
-                    const int cam_i = sm.tab[si], cam_l = sm.tab[sl];
-                    const int blk = sink.blocks != nullptr ? sm.blk[si * kMmaCams + sl] : -1;
-                    if (si != sl) {
-                        sink_add(sink, blk, cam_i, a, cam_l, bq, -v);
-                    } else if (a >= bq) {          // diagonal block: the lower triangle is computed once and mirrored inside the block
-                        sink_add(sink, blk, cam_i, a, cam_l, bq, -v);
-                        if (a != bq) sink_add(sink, blk, cam_i, bq, cam_l, a, -v);
+                    const int col = 24 * sbJ[q] + 8 * jj + 2 * tg + e;
+                    const int ci = sm.gidx[col], sl = col / 10;
+                    // lower block triangle; inside a diagonal block the lower triangle (row >= col) is computed once
+                    if (v == 0.0 || ri < 0 || ci < 0 || sl > si || (sl == si && col > row)) continue;
+                    if (dense) {
+                        atomicAdd(&sink.S[(size_t)ci * sink.ld + ri], -v);
+                    } else {
+                        const int blk = sm.blk[si * kMmaCams + sl];
+                        if (blk < 0) continue;
+                        const int a = row - 10 * si, bq = col - 10 * sl;
+                        atomicAdd(&sink.blocks[(size_t)blk * 100 + a * 10 + bq], -v);
+                        if (sl == si && a != bq) atomicAdd(&sink.blocks[(size_t)blk * 100 + bq * 10 + a], -v);   // stored diagonal blocks are full
                     }
                 }
+        }
     }
     if (w == 7) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int m = lane + 32 * q;
-            if (m >= kMmaRows) continue;
-            const int s = m / 10, a = m - 10 * s;
-            if (s < nLocal && racc[q] != 0.0) sink_add_rhs(sink, sm.tab[s], a, racc[q]);
+            if (m >= kMmaRows || racc[q] == 0.0) continue;
+            const int r = sm.gidx[m];
+            if (r < 0) continue;
+            const int slot = m / 10;
+            if (dense) atomicAdd(&sink.rhs[r], racc[q]);
+            else atomicAdd(&sink.rhs[(size_t)sm.tab[slot] * 10 + (m - 10 * slot)], racc[q]);
         }
     }
+}
+
+// Bind-time plan of the dense path: which points the tile kernel will leave to the per-point kernel (structure only: more than
+// 16 observations, or a camera outside the tile's table) and how many there are.  Same table construction as k_schur_mma; one
+// thread per point.
+__global__ void __launch_bounds__(256) k_schur_plan(int64_t N, int tile_points, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam,
+                                                    unsigned char* __restrict__ deferred, unsigned long long* __restrict__ n_deferred) {
+    __shared__ int hash[kMmaHash];
+    __shared__ int tab[kMmaCams];
+    __shared__ int n_local;
+    const int tid = threadIdx.x;
+    const int64_t p0 = (int64_t)blockIdx.x * tile_points;
+    const int64_t p1 = min(N, p0 + (int64_t)tile_points);
+    if (p0 >= N) return;
+    for (int i = tid; i < kMmaHash; i += blockDim.x) hash[i] = -1;
+    __syncthreads();
+    const int64_t ob = pt_begin[p0], oe = pt_begin[p1];
+    for (int64_t o = ob + tid; o < oe; o += blockDim.x) {
+        const int cam = obs_cam[o];
+        unsigned h = ((unsigned)cam * 2654435761u) >> 26;
+        for (int probe = 0; probe < kMmaHash; ++probe) {
+            const int prev = atomicCAS(&hash[h], -1, cam);
+            if (prev == -1 || prev == cam) break;
+            h = (h + 1) & (kMmaHash - 1);
+        }
+    }
+    __syncthreads();
+    if (tid < kMmaHash) {
+        const int cam = hash[tid];
+        int rank = 0, total = 0;
+        for (int i = 0; i < kMmaHash; ++i) { const int other = hash[i]; total += other >= 0; rank += (other >= 0 && other < cam); }
+        if (cam >= 0 && rank < kMmaCams) tab[rank] = cam;
+        if (tid == 0) n_local = total < kMmaCams ? total : kMmaCams;
+    }
+    __syncthreads();
+    const int nLocal = n_local;
+    int mine = 0;
+    for (int64_t j = p0 + tid; j < p1; j += blockDim.x) {
+        const int64_t kb = pt_begin[j];
+        const int k = (int)(pt_begin[j + 1] - kb);
+        bool bad = k > 16;
+        for (int i = 0; i < k && !bad; ++i) {
+            const int cam = obs_cam[kb + i];
+            bool found = false;
+            for (int q = 0; q < nLocal; ++q) found |= tab[q] == cam;
+            bad = !found;
+        }
+        deferred[j] = bad ? 1 : 0;
+        mine += bad;
+    }
+    mine = __syncthreads_count(mine) > 0 ? mine : 0;
+    for (int s2 = 16; s2 > 0; s2 >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, s2);
+    if ((tid & 31) == 0 && mine > 0) atomicAdd(n_deferred, (unsigned long long)mine);
+}
+
+void launch_schur_plan(cudaStream_t st, int64_t N, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, unsigned char* deferred,
+                       unsigned long long* n_deferred) {
+    if (N <= 0) return;
+    k_schur_plan<<<(unsigned)((N + tile_points - 1) / tile_points), 256, 0, st>>>(N, tile_points, pt_begin, obs_cam, deferred, n_deferred);
 }
 
 void launch_schur_mma(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
