@@ -11,7 +11,7 @@ python - <<PY
 import json
 d=json.load(open('$OUT/bench_${TAG}.json'))
 print('ms/step', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'])
-for k,v in d['kernels'].items(): print(' ', k, round(v['avg_ms'],3), round(v.get('frac',0),3))
+for k,v in d['kernels'].items(): print(' ', k, round(v.get('avg_ms',0),3), round(v.get('frac',0),3))
 PY
 if [ "$2" != "noncu" ]; then
 timeout 900 ncu --set full --import-source on --clock-control none -k 'regex:k_jacobian|k_residual$|k_schur_mma|k_backsub|k_frame_blocks' -c 9 -o $OUT/prof_stream_${TAG} -f python bench.py --steps 1 --warmup 1 --no-cpu > $OUT/ncu_stream_${TAG}.log 2>&1; echo "ncu rc=$?"
