@@ -44,8 +44,8 @@ __device__ __forceinline__ double fast_rcp(double d) {   // 1/d to ~1 ulp
     x = x + x * (1.0 - d * x);
     return x;
 }
-__global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ dinv, int* __restrict__ info,
-                                                     unsigned char* __restrict__ F, int nblk) {
+template <bool CG>
+__device__ void potrf64_inv_dev(int n, int k0, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk) {
     constexpr int G = 4, E = NB / G;
     __shared__ double col[2][NB];
     __shared__ double wrow[2][NB];
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __re
 #pragma unroll
     for (int i = 0; i < E; ++i) {
         const int c = grp + G * i;
-        t[i] = (r < nb && c < nb && r >= c) ? A[(size_t)(k0 + c) * ld + k0 + r] : ((r == c) ? 1.0 : 0.0);
+        t[i] = (r < nb && c < nb && r >= c) ? (CG ? __ldcg(A + (size_t)(k0 + c) * ld + k0 + r) : A[(size_t)(k0 + c) * ld + k0 + r]) : ((r == c) ? 1.0 : 0.0);
         w[i] = (r == c) ? 1.0 : 0.0;
     }
     if (tid == 0) F[(size_t)(k0 / NB) * nblk + k0 / NB] = 1;
@@ -95,6 +95,10 @@ __global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __re
         if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = t[i] * rsqrt(dv[c]);
         dinv[(size_t)c * NB + r] = (r >= c) ? w[i] * rsr : 0.0;                   // column-major 64x64: Linv(r, c)
     }
+}
+__global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ dinv, int* __restrict__ info,
+                                                     unsigned char* __restrict__ F, int nblk) {
+    potrf64_inv_dev<false>(n, k0, A, ld, dinv, info, F, nblk);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -385,6 +389,181 @@ __global__ void __launch_bounds__(256) k_right_solve_dmma(int rows, int row0, do
             const int c = wc + j * 8 + tg * 2;
             if (row < rows) { A[(size_t)c * lda + row] = acc[i][j][0]; A[(size_t)(c + 1) * lda + row] = acc[i][j][1]; }
         }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Sparse-factor path of the factorisation.  The reduced camera system of a scene with localized visibility is block-banded
+// (plus the wrap-around rows of a closed camera ring): per 64-column step there are a handful of non-zero tiles, the ~1.4 GFLOP of
+// the whole factorisation are nothing, and the run time of the launch-per-operation path above is the latency of ~630 dependent
+// kernel launches.  Here ONE thread-block cluster of 8 CTAs walks the block columns inside a single kernel:
+//     sync A | every CTA lists the non-zero row tiles of column k (F) | right solves X = A(r,k) Linv_k^T, one tile per CTA |
+//     sync B | tile-pair updates C(ra,rb) -= X_a X_b^T spread over CTAs 1..7, fill marked in F |
+//            | CTA 0: update of the next diagonal tile, then potrf of column k+1 (look-ahead: overlaps the other updates)
+// barrier.cluster (release/acquire, ~0.2 us) orders the global-memory tile traffic between the CTAs; tile operands are read with
+// cp.async.cg / ld.global.cg (L2, never a stale L1 line).  F starts as the non-zero tile pattern of the input (k_tile_pattern),
+// fill is tracked symbolically as updates are applied, so the structure handed to the substitutions is exact.
+constexpr int kBandCluster = 8;
+constexpr int kBandTS = NB + 4;        // [k][row] tile stride in shared memory: 68 = 4 (mod 16), conflict-free fragment loads
+constexpr int kBandMaxFill = 4;        // sparse path when the input has <= kBandMaxFill * nblk non-zero off-diagonal tiles
+struct BandSmem {
+    double A[NB * kBandTS];
+    double B[NB * kBandTS];
+    int rows[kMaxRowBlocks];
+    int m;
+};
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+
+// non-zero pattern of the lower 64x64 tiles of A (column-major): F0[c*nblk + r] = 1 iff tile (r, c), r > c, holds a non-zero; count += 1
+__global__ void __launch_bounds__(256) k_tile_pattern(int n, const double* __restrict__ A, int64_t ld, int nblk, unsigned char* __restrict__ F, int* __restrict__ count) {
+    const int c = blockIdx.x, r = blockIdx.y;
+    if (r <= c) return;
+    const int tid = threadIdx.x;
+    int nz = 0;
+#pragma unroll 4
+    for (int it = 0; it < 8; ++it) {        // 64 columns x 32 pairs of rows
+        const int v = tid + 256 * it;
+        const int q = v >> 5, rp = (v & 31) * 2;
+        const int row = r * NB + rp, col = c * NB + q;
+        if (col < n && row + 1 < n) { const double2 x = *reinterpret_cast<const double2*>(A + (size_t)col * ld + row); nz |= (x.x != 0.0) | (x.y != 0.0); }
+        else if (col < n && row < n) nz |= A[(size_t)col * ld + row] != 0.0;
+    }
+    nz = __syncthreads_or(nz);
+    if (tid == 0 && nz) { F[(size_t)c * nblk + r] = 1; atomicAdd(count, 1); }
+}
+
+// s[q*TS + rr] = g(row0 + rr, col0 + q), zero outside the matrix
+__device__ __forceinline__ void band_load_tile(double* s, const double* g, int64_t ld, int row0, int col0, int n) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int v = tid + 256 * it;
+        const int q = v >> 5, rp = (v & 31) * 2;
+        const int row = row0 + rp;
+        int bytes = (n - row) * 8; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+        if (col0 + q >= n) bytes = 0;
+        cp_async16(s + q * kBandTS + rp, g + (bytes > 0 ? (size_t)(col0 + q) * ld + row : 0), bytes);
+    }
+}
+// acc = A_tile(64 x 64) * B_tile(64 x 64)^T from the [k][row] shared-memory tiles; warp (wr, wc) owns 32 x 16
+__device__ __forceinline__ void band_tile_nt(const double* sA, const double* sB, double (&acc)[4][2][2]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16;
+    const int g = lane >> 2, tg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+#pragma unroll 4
+    for (int ks = 0; ks < NB; ks += 4) {
+        double af[4], bf[2];
+        const double* pa = sA + (ks + tg) * kBandTS + wr + g;
+        const double* pb = sB + (ks + tg) * kBandTS + wc + g;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = pa[i * 8];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) bf[j] = pb[j * 8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+}
+
+__global__ void __cluster_dims__(kBandCluster, 1, 1) __launch_bounds__(256, 1)
+k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk) {
+    extern __shared__ __align__(16) unsigned char band_raw[];
+    BandSmem& sm = *reinterpret_cast<BandSmem*>(band_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = (int)cluster_cta_rank();
+    const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16, g = lane >> 2, tg = lane & 3;
+
+    auto solve_tile = [&](int r, int k) {     // A(r,k) <- A(r,k) * Linv_k^T, in place
+        __syncthreads();
+        band_load_tile(sm.A, A, ld, r * NB, k * NB, n);
+        {   // sB[q*TS + c] = Linv(c, q) = dinv_k[q*64 + c]
+            const double* dk = dinv + (size_t)k * NB * NB;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int v = tid + 256 * it;
+                const int q = v >> 5, cp = (v & 31) * 2;
+                cp_async16(sm.B + q * kBandTS + cp, dk + (size_t)q * NB + cp, 16);
+            }
+        }
+        cp_async_commit(); cp_async_wait<0>();
+        __syncthreads();
+        double acc[4][2][2];
+        band_tile_nt(sm.A, sm.B, acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = r * NB + wr + 8 * i + g, col = k * NB + wc + 8 * j + 2 * tg + e;
+                    if (row < n && col < n) A[(size_t)col * ld + row] = acc[i][j][e];
+                }
+    };
+    auto update_pair = [&](int ra, int rb, int k) {   // A(ra, rb) -= X(ra,k) X(rb,k)^T   (ra >= rb > k)
+        __syncthreads();
+        band_load_tile(sm.A, A, ld, ra * NB, k * NB, n);
+        band_load_tile(sm.B, A, ld, rb * NB, k * NB, n);
+        cp_async_commit(); cp_async_wait<0>();
+        __syncthreads();
+        double acc[4][2][2];
+        band_tile_nt(sm.A, sm.B, acc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = ra * NB + wr + 8 * i + g, col = rb * NB + wc + 8 * j + 2 * tg + e;
+                    if (row < n && col < n && row >= col) {
+                        double* p = A + (size_t)col * ld + row;
+                        *p = __ldcg(p) - acc[i][j][e];
+                    }
+                }
+        if (tid == 0 && ra != rb) F[(size_t)rb * nblk + ra] = 1;   // fill (or already non-zero)
+    };
+
+    if (rank == 0) potrf64_inv_dev<true>(n, 0, A, ld, dinv, info, F, nblk);
+    for (int k = 0; k < nblk; ++k) {
+        cluster_sync_all();                                   // A: potrf(k) and the updates of step k-1 are visible
+        // non-zero row tiles of column k, ascending
+        if (warp == 0) {
+            int m = 0;
+            for (int base = k + 1; base < nblk; base += 32) {
+                const int r = base + lane;
+                const bool nz = r < nblk && __ldcg(F + (size_t)k * nblk + r) != 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                if (nz) sm.rows[m + __popc(bal & ((1u << lane) - 1))] = r;
+                m += __popc(bal);
+            }
+            if (lane == 0) sm.m = m;
+        }
+        __syncthreads();
+        const int m = sm.m;
+        for (int i = rank; i < m; i += kBandCluster) solve_tile(sm.rows[i], k);
+        cluster_sync_all();                                   // B: every X(r,k) is visible
+        const bool next_in_list = m > 0 && sm.rows[0] == k + 1;
+        const int npairs = m * (m + 1) / 2;
+        if (rank == 0) {
+            if (next_in_list) update_pair(k + 1, k + 1, k);
+            __syncthreads();
+            if (k + 1 < nblk) potrf64_inv_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk);
+        } else {
+            for (int p = (next_in_list ? 1 : 0) + (rank - 1); p < npairs; p += kBandCluster - 1) {
+                int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
+                while (a * (a + 1) / 2 > p) --a;
+                while ((a + 1) * (a + 2) / 2 <= p) ++a;
+                const int b = p - a * (a + 1) / 2;
+                update_pair(sm.rows[a], sm.rows[b], k);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -797,6 +976,35 @@ static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
 struct FactorGraph { int n = 0; double* A = nullptr; int64_t ld = 0; double* ws = nullptr; int* info = nullptr; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
 static FactorGraph g_fg;
 
+// Sparse-factor path: tile pattern of the input, then (when it is sparse enough) the single-cluster kernel.  Returns the number of
+// launches, or 0 when the matrix is not sparse and the launch-per-operation path has to run.
+static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
+    const int nblk = chol_nblk(n);
+    if (nblk < 2 || nblk > kMaxRowBlocks) return 0;
+    static int force = -1;    // SRK_CHOL_PATH=dense disables the sparse path, =band forces it (development aid)
+    if (force < 0) { const char* e = getenv("SRK_CHOL_PATH"); force = e == nullptr ? 0 : (e[0] == 'd' ? 1 : (e[0] == 'b' ? 2 : 0)); }
+    if (force == 1) return 0;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(k_band_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BandSmem)) != cudaSuccess) { cudaGetLastError(); return 0; }
+        attr = true;
+    }
+    unsigned char* F = ws_F(ws, n);
+    int* cnt = ws_nzt(ws, n);
+    cudaMemsetAsync(info_dev, 0, sizeof(int), st);
+    cudaMemsetAsync(ws_flags(ws, n), 0, sizeof(int) * nblk, st);
+    cudaMemsetAsync(F, 0, (size_t)nblk * nblk, st);
+    cudaMemsetAsync(cnt, 0, sizeof(int) * 2, st);
+    k_tile_pattern<<<dim3(nblk, nblk), 256, 0, st>>>(n, A, ld, nblk, F, cnt);
+    int h = -1;
+    if (cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (h < 0 || (force != 2 && h > kBandMaxFill * nblk)) return 0;
+    k_band_chol<<<kBandCluster, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk);
+    if (cudaGetLastError() != cudaSuccess) return 0;
+    k_build_trsv_lists<<<1, 1024, 0, st>>>(n, nblk, F, ws_nzt(ws, n), ws_list(ws, n, 0), ws_list(ws, n, 1));
+    return 3;
+}
+
 int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
     set_attrs_once();
     g_epoch = 0;
@@ -804,6 +1012,14 @@ int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
     if (prof_env < 0) { const char* e = getenv("SRK_CHOL_PROFILE"); prof_env = (e != nullptr && e[0] == '1') ? 1 : 0; }
     g_prof = prof_env == 1;
     if (g_prof) return enqueue_factor(st, n, A, ld, ws, info_dev);
+    {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {   // the pattern read-back synchronises: not inside somebody's capture
+            const int64_t nl = try_band_factor(st, n, A, ld, ws, info_dev);
+            if (nl > 0) return nl;
+        }
+    }
     if (g_fg.exec != nullptr && g_fg.n == n && g_fg.A == A && g_fg.ld == ld && g_fg.ws == ws && g_fg.info == info_dev) {
         if (cudaGraphLaunch(g_fg.exec, st) == cudaSuccess) return g_fg.launches;
         cudaGetLastError();
