@@ -96,6 +96,189 @@ __device__ void potrf64_inv_dev(int n, int k0, double* A, int64_t ld, double* di
         dinv[(size_t)c * NB + r] = (r >= c) ? w[i] * rsr : 0.0;                   // column-major 64x64: Linv(r, c)
     }
 }
+// ---------------------------------------------------------------------------------------------------------------------
+// Blocked variant of the 64x64 diagonal-block kernel (used on the latency chain of the sparse-factor path): four 16-column
+// panels.  The 16x16 diagonal block of a panel is factored by ONE warp entirely in registers (lane r holds row r, the
+// pivot column travels by shuffles: no barrier inside the 16 steps, ~150 cycles per pivot instead of ~1000 with a CTA barrier
+// per pivot); the rows below are solved by substitution, one thread per row; the trailing part of the tile is updated by all
+// threads.  L^-1 is then assembled from the 16x16 diagonal inverses (substitution, one thread per column) and three levels of
+// 16x16 block products  M_ij = -M_ii sum_k L_ik M_kj.  scratch: 2 * 64 * 65 doubles of shared memory.
+__device__ long long g_potrf_prof[8];
+constexpr int kPotrfLDT = 65;
+constexpr size_t kPotrfScratchDoubles = 2 * NB * kPotrfLDT;
+template <bool CG>
+__device__ __noinline__ void potrf64_blk_dev(int n, int k0, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk, double* scratch, long long* prof = nullptr) {
+    long long tp_ = clock64();
+#define POTRF_T(slot) do { if (prof != nullptr && threadIdx.x == 0) { const long long now_ = clock64(); prof[slot] += now_ - tp_; tp_ = now_; } } while (0)
+    constexpr int LDT = kPotrfLDT;
+    double* T = scratch;                 // T[r*LDT + c]
+    double* M = scratch + NB * LDT;      // M[r*LDT + c] = Linv(r, c)
+    __shared__ double P[3][16][17];
+    __shared__ double rsd[NB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = min(NB, n - k0);
+    __syncthreads();                     // the scratch region may still be read as operand tiles by the caller
+#pragma unroll
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int c = e >> 6, r = e & 63;
+        double v = (r == c) ? 1.0 : 0.0;
+        if (r < nb && c < nb && r >= c) { const double* src = A + (size_t)(k0 + c) * ld + k0 + r; v = CG ? __ldcg(src) : *src; }
+        T[r * LDT + c] = v;
+        M[r * LDT + c] = 0.0;
+    }
+    if (tid == 0) F[(size_t)(k0 / NB) * nblk + k0 / NB] = 1;
+    __syncthreads();
+    POTRF_T(0);
+#pragma unroll 1                         // code size: the body is executed once per call, unrolling it only adds instruction-cache misses
+    for (int p = 0; p < 4; ++p) {
+        const int j0 = 16 * p;
+        if (warp == 0) {
+            // Division-free elimination on the chain: every stored entry carries a common scale s (1 <= s < 2^16), a step is
+            //   a'(r,c) = 2^-e (d a(r,c) - a(r,j) a(c,j)),  e = exponent of the scaled pivot d,  s' = s * (d 2^-e),
+            // i.e. shuffle + exponent trick + one multiply + one FMA per pivot; the sixteen 1/sqrt are taken afterwards in parallel:
+            // L(r,j) = a(r,j) / sqrt(d_j s_{j-1}).
+            const int r = lane & 15;     // lanes 16..31 mirror lanes 0..15
+            double a[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) a[c] = T[(j0 + r) * LDT + j0 + c];
+            double s_prev = 1.0, my_sc = 1.0, my_sprev = 1.0;
+            // the pivot column travels through a 16-double shared buffer (one store, broadcast vector loads) instead of 15 shuffles
+            double* colb = &P[0][0][0];                            // P is idle during the factorisation; two buffers of 16
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                double* cb = colb + (j & 1) * 16;
+                if (lane < 16) cb[r] = a[j];                       // scaled a(r, j); rows r < j hold stale upper entries nobody reads
+                __syncwarp();
+                const double d = cb[j];
+                if (lane == 0 && !(d > 0.0) && j0 + j < nb) atomicCAS(info, 0, k0 + j0 + j + 1);
+                const double p2 = __hiloint2double((2046 - ((__double2hiint(d) >> 20) & 0x7ff)) << 20, 0);   // 2^-e
+                const double dm = d * p2;                          // in [1, 2)
+                const double lr = a[j] * p2;
+                if (lane == j) { my_sc = d * s_prev; my_sprev = s_prev; }
+                s_prev *= dm;
+#pragma unroll
+                for (int c = j + 1; c < 16; ++c) a[c] = dm * a[c] - lr * cb[c];
+            }
+            const double rs = rsqrt(my_sc);
+            if (lane < 16) rsd[j0 + lane] = rs * my_sprev;         // 1 / L(j,j)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const double rc = __shfl_sync(0xffffffffu, rs, c);
+                if (lane < 16) T[(j0 + r) * LDT + j0 + c] = (c <= r) ? a[c] * rc : 0.0;
+            }
+        }
+        __syncthreads();
+        POTRF_T(1);
+        if (p < 3) {
+            const int R = NB - (j0 + 16);          // rows below the diagonal block
+            if (tid < R) {                         // X L16^T = A : x_c = (a_c - sum_{m<c} x_m L(c,m)) / L(c,c)
+                const int i = j0 + 16 + tid;
+                double x[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    double sacc = T[i * LDT + j0 + c];
+#pragma unroll
+                    for (int m = 0; m < c; ++m) sacc -= x[m] * T[(j0 + c) * LDT + j0 + m];
+                    x[c] = sacc * rsd[j0 + c];
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) T[i * LDT + j0 + c] = x[c];
+            }
+            __syncthreads();
+            POTRF_T(2);
+            {   // trailing part of the tile: T(i, c) -= sum_m X(i, m) X(c, m), i >= c.  Thread (ti, tj) owns rows ti + 16 a, columns tj + 16 b.
+                const int ti = tid >> 4, tj = tid & 15, nA = R >> 4;
+                double acc9[3][3];
+#pragma unroll
+                for (int a2 = 0; a2 < 3; ++a2)
+#pragma unroll
+                    for (int b2 = 0; b2 < 3; ++b2) acc9[a2][b2] = 0.0;
+                const double* xbase = T + (j0 + 16) * LDT + j0;
+#pragma unroll
+                for (int m0 = 0; m0 < 16; m0 += 4) {
+                    double xi[3][4], xc[3][4];
+#pragma unroll
+                    for (int a2 = 0; a2 < 3; ++a2)
+#pragma unroll
+                        for (int m = 0; m < 4; ++m) {
+                            xi[a2][m] = a2 < nA ? xbase[(ti + 16 * a2) * LDT + m0 + m] : 0.0;
+                            xc[a2][m] = a2 < nA ? xbase[(tj + 16 * a2) * LDT + m0 + m] : 0.0;
+                        }
+#pragma unroll
+                    for (int a2 = 0; a2 < 3; ++a2)
+#pragma unroll
+                        for (int b2 = 0; b2 <= a2; ++b2)
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) acc9[a2][b2] += xi[a2][m] * xc[b2][m];
+                }
+#pragma unroll
+                for (int a2 = 0; a2 < 3; ++a2)
+#pragma unroll
+                    for (int b2 = 0; b2 <= a2; ++b2) {
+                        const int ii = ti + 16 * a2, cc = tj + 16 * b2;
+                        if (a2 < nA && cc <= ii) T[(j0 + 16 + ii) * LDT + j0 + 16 + cc] -= acc9[a2][b2];
+                    }
+            }
+            __syncthreads();
+            POTRF_T(3);
+        }
+    }
+    // ---- inverse: diagonal 16x16 blocks, one thread per column
+    if (tid < NB) {
+        const int b0 = tid & ~15, c = tid & 15;
+        double x[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            double sacc = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int m = 0; m < r; ++m) if (m >= c) sacc -= T[(b0 + r) * LDT + b0 + m] * x[m];
+            x[r] = (r >= c) ? sacc * rsd[b0 + r] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) M[(b0 + r) * LDT + b0 + c] = x[r];
+    }
+    __syncthreads();
+    POTRF_T(4);
+    // ---- off-diagonal blocks, level d = i - j
+    const int rr = tid >> 4, cc = tid & 15;
+#pragma unroll 1
+    for (int d = 1; d < 4; ++d) {
+#pragma unroll 1
+        for (int q = 0; q < 4 - d; ++q) {          // P_q = sum_{k=j}^{i-1} L_ik M_kj
+            const int i = d + q, j = q;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+            for (int kk = 16 * j; kk < 16 * i; kk += 4) {
+                s0 += T[(16 * i + rr) * LDT + kk] * M[kk * LDT + 16 * j + cc];
+                s1 += T[(16 * i + rr) * LDT + kk + 1] * M[(kk + 1) * LDT + 16 * j + cc];
+                s2 += T[(16 * i + rr) * LDT + kk + 2] * M[(kk + 2) * LDT + 16 * j + cc];
+                s3 += T[(16 * i + rr) * LDT + kk + 3] * M[(kk + 3) * LDT + 16 * j + cc];
+            }
+            P[q][rr][cc] = (s0 + s1) + (s2 + s3);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int q = 0; q < 4 - d; ++q) {          // M_ij = -M_ii P_q   (M_ii lower triangular)
+            const int i = d + q, j = q;
+            double s0 = 0.0, s1 = 0.0;      // M_ii is lower triangular: the terms m > rr are zeros of M
+#pragma unroll
+            for (int m = 0; m < 16; m += 2) { s0 += M[(16 * i + rr) * LDT + 16 * i + m] * P[q][m][cc]; s1 += M[(16 * i + rr) * LDT + 16 * i + m + 1] * P[q][m + 1][cc]; }
+            M[(16 * i + rr) * LDT + 16 * j + cc] = -(s0 + s1);
+        }
+        __syncthreads();
+    }
+    POTRF_T(5);
+#pragma unroll
+    for (int e = tid; e < NB * NB; e += 256) {
+        const int c = e >> 6, r = e & 63;
+        if (r < nb && c < nb && r >= c) A[(size_t)(k0 + c) * ld + k0 + r] = T[r * LDT + c];
+        dinv[(size_t)c * NB + r] = (r >= c) ? M[r * LDT + c] : 0.0;
+    }
+    __syncthreads();
+    POTRF_T(6);
+#undef POTRF_T
+}
+
 __global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ dinv, int* __restrict__ info,
                                                      unsigned char* __restrict__ F, int nblk) {
     potrf64_inv_dev<false>(n, k0, A, ld, dinv, info, F, nblk);
@@ -472,6 +655,59 @@ __device__ __forceinline__ void band_tile_nt(const double* sA, const double* sB,
     }
 }
 
+// One 64x64x64 tile operation of the cluster kernel (one copy of the code: it runs a few times per step, every copy would be
+// another set of instruction-cache misses).  mode 0: A(ra,k) <- A(ra,k) Linv_k^T in place;  mode 1: A(ra,rb) -= X(ra,k) X(rb,k)^T.
+__device__ __noinline__ void band_tile_op(BandSmem& sm, int n, double* A, int64_t ld, const double* dinv, unsigned char* F, int nblk, int mode, int ra, int rb, int k) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16, g = lane >> 2, tg = lane & 3;
+    __syncthreads();
+    band_load_tile(sm.A, A, ld, ra * NB, k * NB, n);
+    if (mode == 0) {   // sB[q*TS + c] = Linv(c, q) = dinv_k[q*64 + c]
+        const double* dk = dinv + (size_t)k * NB * NB;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int v = tid + 256 * it;
+            const int q = v >> 5, cp = (v & 31) * 2;
+            cp_async16(sm.B + q * kBandTS + cp, dk + (size_t)q * NB + cp, 16);
+        }
+    } else {
+        band_load_tile(sm.B, A, ld, rb * NB, k * NB, n);
+    }
+    cp_async_commit(); cp_async_wait<0>();
+    __syncthreads();
+    double acc[4][2][2];
+    band_tile_nt(sm.A, sm.B, acc);
+    const int cbase = (mode == 0 ? k : rb) * NB;
+    double cur[4][2][2];
+    if (mode == 1) {   // all 16 loads of the read-modify-write first: behind a store the compiler has to assume aliasing and serialises them
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int row = ra * NB + wr + 8 * i + g, col = cbase + wc + 8 * j + 2 * tg + e;
+                    cur[i][j][e] = (row < n && col < n && row >= col) ? __ldcg(A + (size_t)col * ld + row) : 0.0;
+                }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = ra * NB + wr + 8 * i + g, col = cbase + wc + 8 * j + 2 * tg + e;
+                if (row >= n || col >= n) continue;
+                double* p = A + (size_t)col * ld + row;
+                if (mode == 0) *p = acc[i][j][e];
+                else if (row >= col) *p = cur[i][j][e] - acc[i][j][e];
+            }
+    if (mode == 1 && tid == 0 && ra != rb) F[(size_t)rb * nblk + ra] = 1;   // fill (or already non-zero)
+}
+
+// development aid: clock64() per phase, CTA 0 (slots 0..5: wait A, list, solve, wait B, diag update, potrf) and CTA 1 (8..11: wait A, solve, wait B, updates)
+__device__ long long g_band_prof[16];
+#define BAND_T(slot) do { if (tid == 0 && rank <= 1) { const long long now_ = clock64(); g_band_prof[rank * 8 + (slot)] += now_ - t_prev; t_prev = now_; } } while (0)
 __global__ void __cluster_dims__(kBandCluster, 1, 1) __launch_bounds__(256, 1)
 k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk) {
     extern __shared__ __align__(16) unsigned char band_raw[];
@@ -480,58 +716,15 @@ k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char
     const int rank = (int)cluster_cta_rank();
     const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16, g = lane >> 2, tg = lane & 3;
 
-    auto solve_tile = [&](int r, int k) {     // A(r,k) <- A(r,k) * Linv_k^T, in place
-        __syncthreads();
-        band_load_tile(sm.A, A, ld, r * NB, k * NB, n);
-        {   // sB[q*TS + c] = Linv(c, q) = dinv_k[q*64 + c]
-            const double* dk = dinv + (size_t)k * NB * NB;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const int v = tid + 256 * it;
-                const int q = v >> 5, cp = (v & 31) * 2;
-                cp_async16(sm.B + q * kBandTS + cp, dk + (size_t)q * NB + cp, 16);
-            }
-        }
-        cp_async_commit(); cp_async_wait<0>();
-        __syncthreads();
-        double acc[4][2][2];
-        band_tile_nt(sm.A, sm.B, acc);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int row = r * NB + wr + 8 * i + g, col = k * NB + wc + 8 * j + 2 * tg + e;
-                    if (row < n && col < n) A[(size_t)col * ld + row] = acc[i][j][e];
-                }
-    };
-    auto update_pair = [&](int ra, int rb, int k) {   // A(ra, rb) -= X(ra,k) X(rb,k)^T   (ra >= rb > k)
-        __syncthreads();
-        band_load_tile(sm.A, A, ld, ra * NB, k * NB, n);
-        band_load_tile(sm.B, A, ld, rb * NB, k * NB, n);
-        cp_async_commit(); cp_async_wait<0>();
-        __syncthreads();
-        double acc[4][2][2];
-        band_tile_nt(sm.A, sm.B, acc);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int row = ra * NB + wr + 8 * i + g, col = rb * NB + wc + 8 * j + 2 * tg + e;
-                    if (row < n && col < n && row >= col) {
-                        double* p = A + (size_t)col * ld + row;
-                        *p = __ldcg(p) - acc[i][j][e];
-                    }
-                }
-        if (tid == 0 && ra != rb) F[(size_t)rb * nblk + ra] = 1;   // fill (or already non-zero)
-    };
+    auto solve_tile = [&](int r, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 0, r, r, k); };
+    auto update_pair = [&](int ra, int rb, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 1, ra, rb, k); };
 
-    if (rank == 0) potrf64_inv_dev<true>(n, 0, A, ld, dinv, info, F, nblk);
+    static_assert(2 * NB * kBandTS >= (int)kPotrfScratchDoubles, "potrf scratch must fit the two operand tiles");
+    if (rank == 0) potrf64_blk_dev<true>(n, 0, A, ld, dinv, info, F, nblk, sm.A);
+    long long t_prev = clock64();
     for (int k = 0; k < nblk; ++k) {
         cluster_sync_all();                                   // A: potrf(k) and the updates of step k-1 are visible
+        BAND_T(0);
         // non-zero row tiles of column k, ascending
         if (warp == 0) {
             int m = 0;
@@ -545,15 +738,20 @@ k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char
             if (lane == 0) sm.m = m;
         }
         __syncthreads();
+        BAND_T(1);
         const int m = sm.m;
         for (int i = rank; i < m; i += kBandCluster) solve_tile(sm.rows[i], k);
+        BAND_T(2);
         cluster_sync_all();                                   // B: every X(r,k) is visible
+        BAND_T(3);
         const bool next_in_list = m > 0 && sm.rows[0] == k + 1;
         const int npairs = m * (m + 1) / 2;
         if (rank == 0) {
             if (next_in_list) update_pair(k + 1, k + 1, k);
             __syncthreads();
-            if (k + 1 < nblk) potrf64_inv_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk);
+            BAND_T(4);
+            if (k + 1 < nblk) potrf64_blk_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk, sm.A, g_potrf_prof);
+            BAND_T(5);
         } else {
             for (int p = (next_in_list ? 1 : 0) + (rank - 1); p < npairs; p += kBandCluster - 1) {
                 int a = (int)((sqrtf(8.0f * (float)p + 1.0f) - 1.0f) * 0.5f);
@@ -562,7 +760,23 @@ k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char
                 const int b = p - a * (a + 1) / 2;
                 update_pair(sm.rows[a], sm.rows[b], k);
             }
+            BAND_T(4);
         }
+    }
+}
+void dense_cholesky_band_profile_report() {
+    long long h[16];
+    if (cudaMemcpyFromSymbol(h, g_band_prof, sizeof(h)) != cudaSuccess) return;
+    const char* n0[6] = {"wait A", "list", "solve", "wait B", "diag update", "potrf"};
+    printf("  band kernel, CTA 0 (cycles):");
+    for (int i = 0; i < 6; ++i) printf(" %s=%lld", n0[i], h[i]);
+    printf("\n  band kernel, CTA 1 (cycles): wait A=%lld list=%lld solve=%lld wait B=%lld updates=%lld\n", h[8], h[9], h[10], h[11], h[12]);
+    long long z[16] = {0};
+    cudaMemcpyToSymbol(g_band_prof, z, sizeof(z));
+    long long hp[8];
+    if (cudaMemcpyFromSymbol(hp, g_potrf_prof, sizeof(hp)) == cudaSuccess) {
+        printf("  potrf64_blk (cycles): load=%lld potrf16=%lld trsm=%lld syrk=%lld inv_diag=%lld inv_offdiag=%lld store=%lld\n", hp[0], hp[1], hp[2], hp[3], hp[4], hp[5], hp[6]);
+        cudaMemcpyToSymbol(g_potrf_prof, z, sizeof(hp));
     }
 }
 

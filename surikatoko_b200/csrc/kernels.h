@@ -43,6 +43,7 @@ void launch_debug_F_blocks(cudaStream_t st, int64_t O, const double* J, double* 
 // first non-positive pivot (0 = success).  All return launch counts.
 size_t dense_cholesky_dinv_doubles(int n);
 void dense_cholesky_profile_report();
+void dense_cholesky_band_profile_report();
 // column-major 64x64 inverse of the kb-th diagonal block of L inside the workspace
 inline const double* dense_cholesky_dinv_block(const double* ws, int kb) { return ws + (size_t)kb * 64 * 64; }
 // C (m x n, ldc) -= A (m x K, lda) * B (n x K, ldb)^T, all column-major, DMMA 128x128 tiles; lower_only: only tiles / entries with row >= col.
