@@ -771,6 +771,7 @@ void dense_cholesky_band_profile_report() {
     printf("  band kernel, CTA 0 (cycles):");
     for (int i = 0; i < 6; ++i) printf(" %s=%lld", n0[i], h[i]);
     printf("\n  band kernel, CTA 1 (cycles): wait A=%lld list=%lld solve=%lld wait B=%lld updates=%lld\n", h[8], h[9], h[10], h[11], h[12]);
+    printf("  trsv cluster, CTA 0 (cycles): diag=%lld cluster wait=%lld tile ops=%lld\n", h[13], h[14], h[15]);
     long long z[16] = {0};
     cudaMemcpyToSymbol(g_band_prof, z, sizeof(z));
     long long hp[8];
@@ -933,6 +934,123 @@ __global__ void __launch_bounds__(256, 1) k_trsv_single(int n, const double* __r
         step(t, vA, vC);
         step(t + 1, vB, vA);
         step(t + 2, vC, vB);
+    }
+}
+
+// Cluster version of the sparse-factor substitutions: the op list is split over the 8 CTAs of one thread-block cluster by the
+// owner of the row block an op writes (block j belongs to CTA j mod 8, which keeps b_j in shared memory).  The owner of block k
+// turns b_k into the solved y_k (GEMV with the stored inverse) and publishes it in global memory; ONE barrier.cluster per block
+// column makes it visible; every CTA then applies its own tiles of that column.  A single CTA can keep ~64 KB of tile loads in
+// flight (~40 GB/s: the 30 MB of tiles took 0.8 ms); eight CTAs with a 4-deep cp.async ring each keep ~0.8 MB in flight.
+constexpr int kTrsvClRing = 4;
+constexpr int kTrsvClLDT = NB + 2;                      // 66: 16-byte aligned rows; forward ops read [c][r] (conflict-free), backward ops read
+                                                        // [r][c] with 16-byte loads (row stride 33 x 16 B: conflict-free per quarter warp)
+constexpr int kTrsvClMaxOwn = (kTrsvSparseMaxBlk + kBandCluster - 1) / kBandCluster;
+struct TrsvClSmem {
+    double ring[kTrsvClRing][NB * kTrsvClLDT];
+    double bown[kTrsvClMaxOwn][NB];
+    double yk[2][NB];                                   // y_k of the current / next block column, pushed by its owner (DSMEM)
+    int ops[(kTrsvSparseFill + 1) * kTrsvSparseMaxBlk];
+    int nmy;
+};
+// ring slot <- the 64x64 operand of `op` as it lies in memory: element (major m, minor i) lands at slot[m*66 + i].
+// forward: diag Linv(i, m), tile L(j0+i, k0+m);  backward: diag Linv(i, m) read transposed, tile L(k0+i, j0+m).
+__device__ __forceinline__ void trsv_cl_issue(double* slot, int op, int n, const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv, int backward) {
+    const int k = op >> 16, j = op & 0xffff;
+    const int tid = threadIdx.x;
+    const double* base; int64_t smaj; int row0;
+    if (k == j) { base = dinv + (size_t)k * NB * NB; smaj = NB; row0 = 0; }
+    else if (!backward) { base = L + (size_t)(k * NB) * ld + j * NB; smaj = ld; row0 = j * NB; }
+    else { base = L + (size_t)(j * NB) * ld + k * NB; smaj = ld; row0 = k * NB; }
+    const int lim = (k == j) ? NB : n - row0;          // valid minor indices: [0, lim)
+    const int mi = (tid & 31) * 2;
+    int bytes = (lim - mi) * 8; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+    const double* src = base + (bytes > 0 ? mi : 0);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int mj = (tid >> 5) + 8 * it;
+        cp_async16(slot + mj * kTrsvClLDT + mi, bytes > 0 ? src + (size_t)mj * smaj : base, bytes);
+    }
+}
+__global__ void __cluster_dims__(kBandCluster, 1, 1) __launch_bounds__(256, 1)
+k_trsv_cluster(int n, const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv, double* b, const int* __restrict__ stats,
+               const int* __restrict__ list, int backward) {
+    extern __shared__ __align__(16) unsigned char trsv_raw[];
+    TrsvClSmem& sm = *reinterpret_cast<TrsvClSmem*>(trsv_raw);
+    const int nblk = (n + NB - 1) / NB;
+    if (!trsv_use_sparse(n, nblk, stats[0])) return;      // uniform over the cluster
+    const int nops = stats[1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    // my ops, in list order: an op (k, j) writes row block j
+    if (warp == 0) {
+        int m = 0;
+        for (int base = 0; base < nops; base += 32) {
+            const int t = base + lane;
+            const int op = t < nops ? list[t] : 0;
+            const bool mine = t < nops && ((op & 0xffff) % kBandCluster) == rank;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (mine) sm.ops[m + __popc(bal & ((1u << lane) - 1))] = op;
+            m += __popc(bal);
+        }
+        if (lane == 0) sm.nmy = m;
+    }
+    for (int jb = rank; jb < nblk; jb += kBandCluster)
+        for (int i = tid; i < NB; i += 256) sm.bown[jb / kBandCluster][i] = (jb * NB + i < n) ? b[jb * NB + i] : 0.0;
+    __syncthreads();
+    const int nmy = sm.nmy;
+    for (int i = 0; i < kTrsvClRing - 1; ++i) { if (i < nmy) trsv_cl_issue(sm.ring[i], sm.ops[i], n, L, ld, dinv, backward); cp_async_commit(); }
+    int t = 0;
+    // one op: the operand tile of op t is in ring[t % R]; x = the 64 multipliers; thread tid < 64 returns its dot product
+    auto run_op = [&](const double* x) -> double {
+        { const int nx = t + kTrsvClRing - 1; if (nx < nmy) trsv_cl_issue(sm.ring[nx % kTrsvClRing], sm.ops[nx], n, L, ld, dinv, backward); cp_async_commit(); }
+        cp_async_wait<kTrsvClRing - 1>();
+        __syncthreads();
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (tid < NB) {
+            const double* T = sm.ring[t % kTrsvClRing];
+            if (!backward) {
+#pragma unroll
+                for (int c = 0; c < NB; c += 4) {
+                    s0 += T[c * kTrsvClLDT + tid] * x[c]; s1 += T[(c + 1) * kTrsvClLDT + tid] * x[c + 1];
+                    s2 += T[(c + 2) * kTrsvClLDT + tid] * x[c + 2]; s3 += T[(c + 3) * kTrsvClLDT + tid] * x[c + 3];
+                }
+            } else {
+                const double2* T2 = reinterpret_cast<const double2*>(T + tid * kTrsvClLDT);
+                const double2* x2 = reinterpret_cast<const double2*>(x);
+#pragma unroll
+                for (int c = 0; c < NB / 2; c += 2) {
+                    const double2 a0 = T2[c], a1 = T2[c + 1], x0 = x2[c], x1 = x2[c + 1];
+                    s0 += a0.x * x0.x; s1 += a0.y * x0.y; s2 += a1.x * x1.x; s3 += a1.y * x1.y;
+                }
+            }
+        }
+        return (s0 + s1) + (s2 + s3);
+    };
+    cluster.sync();                                           // every CTA of the cluster is running before the first remote store
+    for (int sidx = 0; sidx < nblk; ++sidx) {
+        const int k = backward ? nblk - 1 - sidx : sidx;
+        if (t < nmy && sm.ops[t] == ((k << 16) | k)) {      // I own block k: every update of b_k has been applied (list order)
+            double* bk = sm.bown[k / kBandCluster];
+            const double y = run_op(bk);
+            if (tid < NB) {
+                if (k * NB + tid < n) b[k * NB + tid] = y;
+#pragma unroll
+                for (int dst = 0; dst < kBandCluster; ++dst) *cluster.map_shared_rank(&sm.yk[sidx & 1][tid], dst) = y;   // DSMEM push to the whole cluster
+            }
+            ++t;
+            __syncthreads();
+        }
+        cluster_sync_all();                                   // y_k has arrived everywhere
+        const double* yk = sm.yk[sidx & 1];
+        while (t < nmy && (sm.ops[t] >> 16) == k) {
+            const int j = sm.ops[t] & 0xffff;
+            const double d = run_op(yk);
+            if (tid < NB) sm.bown[j / kBandCluster][tid] -= d;
+            ++t;
+            __syncthreads();                                  // the ring slot and b_j are settled before the next op touches them
+        }
     }
 }
 
@@ -1276,8 +1394,15 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
     if (n <= kTrsvSparseMaxN) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_trsv_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTrsvSparseMaxN + sizeof(int) * (kTrsvSparseFill + 1) * kTrsvSparseMaxBlk)); attr = true; }
-        k_trsv_single<<<1, 256, sizeof(double) * (size_t)nblk * NB + sizeof(int) * (size_t)(kTrsvSparseFill + 1) * nblk, st>>>(n, L, ld, dinv, b, nzt, ws_list(ws, n, backward),
-                                                                                                                             backward);
+        static int use_cluster = -1;
+        if (use_cluster < 0) {
+            const char* e = getenv("SRK_TRSV_CLUSTER");
+            use_cluster = (e != nullptr && e[0] == '0') ? 0 : 1;
+            if (use_cluster && cudaFuncSetAttribute(k_trsv_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsvClSmem)) != cudaSuccess) { cudaGetLastError(); use_cluster = 0; }
+        }
+        if (use_cluster) k_trsv_cluster<<<kBandCluster, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, ws_list(ws, n, backward), backward);
+        else k_trsv_single<<<1, 256, sizeof(double) * (size_t)nblk * NB + sizeof(int) * (size_t)(kTrsvSparseFill + 1) * nblk, st>>>(n, L, ld, dinv, b, nzt, ws_list(ws, n, backward),
+                                                                                                                                  backward);
         if (g_prof) {
             int h[2] = {0, 0};
             cudaStreamSynchronize(st); cudaMemcpy(h, nzt, sizeof(h), cudaMemcpyDeviceToHost);
