@@ -279,9 +279,13 @@ __device__ __noinline__ void potrf64_blk_dev(int n, int k0, double* A, int64_t l
 #undef POTRF_T
 }
 
+// The launch-per-operation path uses the blocked variant too (dynamic shared memory = its scratch); the row-operation variant
+// above stays as the reference implementation behind SRK_POTRF=rowops.
 __global__ void __launch_bounds__(256) k_potrf64_inv(int n, int k0, double* __restrict__ A, int64_t ld, double* __restrict__ dinv, int* __restrict__ info,
-                                                     unsigned char* __restrict__ F, int nblk) {
-    potrf64_inv_dev<false>(n, k0, A, ld, dinv, info, F, nblk);
+                                                     unsigned char* __restrict__ F, int nblk, int rowops) {
+    extern __shared__ __align__(16) double potrf_scratch[];
+    if (rowops) potrf64_inv_dev<false>(n, k0, A, ld, dinv, info, F, nblk);
+    else potrf64_blk_dev<false>(n, k0, A, ld, dinv, info, F, nblk, potrf_scratch);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -477,7 +481,18 @@ __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads) k_syrk_dmma(int n, do
         }
         cp_async_wait<0>();
         __syncthreads();   // the stage buffers are free for the next tile
-        // epilogue: C(row, col) -= acc on the lower triangle inside [origin, col_end)
+        // epilogue: C(row, col) -= acc on the lower triangle inside [origin, col_end).  All loads of the read-modify-write are
+        // issued before the first store: behind a store to A the compiler must assume aliasing and would serialise them.
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int row = i0 + wr + i * 8 + g;
+                const int col = j0 + wc + j * 8 + tg * 2;
+                const bool ok0 = row < n && col < col_end && row >= col, ok1 = row < n && col + 1 < col_end && row >= col + 1;
+                acc[i][j][0] = (ok0 ? A[(size_t)col * ld + row] : 0.0) - acc[i][j][0];
+                acc[i][j][1] = (ok1 ? A[(size_t)(col + 1) * ld + row] : 0.0) - acc[i][j][1];
+            }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -485,8 +500,8 @@ __global__ void __launch_bounds__(SyrkCfg<TILE>::kThreads) k_syrk_dmma(int n, do
                 const int row = i0 + wr + i * 8 + g;
                 const int col = j0 + wc + j * 8 + tg * 2;
                 if (row < n) {
-                    if (col < col_end && row >= col) A[(size_t)col * ld + row] -= acc[i][j][0];
-                    if (col + 1 < col_end && row >= col + 1) A[(size_t)(col + 1) * ld + row] -= acc[i][j][1];
+                    if (col < col_end && row >= col) A[(size_t)col * ld + row] = acc[i][j][0];
+                    if (col + 1 < col_end && row >= col + 1) A[(size_t)(col + 1) * ld + row] = acc[i][j][1];
                 }
             }
     }
@@ -1225,6 +1240,7 @@ __global__ void k_axpy1(int n, const double* __restrict__ d, double* __restrict_
 constexpr size_t kPanelSolveSmem = sizeof(double) * (NB * NB + NB * PS_ROWS);
 
 static int g_coop_blocks = 0;
+static int g_potrf_rowops = 0;
 static int g_sms = 148;
 static void launch_syrk(cudaStream_t st, int n, double* A, int64_t ld, int kcol0, int K, int origin, int col_end, const unsigned char* F, int nblk);
 static int g_epoch = 0;
@@ -1232,6 +1248,8 @@ static void set_attrs_once() {
     static bool attr_set = false;
     if (attr_set) return;
     cudaFuncSetAttribute(k_panel_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSolveSmem);
+    cudaFuncSetAttribute(k_potrf64_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kPotrfScratchDoubles));
+    { const char* e = getenv("SRK_POTRF"); g_potrf_rowops = (e != nullptr && e[0] == 'r') ? 1 : 0; }
     cudaFuncSetAttribute(k_right_solve_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRightSolveSmem);
     cudaFuncSetAttribute(k_syrk_dmma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<128>::kSmem);
     cudaFuncSetAttribute(k_syrk_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SyrkCfg<64>::kSmem);
@@ -1286,7 +1304,7 @@ static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
         const int pend = min(n, p0 + PB);
         for (int k0 = p0; k0 < pend; k0 += NB) {
             double* di = ws + (size_t)(k0 / NB) * NB * NB;
-            { ProfScope ps(0, st); k_potrf64_inv<<<1, 256, 0, st>>>(n, k0, A, ld, di, info_dev, F, nblk); } ++launches;
+            { ProfScope ps(0, st); k_potrf64_inv<<<1, 256, sizeof(double) * kPotrfScratchDoubles, st>>>(n, k0, A, ld, di, info_dev, F, nblk, g_potrf_rowops); } ++launches;
             const int below = n - (k0 + NB);
             if (below <= 0) continue;
             { ProfScope ps(1, st); k_right_solve_dmma<<<(below + RS_ROWS - 1) / RS_ROWS, 256, kRightSolveSmem, st>>>(n, k0 + NB, A + (size_t)k0 * ld, ld, di, F + (size_t)(k0 / NB) * nblk, nblk); } ++launches;
@@ -1517,9 +1535,19 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int K, co
             for (int j = 0; j < NJ; ++j) {
                 const int row = i0 + wr + i * 8 + g;
                 const int col = j0 + wc + j * 8 + tg * 2;
+                const bool ok0 = row < m && col < n && (!lower_only || row >= col), ok1 = row < m && col + 1 < n && (!lower_only || row >= col + 1);
+                acc[i][j][0] = (ok0 ? C[(size_t)col * ldc + row] : 0.0) - acc[i][j][0];     // every load of the read-modify-write before the first store
+                acc[i][j][1] = (ok1 ? C[(size_t)(col + 1) * ldc + row] : 0.0) - acc[i][j][1];
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int row = i0 + wr + i * 8 + g;
+                const int col = j0 + wc + j * 8 + tg * 2;
                 if (row < m) {
-                    if (col < n && (!lower_only || row >= col)) C[(size_t)col * ldc + row] -= acc[i][j][0];
-                    if (col + 1 < n && (!lower_only || row >= col + 1)) C[(size_t)(col + 1) * ldc + row] -= acc[i][j][1];
+                    if (col < n && (!lower_only || row >= col)) C[(size_t)col * ldc + row] = acc[i][j][0];
+                    if (col + 1 < n && (!lower_only || row >= col + 1)) C[(size_t)(col + 1) * ldc + row] = acc[i][j][1];
                 }
             }
     }

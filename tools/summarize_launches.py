@@ -31,12 +31,21 @@ def main():
     for name, ms in launches:
         a = agg.setdefault(name, [0, 0.0, 0.0])
         a[0] += 1; a[1] += ms; a[2] = max(a[2], ms)
-    tot = sum(a[1] for a in agg.values())
+    ours = {k: v for k, v in agg.items() if k.startswith("srk::")}
+    other = {k: v for k, v in agg.items() if not k.startswith("srk::")}
+    tot = sum(a[1] for a in ours.values())
+    print("Kernels of this repository (`srk::`), share = share of the summed kernel time of the engine:\n")
     print("| kernel | launches | total ms | avg ms | max ms | share |")
     print("|---|---:|---:|---:|---:|---:|")
-    for name, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print("| `%s` | %d | %.3f | %.4f | %.4f | %.1f %% |" % (name, a[0], a[1], a[1] / a[0], a[2], 100 * a[1] / tot))
-    print("| **all** | %d | %.3f | | | |" % (len(launches), tot))
+    for name, a in sorted(ours.items(), key=lambda kv: -kv[1][1]):
+        print("| `%s` | %d | %.3f | %.4f | %.4f | %.1f %% |" % (name[5:], a[0], a[1], a[1] / a[0], a[2], 100 * a[1] / tot))
+    print("| **all srk kernels** | %d | %.3f | | | |" % (sum(a[0] for a in ours.values()), tot))
+    if other:
+        print("\nOther kernels in the same process (bench.py's own cuBLAS DGEMM 8192^3 peak measurement and torch helpers; not part of a step):\n")
+        print("| kernel | launches | total ms | avg ms |")
+        print("|---|---:|---:|---:|")
+        for name, a in sorted(other.items(), key=lambda kv: -kv[1][1]):
+            print("| `%s` | %d | %.3f | %.4f |" % (name[:80], a[0], a[1], a[1] / a[0]))
 
 
 if __name__ == "__main__":
