@@ -127,7 +127,7 @@ def run_reference(args):
            "config": {"workload": WORKLOADS[args.workload][3], "sample": cb["sample"]},
            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
 
 
 def fp64_gemm_peak(torch, dev):
@@ -318,7 +318,7 @@ def run_ours(args):
            "err_initial": rep.err_initial, "err_after_step": rep.err_final}
     if cpu is not None:
         out["cpu_baseline"] = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -402,10 +402,25 @@ def run_ekf(args):
            "kernels": kernels, "fp64_gemm_peak_tflops": f64_peak, "chol_info": int(info)}
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    print(json.dumps(out))
+    emit(out)
+
+
+RESULT = sys.stdout
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the process's real stdout."""
+    RESULT.write(json.dumps(obj) + "\n")
+    RESULT.flush()
 
 
 def main():
+    # stdout carries exactly one JSON line: everything else that libraries print there (NCCL's "NCCL version ..." banner under
+    # NCCL_DEBUG=VERSION, torch notices) is sent to stderr by pointing file descriptor 1 at stderr and keeping a private copy
+    global RESULT
+    RESULT = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

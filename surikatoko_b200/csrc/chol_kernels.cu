@@ -729,7 +729,6 @@ k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char
     BandSmem& sm = *reinterpret_cast<BandSmem*>(band_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_cta_rank();
-    const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16, g = lane >> 2, tg = lane & 3;
 
     auto solve_tile = [&](int r, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 0, r, r, k); };
     auto update_pair = [&](int ra, int rb, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 1, ra, rb, k); };

@@ -56,6 +56,10 @@ int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t 
 int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
 // mirror the lower triangle into the upper one
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld);
+// multi-GPU exchange of the non-zero 64x64 tiles of S only (aux_kernels.cu)
+void launch_tile_mask(cudaStream_t st, int n, const double* S, int64_t ld, double* mask);
+void launch_tile_list(cudaStream_t st, int n, const double* mask, int* list, int* count);
+void launch_tile_pack(cudaStream_t st, int n, double* S, int64_t ld, const int* list, int count, double* rhs, int64_t nrhs, double* packed, int dir);
 // r = b - A*x, symmetric A with both triangles stored, double-double accumulation
 void launch_residual_dd(cudaStream_t st, int n, const double* A, int64_t ld, const double* x, const double* b, double* r);
 void launch_axpy1(cudaStream_t st, int n, const double* d, double* x);
