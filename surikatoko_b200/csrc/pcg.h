@@ -30,7 +30,8 @@ struct PcgWorkspace {
     double* rhs = nullptr; size_t vec_cap = 0;              // [10M] and the PCG vectors r, z, p, y
     double *r = nullptr, *z = nullptr, *p = nullptr, *y = nullptr;
     double* diag = nullptr; size_t diag_cap = 0;            // [100M] diagonal blocks, then their inverses
-    double* scal = nullptr;                                 // [8] device scalars: rz, bb, rr, pAp, iteration flag
+    double* scal = nullptr;                                 // [16] device scalars, two parities of {rz, bb, rr, pAp}
+    double* partials = nullptr; size_t partials_cap = 0;    // per-CTA partial sums of the dot products (fixed-order second stage)
     double* h_scal = nullptr;                               // pinned mirror
 };
 

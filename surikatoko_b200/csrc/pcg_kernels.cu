@@ -136,90 +136,144 @@ __global__ void k_invert_diag(int M, double* __restrict__ diag) {
     for (int i = 0; i < 10; ++i) for (int j = 0; j < 10; ++j) d[i * 10 + j] = inv[i][j];
 }
 
-// y = S v.  Ten threads per block row (camera), three rows per warp; thread a accumulates y[a] over the row's entries in column
-// order.  A stored block is row-major [10][10] = B(rows: larger camera, cols: smaller camera); the mirrored entry reads it transposed.
-__global__ void __launch_bounds__(128) k_bsr_spmv(int M, const int64_t* __restrict__ row_ptr, const int* __restrict__ row_ent, const double* __restrict__ blocks,
-                                                  const double* __restrict__ v, double* __restrict__ y) {
-    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int sub = lane / 10, a = lane % 10;
-    const int cam = warp * 3 + sub;
-    if (sub >= 3 || cam >= M) return;
-    double acc = 0.0;
-    for (int64_t e = row_ptr[cam]; e < row_ptr[cam + 1]; ++e) {
-        const int ent = row_ent[2 * e], col = row_ent[2 * e + 1];
-        const double* B = blocks + (size_t)(ent & 0x3fffffff) * 100;
-        const double* vc = v + (size_t)col * 10;
-        if (ent & (1 << 30)) {
-#pragma unroll
-            for (int b = 0; b < 10; ++b) acc += B[b * 10 + a] * vc[b];
-        } else {
-#pragma unroll
-            for (int b = 0; b < 10; ++b) acc += B[a * 10 + b] * vc[b];
-        }
-    }
-    y[(size_t)cam * 10 + a] = acc;
-}
+// ---- PCG iteration on the whole GPU, deterministic --------------------------------------------------------------------------
+// One iteration = three grid-wide kernels (the vector half used to be ONE CTA streaming 12 MB per iteration through one SM:
+// 0.16 ms per iteration at configs[4]):
+//   k_bsr_spmv_dot   y = S p  and per-CTA partials of p.y                       (k_dot_partials after the all-reduce of y when multi-GPU)
+//   k_pcg_update     alpha = rz / sum(partials); x += alpha p; r -= alpha y; z = Minv r; per-CTA partials of r.z and r.r
+//   k_pcg_direction  beta = sum(partials r.z) / rz; p = z + beta p; block 0 publishes the scalars of the next parity
+// Every dot product is a two-stage sum with a fixed shape: shuffle tree inside a warp, warps in order, CTAs in order (every CTA
+// re-reduces the partial array itself, so no extra launch and identical bits everywhere).
+// scal[par*8 + {0: rz, 1: bb, 2: rr, 3: pAp}]: an iteration reads parity par and writes parity par^1.
+constexpr int kPcgThreads = 256;   // full warps (the reductions shuffle with a full mask)
+constexpr int kPcgPerCta = 250;    // entries per CTA of the vector kernels: 25 cameras of 10 variables, threads 250..255 idle
 
-// ---- the vector half of a PCG iteration, one CTA (fixed reduction order, device-resident scalars) -----------------------
-__device__ double block_sum(double v, double* red) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+__device__ __forceinline__ double cta_sum_fixed(double v, double* red) {   // fixed shape: lanes (tree), warps in order
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     __syncthreads();
     if (lane == 0) red[w] = v;
     __syncthreads();
     double t = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    for (int i = 0; i < (int)((blockDim.x + 31) >> 5); ++i) t += red[i];
     return t;
 }
-// scal: [0] rz, [1] bb, [2] rr, [3] pAp
-__global__ void __launch_bounds__(1024) k_pcg_init(int n, const double* __restrict__ b, const double* __restrict__ Minv, double* __restrict__ x, double* __restrict__ r,
-                                                   double* __restrict__ z, double* __restrict__ p, double* __restrict__ scal) {
-    __shared__ double red[32];
+// sum of partial[0..n) in a fixed order, identical in every CTA: thread t adds the entries t, t+T, ... then the CTA tree
+__device__ __forceinline__ double reduce_partials(const double* __restrict__ partial, int n, int stride, int off, double* red) {
+    double v = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) v += partial[(size_t)i * stride + off];
+    return cta_sum_fixed(v, red);
+}
+
+// y = S v (10 threads per block row, 3 rows per warp, entries in column order) + partial of v.y per CTA
+__global__ void __launch_bounds__(128) k_bsr_spmv_dot(int M, const int64_t* __restrict__ row_ptr, const int* __restrict__ row_ent, const double* __restrict__ blocks,
+                                                      const double* __restrict__ v, double* __restrict__ y, double* __restrict__ partial) {
+    __shared__ double red[4];
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sub = lane / 10, a = lane % 10;
+    const int cam = warp * 3 + sub;
+    double dot = 0.0;
+    if (sub < 3 && cam < M) {
+        double acc = 0.0;
+        for (int64_t e = row_ptr[cam]; e < row_ptr[cam + 1]; ++e) {
+            const int ent = row_ent[2 * e], col = row_ent[2 * e + 1];
+            const double* B = blocks + (size_t)(ent & 0x3fffffff) * 100;
+            const double* vc = v + (size_t)col * 10;
+            if (ent & (1 << 30)) {
+#pragma unroll
+                for (int b = 0; b < 10; ++b) acc += B[b * 10 + a] * vc[b];
+            } else {
+#pragma unroll
+                for (int b = 0; b < 10; ++b) acc += B[a * 10 + b] * vc[b];
+            }
+        }
+        y[(size_t)cam * 10 + a] = acc;
+        dot = v[(size_t)cam * 10 + a] * acc;
+    }
+    if (partial != nullptr) {
+        const double t = cta_sum_fixed(dot, red);
+        if (threadIdx.x == 0) partial[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) k_dot_partials(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ partial) {
+    __shared__ double red[8];
+    double v = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v += a[i] * b[i];
+    const double t = cta_sum_fixed(v, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+}
+// x = 0, r = b, z = Minv b, p = z; partials of r.z and b.b  (10 lanes per camera)
+__global__ void __launch_bounds__(kPcgThreads) k_pcg_init(int M, const double* __restrict__ b, const double* __restrict__ Minv, double* __restrict__ x, double* __restrict__ r,
+                                                          double* __restrict__ z, double* __restrict__ p, double* __restrict__ partial) {
+    __shared__ double red[8];
     double rz = 0.0, bb = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int cam = i / 10, a = i % 10;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M * 10; i += gridDim.x * blockDim.x) {
+        const int cam = i / 10, a = i - cam * 10;
         const double* Mi = Minv + (size_t)cam * 100 + a * 10;
         const double* bc = b + (size_t)cam * 10;
         double zi = 0.0;
 #pragma unroll
         for (int k = 0; k < 10; ++k) zi += Mi[k] * bc[k];
-        const double bi = b[i];
+        const double bi = bc[a];
         x[i] = 0.0; r[i] = bi; z[i] = zi; p[i] = zi;
         rz += bi * zi; bb += bi * bi;
     }
-    rz = block_sum(rz, red); bb = block_sum(bb, red);
+    rz = cta_sum_fixed(rz, red); bb = cta_sum_fixed(bb, red);
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = rz; partial[2 * blockIdx.x + 1] = bb; }
+}
+__global__ void __launch_bounds__(256) k_pcg_init_scal(int nparts, const double* __restrict__ partial, double* __restrict__ scal) {
+    __shared__ double red[8];
+    const double rz = reduce_partials(partial, nparts, 2, 0, red), bb = reduce_partials(partial, nparts, 2, 1, red);
     if (threadIdx.x == 0) { scal[0] = rz; scal[1] = bb; scal[2] = bb; scal[3] = 0.0; }
 }
-__global__ void __launch_bounds__(1024) k_pcg_step(int n, const double* __restrict__ Minv, const double* __restrict__ y, double* __restrict__ x, double* __restrict__ r,
-                                                   double* __restrict__ z, double* __restrict__ p, double* __restrict__ scal) {
-    __shared__ double red[32];
-    double pAp = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) pAp += p[i] * y[i];
-    pAp = block_sum(pAp, red);
-    const double rz = scal[0];
+// alpha from the partials of p.y; x += alpha p; r -= alpha y; z = Minv r (the 10 lanes of a camera exchange r through shared memory);
+// partials of r.z and r.r.  The grid covers M cameras: CTA c owns cameras [24 c, 24 c + 24).
+__global__ void __launch_bounds__(kPcgThreads) k_pcg_update(int M, int n_dot_parts, const double* __restrict__ dot_partial, const double* __restrict__ Minv,
+                                                            const double* __restrict__ y, const double* __restrict__ p, double* __restrict__ x, double* __restrict__ r,
+                                                            double* __restrict__ z, const double* __restrict__ scal_in, double* __restrict__ partial) {
+    __shared__ double red[8];
+    __shared__ double rs[kPcgThreads];
+    const double pAp = reduce_partials(dot_partial, n_dot_parts, 1, 0, red);
+    const double rz = scal_in[0];
     const double alpha = (pAp != 0.0) ? rz / pAp : 0.0;
-    double rr = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int i = blockIdx.x * kPcgPerCta + threadIdx.x;
+    const int lc = threadIdx.x / 10, a = threadIdx.x - lc * 10;
+    double ri = 0.0;
+    const bool in = threadIdx.x < kPcgPerCta && i < M * 10;
+    if (in) {
         x[i] += alpha * p[i];
-        const double ri = r[i] - alpha * y[i];
-        r[i] = ri; rr += ri * ri;
+        ri = r[i] - alpha * y[i];
+        r[i] = ri;
     }
-    rr = block_sum(rr, red);   // also orders the writes of r before the preconditioner reads them
-    double rz_new = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const int cam = i / 10, a = i % 10;
+    rs[threadIdx.x] = ri;
+    __syncthreads();
+    double rzn = 0.0, rr = 0.0;
+    if (in) {
+        const int cam = i / 10;
         const double* Mi = Minv + (size_t)cam * 100 + a * 10;
-        const double* rc = r + (size_t)cam * 10;
         double zi = 0.0;
 #pragma unroll
-        for (int k = 0; k < 10; ++k) zi += Mi[k] * rc[k];
-        z[i] = zi; rz_new += r[i] * zi;
+        for (int k = 0; k < 10; ++k) zi += Mi[k] * rs[lc * 10 + k];
+        z[i] = zi;
+        rzn = ri * zi; rr = ri * ri;
     }
-    rz_new = block_sum(rz_new, red);
-    const double beta = (rz != 0.0) ? rz_new / rz : 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = z[i] + beta * p[i];
-    if (threadIdx.x == 0) { scal[0] = rz_new; scal[2] = rr; scal[3] = pAp; }
+    rzn = cta_sum_fixed(rzn, red); rr = cta_sum_fixed(rr, red);
+    if (threadIdx.x == 0) { partial[3 * blockIdx.x] = rzn; partial[3 * blockIdx.x + 1] = rr; partial[3 * blockIdx.x + 2] = pAp; }
+}
+// beta from the partials of r.z; p = z + beta p; block 0 publishes the scalars of the next parity
+__global__ void __launch_bounds__(kPcgThreads) k_pcg_direction(int M, int nparts, const double* __restrict__ partial, const double* __restrict__ z, double* __restrict__ p,
+                                                               const double* __restrict__ scal_in, double* __restrict__ scal_out) {
+    __shared__ double red[8];
+    const double rzn = reduce_partials(partial, nparts, 3, 0, red);
+    const double rz = scal_in[0];
+    const double beta = (rz != 0.0) ? rzn / rz : 0.0;
+    const int i = blockIdx.x * kPcgPerCta + threadIdx.x;
+    if (threadIdx.x < kPcgPerCta && i < M * 10) p[i] = z[i] + beta * p[i];
+    if (blockIdx.x == 0) {
+        const double rr = reduce_partials(partial, nparts, 3, 1, red);
+        if (threadIdx.x == 0) { scal_out[0] = rzn; scal_out[1] = scal_in[1]; scal_out[2] = rr; scal_out[3] = partial[2]; }
+    }
 }
 
 // parity hook: scatter the block-sparse system into the dense gauge-reduced layout
@@ -255,7 +309,7 @@ int pcg_build_structure(PcgWorkspace& ws, cudaStream_t st, int64_t N, int64_t O,
     PCG_CUDA(ensure(ws.cnt, ws.cnt_cap, (size_t)M + 2)); PCG_CUDA(ensure(ws.row_ptr, ws.row_ptr_cap, (size_t)M + 1));
     PCG_CUDA(ensure(ws.diag_id, ws.diag_id_cap, (size_t)M));
     if (ws.misc == nullptr) PCG_CUDA(cudaMalloc((void**)&ws.misc, sizeof(int) * 4));
-    if (ws.scal == nullptr) PCG_CUDA(cudaMalloc((void**)&ws.scal, sizeof(double) * 8));
+    if (ws.scal == nullptr) PCG_CUDA(cudaMalloc((void**)&ws.scal, sizeof(double) * 16));
     if (ws.h_scal == nullptr) PCG_CUDA(cudaMallocHost((void**)&ws.h_scal, sizeof(double) * 8));
     ws.hmask = (unsigned)(cap - 1);
     PCG_CUDA(cudaMemsetAsync(ws.hkeys, 0xff, sizeof(unsigned long long) * cap, st));
@@ -315,8 +369,20 @@ int pcg_solve(PcgWorkspace& ws, cudaStream_t st, int M, double* x, int max_iters
     k_gather_diag<<<M, 128, 0, st>>>(M, ws.diag_id, ws.blocks, ws.diag);
     if (multi && ar(ar_user, ws.diag, (int64_t)100 * M, (void*)st) != 0) return SRK_E_CUDA;
     k_invert_diag<<<cdiv(M, 64), 64, 0, st>>>(M, ws.diag);
-    k_pcg_init<<<1, 1024, 0, st>>>(n, ws.rhs, ws.diag, x, ws.r, ws.z, ws.p, ws.scal);
-    *launches += 3;
+    const int g_spmv = (int)cdiv((int64_t)((M + 2) / 3) * 32, 128);       // CTAs of the mat-vec = partials of p.y (single GPU)
+    const int g_vec = (int)cdiv((int64_t)n, kPcgPerCta);                  // CTAs of the vector kernels (25 cameras each)
+    const int g_dot = 296;                                                 // CTAs of the separate dot product (multi-GPU)
+    const int g_init = g_vec < 1184 ? g_vec : 1184;
+    {
+        const size_t need = (size_t)(g_spmv > g_dot ? g_spmv : g_dot) + 3 * (size_t)g_vec + 2 * (size_t)g_init + 16;
+        PCG_CUDA(ensure(ws.partials, ws.partials_cap, need));
+    }
+    double* part_dot = ws.partials;
+    double* part_vec = ws.partials + (g_spmv > g_dot ? g_spmv : g_dot);
+    double* part_init = part_vec + 3 * (size_t)g_vec;
+    k_pcg_init<<<g_init, kPcgThreads, 0, st>>>(M, ws.rhs, ws.diag, x, ws.r, ws.z, ws.p, part_init);
+    k_pcg_init_scal<<<1, 256, 0, st>>>(g_init, part_init, ws.scal);
+    *launches += 4;
     const int check_every = 16;
     int it = 0;
     double rel = 1.0;
@@ -324,13 +390,23 @@ int pcg_solve(PcgWorkspace& ws, cudaStream_t st, int M, double* x, int max_iters
     while (it < max_iters) {
         const int batch = (max_iters - it) < check_every ? (max_iters - it) : check_every;
         for (int k = 0; k < batch; ++k) {
-            k_bsr_spmv<<<cdiv((int64_t)((M + 2) / 3) * 32, 128), 128, 0, st>>>(M, ws.row_ptr, ws.row_ent, ws.blocks, ws.p, ws.y);
-            if (multi && ar(ar_user, ws.y, n, (void*)st) != 0) return SRK_E_CUDA;
-            k_pcg_step<<<1, 1024, 0, st>>>(n, ws.diag, ws.y, x, ws.r, ws.z, ws.p, ws.scal);
+            const int par = (it + k) & 1;
+            double* s_in = ws.scal + 8 * par; double* s_out = ws.scal + 8 * (par ^ 1);
+            int n_dot = g_spmv;
+            if (!multi) {
+                k_bsr_spmv_dot<<<g_spmv, 128, 0, st>>>(M, ws.row_ptr, ws.row_ent, ws.blocks, ws.p, ws.y, part_dot);
+            } else {
+                k_bsr_spmv_dot<<<g_spmv, 128, 0, st>>>(M, ws.row_ptr, ws.row_ent, ws.blocks, ws.p, ws.y, nullptr);
+                if (ar(ar_user, ws.y, n, (void*)st) != 0) return SRK_E_CUDA;
+                k_dot_partials<<<g_dot, 256, 0, st>>>(n, ws.p, ws.y, part_dot);
+                n_dot = g_dot; *launches += 1;
+            }
+            k_pcg_update<<<g_vec, kPcgThreads, 0, st>>>(M, n_dot, part_dot, ws.diag, ws.y, ws.p, x, ws.r, ws.z, s_in, part_vec);
+            k_pcg_direction<<<g_vec, kPcgThreads, 0, st>>>(M, g_vec, part_vec, ws.z, ws.p, s_in, s_out);
         }
-        *launches += 2 * batch;
+        *launches += 3 * batch;
         it += batch;
-        PCG_CUDA(cudaMemcpyAsync(ws.h_scal, ws.scal, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+        PCG_CUDA(cudaMemcpyAsync(ws.h_scal, ws.scal + 8 * (it & 1), sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
         PCG_CUDA(cudaStreamSynchronize(st));
         const double bb = ws.h_scal[1], rr = ws.h_scal[2];
         if (!(bb > 0.0)) { rel = 0.0; break; }
@@ -354,7 +430,7 @@ int pcg_debug_to_dense(PcgWorkspace& ws, cudaStream_t st, int M, int unity, doub
 }
 
 void pcg_release(PcgWorkspace& ws) {
-    void* ptrs[] = {ws.hkeys, ws.hids, ws.blk_cams, ws.row_ptr, ws.row_ent, ws.diag_id, ws.cnt, ws.misc, ws.blocks, ws.rhs, ws.diag, ws.scal};
+    void* ptrs[] = {ws.hkeys, ws.hids, ws.blk_cams, ws.row_ptr, ws.row_ent, ws.diag_id, ws.cnt, ws.misc, ws.blocks, ws.rhs, ws.diag, ws.scal, ws.partials};
     for (void* p : ptrs) if (p != nullptr) cudaFree(p);
     if (ws.h_scal != nullptr) cudaFreeHost(ws.h_scal);
     ws = PcgWorkspace();

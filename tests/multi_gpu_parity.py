@@ -30,7 +30,8 @@ def main():
     eng = sb.Engine(local)
     eng.set_stream(stream.cuda_stream)
     attach_allreduce(eng, stream, dev)
-    opt = sb.BAOptions(err_change=1e-10, max_outer_iters=4)
+    solver = sb.SOLVER_BLOCK_PCG if os.environ.get("SRK_TEST_SOLVER", "") == "pcg" else sb.SOLVER_AUTO
+    opt = sb.BAOptions(err_change=1e-10, max_outer_iters=4, solver=solver)
     with torch.cuda.stream(stream):
         rep = eng.solve(shard, opt)
     torch.cuda.synchronize()
@@ -56,7 +57,7 @@ def main():
         assert dev_[0] < 1e-9 and np.all(dev_ <= np.maximum(1e-9, noise)), (dev_, noise)
         assert np.max(np.abs(pts.cpu().numpy() - ref.points)) / np.max(np.abs(ref.points)) < 1e-6
         assert np.max(np.abs(shard.cams - ref.cams)) < 1e-6
-        print("multi-gpu parity ok: world=%d, per-iteration deviation %s" % (world, dev_))
+        print("multi-gpu parity ok: world=%d, solver=%s, per-iteration deviation %s" % (world, "pcg" if rep.solver_used == sb.SOLVER_BLOCK_PCG else "cholesky", dev_))
     dist.barrier()
     dist.destroy_process_group()
 
