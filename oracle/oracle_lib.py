@@ -258,3 +258,14 @@ def ekf_predict(P, F13, GQGt13, fix_symmetry=True):
     lib().srk_oracle_ekf_predict(C.c_int64(Pn.shape[0]), Pn.ctypes.data_as(C.POINTER(C.c_double)), F.ctypes.data_as(C.POINTER(C.c_double)),
                                  Q.ctypes.data_as(C.POINTER(C.c_double)), C.c_int(1 if fix_symmetry else 0))
     return np.array(Pn)
+
+
+def triangulate(track_begin, obs_frame, obs_xy, proj, f0):
+    """Triangulate3DPointByLeastSquares per track (obs-geom.cpp:679-727); proj: [n_frames, 12] 3x4 column-major."""
+    tb = np.ascontiguousarray(track_begin, dtype=np.int64); fr = np.ascontiguousarray(obs_frame, dtype=np.int32)
+    xy = np.ascontiguousarray(obs_xy, dtype=np.float64); pm = np.ascontiguousarray(proj, dtype=np.float64)
+    out = np.zeros((len(tb) - 1, 3))
+    L = lib()
+    L.srk_oracle_triangulate.argtypes = [C.c_int64] + [C.c_void_p] * 4 + [C.c_double, C.c_void_p]
+    L.srk_oracle_triangulate(len(tb) - 1, tb.ctypes.data, fr.ctypes.data, xy.ctypes.data, pm.ctypes.data, float(f0), out.ctypes.data)
+    return out

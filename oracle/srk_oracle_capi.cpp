@@ -65,6 +65,8 @@ void Configure(BA& ba, int flow, int solve_impl, int unity_ind, double unity_val
 
 }  // namespace
 
+#include "srk_oracle_frontend.hpp"
+
 extern "C" {
 
 struct srk_oracle_report {
@@ -325,6 +327,12 @@ int srk_oracle_ekf_predict(int64_t n, double* P, const double* F13, const double
     std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);
     EkfPredictCovariance(&Pm, F13, GQGt13, fix_symmetry != 0);
     std::memcpy(P, Pm.d.data(), sizeof(double) * (size_t)n * (size_t)n);
+    return 0;
+}
+
+int srk_oracle_triangulate(int64_t n_tracks, const int64_t* track_begin, const int32_t* obs_frame, const double* obs_xy, const double* proj, double f0,
+                           double* out) {
+    srk_oracle::Triangulate(n_tracks, track_begin, obs_frame, obs_xy, proj, f0, out);
     return 0;
 }
 

@@ -169,6 +169,17 @@ __device__ __forceinline__ int cam_table_insert(CamTable& t, int cam) {
     }
     return -1;
 }
+// after a barrier: hash position of a camera that was inserted before it (or -1: the set was full)
+__device__ __forceinline__ int cam_table_find(const CamTable& t, int cam) {
+    unsigned h = ((unsigned)cam * 2654435761u) >> 26;
+    for (int probe = 0; probe < kCamTabHash; ++probe) {
+        const int k = t.key[h];
+        if (k == cam) return (int)h;
+        if (k == -1) return -1;
+        h = (h + 1) & (kCamTabHash - 1);
+    }
+    return -1;
+}
 // after a barrier: copies the records of the collected cameras (coalesced), caller issues the next barrier
 __device__ __forceinline__ void cam_table_stage(CamTable& t, const double* __restrict__ camd) {
     const int n = min(t.count, kCamTabSlots) * kCamStride;

@@ -52,5 +52,7 @@ int main() {
     const double e1 = ba.ReprojError(f0, map, cams, tracks, nullptr, &Ks);
     std::printf("%.17g %.17g %d \"%s\" %lld %zu %.6f\n", e0, e1, ok ? 1 : 0, ba.OptimizationStatusString().c_str(), (long long)ba.LastReport().gpu_launches, seen,
                 ba.ReprojErrorPixPerPoint(e1, seen));
-    return (e1 < e0 && std::fabs(e1 - ba.LastReport().err_final) <= 1e-9 * e1) ? 0 : 1;
+    // e1 is re-evaluated on the un-normalised scene: at convergence on exact pixels it is a sum of ~1e-14 squares whose own rounding
+    // noise (2 |rho| eps per term) is ~1e-9 relative, hence the 1e-6
+    return (e1 < e0 && std::fabs(e1 - ba.LastReport().err_final) <= 1e-6 * e1) ? 0 : 1;
 }
