@@ -33,10 +33,11 @@ WORKLOADS = {
     "c5": (10_000, 5_000_000, 10, "synthetic city-scale BA: 10,000 cameras x 5M points x 50M observations, PCG solve (configs[4])"),
     "tiny": (40, 4000, 8, "tiny ring scene (smoke)"),
     "c3s": (1000, 50_000, 10, "profiling aid: the 1,000-camera reduced system of configs[2] with 50k points"),
+    "tri": (1000, 1_000_000, 10, "front end (SURVEY 8f row 1): linear triangulation of 1M tracks x 10 corners, the scene of configs[2]"),
     "c4": (0, 2000, 0, "Davison MonoSLAM EKF with 2,000 salient points: dense 6013x6013 covariance predict + stacked update per frame (configs[3])"),
 }
 # bounded CPU sample of each workload (same generator, fewer cameras/points so the oracle finishes in ~10-30 s)
-CPU_SAMPLES = {"c3": (100, 100_000, 10), "c2": (50, 2_000, 50), "c5": (100, 100_000, 10), "tiny": (40, 4000, 8), "c3s": (100, 100_000, 10), "c4": (0, 250, 0)}
+CPU_SAMPLES = {"tri": (1000, 200_000, 10), "c3": (100, 100_000, 10), "c2": (50, 2_000, 50), "c5": (100, 100_000, 10), "tiny": (40, 4000, 8), "c3s": (100, 100_000, 10), "c4": (0, 250, 0)}
 METRIC = "BA reprojection residuals/sec through full LM iterations"
 UNIT = "residuals/s"
 
@@ -414,6 +415,70 @@ def emit(obj):
     RESULT.flush()
 
 
+def run_triangulation(args):
+    """--workload tri: one step = Triangulate3DPointByLeastSquares of every track through the C ABI (host buffers in, points out)."""
+    import torch
+    from surikatoko_b200 import frontend, scenes
+    local = int(os.environ.get("LOCAL_RANK", "0")); rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    M, N, k, desc = WORKLOADS["tri"]
+
+    def scene(n):
+        prob = scenes.ring_scene(M, n, k, seed=1234 + rank)
+        cams = prob.gt_cams
+        R = cams[:, 3:].reshape(-1, 3, 3).transpose(0, 2, 1); T = cams[:, :3]
+        Kn = prob.K.reshape(-1, 3, 3).transpose(0, 2, 1)
+        P = np.einsum("mij,mjk->mik", Kn, np.concatenate([R, T[:, :, None]], axis=2))
+        return prob, P, np.arange(0, prob.n_obs + 1, k)
+    prob, P, tb = scene(N)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    tbp, frp, xyp = pin(tb), pin(prob.obs_cam), pin(prob.obs_xy)
+    Xp = pin(np.zeros((N, 3)))
+    for _ in range(args.warmup):
+        frontend.Triangulate3DPointByLeastSquares(tbp, frp, xyp, P, prob.f0, device=local, out=Xp)
+    clocks = ClockSampler(local); clocks.start()
+    torch.cuda.synchronize(); t0 = time.perf_counter(); kms = 0.0
+    for _ in range(args.steps):
+        X = frontend.Triangulate3DPointByLeastSquares(tbp, frp, xyp, P, prob.f0, device=local, out=Xp)
+        kms += frontend.last_triangulation_kernel_ms()
+    torch.cuda.synchronize(); ms = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop()
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    O = prob.n_obs
+    alg_bytes = 20.0 * O + 8.0 * N + 24.0 * N + 96.0 * M
+    kavg = kms / args.steps
+    cpu = None
+    if not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_lib as ol
+        ol.build()
+        sp, sP, stb = scene(CPU_SAMPLES["tri"][1])
+        pm = np.ascontiguousarray(sP.transpose(0, 2, 1)).reshape(-1, 12)
+        c0 = time.perf_counter(); ol.triangulate(stb, sp.obs_cam, sp.obs_xy, pm, sp.f0); cs = time.perf_counter() - c0
+        cpu = {"value": sp.n_points / cs, "unit": "tracks/s", "cores": 1, "kind": "port",
+               "sample": "%d tracks x %d corners, oracle restatement (column-pivoted Householder QR per track), one thread" % (sp.n_points, k)}
+    out = {"metric": "front end: tracks triangulated per second (Triangulate3DPointByLeastSquares)", "value": N * world / (kavg * 1e-3), "unit": "tracks/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": kavg, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": desc, "n_tracks": N, "n_corners": int(O), "l2": "inputs larger than L2 (%.0f MB of corners)" % (20.0 * O / 1e6),
+                                           "value_is": "kernel only (CUDA events); e2e is the whole C-ABI call with host buffers"},
+           "clocks": clk, "e2e": {"value": N * world * args.steps / (ms * 1e-3), "unit": "tracks/s", "h2d_bytes_per_step": int(20 * O + 8 * (N + 1) + 96 * M),
+                                  "d2h_bytes_per_step": int(24 * N), "ms_per_step": ms / args.steps},
+           "gpu_launches": args.steps,
+           "roofline": {"kernel": "k_triangulate", "bound": "hbm", "achieved": alg_bytes / (kavg * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (kavg * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+           "max_abs_error_vs_generating_points": float(np.max(np.abs(X - prob.gt_points)))}
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    emit(out)
+
+
 def main():
     # stdout carries exactly one JSON line: everything else that libraries print there (NCCL's "NCCL version ..." banner under
     # NCCL_DEBUG=VERSION, torch notices) is sent to stderr by pointing file descriptor 1 at stderr and keeping a private copy
@@ -434,6 +499,8 @@ def main():
         run_reference(args)
     elif args.workload == "c4":
         run_ekf(args)
+    elif args.workload == "tri":
+        run_triangulation(args)
     else:
         run_ours(args)
 

@@ -23,6 +23,9 @@ extern "C" {
 SRK_API int srk_triangulate_tracks(int device, int64_t n_tracks, int64_t n_obs, int32_t n_frames, const int64_t* track_begin,
                                    const int32_t* obs_frame, const double* obs_xy, const double* proj, double f0, double* points_out);
 
+/* CUDA-event duration (ms) of the triangulation kernel of the last srk_triangulate_tracks call on this thread (for bench.py). */
+SRK_API double srk_triangulate_last_kernel_ms(void);
+
 /* P[3x4] -> scale_factor, K[9] (upper triangular, K(2,2) = 1), direct camera pose {T[3], R[9] col-major} with
  * P = scale_factor * K * R^T * [I | -T]   (obs-geom.cpp:606-677).  Returns 1 when Q Q^T is not positive definite (the reference
  * returns false), 0 on success. */

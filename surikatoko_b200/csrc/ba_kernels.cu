@@ -170,7 +170,6 @@ __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __re
 #pragma unroll
         for (int rr = 0; rr < kResRows; ++rr) { const int64_t o = base + 256 * rr; cam[rr] = o < O ? obs_cam[o] : -1; }
         __syncthreads();
-#pragma unroll
         int hp[kResRows];
 #pragma unroll
         for (int rr = 0; rr < kResRows; ++rr) hp[rr] = cam[rr] >= 0 ? cam_table_insert(tab, cam[rr]) : -1;

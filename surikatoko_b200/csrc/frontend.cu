@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -31,8 +32,9 @@ __device__ __forceinline__ void givens_fold(double (&R)[6], double (&qb)[3], dou
         const int d = c == 0 ? 0 : (c == 1 ? 3 : 5);       // index of R(c,c)
         const double x = R[d], y = row[c];
         if (y == 0.0) continue;
-        const double h = hypot(x, y);
-        const double cs = x / h, sn = y / h;
+        const double h = sqrt(x * x + y * y);              // entries are O(1) in f0 units: no overflow guard (hypot) needed
+        const double ih = 1.0 / h;
+        const double cs = x * ih, sn = y * ih;
         R[d] = h;
 #pragma unroll
         for (int k = c + 1; k < 3; ++k) {
@@ -49,8 +51,8 @@ __device__ __forceinline__ void givens_fold(double (&R)[6], double (&qb)[3], dou
 }
 
 __global__ void __launch_bounds__(128) k_triangulate(int64_t n_tracks, const int64_t* __restrict__ track_begin, const int32_t* __restrict__ obs_frame,
-                                                     const double* __restrict__ obs_xy, const double* __restrict__ proj, double f0, double* __restrict__ out,
-                                                     int* __restrict__ err) {
+                                                     const double* __restrict__ obs_xy, const double* __restrict__ proj, int n_frames, double f0,
+                                                     double* __restrict__ out, int* __restrict__ err) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tracks) return;
     const int64_t b = track_begin[t], e = track_begin[t + 1];
@@ -58,7 +60,9 @@ __global__ void __launch_bounds__(128) k_triangulate(int64_t n_tracks, const int
     double R[6] = {0, 0, 0, 0, 0, 0}, qb[3] = {0, 0, 0};
     for (int64_t o = b; o < e; ++o) {
         const double x = obs_xy[2 * o], y = obs_xy[2 * o + 1];
-        const double* P = proj + (size_t)obs_frame[o] * 12;       // column-major 3x4: P(r,c) = P[c*3 + r]
+        const int fr = obs_frame[o];
+        if (fr < 0 || fr >= n_frames) { atomicOr(err, 2); return; }
+        const double* P = proj + (size_t)fr * 12;                 // column-major 3x4: P(r,c) = P[c*3 + r]
         // obs-geom.cpp:694-709
         givens_fold(R, qb, x * P[2] - f0 * P[0], x * P[5] - f0 * P[3], x * P[8] - f0 * P[6], -(x * P[11] - f0 * P[9]));
         givens_fold(R, qb, y * P[2] - f0 * P[1], y * P[5] - f0 * P[4], y * P[8] - f0 * P[7], -(y * P[11] - f0 * P[10]));
@@ -69,11 +73,23 @@ __global__ void __launch_bounds__(128) k_triangulate(int64_t n_tracks, const int
     out[3 * t] = xv; out[3 * t + 1] = yv; out[3 * t + 2] = z;
 }
 
+thread_local float g_last_kernel_ms = 0.f;   // CUDA-event time of the last k_triangulate launch on this thread (bench.py)
+
+// grow-only device buffers + one stream, cached per process (the front end is called once per scene; the mutex serialises callers)
 struct DevBuf {
-    void* p = nullptr;
-    ~DevBuf() { if (p != nullptr) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes < 16 ? 16 : bytes); }
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t alloc(size_t bytes) {
+        if (bytes < 16) bytes = 16;
+        if (p != nullptr && bytes <= cap) return cudaSuccess;
+        if (p != nullptr) { cudaFree(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
 };
+struct TriPool { int device = -1; DevBuf tb, fr, xy, pm, out, err; cudaStream_t st = nullptr; cudaEvent_t e0 = nullptr, e1 = nullptr; };
+TriPool g_pool;
+std::mutex g_pool_mutex;
 
 #define FE_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { srk_internal_set_error((std::string(#call) + ": " + cudaGetErrorString(e__)).c_str()); return SRK_E_CUDA; } } while (0)
 
@@ -102,33 +118,48 @@ int srk_triangulate_tracks(int device, int64_t n_tracks, int64_t n_obs, int32_t 
         (n_tracks > 0 && points_out == nullptr)) { srk_internal_set_error("null or negative-sized triangulation input"); return SRK_E_INVALID_ARG; }
     if (n_tracks == 0) return SRK_OK;
     if (track_begin[0] != 0 || track_begin[n_tracks] != n_obs) { srk_internal_set_error("track_begin must run from 0 to n_obs"); return SRK_E_INVALID_ARG; }
-    for (int64_t o = 0; o < n_obs; ++o) if (obs_frame[o] < 0 || obs_frame[o] >= n_frames) { srk_internal_set_error("frame index out of range"); return SRK_E_INVALID_ARG; }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) { cudaGetLastError(); srk_internal_set_error("no CUDA device (there is no CPU fallback)"); return SRK_E_NO_DEVICE; }
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
     FE_CUDA(cudaSetDevice(device));
-    DevBuf tb, fr, xy, pm, out, err;
-    FE_CUDA(tb.alloc(sizeof(int64_t) * (n_tracks + 1))); FE_CUDA(fr.alloc(sizeof(int32_t) * n_obs)); FE_CUDA(xy.alloc(sizeof(double) * 2 * n_obs));
-    FE_CUDA(pm.alloc(sizeof(double) * 12 * (size_t)n_frames)); FE_CUDA(out.alloc(sizeof(double) * 3 * n_tracks)); FE_CUDA(err.alloc(sizeof(int)));
-    cudaStream_t st;
-    FE_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    int rc = SRK_OK;
-    do {
-        if (cudaMemcpyAsync(tb.p, track_begin, sizeof(int64_t) * (n_tracks + 1), cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaMemcpyAsync(fr.p, obs_frame, sizeof(int32_t) * n_obs, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaMemcpyAsync(xy.p, obs_xy, sizeof(double) * 2 * n_obs, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaMemcpyAsync(pm.p, proj, sizeof(double) * 12 * (size_t)n_frames, cudaMemcpyHostToDevice, st) != cudaSuccess ||
-            cudaMemsetAsync(err.p, 0, sizeof(int), st) != cudaSuccess) { rc = SRK_E_CUDA; break; }
-        k_triangulate<<<(unsigned)((n_tracks + 127) / 128), 128, 0, st>>>(n_tracks, (const int64_t*)tb.p, (const int32_t*)fr.p, (const double*)xy.p, (const double*)pm.p, f0,
-                                                                       (double*)out.p, (int*)err.p);
-        int h_err = 0;
-        if (cudaMemcpyAsync(points_out, out.p, sizeof(double) * 3 * n_tracks, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
-            cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = SRK_E_CUDA; break; }
-        if (h_err != 0) { srk_internal_set_error("Provide 2 or more projections of a 3D point (obs-geom.cpp:687)"); rc = SRK_E_INVALID_ARG; }
-    } while (false);
-    if (rc == SRK_E_CUDA) srk_internal_set_error(cudaGetErrorString(cudaGetLastError()));
-    cudaStreamDestroy(st);
-    return rc;
+    TriPool& pl = g_pool;
+    if (pl.device != device) {
+        if (pl.device >= 0) {   // buffers of another device: drop them
+            cudaSetDevice(pl.device);
+            for (DevBuf* d : {&pl.tb, &pl.fr, &pl.xy, &pl.pm, &pl.out, &pl.err}) { if (d->p) cudaFree(d->p); d->p = nullptr; d->cap = 0; }
+            if (pl.st) cudaStreamDestroy(pl.st);
+            if (pl.e0) cudaEventDestroy(pl.e0);
+            if (pl.e1) cudaEventDestroy(pl.e1);
+            pl.st = nullptr; pl.e0 = pl.e1 = nullptr;
+            cudaSetDevice(device);
+        }
+        pl.device = device;
+    }
+    if (pl.st == nullptr) { FE_CUDA(cudaStreamCreateWithFlags(&pl.st, cudaStreamNonBlocking)); FE_CUDA(cudaEventCreate(&pl.e0)); FE_CUDA(cudaEventCreate(&pl.e1)); }
+    FE_CUDA(pl.tb.alloc(sizeof(int64_t) * (n_tracks + 1))); FE_CUDA(pl.fr.alloc(sizeof(int32_t) * n_obs)); FE_CUDA(pl.xy.alloc(sizeof(double) * 2 * n_obs));
+    FE_CUDA(pl.pm.alloc(sizeof(double) * 12 * (size_t)n_frames)); FE_CUDA(pl.out.alloc(sizeof(double) * 3 * n_tracks)); FE_CUDA(pl.err.alloc(sizeof(int)));
+    cudaStream_t st = pl.st;
+    FE_CUDA(cudaMemcpyAsync(pl.tb.p, track_begin, sizeof(int64_t) * (n_tracks + 1), cudaMemcpyHostToDevice, st));
+    FE_CUDA(cudaMemcpyAsync(pl.fr.p, obs_frame, sizeof(int32_t) * n_obs, cudaMemcpyHostToDevice, st));
+    FE_CUDA(cudaMemcpyAsync(pl.xy.p, obs_xy, sizeof(double) * 2 * n_obs, cudaMemcpyHostToDevice, st));
+    FE_CUDA(cudaMemcpyAsync(pl.pm.p, proj, sizeof(double) * 12 * (size_t)n_frames, cudaMemcpyHostToDevice, st));
+    FE_CUDA(cudaMemsetAsync(pl.err.p, 0, sizeof(int), st));
+    FE_CUDA(cudaEventRecord(pl.e0, st));
+    k_triangulate<<<(unsigned)((n_tracks + 127) / 128), 128, 0, st>>>(n_tracks, (const int64_t*)pl.tb.p, (const int32_t*)pl.fr.p, (const double*)pl.xy.p,
+                                                                   (const double*)pl.pm.p, n_frames, f0, (double*)pl.out.p, (int*)pl.err.p);
+    FE_CUDA(cudaEventRecord(pl.e1, st));
+    int h_err = 0;
+    FE_CUDA(cudaMemcpyAsync(points_out, pl.out.p, sizeof(double) * 3 * n_tracks, cudaMemcpyDeviceToHost, st));
+    FE_CUDA(cudaMemcpyAsync(&h_err, pl.err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FE_CUDA(cudaStreamSynchronize(st));
+    FE_CUDA(cudaGetLastError());
+    cudaEventElapsedTime(&g_last_kernel_ms, pl.e0, pl.e1);
+    if (h_err & 2) { srk_internal_set_error("frame index out of range"); return SRK_E_INVALID_ARG; }
+    if (h_err & 1) { srk_internal_set_error("Provide 2 or more projections of a 3D point (obs-geom.cpp:687)"); return SRK_E_INVALID_ARG; }
+    return SRK_OK;
 }
+
+double srk_triangulate_last_kernel_ms(void) { return (double)g_last_kernel_ms; }
 
 int srk_decompose_proj_mat(const double* P, double* scale_factor, double* K, double* direct_pose) {
     if (P == nullptr || scale_factor == nullptr || K == nullptr || direct_pose == nullptr) { srk_internal_set_error("null argument"); return SRK_E_INVALID_ARG; }

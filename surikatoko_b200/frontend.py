@@ -14,6 +14,7 @@ def _lib():
         L.srk_triangulate_tracks.argtypes = [C.c_int, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         L.srk_decompose_proj_mat.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
         L.srk_read_matrix_from_file.argtypes = [C.c_char_p, C.c_char, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.srk_triangulate_last_kernel_ms.restype = C.c_double
         L._frontend_bound = True
     return L
 
@@ -24,17 +25,24 @@ def _check(rc):
     return rc
 
 
-def Triangulate3DPointByLeastSquares(track_begin, obs_frame, obs_xy, proj_mats, f0, device=0):
-    """Batched obs-geom.cpp:679-727.  proj_mats: [n_frames, 3, 4] (f0-scaled projection matrices); returns [n_tracks, 3]."""
+def Triangulate3DPointByLeastSquares(track_begin, obs_frame, obs_xy, proj_mats, f0, device=0, out=None):
+    """Batched obs-geom.cpp:679-727.  proj_mats: [n_frames, 3, 4] (f0-scaled projection matrices); returns [n_tracks, 3]
+    (written into `out` when given, e.g. a pinned buffer)."""
     tb = np.ascontiguousarray(track_begin, dtype=np.int64)
     fr = np.ascontiguousarray(obs_frame, dtype=np.int32)
     xy = np.ascontiguousarray(obs_xy, dtype=np.float64).reshape(-1, 2)
     P = np.asarray(proj_mats, dtype=np.float64).reshape(-1, 3, 4)
     pm = np.ascontiguousarray(P.transpose(0, 2, 1)).reshape(-1, 12)      # column-major per frame
-    out = np.zeros((len(tb) - 1, 3))
+    if out is None:
+        out = np.zeros((len(tb) - 1, 3))
+    assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == 3 * (len(tb) - 1)
     _check(_lib().srk_triangulate_tracks(device, len(tb) - 1, len(fr), P.shape[0], tb.ctypes.data, fr.ctypes.data, xy.ctypes.data, pm.ctypes.data,
                                          float(f0), out.ctypes.data))
     return out
+
+
+def last_triangulation_kernel_ms():
+    return float(_lib().srk_triangulate_last_kernel_ms())
 
 
 def DecomposeProjMat(proj_mat):
