@@ -156,6 +156,12 @@ SRK_API int srk_ba_get_timing(void* h, const char* name, double* ms_last, double
  * and the floating-point operations the factorisation executed (zero tiles are skipped, so a block-banded system costs what
  * its fill costs).  bench.py uses it for the FP64 roofline. */
 SRK_API int srk_ba_solve_stats(void* h, int64_t* n_f, int64_t* block_rows, int64_t* nonzero_tiles, double* factor_flops);
+/* Order in which the last dense solve factored the reduced camera system (the reference factors in capture order, BA.cpp:1911; a
+ * symmetric permutation does not change the solution).  parts = 0: capture order, one chain of block_rows dependent block columns.
+ * parts > 0: nested-dissection order -- `parts` independent groups of cameras factored concurrently (the longest is max_part_blocks
+ * block columns) followed by a separator of separator_blocks block columns; ordered_n = n_f + padding to 64-column part boundaries.
+ * SRK_SOLVE_ORDER=0 in the environment of srk_ba_create forces capture order. */
+SRK_API int srk_ba_solve_order(void* h, int64_t* ordered_n, int64_t* parts, int64_t* max_part_blocks, int64_t* separator_blocks);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,7 @@ def load_library():
     L.srk_ba_set_timing.argtypes = [C.c_void_p, C.c_int]
     L.srk_ba_get_timing.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.srk_ba_solve_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.srk_ba_solve_order.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.srk_ba_default_options.argtypes = [C.POINTER(_Options)]
     L.srk_ba_default_options.restype = None
     _lib = L
@@ -273,7 +274,10 @@ class Engine:
         """Structure of the last dense Cholesky factor: n_f, 64-wide block rows, non-zero tiles of L, flops executed."""
         nf, nb, nz, fl = C.c_int64(), C.c_int64(), C.c_int64(), C.c_double()
         _check(self._lib.srk_ba_solve_stats(self._h, C.byref(nf), C.byref(nb), C.byref(nz), C.byref(fl)))
-        return dict(n_f=nf.value, block_rows=nb.value, nonzero_tiles=nz.value, factor_flops=fl.value)
+        on, parts, mp, sb = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _check(self._lib.srk_ba_solve_order(self._h, C.byref(on), C.byref(parts), C.byref(mp), C.byref(sb)))
+        return dict(n_f=nf.value, block_rows=nb.value, nonzero_tiles=nz.value, factor_flops=fl.value, ordered_n=on.value, parts=parts.value,
+                    max_part_blocks=mp.value, separator_blocks=sb.value)
 
     def set_timing(self, enabled):
         _check(self._lib.srk_ba_set_timing(self._h, 1 if enabled else 0))

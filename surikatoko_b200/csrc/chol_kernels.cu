@@ -601,6 +601,7 @@ __global__ void __launch_bounds__(256) k_right_solve_dmma(int rows, int row0, do
 // cp.async.cg / ld.global.cg (L2, never a stale L1 line).  F starts as the non-zero tile pattern of the input (k_tile_pattern),
 // fill is tracked symbolically as updates are applied, so the structure handed to the substitutions is exact.
 constexpr int kBandCluster = 8;
+constexpr int kCholMaxParts = CholPartition::kMaxParts;
 constexpr int kBandTS = NB + 4;        // [k][row] tile stride in shared memory: 68 = 4 (mod 16), conflict-free fragment loads
 constexpr int kBandMaxFill = 4;        // sparse path when the input has <= kBandMaxFill * nblk non-zero off-diagonal tiles
 struct BandSmem {
@@ -672,7 +673,10 @@ __device__ __forceinline__ void band_tile_nt(const double* sA, const double* sB,
 
 // One 64x64x64 tile operation of the cluster kernel (one copy of the code: it runs a few times per step, every copy would be
 // another set of instruction-cache misses).  mode 0: A(ra,k) <- A(ra,k) Linv_k^T in place;  mode 1: A(ra,rb) -= X(ra,k) X(rb,k)^T.
-__device__ __noinline__ void band_tile_op(BandSmem& sm, int n, double* A, int64_t ld, const double* dinv, unsigned char* F, int nblk, int mode, int ra, int rb, int k) {
+// atomic (mode 1 only): the destination tile lies in the separator block shared by several clusters (nested-dissection order,
+// see dense_cholesky_set_partition): the update goes out as red.global.add.f64 instead of a read-modify-write.
+__device__ __noinline__ void band_tile_op(BandSmem& sm, int n, double* A, int64_t ld, const double* dinv, unsigned char* F, int nblk, int mode, int ra, int rb, int k,
+                                          bool atomic) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16, g = lane >> 2, tg = lane & 3;
     __syncthreads();
@@ -694,7 +698,7 @@ __device__ __noinline__ void band_tile_op(BandSmem& sm, int n, double* A, int64_
     band_tile_nt(sm.A, sm.B, acc);
     const int cbase = (mode == 0 ? k : rb) * NB;
     double cur[4][2][2];
-    if (mode == 1) {   // all 16 loads of the read-modify-write first: behind a store the compiler has to assume aliasing and serialises them
+    if (mode == 1 && !atomic) {   // all 16 loads of the read-modify-write first: behind a store the compiler has to assume aliasing and serialises them
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -715,28 +719,38 @@ __device__ __noinline__ void band_tile_op(BandSmem& sm, int n, double* A, int64_
                 if (row >= n || col >= n) continue;
                 double* p = A + (size_t)col * ld + row;
                 if (mode == 0) *p = acc[i][j][e];
-                else if (row >= col) *p = cur[i][j][e] - acc[i][j][e];
+                else if (row >= col) { if (atomic) atomicAdd(p, -acc[i][j][e]); else *p = cur[i][j][e] - acc[i][j][e]; }
             }
     if (mode == 1 && tid == 0 && ra != rb) F[(size_t)rb * nblk + ra] = 1;   // fill (or already non-zero)
 }
 
 // development aid: clock64() per phase, CTA 0 (slots 0..5: wait A, list, solve, wait B, diag update, potrf) and CTA 1 (8..11: wait A, solve, wait B, updates)
 __device__ long long g_band_prof[16];
-#define BAND_T(slot) do { if (tid == 0 && rank <= 1) { const long long now_ = clock64(); g_band_prof[rank * 8 + (slot)] += now_ - t_prev; t_prev = now_; } } while (0)
+#define BAND_T(slot) do { if (tid == 0 && rank <= 1 && blockIdx.x < kBandCluster) { const long long now_ = clock64(); g_band_prof[rank * 8 + (slot)] += now_ - t_prev; t_prev = now_; } } while (0)
+// Column ranges of the clusters (nested-dissection order of the reduced camera system, solve_order.h): in phase 0 cluster c
+// factors the block columns [k0[c], k1[c]) of its own part -- parts do not touch each other's tiles; what they contribute to the
+// separator block (rows and columns >= ksep) is added atomically -- and in phase 1 ONE cluster factors [ksep, nblk).
+// An unpartitioned factorisation is phase 1 with ksep = 0.
+using BandParts = CholPartition;
 __global__ void __cluster_dims__(kBandCluster, 1, 1) __launch_bounds__(256, 1)
-k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk) {
+k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk, const BandParts bp, int phase) {
     extern __shared__ __align__(16) unsigned char band_raw[];
     BandSmem& sm = *reinterpret_cast<BandSmem*>(band_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = (int)cluster_cta_rank();
+    const int cl = blockIdx.x / kBandCluster;
+    const int kbeg = phase == 0 ? bp.k0[cl] : bp.ksep;
+    const int kend = phase == 0 ? bp.k1[cl] : nblk;
+    const int shared_from = phase == 0 ? bp.ksep : 0x7fffffff;      // tiles (ra, rb) with rb >= shared_from are shared between clusters
+    if (kbeg >= kend) return;                                        // uniform over the cluster
 
-    auto solve_tile = [&](int r, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 0, r, r, k); };
-    auto update_pair = [&](int ra, int rb, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 1, ra, rb, k); };
+    auto solve_tile = [&](int r, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 0, r, r, k, false); };
+    auto update_pair = [&](int ra, int rb, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 1, ra, rb, k, rb >= shared_from); };
 
     static_assert(2 * NB * kBandTS >= (int)kPotrfScratchDoubles, "potrf scratch must fit the two operand tiles");
-    if (rank == 0) potrf64_blk_dev<true>(n, 0, A, ld, dinv, info, F, nblk, sm.A);
+    if (rank == 0) potrf64_blk_dev<true>(n, kbeg * NB, A, ld, dinv + (size_t)kbeg * NB * NB, info, F, nblk, sm.A);
     long long t_prev = clock64();
-    for (int k = 0; k < nblk; ++k) {
+    for (int k = kbeg; k < kend; ++k) {
         cluster_sync_all();                                   // A: potrf(k) and the updates of step k-1 are visible
         BAND_T(0);
         // non-zero row tiles of column k, ascending
@@ -764,7 +778,7 @@ k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char
             if (next_in_list) update_pair(k + 1, k + 1, k);
             __syncthreads();
             BAND_T(4);
-            if (k + 1 < nblk) potrf64_blk_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk, sm.A, g_potrf_prof);
+            if (k + 1 < kend) potrf64_blk_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk, sm.A, g_potrf_prof);
             BAND_T(5);
         } else {
             for (int p = (next_in_list ? 1 : 0) + (rank - 1); p < npairs; p += kBandCluster - 1) {
@@ -986,9 +1000,13 @@ __device__ __forceinline__ void trsv_cl_issue(double* slot, int op, int n, const
         cp_async16(slot + mj * kTrsvClLDT + mi, bytes > 0 ? src + (size_t)mj * smaj : base, bytes);
     }
 }
+// Partitioned factor (BandParts): the substitutions run as four launches -- forward over the parts (one cluster each; what a part
+// subtracts from the separator rows is collected from zero and added atomically at the end), forward + backward over the separator
+// (one cluster), backward over the parts (the separator's solved blocks are read as given multipliers first).
+//   phase 0: blocks [k0[c], k1[c]) of part c;   phase 1: blocks [ksep, nblk) (ksep = 0: the whole unpartitioned system).
 __global__ void __cluster_dims__(kBandCluster, 1, 1) __launch_bounds__(256, 1)
 k_trsv_cluster(int n, const double* __restrict__ L, int64_t ld, const double* __restrict__ dinv, double* b, const int* __restrict__ stats,
-               const int* __restrict__ list, int backward) {
+               const int* __restrict__ list, int backward, const BandParts bp, int phase) {
     extern __shared__ __align__(16) unsigned char trsv_raw[];
     TrsvClSmem& sm = *reinterpret_cast<TrsvClSmem*>(trsv_raw);
     const int nblk = (n + NB - 1) / NB;
@@ -997,21 +1015,34 @@ k_trsv_cluster(int n, const double* __restrict__ L, int64_t ld, const double* __
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    // my ops, in list order: an op (k, j) writes row block j
+    const int cl = blockIdx.x / kBandCluster;
+    const int kbeg = phase == 0 ? bp.k0[cl] : bp.ksep;
+    const int kend = phase == 0 ? bp.k1[cl] : nblk;
+    const int ksep = phase == 0 ? bp.ksep : nblk;         // phase 0: blocks >= ksep belong to the separator
+    if (kbeg >= kend) return;
+    // my ops, in list order: an op (k, j) writes row block j.
+    //   forward:  solved block k in my range; j in my range or (phase 0) in the separator
+    //   backward: j in my range; k in my range or (phase 0) in the separator
     if (warp == 0) {
         int m = 0;
         for (int base = 0; base < nops; base += 32) {
             const int t = base + lane;
             const int op = t < nops ? list[t] : 0;
-            const bool mine = t < nops && ((op & 0xffff) % kBandCluster) == rank;
+            const int k = op >> 16, j = op & 0xffff;
+            const bool kin = k >= kbeg && k < kend, jin = j >= kbeg && j < kend;
+            const bool sel = backward ? (jin && (kin || k >= ksep)) : (kin && (jin || j >= ksep));
+            const bool mine = t < nops && sel && (j % kBandCluster) == rank;
             const unsigned bal = __ballot_sync(0xffffffffu, mine);
             if (mine) sm.ops[m + __popc(bal & ((1u << lane) - 1))] = op;
             m += __popc(bal);
         }
         if (lane == 0) sm.nmy = m;
     }
-    for (int jb = rank; jb < nblk; jb += kBandCluster)
-        for (int i = tid; i < NB; i += 256) sm.bown[jb / kBandCluster][i] = (jb * NB + i < n) ? b[jb * NB + i] : 0.0;
+    for (int jb = rank; jb < nblk; jb += kBandCluster) {
+        const bool own = jb >= kbeg && jb < kend;
+        if (!own && jb < ksep) continue;
+        for (int i = tid; i < NB; i += 256) sm.bown[jb / kBandCluster][i] = (own && jb * NB + i < n) ? b[jb * NB + i] : 0.0;   // separator rows: partial sums from zero
+    }
     __syncthreads();
     const int nmy = sm.nmy;
     for (int i = 0; i < kTrsvClRing - 1; ++i) { if (i < nmy) trsv_cl_issue(sm.ring[i], sm.ops[i], n, L, ld, dinv, backward); cp_async_commit(); }
@@ -1043,8 +1074,30 @@ k_trsv_cluster(int n, const double* __restrict__ L, int64_t ld, const double* __
         return (s0 + s1) + (s2 + s3);
     };
     cluster.sync();                                           // every CTA of the cluster is running before the first remote store
-    for (int sidx = 0; sidx < nblk; ++sidx) {
-        const int k = backward ? nblk - 1 - sidx : sidx;
+    int sidx = 0;
+    auto apply_column = [&](int k) {                          // my tiles of block column k, multipliers in yk[sidx & 1]
+        const double* yk = sm.yk[sidx & 1];
+        while (t < nmy && (sm.ops[t] >> 16) == k) {
+            const int j = sm.ops[t] & 0xffff;
+            const double d = run_op(yk);
+            if (tid < NB) sm.bown[j / kBandCluster][tid] -= d;
+            ++t;
+            __syncthreads();                                  // the ring slot and b_j are settled before the next op touches them
+        }
+    };
+    if (backward && phase == 0) {
+        // the separator is solved: its blocks are plain multipliers, every CTA reads them from global memory itself
+        for (int k = nblk - 1; k >= ksep; --k, ++sidx) {
+            if (!(t < nmy && (sm.ops[t] >> 16) == k)) continue;   // no tile of mine in this column (CTA-uniform)
+            if (tid < NB) sm.yk[sidx & 1][tid] = (k * NB + tid < n) ? __ldcg(b + k * NB + tid) : 0.0;
+            __syncthreads();
+            apply_column(k);
+        }
+        sidx = (sidx + 1) & ~1;
+        cluster.sync();                                       // nobody still reads its local yk when the first remote push arrives
+    }
+    for (int s2 = 0; s2 < kend - kbeg; ++s2, ++sidx) {
+        const int k = backward ? kend - 1 - s2 : kbeg + s2;
         if (t < nmy && sm.ops[t] == ((k << 16) | k)) {      // I own block k: every update of b_k has been applied (list order)
             double* bk = sm.bown[k / kBandCluster];
             const double y = run_op(bk);
@@ -1057,13 +1110,12 @@ k_trsv_cluster(int n, const double* __restrict__ L, int64_t ld, const double* __
             __syncthreads();
         }
         cluster_sync_all();                                   // y_k has arrived everywhere
-        const double* yk = sm.yk[sidx & 1];
-        while (t < nmy && (sm.ops[t] >> 16) == k) {
-            const int j = sm.ops[t] & 0xffff;
-            const double d = run_op(yk);
-            if (tid < NB) sm.bown[j / kBandCluster][tid] -= d;
-            ++t;
-            __syncthreads();                                  // the ring slot and b_j are settled before the next op touches them
+        apply_column(k);
+    }
+    if (!backward && phase == 0) {                            // what this part subtracts from the separator's right-hand side
+        for (int jb = rank; jb < nblk; jb += kBandCluster) {
+            if (jb < ksep) continue;
+            if (tid < NB && jb * NB + tid < n) { const double v = sm.bown[jb / kBandCluster][tid]; if (v != 0.0) atomicAdd(b + jb * NB + tid, v); }
         }
     }
 }
@@ -1327,7 +1379,7 @@ static FactorGraph g_fg;
 
 // Sparse-factor path: tile pattern of the input, then (when it is sparse enough) the single-cluster kernel.  Returns the number of
 // launches, or 0 when the matrix is not sparse and the launch-per-operation path has to run.
-static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
+static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part) {
     const int nblk = chol_nblk(n);
     if (nblk < 2 || nblk > kMaxRowBlocks) return 0;
     static int force = -1;    // SRK_CHOL_PATH=dense disables the sparse path, =band forces it (development aid)
@@ -1347,14 +1399,24 @@ static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, do
     k_tile_pattern<<<dim3(nblk, nblk), 256, 0, st>>>(n, A, ld, nblk, F, cnt);
     int h = -1;
     if (cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return 0; }
-    if (h < 0 || (force != 2 && h > kBandMaxFill * nblk)) return 0;
-    k_band_chol<<<kBandCluster, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk);
+    const int max_fill = (part != nullptr && part->nparts > 0) ? 2 * kBandMaxFill : kBandMaxFill;   // a partitioned pattern carries the separator rows as well
+    if (h < 0 || (force != 2 && h > max_fill * nblk)) return 0;
+    int64_t nl = 2;
+    if (part != nullptr && part->nparts > 0) {
+        k_band_chol<<<kBandCluster * part->nparts, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 0);
+        k_band_chol<<<kBandCluster, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 1);
+        nl += 2;
+    } else {
+        CholPartition whole; whole.nparts = 0; whole.ksep = 0;
+        k_band_chol<<<kBandCluster, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk, whole, 1);
+        nl += 1;
+    }
     if (cudaGetLastError() != cudaSuccess) return 0;
     k_build_trsv_lists<<<1, 1024, 0, st>>>(n, nblk, F, ws_nzt(ws, n), ws_list(ws, n, 0), ws_list(ws, n, 1));
-    return 3;
+    return nl;
 }
 
-int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part) {
     set_attrs_once();
     g_epoch = 0;
     static int prof_env = -1;
@@ -1365,7 +1427,7 @@ int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
         if (cs == cudaStreamCaptureStatusNone) {   // the pattern read-back synchronises: not inside somebody's capture
-            const int64_t nl = try_band_factor(st, n, A, ld, ws, info_dev);
+            const int64_t nl = try_band_factor(st, n, A, ld, ws, info_dev, part);
             if (nl > 0) return nl;
         }
     }
@@ -1397,7 +1459,7 @@ static void launch_syrk(cudaStream_t st, int n, double* A, int64_t ld, int kcol0
     k_syrk_dmma<64><<<g_sms * 3, SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmem, st>>>(n, A, ld, kcol0, K, origin, col_end, F, nblk);
 }
 
-static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, int backward) {
+static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, int backward, const CholPartition* part) {
     set_attrs_once();
     const int nblk = chol_nblk(n);
     int blocks = g_coop_blocks < nblk ? g_coop_blocks : nblk;
@@ -1417,7 +1479,17 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
             use_cluster = (e != nullptr && e[0] == '0') ? 0 : 1;
             if (use_cluster && cudaFuncSetAttribute(k_trsv_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsvClSmem)) != cudaSuccess) { cudaGetLastError(); use_cluster = 0; }
         }
-        if (use_cluster) k_trsv_cluster<<<kBandCluster, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, ws_list(ws, n, backward), backward);
+        if (use_cluster) {
+            const int* lst = ws_list(ws, n, backward);
+            if (part != nullptr && part->nparts > 0) {
+                if (!backward) k_trsv_cluster<<<kBandCluster * part->nparts, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, *part, 0);
+                k_trsv_cluster<<<kBandCluster, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, *part, 1);
+                if (backward) k_trsv_cluster<<<kBandCluster * part->nparts, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, *part, 0);
+            } else {
+                CholPartition whole; whole.nparts = 0; whole.ksep = 0;
+                k_trsv_cluster<<<kBandCluster, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, whole, 1);
+            }
+        }
         else k_trsv_single<<<1, 256, sizeof(double) * (size_t)nblk * NB + sizeof(int) * (size_t)(kTrsvSparseFill + 1) * nblk, st>>>(n, L, ld, dinv, b, nzt, ws_list(ws, n, backward),
                                                                                                                                   backward);
         if (g_prof) {
@@ -1431,7 +1503,7 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
     void* args[] = {(void*)&n, (void*)&L, (void*)&ld, (void*)&dinv, (void*)&b, (void*)&ybuf, (void*)&flags, (void*)&F, (void*)&epoch, (void*)&backward,
                     (void*)&cacheF, (void*)&nzt};
     cudaLaunchCooperativeKernel((void*)k_trsv_flags, dim3(blocks), dim3(256), args, smem, st);
-    return 2;
+    return 2 + ((part != nullptr && part->nparts > 0 && n <= kTrsvSparseMaxN) ? 1 : 0);
 }
 // Structure of the last factor held in `ws`: non-zero 64x64 tiles of L and the flops the factorisation actually executed
 // (potrf 64^3/3 per diagonal block, 64^3 per off-diagonal tile for the right solve, 2*64^3 per pair of non-zero tiles of a
@@ -1456,8 +1528,8 @@ int dense_cholesky_stats(cudaStream_t st, int n, const double* ws, int64_t* nblk
     if (factor_flops) *factor_flops = fl;
     return 0;
 }
-int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 0); }
-int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b) { return trsv(st, n, L, ld, ws, b, 1); }
+int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part) { return trsv(st, n, L, ld, ws, b, 0, part); }
+int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part) { return trsv(st, n, L, ld, ws, b, 1, part); }
 
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 
 #include "../../include/srk/ba_c_api.h"
 #include "kernels.h"
+#include "solve_order.h"
 #include "pcg.h"
 #include "prep.h"
 
@@ -111,6 +112,11 @@ struct Engine {
     // derivative pass and solve
     Buf J, Ggf, pinv, skipped, deferred, Srhs, Lfac, dinv, xsol, resid, dfull, partial, errsum, slots, flags, skipped_cnt, dbg;
     Buf tmask, tlist, tpacked;   // multi-GPU tile exchange of S
+    // nested-dissection order of the reduced camera system (solve_order.h): built lazily at the first dense solve after a bind
+    srk::SolveOrder order;
+    bool order_ready = false;
+    int solve_order_enabled = 1; // SRK_SOLVE_ORDER=0: always factor in capture order (cross-check)
+    Buf adjbuf, order_src, xperm;
     int tile_exchange = 1;       // SRK_TILE_EXCHANGE=0: always all-reduce the whole dense system
     int64_t n_deferred = 0;   // points the tiled Schur kernel leaves to the per-point kernel (structure only, known at bind time)
     int schur_tile_points = 256;
@@ -320,6 +326,7 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     SRK_CUDA(cudaStreamSynchronize(st));
     SRK_CUDA(cudaGetLastError());
     e.bound = true;
+    e.order_ready = false;
     return e.norm_failed ? 1 : SRK_OK;
 }
 
@@ -394,6 +401,41 @@ int derivative_pass(Engine& e) {
     return do_allreduce(e, e.Ggf.as<double>(), 110 * (int64_t)e.M);
 }
 
+// Order of the reduced camera system for the sparse-factor Cholesky: camera co-visibility graph of the bound observations (union over
+// ranks, so that every rank factors in the same order and takes bit-identical decisions) -> host nested dissection (solve_order.cu).
+int ensure_solve_order(Engine& e) {
+    if (e.order_ready) return SRK_OK;
+    e.order = srk::SolveOrder{};
+    e.order_ready = true;
+    const int M = e.M;
+    if (!e.solve_order_enabled || e.nf < 24 * 64 || M < 8) return SRK_OK;
+    cudaStream_t st = e.stream;
+    const size_t cells = (size_t)M * (size_t)M;
+    SRK_CUDA(e.adjbuf.ensure(sizeof(double) * cells));
+    SRK_CUDA(cudaMemsetAsync(e.adjbuf.p, 0, sizeof(double) * cells, st));
+    srk::launch_cam_adjacency(st, e.N, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), M, e.adjbuf.as<double>()); e.launches += e.N > 0 ? 1 : 0;
+    int rc = do_allreduce(e, e.adjbuf.as<double>(), (int64_t)cells);
+    if (rc != SRK_OK) return rc;
+    std::vector<double> h(cells);
+    SRK_CUDA(cudaMemcpyAsync(h.data(), e.adjbuf.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, st));
+    SRK_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned char> adj(cells);
+    for (size_t i = 0; i < cells; ++i) adj[i] = h[i] != 0.0;
+    std::vector<int> gsize(M, 10);
+    gsize[0] = 4; gsize[1] = 9;                          // quirk Q13: frame 0 keeps its intrinsics, frame 1 loses T[unity]
+    e.order = srk::build_solve_order(M, gsize.data(), adj.data());
+    if (!e.order.active) return SRK_OK;
+    if (e.order.n != e.nf) { e.order = srk::SolveOrder{}; return SRK_OK; }
+    const int np = e.order.np; const size_t ldp = ((size_t)np + 7) & ~(size_t)7;
+    SRK_CUDA(e.order_src.ensure(sizeof(int) * (size_t)np));
+    SRK_CUDA(cudaMemcpyAsync(e.order_src.p, e.order.src.data(), sizeof(int) * (size_t)np, cudaMemcpyHostToDevice, st));
+    SRK_CUDA(cudaStreamSynchronize(st));
+    SRK_CUDA(e.xperm.ensure(sizeof(double) * ldp));
+    SRK_CUDA(e.Lfac.ensure(sizeof(double) * ldp * (size_t)np));
+    SRK_CUDA(e.dinv.ensure(sizeof(double) * srk::dense_cholesky_dinv_doubles(np)));
+    return SRK_OK;
+}
+
 // Sum of the dense reduced camera system over ranks.  The union of the ranks' non-zero 64x64 tiles is found first (a small mask
 // all-reduce); when it is sparse only those tiles (+ rhs) travel: 16 MB instead of 0.8 GB at configs[2].
 int allreduce_system(Engine& e, double* S, double* rhs) {
@@ -460,26 +502,51 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
         }
         int rc = allreduce_system(e, S, rhs);
         if (rc != SRK_OK) return rc;
+        rc = ensure_solve_order(e);
+        if (rc != SRK_OK) return rc;
         {
             Scope s(e, F_SOLVE);
             int refine = opt != nullptr ? opt->refine_steps : 1;
             double* L = e.Lfac.as<double>();
-            if (refine > 0) { srk::launch_mirror_lower(st, nf, S, ld); e.launches += 1; }
-            SRK_CUDA(cudaMemcpyAsync(L, S, sizeof(double) * (size_t)ld * nf, cudaMemcpyDeviceToDevice, st));
-            SRK_CUDA(cudaMemcpyAsync(x, rhs, sizeof(double) * nf, cudaMemcpyDeviceToDevice, st));
             double* di = e.dinv.as<double>();
-            { Scope s2(e, F_FACTOR); e.launches += srk::dense_cholesky_factor(st, nf, L, ld, e.dinv.as<double>(), e.flags.as<int>() + 2); }
-            { Scope s2(e, F_TRSV);
-              e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, x);
-              e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, x); }
             double* r = e.resid.as<double>();
-            for (int it = 0; it < refine; ++it) {
-                srk::launch_residual_dd(st, nf, S, ld, x, rhs, r);
-                e.launches += 1;
+            if (refine > 0) { srk::launch_mirror_lower(st, nf, S, ld); e.launches += 1; }
+            if (e.order.active) {
+                // factor P S P^T (parts concurrently, separator last); vectors travel natural -> ordered -> natural
+                const int np = e.order.np; const int64_t ldp = ((int64_t)np + 7) & ~(int64_t)7;
+                const int* src = e.order_src.as<int>(); double* xp = e.xperm.as<double>();
+                const srk::CholPartition* part = &e.order.part;
+                srk::launch_permute_sym(st, nf, S, ld, refine > 0 ? 1 : 0, np, src, L, ldp); e.launches += 1;
+                srk::launch_gather_vec(st, np, src, rhs, xp); e.launches += 1;
+                { Scope s2(e, F_FACTOR); e.launches += srk::dense_cholesky_factor(st, np, L, ldp, di, e.flags.as<int>() + 2, part); }
                 { Scope s2(e, F_TRSV);
-                  e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, r);
-                  e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, r); }
-                srk::launch_axpy1(st, nf, r, x); e.launches += 1;
+                  e.launches += srk::dense_cholesky_forward(st, np, L, ldp, di, xp, part);
+                  e.launches += srk::dense_cholesky_backward(st, np, L, ldp, di, xp, part); }
+                srk::launch_scatter_vec(st, np, src, xp, x); e.launches += 1;
+                for (int it = 0; it < refine; ++it) {
+                    srk::launch_residual_dd(st, nf, S, ld, x, rhs, r); e.launches += 1;
+                    srk::launch_gather_vec(st, np, src, r, xp); e.launches += 1;
+                    { Scope s2(e, F_TRSV);
+                      e.launches += srk::dense_cholesky_forward(st, np, L, ldp, di, xp, part);
+                      e.launches += srk::dense_cholesky_backward(st, np, L, ldp, di, xp, part); }
+                    srk::launch_scatter_vec(st, np, src, xp, r); e.launches += 1;
+                    srk::launch_axpy1(st, nf, r, x); e.launches += 1;
+                }
+            } else {
+                SRK_CUDA(cudaMemcpyAsync(L, S, sizeof(double) * (size_t)ld * nf, cudaMemcpyDeviceToDevice, st));
+                SRK_CUDA(cudaMemcpyAsync(x, rhs, sizeof(double) * nf, cudaMemcpyDeviceToDevice, st));
+                { Scope s2(e, F_FACTOR); e.launches += srk::dense_cholesky_factor(st, nf, L, ld, di, e.flags.as<int>() + 2); }
+                { Scope s2(e, F_TRSV);
+                  e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, x);
+                  e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, x); }
+                for (int it = 0; it < refine; ++it) {
+                    srk::launch_residual_dd(st, nf, S, ld, x, rhs, r);
+                    e.launches += 1;
+                    { Scope s2(e, F_TRSV);
+                      e.launches += srk::dense_cholesky_forward(st, nf, L, ld, di, r);
+                      e.launches += srk::dense_cholesky_backward(st, nf, L, ld, di, r); }
+                    srk::launch_axpy1(st, nf, r, x); e.launches += 1;
+                }
             }
         }
         e.solver_used = SRK_SOLVER_DENSE_CHOLESKY;
@@ -701,6 +768,7 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     e->device = dev;
     if (const char* v = std::getenv("SRK_SCHUR_IMPL")) e->schur_impl = std::atoi(v) == 1 ? 1 : 0;
     if (const char* v = std::getenv("SRK_TILE_EXCHANGE")) e->tile_exchange = std::atoi(v) != 0 ? 1 : 0;
+    if (const char* v = std::getenv("SRK_SOLVE_ORDER")) e->solve_order_enabled = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SCHUR_TILE")) { const int t = std::atoi(v); if (t >= 16 && t <= 4096 && t % 16 == 0) e->schur_tile_fixed = t; }
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; set_error("cudaStreamCreate failed"); return SRK_E_CUDA; }
     e->stream = e->own_stream;
@@ -898,7 +966,19 @@ int srk_ba_solve_stats(void* h, int64_t* n_f, int64_t* block_rows, int64_t* nonz
     if (!e.bound || e.solver_used != SRK_SOLVER_DENSE_CHOLESKY || e.dinv.p == nullptr) { set_error("no dense factor on this handle"); return SRK_E_NOT_BOUND; }
     SRK_CUDA(cudaSetDevice(e.device));
     if (n_f != nullptr) *n_f = e.nf;
-    if (srk::dense_cholesky_stats(e.stream, e.nf, e.dinv.as<double>(), block_rows, nonzero_tiles, factor_flops) != 0) { set_error("could not read the factor structure"); return SRK_E_CUDA; }
+    if (srk::dense_cholesky_stats(e.stream, (e.order_ready && e.order.active) ? e.order.np : e.nf, e.dinv.as<double>(), block_rows, nonzero_tiles, factor_flops) != 0) { set_error("could not read the factor structure"); return SRK_E_CUDA; }
+    return SRK_OK;
+}
+
+int srk_ba_solve_order(void* h, int64_t* ordered_n, int64_t* parts, int64_t* max_part_blocks, int64_t* separator_blocks) {
+    if (h == nullptr) { set_error("null handle"); return SRK_E_INVALID_ARG; }
+    Engine& e = *(Engine*)h;
+    if (!e.bound) { set_error("no problem bound"); return SRK_E_NOT_BOUND; }
+    const bool on = e.order_ready && e.order.active;
+    if (ordered_n != nullptr) *ordered_n = on ? e.order.np : e.nf;
+    if (parts != nullptr) *parts = on ? e.order.part.nparts : 0;
+    if (max_part_blocks != nullptr) *max_part_blocks = on ? e.order.max_part_blocks : 0;
+    if (separator_blocks != nullptr) *separator_blocks = on ? e.order.sep_blocks : 0;
     return SRK_OK;
 }
 

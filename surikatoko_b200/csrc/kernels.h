@@ -50,10 +50,14 @@ inline const double* dense_cholesky_dinv_block(const double* ws, int kb) { retur
 void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only);
 // X (rows x 64 at A, lda) <- X * Linv^T with Linv a column-major 64x64 lower-triangular inverse (right-side triangular solve of one block column)
 void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block);
-int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev);
+// Optional scheduling hint for block-sparse systems ordered by nested dissection (solve_order.h): the block columns (64 wide) of
+// part p are [k0[p], k1[p]); no non-zero tile couples two different parts; [ksep, nblk) is the separator block, ordered last.
+// The parts are then factored / substituted by one thread-block cluster each, concurrently, the separator afterwards.
+struct CholPartition { static constexpr int kMaxParts = 32; int nparts; int ksep; int k0[kMaxParts]; int k1[kMaxParts]; };
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part = nullptr);
 int dense_cholesky_stats(cudaStream_t st, int n, const double* ws, int64_t* nblk, int64_t* nz_tiles, double* factor_flops);
-int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
-int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b);
+int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part = nullptr);
+int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part = nullptr);
 // mirror the lower triangle into the upper one
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld);
 // multi-GPU exchange of the non-zero 64x64 tiles of S only (aux_kernels.cu)

@@ -1,0 +1,249 @@
+// suriko-b200 — nested-dissection order of the reduced camera system (host) and the kernels that move a system into it.
+// See solve_order.h.  The reference solves the system in capture order with a dense Householder QR (BA.cpp:1911); any
+// symmetric permutation gives the same solution up to rounding, and the engine refines the solution against the natural-order
+// system afterwards (k_residual_dd), so the order is purely a scheduling decision.
+#include "solve_order.h"
+#include <algorithm>
+#include <numeric>
+#include <queue>
+
+namespace srk {
+
+namespace {
+
+constexpr int kTile = 64;
+constexpr int kMaxConcurrentParts = 16;     // clusters of 8 CTAs that are co-resident on 148 SMs
+
+struct Graph {
+    int G;
+    std::vector<std::vector<int>> nb;
+};
+
+// BFS levels over ALL components (later components continue the level numbering); returns the number of levels
+int bfs_levels(const Graph& g, int root, std::vector<int>& level) {
+    level.assign(g.G, -1);
+    int maxl = -1;
+    auto run = [&](int r, int base) {
+        std::queue<int> q;
+        level[r] = base; q.push(r);
+        while (!q.empty()) {
+            const int u = q.front(); q.pop();
+            maxl = std::max(maxl, level[u]);
+            for (int v : g.nb[u]) if (level[v] < 0) { level[v] = level[u] + 1; q.push(v); }
+        }
+    };
+    run(root, 0);
+    for (int u = 0; u < g.G; ++u) if (level[u] < 0) run(u, maxl + 1);
+    return maxl + 1;
+}
+
+// chain length of the separator block when it is factored as a dense block of s tiles by one cluster: one step per block column,
+// plus the tile-pair updates that do not hide behind the look-ahead potrf (4 rounds of 7 pairs do)
+double dense_chain_cost(int s) {
+    double c = 0.0;
+    for (int j = 0; j < s; ++j) {
+        const int m = s - j - 1;
+        const int rounds = (m * (m + 1) / 2 + 6) / 7;
+        c += 1.0 + 0.16 * std::max(0, rounds - 4);
+    }
+    return c;
+}
+
+struct Candidate {
+    double cost = 1e300;
+    std::vector<char> is_sep_level;
+    std::vector<int> comp;                  // component id per group (-1 = separator)
+    std::vector<int> bin_of_comp;
+    int nbins = 0, sep_tiles = 0, max_bin_tiles = 0, nsep_levels = 0;
+};
+
+Candidate evaluate(const Graph& g, const int* gsize, const std::vector<int>& level, int nlevels, const std::vector<char>& sep_level) {
+    Candidate c;
+    c.is_sep_level = sep_level;
+    c.comp.assign(g.G, -1);
+    int ncomp = 0;
+    std::vector<int> comp_vars;
+    int sep_vars = 0;
+    for (int u = 0; u < g.G; ++u) {
+        if (sep_level[level[u]]) { sep_vars += gsize[u]; continue; }
+        if (c.comp[u] >= 0) continue;
+        std::queue<int> q;
+        c.comp[u] = ncomp; q.push(u);
+        int vars = 0;
+        while (!q.empty()) {
+            const int a = q.front(); q.pop();
+            vars += gsize[a];
+            for (int b : g.nb[a]) if (!sep_level[level[b]] && c.comp[b] < 0) { c.comp[b] = ncomp; q.push(b); }
+        }
+        comp_vars.push_back(vars);
+        ++ncomp;
+    }
+    for (char s : sep_level) c.nsep_levels += s ? 1 : 0;
+    if (ncomp < 2) return c;
+    // longest-processing-time packing of the components into at most kMaxConcurrentParts bins
+    const int nbins = std::min(ncomp, kMaxConcurrentParts);
+    std::vector<int> order(ncomp);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return comp_vars[a] != comp_vars[b] ? comp_vars[a] > comp_vars[b] : a < b; });
+    std::vector<int> bin_vars(nbins, 0);
+    c.bin_of_comp.assign(ncomp, 0);
+    for (int ci : order) {
+        int best = 0;
+        for (int b = 1; b < nbins; ++b) if (bin_vars[b] < bin_vars[best]) best = b;
+        c.bin_of_comp[ci] = best;
+        bin_vars[best] += comp_vars[ci];
+    }
+    c.nbins = nbins;
+    int maxb = 0;
+    for (int b = 0; b < nbins; ++b) maxb = std::max(maxb, (bin_vars[b] + kTile - 1) / kTile);
+    c.max_bin_tiles = maxb;
+    c.sep_tiles = (sep_vars + kTile - 1) / kTile;
+    c.cost = (double)maxb + dense_chain_cost(c.sep_tiles);
+    (void)nlevels;
+    return c;
+}
+
+}  // namespace
+
+SolveOrder build_solve_order(int G, const int* gsize, const unsigned char* adj) {
+    SolveOrder o;
+    int n = 0;
+    for (int g = 0; g < G; ++g) n += gsize[g];
+    o.n = n;
+    const int nblk0 = (n + kTile - 1) / kTile;
+    if (G < 8 || nblk0 < 24) return o;
+    Graph g; g.G = G; g.nb.resize(G);
+    for (int a = 0; a < G; ++a)
+        for (int b = 0; b < G; ++b)
+            if (a != b && (adj[(size_t)a * G + b] != 0 || adj[(size_t)b * G + a] != 0)) g.nb[a].push_back(b);
+    // pseudo-peripheral root: the farthest, lowest-degree group of a few successive BFS runs
+    std::vector<int> level;
+    int root = 0, nlevels = 0;
+    for (int it = 0; it < 3; ++it) {
+        nlevels = bfs_levels(g, root, level);
+        int far = root;
+        for (int u = 0; u < G; ++u) {
+            if (level[u] > level[far] || (level[u] == level[far] && g.nb[u].size() < g.nb[far].size())) far = u;
+        }
+        if (it < 2) root = far;
+    }
+    nlevels = bfs_levels(g, root, level);
+    o.levels = nlevels;
+    if (nlevels < 5) return o;
+    std::vector<int64_t> cum(nlevels + 1, 0);
+    {
+        std::vector<int> w(nlevels, 0);
+        for (int u = 0; u < G; ++u) w[level[u]] += gsize[u];
+        for (int l = 0; l < nlevels; ++l) cum[l + 1] = cum[l] + w[l];
+    }
+    // candidates: q whole levels as separators, spaced evenly in unknowns (scheme 0) or with half-width end gaps (scheme 1: on a ring
+    // the end gaps are one component each, the inner gaps split into two)
+    Candidate best;
+    const int qmax = std::min(24, (nlevels - 1) / 2);
+    for (int q = 1; q <= qmax; ++q) {
+        for (int scheme = 0; scheme < 2; ++scheme) {
+            std::vector<char> sep(nlevels, 0);
+            int placed = 0;
+            for (int i = 1; i <= q; ++i) {
+                const double frac = scheme == 0 ? (double)i / (q + 1) : ((double)i - 0.5) / q;
+                const int64_t target = (int64_t)(frac * (double)n);
+                int l = (int)(std::upper_bound(cum.begin(), cum.end(), target) - cum.begin()) - 1;
+                l = std::max(1, std::min(nlevels - 2, l));
+                while (l < nlevels - 2 && sep[l]) ++l;
+                if (!sep[l]) { sep[l] = 1; ++placed; }
+            }
+            if (placed == 0) continue;
+            Candidate c = evaluate(g, gsize, level, nlevels, sep);
+            if (c.cost < best.cost) best = std::move(c);
+        }
+    }
+    if (!(best.cost < 0.75 * (double)nblk0) || best.nbins < 2) return o;
+
+    // positions: bins in order, inside a bin components in id order, inside a component groups by (level, index); separator last
+    std::vector<int> gstart(G + 1, 0);
+    for (int u = 0; u < G; ++u) gstart[u + 1] = gstart[u] + gsize[u];
+    o.pos.assign(n, -1);
+    int cursor = 0;
+    auto place = [&](int u) { for (int a = 0; a < gsize[u]; ++a) o.pos[gstart[u] + a] = cursor++; };
+    std::vector<int> by_level(G);
+    std::iota(by_level.begin(), by_level.end(), 0);
+    std::stable_sort(by_level.begin(), by_level.end(), [&](int a, int b) { return level[a] < level[b]; });
+    const int ncomp = (int)best.bin_of_comp.size();
+    o.part.nparts = 0;
+    for (int b = 0; b < best.nbins; ++b) {
+        const int k0 = cursor / kTile;
+        for (int ci = 0; ci < ncomp; ++ci) {
+            if (best.bin_of_comp[ci] != b) continue;
+            for (int u : by_level) if (best.comp[u] == ci) place(u);
+        }
+        cursor = (cursor + kTile - 1) / kTile * kTile;
+        const int k1 = cursor / kTile;
+        if (k1 > k0) { o.part.k0[o.part.nparts] = k0; o.part.k1[o.part.nparts] = k1; ++o.part.nparts; o.max_part_blocks = std::max(o.max_part_blocks, k1 - k0); }
+    }
+    o.part.ksep = cursor / kTile;
+    for (int u : by_level) if (best.comp[u] < 0) place(u);
+    o.np = cursor;
+    o.src.assign(o.np, -1);
+    for (int i = 0; i < n; ++i) o.src[o.pos[i]] = i;
+    o.sep_levels = best.nsep_levels;
+    o.sep_blocks = (o.np + kTile - 1) / kTile - o.part.ksep;
+    o.active = o.part.nparts >= 2;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_permute_sym(int n, const double* __restrict__ S, int64_t ld, int mirrored, int np, const int* __restrict__ src,
+                                                     double* __restrict__ L, int64_t ldp) {
+    const int jd = blockIdx.x;
+    const int js = src[jd];
+    double* out = L + (size_t)jd * ldp;
+    if (js < 0) {
+        for (int id = jd + threadIdx.x; id < np; id += 256) out[id] = id == jd ? 1.0 : 0.0;
+        return;
+    }
+    const double* col = S + (size_t)js * ld;
+    for (int id = jd + threadIdx.x; id < np; id += 256) {
+        const int is = src[id];
+        double v = 0.0;
+        if (is >= 0) v = (mirrored || is >= js) ? col[is] : S[(size_t)is * ld + js];
+        out[id] = v;
+    }
+}
+__global__ void k_gather_vec(int np, const int* __restrict__ src, const double* __restrict__ in, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) { const int s = src[i]; out[i] = s >= 0 ? in[s] : 0.0; }
+}
+__global__ void k_scatter_vec(int np, const int* __restrict__ src, const double* __restrict__ in, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) { const int s = src[i]; if (s >= 0) out[s] = in[i]; }
+}
+// one thread per point: every pair of its cameras is marked (both orders); the test before the store keeps the write traffic
+// to the first few points of a pair
+__global__ void k_cam_adjacency(int64_t N, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam, int M, double* adj) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const int64_t b = pt_begin[j], e = pt_begin[j + 1];
+    for (int64_t a = b; a < e; ++a) {
+        const int ca = obs_cam[a];
+        for (int64_t c = b; c < a; ++c) {
+            const int cc = obs_cam[c];
+            double* p = adj + (size_t)ca * M + cc;
+            if (*p == 0.0) { *p = 1.0; adj[(size_t)cc * M + ca] = 1.0; }
+        }
+    }
+}
+
+void launch_permute_sym(cudaStream_t st, int n, const double* S, int64_t ld, int mirrored, int np, const int* src_dev, double* L, int64_t ldp) {
+    if (np > 0) k_permute_sym<<<np, 256, 0, st>>>(n, S, ld, mirrored, np, src_dev, L, ldp);
+}
+void launch_gather_vec(cudaStream_t st, int np, const int* src_dev, const double* in, double* out) {
+    if (np > 0) k_gather_vec<<<(np + 255) / 256, 256, 0, st>>>(np, src_dev, in, out);
+}
+void launch_scatter_vec(cudaStream_t st, int np, const int* src_dev, const double* in, double* out) {
+    if (np > 0) k_scatter_vec<<<(np + 255) / 256, 256, 0, st>>>(np, src_dev, in, out);
+}
+void launch_cam_adjacency(cudaStream_t st, int64_t N, const int64_t* pt_begin, const int32_t* obs_cam, int M, double* adj) {
+    if (N > 0) k_cam_adjacency<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, pt_begin, obs_cam, M, adj);
+}
+
+}  // namespace srk

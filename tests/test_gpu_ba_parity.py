@@ -4,6 +4,8 @@ Tolerances (FP64): per-observation / per-block quantities 1e-11 relative to the 
 mask, accept/reject flags and stop reasons exact; accepted per-iteration errors 1e-9 relative (north_star); final RMS
 reprojection error 1e-6 px.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -212,6 +214,50 @@ def test_lm_trajectory_sparse_scenes(oracle, engine, name):
     pr = as_oracle_problem(oracle, prob)
     ref, rep, out = run_pair(oracle, engine, pr, 1e-10, 5)
     check_trajectory(ref, rep, pr, out, pr.f0)
+
+
+def test_ordered_partitioned_solve_matches_oracle(oracle, engine):
+    """170 cameras on a ring: large enough (n_f = 1693, 27 block columns) for the nested-dissection order of csrc/solve_order.cu --
+    parts factored concurrently, separator last.  The corrections must still be the reference's (BA.cpp:1911 solves in capture order;
+    a symmetric permutation does not change the solution): compared with the exact oracle through the error after the step, and
+    with the same engine forced to capture order (SRK_SOLVE_ORDER=0)."""
+    import surikatoko_b200 as sb
+    from surikatoko_b200 import scenes
+    prob = scenes.ring_scene(170, 4000, 6, seed=9)
+    pr = as_oracle_problem(oracle, prob)
+    c = 1e-4
+    ref = oracle.derivs_and_solve(normalized_problem(oracle, pr), c=c, flow="sparse", solve="chol", acc="ld")
+    assert engine.bind(to_problem(pr))
+    got = engine.debug_derivs_and_solve(c=c)
+    st = engine.solve_stats()
+    assert st["parts"] >= 2 and st["ordered_n"] >= st["n_f"] and st["separator_blocks"] >= 1
+    assert np.array_equal(got["skipped"], ref["skipped"])
+    assert np.array_equal(got["S"] != 0, ref["S"] != 0)
+    assert relerr(got["S"], ref["S"]) < 1e-11
+    q = normalized_problem(oracle, pr)
+    _, p2, c2 = (None,) + oracle.apply_corrections(q.points, q.cams, ref["corrections"])
+    q.points = p2; q.cams = c2
+    e_ref, _ = oracle.reproj_error(q)
+    e_gpu = engine.debug_apply(got["corrections"])
+    assert abs(e_gpu - e_ref) <= 1e-7 * abs(e_ref)
+    os.environ["SRK_SOLVE_ORDER"] = "0"
+    try:
+        eng_nat = sb.Engine(0)
+    finally:
+        del os.environ["SRK_SOLVE_ORDER"]
+    try:
+        assert eng_nat.bind(to_problem(pr))
+        nat = eng_nat.debug_derivs_and_solve(c=c)
+        assert eng_nat.solve_stats()["parts"] == 0
+        e_nat = eng_nat.debug_apply(nat["corrections"])
+        assert abs(e_gpu - e_nat) <= 1e-9 * abs(e_nat)
+        # whole LM trajectories, ordered vs capture order: same decisions, same residual norms
+        opt = sb.BAOptions(err_change=1e-10, max_outer_iters=4)
+        r1 = engine.solve(to_problem(pr), opt); r0 = eng_nat.solve(to_problem(pr), opt)
+        assert np.array_equal(r1.attempts[:, 2], r0.attempts[:, 2]) and r1.stop_reason == r0.stop_reason
+        assert np.all(np.abs(np.sqrt(r1.err_trace) - np.sqrt(r0.err_trace)) <= 1e-9 * np.sqrt(r0.err_trace))
+    finally:
+        eng_nat.close()
 
 
 def test_skipped_points_mask_is_reproduced(oracle, engine):

@@ -60,12 +60,29 @@ def test_full_size_lm_step_properties(c3_scene, engine):
     assert abs(rep1.err_initial - e_np) <= 1e-10 * e_np
     assert rep1.err_final < rep1.err_initial and rep1.outer_iters == 1
     st = engine.solve_stats()
-    assert st["n_f"] == 10 * M - 7 and st["block_rows"] == (10 * M - 7 + 63) // 64
+    # nested-dissection order (csrc/solve_order.cu): the ring splits into independent arcs + a separator, every part padded to a 64-column boundary
+    assert st["n_f"] == 10 * M - 7 and st["block_rows"] == (st["ordered_n"] + 63) // 64 and st["ordered_n"] >= st["n_f"]
+    assert st["parts"] >= 4 and st["max_part_blocks"] + st["separator_blocks"] < st["block_rows"] // 3
     # 10 ring-nearest cameras per point: block band of 2-3 tiles per block column + the wrap-around rows, far from dense
     assert st["block_rows"] < st["nonzero_tiles"] < 8 * st["block_rows"]
     engine.reset()
     rep2 = engine.run(opt)
     assert abs(rep2.err_final - rep1.err_final) <= 1e-12 * rep1.err_final      # atomics reorder sums: not bit-exact, but far below 1e-9
+
+    # capture-order factorisation (one chain of 157 block columns) as a cross-check of the ordered, partitioned one
+    os.environ["SRK_SOLVE_ORDER"] = "0"
+    try:
+        eng_nat = sb.Engine(0)
+    finally:
+        del os.environ["SRK_SOLVE_ORDER"]
+    try:
+        assert eng_nat.bind(prob, opt)
+        rep_nat = eng_nat.run(opt)
+        st_nat = eng_nat.solve_stats()
+        assert st_nat["parts"] == 0 and st_nat["block_rows"] == (10 * M - 7 + 63) // 64
+        assert abs(rep_nat.err_final - rep1.err_final) <= 1e-11 * rep1.err_final, (rep_nat.err_final, rep1.err_final)
+    finally:
+        eng_nat.close()
 
     # second, independent implementation of K2
     os.environ["SRK_SCHUR_IMPL"] = "1"

@@ -5,10 +5,12 @@
 #include <vector>
 #include <cmath>
 #include "kernels.h"
+#include "solve_order.h"
 using namespace srk;
 int main(int argc, char** argv) {
     int n = argc > 1 ? atoi(argv[1]) : 9993;
     int band = argc > 2 ? atoi(argv[2]) : 100;   // half bandwidth; 0 = dense
+    int nd = argc > 3 ? atoi(argv[3]) : 0;       // 1: nested-dissection order + partitioned factorisation (solve_order.h)
     int64_t ld = (n + 7) & ~7;
     std::vector<double> h((size_t)ld * n, 0.0);
     srand(1);
@@ -44,6 +46,44 @@ int main(int argc, char** argv) {
                (long long)nl, (double)n * n * n / 3.0 / (f * 1e-3) / 1e12, a, c, hinfo, cudaGetErrorString(cudaGetLastError()));
         if (it == 3) { dense_cholesky_profile_report(); dense_cholesky_band_profile_report(); }
         else if (it == 2) { cudaDeviceSynchronize(); long long z[16] = {0}; (void)z; }
+    }
+    if (nd) {
+        // groups of 10 unknowns (the first two 4 and 9, as in the gauge-reduced camera system), coupling read off the matrix
+        std::vector<int> gsize; { int left = n; gsize.push_back(4); gsize.push_back(9); left -= 13; while (left > 0) { gsize.push_back(left < 10 ? left : 10); left -= 10; } }
+        const int G = (int)gsize.size();
+        std::vector<int> gof(n); { int i = 0; for (int g = 0; g < G; ++g) for (int a = 0; a < gsize[g]; ++a) gof[i++] = g; }
+        std::vector<unsigned char> adj((size_t)G * G, 0);
+        for (int c = 0; c < n; ++c) for (int r = c; r < n; ++r) if (h[(size_t)c * ld + r] != 0.0) { adj[(size_t)gof[r] * G + gof[c]] = 1; adj[(size_t)gof[c] * G + gof[r]] = 1; }
+        SolveOrder o = build_solve_order(G, gsize.data(), adj.data());
+        printf("order: active=%d n=%d np=%d levels=%d sep_levels=%d parts=%d max_part_blocks=%d ksep=%d sep_blocks=%d\n", (int)o.active, o.n, o.np, o.levels, o.sep_levels,
+               o.part.nparts, o.max_part_blocks, o.part.ksep, o.sep_blocks);
+        if (o.active) {
+            const int np = o.np; const int64_t ldp = (np + 7) & ~7;
+            double *Lp, *wsp, *bp, *xb; int* srcd;
+            cudaMalloc(&Lp, sizeof(double) * ldp * np); cudaMalloc(&wsp, sizeof(double) * dense_cholesky_dinv_doubles(np)); cudaMalloc(&bp, sizeof(double) * ldp);
+            cudaMalloc(&xb, sizeof(double) * ld); cudaMalloc(&srcd, sizeof(int) * np);
+            cudaMemcpy(srcd, o.src.data(), sizeof(int) * np, cudaMemcpyHostToDevice);
+            cudaEvent_t ep; cudaEventCreate(&ep);
+            for (int it = 0; it < 4; ++it) {
+                cudaMemcpyAsync(b, hb.data(), sizeof(double) * ld, cudaMemcpyHostToDevice, st);
+                cudaEventRecord(ep, st);
+                launch_permute_sym(st, n, A, ld, 0, np, srcd, Lp, ldp);
+                launch_gather_vec(st, np, srcd, b, bp);
+                cudaEventRecord(e0, st);
+                int64_t nl = dense_cholesky_factor(st, np, Lp, ldp, wsp, info, &o.part);
+                cudaEventRecord(e1, st);
+                dense_cholesky_forward(st, np, Lp, ldp, wsp, bp, &o.part);
+                cudaEventRecord(e2, st);
+                dense_cholesky_backward(st, np, Lp, ldp, wsp, bp, &o.part);
+                cudaEventRecord(e3, st);
+                launch_scatter_vec(st, np, srcd, bp, b);
+                cudaStreamSynchronize(st);
+                float pm, f, a, c; cudaEventElapsedTime(&pm, ep, e0); cudaEventElapsedTime(&f, e0, e1); cudaEventElapsedTime(&a, e1, e2); cudaEventElapsedTime(&c, e2, e3);
+                int hinfo; cudaMemcpy(&hinfo, info, 4, cudaMemcpyDeviceToHost);
+                printf("ND n=%d np=%d iter %d: permute %.3f ms factor %.3f ms (%lld launches) fwd %.3f ms bwd %.3f ms info=%d err=%s\n", n, np, it, pm, f, (long long)nl, a, c, hinfo,
+                       cudaGetErrorString(cudaGetLastError()));
+            }
+        }
     }
     // residual check: A x = 1
     std::vector<double> x(ld); cudaMemcpy(x.data(), b, sizeof(double) * ld, cudaMemcpyDeviceToHost);
