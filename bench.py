@@ -209,9 +209,14 @@ def run_ours(args):
         timing = eng.get_timing()
         eng.set_timing(False)
         # ---------------- end to end through srk_ba_solve with host buffers
+        # every step is one srk_ba_solve call on its own pinned host copy of the scene state (the call refines points and poses in
+        # place, so a step cannot reuse the previous step's buffers; preparing the copies is not part of a step)
         e2e_steps = max(1, min(args.steps, 5))
+        fresh = []
         for i in range(1 + e2e_steps):
-            prob.points[:] = pts0; prob.cams[:] = cams0
+            tp, vp = pin(pts0); tc, vc = pin(cams0); keep += [tp, tc]; fresh.append((vp, vc))
+        for i in range(1 + e2e_steps):
+            prob.points, prob.cams = fresh[i]
             if i == 1:
                 barrier(); t0 = time.perf_counter(); g0 = torch.cuda.Event(enable_timing=True); g0.record(stream)
             rep_e = eng.solve(prob, opt1)

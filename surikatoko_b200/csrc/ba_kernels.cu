@@ -112,10 +112,27 @@ __global__ void __launch_bounds__(128) k_frame_blocks(int M, const int64_t* __re
     double acc[65];
 #pragma unroll
     for (int i = 0; i < 65; ++i) acc[i] = 0.0;
-    for (int64_t o = sb + threadIdx.x; o < se; o += blockDim.x) {
-        int pt = c_pt[o];
+    // Two-deep software pipeline: the gather X[pt] of observation i+1 and the index / pixel loads of observation i+2 are in flight
+    // while observation i is evaluated (one CTA keeps 4 warps per camera slice: without it every iteration waits for two dependent
+    // L2 round trips -- ncu: long-scoreboard 4.2 stalls per issue).
+    const int stride = blockDim.x;
+    int64_t o = sb + threadIdx.x;
+    bool v1 = o < se;
+    int pt1 = 0; double x1 = 0.0, y1 = 0.0;
+    if (v1) { pt1 = c_pt[o]; x1 = c_x[o]; y1 = c_y[o]; }
+    bool vc = v1;
+    double X0 = 0.0, X1 = 0.0, X2 = 0.0, xc = x1, yc = y1;
+    if (vc) { X0 = X[pt1]; X1 = X[N + pt1]; X2 = X[2 * N + pt1]; }
+    o += stride; v1 = o < se;
+    if (v1) { pt1 = c_pt[o]; x1 = c_x[o]; y1 = c_y[o]; }
+    while (vc) {
+        double nX0 = 0.0, nX1 = 0.0, nX2 = 0.0;
+        const bool nv = v1; const double nx = x1, ny = y1;
+        if (nv) { nX0 = X[pt1]; nX1 = X[N + pt1]; nX2 = X[2 * N + pt1]; }
+        o += stride; v1 = o < se;
+        if (v1) { pt1 = c_pt[o]; x1 = c_x[o]; y1 = c_y[o]; }
         double rx, ry, jp[6], jc[20];
-        obs_jacobian(cd, X[pt], X[N + pt], X[2 * N + pt], c_x[o], c_y[o], rx, ry, jp, jc);
+        obs_jacobian(cd, X0, X1, X2, xc, yc, rx, ry, jp, jc);
         int idx = 0;
 #pragma unroll
         for (int a = 0; a < 10; ++a)
@@ -123,6 +140,7 @@ __global__ void __launch_bounds__(128) k_frame_blocks(int M, const int64_t* __re
             for (int bb = a; bb < 10; ++bb) { acc[idx] += jc[a * 2] * jc[bb * 2] + jc[a * 2 + 1] * jc[bb * 2 + 1]; ++idx; }
 #pragma unroll
         for (int a = 0; a < 10; ++a) acc[55 + a] += jc[a * 2] * rx + jc[a * 2 + 1] * ry;
+        X0 = nX0; X1 = nX1; X2 = nX2; xc = nx; yc = ny; vc = nv;
     }
     __shared__ double red[4][65];
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -117,6 +117,9 @@ struct Engine {
     bool order_ready = false;
     int solve_order_enabled = 1; // SRK_SOLVE_ORDER=0: always factor in capture order (cross-check)
     Buf adjbuf, order_src, xperm;
+    std::vector<unsigned char> order_adj;   // the graph `order` was built from
+    unsigned char* h_adj = nullptr;         // pinned
+    size_t h_adj_cap = 0;
     int tile_exchange = 1;       // SRK_TILE_EXCHANGE=0: always all-reduce the whole dense system
     int64_t n_deferred = 0;   // points the tiled Schur kernel leaves to the per-point kernel (structure only, known at bind time)
     int schur_tile_points = 256;
@@ -392,8 +395,10 @@ int derivative_pass(Engine& e) {
     {
         Scope s(e, F_FRAME);
         // split a camera's observation list over several CTAs when there are few cameras (grid >= 2 waves of 148 SMs)
+        // (two slices add commutatively, so up to 2 the blocks stay bit-reproducible; more only for few cameras)
         int splits = 1;
-        if (e.M < 296) { splits = (296 + e.M - 1) / e.M; int64_t per = e.M > 0 ? e.O / e.M : 0; while (splits > 1 && per / splits < 256) --splits; }
+        { const int want = e.M < 296 ? 296 : 1184; splits = (want + e.M - 1) / e.M; int64_t per = e.M > 0 ? e.O / e.M : 0;
+          const int64_t min_per = e.M < 296 ? 256 : 2048; while (splits > 1 && per / splits < min_per) --splits; }
         srk::launch_frame_blocks(st, e.M, e.cam_begin.as<int64_t>(), e.c_pt.as<int32_t>(), e.c_x.as<double>(), e.c_y.as<double>(), e.X_cur, e.N, e.camd_cur,
                                  e.Ggf.as<double>(), e.Ggf.as<double>() + 100 * (size_t)e.M, splits);
         e.launches += 1;
@@ -405,27 +410,37 @@ int derivative_pass(Engine& e) {
 // ranks, so that every rank factors in the same order and takes bit-identical decisions) -> host nested dissection (solve_order.cu).
 int ensure_solve_order(Engine& e) {
     if (e.order_ready) return SRK_OK;
-    e.order = srk::SolveOrder{};
     e.order_ready = true;
     const int M = e.M;
-    if (!e.solve_order_enabled || e.nf < 24 * 64 || M < 8) return SRK_OK;
+    if (!e.solve_order_enabled || e.nf < 24 * 64 || M < 8) { e.order = srk::SolveOrder{}; return SRK_OK; }
     cudaStream_t st = e.stream;
     const size_t cells = (size_t)M * (size_t)M;
-    SRK_CUDA(e.adjbuf.ensure(sizeof(double) * cells));
-    SRK_CUDA(cudaMemsetAsync(e.adjbuf.p, 0, sizeof(double) * cells, st));
-    srk::launch_cam_adjacency(st, e.N, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), M, e.adjbuf.as<double>()); e.launches += e.N > 0 ? 1 : 0;
-    int rc = do_allreduce(e, e.adjbuf.as<double>(), (int64_t)cells);
-    if (rc != SRK_OK) return rc;
-    std::vector<double> h(cells);
-    SRK_CUDA(cudaMemcpyAsync(h.data(), e.adjbuf.p, sizeof(double) * cells, cudaMemcpyDeviceToHost, st));
+    SRK_CUDA(e.adjbuf.ensure(cells));
+    SRK_CUDA(cudaMemsetAsync(e.adjbuf.p, 0, cells, st));
+    srk::launch_cam_adjacency(st, e.N, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), M, e.adjbuf.as<unsigned char>()); e.launches += e.N > 0 ? 1 : 0;
+    if (e.ar != nullptr && e.world > 1) {
+        SRK_CUDA(e.tmask.ensure(sizeof(double) * cells));
+        srk::launch_bytes_to_doubles(st, (int64_t)cells, e.adjbuf.as<unsigned char>(), e.tmask.as<double>()); e.launches += 1;
+        int rc = do_allreduce(e, e.tmask.as<double>(), (int64_t)cells);
+        if (rc != SRK_OK) return rc;
+        srk::launch_doubles_to_bytes(st, (int64_t)cells, e.tmask.as<double>(), e.adjbuf.as<unsigned char>()); e.launches += 1;
+    }
+    if (e.h_adj_cap < cells) {
+        if (e.h_adj != nullptr) cudaFreeHost(e.h_adj);
+        e.h_adj = nullptr; e.h_adj_cap = 0;
+        SRK_CUDA(cudaMallocHost((void**)&e.h_adj, cells));
+        e.h_adj_cap = cells;
+    }
+    SRK_CUDA(cudaMemcpyAsync(e.h_adj, e.adjbuf.p, cells, cudaMemcpyDeviceToHost, st));
     SRK_CUDA(cudaStreamSynchronize(st));
-    std::vector<unsigned char> adj(cells);
-    for (size_t i = 0; i < cells; ++i) adj[i] = h[i] != 0.0;
+    // the co-visibility graph of a re-bound scene is usually the one already ordered: keep the order (and its device copy) then
+    if (e.order_adj.size() == cells && e.order.n == e.nf && std::memcmp(e.order_adj.data(), e.h_adj, cells) == 0) return SRK_OK;
+    e.order_adj.assign(e.h_adj, e.h_adj + cells);
     std::vector<int> gsize(M, 10);
     gsize[0] = 4; gsize[1] = 9;                          // quirk Q13: frame 0 keeps its intrinsics, frame 1 loses T[unity]
-    e.order = srk::build_solve_order(M, gsize.data(), adj.data());
+    e.order = srk::build_solve_order(M, gsize.data(), e.order_adj.data());
     if (!e.order.active) return SRK_OK;
-    if (e.order.n != e.nf) { e.order = srk::SolveOrder{}; return SRK_OK; }
+    if (e.order.n != e.nf) { e.order = srk::SolveOrder{}; e.order_adj.clear(); return SRK_OK; }
     const int np = e.order.np; const size_t ldp = ((size_t)np + 7) & ~(size_t)7;
     SRK_CUDA(e.order_src.ensure(sizeof(int) * (size_t)np));
     SRK_CUDA(cudaMemcpyAsync(e.order_src.p, e.order.src.data(), sizeof(int) * (size_t)np, cudaMemcpyHostToDevice, st));
@@ -788,6 +803,7 @@ void srk_ba_destroy(void* h) {
     for (Buf* b : bufs) b->release();
     srk::pcg_release(e->pcg);
     if (e->h_slots != nullptr) cudaFreeHost(e->h_slots);
+    if (e->h_adj != nullptr) cudaFreeHost(e->h_adj);
     for (int f = 0; f < F_COUNT; ++f) {
         for (cudaEvent_t ev : e->timers[f].pending) cudaEventDestroy(ev);
         for (cudaEvent_t ev : e->timers[f].pool) cudaEventDestroy(ev);

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <numeric>
 #include <queue>
+#include <cstring>
 
 namespace srk {
 
@@ -113,9 +114,19 @@ SolveOrder build_solve_order(int G, const int* gsize, const unsigned char* adj) 
     const int nblk0 = (n + kTile - 1) / kTile;
     if (G < 8 || nblk0 < 24) return o;
     Graph g; g.G = G; g.nb.resize(G);
-    for (int a = 0; a < G; ++a)
-        for (int b = 0; b < G; ++b)
-            if (a != b && (adj[(size_t)a * G + b] != 0 || adj[(size_t)b * G + a] != 0)) g.nb[a].push_back(b);
+    for (int a = 0; a < G; ++a) {          // rows are mostly zero: test eight cells at a time
+        const unsigned char* row = adj + (size_t)a * G;
+        int b = 0;
+        for (; b + 8 <= G; b += 8) {
+            uint64_t w; memcpy(&w, row + b, 8);
+            if (w == 0) continue;
+            for (int t = b; t < b + 8; ++t) if (row[t] != 0 && t != a) { g.nb[a].push_back(t); }
+        }
+        for (; b < G; ++b) if (row[b] != 0 && b != a) g.nb[a].push_back(b);
+    }
+    for (int a = 0; a < G; ++a)            // symmetrise (the device kernel marks both orders; a caller's matrix may hold one triangle)
+        for (int b : g.nb[a]) if (adj[(size_t)b * G + a] == 0) g.nb[b].push_back(a);
+    for (int a = 0; a < G; ++a) { std::sort(g.nb[a].begin(), g.nb[a].end()); g.nb[a].erase(std::unique(g.nb[a].begin(), g.nb[a].end()), g.nb[a].end()); }
     // pseudo-peripheral root: the farthest, lowest-degree group of a few successive BFS runs
     std::vector<int> level;
     int root = 0, nlevels = 0;
@@ -219,7 +230,7 @@ __global__ void k_scatter_vec(int np, const int* __restrict__ src, const double*
 }
 // one thread per point: every pair of its cameras is marked (both orders); the test before the store keeps the write traffic
 // to the first few points of a pair
-__global__ void k_cam_adjacency(int64_t N, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam, int M, double* adj) {
+__global__ void k_cam_adjacency(int64_t N, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam, int M, unsigned char* adj) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     const int64_t b = pt_begin[j], e = pt_begin[j + 1];
@@ -227,8 +238,8 @@ __global__ void k_cam_adjacency(int64_t N, const int64_t* __restrict__ pt_begin,
         const int ca = obs_cam[a];
         for (int64_t c = b; c < a; ++c) {
             const int cc = obs_cam[c];
-            double* p = adj + (size_t)ca * M + cc;
-            if (*p == 0.0) { *p = 1.0; adj[(size_t)cc * M + ca] = 1.0; }
+            unsigned char* p = adj + (size_t)ca * M + cc;
+            if (*p == 0) { *p = 1; adj[(size_t)cc * M + ca] = 1; }
         }
     }
 }
@@ -242,8 +253,22 @@ void launch_gather_vec(cudaStream_t st, int np, const int* src_dev, const double
 void launch_scatter_vec(cudaStream_t st, int np, const int* src_dev, const double* in, double* out) {
     if (np > 0) k_scatter_vec<<<(np + 255) / 256, 256, 0, st>>>(np, src_dev, in, out);
 }
-void launch_cam_adjacency(cudaStream_t st, int64_t N, const int64_t* pt_begin, const int32_t* obs_cam, int M, double* adj) {
+__global__ void k_bytes_to_doubles(int64_t n, const unsigned char* __restrict__ in, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] != 0 ? 1.0 : 0.0;
+}
+__global__ void k_doubles_to_bytes(int64_t n, const double* __restrict__ in, unsigned char* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] != 0.0 ? 1 : 0;
+}
+void launch_cam_adjacency(cudaStream_t st, int64_t N, const int64_t* pt_begin, const int32_t* obs_cam, int M, unsigned char* adj) {
     if (N > 0) k_cam_adjacency<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, pt_begin, obs_cam, M, adj);
+}
+void launch_bytes_to_doubles(cudaStream_t st, int64_t n, const unsigned char* in, double* out) {
+    if (n > 0) k_bytes_to_doubles<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in, out);
+}
+void launch_doubles_to_bytes(cudaStream_t st, int64_t n, const double* in, unsigned char* out) {
+    if (n > 0) k_doubles_to_bytes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, in, out);
 }
 
 }  // namespace srk

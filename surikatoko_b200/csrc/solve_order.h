@@ -37,8 +37,10 @@ void launch_permute_sym(cudaStream_t st, int n, const double* S, int64_t ld, int
 void launch_gather_vec(cudaStream_t st, int np, const int* src_dev, const double* in, double* out);
 // out[src[i]] = in[i] for src[i] >= 0       (ordered -> natural vector)
 void launch_scatter_vec(cudaStream_t st, int np, const int* src_dev, const double* in, double* out);
-// adj[ci*M + cl] = adj[cl*M + ci] = 1 for every pair of cameras that observe a common point (doubles, so that the f64 sum all-reduce
-// of the multi-GPU path can carry the union over ranks)
-void launch_cam_adjacency(cudaStream_t st, int64_t N, const int64_t* pt_begin, const int32_t* obs_cam, int M, double* adj);
+// adj[ci*M + cl] = adj[cl*M + ci] = 1 for every pair of cameras that observe a common point
+void launch_cam_adjacency(cudaStream_t st, int64_t N, const int64_t* pt_begin, const int32_t* obs_cam, int M, unsigned char* adj);
+// the f64 sum all-reduce of the multi-GPU path carries the union over ranks: bytes -> doubles -> (all-reduce) -> bytes
+void launch_bytes_to_doubles(cudaStream_t st, int64_t n, const unsigned char* in, double* out);
+void launch_doubles_to_bytes(cudaStream_t st, int64_t n, const double* in, unsigned char* out);
 
 }  // namespace srk
