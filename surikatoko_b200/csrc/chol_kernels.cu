@@ -1379,7 +1379,8 @@ static FactorGraph g_fg;
 
 // Sparse-factor path: tile pattern of the input, then (when it is sparse enough) the single-cluster kernel.  Returns the number of
 // launches, or 0 when the matrix is not sparse and the launch-per-operation path has to run.
-static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part) {
+static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part, const unsigned char* pattern_dev,
+                               int pattern_count) {
     const int nblk = chol_nblk(n);
     if (nblk < 2 || nblk > kMaxRowBlocks) return 0;
     static int force = -1;    // SRK_CHOL_PATH=dense disables the sparse path, =band forces it (development aid)
@@ -1396,12 +1397,17 @@ static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, do
     cudaMemsetAsync(ws_flags(ws, n), 0, sizeof(int) * nblk, st);
     cudaMemsetAsync(F, 0, (size_t)nblk * nblk, st);
     cudaMemsetAsync(cnt, 0, sizeof(int) * 2, st);
-    k_tile_pattern<<<dim3(nblk, nblk), 256, 0, st>>>(n, A, ld, nblk, F, cnt);
     int h = -1;
-    if (cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int64_t nl = 2;
+    if (pattern_dev != nullptr) {   // the caller knows the tile structure (solve_order.h): no pass over the matrix, no host round trip
+        if (cudaMemcpyAsync(F, pattern_dev, (size_t)nblk * nblk, cudaMemcpyDeviceToDevice, st) != cudaSuccess) { cudaGetLastError(); return 0; }
+        h = pattern_count; nl = 1;
+    } else {
+        k_tile_pattern<<<dim3(nblk, nblk), 256, 0, st>>>(n, A, ld, nblk, F, cnt);
+        if (cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return 0; }
+    }
     const int max_fill = (part != nullptr && part->nparts > 0) ? 2 * kBandMaxFill : kBandMaxFill;   // a partitioned pattern carries the separator rows as well
     if (h < 0 || (force != 2 && h > max_fill * nblk)) return 0;
-    int64_t nl = 2;
     if (part != nullptr && part->nparts > 0) {
         k_band_chol<<<kBandCluster * part->nparts, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 0);
         k_band_chol<<<kBandCluster, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 1);
@@ -1416,7 +1422,18 @@ static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, do
     return nl;
 }
 
-int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part) {
+// true when a factorisation with this caller-provided pattern is certain to take the sparse-factor (cluster) path
+bool dense_cholesky_pattern_ok(int n, int pattern_count, bool partitioned) {
+    const int nblk = chol_nblk(n);
+    const char* e = getenv("SRK_CHOL_PATH");
+    if (e != nullptr && e[0] == 'd') return false;
+    const char* pe = getenv("SRK_CHOL_PROFILE");
+    if (pe != nullptr && pe[0] == '1') return false;
+    if (nblk < 2 || nblk > kMaxRowBlocks) return false;
+    return pattern_count <= (partitioned ? 2 * kBandMaxFill : kBandMaxFill) * nblk;
+}
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part, const unsigned char* pattern_dev,
+                              int pattern_count) {
     set_attrs_once();
     g_epoch = 0;
     static int prof_env = -1;
@@ -1427,7 +1444,7 @@ int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
         if (cs == cudaStreamCaptureStatusNone) {   // the pattern read-back synchronises: not inside somebody's capture
-            const int64_t nl = try_band_factor(st, n, A, ld, ws, info_dev, part);
+            const int64_t nl = try_band_factor(st, n, A, ld, ws, info_dev, part, pattern_dev, pattern_count);
             if (nl > 0) return nl;
         }
     }

@@ -116,7 +116,11 @@ struct Engine {
     srk::SolveOrder order;
     bool order_ready = false;
     int solve_order_enabled = 1; // SRK_SOLVE_ORDER=0: always factor in capture order (cross-check)
-    Buf adjbuf, order_src, xperm;
+    int solve_tiles_enabled = 1; // SRK_SOLVE_TILES=0: dense passes over S / L even when the tile structure is known (cross-check)
+    Buf adjbuf, order_src, xperm, order_ints, order_pattern;
+    bool order_tiles = false;    // the tile lists of `order` are on the device and the factorisation will take the cluster path
+    int ot_s = 0, ot_resptr = 0, ot_resent = 0, ot_lin = 0, ot_lall = 0;   // offsets into order_ints
+    bool S_clean = false;        // S is zero outside order.s_tiles (so the next attempt only clears those)
     std::vector<unsigned char> order_adj;   // the graph `order` was built from
     unsigned char* h_adj = nullptr;         // pinned
     size_t h_adj_cap = 0;
@@ -330,6 +334,7 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     SRK_CUDA(cudaGetLastError());
     e.bound = true;
     e.order_ready = false;
+    e.S_clean = false;
     return e.norm_failed ? 1 : SRK_OK;
 }
 
@@ -439,9 +444,22 @@ int ensure_solve_order(Engine& e) {
     std::vector<int> gsize(M, 10);
     gsize[0] = 4; gsize[1] = 9;                          // quirk Q13: frame 0 keeps its intrinsics, frame 1 loses T[unity]
     e.order = srk::build_solve_order(M, gsize.data(), e.order_adj.data());
+    e.order_tiles = false;
     if (!e.order.active) return SRK_OK;
     if (e.order.n != e.nf) { e.order = srk::SolveOrder{}; e.order_adj.clear(); return SRK_OK; }
     const int np = e.order.np; const size_t ldp = ((size_t)np + 7) & ~(size_t)7;
+    if (e.solve_tiles_enabled && srk::dense_cholesky_pattern_ok(np, e.order.l_pattern_count, true)) {
+        const srk::SolveOrder& o = e.order;
+        std::vector<int> ints;
+        auto put = [&](const std::vector<int>& v) { const int off = (int)ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return off; };
+        e.ot_s = put(o.s_tiles); e.ot_resptr = put(o.res_ptr); e.ot_resent = put(o.res_ent); e.ot_lin = put(o.l_in_tiles); e.ot_lall = put(o.l_all_tiles);
+        SRK_CUDA(e.order_ints.ensure(sizeof(int) * ints.size()));
+        SRK_CUDA(cudaMemcpyAsync(e.order_ints.p, ints.data(), sizeof(int) * ints.size(), cudaMemcpyHostToDevice, st));
+        SRK_CUDA(e.order_pattern.ensure(o.l_pattern.size()));
+        SRK_CUDA(cudaMemcpyAsync(e.order_pattern.p, o.l_pattern.data(), o.l_pattern.size(), cudaMemcpyHostToDevice, st));
+        SRK_CUDA(cudaStreamSynchronize(st));
+        e.order_tiles = true;
+    }
     SRK_CUDA(e.order_src.ensure(sizeof(int) * (size_t)np));
     SRK_CUDA(cudaMemcpyAsync(e.order_src.p, e.order.src.data(), sizeof(int) * (size_t)np, cudaMemcpyHostToDevice, st));
     SRK_CUDA(cudaStreamSynchronize(st));
@@ -510,14 +528,20 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
         double* S = e.Srhs.as<double>(); double* rhs = S + (size_t)ld * nf;
         {
             Scope s(e, F_SCHUR);
-            SRK_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * ((size_t)ld * nf + ld), st));
+            // the order (and with it the tile structure of S) is needed before S is cleared
+            { int rco = ensure_solve_order(e); if (rco != SRK_OK) return rco; }
+            if (e.order.active && e.order_tiles && e.S_clean) {
+                srk::launch_zero_tiles(st, nf, S, ld, e.order_ints.as<int>() + e.ot_s, (int)e.order.s_tiles.size()); e.launches += 1;
+                SRK_CUDA(cudaMemsetAsync(rhs, 0, sizeof(double) * (size_t)ld, st));
+            } else {
+                SRK_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * ((size_t)ld * nf + ld), st));
+                e.S_clean = e.order.active && e.order_tiles;
+            }
             if (e.rank == 0) { srk::launch_fill_reduced(st, M, G, gf, c, e.unity, S, ld, rhs); e.launches += 1; }
             srk::SchurSink sink{S, ld, rhs, e.unity, nullptr, nullptr, 0, nullptr};
             schur_accumulate(e, sink, c);
         }
         int rc = allreduce_system(e, S, rhs);
-        if (rc != SRK_OK) return rc;
-        rc = ensure_solve_order(e);
         if (rc != SRK_OK) return rc;
         {
             Scope s(e, F_SOLVE);
@@ -525,21 +549,32 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
             double* L = e.Lfac.as<double>();
             double* di = e.dinv.as<double>();
             double* r = e.resid.as<double>();
-            if (refine > 0) { srk::launch_mirror_lower(st, nf, S, ld); e.launches += 1; }
+            const bool tiles = e.order.active && e.order_tiles;
+            if (refine > 0 && !tiles) { srk::launch_mirror_lower(st, nf, S, ld); e.launches += 1; e.S_clean = false; }
             if (e.order.active) {
                 // factor P S P^T (parts concurrently, separator last); vectors travel natural -> ordered -> natural
                 const int np = e.order.np; const int64_t ldp = ((int64_t)np + 7) & ~(int64_t)7;
                 const int* src = e.order_src.as<int>(); double* xp = e.xperm.as<double>();
                 const srk::CholPartition* part = &e.order.part;
-                srk::launch_permute_sym(st, nf, S, ld, refine > 0 ? 1 : 0, np, src, L, ldp); e.launches += 1;
+                const int* oi = e.order_ints.as<int>();
+                if (tiles) {   // only the tiles that can be non-zero: the factor's (symbolic) tiles are cleared, the system's are copied
+                    srk::launch_zero_tiles(st, np, L, ldp, oi + e.ot_lall, (int)e.order.l_all_tiles.size());
+                    srk::launch_permute_tiles(st, nf, S, ld, np, src, L, ldp, oi + e.ot_lin, (int)e.order.l_in_tiles.size()); e.launches += 2;
+                } else {
+                    srk::launch_permute_sym(st, nf, S, ld, refine > 0 ? 1 : 0, np, src, L, ldp); e.launches += 1;
+                }
                 srk::launch_gather_vec(st, np, src, rhs, xp); e.launches += 1;
-                { Scope s2(e, F_FACTOR); e.launches += srk::dense_cholesky_factor(st, np, L, ldp, di, e.flags.as<int>() + 2, part); }
+                { Scope s2(e, F_FACTOR);
+                  e.launches += srk::dense_cholesky_factor(st, np, L, ldp, di, e.flags.as<int>() + 2, part, tiles ? e.order_pattern.as<unsigned char>() : nullptr,
+                                                           tiles ? e.order.l_pattern_count : 0); }
                 { Scope s2(e, F_TRSV);
                   e.launches += srk::dense_cholesky_forward(st, np, L, ldp, di, xp, part);
                   e.launches += srk::dense_cholesky_backward(st, np, L, ldp, di, xp, part); }
                 srk::launch_scatter_vec(st, np, src, xp, x); e.launches += 1;
                 for (int it = 0; it < refine; ++it) {
-                    srk::launch_residual_dd(st, nf, S, ld, x, rhs, r); e.launches += 1;
+                    if (tiles) srk::launch_residual_dd_tiles(st, nf, S, ld, x, rhs, r, oi + e.ot_resptr, oi + e.ot_resent);
+                    else srk::launch_residual_dd(st, nf, S, ld, x, rhs, r);
+                    e.launches += 1;
                     srk::launch_gather_vec(st, np, src, r, xp); e.launches += 1;
                     { Scope s2(e, F_TRSV);
                       e.launches += srk::dense_cholesky_forward(st, np, L, ldp, di, xp, part);
@@ -784,6 +819,7 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     if (const char* v = std::getenv("SRK_SCHUR_IMPL")) e->schur_impl = std::atoi(v) == 1 ? 1 : 0;
     if (const char* v = std::getenv("SRK_TILE_EXCHANGE")) e->tile_exchange = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SOLVE_ORDER")) e->solve_order_enabled = std::atoi(v) != 0 ? 1 : 0;
+    if (const char* v = std::getenv("SRK_SOLVE_TILES")) e->solve_tiles_enabled = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SCHUR_TILE")) { const int t = std::atoi(v); if (t >= 16 && t <= 4096 && t % 16 == 0) e->schur_tile_fixed = t; }
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; set_error("cudaStreamCreate failed"); return SRK_E_CUDA; }
     e->stream = e->own_stream;
@@ -924,7 +960,8 @@ int srk_ba_debug_derivs_and_solve_ex(void* h, double c, int32_t solver, double* 
             rc = srk::pcg_debug_to_dense(e.pcg, st, M, e.unity, dS, ld, dS + (size_t)ld * nf, &e.launches);
             if (rc != SRK_OK) { set_error("pcg_debug_to_dense failed"); return rc; }
             if (pcg_iters != nullptr) *pcg_iters = e.pcg_iters_last;
-        } else if (opt.refine_steps <= 0) { srk::launch_mirror_lower(st, nf, dS, ld); e.launches += 1; }
+        } else if (opt.refine_steps <= 0 || (e.order.active && e.order_tiles)) { srk::launch_mirror_lower(st, nf, dS, ld); e.launches += 1; }
+        e.S_clean = false;   // the inspection copy fills tiles the solve never clears
         if (S != nullptr) SRK_CUDA(cudaMemcpy2DAsync(S, sizeof(double) * nf, dS, sizeof(double) * ld, sizeof(double) * nf, nf, cudaMemcpyDeviceToHost, st));
         if (rhs != nullptr) SRK_CUDA(cudaMemcpyAsync(rhs, dS + (size_t)ld * nf, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
         if (skipped != nullptr && N > 0) SRK_CUDA(cudaMemcpyAsync(skipped, e.skipped.p, (size_t)N, cudaMemcpyDeviceToHost, st));

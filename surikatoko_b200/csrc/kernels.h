@@ -54,7 +54,12 @@ void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda,
 // part p are [k0[p], k1[p]); no non-zero tile couples two different parts; [ksep, nblk) is the separator block, ordered last.
 // The parts are then factored / substituted by one thread-block cluster each, concurrently, the separator afterwards.
 struct CholPartition { static constexpr int kMaxParts = 32; int nparts; int ksep; int k0[kMaxParts]; int k1[kMaxParts]; };
-int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part = nullptr);
+// pattern_dev (optional, device, nblk x nblk bytes, [c*nblk + r] = 1 for a strictly lower tile that may hold a non-zero) + its count:
+// the caller's knowledge of the tile structure replaces the pattern pass over A and its host round trip.  A must then be zero in
+// every tile outside the pattern that the factorisation fills (SolveOrder::l_all_tiles).
+int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part = nullptr,
+                              const unsigned char* pattern_dev = nullptr, int pattern_count = 0);
+bool dense_cholesky_pattern_ok(int n, int pattern_count, bool partitioned);
 int dense_cholesky_stats(cudaStream_t st, int n, const double* ws, int64_t* nblk, int64_t* nz_tiles, double* factor_flops);
 int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part = nullptr);
 int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part = nullptr);

@@ -199,6 +199,41 @@ SolveOrder build_solve_order(int G, const int* gsize, const unsigned char* adj) 
     o.sep_levels = best.nsep_levels;
     o.sep_blocks = (o.np + kTile - 1) / kTile - o.part.ksep;
     o.active = o.part.nparts >= 2;
+    if (!o.active) return o;
+
+    // ---- tile structure of the natural and of the ordered system
+    const int nb0 = nblk0, nb1 = (o.np + kTile - 1) / kTile;
+    std::vector<unsigned char> sm((size_t)nb0 * nb0, 0), lm((size_t)nb1 * nb1, 0);   // [c*nb + r], r >= c
+    auto mark_pair = [&](int a, int b) {       // every tile the block of groups (a, b) touches, mirrored into the lower triangle
+        const int a0 = gstart[a], a1 = gstart[a + 1] - 1, b0 = gstart[b], b1 = gstart[b + 1] - 1;
+        for (int R = a0 / kTile; R <= a1 / kTile; ++R)
+            for (int C = b0 / kTile; C <= b1 / kTile; ++C) { const int r = std::max(R, C), c = std::min(R, C); sm[(size_t)c * nb0 + r] = 1; }
+        // ordered positions of a group are consecutive
+        const int pa0 = o.pos[a0], pa1 = o.pos[a1], pb0 = o.pos[b0], pb1 = o.pos[b1];
+        for (int R = pa0 / kTile; R <= pa1 / kTile; ++R)
+            for (int C = pb0 / kTile; C <= pb1 / kTile; ++C) { const int r = std::max(R, C), c = std::min(R, C); lm[(size_t)c * nb1 + r] = 1; }
+    };
+    for (int a = 0; a < G; ++a) { mark_pair(a, a); for (int b : g.nb[a]) if (b < a) mark_pair(a, b); }
+    for (int k = 0; k < nb1; ++k) lm[(size_t)k * nb1 + k] = 1;                          // padding unknowns sit on the diagonal
+    for (int c = 0; c < nb0; ++c) for (int r = c; r < nb0; ++r) if (sm[(size_t)c * nb0 + r]) o.s_tiles.push_back((r << 16) | c);
+    o.res_ptr.assign(nb0 + 1, 0);
+    for (int R = 0; R < nb0; ++R) {
+        for (int C = 0; C <= R; ++C) if (sm[(size_t)C * nb0 + R]) o.res_ent.push_back((C << 1) | 0);
+        for (int R2 = R + 1; R2 < nb0; ++R2) if (sm[(size_t)R * nb0 + R2]) o.res_ent.push_back((R2 << 1) | 1);
+        o.res_ptr[R + 1] = (int)o.res_ent.size();
+    }
+    o.l_pattern.assign((size_t)nb1 * nb1, 0);
+    for (int c = 0; c < nb1; ++c)
+        for (int r = c; r < nb1; ++r)
+            if (lm[(size_t)c * nb1 + r]) { o.l_in_tiles.push_back((r << 16) | c); if (r > c) { o.l_pattern[(size_t)c * nb1 + r] = 1; ++o.l_pattern_count; } }
+    // symbolic factorisation, tile level: column k's rows fill each other's tiles
+    std::vector<int> rows;
+    for (int k = 0; k < nb1; ++k) {
+        rows.clear();
+        for (int r = k + 1; r < nb1; ++r) if (lm[(size_t)k * nb1 + r]) rows.push_back(r);
+        for (size_t i = 0; i < rows.size(); ++i) for (size_t j = 0; j <= i; ++j) lm[(size_t)rows[j] * nb1 + rows[i]] = 1;
+    }
+    for (int c = 0; c < nb1; ++c) for (int r = c; r < nb1; ++r) if (lm[(size_t)c * nb1 + r]) o.l_all_tiles.push_back((r << 16) | c);
     return o;
 }
 
@@ -218,6 +253,79 @@ __global__ void __launch_bounds__(256) k_permute_sym(int n, const double* __rest
         double v = 0.0;
         if (is >= 0) v = (mirrored || is >= js) ? col[is] : S[(size_t)is * ld + js];
         out[id] = v;
+    }
+}
+__global__ void __launch_bounds__(256) k_zero_tiles(int n, double* __restrict__ A, int64_t ld, const int* __restrict__ tiles) {
+    const int t = tiles[blockIdx.x];
+    const int r0 = (t >> 16) * kTile, c0 = (t & 0xffff) * kTile;
+    for (int e = threadIdx.x; e < kTile * kTile; e += 256) {
+        const int r = r0 + (e & 63), c = c0 + (e >> 6);
+        if (r < n && c < n) A[(size_t)c * ld + r] = 0.0;
+    }
+}
+__global__ void __launch_bounds__(256) k_permute_tiles(int n, const double* __restrict__ S, int64_t ld, int np, const int* __restrict__ src, double* __restrict__ L,
+                                                       int64_t ldp, const int* __restrict__ tiles) {
+    __shared__ int srow[kTile], scol[kTile];
+    const int t = tiles[blockIdx.x];
+    const int r0 = (t >> 16) * kTile, c0 = (t & 0xffff) * kTile;
+    if (threadIdx.x < kTile) srow[threadIdx.x] = r0 + threadIdx.x < np ? src[r0 + threadIdx.x] : -2;
+    else if (threadIdx.x < 2 * kTile) scol[threadIdx.x - kTile] = c0 + threadIdx.x - kTile < np ? src[c0 + threadIdx.x - kTile] : -2;
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTile * kTile; e += 256) {
+        const int rr = e & 63, cc = e >> 6;
+        const int id = r0 + rr, jd = c0 + cc;
+        const int is = srow[rr], js = scol[cc];
+        if (is == -2 || js == -2 || id < jd) continue;
+        double v;
+        if (is < 0 || js < 0) v = id == jd ? 1.0 : 0.0;
+        else v = is >= js ? S[(size_t)js * ld + is] : S[(size_t)is * ld + js];
+        L[(size_t)jd * ldp + id] = v;
+    }
+}
+__device__ __forceinline__ void dd_acc(double& hi, double& lo, double bh, double bl) {   // (hi, lo) += (bh, bl), two-sum
+    double s = __dadd_rn(hi, bh);
+    double bb = __dadd_rn(s, -hi);
+    double e = __dadd_rn(__dadd_rn(hi, -__dadd_rn(s, -bb)), __dadd_rn(bh, -bb));
+    e = __dadd_rn(e, __dadd_rn(lo, bl));
+    hi = __dadd_rn(s, e);
+    lo = __dadd_rn(e, -__dadd_rn(hi, -s));
+}
+// one CTA per row block R; thread (row = tid & 63, q = tid >> 6) sums the columns c == q (mod 4) of its row over the block's tiles
+__global__ void __launch_bounds__(256) k_residual_dd_tiles(int n, const double* __restrict__ S, int64_t ld, const double* __restrict__ x, const double* __restrict__ b,
+                                                           double* __restrict__ r, const int* __restrict__ res_ptr, const int* __restrict__ res_ent) {
+    __shared__ double xs[kTile];
+    __shared__ double ph[4][kTile], pl[4][kTile];
+    const int R = blockIdx.x, row = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int i = R * kTile + row;
+    double hi = 0.0, lo = 0.0;
+    for (int t = res_ptr[R]; t < res_ptr[R + 1]; ++t) {
+        const int ent = res_ent[t];
+        const int other = ent >> 1, tr = ent & 1;
+        __syncthreads();
+        if (threadIdx.x < kTile) xs[threadIdx.x] = other * kTile + threadIdx.x < n ? x[other * kTile + threadIdx.x] : 0.0;
+        __syncthreads();
+        if (i >= n) continue;
+#pragma unroll 4
+        for (int cc = q; cc < kTile; cc += 4) {
+            const int j = other * kTile + cc;
+            if (j >= n) break;
+            // tile (R, other): S(i, j) lower as stored;  transposed tile (other, R): S(i, j) = S(j, i), j > i
+            double a;
+            if (!tr) { if (other == R && j > i) a = S[(size_t)i * ld + j]; else a = S[(size_t)j * ld + i]; }
+            else a = S[(size_t)i * ld + j];
+            const double xv = xs[cc];
+            const double p = __dmul_rn(a, xv);
+            const double e = __fma_rn(a, xv, -p);
+            dd_acc(hi, lo, p, e);
+        }
+    }
+    ph[q][row] = hi; pl[q][row] = lo;
+    __syncthreads();
+    if (q == 0 && i < n) {
+        for (int k = 1; k < 4; ++k) dd_acc(hi, lo, ph[k][row], pl[k][row]);
+        double rh = b[i], rl = 0.0;
+        dd_acc(rh, rl, -hi, -lo);
+        r[i] = rh;
     }
 }
 __global__ void k_gather_vec(int np, const int* __restrict__ src, const double* __restrict__ in, double* __restrict__ out) {
@@ -246,6 +354,16 @@ __global__ void k_cam_adjacency(int64_t N, const int64_t* __restrict__ pt_begin,
 
 void launch_permute_sym(cudaStream_t st, int n, const double* S, int64_t ld, int mirrored, int np, const int* src_dev, double* L, int64_t ldp) {
     if (np > 0) k_permute_sym<<<np, 256, 0, st>>>(n, S, ld, mirrored, np, src_dev, L, ldp);
+}
+void launch_zero_tiles(cudaStream_t st, int n, double* A, int64_t ld, const int* tiles, int count) {
+    if (count > 0) k_zero_tiles<<<count, 256, 0, st>>>(n, A, ld, tiles);
+}
+void launch_permute_tiles(cudaStream_t st, int n, const double* S, int64_t ld, int np, const int* src_dev, double* L, int64_t ldp, const int* tiles, int count) {
+    if (count > 0) k_permute_tiles<<<count, 256, 0, st>>>(n, S, ld, np, src_dev, L, ldp, tiles);
+}
+void launch_residual_dd_tiles(cudaStream_t st, int n, const double* S, int64_t ld, const double* x, const double* b, double* r, const int* res_ptr, const int* res_ent) {
+    const int nb = (n + kTile - 1) / kTile;
+    if (nb > 0) k_residual_dd_tiles<<<nb, 256, 0, st>>>(n, S, ld, x, b, r, res_ptr, res_ent);
 }
 void launch_gather_vec(cudaStream_t st, int np, const int* src_dev, const double* in, double* out) {
     if (np > 0) k_gather_vec<<<(np + 255) / 256, 256, 0, st>>>(np, src_dev, in, out);

@@ -24,6 +24,14 @@ struct SolveOrder {
     std::vector<int> src;       // [np] ordered index -> natural index, -1 = padding
     CholPartition part{};       // block-column ranges of the parts and of the separator
     int levels = 0, sep_levels = 0, sep_blocks = 0, max_part_blocks = 0;   // diagnostics
+    // 64x64 tile structure (from the same graph, so a superset of whatever the damping / skip rule leaves non-zero), which lets
+    // every pass over the system touch its ~4 % non-zero tiles instead of n^2 entries.  Tiles are packed (row << 16) | col, row >= col.
+    std::vector<int> s_tiles;            // natural-order system: lower tiles that can hold a non-zero
+    std::vector<int> res_ptr, res_ent;   // per natural row block R: entries (other << 1) | t;  t = 0: tile (R, other);  t = 1: tile (other, R) transposed
+    std::vector<int> l_in_tiles;         // ordered system: lower tiles of P S P^T that can hold a non-zero (every diagonal tile included)
+    std::vector<int> l_all_tiles;        // ... plus the fill of the factorisation (symbolic, tile level)
+    std::vector<unsigned char> l_pattern;   // [nblk x nblk] l_pattern[c*nblk + r] = 1 for the strictly lower tiles of l_in_tiles
+    int l_pattern_count = 0;
 };
 
 // groups: consecutive runs of unknowns that stay together (one camera each); gsize[g] unknowns; adj[g*G + h] != 0 iff the groups are
@@ -33,6 +41,12 @@ SolveOrder build_solve_order(int G, const int* gsize, const unsigned char* adj);
 // L (np x np, ldp, lower triangle + diagonal) <- P S P^T; S is n x n (ld) with BOTH triangles stored when `mirrored`, else the lower one.
 // Padding unknowns get a unit diagonal.  src_dev: [np] ordered -> natural (-1 = padding).
 void launch_permute_sym(cudaStream_t st, int n, const double* S, int64_t ld, int mirrored, int np, const int* src_dev, double* L, int64_t ldp);
+// Tile-list forms (SolveOrder::s_tiles / l_in_tiles / l_all_tiles / res_*), one CTA per tile or row block:
+void launch_zero_tiles(cudaStream_t st, int n, double* A, int64_t ld, const int* tiles, int count);
+// listed tiles of L <- P S P^T read from the LOWER triangle of S only
+void launch_permute_tiles(cudaStream_t st, int n, const double* S, int64_t ld, int np, const int* src_dev, double* L, int64_t ldp, const int* tiles, int count);
+// r = b - S x, S symmetric with only the lower tiles stored, double-double accumulation in a fixed order
+void launch_residual_dd_tiles(cudaStream_t st, int n, const double* S, int64_t ld, const double* x, const double* b, double* r, const int* res_ptr, const int* res_ent);
 // out[i] = src[i] >= 0 ? in[src[i]] : 0     (natural -> ordered vector)
 void launch_gather_vec(cudaStream_t st, int np, const int* src_dev, const double* in, double* out);
 // out[src[i]] = in[i] for src[i] >= 0       (ordered -> natural vector)
