@@ -119,7 +119,7 @@ struct Engine {
     int solve_tiles_enabled = 1; // SRK_SOLVE_TILES=0: dense passes over S / L even when the tile structure is known (cross-check)
     Buf adjbuf, order_src, xperm, order_ints, order_pattern;
     bool order_tiles = false;    // the tile lists of `order` are on the device and the factorisation will take the cluster path
-    int ot_s = 0, ot_resptr = 0, ot_resent = 0, ot_lin = 0, ot_lall = 0;   // offsets into order_ints
+    int ot_s = 0, ot_resptr = 0, ot_resent = 0, ot_lin = 0, ot_lall = 0, ot_scn = 0;   // offsets into order_ints
     bool S_clean = false;        // S is zero outside order.s_tiles (so the next attempt only clears those)
     std::vector<unsigned char> order_adj;   // the graph `order` was built from
     unsigned char* h_adj = nullptr;         // pinned
@@ -453,6 +453,9 @@ int ensure_solve_order(Engine& e) {
         std::vector<int> ints;
         auto put = [&](const std::vector<int>& v) { const int off = (int)ints.size(); ints.insert(ints.end(), v.begin(), v.end()); return off; };
         e.ot_s = put(o.s_tiles); e.ot_resptr = put(o.res_ptr); e.ot_resent = put(o.res_ent); e.ot_lin = put(o.l_in_tiles); e.ot_lall = put(o.l_all_tiles);
+        { std::vector<int> cn(o.s_tiles.size()); const int nb0 = (e.nf + 63) / 64;       // the same tiles in the exchange kernels' c * nblk + r form
+          for (size_t i = 0; i < cn.size(); ++i) cn[i] = (o.s_tiles[i] & 0xffff) * nb0 + (o.s_tiles[i] >> 16);
+          e.ot_scn = put(cn); }
         SRK_CUDA(e.order_ints.ensure(sizeof(int) * ints.size()));
         SRK_CUDA(cudaMemcpyAsync(e.order_ints.p, ints.data(), sizeof(int) * ints.size(), cudaMemcpyHostToDevice, st));
         SRK_CUDA(e.order_pattern.ensure(o.l_pattern.size()));
@@ -477,6 +480,17 @@ int allreduce_system(Engine& e, double* S, double* rhs) {
     const int nf = e.nf; const int64_t ld = e.ld;
     const int nblk = (nf + 63) / 64;
     if (nblk < 8 || e.tile_exchange == 0) return do_allreduce(e, S, ld * nf + ld);
+    if (e.order_ready && e.order.active && e.order_tiles) {   // the tile structure is known (union over ranks): no mask pass, no host round trip
+        const int cnt = (int)e.order.s_tiles.size();
+        const int* lst = e.order_ints.as<int>() + e.ot_scn;
+        const int64_t npk = (int64_t)cnt * 4096 + ld;
+        SRK_CUDA(e.tpacked.ensure(sizeof(double) * (size_t)npk));
+        srk::launch_tile_pack(st, nf, S, ld, lst, cnt, rhs, ld, e.tpacked.as<double>(), 0); e.launches += 1;
+        int rc2 = do_allreduce(e, e.tpacked.as<double>(), npk);
+        if (rc2 != SRK_OK) return rc2;
+        srk::launch_tile_pack(st, nf, S, ld, lst, cnt, rhs, ld, e.tpacked.as<double>(), 1); e.launches += 1;
+        return SRK_OK;
+    }
     SRK_CUDA(e.tmask.ensure(sizeof(double) * (size_t)nblk * nblk));
     SRK_CUDA(e.tlist.ensure(sizeof(int) * ((size_t)nblk * nblk + 4)));
     double* mask = e.tmask.as<double>(); int* list = e.tlist.as<int>() + 4; int* cnt = e.tlist.as<int>();

@@ -53,6 +53,44 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// One super-block (NI x NJ fragments of 8x8; DIAG: only the fragments on and below its diagonal) over one batch: straight-line DMMA
+// code for every shape, chosen per tile -- a predicate per fragment inside the loop was measured slower than computing the zeros.
+template <int NI, int NJ, bool DIAG>
+__device__ __forceinline__ void sb_batch(double (&acc)[3][3][2], const double* __restrict__ pa, const double* __restrict__ pb) {
+#pragma unroll 4
+    for (int ks = 0; ks < kMmaK / 4; ++ks) {
+        const int off = ks * 4 * kMmaSLD;
+        double af[NI], bf[NJ];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) af[i] = pa[off + 8 * i];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) bf[j] = pb[off + 8 * j];
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj)
+                if (!DIAG || jj <= i) dmma884(acc[i][jj][0], acc[i][jj][1], af[i], bf[jj]);
+    }
+}
+// shape code: off-diagonal (ni - 1) * 3 + (nj - 1) in 0..8, diagonal 9 + (ni - 1) in 9..11, -1 = nothing to do
+__device__ __forceinline__ void sb_dispatch(int code, double (&acc)[3][3][2], const double* pa, const double* pb) {
+    switch (code) {
+        case 0: sb_batch<1, 1, false>(acc, pa, pb); break;
+        case 1: sb_batch<1, 2, false>(acc, pa, pb); break;
+        case 2: sb_batch<1, 3, false>(acc, pa, pb); break;
+        case 3: sb_batch<2, 1, false>(acc, pa, pb); break;
+        case 4: sb_batch<2, 2, false>(acc, pa, pb); break;
+        case 5: sb_batch<2, 3, false>(acc, pa, pb); break;
+        case 6: sb_batch<3, 1, false>(acc, pa, pb); break;
+        case 7: sb_batch<3, 2, false>(acc, pa, pb); break;
+        case 8: sb_batch<3, 3, false>(acc, pa, pb); break;
+        case 9: sb_batch<1, 1, true>(acc, pa, pb); break;
+        case 10: sb_batch<2, 2, true>(acc, pa, pb); break;
+        case 11: sb_batch<3, 3, true>(acc, pa, pb); break;
+        default: break;
+    }
+}
+
 __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t O, int tile_points, const int64_t* __restrict__ pt_begin,
                                                               const int32_t* __restrict__ obs_cam, const double* __restrict__ J, double c, SchurSink sink,
                                                               double* __restrict__ pinv, unsigned char* __restrict__ skipped,
@@ -250,15 +288,28 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t
 
     // ---- consumers: super-block sb = I(I+1)/2 + Jc covers rows [24 I, 24 I + 24) x columns [24 Jc, 24 Jc + 24)
     const int g = lane >> 2, tg = lane & 3;
-    int sbI[2] = {0, 0}, sbJ[2] = {0, 0};
+    // Assignment of the 15 super-blocks (24x24) to the 8 consumer warps.  A warp issues its DMMAs at a fixed rate, so the warp with
+    // the most fragments sets the pace of a batch: a diagonal super-block (d) only computes the 6 fragments on and below its diagonal,
+    // and fragments in rows / columns beyond the tile's last camera slot (10 * nLocal) are not computed at all -- with 11 cameras in
+    // the table the 15th fragment row is empty and the super-blocks of row I = 4 shrink to 2 fragment rows.  Fragments per warp with
+    // 11 (12) cameras: w0 {1,10} 15 (18), w4 {3,11} 15 (18), w1 {4,12} 15 (18), w5 {6,13} 15 (18), w2 {7,0d} 15 (15), w6 {8,2d} 15 (15),
+    // w3 {5d,9d} 12 (12), w7 {14d} 3 (6) + the rhs GEMV.  It was 18 for every warp, zeros included.
+    int sbI[2] = {0, 0}, sbJ[2] = {0, 0}, code[2] = {-1, -1};
     int nsb = 0;
-    for (int q = 0; q < 2; ++q) {
-        const int sb = w + 8 * q;
-        if (sb >= 15) break;
-        int I = 0;
-        while ((I + 1) * (I + 2) / 2 <= sb) ++I;
-        sbI[q] = I; sbJ[q] = sb - I * (I + 1) / 2;
-        nsb = q + 1;
+    {
+        constexpr int kSbOf[8][2] = {{1, 10}, {4, 12}, {7, 0}, {5, 9}, {3, 11}, {6, 13}, {8, 2}, {14, -1}};
+        const int lim = 10 * nLocal;
+        for (int q = 0; q < 2; ++q) {
+            const int sb = kSbOf[w][q];
+            if (sb < 0) break;
+            int I = 0;
+            while ((I + 1) * (I + 2) / 2 <= sb) ++I;
+            sbI[q] = I; sbJ[q] = sb - I * (I + 1) / 2;
+            nsb = q + 1;
+            int ni = (lim - 24 * sbI[q] + 7) / 8; ni = ni < 0 ? 0 : (ni > 3 ? 3 : ni);
+            int nj = (lim - 24 * sbJ[q] + 7) / 8; nj = nj < 0 ? 0 : (nj > 3 ? 3 : nj);
+            if (ni > 0 && nj > 0) code[q] = sbI[q] == sbJ[q] ? 9 + (ni - 1) : (ni - 1) * 3 + (nj - 1);
+        }
     }
     double acc[2][3][3][2];
 #pragma unroll
@@ -274,29 +325,8 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_schur_mma(int64_t N, int64_t
         const int buf = b & 1;
         const double* F = sm.F[buf];
         const double* W = sm.W[buf];
-        const double* pa0 = F + tg * kMmaSLD + 24 * sbI[0] + g;
-        const double* pb0 = W + tg * kMmaSLD + 24 * sbJ[0] + g;
-        const double* pa1 = F + tg * kMmaSLD + 24 * sbI[1] + g;
-        const double* pb1 = W + tg * kMmaSLD + 24 * sbJ[1] + g;
-#pragma unroll 4
-        for (int ks = 0; ks < kMmaK / 4; ++ks) {
-            const int off = ks * 4 * kMmaSLD;
-            double af[3], bf[3];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) { af[i] = pa0[off + 8 * i]; bf[i] = pb0[off + 8 * i]; }
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int jj = 0; jj < 3; ++jj) dmma884(acc[0][i][jj][0], acc[0][i][jj][1], af[i], bf[jj]);
-            if (nsb > 1) {
-#pragma unroll
-                for (int i = 0; i < 3; ++i) { af[i] = pa1[off + 8 * i]; bf[i] = pb1[off + 8 * i]; }
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int jj = 0; jj < 3; ++jj) dmma884(acc[1][i][jj][0], acc[1][i][jj][1], af[i], bf[jj]);
-            }
-        }
+        sb_dispatch(code[0], acc[0], F + tg * kMmaSLD + 24 * sbI[0] + g, W + tg * kMmaSLD + 24 * sbJ[0] + g);
+        if (nsb > 1) sb_dispatch(code[1], acc[1], F + tg * kMmaSLD + 24 * sbI[1] + g, W + tg * kMmaSLD + 24 * sbJ[1] + g);
         if (w == 7) {   // rhs += Fall^T t
             const double* T = sm.T[buf];
 #pragma unroll
