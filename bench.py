@@ -45,6 +45,12 @@ UNIT = "residuals/s"
 def make_scene(name, rank=0, sample=False):
     from surikatoko_b200 import scenes
     M, N, k = CPU_SAMPLES[name] if sample else WORKLOADS[name][:3]
+    bundle_path = os.environ.get("SRK_BENCH_BUNDLE", "")     # a scene written once by `python -m surikatoko_b200.bundle write` and shared
+    if bundle_path and not sample and rank == 0:
+        from surikatoko_b200 import bundle
+        pr = bundle.read_bundle(bundle_path)
+        assert (pr.n_cams, pr.n_points) == (M, N), "bundle file does not hold the %s workload" % name
+        return pr
     return scenes.ring_scene(M, N, k, seed=1234, point_offset=rank)
 
 

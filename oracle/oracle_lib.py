@@ -88,6 +88,36 @@ class Result:
     world_scale: float = 0.0
 
 
+def read_bundle(path):
+    """Independent (numpy) reader of the bundle format of include/srk/bundle_c_api.h: the oracle's side of a shared scene file."""
+    raw = open(path, "rb").read()
+    if raw[:8] != b"SRKBNDL1":
+        raise ValueError("not a bundle file")
+    n_cams, n_points, n_obs = (int(v) for v in np.frombuffer(raw, dtype="<i8", count=3, offset=8))
+    shared_K = int(np.frombuffer(raw, dtype="<i4", count=1, offset=32)[0]) != 0
+    f0 = float(np.frombuffer(raw, dtype="<f8", count=1, offset=40)[0])
+    off = 48
+
+    def take(dtype, count):
+        nonlocal off
+        a = np.frombuffer(raw, dtype=dtype, count=count, offset=off).copy()
+        off += a.nbytes
+        return a
+    obs_cam = take("<i4", n_obs); obs_point = take("<i4", n_obs); obs_xy = take("<f8", 2 * n_obs).reshape(-1, 2)
+    points = take("<f8", 3 * n_points).reshape(-1, 3); cams = take("<f8", 12 * n_cams).reshape(-1, 12)
+    K = take("<f8", 9 * (1 if shared_K else n_cams)).reshape(-1, 9)
+    h = 1469598103934665603
+    # FNV-1a 64 over the bytes before the checksum (pure-Python loop: small files only; large ones skip the check)
+    if off <= (1 << 20):
+        for b in raw[:off]:
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        if h != int(np.frombuffer(raw, dtype="<u8", count=1, offset=off)[0]):
+            raise ValueError("bundle checksum mismatch")
+    if len(raw) != off + 8:
+        raise ValueError("bundle length mismatch")
+    return Problem(obs_cam, obs_point, obs_xy, points, cams, K, shared_K, f0)
+
+
 def _prob_args(pr):
     return (C.c_int64(pr.n_cams), C.c_int64(pr.n_points), C.c_int64(pr.n_obs), _p(pr.obs_cam, C.c_int32), _p(pr.obs_point, C.c_int32),
             _p(pr.obs_xy, C.c_double))

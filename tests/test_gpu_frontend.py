@@ -57,3 +57,19 @@ def test_triangulation_full_size_property():
     tb = np.arange(0, prob.n_obs + 1, 10)
     X = frontend.Triangulate3DPointByLeastSquares(tb, prob.obs_cam, prob.obs_xy, P, f0)
     assert np.max(np.abs(X - prob.gt_points)) < 1e-7
+
+
+def test_bundle_file_is_a_shared_scene(tmp_path, oracle, engine):
+    """one scene file, read by the engine's C reader and by the oracle's own numpy reader; both refine it alike."""
+    import surikatoko_b200 as sb
+    from surikatoko_b200 import bundle, scenes
+    path = tmp_path / "ring.srkb"
+    bundle.write_bundle(path, scenes.ring_scene(40, 3000, 8, seed=7))
+    prob = bundle.read_bundle(path)
+    pr = oracle.read_bundle(str(path))
+    ref = oracle.ba_solve(pr, err_change=1e-10, max_outer_iters=3, flow="sparse", solve="chol", acc="ld")
+    rep = engine.solve(prob, sb.BAOptions(err_change=1e-10, max_outer_iters=3))
+    assert rep.seen_points == ref.seen_points and abs(rep.err_initial - ref.err_initial) <= 1e-12 * ref.err_initial
+    assert np.array_equal(rep.attempts[:, 2], ref.attempts[:, 2])
+    dev = np.abs(np.sqrt(rep.err_trace) - np.sqrt(ref.err_trace)) / np.sqrt(ref.err_trace)
+    assert dev[0] < 1e-9 and np.all(dev < 1e-7), dev
