@@ -7,3 +7,4 @@ include/suriko_compat/bundle-adj-kanatani.h.  There is no CPU fallback.
 from .capi import (BAProblem, BAOptions, BAReport, Engine, SrkError, load_library, STOP_REASONS,  # noqa: F401
                    SOLVER_AUTO, SOLVER_DENSE_CHOLESKY, SOLVER_BLOCK_PCG)
 from .ba import BundleAdjustmentKanatani, BundleAdjustmentKanataniTermCriteria  # noqa: F401
+from .mvf import MultiViewIterativeFactorizer  # noqa: F401
