@@ -173,40 +173,87 @@ __global__ void __launch_bounds__(128) k_frame_blocks(int M, const int64_t* __re
 // K1': squared residuals.  Fixed grid; a CTA walks chunks of kObsRows*256 observations (camera table per chunk), keeps one
 // partial per thread, then a per-block partial and a fixed-order final sum (deterministic for a given grid).
 constexpr int kResRows = 4;    // observations per thread and chunk in K1' (8 was measured: 104 registers, 2 CTAs per SM, 0.19 ms instead of 0.12 ms)
+constexpr int kResChunk = 256 * kResRows;
+
+// Bind-time structure pass for K1': the distinct cameras of every chunk of kResChunk observations (at most kCamTabSlots of them get a
+// shared-memory slot) and, per observation, the slot of its camera (255 = read the record from global memory).  The observation order
+// never changes during a solve, so K1' itself needs no hash set, no insert phase and reads 1 byte instead of the 4-byte camera id.
+__global__ void __launch_bounds__(256) k_chunk_tables(int64_t O, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt, int* __restrict__ chunk_cams,
+                                                      int* __restrict__ chunk_cnt, int2* __restrict__ chunk_pts, unsigned char* __restrict__ obs_slot) {
+    __shared__ CamTable tab;
+    const int64_t ch = blockIdx.x;
+    const int64_t base = ch * kResChunk + threadIdx.x;
+    cam_table_reset(tab);
+    int cam[kResRows], hp[kResRows];
+#pragma unroll
+    for (int rr = 0; rr < kResRows; ++rr) { const int64_t o = base + 256 * rr; cam[rr] = o < O ? obs_cam[o] : -1; }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < kResRows; ++rr) hp[rr] = cam[rr] >= 0 ? cam_table_insert(tab, cam[rr]) : -1;
+    __syncthreads();
+    const int n = min(tab.count, kCamTabSlots);
+    if (threadIdx.x < kCamTabSlots) chunk_cams[ch * kCamTabSlots + threadIdx.x] = (int)threadIdx.x < n ? tab.cam_of_slot[threadIdx.x] : -1;
+    if (threadIdx.x == 0) {
+        chunk_cnt[ch] = n;
+        // observations are point-major: the chunk's points are the contiguous id range [first, last]
+        const int64_t o0 = ch * kResChunk, o1 = min(O, o0 + kResChunk) - 1;
+        const int p0 = obs_pt[o0], p1 = obs_pt[o1];
+        chunk_pts[ch] = make_int2(p0, p1 >= p0 ? p1 - p0 + 1 : 0);
+    }
+#pragma unroll
+    for (int rr = 0; rr < kResRows; ++rr) {
+        const int64_t o = base + 256 * rr;
+        if (o >= O) continue;
+        const int sl = hp[rr] >= 0 ? tab.slot[hp[rr]] : -1;
+        obs_slot[o] = sl >= 0 ? (unsigned char)sl : (unsigned char)255;
+    }
+}
+
+// K1': squared residuals.  Fixed grid; a CTA walks chunks of kResChunk observations.  Every global load of a chunk is issued up
+// front -- slot / point id / pixel of each observation, the chunk's camera list -> camera records into shared memory (odd stride), the
+// point gather as soon as the ids arrive -- ONE barrier, then arithmetic.  One partial per thread, then a per-block partial and a
+// fixed-order final sum (deterministic for a given grid; same summation order as before the tables existed).
 __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt,
                                                   const double* __restrict__ obs_xs, const double* __restrict__ obs_ys,
                                                   const double* __restrict__ X, int64_t N, const double* __restrict__ camd,
-                                                  double* __restrict__ partial) {
-    __shared__ CamTable tab;
+                                                  const int* __restrict__ chunk_cams, const int* __restrict__ chunk_cnt, const int2* __restrict__ chunk_pts,
+                                                  const unsigned char* __restrict__ obs_slot, double* __restrict__ partial) {
+    __shared__ double rec[kCamTabSlots * kCamRecPad];
+    __shared__ double xsl[3 * kResChunk];      // the chunk's points (a chunk of kResChunk observations spans at most as many point ids)
     double s = 0.0;
-    const int64_t nchunks = (O + 256 * kResRows - 1) / (256 * kResRows);
+    const int64_t nchunks = (O + kResChunk - 1) / kResChunk;
     for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const int64_t base = ch * (256 * kResRows) + threadIdx.x;
-        __syncthreads();                      // the previous chunk's records are no longer read
-        cam_table_reset(tab);
-        int cam[kResRows];
-#pragma unroll
-        for (int rr = 0; rr < kResRows; ++rr) { const int64_t o = base + 256 * rr; cam[rr] = o < O ? obs_cam[o] : -1; }
-        __syncthreads();
-        int hp[kResRows];
-#pragma unroll
-        for (int rr = 0; rr < kResRows; ++rr) hp[rr] = cam[rr] >= 0 ? cam_table_insert(tab, cam[rr]) : -1;
-        // the rest of the observation while the table settles
-        int pt[kResRows]; double xs[kResRows], ys[kResRows];
+        const int64_t base = ch * kResChunk + threadIdx.x;
+        int pt[kResRows], sl[kResRows]; double xs[kResRows], ys[kResRows];
 #pragma unroll
         for (int rr = 0; rr < kResRows; ++rr) {
             const int64_t o = base + 256 * rr;
             const bool in = o < O;
-            pt[rr] = in ? obs_pt[o] : 0; xs[rr] = in ? obs_xs[o] : 0.0; ys[rr] = in ? obs_ys[o] : 0.0;
+            sl[rr] = in ? (int)obs_slot[o] : -1; pt[rr] = in ? obs_pt[o] : 0; xs[rr] = in ? obs_xs[o] : 0.0; ys[rr] = in ? obs_ys[o] : 0.0;
         }
-        __syncthreads();
-        cam_table_stage(tab, camd);
+        const int n = chunk_cnt[ch] * kCamStride;
+        const int2 pr = chunk_pts[ch];
+        const bool staged = pr.y <= kResChunk;   // false only when point ids without observations stretch the range: gather from global then
+        __syncthreads();                      // the previous chunk's records and points are no longer read
+        for (int e = threadIdx.x; e < n; e += 256) {
+            const int sidx = e / kCamStride, f = e - sidx * kCamStride;
+            rec[sidx * kCamRecPad + f] = camd[(size_t)chunk_cams[ch * kCamTabSlots + sidx] * kCamStride + f];
+        }
+        if (staged) {                         // coalesced, and independent of the obs_pt loads above: one round trip for everything
+            for (int e = threadIdx.x; e < pr.y; e += 256) {
+                xsl[e] = X[pr.x + e]; xsl[kResChunk + e] = X[N + pr.x + e]; xsl[2 * kResChunk + e] = X[2 * N + pr.x + e];
+            }
+        }
         __syncthreads();
 #pragma unroll
         for (int rr = 0; rr < kResRows; ++rr) {
-            if (cam[rr] < 0) continue;
+            if (sl[rr] < 0) continue;
+            const double* cd = sl[rr] < 255 ? rec + sl[rr] * kCamRecPad : camd + (size_t)obs_cam[base + 256 * rr] * kCamStride;
+            double X0r, X1r, X2r;
+            if (staged) { const int q = pt[rr] - pr.x; X0r = xsl[q]; X1r = xsl[kResChunk + q]; X2r = xsl[2 * kResChunk + q]; }
+            else { X0r = X[pt[rr]]; X1r = X[N + pt[rr]]; X2r = X[2 * N + pt[rr]]; }
             double rx, ry;
-            obs_residual(cam_table_record(tab, hp[rr], cam[rr], camd), X[pt[rr]], X[N + pt[rr]], X[2 * N + pt[rr]], xs[rr], ys[rr], rx, ry);
+            obs_residual(cd, X0r, X1r, X2r, xs[rr], ys[rr], rx, ry);
             s += rx * rx + ry * ry;
         }
     }
@@ -881,9 +928,15 @@ void launch_frame_blocks(cudaStream_t st, int M, const int64_t* cam_begin, const
     if (splits > 1) { cudaMemsetAsync(G, 0, sizeof(double) * 100 * (size_t)M, st); cudaMemsetAsync(gf, 0, sizeof(double) * 10 * (size_t)M, st); }
     k_frame_blocks<<<dim3(M, splits), 128, 0, st>>>(M, cam_begin, c_pt, c_x, c_y, X, N, camd, G, gf, splits);
 }
+int64_t residual_chunks(int64_t O) { return (O + kResChunk - 1) / kResChunk; }
+int residual_chunk_slots() { return kCamTabSlots; }
+void launch_chunk_tables(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, int* chunk_cams, int* chunk_cnt, int* chunk_pts, unsigned char* obs_slot) {
+    if (O > 0) k_chunk_tables<<<(unsigned)residual_chunks(O), 256, 0, st>>>(O, obs_cam, obs_pt, chunk_cams, chunk_cnt, reinterpret_cast<int2*>(chunk_pts), obs_slot);
+}
 void launch_residual(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
-                     const double* X, int64_t N, const double* camd, double* partial, int nblocks, double* out) {
-    k_residual<<<nblocks, 256, 0, st>>>(O, obs_cam, obs_pt, x, y, X, N, camd, partial);
+                     const double* X, int64_t N, const double* camd, const int* chunk_cams, const int* chunk_cnt, const int* chunk_pts,
+                     const unsigned char* obs_slot, double* partial, int nblocks, double* out) {
+    k_residual<<<nblocks, 256, 0, st>>>(O, obs_cam, obs_pt, x, y, X, N, camd, chunk_cams, chunk_cnt, reinterpret_cast<const int2*>(chunk_pts), obs_slot, partial);
     k_sum_partials<<<1, 256, 0, st>>>(nblocks, partial, out);
 }
 void launch_fill_reduced(cudaStream_t st, int M, const double* G, const double* gf, double c, int unity, double* S, int64_t ld, double* rhs) {

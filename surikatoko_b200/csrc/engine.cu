@@ -106,6 +106,7 @@ struct Engine {
 
     // observations (point-major) and the camera-major copy
     Buf obs_cam, obs_pt, obs_xy, ox, oy, pt_begin, cam_cnt, cam_cursor, cam_begin, c_pt, c_x, c_y;
+    Buf chunk_cams, chunk_cnt, chunk_pts, obs_slot;   // K1' structure: per-chunk camera lists, per-observation table slots (k_chunk_tables)
     // state: current / trial / as bound
     Buf Xa, Xb, Xbound, pts_stage, cams_a, cams_b, cams_bound, Kd, camd_a, camd_b;
     double *X_cur = nullptr, *X_try = nullptr, *cams_cur = nullptr, *cams_try = nullptr, *camd_cur = nullptr, *camd_try = nullptr;
@@ -254,7 +255,16 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     srk::launch_scan_counts(st, M, e.cam_cnt.as<unsigned long long>(), e.cam_begin.as<int64_t>(), e.cam_cursor.as<unsigned long long>());
     srk::launch_scatter_by_cam(st, O, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.ox.as<double>(), e.oy.as<double>(),
                                e.cam_cursor.as<unsigned long long>(), e.c_pt.as<int32_t>(), e.c_x.as<double>(), e.c_y.as<double>());
-    e.launches += 3;
+    {
+        const int64_t nch = srk::residual_chunks(O);
+        SRK_CUDA(e.chunk_cams.ensure(sizeof(int) * (size_t)(nch > 0 ? nch : 1) * srk::residual_chunk_slots()));
+        SRK_CUDA(e.chunk_cnt.ensure(sizeof(int) * (size_t)(nch > 0 ? nch : 1)));
+        SRK_CUDA(e.chunk_pts.ensure(sizeof(int) * 2 * (size_t)(nch > 0 ? nch : 1)));
+        SRK_CUDA(e.obs_slot.ensure((size_t)(O > 0 ? O : 1)));
+        srk::launch_chunk_tables(st, O, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.chunk_cams.as<int>(), e.chunk_cnt.as<int>(), e.chunk_pts.as<int>(),
+                                 e.obs_slot.as<unsigned char>());
+    }
+    e.launches += 4;
     int h_flag = 0;
     SRK_CUDA(cudaMemcpyAsync(&h_flag, e.flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SRK_CUDA(cudaStreamSynchronize(st));
@@ -367,7 +377,8 @@ int pick_solver(const Engine& e, const srk_ba_options* opt) {
 void residual_of(Engine& e, const double* X, const double* camd) {
     Scope s(e, F_RESIDUAL);
     srk::launch_residual(e.stream, e.O, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.ox.as<double>(), e.oy.as<double>(), X, e.N, camd,
-                         e.partial.as<double>(), e.residual_blocks, e.errsum.as<double>());
+                         e.chunk_cams.as<int>(), e.chunk_cnt.as<int>(), e.chunk_pts.as<int>(), e.obs_slot.as<unsigned char>(), e.partial.as<double>(), e.residual_blocks,
+                         e.errsum.as<double>());
     e.launches += 2;
 }
 

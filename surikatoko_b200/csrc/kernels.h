@@ -11,8 +11,13 @@ void launch_jacobian(cudaStream_t st, int64_t O, const int32_t* obs_cam, const i
                      const double* X, int64_t N, const double* camd, double* J);
 void launch_frame_blocks(cudaStream_t st, int M, const int64_t* cam_begin, const int32_t* c_pt, const double* c_x, const double* c_y,
                          const double* X, int64_t N, const double* camd, double* G, double* gf, int splits);
+// bind-time structure pass of K1' (per-chunk camera lists + per-observation slots), see k_chunk_tables
+int64_t residual_chunks(int64_t O);
+int residual_chunk_slots();
+void launch_chunk_tables(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, int* chunk_cams, int* chunk_cnt, int* chunk_pts /*int2 per chunk*/, unsigned char* obs_slot);
 void launch_residual(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
-                     const double* X, int64_t N, const double* camd, double* partial, int nblocks, double* out);
+                     const double* X, int64_t N, const double* camd, const int* chunk_cams, const int* chunk_cnt, const int* chunk_pts,
+                     const unsigned char* obs_slot, double* partial, int nblocks, double* out);
 void launch_fill_reduced(cudaStream_t st, int M, const double* G, const double* gf, double c, int unity, double* S, int64_t ld, double* rhs);
 struct SchurSink;   // common.cuh
 void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
