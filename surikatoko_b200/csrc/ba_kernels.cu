@@ -784,6 +784,68 @@ __global__ void __launch_bounds__(256) k_backsub(int64_t N, int64_t O, const int
     }
 }
 
+// K2' with one thread per OBSERVATION (every lane of a warp load carries data: the point-per-half-warp form above leaves 6 of 16 lanes
+// idle at 10 observations per point and was bound by load latency at 58 % of the HBM peak).  A lane forms its observation's
+// contribution F_i * df[cam_i]; the lanes of one point are contiguous (observations are point-major), so a segmented shuffle
+// reduction gives the point's partial sum, which the segment's first lane adds to tacc[3][N].  A point spans at most two warps for tracks
+// of up to 32 observations, and two partial sums add commutatively onto an exact zero: the result is bit-reproducible.
+// k_backsub_finish then applies -Einv (t + g_p), writes the trial points and re-zeroes tacc for the next attempt.
+__global__ void __launch_bounds__(256) k_backsub_obs(int64_t O, int64_t N, const int32_t* __restrict__ obs_pt, const int32_t* __restrict__ obs_cam,
+                                                     const double* __restrict__ J, const double* __restrict__ df, const unsigned char* __restrict__ skipped,
+                                                     double* __restrict__ tacc) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in = o < O;
+    const int pt = in ? obs_pt[o] : -1;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    bool live = false;
+    if (in) {
+        const int cam = obs_cam[o];
+        live = skipped[pt] == 0;
+        if (live) {
+            const double* d = df + (size_t)cam * 10;
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int a = 0; a < 10; ++a) {
+                const double da = d[a];
+                s0 += J[(int64_t)(8 + a * 2) * O + o] * da;
+                s1 += J[(int64_t)(9 + a * 2) * O + o] * da;
+            }
+            c0 = 2.0 * (J[(int64_t)2 * O + o] * s0 + J[(int64_t)3 * O + o] * s1);
+            c1 = 2.0 * (J[(int64_t)4 * O + o] * s0 + J[(int64_t)5 * O + o] * s1);
+            c2 = 2.0 * (J[(int64_t)6 * O + o] * s0 + J[(int64_t)7 * O + o] * s1);
+        }
+    }
+    // segment heads: first lane of the warp or a new point id
+    const int prev = __shfl_up_sync(0xffffffffu, pt, 1);
+    const bool head = lane == 0 || pt != prev;
+    const unsigned heads = __ballot_sync(0xffffffffu, head);
+    const unsigned later = heads & ~((2u << lane) - 1u);            // heads strictly after this lane
+    const int seg_end = later ? __ffs(later) - 1 : 32;              // first lane of the next segment
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double v0 = __shfl_down_sync(0xffffffffu, c0, off), v1 = __shfl_down_sync(0xffffffffu, c1, off), v2 = __shfl_down_sync(0xffffffffu, c2, off);
+        if (lane + off < seg_end) { c0 += v0; c1 += v1; c2 += v2; }
+    }
+    if (head && live) { atomicAdd(&tacc[pt], c0); atomicAdd(&tacc[N + pt], c1); atomicAdd(&tacc[2 * N + pt], c2); }
+}
+__global__ void __launch_bounds__(256) k_backsub_finish(int64_t N, double* __restrict__ tacc, const double* __restrict__ pinv, const unsigned char* __restrict__ skipped,
+                                                        const double* __restrict__ X, double* __restrict__ Xtry, double* __restrict__ dp_out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+    if (skipped[j] == 0) {
+        const double i0 = pinv[j], i1 = pinv[N + j], i2 = pinv[2 * N + j], i3 = pinv[3 * N + j], i4 = pinv[4 * N + j], i5 = pinv[5 * N + j];
+        const double u0 = tacc[j] + pinv[6 * N + j], u1 = tacc[N + j] + pinv[7 * N + j], u2 = tacc[2 * N + j] + pinv[8 * N + j];
+        d0 = -(i0 * u0 + i1 * u1 + i2 * u2);
+        d1 = -(i1 * u0 + i3 * u1 + i4 * u2);
+        d2 = -(i2 * u0 + i4 * u1 + i5 * u2);
+        tacc[j] = 0.0; tacc[N + j] = 0.0; tacc[2 * N + j] = 0.0;
+    }
+    Xtry[j] = X[j] + d0; Xtry[N + j] = X[N + j] + d1; Xtry[2 * N + j] = X[2 * N + j] + d2;
+    if (dp_out != nullptr) { dp_out[3 * j] = d0; dp_out[3 * j + 1] = d1; dp_out[3 * j + 2] = d2; }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // K4: per-camera update (ApplyCorrections, BA.cpp:2021-2062): direct = SE3Inv(inverse); T_d += dT;
 // R_d <- Rodrigues(dW)*R_d unless |dW| is ~0 (IsClose(0, ang), quirk Q6); inverse = SE3Inv(direct).
@@ -932,6 +994,11 @@ int64_t residual_chunks(int64_t O) { return (O + kResChunk - 1) / kResChunk; }
 int residual_chunk_slots() { return kCamTabSlots; }
 void launch_chunk_tables(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, int* chunk_cams, int* chunk_cnt, int* chunk_pts, unsigned char* obs_slot) {
     if (O > 0) k_chunk_tables<<<(unsigned)residual_chunks(O), 256, 0, st>>>(O, obs_cam, obs_pt, chunk_cams, chunk_cnt, reinterpret_cast<int2*>(chunk_pts), obs_slot);
+}
+void launch_backsub_obs(cudaStream_t st, int64_t N, int64_t O, const int32_t* obs_pt, const int32_t* obs_cam, const double* J, const double* df, const double* pinv,
+                        const unsigned char* skipped, const double* X, double* Xtry, double* dp_out, double* tacc) {
+    if (O > 0) k_backsub_obs<<<cdiv(O, 256), 256, 0, st>>>(O, N, obs_pt, obs_cam, J, df, skipped, tacc);
+    if (N > 0) k_backsub_finish<<<cdiv(N, 256), 256, 0, st>>>(N, tacc, pinv, skipped, X, Xtry, dp_out);
 }
 void launch_residual(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
                      const double* X, int64_t N, const double* camd, const int* chunk_cams, const int* chunk_cnt, const int* chunk_pts,

@@ -516,8 +516,9 @@ constexpr int RS_ROWS = 128;
 constexpr int RS_SLDA = RS_ROWS + 4;
 constexpr int RS_SLDB = NB + 4;
 constexpr size_t kRightSolveSmem = sizeof(double) * (NB * RS_SLDA + NB * RS_SLDB);
+// ncols (<= 64): columns of the block that exist (a ragged last block of a caller whose matrix ends there: neither read nor written beyond)
 __global__ void __launch_bounds__(256) k_right_solve_dmma(int rows, int row0, double* __restrict__ A, int64_t lda, const double* __restrict__ dinv,
-                                                          unsigned char* __restrict__ Frow, int nblk) {
+                                                          unsigned char* __restrict__ Frow, int nblk, int ncols) {
     extern __shared__ double sm[];
     double* sA = sm;                       // [q][row]
     double* sB = sm + NB * RS_SLDA;        // [q][c] = Linv(c, q)
@@ -529,6 +530,7 @@ __global__ void __launch_bounds__(256) k_right_solve_dmma(int rows, int row0, do
         const int q = v >> 6, rp = (v & 63) * 2;
         const int row = r0 + rp;
         int bytes = (rows - row) * 8; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+        if (q >= ncols) bytes = 0;
         cp_async16(sA + q * RS_SLDA + rp, A + (bytes > 0 ? (size_t)q * lda + row : 0), bytes);
     }
 #pragma unroll
@@ -585,7 +587,7 @@ __global__ void __launch_bounds__(256) k_right_solve_dmma(int rows, int row0, do
         for (int j = 0; j < 4; ++j) {
             const int row = r0 + wr + i * 8 + g;
             const int c = wc + j * 8 + tg * 2;
-            if (row < rows) { A[(size_t)c * lda + row] = acc[i][j][0]; A[(size_t)(c + 1) * lda + row] = acc[i][j][1]; }
+            if (row < rows) { if (c < ncols) A[(size_t)c * lda + row] = acc[i][j][0]; if (c + 1 < ncols) A[(size_t)(c + 1) * lda + row] = acc[i][j][1]; }
         }
 }
 
@@ -1358,7 +1360,7 @@ static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
             { ProfScope ps(0, st); k_potrf64_inv<<<1, 256, sizeof(double) * kPotrfScratchDoubles, st>>>(n, k0, A, ld, di, info_dev, F, nblk, g_potrf_rowops); } ++launches;
             const int below = n - (k0 + NB);
             if (below <= 0) continue;
-            { ProfScope ps(1, st); k_right_solve_dmma<<<(below + RS_ROWS - 1) / RS_ROWS, 256, kRightSolveSmem, st>>>(n, k0 + NB, A + (size_t)k0 * ld, ld, di, F + (size_t)(k0 / NB) * nblk, nblk); } ++launches;
+            { ProfScope ps(1, st); k_right_solve_dmma<<<(below + RS_ROWS - 1) / RS_ROWS, 256, kRightSolveSmem, st>>>(n, k0 + NB, A + (size_t)k0 * ld, ld, di, F + (size_t)(k0 / NB) * nblk, nblk, NB); } ++launches;
             const int origin = k0 + NB;
             if (origin < pend) {   // rest of the current panel, K = 64
                 { ProfScope ps(2, st); launch_syrk(st, n, A, ld, k0, NB, origin, pend, F, nblk); } launches += 2;
@@ -1679,9 +1681,9 @@ __global__ void __launch_bounds__(256) k_block_right_solve(int rows, double* __r
         for (int i = 0; i < 32; ++i) A[(size_t)(cbase + i) * lda + r0 + r] = acc[i];
     }
 }
-void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block) {
+void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block, int ncols) {
     set_attrs_once();
-    if (rows > 0) k_right_solve_dmma<<<(rows + RS_ROWS - 1) / RS_ROWS, 256, kRightSolveSmem, st>>>(rows, 0, A, lda, dinv_block, nullptr, 0);
+    if (rows > 0 && ncols > 0) k_right_solve_dmma<<<(rows + RS_ROWS - 1) / RS_ROWS, 256, kRightSolveSmem, st>>>(rows, 0, A, lda, dinv_block, nullptr, 0, ncols < NB ? ncols : NB);
 }
 
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld) {

@@ -213,6 +213,8 @@ struct DBuf {
         size_t want = bytes < 256 ? 256 : bytes;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
+        // development aid: SRK_POISON=1 fills fresh buffers with NaN patterns, so that a read of memory nobody wrote shows up at once
+        if (e == cudaSuccess && getenv("SRK_POISON") != nullptr) cudaMemset(p, 0xFF, want);
         return e;
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
@@ -300,7 +302,7 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
         const int nblk = (m2 + 63) / 64;
         for (int kb = 0; kb < nblk; ++kb) {
             const int k0 = kb * 64;
-            srk::launch_block_right_solve(st, n, PHt + (size_t)k0 * ldz, ldz, srk::dense_cholesky_dinv_block(ws, kb));
+            srk::launch_block_right_solve(st, n, PHt + (size_t)k0 * ldz, ldz, srk::dense_cholesky_dinv_block(ws, kb), m2 - k0);   // the last block may be ragged
             e.launches += 1;
             const int rest = m2 - (k0 + 64);
             if (rest > 0) {

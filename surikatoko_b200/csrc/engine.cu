@@ -44,6 +44,8 @@ struct Buf {
         size_t want = bytes < 256 ? 256 : bytes;
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
+        // development aid: SRK_POISON=1 fills fresh buffers with NaN patterns, so that a read of memory nobody wrote shows up at once
+        if (e == cudaSuccess && std::getenv("SRK_POISON") != nullptr) cudaMemset(p, 0xFF, want);
         return e;
     }
     void release() { if (p != nullptr) cudaFree(p); p = nullptr; cap = 0; }
@@ -106,7 +108,10 @@ struct Engine {
 
     // observations (point-major) and the camera-major copy
     Buf obs_cam, obs_pt, obs_xy, ox, oy, pt_begin, cam_cnt, cam_cursor, cam_begin, c_pt, c_x, c_y;
-    Buf chunk_cams, chunk_cnt, chunk_pts, obs_slot;   // K1' structure: per-chunk camera lists, per-observation table slots (k_chunk_tables)
+    Buf chunk_cams, chunk_cnt, chunk_pts, obs_slot;
+    Buf tacc;                 // K2' per-point accumulators [3N]; zero between attempts (k_backsub_finish re-zeroes what it reads)
+    bool tacc_zero = false;
+    int backsub_impl = 1;     // SRK_BACKSUB_IMPL=0: the point-per-half-warp kernel   // K1' structure: per-chunk camera lists, per-observation table slots (k_chunk_tables)
     // state: current / trial / as bound
     Buf Xa, Xb, Xbound, pts_stage, cams_a, cams_b, cams_bound, Kd, camd_a, camd_b;
     double *X_cur = nullptr, *X_try = nullptr, *cams_cur = nullptr, *cams_try = nullptr, *camd_cur = nullptr, *camd_try = nullptr;
@@ -345,6 +350,7 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     e.bound = true;
     e.order_ready = false;
     e.S_clean = false;
+    e.tacc_zero = false;
     return e.norm_failed ? 1 : SRK_OK;
 }
 
@@ -658,9 +664,16 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
     {
         Scope s(e, F_BACKSUB);
         int64_t avg = e.N > 0 ? e.O / e.N : 0;
-        srk::launch_backsub(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), e.dfull.as<double>(), e.pinv.as<double>(),
-                            e.skipped.as<unsigned char>(), e.X_cur, e.X_try, dp_out, (int)(avg < 4 ? 4 : avg));
-        e.launches += e.N > 0 ? 1 : 0;
+        if (e.backsub_impl == 1 && e.N > 0) {
+            if (!e.tacc_zero) { SRK_CUDA(e.tacc.ensure(sizeof(double) * 3 * (size_t)e.N)); SRK_CUDA(cudaMemsetAsync(e.tacc.p, 0, sizeof(double) * 3 * (size_t)e.N, st)); e.tacc_zero = true; }
+            srk::launch_backsub_obs(st, e.N, e.O, e.obs_pt.as<int32_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), e.dfull.as<double>(), e.pinv.as<double>(),
+                                    e.skipped.as<unsigned char>(), e.X_cur, e.X_try, dp_out, e.tacc.as<double>());
+            e.launches += 2;
+        } else {
+            srk::launch_backsub(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), e.dfull.as<double>(), e.pinv.as<double>(),
+                                e.skipped.as<unsigned char>(), e.X_cur, e.X_try, dp_out, (int)(avg < 4 ? 4 : avg));
+            e.launches += e.N > 0 ? 1 : 0;
+        }
     }
     srk::launch_finite_flag(st, 3 * e.N, e.X_try, e.flags.as<int>() + 1); e.launches += e.N > 0 ? 1 : 0;  // BA.cpp:1953-1954
     srk::launch_count_skipped(st, e.N, e.skipped.as<unsigned char>(), e.skipped_cnt.as<unsigned long long>()); e.launches += e.N > 0 ? 1 : 0;
@@ -844,6 +857,7 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     if (const char* v = std::getenv("SRK_SCHUR_IMPL")) e->schur_impl = std::atoi(v) == 1 ? 1 : 0;
     if (const char* v = std::getenv("SRK_TILE_EXCHANGE")) e->tile_exchange = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SOLVE_ORDER")) e->solve_order_enabled = std::atoi(v) != 0 ? 1 : 0;
+    if (const char* v = std::getenv("SRK_BACKSUB_IMPL")) e->backsub_impl = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SOLVE_TILES")) e->solve_tiles_enabled = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SCHUR_TILE")) { const int t = std::atoi(v); if (t >= 16 && t <= 4096 && t % 16 == 0) e->schur_tile_fixed = t; }
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; set_error("cudaStreamCreate failed"); return SRK_E_CUDA; }

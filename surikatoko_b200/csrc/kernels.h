@@ -34,6 +34,9 @@ void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, c
                        unsigned long long* plan_keys, unsigned plan_mask, int* plan_overflow);
 void launch_backsub(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, const double* df,
                     const double* pinv, const unsigned char* skipped, const double* X, double* Xtry, double* dp_out, int lanes_per_point);
+// K2' with one thread per observation + per-point finish; tacc: [3N] doubles, zero on entry, zero again on exit
+void launch_backsub_obs(cudaStream_t st, int64_t N, int64_t O, const int32_t* obs_pt, const int32_t* obs_cam, const double* J, const double* df, const double* pinv,
+                        const unsigned char* skipped, const double* X, double* Xtry, double* dp_out, double* tacc);
 void launch_cam_update(cudaStream_t st, int M, const double* cams, const double* df, double* cams_try);
 void launch_expand_df(cudaStream_t st, int M, const double* dfr, int unity, double* df);
 void launch_normalize_points(cudaStream_t st, int64_t N, double* X, const double* cam0_dev, double s, int revert);
@@ -54,7 +57,8 @@ inline const double* dense_cholesky_dinv_block(const double* ws, int kb) { retur
 // C (m x n, ldc) -= A (m x K, lda) * B (n x K, ldb)^T, all column-major, DMMA 128x128 tiles; lower_only: only tiles / entries with row >= col.
 void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only);
 // X (rows x 64 at A, lda) <- X * Linv^T with Linv a column-major 64x64 lower-triangular inverse (right-side triangular solve of one block column)
-void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block);
+// ncols: how many of the 64 columns exist (the caller's matrix may end inside the last block)
+void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block, int ncols = 64);
 // Optional scheduling hint for block-sparse systems ordered by nested dissection (solve_order.h): the block columns (64 wide) of
 // part p are [k0[p], k1[p]); no non-zero tile couples two different parts; [ksep, nblk) is the separator block, ordered last.
 // The parts are then factored / substituted by one thread-block cluster each, concurrently, the separator afterwards.
