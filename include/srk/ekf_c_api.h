@@ -44,12 +44,29 @@ SRK_API int srk_ekf_predict_resident(void* h, const double* F13, const double* G
 SRK_API int srk_ekf_update_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z,
                                     const double* h_pred, double meas_var, int32_t* info);
 
+/* What ProjectCameraSalientPoint / DistortPixel read (EKF.cpp:3007-3033, :2960-3005): CameraIntrinsicParams::FocalLengthPix(),
+ * principal_point_pix, pixel_size_mm, MikhailRadialDistortionParams k1 / k2, cam_enable_distortion_. */
+typedef struct srk_ekf_camera {
+    double fx_pix, fy_pix, cx, cy, dx_mm, dy_mm, k1, k2;
+    int32_t enable_distortion;
+} srk_ekf_camera;
+
+/* Hypothesis scoring of the 1-point RANSAC update on the resident state: OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391), every
+ * matched point as a hypothesis, all at once.  Inputs as srk_ekf_update_resident (the projections are formed on the device from the
+ * state: no h_pred).  support[m] (optional) = size of each hypothesis' consensus set (matched points whose projection under the
+ * hypothesis state lies within max_divergence_pix of their corner), *best = the winning hypothesis (the earliest maximum, -1 when no
+ * support at all: the reference replaces its best only on strictly more support, :1383), best_inliers[m] (optional) its 0/1 mask =
+ * low_innov_inliers.  The state is not modified. */
+SRK_API int srk_ekf_ransac_consensus_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z,
+                                              double meas_var, const srk_ekf_camera* camera, double max_divergence_pix, int32_t* support, int32_t* best,
+                                              unsigned char* best_inliers);
+
 /* One-shot forms with host buffers (upload, operate, download). */
 SRK_API int srk_ekf_update(void* h, int64_t n, int64_t m, double* P, double* x, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s,
                            const double* z, const double* h_pred, double meas_var);
 SRK_API int srk_ekf_predict(void* h, int64_t n, double* P, const double* F13, const double* GQGt13);
 
-/* Kernel-family timing (CUDA events on the handle's stream): "pht", "innov", "chol", "trsm", "syrk", "state", "predict". */
+/* Kernel-family timing (CUDA events on the handle's stream): "pht", "innov", "chol", "trsm", "syrk", "state", "predict", "ransac". */
 SRK_API int srk_ekf_set_timing(void* h, int enabled);
 SRK_API int srk_ekf_get_timing(void* h, const char* name, double* ms_total, int64_t* count);
 SRK_API int64_t srk_ekf_launches(void* h);

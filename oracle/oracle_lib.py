@@ -282,6 +282,33 @@ def ekf_update(P, x, Hcam, Hpt, pt_off, z, hpred, meas_var, fix_symmetry=True):
     return rc == 0, np.array(Pn), xn, sec.value
 
 
+def ekf_camera(fx_pix, fy_pix, cx, cy, dx_mm, dy_mm, k1, k2, enable_distortion=True):
+    return np.array([fx_pix, fy_pix, cx, cy, dx_mm, dy_mm, k1, k2, 1.0 if enable_distortion else 0.0], dtype=np.float64)
+
+
+def ekf_project(x, pt_off, s, cam9):
+    """ProjectInternalSalientPoint (EKF.cpp:2947-2958) of every listed salient point at state x -> [m, 2] distorted pixels."""
+    xs = np.ascontiguousarray(x, dtype=np.float64); off = np.ascontiguousarray(pt_off, dtype=np.int64)
+    out = np.zeros((len(off), 2))
+    lib().srk_oracle_ekf_ransac(C.c_int64(len(xs)), C.c_int64(len(off)), None, _p(xs, C.c_double), None, None, _p(off, C.c_int64), C.c_int(s), None, C.c_double(0.0),
+                                _p(np.ascontiguousarray(cam9), C.c_double), C.c_double(0.0), None, None, _p(out, C.c_double))
+    return out
+
+
+def ekf_ransac(P, x, Hcam, Hpt, pt_off, z, meas_var, cam9, max_divergence_pix):
+    """OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391).  Returns (best, support[m], best_inliers[m])."""
+    Pn = np.asfortranarray(np.array(P, dtype=np.float64)); xs = np.ascontiguousarray(x, dtype=np.float64)
+    Hc = np.ascontiguousarray(Hcam, dtype=np.float64); Hp = np.ascontiguousarray(Hpt, dtype=np.float64)
+    off = np.ascontiguousarray(pt_off, dtype=np.int64); zz = np.ascontiguousarray(z, dtype=np.float64)
+    m = len(off); s = Hp.shape[1]
+    support = np.zeros(m, dtype=np.int32); inl = np.zeros(m, dtype=np.uint8)
+    cam = np.ascontiguousarray(cam9, dtype=np.float64)
+    best = lib().srk_oracle_ekf_ransac(C.c_int64(len(xs)), C.c_int64(m), Pn.ctypes.data_as(C.POINTER(C.c_double)), _p(xs, C.c_double), _p(Hc, C.c_double),
+                                       _p(Hp, C.c_double), _p(off, C.c_int64), C.c_int(s), _p(zz, C.c_double), C.c_double(meas_var), _p(cam, C.c_double),
+                                       C.c_double(max_divergence_pix), _p(support, C.c_int32), inl.ctypes.data_as(C.POINTER(C.c_ubyte)), None)
+    return int(best), support, inl
+
+
 def ekf_predict(P, F13, GQGt13, fix_symmetry=True):
     Pn = np.asfortranarray(np.array(P, dtype=np.float64))
     F = np.asfortranarray(np.array(F13, dtype=np.float64)); Q = np.asfortranarray(np.array(GQGt13, dtype=np.float64))

@@ -9,6 +9,7 @@
 #include "srk_oracle_ba.hpp"
 #include "srk_oracle_scene.hpp"
 #include "srk_oracle_ekf.hpp"
+#include "srk_oracle_ekf_ransac.hpp"
 
 using namespace srk_oracle;
 
@@ -321,6 +322,19 @@ int srk_oracle_ekf_update(int64_t n, int64_t m, double* P, double* x, const doub
     std::memcpy(P, Pm.d.data(), sizeof(double) * (size_t)n * (size_t)n);
     std::memcpy(x, xs.data(), sizeof(double) * (size_t)n);
     return ok ? 0 : 1;
+}
+// OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391).  cam9 = {fx_pix, fy_pix, cx, cy, dx_mm, dy_mm, k1, k2, enable_distortion}.
+// Returns the winning hypothesis or -1.  project_only != 0: just fills hd_out[2m] with the projections at the given state.
+int srk_oracle_ekf_ransac(int64_t n, int64_t m, const double* P, const double* x, const double* Hcam, const double* Hpt, const int64_t* pt_off, int s, const double* z,
+                          double meas_var, const double* cam9, double max_divergence_pix, int32_t* support, unsigned char* best_inliers, double* hd_out) {
+    EkfCamera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8] != 0.0 ? 1 : 0};
+    std::vector<double> xs(x, x + n);
+    if (hd_out != nullptr)
+        for (int64_t i = 0; i < m; ++i) EkfProjectSalientPoint(cam, xs.data(), xs.data() + pt_off[i], s, hd_out + 2 * i);
+    if (P == nullptr) return -1;
+    EkfMat Pm((size_t)n, (size_t)n);
+    std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);
+    return EkfRansacConsensus(xs, Pm, m, Hcam, Hpt, pt_off, s, z, meas_var, cam, max_divergence_pix, support, best_inliers);
 }
 int srk_oracle_ekf_predict(int64_t n, double* P, const double* F13, const double* GQGt13, int fix_symmetry) {
     EkfMat Pm((size_t)n, (size_t)n);

@@ -199,6 +199,196 @@ __global__ void k_ekf_predict_vm(int n, double* __restrict__ P, const double* __
     for (int i = 0; i < kCam; ++i) { P[(size_t)c * n + i] = res[i]; P[(size_t)i * n + c] = res[i]; }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 1-point RANSAC hypothesis scoring (OnePointRansac_GetConsensusMatches, EKF.cpp:1271-1391), all m hypotheses at once.
+// Hypothesis i integrates ONLY matched point i into the state: S_i (2x2) = Hx Pxx Hx^T + mid + mid^T + Hy Pyy Hy^T + R (:1321-1326),
+// x_i = x + (P[:, cam] Hx^T + P[:, pt_i] Hy^T) S_i^-1 (z_i - h_i) (:1331-1347), and its support is the number of matched points j
+// whose projection under x_i lands within max_divergence pixels of their corner (:1349-1381).  The reference forms the whole
+// n-vector x_i per hypothesis (m * n * 2 * (13 + s) multiply-adds and m^2 projections, one after the other); only the camera part
+// and point j's own s components of x_i enter projection j, so the work is  m  small per-hypothesis solves (k_ransac_hyp)  and
+// m^2 independent (s x (13 + s)) products + projections (k_ransac_support), which read every s x s block of P exactly once.
+struct EkfCam { double fx, fy, cx, cy, dx, dy, k1, k2; int distort; };
+
+__device__ __forceinline__ void ekf_rot_from_quat(const double* q, double (&R)[3][3]) {   // quat.cpp:75-91
+    R[0][0] = q[0] * q[0] + q[1] * q[1] - q[2] * q[2] - q[3] * q[3];
+    R[0][1] = 2 * (q[1] * q[2] - q[0] * q[3]);
+    R[0][2] = 2 * (q[1] * q[3] + q[0] * q[2]);
+    R[1][0] = 2 * (q[1] * q[2] + q[0] * q[3]);
+    R[1][1] = q[0] * q[0] - q[1] * q[1] + q[2] * q[2] - q[3] * q[3];
+    R[1][2] = 2 * (q[2] * q[3] - q[0] * q[1]);
+    R[2][0] = 2 * (q[1] * q[3] - q[0] * q[2]);
+    R[2][1] = 2 * (q[2] * q[3] + q[0] * q[1]);
+    R[2][2] = q[0] * q[0] - q[1] * q[1] - q[2] * q[2] + q[3] * q[3];
+}
+// ProjectInternalSalientPoint (EKF.cpp:2947-2958) with the camera rotation already formed: A.22 / A.21 (scaled by the inverse
+// distance), pinhole (:3021-3022), radial distortion (:2960-3005; the closed-form cube roots use the reference's float exponent).
+template <int S>
+__device__ __forceinline__ void ekf_project(const EkfCam& c, const double* pos, const double (&R)[3][3], const double* sp, double& h0, double& h1) {
+    double v[3];
+    if (S == 3) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = sp[k] - pos[k];
+    } else {
+        const double cos_th = cos(sp[3]), sin_th = sin(sp[3]), cos_ph = cos(sp[4]), sin_ph = sin(sp[4]);
+        const double m[3] = {cos_ph * sin_th, -sin_ph, cos_ph * cos_th};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = sp[5] * (sp[k] - pos[k]) + m[k];
+    }
+    double pc[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) pc[r] = R[0][r] * v[0] + R[1][r] * v[1] + R[2][r] * v[2];
+    const double hu0 = c.cx - c.fx * pc[0] / pc[2], hu1 = c.cy - c.fy * pc[1] / pc[2];
+    if (!c.distort) { h0 = hu0; h1 = hu1; return; }
+    const double ru = sqrt((c.dx * (hu0 - c.cx)) * (c.dx * (hu0 - c.cx)) + (c.dy * (hu1 - c.cy)) * (c.dy * (hu1 - c.cy)));
+    double rd;
+    if (c.k2 != 0) {           // single real root of the increasing quintic rd + k1 rd^3 + k2 rd^5 = ru (Eigen PolynomialSolver in the reference)
+        rd = ru;
+        for (int it = 0; it < 60; ++it) {
+            const double r2 = rd * rd;
+            const double f = rd + c.k1 * r2 * rd + c.k2 * r2 * r2 * rd - ru;
+            const double df = 1 + 3 * c.k1 * r2 + 5 * c.k2 * r2 * r2;
+            const double step = f / df;
+            rd -= step;
+            if (fabs(step) <= 1e-17 * fabs(rd)) break;
+        }
+    } else if (c.k1 == 0) {
+        rd = ru;
+    } else {
+        const double third = (double)(1.0f / 3);
+        const double e = pow(9 * c.k1 * c.k1 * ru + sqrt(3 * c.k1 * c.k1 * c.k1 * (4 + 27 * c.k1 * ru * ru)), third);
+        rd = (-2 * pow(3.0, third) * c.k1 + pow(2.0, third) * e * e) / (pow(6.0, 2.0 / 3) * c.k1 * e);
+    }
+    const double stretch = 1 + c.k1 * (rd * rd) + c.k2 * (rd * rd) * (rd * rd);
+    h0 = c.cx + (hu0 - c.cx) / stretch;
+    h1 = c.cy + (hu1 - c.cy) / stretch;
+}
+
+// hyp[i] = { u[13] = Hx^T w, v[S] = Hy^T w, dcam[13] = Pxx u + Pxy_i v },  w = S_i^-1 (z_i - h_i).  One thread per hypothesis.
+constexpr int kHypStride = 13 + 6 + 13;
+template <int S>
+__global__ void __launch_bounds__(128) k_ransac_hyp(int n, int m, const double* __restrict__ P, const double* __restrict__ x, const double* __restrict__ Hcam,
+                                                    const double* __restrict__ Hpt, const int64_t* __restrict__ off, const double* __restrict__ z, double meas_var,
+                                                    EkfCam cam, double* __restrict__ hyp) {
+    __shared__ double Pxx[kCam * kCam];
+    for (int e = threadIdx.x; e < kCam * kCam; e += blockDim.x) Pxx[e] = P[(size_t)(e / kCam) * n + (e % kCam)];   // Pxx[c*13 + r] = P(r, c)
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double* Hx = Hcam + (size_t)(2 * i) * kCam;
+    const double* Hy = Hpt + (size_t)(2 * i) * S;
+    const size_t oi = (size_t)off[i];
+    double hx[2][kCam], hy[2][S];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int c = 0; c < kCam; ++c) hx[a][c] = Hx[a * kCam + c];
+#pragma unroll
+        for (int c = 0; c < S; ++c) hy[a][c] = Hy[a * S + c];
+    }
+    // A = Pxx Hx^T (13 x 2),  B = Pxy Hy^T (13 x 2),  Cc = Pyy Hy^T (S x 2)
+    double A[kCam][2], B[kCam][2], Cc[S][2];
+#pragma unroll
+    for (int r = 0; r < kCam; ++r)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < kCam; ++c) t += Pxx[c * kCam + r] * hx[a][c];
+            A[r][a] = t;
+            double t2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < S; ++c) t2 += P[(oi + c) * (size_t)n + r] * hy[a][c];
+            B[r][a] = t2;
+        }
+#pragma unroll
+    for (int r = 0; r < S; ++r)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < S; ++c) t += P[(oi + c) * (size_t)n + oi + r] * hy[a][c];
+            Cc[r][a] = t;
+        }
+    double Sm[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            double t1 = 0.0, mab = 0.0, mba = 0.0, t3 = 0.0;
+#pragma unroll
+            for (int r = 0; r < kCam; ++r) { t1 += hx[a][r] * A[r][b]; mab += hx[a][r] * B[r][b]; mba += hx[b][r] * B[r][a]; }
+#pragma unroll
+            for (int r = 0; r < S; ++r) t3 += hy[a][r] * Cc[r][b];
+            Sm[a][b] = t1 + mab + mba + t3 + (a == b ? meas_var : 0.0);
+        }
+    const double idet = 1.0 / (Sm[0][0] * Sm[1][1] - Sm[0][1] * Sm[1][0]);
+    double R[3][3];
+    ekf_rot_from_quat(x + 3, R);
+    double sp[S];
+#pragma unroll
+    for (int c = 0; c < S; ++c) sp[c] = x[oi + c];
+    double h0, h1;
+    ekf_project<S>(cam, x, R, sp, h0, h1);
+    const double r0 = z[2 * i] - h0, r1 = z[2 * i + 1] - h1;
+    const double w0 = (Sm[1][1] * r0 - Sm[0][1] * r1) * idet, w1 = (-Sm[1][0] * r0 + Sm[0][0] * r1) * idet;
+    double* out = hyp + (size_t)i * kHypStride;
+#pragma unroll
+    for (int c = 0; c < kCam; ++c) out[c] = hx[0][c] * w0 + hx[1][c] * w1;                       // u
+#pragma unroll
+    for (int c = 0; c < S; ++c) out[kCam + c] = hy[0][c] * w0 + hy[1][c] * w1;                    // v
+#pragma unroll
+    for (int r = 0; r < kCam; ++r) out[kCam + 6 + r] = (A[r][0] + B[r][0]) * w0 + (A[r][1] + B[r][1]) * w1;   // camera part of K (z - h)
+}
+
+// grid (ceil(m / 256), m): CTA (jb, i) scores hypothesis i on the matched points j of its slice: point j's components of x_i are
+// x_j + P[j.., cam] u_i + P[j.., pt_i] v_i (threads along j: every P column is read as one contiguous run), then the projection.
+template <int S>
+__global__ void __launch_bounds__(256) k_ransac_support(int n, int m, const double* __restrict__ P, const double* __restrict__ x, const int64_t* __restrict__ off,
+                                                        const double* __restrict__ z, EkfCam cam, double max_div, const double* __restrict__ hyp,
+                                                        int* __restrict__ support, unsigned* __restrict__ bits, int words) {
+    __shared__ double sh[kHypStride];
+    __shared__ double camn[kCam];
+    __shared__ int cnt;
+    const int i = blockIdx.y;
+    if (threadIdx.x < kHypStride) sh[threadIdx.x] = hyp[(size_t)i * kHypStride + threadIdx.x];
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    if (threadIdx.x < kCam) camn[threadIdx.x] = x[threadIdx.x] + sh[kCam + 6 + threadIdx.x];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t oi = (size_t)off[i];
+    bool inl = false;
+    if (j < m) {
+        const size_t oj = (size_t)off[j];
+        double sp[S];
+#pragma unroll
+        for (int r = 0; r < S; ++r) {
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < kCam; ++c) t += P[(size_t)c * n + oj + r] * sh[c];
+            double t2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < S; ++c) t2 += P[(oi + c) * (size_t)n + oj + r] * sh[kCam + c];
+            sp[r] = x[oj + r] + (t + t2);
+        }
+        double R[3][3];
+        ekf_rot_from_quat(camn + 3, R);
+        double h0, h1;
+        ekf_project<S>(cam, camn, R, sp, h0, h1);
+        const double d0 = z[2 * j] - h0, d1 = z[2 * j + 1] - h1;
+        inl = sqrt(d0 * d0 + d1 * d1) < max_div;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, inl);
+    if ((threadIdx.x & 31) == 0) {
+        const int wj = j >> 5;
+        if (wj < words) bits[(size_t)i * words + wj] = bal;
+        if (bal) atomicAdd(&cnt, __popc(bal));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && cnt > 0) atomicAdd(&support[i], cnt);
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 struct ErrSink { ErrSink& operator=(const std::string& s) { srk_internal_set_error(s.c_str()); return *this; } ErrSink& operator=(const char* s) { srk_internal_set_error(s); return *this; } };
 ErrSink g_ekf_error;
@@ -219,19 +409,20 @@ struct DBuf {
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
-const char* kEkfFam[] = {"pht", "innov", "chol", "trsm", "syrk", "state", "predict"};
-enum { E_PHT = 0, E_INNOV, E_CHOL, E_TRSM, E_SYRK, E_STATE, E_PREDICT, E_COUNT };
+const char* kEkfFam[] = {"pht", "innov", "chol", "trsm", "syrk", "state", "predict", "ransac"};
+enum { E_PHT = 0, E_INNOV, E_CHOL, E_TRSM, E_SYRK, E_STATE, E_PREDICT, E_RANSAC, E_COUNT };
 
 struct Ekf {
     int device = 0;
     cudaStream_t own = nullptr, st = nullptr;
     int64_t n = 0;
     DBuf P, x, PHt, S, ws, w, Hcam, Hpt, off, z, h, aux, tmp, neg, info, small;
+    DBuf r_hyp, r_support, r_bits;   // 1-point RANSAC scoring: per-hypothesis vectors, support counts, inlier bit rows
     int64_t launches = 0;
     bool timing = false;
     std::vector<cudaEvent_t> pend[E_COUNT];
-    double total[E_COUNT] = {0, 0, 0, 0, 0, 0, 0};
-    int64_t count[E_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    double total[E_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t count[E_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 struct EScope {
     Ekf& e; int f; cudaEvent_t b = nullptr;
@@ -362,6 +553,64 @@ int predict_resident(Ekf& e, const double* F13, const double* GQGt13, const doub
     return SRK_OK;
 }
 
+
+int ransac_consensus(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int s, const double* z, double meas_var, const srk_ekf_camera* cp,
+                     double max_div, int32_t* support_out, int32_t* best_out, unsigned char* best_inliers) {
+    if (e.n <= 0) { g_ekf_error = "srk_ekf_ransac_consensus_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
+    if (m <= 0 || Hcam == nullptr || Hpt == nullptr || pt_off == nullptr || z == nullptr || cp == nullptr || (s != 3 && s != 6)) {
+        g_ekf_error = "bad consensus arguments (s must be 3 or 6)"; return SRK_E_INVALID_ARG;
+    }
+    for (int64_t i = 0; i < m; ++i) if (pt_off[i] < kCam || pt_off[i] + s > e.n) { g_ekf_error = "salient point offset out of range"; return SRK_E_INVALID_ARG; }
+    EKF_CUDA(cudaSetDevice(e.device));
+    const int n = (int)e.n, mi = (int)m, m2 = (int)(2 * m);
+    const int words = (mi + 31) / 32;
+    cudaStream_t st = e.st;
+    EKF_CUDA(e.Hcam.ensure(sizeof(double) * (size_t)m2 * kCam)); EKF_CUDA(e.Hpt.ensure(sizeof(double) * (size_t)m2 * s));
+    EKF_CUDA(e.off.ensure(sizeof(int64_t) * (size_t)m)); EKF_CUDA(e.z.ensure(sizeof(double) * m2));
+    EKF_CUDA(e.r_hyp.ensure(sizeof(double) * (size_t)m * kHypStride)); EKF_CUDA(e.r_support.ensure(sizeof(int) * (size_t)m));
+    EKF_CUDA(e.r_bits.ensure(sizeof(unsigned) * (size_t)m * words));
+    EKF_CUDA(cudaMemcpyAsync(e.Hcam.p, Hcam, sizeof(double) * (size_t)m2 * kCam, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.Hpt.p, Hpt, sizeof(double) * (size_t)m2 * s, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.off.p, pt_off, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.z.p, z, sizeof(double) * m2, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemsetAsync(e.r_support.p, 0, sizeof(int) * (size_t)m, st));
+    EkfCam cam{cp->fx_pix, cp->fy_pix, cp->cx, cp->cy, cp->dx_mm, cp->dy_mm, cp->k1, cp->k2, cp->enable_distortion != 0 ? 1 : 0};
+    {
+        EScope sc(e, E_RANSAC);
+        const dim3 gs((mi + 255) / 256, mi);
+        if (s == 3) {
+            k_ransac_hyp<3><<<(mi + 127) / 128, 128, 0, st>>>(n, mi, e.P.as<double>(), e.x.as<double>(), e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(),
+                                                             e.z.as<double>(), meas_var, cam, e.r_hyp.as<double>());
+            k_ransac_support<3><<<gs, 256, 0, st>>>(n, mi, e.P.as<double>(), e.x.as<double>(), e.off.as<int64_t>(), e.z.as<double>(), cam, max_div, e.r_hyp.as<double>(),
+                                                    e.r_support.as<int>(), e.r_bits.as<unsigned>(), words);
+        } else {
+            k_ransac_hyp<6><<<(mi + 127) / 128, 128, 0, st>>>(n, mi, e.P.as<double>(), e.x.as<double>(), e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(),
+                                                             e.z.as<double>(), meas_var, cam, e.r_hyp.as<double>());
+            k_ransac_support<6><<<gs, 256, 0, st>>>(n, mi, e.P.as<double>(), e.x.as<double>(), e.off.as<int64_t>(), e.z.as<double>(), cam, max_div, e.r_hyp.as<double>(),
+                                                    e.r_support.as<int>(), e.r_bits.as<unsigned>(), words);
+        }
+        e.launches += 2;
+    }
+    std::vector<int32_t> sup((size_t)m);
+    EKF_CUDA(cudaMemcpyAsync(sup.data(), e.r_support.p, sizeof(int) * (size_t)m, cudaMemcpyDeviceToHost, st));
+    EKF_CUDA(cudaStreamSynchronize(st));
+    int best = -1; int32_t best_cnt = 0;
+    for (int64_t i = 0; i < m; ++i) if (sup[(size_t)i] > best_cnt) { best_cnt = sup[(size_t)i]; best = (int)i; }   // strictly more: the earliest maximum (EKF.cpp:1383)
+    if (support_out != nullptr) std::memcpy(support_out, sup.data(), sizeof(int32_t) * (size_t)m);
+    if (best_out != nullptr) *best_out = best;
+    if (best_inliers != nullptr) {
+        std::memset(best_inliers, 0, (size_t)m);
+        if (best >= 0) {
+            std::vector<unsigned> row((size_t)words);
+            EKF_CUDA(cudaMemcpyAsync(row.data(), e.r_bits.as<unsigned>() + (size_t)best * words, sizeof(unsigned) * (size_t)words, cudaMemcpyDeviceToHost, st));
+            EKF_CUDA(cudaStreamSynchronize(st));
+            for (int64_t j = 0; j < m; ++j) best_inliers[j] = (row[(size_t)(j >> 5)] >> (j & 31)) & 1u;
+        }
+    }
+    EKF_CUDA(cudaGetLastError());
+    return SRK_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -423,6 +672,11 @@ int srk_ekf_get_state(void* h, double* P, double* x) {
 int srk_ekf_predict_resident(void* h, const double* F13, const double* GQGt13, const double* cam_state_new) {
     if (h == nullptr) return SRK_E_INVALID_ARG;
     return predict_resident(*(Ekf*)h, F13, GQGt13, cam_state_new);
+}
+int srk_ekf_ransac_consensus_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z, double meas_var,
+                                      const srk_ekf_camera* camera, double max_divergence_pix, int32_t* support, int32_t* best, unsigned char* best_inliers) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    return ransac_consensus(*(Ekf*)h, m, Hcam, Hpt, pt_off, s, z, meas_var, camera, max_divergence_pix, support, best, best_inliers);
 }
 int srk_ekf_update_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z, const double* h_pred,
                             double meas_var, int32_t* info) {

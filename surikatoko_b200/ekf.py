@@ -10,7 +10,7 @@ import numpy as np
 from .capi import SrkError, load_library
 
 CAM = 13
-EKF_FAMILIES = ("pht", "innov", "chol", "trsm", "syrk", "state", "predict")
+EKF_FAMILIES = ("pht", "innov", "chol", "trsm", "syrk", "state", "predict", "ransac")
 
 
 def _lib():
@@ -24,6 +24,8 @@ def _lib():
         L.srk_ekf_predict_resident.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.srk_ekf_update_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double,
                                               C.POINTER(C.c_int32)]
+        L.srk_ekf_ransac_consensus_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double,
+                                                        C.c_void_p, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
         L.srk_ekf_update.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_double]
         L.srk_ekf_predict.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -42,6 +44,20 @@ def _chk(rc):
 
 def _p(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class EkfCamera(C.Structure):
+    """srk_ekf_camera: what ProjectCameraSalientPoint / DistortPixel read (EKF.cpp:3007-3033, :2960-3005)."""
+    _fields_ = [("fx_pix", C.c_double), ("fy_pix", C.c_double), ("cx", C.c_double), ("cy", C.c_double), ("dx_mm", C.c_double), ("dy_mm", C.c_double),
+                ("k1", C.c_double), ("k2", C.c_double), ("enable_distortion", C.c_int32)]
+
+    def as_array(self):
+        return np.array([self.fx_pix, self.fy_pix, self.cx, self.cy, self.dx_mm, self.dy_mm, self.k1, self.k2, float(self.enable_distortion)])
+
+
+def scenario01_camera(enable_distortion=True, k1=0.06, k2=0.01):
+    """The camera of cpp_impl/demo-monoslam-scenario01.json: 320x240, f = 1.95 mm, 0.01 mm pixels, k1 k2 = (0.06, 0.01)."""
+    return EkfCamera(1.95 / 0.01, 1.95 / 0.01, 160.0, 120.0, 0.01, 0.01, k1, k2, 1 if enable_distortion else 0)
 
 
 class EkfEngine:
@@ -87,6 +103,16 @@ class EkfEngine:
         info = C.c_int32(0)
         _chk(self._L.srk_ekf_update_resident(self._h, off.shape[0], _p(Hc), _p(Hp), _p(off), Hp.shape[1], _p(zz), _p(hh), float(meas_var), C.byref(info)))
         return info.value
+
+    def ransac_consensus(self, Hcam, Hpt, pt_off, z, meas_var, camera, max_divergence_pix):
+        """OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391) on the resident state: (best, support[m], best_inliers[m])."""
+        Hc = np.ascontiguousarray(Hcam, dtype=np.float64); Hp = np.ascontiguousarray(Hpt, dtype=np.float64)
+        off = np.ascontiguousarray(pt_off, dtype=np.int64); zz = np.ascontiguousarray(z, dtype=np.float64)
+        m = off.shape[0]
+        support = np.zeros(m, dtype=np.int32); inl = np.zeros(m, dtype=np.uint8); best = C.c_int32(-1)
+        _chk(self._L.srk_ekf_ransac_consensus_resident(self._h, m, _p(Hc), _p(Hp), _p(off), Hp.shape[1], _p(zz), float(meas_var), C.addressof(camera),
+                                                       float(max_divergence_pix), _p(support), C.byref(best), _p(inl)))
+        return best.value, support, inl
 
     def update_host(self, P, x, Hcam, Hpt, pt_off, z, h_pred, meas_var):
         """One-shot srk_ekf_update with host buffers; P (Fortran order) and x are updated in place."""
@@ -166,3 +192,83 @@ def synthetic_ekf_frame(n_points=2000, s=3, seed=1234, cov_rank=24, pix_sigma=1.
     Q = np.diag([0.15 ** 2] * 3 + [0.01 ** 2] * 3)
     return dict(P=P, x=x, Hcam=Hcam, Hpt=Hpt, pt_off=off, z=z, h=h.reshape(-1), meas_var=pix_sigma ** 2, F=np.asfortranarray(F),
                 GQGt=np.asfortranarray(Gm @ Q @ Gm.T), n=n, m=n_points, s=s)
+
+
+def project_salient_points(x, pt_off, s, cam):
+    """numpy statement of ProjectInternalSalientPoint (EKF.cpp:2947-2958; A.22 / A.21 scaled by the inverse distance, pinhole :3021-3022,
+    radial distortion :2960-3005) used to SYNTHESISE measurements and Jacobians for the scenario below (the device has its own)."""
+    x = np.asarray(x, dtype=np.float64); off = np.asarray(pt_off, dtype=np.int64)
+    q = x[3:7]
+    R = np.array([[q[0] ** 2 + q[1] ** 2 - q[2] ** 2 - q[3] ** 2, 2 * (q[1] * q[2] - q[0] * q[3]), 2 * (q[1] * q[3] + q[0] * q[2])],
+                  [2 * (q[1] * q[2] + q[0] * q[3]), q[0] ** 2 - q[1] ** 2 + q[2] ** 2 - q[3] ** 2, 2 * (q[2] * q[3] - q[0] * q[1])],
+                  [2 * (q[1] * q[3] - q[0] * q[2]), 2 * (q[2] * q[3] + q[0] * q[1]), q[0] ** 2 - q[1] ** 2 - q[2] ** 2 + q[3] ** 2]])
+    sp = x[off[:, None] + np.arange(s)]
+    if s == 3:
+        v = sp[:, :3] - x[0:3]
+    else:
+        th, ph, rho = sp[:, 3], sp[:, 4], sp[:, 5]
+        mdir = np.stack([np.cos(ph) * np.sin(th), -np.sin(ph), np.cos(ph) * np.cos(th)], axis=1)
+        v = rho[:, None] * (sp[:, :3] - x[0:3]) + mdir
+    pc = v @ R                                  # R^T v per row
+    hu = np.stack([cam.cx - cam.fx_pix * pc[:, 0] / pc[:, 2], cam.cy - cam.fy_pix * pc[:, 1] / pc[:, 2]], axis=1)
+    if not cam.enable_distortion:
+        return hu
+    ru = np.sqrt((cam.dx_mm * (hu[:, 0] - cam.cx)) ** 2 + (cam.dy_mm * (hu[:, 1] - cam.cy)) ** 2)
+    if cam.k2 != 0:
+        rd = ru.copy()
+        for _ in range(60):
+            rd = rd - (rd + cam.k1 * rd ** 3 + cam.k2 * rd ** 5 - ru) / (1 + 3 * cam.k1 * rd ** 2 + 5 * cam.k2 * rd ** 4)
+    elif cam.k1 == 0:
+        rd = ru
+    else:
+        third = float(np.float32(1.0) / np.float32(3.0))
+        e = (9 * cam.k1 ** 2 * ru + np.sqrt(3 * cam.k1 ** 3 * (4 + 27 * cam.k1 * ru ** 2))) ** third
+        rd = (-2 * 3.0 ** third * cam.k1 + 2.0 ** third * e * e) / (6.0 ** (2.0 / 3) * cam.k1 * e)
+    stretch = 1 + cam.k1 * rd ** 2 + cam.k2 * rd ** 4
+    return np.stack([cam.cx + (hu[:, 0] - cam.cx) / stretch, cam.cy + (hu[:, 1] - cam.cy) / stretch], axis=1)
+
+
+def synthetic_ransac_frame(n_points=200, s=3, seed=7, camera=None, outlier_frac=0.2, pix_sigma=0.1, cov_rank=16):
+    """A frame for the 1-point RANSAC scoring (EKF.cpp:1271-1391) in the reference's own camera model: a camera in front of a wall of
+    salient points (XYZ, s = 3, or first-camera / azimuth / elevation / inverse-distance, s = 6); every point is matched, a fraction of
+    the corners are gross outliers (tens of pixels off).  H by central differences of project_salient_points.
+    Returns dict(P, x, Hcam, Hpt, pt_off, z, meas_var, camera, outliers)."""
+    rng = np.random.default_rng(seed)
+    cam = camera or scenario01_camera()
+    n = CAM + s * n_points
+    x = np.zeros(n)
+    x[0:3] = [0.05, -0.02, 0.1]
+    q = np.array([0.998, 0.02, -0.03, 0.015]); x[3:7] = q / np.linalg.norm(q)
+    x[7:13] = rng.normal(0, 0.01, 6)
+    g = int(np.ceil(np.sqrt(n_points)))
+    gx, gy = np.meshgrid(np.linspace(-1.2, 1.2, g), np.linspace(-0.9, 0.9, g))
+    pts = np.stack([gx.ravel()[:n_points], gy.ravel()[:n_points], 4.0 + 0.5 * rng.normal(size=n_points)], axis=1)
+    off = CAM + s * np.arange(n_points, dtype=np.int64)
+    if s == 3:
+        x[off[:, None] + np.arange(3)] = pts
+    else:
+        first = np.array([0.3, 0.1, -0.2]) + 0.05 * rng.normal(size=(n_points, 3))
+        d = pts - first
+        dist = np.linalg.norm(d, axis=1)
+        x[off[:, None] + np.arange(3)] = first
+        x[off + 3] = np.arctan2(d[:, 0], d[:, 2])            # azimuth:  m = (cos(phi) sin(theta), -sin(phi), cos(phi) cos(theta))
+        x[off + 4] = -np.arcsin(d[:, 1] / dist)              # elevation
+        x[off + 5] = 1.0 / dist
+    h = project_salient_points(x, off, s, cam)
+    Hcam = np.zeros((2 * n_points, CAM)); Hpt = np.zeros((2 * n_points, s))
+    eps = 1e-6
+    for c in range(7):
+        d = np.zeros(n); d[c] = eps
+        Hcam[:, c] = ((project_salient_points(x + d, off, s, cam) - project_salient_points(x - d, off, s, cam)) / (2 * eps)).reshape(-1)
+    for c in range(s):
+        d = np.zeros(n); d[off + c] = eps
+        Hpt[:, c] = ((project_salient_points(x + d, off, s, cam) - project_salient_points(x - d, off, s, cam)) / (2 * eps)).reshape(-1)
+    z = h + rng.normal(0, pix_sigma, h.shape)
+    outliers = rng.random(n_points) < outlier_frac
+    z[outliers] += rng.choice([-1.0, 1.0], size=(int(outliers.sum()), 2)) * rng.uniform(15.0, 40.0, size=(int(outliers.sum()), 2))
+    U = rng.normal(0, 0.01, (n, cov_rank)); U[:CAM] *= 2.0
+    P = np.asfortranarray(U @ U.T)
+    P[np.diag_indices(n)] += np.concatenate([np.full(CAM, 2e-4), np.full(n - CAM, 1e-3)])
+    if s == 6:
+        P[np.ix_(off + 5, off + 5)] *= 0.1
+    return dict(P=P, x=x, Hcam=Hcam, Hpt=Hpt, pt_off=off, z=z.reshape(-1), h=h.reshape(-1), meas_var=1.0, camera=cam, outliers=outliers, n=n, m=n_points, s=s)

@@ -1,0 +1,54 @@
+"""CPU checks of the oracle's restatement of the 1-point RANSAC scoring (oracle/srk_oracle_ekf_ransac.hpp, EKF.cpp:1271-1391) and of the
+reference's projection model (EKF.cpp:2887-3033), against an independent numpy statement and against properties the algorithm has."""
+import numpy as np
+import pytest
+
+
+@pytest.mark.parametrize("s", [3, 6])
+@pytest.mark.parametrize("dist,k1,k2", [(True, 0.06, 0.01), (True, 0.06, 0.0), (True, 0.0, 0.0), (False, 0.06, 0.01)])
+def test_projection_matches_numpy_statement(oracle, s, dist, k1, k2):
+    from surikatoko_b200 import ekf
+    cam = ekf.scenario01_camera(dist, k1, k2)
+    fr = ekf.synthetic_ransac_frame(120, s, seed=11, camera=cam)
+    hd = oracle.ekf_project(fr["x"], fr["pt_off"], s, cam.as_array())
+    assert np.max(np.abs(hd.reshape(-1) - fr["h"])) < 1e-11
+    if dist and (k1 != 0 or k2 != 0):       # the distortion pulls corners towards the principal point (stretch > 1)
+        und = oracle.ekf_project(fr["x"], fr["pt_off"], s, ekf.scenario01_camera(False).as_array())
+        c = np.array([cam.cx, cam.cy])
+        assert np.all(np.linalg.norm(hd - c, axis=1) <= np.linalg.norm(und - c, axis=1) + 1e-12)
+
+
+def test_cubic_distortion_uses_the_float_exponent(oracle):
+    """EKF.cpp:2990-2991 writes std::pow(..., 1.0f / 3): the closed-form root differs from the exact cube root at the 1e-8 level."""
+    from surikatoko_b200 import ekf
+    cam = ekf.scenario01_camera(True, 0.06, 0.0)
+    fr = ekf.synthetic_ransac_frame(60, 3, seed=2, camera=cam)
+    hd = oracle.ekf_project(fr["x"], fr["pt_off"], 3, cam.as_array())
+    und = oracle.ekf_project(fr["x"], fr["pt_off"], 3, ekf.scenario01_camera(False).as_array())
+    ru = np.sqrt((cam.dx_mm * (und[:, 0] - cam.cx)) ** 2 + (cam.dy_mm * (und[:, 1] - cam.cy)) ** 2)
+    rd = ru.copy()
+    for _ in range(80):
+        rd = rd - (rd + cam.k1 * rd ** 3 - ru) / (1 + 3 * cam.k1 * rd ** 2)
+    exact = cam.cx + (und[:, 0] - cam.cx) / (1 + cam.k1 * rd ** 2)
+    dev = np.max(np.abs(exact - hd[:, 0]))
+    assert 1e-12 < dev < 1e-5, dev
+
+
+@pytest.mark.parametrize("s", [3, 6])
+def test_consensus_properties(oracle, s):
+    from surikatoko_b200 import ekf
+    fr = ekf.synthetic_ransac_frame(90, s, seed=5, outlier_frac=0.25)
+    cam = fr["camera"].as_array()
+    best, sup, inl = oracle.ekf_ransac(fr["P"], fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["meas_var"], cam, 1.0)
+    out = fr["outliers"]
+    assert best >= 0 and not out[best]                                   # an inlier wins
+    assert sup[best] == sup.max() and best == int(np.argmax(sup))        # the earliest maximum (strictly-more rule, :1383)
+    assert np.all(inl[out] == 0) and inl[~out].sum() >= 0.9 * (~out).sum()
+    assert np.all(sup[out] <= 2)                                         # a gross outlier drags the state away from everybody else
+    # exact corners, no outliers: every hypothesis leaves the state where it is and everybody agrees
+    z0 = oracle.ekf_project(fr["x"], fr["pt_off"], s, cam).reshape(-1)
+    b0, sup0, inl0 = oracle.ekf_ransac(fr["P"], fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], z0, fr["meas_var"], cam, 1e-6)
+    assert b0 == 0 and np.all(sup0 == 90) and np.all(inl0 == 1)
+    # a threshold nobody meets: no winner
+    b1, sup1, inl1 = oracle.ekf_ransac(fr["P"], fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["meas_var"], cam, 0.0)
+    assert b1 == -1 and np.all(sup1 == 0) and np.all(inl1 == 0)

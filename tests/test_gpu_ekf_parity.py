@@ -87,3 +87,34 @@ def test_bad_arguments_fail_loudly(ekf):
     bad = fr["pt_off"].copy(); bad[0] = 5                       # inside the camera block
     with pytest.raises(sb.SrkError):
         ekf.update(fr["Hcam"], fr["Hpt"], bad, fr["z"], fr["h"], fr["meas_var"])
+
+
+@pytest.mark.parametrize("npts,s,dist,k1,k2,thr", [(150, 3, True, 0.06, 0.01, 0.25), (97, 6, True, 0.06, 0.01, 0.3), (130, 3, True, 0.06, 0.0, 0.25),
+                                                    (64, 6, False, 0.0, 0.0, 0.25), (333, 3, True, 0.06, 0.01, 1.0)])
+def test_one_point_ransac_consensus_matches_oracle(oracle, ekf, npts, s, dist, k1, k2, thr):
+    """OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391), every matched point as a hypothesis.  Support counts,
+    the winner and its inlier mask are integers: exact.  (A corner sitting within rounding of the threshold could legitimately flip;
+    the scenes are checked not to have one.)"""
+    from surikatoko_b200.ekf import scenario01_camera, synthetic_ransac_frame
+    cam = scenario01_camera(dist, k1, k2)
+    fr = synthetic_ransac_frame(npts, s, seed=21 + npts, camera=cam, outlier_frac=0.2)
+    best_ref, sup_ref, inl_ref = oracle.ekf_ransac(fr["P"], fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["meas_var"], cam.as_array(), thr)
+    ekf.set_state(fr["P"], fr["x"])
+    best, sup, inl = ekf.ransac_consensus(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["meas_var"], cam, thr)
+    assert len(np.unique(sup_ref)) > 3, "scene does not discriminate between hypotheses"
+    assert np.array_equal(sup, sup_ref), np.nonzero(sup != sup_ref)
+    assert best == best_ref and np.array_equal(inl, inl_ref)
+    P, x = ekf.get_state()
+    assert np.array_equal(P, fr["P"]) and np.array_equal(x, fr["x"]), "scoring must not modify the state"
+
+
+def test_ransac_consensus_on_a_subset_of_matched_points(oracle, ekf):
+    from surikatoko_b200.ekf import synthetic_ransac_frame
+    fr = synthetic_ransac_frame(120, 3, seed=9)
+    sel = np.arange(1, 120, 4)
+    rows = np.stack([2 * sel, 2 * sel + 1], axis=1).reshape(-1)
+    args = (fr["Hcam"][rows], fr["Hpt"][rows], fr["pt_off"][sel], fr["z"][rows], fr["meas_var"])
+    best_ref, sup_ref, inl_ref = oracle.ekf_ransac(fr["P"], fr["x"], *args, fr["camera"].as_array(), 0.3)
+    ekf.set_state(fr["P"], fr["x"])
+    best, sup, inl = ekf.ransac_consensus(*args, fr["camera"], 0.3)
+    assert best == best_ref and np.array_equal(sup, sup_ref) and np.array_equal(inl, inl_ref)
