@@ -390,6 +390,20 @@ def run_ekf(args):
             eng.update_host(P, x, *[np.ascontiguousarray(a) if isinstance(a, np.ndarray) else a for a in args_u])
         torch.cuda.synchronize()
         ms_e2e = (time.perf_counter() - t0) * 1e3
+        # 1-point RANSAC hypothesis scoring on a frame in the reference's camera model: 2000 hypotheses x 2000 projections
+        from surikatoko_b200.ekf import synthetic_ransac_frame
+        rf = synthetic_ransac_frame(npts, 3, seed=77)
+        eng.set_state(rf["P"], rf["x"])
+        r_args = (rf["Hcam"], rf["Hpt"], rf["pt_off"], rf["z"], rf["meas_var"], rf["camera"], 0.3)
+        for _ in range(2):
+            r_best, r_sup, _ = eng.ransac_consensus(*r_args)
+        eng.set_timing(True)
+        t0r = time.perf_counter()
+        for _ in range(5):
+            eng.ransac_consensus(*r_args)
+        torch.cuda.synchronize()
+        ransac_call_ms = (time.perf_counter() - t0r) * 1e3 / 5
+        tm_r = eng.get_timing()["ransac"]; eng.set_timing(False)
     if rank != 0:
         return
     f64_peak = fp64_gemm_peak(torch, dev)
@@ -425,6 +439,24 @@ def run_ekf(args):
            "roofline": {"kernel": dom, "bound": "tensor", "achieved": kernels[dom]["achieved"], "peak": f64_peak, "unit": "TFLOP/s", "frac": kernels[dom]["frac"],
                         "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (no FP64 entry in MEASURED_PEAKS.json)"},
            "kernels": kernels, "fp64_gemm_peak_tflops": f64_peak, "chol_info": int(info)}
+    if tm_r["count"]:
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+        except Exception:
+            hbm_peak = 6650.0
+        k_ms = tm_r["ms_total"] / tm_r["count"]
+        rbytes = 8.0 * rf["n"] * rf["n"]     # every s x s block of P is read once; the camera columns and the state stay in L2
+        out["ransac"] = {"what": "OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391): %d hypotheses x %d projections" % (rf["m"], rf["m"]),
+                         "kernel_ms": k_ms, "call_ms_host_buffers": ransac_call_ms, "hypotheses_per_s": rf["m"] / (k_ms * 1e-3), "bound": "hbm",
+                         "achieved": rbytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": rbytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                         "best": int(r_best), "support_of_best": int(r_sup.max())}
+        if not args.no_cpu:
+            rs = synthetic_ransac_frame(300, 3, seed=77)
+            t0c = time.perf_counter()
+            ol.ekf_ransac(rs["P"], rs["x"], rs["Hcam"], rs["Hpt"], rs["pt_off"], rs["z"], rs["meas_var"], rs["camera"].as_array(), 0.3)
+            sec = time.perf_counter() - t0c
+            out["ransac"]["cpu_baseline"] = {"value": rs["m"] / sec, "unit": "hypotheses/s", "cores": 1, "kind": "port",
+                                             "sample": "%d matched points (n = %d): per hypothesis an n x 2 gain and %d projections, as the reference does; cost ~ m * (n + m)" % (rs["m"], rs["n"], rs["m"])}
     if cpu is not None:
         out["cpu_baseline"] = cpu
     emit(out)
