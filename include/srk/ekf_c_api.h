@@ -51,6 +51,13 @@ typedef struct srk_ekf_camera {
     int32_t enable_distortion;
 } srk_ekf_camera;
 
+/* Measurement Jacobians of the matched points at the resident state: Deriv_hd_by_cam_state_and_sal_pnt batched over points
+ * (EKF.cpp:3067-3159; the reference fills a dense, zero-initialised [2m x n] H point by point before every update).  Outputs in the
+ * layout srk_ekf_update_resident / srk_ekf_ransac_consensus_resident take: Hcam [2m x 13] (velocity columns zero), Hpt [2m x s],
+ * h_pred [2m] = ProjectInternalSalientPoint (EKF.cpp:2947-2958). */
+SRK_API int srk_ekf_measurement_jacobians_resident(void* h, int64_t m, const int64_t* pt_off, int32_t s, const srk_ekf_camera* camera, double* Hcam, double* Hpt,
+                                                   double* h_pred);
+
 /* Hypothesis scoring of the 1-point RANSAC update on the resident state: OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391), every
  * matched point as a hypothesis, all at once.  Inputs as srk_ekf_update_resident (the projections are formed on the device from the
  * state: no h_pred).  support[m] (optional) = size of each hypothesis' consensus set (matched points whose projection under the

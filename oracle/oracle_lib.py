@@ -295,6 +295,16 @@ def ekf_project(x, pt_off, s, cam9):
     return out
 
 
+def ekf_jacobians(x, pt_off, s, cam9):
+    """Deriv_hd_by_cam_state_and_sal_pnt for every listed point (EKF.cpp:3067-3159): (Hcam [2m, 13], Hpt [2m, s], hd [2m])."""
+    xs = np.ascontiguousarray(x, dtype=np.float64); off = np.ascontiguousarray(pt_off, dtype=np.int64)
+    m = len(off)
+    Hc = np.zeros((2 * m, 13)); Hp = np.zeros((2 * m, s)); hd = np.zeros(2 * m)
+    lib().srk_oracle_ekf_jacobians(C.c_int64(len(xs)), C.c_int64(m), _p(xs, C.c_double), _p(off, C.c_int64), C.c_int(s), _p(np.ascontiguousarray(cam9), C.c_double),
+                                   _p(Hc, C.c_double), _p(Hp, C.c_double), _p(hd, C.c_double))
+    return Hc, Hp, hd
+
+
 def ekf_ransac(P, x, Hcam, Hpt, pt_off, z, meas_var, cam9, max_divergence_pix):
     """OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391).  Returns (best, support[m], best_inliers[m])."""
     Pn = np.asfortranarray(np.array(P, dtype=np.float64)); xs = np.ascontiguousarray(x, dtype=np.float64)

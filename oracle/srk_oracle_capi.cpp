@@ -336,6 +336,13 @@ int srk_oracle_ekf_ransac(int64_t n, int64_t m, const double* P, const double* x
     std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);
     return EkfRansacConsensus(xs, Pm, m, Hcam, Hpt, pt_off, s, z, meas_var, cam, max_divergence_pix, support, best_inliers);
 }
+// Deriv_H_by_estim_vars in the sparse form of the C ABI (EKF.cpp:3115-3159): Hcam [2m x 13], Hpt [2m x s], hd [2m]
+int srk_oracle_ekf_jacobians(int64_t n, int64_t m, const double* x, const int64_t* pt_off, int s, const double* cam9, double* Hcam, double* Hpt, double* hd) {
+    (void)n;
+    EkfCamera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8] != 0.0 ? 1 : 0};
+    for (int64_t i = 0; i < m; ++i) EkfMeasurementJacobian(cam, x, x + pt_off[i], s, Hcam + (size_t)(2 * i) * 13, Hpt + (size_t)(2 * i) * s, hd + 2 * i);
+    return 0;
+}
 int srk_oracle_ekf_predict(int64_t n, double* P, const double* F13, const double* GQGt13, int fix_symmetry) {
     EkfMat Pm((size_t)n, (size_t)n);
     std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);

@@ -79,6 +79,83 @@ inline void EkfProjectSalientPoint(const EkfCamera& c, const double* cam13, cons
     if (c.enable_distortion) EkfDistortPixel(c, hu, hd); else { hd[0] = hu[0]; hd[1] = hu[1]; }
 }
 
+// Deriv_hd_by_cam_state_and_sal_pnt (EKF.cpp:3067-3113): hd and its derivatives by the 13 camera variables (Hx[k*13 + c]) and by the
+// salient point's own s variables (Hy[k*s + c]), as the chain  hd <- hu (A.32/A.33, :2651-2687) <- hc (A.34, :2689-2704) <- state:
+// camera position A.35/A.36, quaternion A.37-A.49 through q_cw = conj(q_wc) (:2747-2817; velocity columns stay zero), point A.51-A.55 (:2819-2865).
+inline void EkfMeasurementJacobian(const EkfCamera& c, const double* cam13, const double* sp, int s, double* Hx, double* Hy, double hd[2]) {
+    EkfProjectSalientPoint(c, cam13, sp, s, hd);
+    double Rwfc[3][3];
+    EkfRotMatFromQuat(cam13 + 3, Rwfc);
+    double Rcw[3][3];
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) Rcw[r][k] = Rwfc[k][r];
+    // part2 = what Rcw multiplies (the scaled camera-frame point hc = Rcw part2), m = first-camera unity direction
+    double part2[3], mdir[3] = {0, 0, 0}, rho = 1.0;
+    if (s == 3) {
+        for (int k = 0; k < 3; ++k) part2[k] = sp[k] - cam13[k];
+    } else {
+        const double cos_th = std::cos(sp[3]), sin_th = std::sin(sp[3]), cos_ph = std::cos(sp[4]), sin_ph = std::sin(sp[4]);
+        mdir[0] = cos_ph * sin_th; mdir[1] = -sin_ph; mdir[2] = cos_ph * cos_th;
+        rho = sp[5];
+        for (int k = 0; k < 3; ++k) part2[k] = rho * (sp[k] - cam13[k]) + mdir[k];
+    }
+    double hc[3];
+    for (int r = 0; r < 3; ++r) hc[r] = Rcw[r][0] * part2[0] + Rcw[r][1] * part2[1] + Rcw[r][2] * part2[2];
+    // hd_by_hu = inverse of hu_by_hd (A.32, A.33)
+    double hd_by_hu[2][2] = {{1, 0}, {0, 1}};
+    if (c.enable_distortion) {
+        const double ax = hd[0] - c.cx, ay = hd[1] - c.cy;
+        const double rd = std::sqrt((c.dx_mm * ax) * (c.dx_mm * ax) + (c.dy_mm * ay) * (c.dy_mm * ay));   // Calc_rd, A.24 (:48-59)
+        const double stretch = 1 + c.k1 * (rd * rd) + c.k2 * (rd * rd) * (rd * rd);
+        const double kk = c.k1 + 2 * c.k2 * (rd * rd);
+        const double side = 2 * kk * ay * ax;
+        const double r00 = stretch + 2 * kk * ((c.dx_mm * ax) * (c.dx_mm * ax)), r11 = stretch + 2 * kk * ((c.dy_mm * ay) * (c.dy_mm * ay));
+        const double r10 = side * (c.dx_mm * c.dx_mm), r01 = side * (c.dy_mm * c.dy_mm);
+        const double idet = 1.0 / (r00 * r11 - r01 * r10);
+        hd_by_hu[0][0] = r11 * idet; hd_by_hu[0][1] = -r01 * idet; hd_by_hu[1][0] = -r10 * idet; hd_by_hu[1][1] = r00 * idet;
+    }
+    const double hu_by_hc[2][3] = {{-c.fx_pix / hc[2], 0.0, c.fx_pix * hc[0] / (hc[2] * hc[2])}, {0.0, -c.fy_pix / hc[2], c.fy_pix * hc[1] / (hc[2] * hc[2])}};
+    double D[2][3];   // hd_by_hc = hd_by_hu * hu_by_hc
+    for (int a = 0; a < 2; ++a) for (int k = 0; k < 3; ++k) D[a][k] = hd_by_hu[a][0] * hu_by_hc[0][k] + hd_by_hu[a][1] * hu_by_hc[1][k];
+    for (int e = 0; e < 2 * 13; ++e) Hx[e] = 0.0;
+    // camera position: hc_by_rwc = -Rcw (A.36) or -rho Rcw (A.35)
+    for (int a = 0; a < 2; ++a)
+        for (int k = 0; k < 3; ++k) {
+            double t = 0;
+            for (int r = 0; r < 3; ++r) t += D[a][r] * (-(s == 3 ? 1.0 : rho) * Rcw[r][k]);
+            Hx[a * 13 + k] = t;
+        }
+    // quaternion: q_cw = conj(q_wc); dRcw/dq_cw (A.46-A.49) applied to part2; d q_cw / d q_wc = diag(1, -1, -1, -1) (A.39)
+    const double q[4] = {cam13[3], -cam13[4], -cam13[5], -cam13[6]};
+    const double dR[4][3][3] = {
+        {{2 * q[0], -2 * q[3], 2 * q[2]}, {2 * q[3], 2 * q[0], -2 * q[1]}, {-2 * q[2], 2 * q[1], 2 * q[0]}},
+        {{2 * q[1], 2 * q[2], 2 * q[3]}, {2 * q[2], -2 * q[1], -2 * q[0]}, {2 * q[3], 2 * q[0], -2 * q[1]}},
+        {{-2 * q[2], 2 * q[1], 2 * q[0]}, {2 * q[1], 2 * q[2], 2 * q[3]}, {-2 * q[0], 2 * q[3], -2 * q[2]}},
+        {{-2 * q[3], -2 * q[0], 2 * q[1]}, {2 * q[0], -2 * q[3], 2 * q[2]}, {2 * q[1], 2 * q[2], 2 * q[3]}}};
+    for (int qi = 0; qi < 4; ++qi) {
+        double col[3];
+        for (int r = 0; r < 3; ++r) col[r] = dR[qi][r][0] * part2[0] + dR[qi][r][1] * part2[1] + dR[qi][r][2] * part2[2];
+        const double sign = qi == 0 ? 1.0 : -1.0;
+        for (int a = 0; a < 2; ++a) Hx[a * 13 + 3 + qi] = (D[a][0] * col[0] + D[a][1] * col[1] + D[a][2] * col[2]) * sign;
+    }
+    // salient point: dhc_by_dy = Rcw (A.55) or [rho Rcw | Rcw dm/dtheta | Rcw dm/dphi | Rcw (first_cam_pos - cam_pos)] (A.52-A.54)
+    double dy[3][6];
+    if (s == 3) {
+        for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) dy[r][k] = Rcw[r][k];
+    } else {
+        const double cos_th = std::cos(sp[3]), sin_th = std::sin(sp[3]), cos_ph = std::cos(sp[4]), sin_ph = std::sin(sp[4]);
+        const double dth[3] = {cos_ph * cos_th, 0.0, -cos_ph * sin_th}, dph[3] = {-sin_ph * sin_th, -cos_ph, -sin_ph * cos_th};
+        const double dp[3] = {sp[0] - cam13[0], sp[1] - cam13[1], sp[2] - cam13[2]};
+        for (int r = 0; r < 3; ++r) {
+            for (int k = 0; k < 3; ++k) dy[r][k] = rho * Rcw[r][k];
+            dy[r][3] = Rcw[r][0] * dth[0] + Rcw[r][1] * dth[1] + Rcw[r][2] * dth[2];
+            dy[r][4] = Rcw[r][0] * dph[0] + Rcw[r][1] * dph[1] + Rcw[r][2] * dph[2];
+            dy[r][5] = Rcw[r][0] * dp[0] + Rcw[r][1] * dp[1] + Rcw[r][2] * dp[2];
+        }
+    }
+    for (int a = 0; a < 2; ++a)
+        for (int k = 0; k < s; ++k) Hy[a * s + k] = D[a][0] * dy[0][k] + D[a][1] * dy[1][k] + D[a][2] * dy[2][k];
+}
+
 // OnePointRansac_GetConsensusMatches.  x [n], P [n x n] column-major; per matched point i: Hcam [2 x 13], Hpt [2 x s] (row-major
 // per observation row), pt_off[i], measured corner z[2i..2i+1].  support[i] = size of the consensus set of hypothesis i;
 // returns the winning hypothesis (-1 when every support is zero) and its inlier mask.

@@ -389,6 +389,108 @@ __global__ void __launch_bounds__(256) k_ransac_support(int n, int m, const doub
     if (threadIdx.x == 0 && cnt > 0) atomicAdd(&support[i], cnt);
 }
 
+
+// Deriv_hd_by_cam_state_and_sal_pnt for every matched point (EKF.cpp:3067-3159; chain rule A.31-A.55 as in :2651-2865): one thread per
+// point writes its two rows of Hcam [2m x 13] (velocity columns zero), Hpt [2m x S] and the projection hd -- what the reference builds
+// point by point into a dense [2m x n] H (zero-filled, :3126-3127) before every update.
+template <int S>
+__global__ void __launch_bounds__(128) k_ekf_jacobians(int m, const double* __restrict__ x, const int64_t* __restrict__ off, EkfCam c, double* __restrict__ Hcam,
+                                                       double* __restrict__ Hpt, double* __restrict__ hd_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const size_t oi = (size_t)off[i];
+    double sp[S];
+#pragma unroll
+    for (int k = 0; k < S; ++k) sp[k] = x[oi + k];
+    double pos[3] = {x[0], x[1], x[2]};
+    double Rw[3][3];
+    ekf_rot_from_quat(x + 3, Rw);
+    double h0, h1;
+    ekf_project<S>(c, pos, Rw, sp, h0, h1);
+    hd_out[2 * i] = h0; hd_out[2 * i + 1] = h1;
+    double part2[3], rho = 1.0, cos_th = 0, sin_th = 0, cos_ph = 0, sin_ph = 0;
+    if (S == 3) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) part2[k] = sp[k] - pos[k];
+    } else {
+        cos_th = cos(sp[3]); sin_th = sin(sp[3]); cos_ph = cos(sp[4]); sin_ph = sin(sp[4]);
+        const double md[3] = {cos_ph * sin_th, -sin_ph, cos_ph * cos_th};
+        rho = sp[5];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) part2[k] = rho * (sp[k] - pos[k]) + md[k];
+    }
+    double hc[3];   // Rcw(r, k) = Rw[k][r]
+#pragma unroll
+    for (int r = 0; r < 3; ++r) hc[r] = Rw[0][r] * part2[0] + Rw[1][r] * part2[1] + Rw[2][r] * part2[2];
+    double u00 = 1, u01 = 0, u10 = 0, u11 = 1;   // hd_by_hu
+    if (c.distort) {
+        const double ax = h0 - c.cx, ay = h1 - c.cy;
+        const double rd = sqrt((c.dx * ax) * (c.dx * ax) + (c.dy * ay) * (c.dy * ay));
+        const double stretch = 1 + c.k1 * (rd * rd) + c.k2 * (rd * rd) * (rd * rd);
+        const double kk = c.k1 + 2 * c.k2 * (rd * rd);
+        const double side = 2 * kk * ay * ax;
+        const double r00 = stretch + 2 * kk * ((c.dx * ax) * (c.dx * ax)), r11 = stretch + 2 * kk * ((c.dy * ay) * (c.dy * ay));
+        const double r10 = side * (c.dx * c.dx), r01 = side * (c.dy * c.dy);
+        const double idet = 1.0 / (r00 * r11 - r01 * r10);
+        u00 = r11 * idet; u01 = -r01 * idet; u10 = -r10 * idet; u11 = r00 * idet;
+    }
+    const double a00 = -c.fx / hc[2], a02 = c.fx * hc[0] / (hc[2] * hc[2]), a11 = -c.fy / hc[2], a12 = c.fy * hc[1] / (hc[2] * hc[2]);
+    double D[2][3];
+    D[0][0] = u00 * a00 + u01 * 0.0; D[0][1] = u00 * 0.0 + u01 * a11; D[0][2] = u00 * a02 + u01 * a12;
+    D[1][0] = u10 * a00 + u11 * 0.0; D[1][1] = u10 * 0.0 + u11 * a11; D[1][2] = u10 * a02 + u11 * a12;
+    double* Hx = Hcam + (size_t)(2 * i) * kCam;
+    double* Hy = Hpt + (size_t)(2 * i) * S;
+#pragma unroll
+    for (int e = 0; e < 2 * kCam; ++e) Hx[e] = 0.0;
+    const double scale = S == 3 ? 1.0 : rho;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double t = 0.0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) t += D[a][r] * (-scale * Rw[k][r]);
+            Hx[a * kCam + k] = t;
+        }
+    const double q[4] = {x[3], -x[4], -x[5], -x[6]};
+    const double dR[4][3][3] = {
+        {{2 * q[0], -2 * q[3], 2 * q[2]}, {2 * q[3], 2 * q[0], -2 * q[1]}, {-2 * q[2], 2 * q[1], 2 * q[0]}},
+        {{2 * q[1], 2 * q[2], 2 * q[3]}, {2 * q[2], -2 * q[1], -2 * q[0]}, {2 * q[3], 2 * q[0], -2 * q[1]}},
+        {{-2 * q[2], 2 * q[1], 2 * q[0]}, {2 * q[1], 2 * q[2], 2 * q[3]}, {-2 * q[0], 2 * q[3], -2 * q[2]}},
+        {{-2 * q[3], -2 * q[0], 2 * q[1]}, {2 * q[0], -2 * q[3], 2 * q[2]}, {2 * q[1], 2 * q[2], 2 * q[3]}}};
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+        double col[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) col[r] = dR[qi][r][0] * part2[0] + dR[qi][r][1] * part2[1] + dR[qi][r][2] * part2[2];
+        const double sign = qi == 0 ? 1.0 : -1.0;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) Hx[a * kCam + 3 + qi] = (D[a][0] * col[0] + D[a][1] * col[1] + D[a][2] * col[2]) * sign;
+    }
+    double dy[3][S];
+    if (S == 3) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dy[r][k] = Rw[k][r];
+    } else {
+        const double dth[3] = {cos_ph * cos_th, 0.0, -cos_ph * sin_th}, dph[3] = {-sin_ph * sin_th, -cos_ph, -sin_ph * cos_th};
+        const double dp[3] = {sp[0] - pos[0], sp[1] - pos[1], sp[2] - pos[2]};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) dy[r][k] = rho * Rw[k][r];
+            dy[r][3 % S] = Rw[0][r] * dth[0] + Rw[1][r] * dth[1] + Rw[2][r] * dth[2];
+            dy[r][4 % S] = Rw[0][r] * dph[0] + Rw[1][r] * dph[1] + Rw[2][r] * dph[2];
+            dy[r][5 % S] = Rw[0][r] * dp[0] + Rw[1][r] * dp[1] + Rw[2][r] * dp[2];
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int k = 0; k < S; ++k) Hy[a * S + k] = D[a][0] * dy[0][k] + D[a][1] * dy[1][k] + D[a][2] * dy[2][k];
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 struct ErrSink { ErrSink& operator=(const std::string& s) { srk_internal_set_error(s.c_str()); return *this; } ErrSink& operator=(const char* s) { srk_internal_set_error(s); return *this; } };
 ErrSink g_ekf_error;
@@ -554,6 +656,33 @@ int predict_resident(Ekf& e, const double* F13, const double* GQGt13, const doub
 }
 
 
+int measurement_jacobians(Ekf& e, int64_t m, const int64_t* pt_off, int s, const srk_ekf_camera* cp, double* Hcam, double* Hpt, double* h_pred) {
+    if (e.n <= 0) { g_ekf_error = "srk_ekf_measurement_jacobians_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
+    if (m <= 0 || pt_off == nullptr || cp == nullptr || Hcam == nullptr || Hpt == nullptr || h_pred == nullptr || (s != 3 && s != 6)) {
+        g_ekf_error = "bad Jacobian arguments (s must be 3 or 6)"; return SRK_E_INVALID_ARG;
+    }
+    for (int64_t i = 0; i < m; ++i) if (pt_off[i] < kCam || pt_off[i] + s > e.n) { g_ekf_error = "salient point offset out of range"; return SRK_E_INVALID_ARG; }
+    EKF_CUDA(cudaSetDevice(e.device));
+    const int mi = (int)m, m2 = (int)(2 * m);
+    cudaStream_t st = e.st;
+    EKF_CUDA(e.Hcam.ensure(sizeof(double) * (size_t)m2 * kCam)); EKF_CUDA(e.Hpt.ensure(sizeof(double) * (size_t)m2 * s));
+    EKF_CUDA(e.off.ensure(sizeof(int64_t) * (size_t)m)); EKF_CUDA(e.h.ensure(sizeof(double) * m2));
+    EKF_CUDA(cudaMemcpyAsync(e.off.p, pt_off, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, st));
+    EkfCam cam{cp->fx_pix, cp->fy_pix, cp->cx, cp->cy, cp->dx_mm, cp->dy_mm, cp->k1, cp->k2, cp->enable_distortion != 0 ? 1 : 0};
+    {
+        EScope sc(e, E_STATE);
+        if (s == 3) k_ekf_jacobians<3><<<(mi + 127) / 128, 128, 0, st>>>(mi, e.x.as<double>(), e.off.as<int64_t>(), cam, e.Hcam.as<double>(), e.Hpt.as<double>(), e.h.as<double>());
+        else k_ekf_jacobians<6><<<(mi + 127) / 128, 128, 0, st>>>(mi, e.x.as<double>(), e.off.as<int64_t>(), cam, e.Hcam.as<double>(), e.Hpt.as<double>(), e.h.as<double>());
+        e.launches += 1;
+    }
+    EKF_CUDA(cudaMemcpyAsync(Hcam, e.Hcam.p, sizeof(double) * (size_t)m2 * kCam, cudaMemcpyDeviceToHost, st));
+    EKF_CUDA(cudaMemcpyAsync(Hpt, e.Hpt.p, sizeof(double) * (size_t)m2 * s, cudaMemcpyDeviceToHost, st));
+    EKF_CUDA(cudaMemcpyAsync(h_pred, e.h.p, sizeof(double) * m2, cudaMemcpyDeviceToHost, st));
+    EKF_CUDA(cudaStreamSynchronize(st));
+    EKF_CUDA(cudaGetLastError());
+    return SRK_OK;
+}
+
 int ransac_consensus(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int s, const double* z, double meas_var, const srk_ekf_camera* cp,
                      double max_div, int32_t* support_out, int32_t* best_out, unsigned char* best_inliers) {
     if (e.n <= 0) { g_ekf_error = "srk_ekf_ransac_consensus_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
@@ -672,6 +801,10 @@ int srk_ekf_get_state(void* h, double* P, double* x) {
 int srk_ekf_predict_resident(void* h, const double* F13, const double* GQGt13, const double* cam_state_new) {
     if (h == nullptr) return SRK_E_INVALID_ARG;
     return predict_resident(*(Ekf*)h, F13, GQGt13, cam_state_new);
+}
+int srk_ekf_measurement_jacobians_resident(void* h, int64_t m, const int64_t* pt_off, int32_t s, const srk_ekf_camera* camera, double* Hcam, double* Hpt, double* h_pred) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    return measurement_jacobians(*(Ekf*)h, m, pt_off, s, camera, Hcam, Hpt, h_pred);
 }
 int srk_ekf_ransac_consensus_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z, double meas_var,
                                       const srk_ekf_camera* camera, double max_divergence_pix, int32_t* support, int32_t* best, unsigned char* best_inliers) {

@@ -26,6 +26,7 @@ def _lib():
                                               C.POINTER(C.c_int32)]
         L.srk_ekf_ransac_consensus_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double,
                                                         C.c_void_p, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
+        L.srk_ekf_measurement_jacobians_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.srk_ekf_update.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_double]
         L.srk_ekf_predict.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -103,6 +104,14 @@ class EkfEngine:
         info = C.c_int32(0)
         _chk(self._L.srk_ekf_update_resident(self._h, off.shape[0], _p(Hc), _p(Hp), _p(off), Hp.shape[1], _p(zz), _p(hh), float(meas_var), C.byref(info)))
         return info.value
+
+    def measurement_jacobians(self, pt_off, s, camera):
+        """Deriv_hd_by_cam_state_and_sal_pnt for every listed point at the resident state (EKF.cpp:3067-3159): (Hcam, Hpt, h_pred)."""
+        off = np.ascontiguousarray(pt_off, dtype=np.int64)
+        m = off.shape[0]
+        Hc = np.zeros((2 * m, CAM)); Hp = np.zeros((2 * m, s)); hp = np.zeros(2 * m)
+        _chk(self._L.srk_ekf_measurement_jacobians_resident(self._h, m, _p(off), s, C.addressof(camera), _p(Hc), _p(Hp), _p(hp)))
+        return Hc, Hp, hp
 
     def ransac_consensus(self, Hcam, Hpt, pt_off, z, meas_var, camera, max_divergence_pix):
         """OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391) on the resident state: (best, support[m], best_inliers[m])."""
@@ -269,6 +278,7 @@ def synthetic_ransac_frame(n_points=200, s=3, seed=7, camera=None, outlier_frac=
     U = rng.normal(0, 0.01, (n, cov_rank)); U[:CAM] *= 2.0
     P = np.asfortranarray(U @ U.T)
     P[np.diag_indices(n)] += np.concatenate([np.full(CAM, 2e-4), np.full(n - CAM, 1e-3)])
-    if s == 6:
-        P[np.ix_(off + 5, off + 5)] *= 0.1
+    if s == 6:      # inverse distances are known more tightly; scaled as a congruence D P D so that P stays positive definite
+        d = np.ones(n); d[off + 5] = 0.3
+        P = np.asfortranarray(P * d[:, None] * d[None, :])
     return dict(P=P, x=x, Hcam=Hcam, Hpt=Hpt, pt_off=off, z=z.reshape(-1), h=h.reshape(-1), meas_var=1.0, camera=cam, outliers=outliers, n=n, m=n_points, s=s)

@@ -118,3 +118,27 @@ def test_ransac_consensus_on_a_subset_of_matched_points(oracle, ekf):
     ekf.set_state(fr["P"], fr["x"])
     best, sup, inl = ekf.ransac_consensus(*args, fr["camera"], 0.3)
     assert best == best_ref and np.array_equal(sup, sup_ref) and np.array_equal(inl, inl_ref)
+
+
+@pytest.mark.parametrize("npts,s,dist,k1,k2", [(150, 3, True, 0.06, 0.01), (97, 6, True, 0.06, 0.01), (64, 3, True, 0.06, 0.0), (64, 6, False, 0.0, 0.0)])
+def test_batched_measurement_jacobians_match_oracle(oracle, ekf, npts, s, dist, k1, k2):
+    """Deriv_hd_by_cam_state_and_sal_pnt batched over the matched points (EKF.cpp:3067-3159), then the frame step on
+    the device's own Jacobians: consensus set and stacked update agree with the oracle fed by the oracle's Jacobians."""
+    from surikatoko_b200.ekf import scenario01_camera, synthetic_ransac_frame
+    cam = scenario01_camera(dist, k1, k2)
+    fr = synthetic_ransac_frame(npts, s, seed=31 + npts, camera=cam)
+    Hc_ref, Hp_ref, hd_ref = oracle.ekf_jacobians(fr["x"], fr["pt_off"], s, cam.as_array())
+    ekf.set_state(fr["P"], fr["x"])
+    Hc, Hp, hd = ekf.measurement_jacobians(fr["pt_off"], s, cam)
+    assert relerr(hd, hd_ref) < 1e-13 and relerr(Hc, Hc_ref) < 1e-12 and relerr(Hp, Hp_ref) < 1e-12
+    assert np.all(Hc[:, 7:] == 0.0)
+    best_ref, sup_ref, inl_ref = oracle.ekf_ransac(fr["P"], fr["x"], Hc_ref, Hp_ref, fr["pt_off"], fr["z"], fr["meas_var"], cam.as_array(), 0.3)
+    best, sup, inl = ekf.ransac_consensus(Hc, Hp, fr["pt_off"], fr["z"], fr["meas_var"], cam, 0.3)
+    assert best == best_ref and np.array_equal(sup, sup_ref) and np.array_equal(inl, inl_ref)
+    sel = np.nonzero(inl_ref)[0]                            # the low-innovation inliers feed the stacked update (EKF.cpp:1393-1440)
+    rows = np.stack([2 * sel, 2 * sel + 1], axis=1).reshape(-1)
+    ok, P_ref, x_ref, _ = oracle.ekf_update(fr["P"], fr["x"], Hc_ref[rows], Hp_ref[rows], fr["pt_off"][sel], fr["z"][rows], hd_ref[rows], fr["meas_var"])
+    assert ok
+    assert ekf.update(Hc[rows], Hp[rows], fr["pt_off"][sel], fr["z"][rows], hd[rows], fr["meas_var"]) == 0
+    P, x = ekf.get_state()
+    assert relerr(x, x_ref) < TOL and relerr(P, P_ref) < TOL
