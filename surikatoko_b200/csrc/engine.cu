@@ -95,6 +95,8 @@ bool is_close(double a, double b, double rtol = 1.0e-5, double atol = 1.0e-8) { 
 struct Engine {
     int device = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // structure pass of a bind, concurrent with the H2D copies on `stream`
+    cudaEvent_t ev_idx = nullptr;
     cudaStream_t stream = nullptr;
 
     bool bound = false, norm_failed = false, normalized = false;
@@ -108,7 +110,7 @@ struct Engine {
 
     // observations (point-major) and the camera-major copy
     Buf obs_cam, obs_pt, obs_xy, ox, oy, pt_begin, cam_cnt, cam_cursor, cam_begin, c_pt, c_x, c_y;
-    Buf chunk_cams, chunk_cnt, chunk_pts, obs_slot;
+    Buf chunk_cams, chunk_cnt, chunk_pts, obs_slot, obs_pos;
     Buf tacc;                 // K2' per-point accumulators [3N]; zero between attempts (k_backsub_finish re-zeroes what it reads)
     bool tacc_zero = false;
     int backsub_impl = 1;     // SRK_BACKSUB_IMPL=0: the point-per-half-warp kernel   // K1' structure: per-chunk camera lists, per-observation table slots (k_chunk_tables)
@@ -244,40 +246,80 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     e.cams_cur = e.cams_a.as<double>(); e.cams_try = e.cams_b.as<double>();
     e.camd_cur = e.camd_a.as<double>(); e.camd_try = e.camd_b.as<double>();
 
-    // ---- observations: H2D, validation, point CSR, camera-major copy
-    if (O > 0) {
-        SRK_CUDA(cudaMemcpyAsync(e.obs_cam.p, p->obs_cam, sizeof(int32_t) * O, cudaMemcpyHostToDevice, st));
-        SRK_CUDA(cudaMemcpyAsync(e.obs_pt.p, p->obs_point, sizeof(int32_t) * O, cudaMemcpyHostToDevice, st));
-        SRK_CUDA(cudaMemcpyAsync(e.obs_xy.p, p->obs_xy, sizeof(double) * 2 * O, cudaMemcpyHostToDevice, st));
-    }
-    if (N > 0) SRK_CUDA(cudaMemcpyAsync(e.pts_stage.p, p->points, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
-    SRK_CUDA(cudaMemcpyAsync(e.Kd.p, p->K, sizeof(double) * 9 * (e.shared_K ? 1 : M), cudaMemcpyHostToDevice, st));
-    SRK_CUDA(cudaMemsetAsync(e.flags.p, 0, sizeof(int) * 8, st));
-    SRK_CUDA(cudaMemsetAsync(e.cam_cnt.p, 0, sizeof(unsigned long long) * (M + 1), st));
-    if (O == 0) SRK_CUDA(cudaMemsetAsync(e.pt_begin.p, 0, sizeof(int64_t) * (N + 1), st));
-    srk::launch_prep_obs(st, O, N, M, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.obs_xy.as<double>(), e.f0, e.ox.as<double>(), e.oy.as<double>(),
-                         e.pt_begin.as<int64_t>(), e.cam_cnt.as<unsigned long long>(), e.flags.as<int>());
-    srk::launch_scan_counts(st, M, e.cam_cnt.as<unsigned long long>(), e.cam_begin.as<int64_t>(), e.cam_cursor.as<unsigned long long>());
-    srk::launch_scatter_by_cam(st, O, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.ox.as<double>(), e.oy.as<double>(),
-                               e.cam_cursor.as<unsigned long long>(), e.c_pt.as<int32_t>(), e.c_x.as<double>(), e.c_y.as<double>());
+    // ---- observations: H2D, validation, point CSR, camera-major copy.  The indices (8 B per observation) travel first; the whole
+    // structure pass (validation, CSR, camera histogram + scatter positions, K1' chunk tables, and further down the Schur plan) runs on
+    // the side stream while the pixels (16 B per observation), the points and K are still crossing PCIe on the main stream.
+    cudaStream_t ss = e.side_stream != nullptr ? e.side_stream : st;
+    SRK_CUDA(e.obs_pos.ensure(sizeof(unsigned) * (size_t)(O > 0 ? O : 1)));
     {
         const int64_t nch = srk::residual_chunks(O);
         SRK_CUDA(e.chunk_cams.ensure(sizeof(int) * (size_t)(nch > 0 ? nch : 1) * srk::residual_chunk_slots()));
         SRK_CUDA(e.chunk_cnt.ensure(sizeof(int) * (size_t)(nch > 0 ? nch : 1)));
         SRK_CUDA(e.chunk_pts.ensure(sizeof(int) * 2 * (size_t)(nch > 0 ? nch : 1)));
         SRK_CUDA(e.obs_slot.ensure((size_t)(O > 0 ? O : 1)));
-        srk::launch_chunk_tables(st, O, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.chunk_cams.as<int>(), e.chunk_cnt.as<int>(), e.chunk_pts.as<int>(),
-                                 e.obs_slot.as<unsigned char>());
     }
+    SRK_CUDA(cudaMemsetAsync(e.flags.p, 0, sizeof(int) * 8, st));
+    SRK_CUDA(cudaMemsetAsync(e.cam_cnt.p, 0, sizeof(unsigned long long) * (M + 1), st));
+    if (O == 0) SRK_CUDA(cudaMemsetAsync(e.pt_begin.p, 0, sizeof(int64_t) * (N + 1), st));
+    if (O > 0) {
+        SRK_CUDA(cudaMemcpyAsync(e.obs_cam.p, p->obs_cam, sizeof(int32_t) * O, cudaMemcpyHostToDevice, st));
+        SRK_CUDA(cudaMemcpyAsync(e.obs_pt.p, p->obs_point, sizeof(int32_t) * O, cudaMemcpyHostToDevice, st));
+    }
+    if (ss != st) { SRK_CUDA(cudaEventRecord(e.ev_idx, st)); SRK_CUDA(cudaStreamWaitEvent(ss, e.ev_idx, 0)); }
+    if (O > 0) SRK_CUDA(cudaMemcpyAsync(e.obs_xy.p, p->obs_xy, sizeof(double) * 2 * O, cudaMemcpyHostToDevice, st));
+    if (N > 0) SRK_CUDA(cudaMemcpyAsync(e.pts_stage.p, p->points, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
+    SRK_CUDA(cudaMemcpyAsync(e.Kd.p, p->K, sizeof(double) * 9 * (e.shared_K ? 1 : M), cudaMemcpyHostToDevice, st));
+    srk::launch_prep_index(ss, O, N, M, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.pt_begin.as<int64_t>(), e.cam_cnt.as<unsigned long long>(), e.flags.as<int>());
+    srk::launch_scan_counts(ss, M, e.cam_cnt.as<unsigned long long>(), e.cam_begin.as<int64_t>(), e.cam_cursor.as<unsigned long long>());
+    srk::launch_scatter_index(ss, O, N, M, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.cam_cursor.as<unsigned long long>(), e.c_pt.as<int32_t>(),
+                              e.obs_pos.as<unsigned>());
+    srk::launch_chunk_tables(ss, O, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.chunk_cams.as<int>(), e.chunk_cnt.as<int>(), e.chunk_pts.as<int>(),
+                             e.obs_slot.as<unsigned char>());
     e.launches += 4;
     int h_flag = 0;
-    SRK_CUDA(cudaMemcpyAsync(&h_flag, e.flags.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SRK_CUDA(cudaStreamSynchronize(st));
+    SRK_CUDA(cudaMemcpyAsync(&h_flag, e.flags.p, sizeof(int), cudaMemcpyDeviceToHost, ss));
+    SRK_CUDA(cudaStreamSynchronize(ss));
     if (h_flag != 0) {
+        cudaStreamSynchronize(st);     // the caller's buffers are still being read by the copies in flight
         set_error(h_flag & 1 ? "observation index out of range" : "observations must be sorted by (pnt_ind, frame_ind) with at most one per pair");
         return SRK_E_INVALID_ARG;
     }
 
+    // ---- plan of the tiled Schur kernel: which points fall back to the per-point kernel (long tracks, scattered cameras).
+    // Larger tiles amortise the per-tile table build and the flush of the accumulators, but a tile may only touch 12 cameras:
+    // take the largest tile size that defers (almost) no more points than the smallest one.  Structure only, once per bind.
+    SRK_CUDA(e.deferred.ensure((size_t)(N > 0 ? N : 1)));
+    e.n_deferred = 0;
+    if (N > 0) {
+        auto plan = [&](int tile, int64_t* out) -> int {
+            SRK_CUDA(cudaMemsetAsync(e.skipped_cnt.p, 0, sizeof(unsigned long long), ss));
+            srk::launch_schur_plan(ss, N, tile, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.deferred.as<unsigned char>(),
+                                   e.skipped_cnt.as<unsigned long long>());
+            e.launches += 1;
+            unsigned long long nd = 0;
+            SRK_CUDA(cudaMemcpyAsync(&nd, e.skipped_cnt.p, sizeof(nd), cudaMemcpyDeviceToHost, ss));
+            SRK_CUDA(cudaStreamSynchronize(ss));
+            *out = (int64_t)nd;
+            return SRK_OK;
+        };
+        int64_t nd_small = 0;
+        int rcp = plan(256, &nd_small);
+        if (rcp != SRK_OK) return rcp;
+        e.schur_tile_points = 256; e.n_deferred = nd_small;
+        if (e.schur_tile_fixed > 0) {
+            if (e.schur_tile_fixed != 256) { rcp = plan(e.schur_tile_fixed, &e.n_deferred); if (rcp != SRK_OK) return rcp; e.schur_tile_points = e.schur_tile_fixed; }
+        } else if (N >= 148 * 4 * 1024) {   // enough tiles to keep every SM busy for several waves
+            const int cands[2] = {1024, 512};
+            bool chosen = false;
+            for (int t : cands) {
+                int64_t nd = 0;
+                rcp = plan(t, &nd);
+                if (rcp != SRK_OK) return rcp;
+                if (nd <= nd_small + N / 1000) { e.schur_tile_points = t; e.n_deferred = nd; chosen = true; break; }
+            }
+            if (!chosen) { rcp = plan(256, &e.n_deferred); if (rcp != SRK_OK) return rcp; }   // restore the flags of the small tiling
+        }
+    }
     // ---- gauge normalisation (BA.cpp:203-247): cameras on the host (M records), points on the device
     std::vector<Pose> cams((size_t)M);
     std::memcpy(cams.data(), p->cams, sizeof(double) * 12 * (size_t)M);
@@ -310,41 +352,10 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     SRK_CUDA(cudaMemcpyAsync(e.cams_bound.p, e.cams_cur, sizeof(double) * 12 * M, cudaMemcpyDeviceToDevice, st));
     if (N > 0) SRK_CUDA(cudaMemcpyAsync(e.Xbound.p, e.X_cur, sizeof(double) * 3 * N, cudaMemcpyDeviceToDevice, st));
     srk::launch_cam_prep(st, M, e.cams_cur, e.Kd.as<double>(), e.shared_K, e.f0, e.camd_cur); e.launches += 1;
-    // ---- plan of the tiled Schur kernel: which points fall back to the per-point kernel (long tracks, scattered cameras).
-    // Larger tiles amortise the per-tile table build and the flush of the accumulators, but a tile may only touch 12 cameras:
-    // take the largest tile size that defers (almost) no more points than the smallest one.  Structure only, once per bind.
-    SRK_CUDA(e.deferred.ensure((size_t)(N > 0 ? N : 1)));
-    e.n_deferred = 0;
-    if (N > 0) {
-        auto plan = [&](int tile, int64_t* out) -> int {
-            SRK_CUDA(cudaMemsetAsync(e.skipped_cnt.p, 0, sizeof(unsigned long long), st));
-            srk::launch_schur_plan(st, N, tile, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.deferred.as<unsigned char>(),
-                                   e.skipped_cnt.as<unsigned long long>());
-            e.launches += 1;
-            unsigned long long nd = 0;
-            SRK_CUDA(cudaMemcpyAsync(&nd, e.skipped_cnt.p, sizeof(nd), cudaMemcpyDeviceToHost, st));
-            SRK_CUDA(cudaStreamSynchronize(st));
-            *out = (int64_t)nd;
-            return SRK_OK;
-        };
-        int64_t nd_small = 0;
-        int rcp = plan(256, &nd_small);
-        if (rcp != SRK_OK) return rcp;
-        e.schur_tile_points = 256; e.n_deferred = nd_small;
-        if (e.schur_tile_fixed > 0) {
-            if (e.schur_tile_fixed != 256) { rcp = plan(e.schur_tile_fixed, &e.n_deferred); if (rcp != SRK_OK) return rcp; e.schur_tile_points = e.schur_tile_fixed; }
-        } else if (N >= 148 * 4 * 1024) {   // enough tiles to keep every SM busy for several waves
-            const int cands[2] = {1024, 512};
-            bool chosen = false;
-            for (int t : cands) {
-                int64_t nd = 0;
-                rcp = plan(t, &nd);
-                if (rcp != SRK_OK) return rcp;
-                if (nd <= nd_small + N / 1000) { e.schur_tile_points = t; e.n_deferred = nd; chosen = true; break; }
-            }
-            if (!chosen) { rcp = plan(256, &e.n_deferred); if (rcp != SRK_OK) return rcp; }   // restore the flags of the small tiling
-        }
-    }
+    // the pixels have arrived by now (or arrive while the main stream waits): value half of the observation prep
+    srk::launch_prep_xy(st, O, e.obs_xy.as<double>(), e.f0, e.obs_pos.as<unsigned>(), e.ox.as<double>(), e.oy.as<double>(), e.c_x.as<double>(), e.c_y.as<double>());
+    e.launches += O > 0 ? 1 : 0;
+    SRK_CUDA(cudaStreamSynchronize(ss));
     SRK_CUDA(cudaStreamSynchronize(st));
     SRK_CUDA(cudaGetLastError());
     e.bound = true;
@@ -862,6 +873,10 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     if (const char* v = std::getenv("SRK_SCHUR_TILE")) { const int t = std::atoi(v); if (t >= 16 && t <= 4096 && t % 16 == 0) e->schur_tile_fixed = t; }
     if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; set_error("cudaStreamCreate failed"); return SRK_E_CUDA; }
     e->stream = e->own_stream;
+    if (cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_idx, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (e->side_stream != nullptr) { cudaStreamDestroy(e->side_stream); e->side_stream = nullptr; }   // everything on the main stream then
+    }
     *h = e;
     return SRK_OK;
 }
@@ -883,6 +898,8 @@ void srk_ba_destroy(void* h) {
         for (cudaEvent_t ev : e->timers[f].pending) cudaEventDestroy(ev);
         for (cudaEvent_t ev : e->timers[f].pool) cudaEventDestroy(ev);
     }
+    if (e->side_stream != nullptr) cudaStreamDestroy(e->side_stream);
+    if (e->ev_idx != nullptr) cudaEventDestroy(e->ev_idx);
     if (e->own_stream != nullptr) cudaStreamDestroy(e->own_stream);
     delete e;
 }

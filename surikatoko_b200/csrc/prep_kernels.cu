@@ -9,6 +9,54 @@
 
 namespace srk {
 
+// The structure half (indices only) and the value half (pixels) are separate kernels: the indices arrive first over PCIe and the
+// whole structure pass of a bind (CSR, camera histogram / scatter positions, chunk tables, Schur plan, solve order) runs on a side
+// stream while the 16 bytes per observation of pixel data are still in flight.
+__global__ void k_prep_index(int64_t O, int64_t N, int M, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt, int64_t* __restrict__ pt_begin,
+                             unsigned long long* __restrict__ cam_count, int* __restrict__ err_flag) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = -1;
+    if (o < O) {
+        int p = obs_pt[o];
+        c = obs_cam[o];
+        if (p < 0 || p >= N || c < 0 || c >= M) { atomicOr(err_flag, 1); c = -1; }
+        else {
+            int pp = o > 0 ? obs_pt[o - 1] : -1, pc = o > 0 ? obs_cam[o - 1] : -1;
+            if (p < pp || (p == pp && c <= pc)) atomicOr(err_flag, 2);
+            if (p != pp) for (int q = (pp < 0 ? 0 : pp + 1); q <= p; ++q) pt_begin[q] = o;
+            if (o == O - 1) for (int64_t q = p + 1; q <= N; ++q) pt_begin[q] = O;
+        }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    if (c >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cam_count[c], (unsigned long long)__popc(peers));
+}
+// camera-major position of every observation (obs_pos) and the camera-major point ids
+__global__ void k_scatter_index(int64_t O, int64_t N, int M, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt, unsigned long long* __restrict__ cursor,
+                                int32_t* __restrict__ c_pt, unsigned* __restrict__ obs_pos) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int c = o < O ? obs_cam[o] : -1;
+    const int p = o < O ? obs_pt[o] : -1;
+    if (c < 0 || c >= M || p < 0 || p >= N) c = -1;                  // invalid input is reported by k_prep_index; do not index with it
+    const unsigned peers = __match_any_sync(0xffffffffu, c);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (c >= 0 && lane == leader) base = atomicAdd(&cursor[c], (unsigned long long)__popc(peers));   // one atomic per distinct camera of the warp
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (c < 0) { if (o < O) obs_pos[o] = 0xffffffffu; return; }
+    const unsigned long long pos = base + __popc(peers & ((1u << lane) - 1));
+    c_pt[pos] = p; obs_pos[o] = (unsigned)pos;
+}
+// x/f0, y/f0 of BA.cpp:475-479, formed once, in point-major planes and in the camera-major copy
+__global__ void k_prep_xy(int64_t O, const double* __restrict__ obs_xy, double f0, const unsigned* __restrict__ obs_pos, double* __restrict__ x, double* __restrict__ y,
+                          double* __restrict__ c_x, double* __restrict__ c_y) {
+    int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= O) return;
+    const double2 xy = reinterpret_cast<const double2*>(obs_xy)[o];
+    const double xs = xy.x / f0, ys = xy.y / f0;
+    x[o] = xs; y[o] = ys;
+    const unsigned pos = obs_pos[o];
+    if (pos != 0xffffffffu) { c_x[pos] = xs; c_y[pos] = ys; }
+}
 __global__ void k_prep_obs(int64_t O, int64_t N, int M, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt,
                            const double* __restrict__ obs_xy, double f0, double* __restrict__ x, double* __restrict__ y, int64_t* __restrict__ pt_begin,
                            unsigned long long* __restrict__ cam_count, int* __restrict__ err_flag) {
@@ -89,6 +137,17 @@ static inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1
 void launch_prep_obs(cudaStream_t st, int64_t O, int64_t N, int M, const int32_t* obs_cam, const int32_t* obs_pt, const double* obs_xy, double f0,
                      double* x, double* y, int64_t* pt_begin, unsigned long long* cam_count, int* err_flag) {
     if (O > 0) k_prep_obs<<<cdiv(O, 256), 256, 0, st>>>(O, N, M, obs_cam, obs_pt, obs_xy, f0, x, y, pt_begin, cam_count, err_flag);
+}
+void launch_prep_index(cudaStream_t st, int64_t O, int64_t N, int M, const int32_t* obs_cam, const int32_t* obs_pt, int64_t* pt_begin, unsigned long long* cam_count,
+                       int* err_flag) {
+    if (O > 0) k_prep_index<<<cdiv(O, 256), 256, 0, st>>>(O, N, M, obs_cam, obs_pt, pt_begin, cam_count, err_flag);
+}
+void launch_scatter_index(cudaStream_t st, int64_t O, int64_t N, int M, const int32_t* obs_cam, const int32_t* obs_pt, unsigned long long* cursor, int32_t* c_pt,
+                          unsigned* obs_pos) {
+    if (O > 0) k_scatter_index<<<cdiv(O, 256), 256, 0, st>>>(O, N, M, obs_cam, obs_pt, cursor, c_pt, obs_pos);
+}
+void launch_prep_xy(cudaStream_t st, int64_t O, const double* obs_xy, double f0, const unsigned* obs_pos, double* x, double* y, double* c_x, double* c_y) {
+    if (O > 0) k_prep_xy<<<cdiv(O, 256), 256, 0, st>>>(O, obs_xy, f0, obs_pos, x, y, c_x, c_y);
 }
 void launch_scan_counts(cudaStream_t st, int M, const unsigned long long* cnt, int64_t* cam_begin, unsigned long long* cursor) {
     k_scan_counts<<<1, 1024, 0, st>>>(M, cnt, cam_begin, cursor);
