@@ -199,6 +199,9 @@ inline int residual_grid(int64_t O) {
 }
 
 // Upload + index construction (+ NormalizeSceneInplace when normalize != 0).
+int pick_solver(const Engine& e, const srk_ba_options* opt);
+int ensure_solve_order(Engine& e, cudaStream_t on_stream = nullptr);
+
 int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, bool normalize) {
     if (p == nullptr || p->n_cams < 0 || p->n_points < 0 || p->n_obs < 0) { set_error("null or negative-sized problem"); return SRK_E_INVALID_ARG; }
     if ((p->n_obs > 0 && (p->obs_cam == nullptr || p->obs_point == nullptr || p->obs_xy == nullptr)) || (p->n_points > 0 && p->points == nullptr) ||
@@ -213,6 +216,7 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     }
     SRK_CUDA(cudaSetDevice(e.device));
     e.bound = false;
+    e.order_ready = false;
     e.pcg.structure_valid = false;
     e.N = p->n_points; e.O = p->n_obs; e.M = (int)p->n_cams; e.shared_K = p->shared_K ? 1 : 0; e.f0 = p->f0;
     e.unity = unity; e.unity_val = unity_val;
@@ -320,6 +324,12 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
             if (!chosen) { rcp = plan(256, &e.n_deferred); if (rcp != SRK_OK) return rcp; }   // restore the flags of the small tiling
         }
     }
+    // ---- elimination order of the dense solve (camera co-visibility graph -> nested dissection, solve_order.cu): structure only, so it
+    // also runs under the copies.  Multi-GPU keeps it at the first solve (the graph is a union over ranks: an all-reduce on the main stream).
+    if (normalize && opt != nullptr && e.world <= 1 && pick_solver(e, opt) == SRK_SOLVER_DENSE_CHOLESKY) {
+        int rco = ensure_solve_order(e, ss);
+        if (rco != SRK_OK) { cudaStreamSynchronize(st); return rco; }
+    }
     // ---- gauge normalisation (BA.cpp:203-247): cameras on the host (M records), points on the device
     std::vector<Pose> cams((size_t)M);
     std::memcpy(cams.data(), p->cams, sizeof(double) * 12 * (size_t)M);
@@ -359,7 +369,6 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     SRK_CUDA(cudaStreamSynchronize(st));
     SRK_CUDA(cudaGetLastError());
     e.bound = true;
-    e.order_ready = false;
     e.S_clean = false;
     e.tacc_zero = false;
     return e.norm_failed ? 1 : SRK_OK;
@@ -441,12 +450,12 @@ int derivative_pass(Engine& e) {
 
 // Order of the reduced camera system for the sparse-factor Cholesky: camera co-visibility graph of the bound observations (union over
 // ranks, so that every rank factors in the same order and takes bit-identical decisions) -> host nested dissection (solve_order.cu).
-int ensure_solve_order(Engine& e) {
+int ensure_solve_order(Engine& e, cudaStream_t on_stream) {
     if (e.order_ready) return SRK_OK;
     e.order_ready = true;
     const int M = e.M;
     if (!e.solve_order_enabled || e.nf < 24 * 64 || M < 8) { e.order = srk::SolveOrder{}; return SRK_OK; }
-    cudaStream_t st = e.stream;
+    cudaStream_t st = on_stream != nullptr ? on_stream : e.stream;
     const size_t cells = (size_t)M * (size_t)M;
     SRK_CUDA(e.adjbuf.ensure(cells));
     SRK_CUDA(cudaMemsetAsync(e.adjbuf.p, 0, cells, st));
