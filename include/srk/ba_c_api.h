@@ -145,6 +145,12 @@ SRK_API int srk_ba_debug_derivs_and_solve_ex(void* h, double c, int32_t solver, 
                                              unsigned char* skipped, double* corrections, int32_t* pcg_iters);
 /* Resident (normalised) state as the engine holds it. */
 SRK_API int srk_ba_debug_get_state(void* h, double* points, double* cams);
+/* Host-only inspection hook of the elimination order (csrc/solve_order.cu), no device needed: n_groups groups of unknowns (one per
+ * camera: group_size[g] unknowns, consecutive), adj[g*n_groups + h] != 0 iff two groups are coupled.  Returns 0 when the natural order
+ * is kept, else the number of parts; pos[sum(group_size)] = ordered index of every unknown, *ordered_n = size with padding,
+ * part_k0 / part_k1 [32] = 64-column block ranges of the parts, *ksep = first block column of the separator. */
+SRK_API int srk_ba_debug_build_order(int32_t n_groups, const int32_t* group_size, const unsigned char* adj, int32_t* pos, int64_t* ordered_n, int32_t* part_k0,
+                                     int32_t* part_k1, int32_t* ksep);
 /* ApplyCorrections (BA.cpp:1997-2063) of `corrections` to the resident state, then ReprojError. */
 SRK_API int srk_ba_debug_apply(void* h, const double* corrections, double* err_new);
 

@@ -1088,6 +1088,23 @@ int srk_ba_solve_stats(void* h, int64_t* n_f, int64_t* block_rows, int64_t* nonz
     return SRK_OK;
 }
 
+int srk_ba_debug_build_order(int32_t n_groups, const int32_t* group_size, const unsigned char* adj, int32_t* pos, int64_t* ordered_n, int32_t* part_k0,
+                             int32_t* part_k1, int32_t* ksep) {
+    if (n_groups <= 0 || group_size == nullptr || adj == nullptr) { set_error("null argument"); return SRK_E_INVALID_ARG; }
+    std::vector<int> gs(group_size, group_size + n_groups);
+    const srk::SolveOrder o = srk::build_solve_order(n_groups, gs.data(), adj);
+    if (ordered_n != nullptr) *ordered_n = o.active ? o.np : o.n;
+    if (!o.active) {
+        if (pos != nullptr) for (int i = 0; i < o.n; ++i) pos[i] = i;
+        if (ksep != nullptr) *ksep = 0;
+        return 0;
+    }
+    if (pos != nullptr) for (int i = 0; i < o.n; ++i) pos[i] = o.pos[(size_t)i];
+    for (int p = 0; p < o.part.nparts; ++p) { if (part_k0 != nullptr) part_k0[p] = o.part.k0[p]; if (part_k1 != nullptr) part_k1[p] = o.part.k1[p]; }
+    if (ksep != nullptr) *ksep = o.part.ksep;
+    return o.part.nparts;
+}
+
 int srk_ba_solve_order(void* h, int64_t* ordered_n, int64_t* parts, int64_t* max_part_blocks, int64_t* separator_blocks) {
     if (h == nullptr) { set_error("null handle"); return SRK_E_INVALID_ARG; }
     Engine& e = *(Engine*)h;

@@ -377,3 +377,49 @@ def test_pcg_lm_trajectory(oracle, engine):
     ref, rep, out = run_pair(oracle, engine, pr, 1e-10, 4, solver=sb.SOLVER_BLOCK_PCG)
     assert rep.solver_used == sb.SOLVER_BLOCK_PCG and rep.pcg_iters_last > 0
     check_trajectory(ref, rep, pr, out, pr.f0)
+
+
+def test_ordered_solve_with_loop_closures(engine):
+    """A ring scene with a few long-range co-visibilities (loop closures): the camera graph is no longer a clean band, the nested-
+    dissection order has to route those couplings through its separator.  Ordered / partitioned solve vs capture order, same engine."""
+    import surikatoko_b200 as sb
+    from surikatoko_b200 import scenes
+    base = scenes.ring_scene(170, 4000, 6, seed=12)
+    rng = np.random.default_rng(5)
+    obs_cam = base.obs_cam.copy(); obs_xy = base.obs_xy.copy()
+    K = base.K.reshape(-1, 9)
+    ends = np.searchsorted(base.obs_point, np.arange(base.n_points), side="right") - 1
+    cand = np.nonzero((obs_cam[ends] >= 15) & (obs_cam[ends] < 25))[0]          # one revisited place: cameras 15..24 see cameras 85..97 again
+    pts = rng.choice(cand, size=min(40, len(cand)), replace=False)
+    first = np.searchsorted(base.obs_point, pts, side="left"); last = np.searchsorted(base.obs_point, pts, side="right") - 1
+    for j, a, b in zip(pts, first, last):
+        far = int(obs_cam[b] + 70 + rng.integers(0, 4))
+        if far >= base.n_cams or far <= obs_cam[b]:
+            continue                                  # keeps (pnt_ind, frame_ind) sorted and unique
+        cam = base.cams[far]; T = cam[:3]; R = cam[3:].reshape(3, 3).T       # column-major R
+        Kc = (K[0] if base.shared_K else K[far]).reshape(3, 3).T
+        pc = Kc @ (R @ base.points[j] + T)
+        if pc[2] <= 0:
+            continue
+        obs_cam[b] = far
+        obs_xy[b] = base.f0 * pc[:2] / pc[2] + rng.normal(0, 0.3, 2)
+    assert np.any(obs_cam != base.obs_cam)
+
+    def problem():
+        return sb.BAProblem(obs_cam, base.obs_point, obs_xy, base.points.copy(), base.cams.copy(), base.K, base.shared_K, base.f0)
+    opt = sb.BAOptions(err_change=1e-10, max_outer_iters=3)
+    r1 = engine.solve(problem(), opt)
+    st = engine.solve_stats()
+    assert st["parts"] >= 2, st
+    os.environ["SRK_SOLVE_ORDER"] = "0"
+    try:
+        eng_nat = sb.Engine(0)
+    finally:
+        del os.environ["SRK_SOLVE_ORDER"]
+    try:
+        r0 = eng_nat.solve(problem(), opt)
+        assert eng_nat.solve_stats()["parts"] == 0
+    finally:
+        eng_nat.close()
+    assert np.array_equal(r1.attempts[:, 2], r0.attempts[:, 2]) and r1.stop_reason == r0.stop_reason
+    assert np.all(np.abs(np.sqrt(r1.err_trace) - np.sqrt(r0.err_trace)) <= 1e-9 * np.sqrt(r0.err_trace))
