@@ -590,18 +590,24 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
         EScope sc(e, E_CHOL);
         e.launches += srk::dense_cholesky_factor(st, m2, S, lds, ws, e.info.as<int>());
     }
-    {   // Z = PHt * L^-T, right-looking over 64-column blocks; Z overwrites PHt
+    {   // Z = PHt * L^-T; Z overwrites PHt.  Right-looking over 64-column blocks INSIDE a 256-column panel, then ONE update of everything
+        // right of the panel with K = 256: a K = 64 update of the whole trailing matrix per block column re-reads and re-writes PHt
+        // m2 / 64 times (12 GB at n = 6013, 2m = 4000 -- memory-bound at 14 TFLOP/s); with the panel the trailing traffic drops fourfold.
         EScope sc(e, E_TRSM);
-        const int nblk = (m2 + 63) / 64;
-        for (int kb = 0; kb < nblk; ++kb) {
-            const int k0 = kb * 64;
-            srk::launch_block_right_solve(st, n, PHt + (size_t)k0 * ldz, ldz, srk::dense_cholesky_dinv_block(ws, kb), m2 - k0);   // the last block may be ragged
-            e.launches += 1;
-            const int rest = m2 - (k0 + 64);
-            if (rest > 0) {
-                const int kw = m2 - k0 < 64 ? m2 - k0 : 64;
-                // PHt[:, k0+64:] -= Z_k (n x 64) * L[k0+64:, k0:k0+64]^T
-                srk::launch_gemm_nt_dmma(st, n, rest, kw, PHt + (size_t)k0 * ldz, ldz, S + (size_t)k0 * lds + k0 + 64, lds, PHt + (size_t)(k0 + 64) * ldz, ldz, 0);
+        constexpr int kPanel = 256;
+        for (int p0 = 0; p0 < m2; p0 += kPanel) {
+            const int pend = m2 < p0 + kPanel ? m2 : p0 + kPanel;
+            for (int k0 = p0; k0 < pend; k0 += 64) {
+                srk::launch_block_right_solve(st, n, PHt + (size_t)k0 * ldz, ldz, srk::dense_cholesky_dinv_block(ws, k0 / 64), m2 - k0);   // the last block may be ragged
+                e.launches += 1;
+                const int rest = pend - (k0 + 64);
+                if (rest > 0) {   // the other blocks of the panel: PHt[:, k0+64:pend] -= Z_k (n x 64) * L[k0+64:pend, k0:k0+64]^T
+                    srk::launch_gemm_nt_dmma(st, n, rest, 64, PHt + (size_t)k0 * ldz, ldz, S + (size_t)k0 * lds + k0 + 64, lds, PHt + (size_t)(k0 + 64) * ldz, ldz, 0);
+                    e.launches += 1;
+                }
+            }
+            if (pend < m2) {      // PHt[:, pend:] -= Z_panel (n x 256) * L[pend:, p0:pend]^T
+                srk::launch_gemm_nt_dmma(st, n, m2 - pend, pend - p0, PHt + (size_t)p0 * ldz, ldz, S + (size_t)p0 * lds + pend, lds, PHt + (size_t)pend * ldz, ldz, 0);
                 e.launches += 1;
             }
         }
