@@ -594,7 +594,7 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
         // right of the panel with K = 256: a K = 64 update of the whole trailing matrix per block column re-reads and re-writes PHt
         // m2 / 64 times (12 GB at n = 6013, 2m = 4000 -- memory-bound at 14 TFLOP/s); with the panel the trailing traffic drops fourfold.
         EScope sc(e, E_TRSM);
-        constexpr int kPanel = 256;
+        constexpr int kPanel = 512;
         for (int p0 = 0; p0 < m2; p0 += kPanel) {
             const int pend = m2 < p0 + kPanel ? m2 : p0 + kPanel;
             for (int k0 = p0; k0 < pend; k0 += 64) {
