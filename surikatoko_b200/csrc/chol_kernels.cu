@@ -1478,7 +1478,9 @@ static void launch_syrk(cudaStream_t st, int n, double* A, int64_t ld, int kcol0
     k_syrk_dmma<64><<<g_sms * 3, SyrkCfg<64>::kThreads, SyrkCfg<64>::kSmem, st>>>(n, A, ld, kcol0, K, origin, col_end, F, nblk);
 }
 
-static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, int backward, const CholPartition* part) {
+// true when a factor with nz_tiles non-zero 64x64 tiles (diagonal included) is certain to take the sparse-factor substitution kernels
+bool dense_cholesky_trsv_is_sparse(int n, int64_t nz_tiles) { return trsv_use_sparse(n, chol_nblk(n), (int)(nz_tiles > 0x7fffffff ? 0x7fffffff : nz_tiles)); }
+static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, int backward, const CholPartition* part, bool sparse_certain) {
     set_attrs_once();
     const int nblk = chol_nblk(n);
     int blocks = g_coop_blocks < nblk ? g_coop_blocks : nblk;
@@ -1517,6 +1519,7 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
             printf("  trsv: nblk=%d non-zero tiles=%d ops=%d sparse path=%d\n", nblk, h[0], h[1], (int)trsv_use_sparse(n, nblk, h[0]));
         }
     }
+    if (sparse_certain && n <= kTrsvSparseMaxN && !g_prof) return 1 + ((part != nullptr && part->nparts > 0) ? 1 : 0);   // the caller knows the tile count: no need to launch the dense kernel just to see it return
     int cacheF = nblk * nblk <= kTrsvFCacheMax ? 1 : 0;
     size_t smem = sizeof(double) * 2 * kTrsvOwn * NB * NB + (cacheF ? (size_t)((nblk * nblk + 15) & ~15) : 0);
     void* args[] = {(void*)&n, (void*)&L, (void*)&ld, (void*)&dinv, (void*)&b, (void*)&ybuf, (void*)&flags, (void*)&F, (void*)&epoch, (void*)&backward,
@@ -1547,8 +1550,12 @@ int dense_cholesky_stats(cudaStream_t st, int n, const double* ws, int64_t* nblk
     if (factor_flops) *factor_flops = fl;
     return 0;
 }
-int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part) { return trsv(st, n, L, ld, ws, b, 0, part); }
-int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part) { return trsv(st, n, L, ld, ws, b, 1, part); }
+int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part, bool sparse_certain) {
+    return trsv(st, n, L, ld, ws, b, 0, part, sparse_certain);
+}
+int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part, bool sparse_certain) {
+    return trsv(st, n, L, ld, ws, b, 1, part, sparse_certain);
+}
 
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -615,6 +615,7 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
                 const int* src = e.order_src.as<int>(); double* xp = e.xperm.as<double>();
                 const srk::CholPartition* part = &e.order.part;
                 const int* oi = e.order_ints.as<int>();
+                const bool sc = tiles && srk::dense_cholesky_trsv_is_sparse(np, (int64_t)e.order.l_all_tiles.size());
                 if (tiles) {   // only the tiles that can be non-zero: the factor's (symbolic) tiles are cleared, the system's are copied
                     srk::launch_zero_tiles(st, np, L, ldp, oi + e.ot_lall, (int)e.order.l_all_tiles.size());
                     srk::launch_permute_tiles(st, nf, S, ld, np, src, L, ldp, oi + e.ot_lin, (int)e.order.l_in_tiles.size()); e.launches += 2;
@@ -626,8 +627,8 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
                   e.launches += srk::dense_cholesky_factor(st, np, L, ldp, di, e.flags.as<int>() + 2, part, tiles ? e.order_pattern.as<unsigned char>() : nullptr,
                                                            tiles ? e.order.l_pattern_count : 0); }
                 { Scope s2(e, F_TRSV);
-                  e.launches += srk::dense_cholesky_forward(st, np, L, ldp, di, xp, part);
-                  e.launches += srk::dense_cholesky_backward(st, np, L, ldp, di, xp, part); }
+                  e.launches += srk::dense_cholesky_forward(st, np, L, ldp, di, xp, part, sc);
+                  e.launches += srk::dense_cholesky_backward(st, np, L, ldp, di, xp, part, sc); }
                 srk::launch_scatter_vec(st, np, src, xp, x); e.launches += 1;
                 for (int it = 0; it < refine; ++it) {
                     if (tiles) srk::launch_residual_dd_tiles(st, nf, S, ld, x, rhs, r, oi + e.ot_resptr, oi + e.ot_resent);
@@ -635,8 +636,8 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
                     e.launches += 1;
                     srk::launch_gather_vec(st, np, src, r, xp); e.launches += 1;
                     { Scope s2(e, F_TRSV);
-                      e.launches += srk::dense_cholesky_forward(st, np, L, ldp, di, xp, part);
-                      e.launches += srk::dense_cholesky_backward(st, np, L, ldp, di, xp, part); }
+                      e.launches += srk::dense_cholesky_forward(st, np, L, ldp, di, xp, part, sc);
+                      e.launches += srk::dense_cholesky_backward(st, np, L, ldp, di, xp, part, sc); }
                     srk::launch_scatter_vec(st, np, src, xp, r); e.launches += 1;
                     srk::launch_axpy1(st, nf, r, x); e.launches += 1;
                 }

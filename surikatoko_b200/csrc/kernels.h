@@ -70,8 +70,10 @@ int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
                               const unsigned char* pattern_dev = nullptr, int pattern_count = 0);
 bool dense_cholesky_pattern_ok(int n, int pattern_count, bool partitioned);
 int dense_cholesky_stats(cudaStream_t st, int n, const double* ws, int64_t* nblk, int64_t* nz_tiles, double* factor_flops);
-int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part = nullptr);
-int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part = nullptr);
+// sparse_certain: the caller knows (symbolic factorisation) that L is sparse enough for the sparse-factor kernels: the dense kernel is not launched
+bool dense_cholesky_trsv_is_sparse(int n, int64_t nz_tiles);
+int64_t dense_cholesky_forward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part = nullptr, bool sparse_certain = false);
+int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t ld, double* ws, double* b, const CholPartition* part = nullptr, bool sparse_certain = false);
 // mirror the lower triangle into the upper one
 void launch_mirror_lower(cudaStream_t st, int n, double* A, int64_t ld);
 // multi-GPU exchange of the non-zero 64x64 tiles of S only (aux_kernels.cu)
