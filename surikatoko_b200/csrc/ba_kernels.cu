@@ -784,6 +784,90 @@ __global__ void __launch_bounds__(256) k_backsub(int64_t N, int64_t O, const int
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// K2 for scenes in which a point is seen by MANY cameras (demo-circle-grid: every point in every frame).  There the per-point
+// pair enumeration is quadratic in the track length (50 cameras: 1275 pairs x 100 atomics per point) while the whole Schur
+// complement is ONE dense contraction over the points,  D = Fall^T Wall,  Fall / Wall = the rows [3N x 10M] of F_j and E_cj^-1 F_j
+// (zero where a camera does not see the point): "dense FP64 tensor work where the camera block is a real dense contraction".
+// k_schur_rows builds the rows (one warp per point: E, damping, cofactor inverse with the |det| > 1e-12 rule, F_i, W_i; the rhs terms
+// F_i^T E^-1 g_p go out as atomics, 10 per observation), launch_gemm_nt_dmma contracts them on DMMA with the K range split over the
+// SMs, k_scatter_dense_schur subtracts the lower triangle into the gauge-reduced S.
+__global__ void __launch_bounds__(128) k_schur_rows(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam,
+                                                    const double* __restrict__ J, double c, SchurSink sink, double* __restrict__ pinv, unsigned char* __restrict__ skipped,
+                                                    int M, double* __restrict__ Fall, double* __restrict__ Wall) {
+    const int lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= N) return;
+    const int64_t b = pt_begin[j], e = pt_begin[j + 1];
+    double a9[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a9[i] = 0.0;
+    for (int64_t o = b + lane; o < e; o += 32) {
+        const double rx = J[o], ry = J[O + o];
+        double jp[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+        a9[0] += jp[0] * jp[0] + jp[1] * jp[1];
+        a9[1] += jp[0] * jp[2] + jp[1] * jp[3];
+        a9[2] += jp[0] * jp[4] + jp[1] * jp[5];
+        a9[3] += jp[2] * jp[2] + jp[3] * jp[3];
+        a9[4] += jp[2] * jp[4] + jp[3] * jp[5];
+        a9[5] += jp[4] * jp[4] + jp[5] * jp[5];
+        a9[6] += jp[0] * rx + jp[1] * ry;
+        a9[7] += jp[2] * rx + jp[3] * ry;
+        a9[8] += jp[4] * rx + jp[5] * ry;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double v = a9[i];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        a9[i] = 2.0 * v;
+    }
+    double inv[6];
+    const bool ok = point_block_inverse(a9, c, inv);
+    if (lane == 0) {
+        skipped[j] = ok ? 0 : 1;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pinv[(int64_t)i * N + j] = ok ? inv[i] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) pinv[(int64_t)(6 + i) * N + j] = a9[6 + i];
+    }
+    if (!ok) return;   // rows stay zero (BA.cpp:1877-1881)
+    const double t0 = inv[0] * a9[6] + inv[1] * a9[7] + inv[2] * a9[8];
+    const double t1 = inv[1] * a9[6] + inv[3] * a9[7] + inv[4] * a9[8];
+    const double t2 = inv[2] * a9[6] + inv[4] * a9[7] + inv[5] * a9[8];
+    const int64_t ldr = (int64_t)M * kV;
+    for (int64_t o = b + lane; o < e; o += 32) {
+        const int cam = obs_cam[o];
+        double jp[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+        double* Fr = Fall + (size_t)(3 * j) * ldr + (size_t)cam * kV;
+        double* Wr = Wall + (size_t)(3 * j) * ldr + (size_t)cam * kV;
+#pragma unroll
+        for (int a = 0; a < kV; ++a) {
+            const double j0 = J[(int64_t)(8 + 2 * a) * O + o], j1 = J[(int64_t)(9 + 2 * a) * O + o];
+            const double f0 = 2.0 * (jp[0] * j0 + jp[1] * j1), f1 = 2.0 * (jp[2] * j0 + jp[3] * j1), f2 = 2.0 * (jp[4] * j0 + jp[5] * j1);
+            Fr[a] = f0; Fr[ldr + a] = f1; Fr[2 * ldr + a] = f2;
+            Wr[a] = inv[0] * f0 + inv[1] * f1 + inv[2] * f2;
+            Wr[ldr + a] = inv[1] * f0 + inv[3] * f1 + inv[4] * f2;
+            Wr[2 * ldr + a] = inv[2] * f0 + inv[4] * f1 + inv[5] * f2;
+            sink_add_rhs(sink, cam, a, f0 * t0 + f1 * t1 + f2 * t2);
+        }
+    }
+}
+// S(red(r), red(c)) += D(r, c), D = -(Fall^T Wall) as the GEMM leaves it (C -= A B^T on a zeroed C), for the lower triangle of the full
+// frame-variable space; the 7 gauge variables are skipped
+__global__ void k_scatter_dense_schur(int n_full, const double* __restrict__ D, int unity, double* __restrict__ S, int64_t ld) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, cidx = blockIdx.y;
+    if (r >= n_full || r < cidx) return;
+    const int rr = red_index(r / kV, r % kV, unity), rc = red_index(cidx / kV, cidx % kV, unity);
+    if (rr < 0 || rc < 0) return;
+    const double v = D[(size_t)cidx * n_full + r];
+    if (v != 0.0) S[(size_t)rc * ld + rr] += v;
+}
+
 // K2' with one thread per OBSERVATION (every lane of a warp load carries data: the point-per-half-warp form above leaves 6 of 16 lanes
 // idle at 10 observations per point and was bound by load latency at 58 % of the HBM peak).  A lane forms its observation's
 // contribution F_i * df[cam_i]; the lanes of one point are contiguous (observations are point-major), so a segmented shuffle
@@ -994,6 +1078,13 @@ int64_t residual_chunks(int64_t O) { return (O + kResChunk - 1) / kResChunk; }
 int residual_chunk_slots() { return kCamTabSlots; }
 void launch_chunk_tables(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, int* chunk_cams, int* chunk_cnt, int* chunk_pts, unsigned char* obs_slot) {
     if (O > 0) k_chunk_tables<<<(unsigned)residual_chunks(O), 256, 0, st>>>(O, obs_cam, obs_pt, chunk_cams, chunk_cnt, reinterpret_cast<int2*>(chunk_pts), obs_slot);
+}
+void launch_schur_rows(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
+                       double* pinv, unsigned char* skipped, int M, double* Fall, double* Wall) {
+    if (N > 0) k_schur_rows<<<cdiv(N, 4), 128, 0, st>>>(N, O, pt_begin, obs_cam, J, c, sink, pinv, skipped, M, Fall, Wall);
+}
+void launch_scatter_dense_schur(cudaStream_t st, int n_full, const double* D, int unity, double* S, int64_t ld) {
+    if (n_full > 0) k_scatter_dense_schur<<<dim3(cdiv(n_full, 128), n_full), 128, 0, st>>>(n_full, D, unity, S, ld);
 }
 void launch_backsub_obs(cudaStream_t st, int64_t N, int64_t O, const int32_t* obs_pt, const int32_t* obs_cam, const double* J, const double* df, const double* pinv,
                         const unsigned char* skipped, const double* X, double* Xtry, double* dp_out, double* tacc) {

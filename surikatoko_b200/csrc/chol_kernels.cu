@@ -1561,9 +1561,19 @@ int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t
 // ---------------------------------------------------------------------------------------------------------------------
 // General C -= A * B^T on DMMA (the TRSM and covariance updates of the EKF chain).  Same pipeline as k_syrk_dmma: operands are
 // read in [k][row] order straight from the column-major matrices, 128x128 tiles, persistent CTAs over the tile list.
-__global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int K, const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
-                                                         double* __restrict__ C, int64_t ldc, int lower_only) {
+// ksplit > 1: blockIdx.y owns the K slice [y * Kper, (y + 1) * Kper) and ADDS its product atomically (a short-and-wide product -- few
+// output tiles, long contraction -- would otherwise keep only a handful of SMs busy)
+__global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot, const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                                                         double* __restrict__ C, int64_t ldc, int lower_only, int ksplit) {
     constexpr int TILE = 128, SLD = TILE + 4, NJ = 8;
+    if (ksplit > 1) {
+        const int Kper = (((Ktot + ksplit - 1) / ksplit) + KC - 1) / KC * KC;
+        const int kb = (int)blockIdx.y * Kper;
+        if (kb >= Ktot) return;
+        A += (size_t)kb * lda; B += (size_t)kb * ldb;
+        Ktot = Ktot - kb < Kper ? Ktot - kb : Kper;
+    }
+    const int K = Ktot;
     extern __shared__ double sm[];
     double* sA = sm;
     double* sB = sm + STAGES * KC * SLD;
@@ -1633,9 +1643,15 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int K, co
                 const int row = i0 + wr + i * 8 + g;
                 const int col = j0 + wc + j * 8 + tg * 2;
                 const bool ok0 = row < m && col < n && (!lower_only || row >= col), ok1 = row < m && col + 1 < n && (!lower_only || row >= col + 1);
+                if (ksplit > 1) {
+                    if (ok0) atomicAdd(&C[(size_t)col * ldc + row], -acc[i][j][0]);
+                    if (ok1) atomicAdd(&C[(size_t)(col + 1) * ldc + row], -acc[i][j][1]);
+                    continue;
+                }
                 acc[i][j][0] = (ok0 ? C[(size_t)col * ldc + row] : 0.0) - acc[i][j][0];     // every load of the read-modify-write before the first store
                 acc[i][j][1] = (ok1 ? C[(size_t)(col + 1) * ldc + row] : 0.0) - acc[i][j][1];
             }
+        if (ksplit > 1) continue;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -1650,14 +1666,19 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int K, co
     }
 }
 // the operands need 16-byte aligned columns: lda, ldb even and base pointers 16-byte aligned (the callers guarantee it)
-void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only) {
+void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only,
+                         int allow_split_k) {
     set_attrs_once();
     static bool attr = false;
     const size_t smem = sizeof(double) * (2 * STAGES * KC * (128 + 4));
     if (!attr) { cudaFuncSetAttribute(k_gemm_nt_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
     if (m <= 0 || n <= 0 || K <= 0) return;
-    const int tiles = ((m + 127) / 128) * ((n + 127) / 128);
-    k_gemm_nt_dmma<<<tiles < g_sms ? tiles : g_sms, 256, smem, st>>>(m, n, K, A, lda, B, ldb, C, ldc, lower_only);
+    const int tm = (m + 127) / 128, tn = (n + 127) / 128;
+    const int tiles = lower_only ? tm * (tm + 1) / 2 : tm * tn;          // tiles that do work
+    int ksplit = 1;
+    if (allow_split_k && tiles < g_sms / 2 && K >= 4096) { ksplit = (2 * g_sms + tiles - 1) / tiles; const int maxs = K / 1024; if (ksplit > maxs) ksplit = maxs; if (ksplit < 1) ksplit = 1; }
+    const int gx = tm * tn < g_sms ? tm * tn : g_sms;
+    k_gemm_nt_dmma<<<dim3(gx, ksplit), 256, smem, st>>>(m, n, K, A, lda, B, ldb, C, ldc, lower_only, ksplit);
 }
 
 // X <- X * Linv^T on an (rows x 64) block column: X(r,c) = sum_{q<=c} X(r,q) * Linv(c,q).

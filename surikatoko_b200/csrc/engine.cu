@@ -112,8 +112,11 @@ struct Engine {
     // observations (point-major) and the camera-major copy
     Buf obs_cam, obs_pt, obs_xy, ox, oy, pt_begin, cam_cnt, cam_cursor, cam_begin, c_pt, c_x, c_y;
     Buf chunk_cams, chunk_cnt, chunk_pts, obs_slot, obs_pos;
+    Buf rows_F, rows_W, rows_D;   // dense-rows form of K2 (schur_dense_rows)
+    bool schur_dense_rows = false;
     Buf tacc;                 // K2' per-point accumulators [3N]; zero between attempts (k_backsub_finish re-zeroes what it reads)
     bool tacc_zero = false;
+    int schur_rows_enabled = 1;  // SRK_SCHUR_ROWS=0: never use the dense-rows form of K2
     int backsub_impl = 1;     // SRK_BACKSUB_IMPL=0: the point-per-half-warp kernel   // K1' structure: per-chunk camera lists, per-observation table slots (k_chunk_tables)
     // state: current / trial / as bound
     Buf Xa, Xb, Xbound, pts_stage, cams_a, cams_b, cams_bound, Kd, camd_a, camd_b;
@@ -331,6 +334,9 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
             if (!chosen) { rcp = plan(256, &e.n_deferred); if (rcp != SRK_OK) return rcp; }   // restore the flags of the small tiling
         }
     }
+    // dense-rows K2 when most points are left to the per-point kernel and the rows fit comfortably (2 x 3N x 10M doubles)
+    e.schur_dense_rows = e.schur_rows_enabled && N > 0 && e.n_deferred * 2 > N && e.nf <= 16384 &&
+                         (double)N * 3.0 * (double)M * 10.0 * 16.0 <= 16.0e9 && 3 * N < (int64_t)2000000000;
     // ---- elimination order of the dense solve (camera co-visibility graph -> nested dissection, solve_order.cu): structure only, so it
     // also runs under the copies.  Multi-GPU keeps it at the first solve (the graph is a union over ranks: an all-reduce on the main stream).
     if (normalize && opt != nullptr && e.world <= 1 && pick_solver(e, opt) == SRK_SOLVER_DENSE_CHOLESKY) {
@@ -559,6 +565,26 @@ int allreduce_system(Engine& e, double* S, double* rhs) {
 // K2: per-point blocks + Schur accumulation into `sink` (dense S or block-sparse blocks).
 void schur_accumulate(Engine& e, const srk::SchurSink& sink, double c) {
     cudaStream_t st = e.stream;
+    // Most points fall outside the tile kernel (long tracks: every point in every frame) and the system is dense: one DMMA contraction
+    // over all points instead of per-point pair enumeration with atomics.
+    if (e.schur_dense_rows && sink.blocks == nullptr && e.N > 0) {
+        const int nfull = e.M * 10;
+        const size_t rows = 3 * (size_t)e.N;
+        if (e.rows_F.ensure(sizeof(double) * rows * nfull) == cudaSuccess && e.rows_W.ensure(sizeof(double) * rows * nfull) == cudaSuccess &&
+            e.rows_D.ensure(sizeof(double) * (size_t)nfull * nfull) == cudaSuccess) {
+            cudaMemsetAsync(e.rows_F.p, 0, sizeof(double) * rows * nfull, st);
+            cudaMemsetAsync(e.rows_W.p, 0, sizeof(double) * rows * nfull, st);
+            cudaMemsetAsync(e.rows_D.p, 0, sizeof(double) * (size_t)nfull * nfull, st);
+            srk::launch_schur_rows(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink, e.pinv.as<double>(),
+                                   e.skipped.as<unsigned char>(), e.M, e.rows_F.as<double>(), e.rows_W.as<double>());
+            // rows_D starts at zero and the product is SUBTRACTED from it: D = -(Fall^T Wall); the scatter then adds it with the same sign convention
+            srk::launch_gemm_nt_dmma(st, nfull, nfull, (int)rows, e.rows_F.as<double>(), nfull, e.rows_W.as<double>(), nfull, e.rows_D.as<double>(), nfull, 1, 1);
+            srk::launch_scatter_dense_schur(st, nfull, e.rows_D.as<double>(), sink.unity, sink.S, sink.ld);
+            e.launches += 3;
+            return;
+        }
+        cudaGetLastError();   // not enough memory for the rows: the per-point kernels below
+    }
     if (e.schur_impl == 0)
         srk::launch_schur_mma(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink,
                               e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>());
@@ -885,6 +911,7 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     if (const char* v = std::getenv("SRK_SCHUR_IMPL")) e->schur_impl = std::atoi(v) == 1 ? 1 : 0;
     if (const char* v = std::getenv("SRK_TILE_EXCHANGE")) e->tile_exchange = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SOLVE_ORDER")) e->solve_order_enabled = std::atoi(v) != 0 ? 1 : 0;
+    if (const char* v = std::getenv("SRK_SCHUR_ROWS")) e->schur_rows_enabled = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_BACKSUB_IMPL")) e->backsub_impl = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SOLVE_TILES")) e->solve_tiles_enabled = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SCHUR_TILE")) { const int t = std::atoi(v); if (t >= 16 && t <= 4096 && t % 16 == 0) e->schur_tile_fixed = t; }

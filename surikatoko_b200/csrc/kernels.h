@@ -27,6 +27,10 @@ void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin
 // DMMA formulation of the same accumulation (schur_mma.cu); same deferral rule as the plan pass of launch_schur_tile.
 void launch_schur_mma(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
                       const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred);
+// dense-rows form of K2 (points seen by many cameras): rows of F and E^-1 F [3N x 10M] -> launch_gemm_nt_dmma -> S -= lower(D)
+void launch_schur_rows(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
+                       double* pinv, unsigned char* skipped, int M, double* Fall, double* Wall);
+void launch_scatter_dense_schur(cudaStream_t st, int n_full, const double* D, int unity, double* S, int64_t ld);
 void launch_schur_plan(cudaStream_t st, int64_t N, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, unsigned char* deferred,
                        unsigned long long* n_deferred);
 void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
@@ -55,7 +59,9 @@ void dense_cholesky_band_profile_report();
 // column-major 64x64 inverse of the kb-th diagonal block of L inside the workspace
 inline const double* dense_cholesky_dinv_block(const double* ws, int kb) { return ws + (size_t)kb * 64 * 64; }
 // C (m x n, ldc) -= A (m x K, lda) * B (n x K, ldb)^T, all column-major, DMMA 128x128 tiles; lower_only: only tiles / entries with row >= col.
-void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only);
+// allow_split_k: few output tiles and a long contraction -> the K range is split over blockIdx.y and the slices are added atomically
+void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only,
+                         int allow_split_k = 0);
 // X (rows x 64 at A, lda) <- X * Linv^T with Linv a column-major 64x64 lower-triangular inverse (right-side triangular solve of one block column)
 // ncols: how many of the 64 columns exist (the caller's matrix may end inside the last block)
 void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block, int ncols = 64);
