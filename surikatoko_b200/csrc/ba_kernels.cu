@@ -792,7 +792,8 @@ __global__ void __launch_bounds__(256) k_backsub(int64_t N, int64_t O, const int
 // k_schur_rows builds the rows (one warp per point: E, damping, cofactor inverse with the |det| > 1e-12 rule, F_i, W_i; the rhs terms
 // F_i^T E^-1 g_p go out as atomics, 10 per observation), launch_gemm_nt_dmma contracts them on DMMA with the K range split over the
 // SMs, k_scatter_dense_schur subtracts the lower triangle into the gauge-reduced S.
-__global__ void __launch_bounds__(128) k_schur_rows(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam,
+constexpr int kRowsWarps = 2;
+__global__ void __launch_bounds__(kRowsWarps * 32) k_schur_rows(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam,
                                                     const double* __restrict__ J, double c, SchurSink sink, double* __restrict__ pinv, unsigned char* __restrict__ skipped,
                                                     int M, double* __restrict__ Fall, double* __restrict__ Wall) {
     const int lane = threadIdx.x & 31;
@@ -838,23 +839,45 @@ __global__ void __launch_bounds__(128) k_schur_rows(int64_t N, int64_t O, const 
     const double t1 = inv[1] * a9[6] + inv[3] * a9[7] + inv[4] * a9[8];
     const double t2 = inv[2] * a9[6] + inv[4] * a9[7] + inv[5] * a9[8];
     const int64_t ldr = (int64_t)M * kV;
-    for (int64_t o = b + lane; o < e; o += 32) {
-        const int cam = obs_cam[o];
-        double jp[6];
+    // 32 observations at a time: every lane forms the 3 x 10 blocks F_i, W_i of its observation, the warp stages them in shared memory
+    // and writes the three rows out as runs of consecutive addresses (cameras of a track are mostly consecutive: 80-byte pieces written
+    // lane by lane with a stride of 80 bytes cost 32 sectors per store instruction: 0.64 ms for the 240 MB at configs[1]).
+    __shared__ double sF[kRowsWarps][3][320], sW[kRowsWarps][3][320];
+    __shared__ int sCam[kRowsWarps][32];
+    const int w = threadIdx.x >> 5;
+    for (int64_t o0 = b; o0 < e; o0 += 32) {
+        const int64_t o = o0 + lane;
+        const bool in = o < e;
+        const int cam = in ? obs_cam[o] : -1;
+        sCam[w][lane] = cam;
+        if (in) {
+            double jp[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
-        double* Fr = Fall + (size_t)(3 * j) * ldr + (size_t)cam * kV;
-        double* Wr = Wall + (size_t)(3 * j) * ldr + (size_t)cam * kV;
+            for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
 #pragma unroll
-        for (int a = 0; a < kV; ++a) {
-            const double j0 = J[(int64_t)(8 + 2 * a) * O + o], j1 = J[(int64_t)(9 + 2 * a) * O + o];
-            const double f0 = 2.0 * (jp[0] * j0 + jp[1] * j1), f1 = 2.0 * (jp[2] * j0 + jp[3] * j1), f2 = 2.0 * (jp[4] * j0 + jp[5] * j1);
-            Fr[a] = f0; Fr[ldr + a] = f1; Fr[2 * ldr + a] = f2;
-            Wr[a] = inv[0] * f0 + inv[1] * f1 + inv[2] * f2;
-            Wr[ldr + a] = inv[1] * f0 + inv[3] * f1 + inv[4] * f2;
-            Wr[2 * ldr + a] = inv[2] * f0 + inv[4] * f1 + inv[5] * f2;
-            sink_add_rhs(sink, cam, a, f0 * t0 + f1 * t1 + f2 * t2);
+            for (int a = 0; a < kV; ++a) {
+                const double j0 = J[(int64_t)(8 + 2 * a) * O + o], j1 = J[(int64_t)(9 + 2 * a) * O + o];
+                const double f0 = 2.0 * (jp[0] * j0 + jp[1] * j1), f1 = 2.0 * (jp[2] * j0 + jp[3] * j1), f2 = 2.0 * (jp[4] * j0 + jp[5] * j1);
+                sF[w][0][lane * kV + a] = f0; sF[w][1][lane * kV + a] = f1; sF[w][2][lane * kV + a] = f2;
+                sW[w][0][lane * kV + a] = inv[0] * f0 + inv[1] * f1 + inv[2] * f2;
+                sW[w][1][lane * kV + a] = inv[1] * f0 + inv[3] * f1 + inv[4] * f2;
+                sW[w][2][lane * kV + a] = inv[2] * f0 + inv[4] * f1 + inv[5] * f2;
+                sink_add_rhs(sink, cam, a, f0 * t0 + f1 * t1 + f2 * t2);
+            }
         }
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < kV; ++t) {
+            const int idx = lane + 32 * t;
+            const int l2 = idx / kV, a = idx - kV * l2;
+            const int cam2 = sCam[w][l2];
+            if (cam2 >= 0) {
+                const size_t off = (size_t)(3 * j) * ldr + (size_t)cam2 * kV + a;
+#pragma unroll
+                for (int v = 0; v < 3; ++v) { Fall[off + (size_t)v * ldr] = sF[w][v][idx]; Wall[off + (size_t)v * ldr] = sW[w][v][idx]; }
+            }
+        }
+        __syncwarp();
     }
 }
 // S(red(r), red(c)) += D(r, c), D = -(Fall^T Wall) as the GEMM leaves it (C -= A B^T on a zeroed C), for the lower triangle of the full
@@ -1081,7 +1104,7 @@ void launch_chunk_tables(cudaStream_t st, int64_t O, const int32_t* obs_cam, con
 }
 void launch_schur_rows(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
                        double* pinv, unsigned char* skipped, int M, double* Fall, double* Wall) {
-    if (N > 0) k_schur_rows<<<cdiv(N, 4), 128, 0, st>>>(N, O, pt_begin, obs_cam, J, c, sink, pinv, skipped, M, Fall, Wall);
+    if (N > 0) k_schur_rows<<<cdiv(N, kRowsWarps), kRowsWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, sink, pinv, skipped, M, Fall, Wall);
 }
 void launch_scatter_dense_schur(cudaStream_t st, int n_full, const double* D, int unity, double* S, int64_t ld) {
     if (n_full > 0) k_scatter_dense_schur<<<dim3(cdiv(n_full, 128), n_full), 128, 0, st>>>(n_full, D, unity, S, ld);
