@@ -35,7 +35,7 @@ struct DynMat {  // column-major dense matrix (Eigen default layout)
 };
 
 enum class SchurFlow { DenseReference = 0, SparseEquivalent = 1 };
-enum class SolveImpl { HouseholderQR = 0, CholeskyRefined = 1 };
+enum class SolveImpl { HouseholderQR = 0, CholeskyRefined = 1, None = 2 };   // None: assemble S / rhs only (parity checks of large systems)
 enum StopReason { kStopNone = 0, kStopAbsErrThreshold = 1, kStopSmallErrChange = 2, kStopHessianOverflow = 3, kStopErrConverged = 4,
                   kStopNormalizationFailed = 5, kStopMaxIters = 6 };
 
@@ -580,6 +580,7 @@ public:
 
     bool SolveReduced(std::vector<F>* x) {
         size_t nf = S_.rows;
+        if (solve_impl == SolveImpl::None) { x->assign(nf, F(0)); return true; }
         if (solve_impl == SolveImpl::HouseholderQR) {
             DynMat<F> A; A.resize(nf, nf);
             for (size_t i = 0; i < nf * nf; ++i) A.d[i] = F(S_.d[i]);

@@ -57,7 +57,7 @@ void Collapse(const Mirrors& m, double* points, double* cams) {
 template <class BA>
 void Configure(BA& ba, int flow, int solve_impl, int unity_ind, double unity_val, int max_outer_iters) {
     ba.schur_flow = flow == 0 ? SchurFlow::DenseReference : SchurFlow::SparseEquivalent;
-    ba.solve_impl = solve_impl == 0 ? SolveImpl::HouseholderQR : SolveImpl::CholeskyRefined;
+    ba.solve_impl = solve_impl == 0 ? SolveImpl::HouseholderQR : solve_impl == 2 ? SolveImpl::None : SolveImpl::CholeskyRefined;
     if (solve_impl >= 10) { ba.chol_in_double = true; ba.refine_steps = solve_impl - 10; }  // 10+k: double LL^T with k refinement steps
     ba.unity_t1_comp_ind_ = (size_t)unity_ind;
     ba.unity_t1_comp_value_ = unity_val;
@@ -202,6 +202,27 @@ int srk_oracle_derivs_and_solve(int64_t n_cams, int64_t n_points, int64_t n_obs,
         if (acc == 0) { BundleAdjustmentKanatani<double, double> ba; run(ba); }
         else { BundleAdjustmentKanatani<double, long double> ba; run(ba); }
         return rc;
+    } catch (const std::exception&) { return -1; }
+}
+
+// EstimateCorrectionsNaive (BA.cpp:1700-1769 with FillHessian :1551-1598): the full (3N+10M)^2 damped system with the gauge rows and
+// columns removed, solved by Householder QR -- the reference's own cross-check of the two-phase solve (compare_with_naive, :788-797).
+// Dense flow, tiny scenes only.  corrections[3N+10M] with the gaps re-inserted.
+int srk_oracle_naive_solve(int64_t n_cams, int64_t n_points, int64_t n_obs, const int32_t* obs_cam, const int32_t* obs_point,
+                           const double* obs_xy, const double* points, const double* cams, const double* K, int shared_K, double f0,
+                           int unity_ind, double c, double* corrections) {
+    try {
+        Mirrors m;
+        Expand(n_cams, n_points, n_obs, obs_cam, obs_point, obs_xy, points, cams, K, shared_K, &m);
+        BundleAdjustmentKanatani<double, double> ba;
+        Configure(ba, 0, 0, unity_ind, 1.0, 0);
+        ba.Bind(f0, m.map, m.cams, m.tracks, m.shared ? &m.sharedK : nullptr, m.shared ? nullptr : &m.Ks);
+        ba.EnsureMemoryAllocated();
+        ba.ComputeCloseFormReprErrorDerivatives();
+        std::vector<double> out;
+        if (!ba.EstimateCorrectionsNaive(c, &out)) return 1;
+        for (size_t i = 0; i < out.size(); ++i) corrections[i] = out[i];
+        return 0;
     } catch (const std::exception&) { return -1; }
 }
 

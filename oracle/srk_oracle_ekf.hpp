@@ -59,10 +59,12 @@ inline bool InversePartialPivLU(const EkfMat& A, EkfMat* inv) {
     }
     *inv = EkfMat(n, n);
     std::vector<double> y(n);
+    std::vector<double> rowmaj(n * n);   // the same factors, rows contiguous: the substitutions below walk rows (same operations, same order)
+    for (size_t i = 0; i < n; ++i) for (size_t j = 0; j < n; ++j) rowmaj[i * n + j] = lu(i, j);
     for (size_t c = 0; c < n; ++c) {
         for (size_t i = 0; i < n; ++i) y[i] = perm[i] == c ? 1.0 : 0.0;
-        for (size_t i = 0; i < n; ++i) { double s = y[i]; for (size_t j = 0; j < i; ++j) s -= lu(i, j) * y[j]; y[i] = s; }
-        for (size_t ii = n; ii-- > 0;) { double s = y[ii]; for (size_t j = ii + 1; j < n; ++j) s -= lu(ii, j) * y[j]; y[ii] = s / lu(ii, ii); }
+        for (size_t i = 0; i < n; ++i) { const double* l = &rowmaj[i * n]; double s = y[i]; for (size_t j = 0; j < i; ++j) s -= l[j] * y[j]; y[i] = s; }
+        for (size_t ii = n; ii-- > 0;) { const double* l = &rowmaj[ii * n]; double s = y[ii]; for (size_t j = ii + 1; j < n; ++j) s -= l[j] * y[j]; y[ii] = s / l[ii]; }
         for (size_t i = 0; i < n; ++i) (*inv)(i, c) = y[i];
     }
     return true;

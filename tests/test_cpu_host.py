@@ -191,3 +191,19 @@ def test_two_rank_gloo_sharded_system_matches_unsharded(oracle, tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, "rank %d failed:\n%s" % (r, o)
         assert "ok" in o
+
+
+def test_circle_grid_generator_replays_the_demo_bit_for_bit(oracle):
+    """surikatoko_b200.scenes.circle_grid_scene (the product-side input generator, numpy + Python floats) against the oracle's C++
+    restatement of demo-bundle-adj-circle-grid.cpp:64-257 / scene-generator.cpp:9-55 (std::mt19937 seed 1234 through libstdc++'s
+    uniform_real_distribution, draw order :109-128 then :224-257): every array identical to the last bit, at the demo's default size,
+    a refined grid and the BASELINE configs[1] size (50 cameras x 10 000 points, every point in every frame)."""
+    from surikatoko_b200 import scenes
+    for kw in (dict(), dict(cell_x=0.25, cell_y=0.25), dict(noise_R_hi=0.0), scenes.CIRCLE_GRID_CONFIG):
+        a = scenes.circle_grid_scene(**kw)
+        b = oracle.circle_grid_scene(**kw)
+        for f in ("obs_cam", "obs_point", "obs_xy", "points", "cams", "K", "gt_points", "gt_cams"):
+            x, y = np.asarray(getattr(a, f)), np.asarray(getattr(b, f))
+            assert x.shape == y.shape and np.array_equal(x, y), (kw, f)
+    c = scenes.circle_grid_config()
+    assert (c.n_cams, c.n_points, c.n_obs) == (50, 10_000, 500_000)

@@ -196,3 +196,94 @@ def test_reference_noise_floor_is_documented(oracle):
         n = min(len(ex), len(fa))
         assert n >= 1
         assert abs(np.sqrt(ex[0]) - np.sqrt(fa[0])) / np.sqrt(ex[0]) < 1e-7, name
+
+
+def test_two_phase_solve_matches_naive_full_solve(oracle):
+    """The reference's own cross-check (compare_with_naive, BA.cpp:788-797: EstimateCorrectionsNaive :1700-1769 builds the full damped
+    (3N+10M)^2 Hessian, removes the gauge rows / columns and solves by Householder QR; the reference compares with a loose 0.1).
+    Both are exact solves of the same linear system: through the error after the step they agree to the conditioning of the scene."""
+    pr = oracle.circle_grid_scene(cell_x=0.5, cell_y=0.5)
+    ok, pts, cams, _, _ = oracle.normalize(pr.points, pr.cams)
+    assert ok
+    q = pr.copy(); q.points = pts; q.cams = cams
+    N = q.n_points
+    for c in (1e-4, 1e-2, 1.0):
+        naive = oracle.naive_solve(q, c)
+        two = oracle.derivs_and_solve(q, c=c, flow="dense", solve="qr", acc="double")["corrections"]
+        fixed = [3 * N + i for i in (4, 5, 6, 7, 8, 9, 15)]
+        assert np.all(naive[fixed] == 0) and np.all(two[fixed] == 0)
+        errs = []
+        for corr in (naive, two):
+            p1, c1 = oracle.apply_corrections(q.points, q.cams, corr)
+            t = q.copy(); t.points = p1; t.cams = c1
+            errs.append(oracle.reproj_error(t)[0])
+        assert abs(errs[0] - errs[1]) <= 1e-6 * errs[1], (c, errs)
+        # the reference's own (loose) bound on the corrections themselves
+        assert np.max(np.abs(naive - two)) < 0.1
+        if c >= 1e-2:
+            assert relerr(naive, two) < 1e-6, c
+
+
+def _ld_cholesky_solve(A, B):
+    """Solve A X = B for symmetric positive definite A in numpy long double (row-oriented Cholesky; numpy.linalg has no long double)."""
+    n = A.shape[0]
+    L = np.zeros_like(A)
+    for j in range(n):
+        d = A[j, j] - np.dot(L[j, :j], L[j, :j])
+        L[j, j] = np.sqrt(d)
+        if j + 1 < n:
+            L[j + 1:, j] = (A[j + 1:, j] - L[j + 1:, :j] @ L[j, :j]) / L[j, j]
+    Y = np.zeros_like(B)
+    for i in range(n):
+        Y[i] = (B[i] - L[i, :i] @ Y[:i]) / L[i, i]
+    X = np.zeros_like(B)
+    for i in range(n - 1, -1, -1):
+        X[i] = (Y[i] - L[i + 1:, i] @ X[i + 1:]) / L[i, i]
+    return X
+
+
+@pytest.mark.parametrize("npts,s", [(40, 3), (25, 6)])
+def test_ekf_oracle_is_pinned_by_an_independent_long_double_evaluation(oracle, npts, s):
+    """The reference has no test of its EKF update, so the restatement (explicit LU inverse, K, P - K S K^T, EKF.cpp:977-1125)
+    is pinned here against an independent evaluation of the textbook form P - P H^T (H P H^T + R)^-1 H P, x + P H^T S^-1 (z - h) in numpy
+    long double with a Cholesky solve, followed by the quaternion normalisation written as the congruence J P J^T with the full n x n
+    Jacobian of q / |q| (EKF.cpp:1652-1711 updates the same blocks piecewise) and the symmetrisation (EKF.cpp:1120-1121)."""
+    from surikatoko_b200.ekf import synthetic_ekf_frame
+    fr = synthetic_ekf_frame(npts, s, seed=11 + npts)
+    ok, P_o, x_o, _ = oracle.ekf_update(fr["P"], fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+    assert ok
+    ld = np.longdouble
+    n, m = fr["n"], fr["m"]
+    H = np.zeros((2 * m, n), dtype=ld)
+    H[:, :13] = fr["Hcam"]
+    for i, off in enumerate(fr["pt_off"]):
+        H[2 * i:2 * i + 2, off:off + s] = fr["Hpt"][2 * i:2 * i + 2]
+    P = fr["P"].astype(ld); x = fr["x"].astype(ld)
+    PHt = P @ H.T
+    S = H @ PHt + ld(fr["meas_var"]) * np.eye(2 * m, dtype=ld)
+    W = _ld_cholesky_solve(S, PHt.T)                       # S^-1 H P
+    x1 = x + PHt @ _ld_cholesky_solve(S, (fr["z"] - fr["h"]).astype(ld)[:, None])[:, 0]
+    P1 = P - PHt @ W
+    q = x1[3:7].copy(); qn = np.sqrt(np.dot(q, q))
+    assert abs(float(qn) - 1.0) > 1e-5, "the frame must exercise the normalisation branch"
+    J = np.eye(n, dtype=ld)
+    J[3:7, 3:7] = (np.eye(4, dtype=ld) * np.dot(q, q) - np.outer(q, q)) / qn ** 3
+    x1[3:7] = q / qn
+    P1 = J @ P1 @ J.T
+    P1 = (P1 + P1.T) / 2
+    # the explicit-inverse chain in double is ~cond(S) * eps away from the long-double evaluation
+    assert relerr(x_o, x1.astype(np.float64)) < 5e-10
+    assert relerr(P_o, P1.astype(np.float64)) < 5e-10
+
+
+def test_ekf_predict_oracle_matches_block_formula(oracle):
+    """PredictEstimVars, covariance part (EKF.cpp:669-693): Pvv <- F Pvv F^T + G Q G^T, Pvm <- F Pvm, Pmm unchanged; numpy long double."""
+    from surikatoko_b200.ekf import synthetic_ekf_frame
+    fr = synthetic_ekf_frame(30, 3, seed=5)
+    P_o = oracle.ekf_predict(fr["P"], fr["F"], fr["GQGt"])
+    ld = np.longdouble
+    P = fr["P"].astype(ld); F = fr["F"].astype(ld)
+    P1 = P.copy()
+    P1[:13, :13] = F @ P[:13, :13] @ F.T + fr["GQGt"].astype(ld)
+    P1[:13, 13:] = F @ P[:13, 13:]; P1[13:, :13] = P1[:13, 13:].T
+    assert relerr(P_o, P1.astype(np.float64)) < 1e-14

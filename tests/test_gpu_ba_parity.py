@@ -98,7 +98,28 @@ def run_pair(oracle, engine, pr, err_change, max_outer_iters, **kw):
     return ref, rep, prob
 
 
-def check_trajectory(ref, rep, pr, prob, f0):
+def report_deviation(label, dev, noise):
+    """Makes the tolerance visible: per accepted iteration the achieved deviation of the GPU residual norm from the exact oracle next to
+    the faithful oracle's own deviation (the reference's FP64 noise on that scene); printed (pytest -s / -rP) and appended to
+    gpurun_out/parity_deviation.jsonl so that DESIGN.md can quote measured numbers.  Iterations whose bound had to be relaxed beyond the
+    north star's 1e-9 are counted explicitly."""
+    import json
+    relaxed = int(np.sum((dev > 1e-9)))
+    line = {"scene": label, "iterations": int(len(dev)), "max_dev_vs_exact": float(np.max(dev)) if len(dev) else 0.0,
+            "iters_within_1e-9": int(np.sum(dev <= 1e-9)), "iters_relaxed_to_reference_noise": relaxed,
+            "max_reference_noise": float(np.max(noise[np.isfinite(noise)])) if np.any(np.isfinite(noise)) else None,
+            "dev_first8": [float(v) for v in dev[:8]], "noise_first8": [float(v) for v in noise[:8]]}
+    print("PARITY " + json.dumps(line))
+    try:
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_deviation.jsonl"), "a") as f:
+            f.write(json.dumps(line) + "\n")
+    except OSError:
+        pass
+
+
+def check_trajectory(ref, rep, pr, prob, f0, label="scene"):
     assert rep.seen_points == ref.seen_points
     assert abs(rep.err_initial - ref.err_initial) <= 1e-12 * ref.err_initial
     n = min(len(ref.attempts), len(rep.attempts))
@@ -110,6 +131,7 @@ def check_trajectory(ref, rep, pr, prob, f0):
     # per-iteration residual norms sqrt(err): 1e-9 relative to the exact oracle; the first iteration starts from the identical
     # state and must meet it outright, later ones get max(1e-9, the reference's own double-precision noise at that iteration)
     dev = np.abs(np.sqrt(rep.err_trace) - np.sqrt(ref.err_trace)) / np.sqrt(ref.err_trace)
+    report_deviation(label, dev, ref.noise)
     assert dev[0] < 1e-9
     assert np.all(dev <= np.maximum(1e-9, ref.noise)), (dev, ref.noise)
     assert rep.stop_reason == ref.stop_reason

@@ -1,0 +1,107 @@
+"""GPU parity at the sizes BASELINE.json's configs state, against the CPU oracle.
+
+  configs[1]  the circle-grid demo's own scene at 50 cameras x 10 000 points x 500 000 observations (n_f = 493) -- the dense-rows K2
+              (k_schur_rows + split-K DMMA contraction) and the dense Cholesky: blocks, reduced system, skip mask, an LM trajectory;
+  configs[0]  the dinosaur shape, 36 views x 4983 points x 16 432 observations, the demo's threshold 4.56e-8 (flagfile-demo-dino.txt:10):
+              the WHOLE trajectory -- every accept/reject decision, the stop reason, the final RMS;
+  configs[2]  the 1000-camera reduced system (n_f = 9993) element by element against the sparse oracle on 50k points of the configs[2]
+              scene (the oracle needs minutes per 1M points; the full 10M-observation problem is property-tested in test_gpu_full_size.py);
+  configs[3]  the EKF stacked update at 1000 salient points (n = 3013, 2m = 2000).
+Tolerances as in test_gpu_ba_parity.py; every trajectory prints its achieved per-iteration deviation (report_deviation)."""
+import numpy as np
+import pytest
+
+from conftest import relerr, to_problem
+from test_gpu_ba_parity import as_oracle_problem, check_trajectory, normalized_problem, run_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def circle_grid():
+    from surikatoko_b200 import scenes
+    return scenes.circle_grid_config()
+
+
+def test_config1_circle_grid_blocks_and_system(oracle, engine, circle_grid):
+    pr = as_oracle_problem(oracle, circle_grid)
+    assert (pr.n_cams, pr.n_points, pr.n_obs) == (50, 10_000, 500_000)
+    c = float(np.float32(0.0001))
+    q = normalized_problem(oracle, pr)
+    ref = oracle.derivs_and_solve(q, c=c, flow="sparse", solve="chol", acc="ld")
+    assert engine.bind(to_problem(pr))
+    got = engine.debug_derivs_and_solve(c=c)
+    for k in ("gradE", "E", "G", "F"):
+        assert relerr(got[k], ref[k]) < 1e-11, k
+    assert np.array_equal(got["skipped"], ref["skipped"])
+    assert np.array_equal(got["S"] != 0, ref["S"] != 0)
+    assert relerr(got["S"], ref["S"]) < 1e-11
+    assert relerr(got["rhs"], ref["rhs"]) < 1e-10
+    p2, c2 = oracle.apply_corrections(q.points, q.cams, ref["corrections"])
+    z = q.copy(); z.points = p2; z.cams = c2
+    e_ref, _ = oracle.reproj_error(z)
+    e_gpu = engine.debug_apply(got["corrections"])
+    assert abs(e_gpu - e_ref) <= 1e-7 * abs(e_ref)
+
+
+def test_config1_circle_grid_trajectory(oracle, engine, circle_grid):
+    pr = as_oracle_problem(oracle, circle_grid)
+    ref, rep, out = run_pair(oracle, engine, pr, 1e-8, 2)
+    assert len(ref.attempts) >= 4, "the demo scene rejects its first damping factors: the retry path must be exercised"
+    check_trajectory(ref, rep, pr, out, pr.f0, label="configs[1] circle-grid 50x10000x500000")
+
+
+def test_config0_dino_shape_whole_trajectory(oracle, engine):
+    from surikatoko_b200 import scenes
+    prob = scenes.dino_shaped_scene()
+    assert (prob.n_cams, prob.n_points, prob.n_obs) == (36, 4983, 16432)
+    pr = as_oracle_problem(oracle, prob)
+    ref, rep, out = run_pair(oracle, engine, pr, 4.56e-8, 0)
+    assert ref.stop_reason == "small relative err change" and ref.converged
+    check_trajectory(ref, rep, pr, out, pr.f0, label="configs[0] dino shape 36x4983x16432, threshold 4.56e-8")
+    assert rep.outer_iters == ref.outer_iters
+
+
+def test_config2_thousand_camera_system_matches_sparse_oracle(oracle, engine):
+    from surikatoko_b200 import scenes
+    prob = scenes.ring_scene(1000, 50_000, 10, seed=1234)
+    pr = as_oracle_problem(oracle, prob)
+    c = float(np.float32(0.0001))
+    q = normalized_problem(oracle, pr)
+    ref = oracle.derivs_and_solve(q, c=c, flow="sparse", solve="none", acc="ld")
+    assert engine.bind(to_problem(pr))
+    got = engine.debug_derivs_and_solve(c=c)
+    st = engine.solve_stats()
+    assert st["n_f"] == 9993 and st["parts"] >= 2
+    for k in ("gradE", "E", "G", "F"):
+        assert relerr(got[k], ref[k]) < 1e-11, k
+    assert np.array_equal(got["skipped"], ref["skipped"])
+    assert relerr(got["rhs"], ref["rhs"]) < 1e-10
+    S, Sr = got["S"], ref["S"]
+    assert S.shape == Sr.shape == (9993, 9993)
+    assert np.array_equal(S != 0, Sr != 0), "sparsity structure of the 1000-camera reduced system differs"
+    assert np.max(np.abs(S - Sr)) < 1e-11 * np.max(np.abs(Sr))
+    # the solve: S x = rhs must hold for the engine's own corrections to the accuracy the refinement step promises
+    x = got["corrections"][3 * pr.n_points:]
+    keep = np.ones(10 * pr.n_cams, dtype=bool); keep[[4, 5, 6, 7, 8, 9, 15]] = False
+    r = Sr.astype(np.longdouble) @ x[keep].astype(np.longdouble) - ref["rhs"].astype(np.longdouble)
+    assert float(np.max(np.abs(r))) <= 1e-9 * float(np.max(np.abs(ref["rhs"])))
+
+
+def test_config3_ekf_update_at_1000_points(oracle):
+    from surikatoko_b200.ekf import EkfEngine, synthetic_ekf_frame
+    fr = synthetic_ekf_frame(1000, 3, seed=1003)
+    assert fr["n"] == 3013
+    ok, P_ref, x_ref, _ = oracle.ekf_update(fr["P"], fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+    assert ok
+    ekf = EkfEngine(0)
+    try:
+        ekf.set_state(fr["P"], fr["x"])
+        assert ekf.update(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"]) == 0
+        P, x = ekf.get_state()
+    finally:
+        ekf.close()
+    dx, dP = relerr(x, x_ref), relerr(P, P_ref)
+    print("PARITY ekf n=3013: state %.2e covariance %.2e" % (dx, dP))
+    assert dx < 5e-9 and dP < 5e-9
+    assert np.array_equal(P, P.T)
