@@ -33,6 +33,7 @@ extern "C" {
 #define SRK_E_CUDA (-3)          /* a CUDA call failed; srk_last_error() has the text */
 #define SRK_E_NOT_BOUND (-4)     /* run/fetch/debug call before srk_ba_bind */
 #define SRK_E_TOO_LARGE (-5)     /* reduced camera system does not fit the selected solver */
+#define SRK_E_NOT_POSDEF (-6)    /* EKF: the innovation covariance is not numerically positive definite; state left untouched */
 
 /* Stop reasons: BA.cpp:751, :866-868, :882; 5 = NormalizeSceneInplace failed (BA.cpp:681-682, empty string in the
  * reference); 6 = max_outer_iters reached (an extension: the reference has no iteration cap, quirk Q9). */
@@ -98,6 +99,12 @@ typedef struct srk_ba_report {
     int64_t gpu_launches;              /* kernels launched by this call                                              */
     int32_t solver_used;               /* SRK_SOLVER_DENSE_CHOLESKY or SRK_SOLVER_BLOCK_PCG                           */
     int32_t pcg_iters_last;
+    double pcg_rel_res_last;           /* ||rhs - S x|| / ||rhs|| the last PCG solve stopped at (0 on the dense path)          */
+    int32_t factor_failures;           /* attempts whose Cholesky factorisation met a non-positive pivot: each counts as a failed
+                                          attempt and is retried with hessian_factor * 10 (the reference's QR, BA.cpp:1911, returns
+                                          finite corrections there, which then fail the decrease test, :841); attempt_trace holds
+                                          err_new = +inf for them                                                          */
+    int32_t reserved_;
 } srk_ba_report;
 
 SRK_API void srk_ba_default_options(srk_ba_options* opt);

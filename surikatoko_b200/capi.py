@@ -38,7 +38,8 @@ class _Report(C.Structure):
                 ("err_initial", C.c_double), ("err_final", C.c_double), ("hessian_factor_final", C.c_double),
                 ("seen_points", C.c_int64), ("err_trace", C.c_void_p), ("err_trace_cap", C.c_int32), ("err_trace_len", C.c_int32),
                 ("attempt_trace", C.c_void_p), ("attempt_trace_cap", C.c_int32), ("attempt_trace_len", C.c_int32),
-                ("gpu_launches", C.c_int64), ("solver_used", C.c_int32), ("pcg_iters_last", C.c_int32)]
+                ("gpu_launches", C.c_int64), ("solver_used", C.c_int32), ("pcg_iters_last", C.c_int32),
+                ("pcg_rel_res_last", C.c_double), ("factor_failures", C.c_int32), ("reserved_", C.c_int32)]
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
@@ -153,6 +154,8 @@ class BAReport:
         self.gpu_launches = rep.gpu_launches
         self.solver_used = rep.solver_used
         self.pcg_iters_last = rep.pcg_iters_last
+        self.pcg_rel_res_last = rep.pcg_rel_res_last
+        self.factor_failures = rep.factor_failures
 
     def __repr__(self):
         return ("BAReport(converged=%s, stop=%r, outer_iters=%d, attempts=%d, err %.9g -> %.9g, launches=%d)" %

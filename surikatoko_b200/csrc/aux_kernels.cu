@@ -13,6 +13,7 @@ __global__ void k_pack_attempt(const double* __restrict__ err_sum, const int* __
     if (t == 0) {
         slots[world] = finite_flag != nullptr ? (double)finite_flag[0] : 0.0;
         slots[world + 1] = skipped_cnt != nullptr ? (double)skipped_cnt[0] : 0.0;
+        slots[world + 2] = finite_flag != nullptr ? (double)(finite_flag[1] != 0) : 0.0;   // flags[2]: Cholesky info (first non-positive pivot)
     }
 }
 

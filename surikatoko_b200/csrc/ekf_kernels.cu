@@ -498,6 +498,10 @@ ErrSink g_ekf_error;
 
 struct DBuf {
     void* p = nullptr; size_t cap = 0;
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { if (p != nullptr) cudaFree(p); }   // `delete handle` frees every buffer (r_hyp / r_support / r_bits included)
     cudaError_t ensure(size_t bytes) {
         if (p != nullptr && bytes <= cap) return cudaSuccess;
         if (p != nullptr) cudaFree(p);
@@ -589,6 +593,18 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
     {
         EScope sc(e, E_CHOL);
         e.launches += srk::dense_cholesky_factor(st, m2, S, lds, ws, e.info.as<int>());
+    }
+    {   // A failed factorisation must not reach the state: P and x are still untouched here (P*H^T and S are scratch).  The reference forms
+        // a general inverse (EKF.cpp:1017-1019) and has no such failure; an innovation covariance that is not positive definite means the
+        // filter has already diverged, and the caller is told instead of receiving NaNs.
+        int hchol = 0;
+        EKF_CUDA(cudaMemcpyAsync(&hchol, e.info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        EKF_CUDA(cudaStreamSynchronize(st));
+        if (hchol != 0) {
+            if (info_out != nullptr) *info_out = hchol;
+            g_ekf_error = std::string("innovation covariance H P H^T + R is not numerically positive definite (pivot ") + std::to_string(hchol) + "); state left untouched";
+            return SRK_E_NOT_POSDEF;
+        }
     }
     {   // Z = PHt * L^-T; Z overwrites PHt.  Right-looking over 64-column blocks INSIDE a 256-column panel, then ONE update of everything
         // right of the panel with K = 256: a K = 64 update of the whole trailing matrix per block column re-reads and re-writes PHt
@@ -771,8 +787,6 @@ void srk_ekf_destroy(void* h) {
     Ekf* e = (Ekf*)h;
     cudaSetDevice(e->device);
     ekf_resolve(*e);
-    DBuf* bufs[] = {&e->P, &e->x, &e->PHt, &e->S, &e->ws, &e->w, &e->Hcam, &e->Hpt, &e->off, &e->z, &e->h, &e->aux, &e->tmp, &e->neg, &e->info, &e->small};
-    for (DBuf* b : bufs) if (b->p != nullptr) cudaFree(b->p);
     if (e->own != nullptr) cudaStreamDestroy(e->own);
     delete e;
 }
@@ -828,7 +842,7 @@ int srk_ekf_update(void* h, int64_t n, int64_t m, double* P, double* x, const do
     if (rc != SRK_OK) return rc;
     int32_t info = 0;
     rc = srk_ekf_update_resident(h, m, Hcam, Hpt, pt_off, s, z, h_pred, meas_var, &info);
-    if (rc != SRK_OK) return rc;
+    if (rc != SRK_OK) return rc;              // SRK_E_NOT_POSDEF included: the caller's P and x are not overwritten
     return srk_ekf_get_state(h, P, x);
 }
 int srk_ekf_predict(void* h, int64_t n, double* P, const double* F13, const double* GQGt13) {

@@ -39,6 +39,10 @@ void set_error(const std::string& s) { g_last_error = s; }
 struct Buf {
     void* p = nullptr;
     size_t cap = 0;
+    Buf() = default;
+    Buf(const Buf&) = delete;
+    Buf& operator=(const Buf&) = delete;
+    ~Buf() { release(); }   // `delete engine` frees every buffer, listed anywhere or not (the destroy call selects the device first)
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap && p != nullptr) return cudaSuccess;
         if (p != nullptr) { cudaFree(p); p = nullptr; cap = 0; }
@@ -156,7 +160,10 @@ struct Engine {
     FamilyTimer timers[F_COUNT];
     int64_t launches = 0;
     int32_t pcg_iters_last = 0;
+    double pcg_rel_res_last = 0.0;
     int solver_used = 0;
+    int64_t factor_failures = 0;     // attempts whose Cholesky factorisation met a non-positive pivot (retried with more damping)
+    int debug_fail_factor = 0;       // SRK_DEBUG_FAIL_FACTOR=k: treat the first k factorisations of every run as failed (test hook of that path)
 };
 
 struct Scope {  // CUDA-event bracket of one kernel family on the engine's stream
@@ -244,11 +251,11 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
     SRK_CUDA(e.errsum.ensure(sizeof(double) * 2));
     e.residual_blocks = residual_grid(O);
     SRK_CUDA(e.partial.ensure(sizeof(double) * e.residual_blocks));
-    SRK_CUDA(e.slots.ensure(sizeof(double) * (e.world + 2)));
-    if (e.h_slots_cap < (size_t)(e.world + 2)) {
+    SRK_CUDA(e.slots.ensure(sizeof(double) * (e.world + 3)));
+    if (e.h_slots_cap < (size_t)(e.world + 3)) {
         if (e.h_slots != nullptr) cudaFreeHost(e.h_slots);
-        SRK_CUDA(cudaMallocHost((void**)&e.h_slots, sizeof(double) * (e.world + 2)));
-        e.h_slots_cap = (size_t)(e.world + 2);
+        SRK_CUDA(cudaMallocHost((void**)&e.h_slots, sizeof(double) * (e.world + 3)));
+        e.h_slots_cap = (size_t)(e.world + 3);
     }
     e.X_cur = e.Xa.as<double>(); e.X_try = e.Xb.as<double>();
     e.cams_cur = e.cams_a.as<double>(); e.cams_try = e.cams_b.as<double>();
@@ -421,20 +428,21 @@ void residual_of(Engine& e, const double* X, const double* camd) {
     e.launches += 2;
 }
 
-// Brings (global error, non-finite flag, skipped count) of the current attempt to the host.
-int fetch_attempt_scalars(Engine& e, bool with_flags, double* err, bool* nonfinite, int64_t* skipped) {
+// Brings (global error, non-finite flag, skipped count, Cholesky info) of the current attempt to the host.
+int fetch_attempt_scalars(Engine& e, bool with_flags, double* err, bool* nonfinite, int64_t* skipped, bool* factor_failed = nullptr) {
     srk::launch_pack_attempt(e.stream, e.errsum.as<double>(), with_flags ? e.flags.as<int>() + 1 : nullptr,
                              with_flags ? e.skipped_cnt.as<unsigned long long>() : nullptr, e.rank, e.world, e.slots.as<double>());
     e.launches += 1;
-    int rc = do_allreduce(e, e.slots.as<double>(), e.world + 2);
+    int rc = do_allreduce(e, e.slots.as<double>(), e.world + 3);
     if (rc != SRK_OK) return rc;
-    SRK_CUDA(cudaMemcpyAsync(e.h_slots, e.slots.p, sizeof(double) * (e.world + 2), cudaMemcpyDeviceToHost, e.stream));
+    SRK_CUDA(cudaMemcpyAsync(e.h_slots, e.slots.p, sizeof(double) * (e.world + 3), cudaMemcpyDeviceToHost, e.stream));
     SRK_CUDA(cudaStreamSynchronize(e.stream));
     double s = 0.0;
     for (int r = 0; r < e.world; ++r) s += e.h_slots[r];  // rank order: identical on every rank
     *err = s;
     if (nonfinite != nullptr) *nonfinite = e.h_slots[e.world] != 0.0;
     if (skipped != nullptr) *skipped = (int64_t)e.h_slots[e.world + 1];
+    if (factor_failed != nullptr) *factor_failed = e.h_slots[e.world + 2] != 0.0;   // the solve is replicated: every rank reports the same pivot
     return SRK_OK;
 }
 
@@ -705,6 +713,7 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
             rc = srk::pcg_solve(e.pcg, st, M, e.dfull.as<double>(), opt != nullptr ? opt->pcg_max_iters : 0, opt != nullptr ? opt->pcg_rel_tol : 0.0, e.world,
                                 e.ar, e.ar_user, &e.launches, &e.pcg_iters_last, &rel);
             if (rc != SRK_OK) { set_error("pcg solve failed: " + std::string(cudaGetErrorString(cudaGetLastError()))); return rc; }
+            e.pcg_rel_res_last = rel;
         }
         e.solver_used = SRK_SOLVER_BLOCK_PCG;
     }
@@ -741,6 +750,19 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
     return SRK_OK;
 }
 
+// allFinite over the dense reduced system (S and rhs) of the last attempt -- only on the rare failed-factorisation path.
+int system_is_finite(Engine& e, bool* finite) {
+    *finite = true;
+    if (e.Srhs.p == nullptr) return SRK_OK;
+    SRK_CUDA(cudaMemsetAsync(e.flags.as<int>() + 3, 0, sizeof(int), e.stream));
+    srk::launch_finite_flag(e.stream, e.ld * (int64_t)e.nf + e.ld, e.Srhs.as<double>(), e.flags.as<int>() + 3); e.launches += 1;
+    int h = 0;
+    SRK_CUDA(cudaMemcpyAsync(&h, e.flags.as<int>() + 3, sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+    SRK_CUDA(cudaStreamSynchronize(e.stream));
+    *finite = h == 0;
+    return SRK_OK;
+}
+
 void accept_trial(Engine& e) {
     std::swap(e.X_cur, e.X_try); std::swap(e.cams_cur, e.cams_try); std::swap(e.camd_cur, e.camd_try);
 }
@@ -750,12 +772,14 @@ int run_impl(Engine& e, const srk_ba_options* opt, srk_ba_report* rep) {
     if (!e.bound) { set_error("srk_ba_run before srk_ba_bind"); return SRK_E_NOT_BOUND; }
     srk_ba_options defopt; srk_ba_default_options(&defopt);
     if (opt == nullptr) opt = &defopt;
-    const int64_t launches0 = e.launches;
+    const int64_t launches0 = e.launches, failures0 = e.factor_failures;
+    if (const char* v = std::getenv("SRK_DEBUG_FAIL_FACTOR")) e.debug_fail_factor = std::atoi(v);
     auto finish = [&](int converged, int reason, int iters, int attempts, double e0, double e1, double c, int64_t seen) {
         if (rep == nullptr) return;
         rep->converged = converged; rep->stop_reason = reason; rep->outer_iters = iters; rep->attempts = attempts;
         rep->err_initial = e0; rep->err_final = e1; rep->hessian_factor_final = c; rep->seen_points = seen;
         rep->gpu_launches = e.launches - launches0; rep->solver_used = e.solver_used; rep->pcg_iters_last = e.pcg_iters_last;
+        rep->pcg_rel_res_last = e.pcg_rel_res_last; rep->factor_failures = (int32_t)(e.factor_failures - failures0);
     };
     if (rep != nullptr) { rep->err_trace_len = 0; rep->attempt_trace_len = 0; }
     if (e.norm_failed) { finish(0, SRK_STOP_NORMALIZATION_FAILED, 0, 0, 0.0, 0.0, 0.0, 0); return SRK_OK; }
@@ -800,10 +824,29 @@ int run_impl(Engine& e, const srk_ba_options* opt, srk_ba_report* rep) {
         while (true) {  // try_decrease_targ_fun (BA.cpp:764-852); the trial buffers replace the reference's backup/restore
             rc = attempt(e, solver, opt, hessian_factor, nullptr);
             if (rc != SRK_OK) return rc;
-            bool nonfinite = false; int64_t skipped = 0;
-            rc = fetch_attempt_scalars(e, true, &err_new, &nonfinite, &skipped);
+            bool nonfinite = false, factor_failed = false; int64_t skipped = 0;
+            rc = fetch_attempt_scalars(e, true, &err_new, &nonfinite, &skipped, &factor_failed);
             if (rc != SRK_OK) return rc;
             ++attempts;
+            if (e.debug_fail_factor > 0 && solver == SRK_SOLVER_DENSE_CHOLESKY) { --e.debug_fail_factor; factor_failed = true; }
+            if (factor_failed) {
+                // The reduced system is not numerically positive definite at this damping.  The reference solves with Householder QR
+                // (BA.cpp:1911), which returns finite corrections for any finite S: the step then fails the decrease test and is retried
+                // with hessian_factor * 10 (:841).  Cholesky has no such answer, so a failed factorisation IS the failed attempt -- unless
+                // S itself holds a non-finite entry, where the reference's allFinite test (:1912) ends the run.
+                e.factor_failures += 1;
+                bool finite = true;
+                rc = system_is_finite(e, &finite);
+                if (rc != SRK_OK) return rc;
+                if (!finite) { result = FailedHessianOverflow; break; }
+                if (rep != nullptr && rep->attempt_trace != nullptr && rep->attempt_trace_len < rep->attempt_trace_cap) {
+                    double* a = rep->attempt_trace + 4 * (size_t)rep->attempt_trace_len++;
+                    a[0] = hessian_factor; a[1] = HUGE_VAL; a[2] = 0.0; a[3] = (double)skipped;
+                }
+                hessian_factor *= 10;
+                if (!std::isfinite(hessian_factor) || (opt->has_max_hessian_factor && hessian_factor > opt->max_hessian_factor)) { result = FailedHessianOverflow; break; }
+                continue;
+            }
             if (nonfinite) { result = FailedHessianOverflow; break; }
             bool decreased = (err_new - err_value) < 0;
             if (rep != nullptr && rep->attempt_trace != nullptr && rep->attempt_trace_len < rep->attempt_trace_cap) {
@@ -870,7 +913,7 @@ int fetch_impl(Engine& e, srk_ba_problem* p) {
 // =====================================================================================================================
 extern "C" {
 
-int srk_abi_version(void) { return 1; }
+int srk_abi_version(void) { return 2; }   // 2: srk_ba_report gained pcg_rel_res_last / factor_failures
 void srk_internal_set_error(const char* s) { g_last_error = s != nullptr ? s : ""; }
 const char* srk_last_error(void) { return g_last_error.c_str(); }
 
@@ -930,11 +973,6 @@ void srk_ba_destroy(void* h) {
     Engine* e = (Engine*)h;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    Buf* bufs[] = {&e->obs_cam, &e->obs_pt, &e->obs_xy, &e->ox, &e->oy, &e->pt_begin, &e->cam_cnt, &e->cam_cursor, &e->cam_begin, &e->c_pt, &e->c_x, &e->c_y,
-                   &e->Xa, &e->Xb, &e->Xbound, &e->pts_stage, &e->cams_a, &e->cams_b, &e->cams_bound, &e->Kd, &e->camd_a, &e->camd_b, &e->J, &e->Ggf,
-                   &e->pinv, &e->skipped, &e->deferred, &e->Srhs, &e->Lfac, &e->dinv, &e->xsol, &e->resid, &e->dfull, &e->partial, &e->errsum, &e->slots, &e->flags,
-                   &e->skipped_cnt, &e->dbg, &e->tmask, &e->tlist, &e->tpacked};
-    for (Buf* b : bufs) b->release();
     srk::pcg_release(e->pcg);
     if (e->h_slots != nullptr) cudaFreeHost(e->h_slots);
     if (e->h_adj != nullptr) cudaFreeHost(e->h_adj);

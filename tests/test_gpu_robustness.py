@@ -1,0 +1,106 @@
+"""GPU tests of the failure paths the round-1 review named: a factorisation that meets a non-positive pivot, handle life cycle without
+leaks, an EKF innovation covariance that is not positive definite."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import to_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def test_failed_factorisation_is_a_failed_attempt_not_the_end_of_the_run(oracle):
+    """BA.cpp:1911 solves with Householder QR: an S that is not numerically positive definite still yields finite corrections, the step
+    fails the decrease test and is retried with hessian_factor * 10 (:841).  The Cholesky path must therefore treat a non-positive pivot
+    as a failed attempt.  SRK_DEBUG_FAIL_FACTOR forces the first two factorisations of a run to report one."""
+    import surikatoko_b200 as sb
+    pr = oracle.circle_grid_scene(cell_x=0.25, cell_y=0.25)
+    opt = sb.BAOptions(err_change=1e-10, max_outer_iters=3)
+    eng = sb.Engine(0)
+    try:
+        plain = eng.solve(to_problem(pr), opt)
+    finally:
+        eng.close()
+    os.environ["SRK_DEBUG_FAIL_FACTOR"] = "2"
+    try:
+        eng = sb.Engine(0)
+        try:
+            forced = eng.solve(to_problem(pr), opt)
+        finally:
+            eng.close()
+    finally:
+        del os.environ["SRK_DEBUG_FAIL_FACTOR"]
+    assert plain.factor_failures == 0 and forced.factor_failures == 2
+    assert forced.stop_reason != "hessian overflow" and len(forced.err_trace) == len(plain.err_trace)
+    a = forced.attempts
+    assert np.all(np.isinf(a[:2, 1])) and np.all(a[:2, 2] == 0)
+    c0 = float(np.float32(0.0001))
+    assert np.allclose(a[:3, 0], [c0, c0 * 10, c0 * 100], rtol=1e-15)
+    assert np.all(np.isfinite(a[2:, 1]))
+    assert np.all(np.isfinite(forced.err_trace)) and forced.err_trace[-1] < forced.err_initial
+    # with max_hessian_factor below the retried damping the run ends the way the reference's loop does (:845-848)
+    os.environ["SRK_DEBUG_FAIL_FACTOR"] = "2"
+    try:
+        eng = sb.Engine(0)
+        try:
+            capped = eng.solve(to_problem(pr), sb.BAOptions(err_change=1e-10, max_outer_iters=3, max_hessian_factor=5e-4))
+        finally:
+            eng.close()
+    finally:
+        del os.environ["SRK_DEBUG_FAIL_FACTOR"]
+    assert capped.stop_reason == "hessian overflow" and not capped.converged
+
+
+def test_handle_life_cycle_does_not_leak_device_memory(oracle):
+    """The compat adapter creates and destroys a handle per BundleAdjustmentKanatani object: create / bind / run / destroy in a loop must
+    leave the free device memory where it was (srk_ba_destroy and srk_ekf_destroy free every buffer through RAII)."""
+    import torch
+    import surikatoko_b200 as sb
+    from surikatoko_b200 import scenes
+    from surikatoko_b200.ekf import EkfEngine, synthetic_ransac_frame
+    prob = scenes.circle_grid_scene(cell_x=0.1, cell_y=0.1)        # long tracks: the dense-rows buffers of K2 are allocated too
+    ring = scenes.ring_scene(170, 4000, 6, seed=9)                 # nested-dissection order buffers
+    fr = synthetic_ransac_frame(60, 3, seed=3)
+
+    def cycle():
+        for p in (prob, ring):
+            e = sb.Engine(0)
+            e.solve(p.copy(), sb.BAOptions(max_outer_iters=1))
+            e.close()
+        k = EkfEngine(0)
+        k.set_state(fr["P"], fr["x"])
+        k.ransac_consensus(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["meas_var"], fr["camera"], 0.3)
+        k.update(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+        k.close()
+    cycle(); cycle()                                               # one-time costs (module load, CUDA graphs cache) settle first
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for _ in range(4):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < 8 << 20, "device memory shrank by %.1f MB over 4 create/destroy cycles" % ((free0 - free1) / 1e6)
+
+
+def test_ekf_update_refuses_a_non_positive_definite_innovation_covariance():
+    """srk_ekf_update* must check the Cholesky info before P or x are touched and say so, instead of returning NaNs with SRK_OK."""
+    import surikatoko_b200 as sb
+    from surikatoko_b200.ekf import EkfEngine, synthetic_ekf_frame
+    fr = synthetic_ekf_frame(40, 3, seed=2)
+    ekf = EkfEngine(0)
+    try:
+        ekf.set_state(fr["P"], fr["x"])
+        with pytest.raises(sb.SrkError) as ei:
+            ekf.update(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], -1.0e6)     # S = H P H^T - 1e6 I: indefinite
+        assert ei.value.code == -6 and "positive definite" in str(ei.value)
+        P, x = ekf.get_state()
+        assert np.array_equal(P, fr["P"]) and np.array_equal(x, fr["x"]), "the resident state must be untouched"
+        Ph = np.asfortranarray(fr["P"].copy()); xh = fr["x"].copy()
+        with pytest.raises(sb.SrkError):
+            ekf.update_host(Ph, xh, np.ascontiguousarray(fr["Hcam"]), np.ascontiguousarray(fr["Hpt"]), fr["pt_off"], np.ascontiguousarray(fr["z"]),
+                            np.ascontiguousarray(fr["h"]), -1.0e6)
+        assert np.array_equal(Ph, fr["P"]) and np.array_equal(xh, fr["x"]), "the caller's buffers must be untouched"
+        assert ekf.update(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"]) == 0   # and the handle stays usable
+    finally:
+        ekf.close()
