@@ -295,6 +295,20 @@ def ekf_update(P, x, Hcam, Hpt, pt_off, z, hpred, meas_var, fix_symmetry=True):
     return rc == 0, np.array(Pn), xn, sec.value
 
 
+def ekf_update_exact(P, x, Hcam, Hpt, pt_off, z, hpred, meas_var, fix_symmetry=True):
+    """The same update in long double through S = L L^T, Y = L^-1 H P, P - Y^T Y (srk_oracle_ekf_exact.hpp): the parity target at the
+    sizes where the reference's explicit-inverse chain is itself ~cond(S) * eps off.  Returns (ok, P_new, x_new)."""
+    Pn = np.asfortranarray(np.array(P, dtype=np.float64)); xn = np.array(x, dtype=np.float64)
+    n = xn.shape[0]; m = len(pt_off); s = Hpt.shape[1]
+    Hc = np.ascontiguousarray(Hcam, dtype=np.float64); Hp = np.ascontiguousarray(Hpt, dtype=np.float64)
+    off = np.ascontiguousarray(pt_off, dtype=np.int64)
+    zz = np.ascontiguousarray(z, dtype=np.float64); hh = np.ascontiguousarray(hpred, dtype=np.float64)
+    rc = lib().srk_oracle_ekf_update_exact(C.c_int64(n), C.c_int64(m), Pn.ctypes.data_as(C.POINTER(C.c_double)), _p(xn, C.c_double), _p(Hc, C.c_double),
+                                           _p(Hp, C.c_double), _p(off, C.c_int64), C.c_int(s), _p(zz, C.c_double), _p(hh, C.c_double), C.c_double(meas_var),
+                                           C.c_int(1 if fix_symmetry else 0))
+    return rc == 0, np.array(Pn), xn
+
+
 def ekf_camera(fx_pix, fy_pix, cx, cy, dx_mm, dy_mm, k1, k2, enable_distortion=True):
     return np.array([fx_pix, fy_pix, cx, cy, dx_mm, dy_mm, k1, k2, 1.0 if enable_distortion else 0.0], dtype=np.float64)
 

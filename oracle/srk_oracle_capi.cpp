@@ -9,6 +9,7 @@
 #include "srk_oracle_ba.hpp"
 #include "srk_oracle_scene.hpp"
 #include "srk_oracle_ekf.hpp"
+#include "srk_oracle_ekf_exact.hpp"
 #include "srk_oracle_ekf_ransac.hpp"
 
 using namespace srk_oracle;
@@ -343,6 +344,11 @@ int srk_oracle_ekf_update(int64_t n, int64_t m, double* P, double* x, const doub
     std::memcpy(P, Pm.d.data(), sizeof(double) * (size_t)n * (size_t)n);
     std::memcpy(x, xs.data(), sizeof(double) * (size_t)n);
     return ok ? 0 : 1;
+}
+// The same update evaluated in long double through the Cholesky form (srk_oracle_ekf_exact.hpp): the parity target at large n.
+int srk_oracle_ekf_update_exact(int64_t n, int64_t m, double* P, double* x, const double* Hcam, const double* Hpt, const int64_t* pt_off, int s,
+                                const double* z, const double* hpred, double meas_var, int fix_symmetry) {
+    return EkfStackedUpdateExact(n, m, P, x, Hcam, Hpt, pt_off, s, z, hpred, meas_var, fix_symmetry != 0) ? 0 : 1;
 }
 // OnePointRansac_GetConsensusMatches (EKF.cpp:1271-1391).  cam9 = {fx_pix, fy_pix, cx, cy, dx_mm, dy_mm, k1, k2, enable_distortion}.
 // Returns the winning hypothesis or -1.  project_only != 0: just fills hd_out[2m] with the projections at the given state.

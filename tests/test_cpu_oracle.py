@@ -274,6 +274,11 @@ def test_ekf_oracle_is_pinned_by_an_independent_long_double_evaluation(oracle, n
     # the explicit-inverse chain in double is ~cond(S) * eps away from the long-double evaluation
     assert relerr(x_o, x1.astype(np.float64)) < 5e-10
     assert relerr(P_o, P1.astype(np.float64)) < 5e-10
+    # the oracle's own long-double evaluation (ekf_update_exact, the parity target at large n) is the same computation in C++
+    ok, P_e, x_e = oracle.ekf_update_exact(fr["P"], fr["x"], fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
+    assert ok
+    assert relerr(x_e, x1.astype(np.float64)) < 1e-15
+    assert relerr(P_e, P1.astype(np.float64)) < 1e-14
 
 
 def test_ekf_predict_oracle_matches_block_formula(oracle):
