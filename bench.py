@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """Benchmark of the BA hot path (BASELINE.json metric: BA LM iterations/s and reprojection residuals/s).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5|tiny]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5|tri|tiny] [--scaling strong|weak]
 
 A step = one Levenberg-Marquardt outer iteration (one derivative pass, then solve attempts + trial-state error
 evaluations until the error decreases) from the same resident initial state (srk_ba_reset between steps).
-`value` = reprojection residuals carried through full LM iterations per second, summed over all ranks, inputs resident
-in HBM.  `e2e` = the same through srk_ba_solve with HOST buffers (H2D of the scene and D2H of the refined state inside
-the timed region).  Weak scaling: every rank owns its own 1M points / 10M observations of one shared 1000-camera world;
-the reduced camera system is all-reduced over NCCL and solved redundantly on every rank.
+`value` = reprojection residuals carried through full LM iterations per second over the whole job, inputs resident in HBM.
+`e2e` = the same through srk_ba_solve with HOST buffers (H2D of the scene and D2H of the refined state inside the timed region).
+N > 1 (torchrun, one rank per GPU): STRONG scaling by default -- the ONE 1000-camera x 1M-point x 10M-observation problem of
+BASELINE.json configs[2], its points sharded over the ranks (scenes.shard_points), the partial reduced camera systems summed over
+NCCL, the solve replicated; the line then also carries `multi_gpu_parity` (the sharded step against the unsharded one, measured
+outside the timed region) and `weak_scaling` (every rank its own 1M points, the round-1 measurement) as extra keys.
+At N = 1 the default line also carries `other_configs`: short runs of configs[1] (circle-grid demo scene), configs[3] (EKF) and
+configs[4] (city scale, PCG), each with its own roofline figure.
 
---impl reference times the CPU oracle (the reference's algorithm restated in plain C++, single-threaded like the
-reference) on a bounded sample of the same workload shape.
+--impl reference times the CPU oracle (the reference's algorithm restated in plain C++) on the host cores: for c3 the SAME
+configuration through the oracle's threaded sparse flow (see cpu_oracle_run for what that substitutes).
 """
 import argparse
 import json
@@ -29,28 +33,38 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (n_cams, n_points, obs_per_point, description)
     "c3": (1000, 1_000_000, 10, "synthetic large-scale BA: 1,000 cameras x 1M points x 10M observations (BASELINE.json configs[2])"),
-    "c2": (50, 10_000, 50, "synthetic circle-grid-shaped BA: 50 cameras x 10k points, every point in every frame (configs[1])"),
+    "c2": (50, 10_000, 50, "synthetic circle-grid scene BA: the demo-circle-grid scene at 50 cameras x 10k points, every point in every frame (configs[1])"),
     "c5": (10_000, 5_000_000, 10, "synthetic city-scale BA: 10,000 cameras x 5M points x 50M observations, PCG solve (configs[4])"),
     "tiny": (40, 4000, 8, "tiny ring scene (smoke)"),
     "c3s": (1000, 50_000, 10, "profiling aid: the 1,000-camera reduced system of configs[2] with 50k points"),
     "tri": (1000, 1_000_000, 10, "front end (SURVEY 8f row 1): linear triangulation of 1M tracks x 10 corners, the scene of configs[2]"),
     "c4": (0, 2000, 0, "Davison MonoSLAM EKF with 2,000 salient points: dense 6013x6013 covariance predict + stacked update per frame (configs[3])"),
 }
-# bounded CPU sample of each workload (same generator, fewer cameras/points so the oracle finishes in ~10-30 s)
-CPU_SAMPLES = {"tri": (1000, 200_000, 10), "c3": (100, 100_000, 10), "c2": (50, 2_000, 50), "c5": (100, 100_000, 10), "tiny": (40, 4000, 8), "c3s": (100, 100_000, 10), "c4": (0, 250, 0)}
+# CPU arm: c3 / c3s / c2 / tiny run the SAME configuration as the GPU arm (c3: the oracle's threaded sparse flow, see cpu_oracle_run);
+# the others a bounded sample of the same generator
+CPU_SAMPLES = {"tri": (1000, 200_000, 10), "c5": (1000, 500_000, 10), "c4": (0, 250, 0)}
 METRIC = "BA reprojection residuals/sec through full LM iterations"
 UNIT = "residuals/s"
 
 
-def make_scene(name, rank=0, sample=False):
+def make_scene(name, rank=0, world=1, scaling="strong", sample=False):
+    """The workload's scene.  strong scaling (default): ONE problem of the named size, points sharded over the ranks in contiguous
+    pnt_ind ranges balanced by observation count (scenes.shard_points), cameras replicated.  weak: every rank its own points of the
+    same world.  Returns (problem of this rank, total observations of the whole job's problem or None)."""
     from surikatoko_b200 import scenes
-    M, N, k = CPU_SAMPLES[name] if sample else WORKLOADS[name][:3]
+    if name == "c2" and not sample:
+        pr = scenes.circle_grid_config()
+        return (scenes.shard_points(pr, rank, world)[0] if world > 1 else pr)
+    M, N, k = CPU_SAMPLES[name] if (sample and name in CPU_SAMPLES) else WORKLOADS[name][:3]
     bundle_path = os.environ.get("SRK_BENCH_BUNDLE", "")     # a scene written once by `python -m surikatoko_b200.bundle write` and shared
-    if bundle_path and not sample and rank == 0:
+    if bundle_path and not sample and rank == 0 and world == 1:
         from surikatoko_b200 import bundle
         pr = bundle.read_bundle(bundle_path)
         assert (pr.n_cams, pr.n_points) == (M, N), "bundle file does not hold the %s workload" % name
         return pr
+    if world > 1 and scaling == "strong":
+        full = scenes.ring_scene(M, N, k, seed=1234)
+        return scenes.shard_points(full, rank, world)[0]
     return scenes.ring_scene(M, N, k, seed=1234, point_offset=rank)
 
 
@@ -100,41 +114,104 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_oracle_run(name, steps, warmup):
-    """Oracle (the reference's algorithm, plain C++17, 1 thread) on the bounded sample: residuals/s through LM iterations."""
+def job_config(name, n_cams, n_points, n_obs, world, scaling):
+    """`config` of the JSON line: names the workload of the whole job; identical in both arms (arm-specific facts go to `config_detail`)."""
+    return {"workload": WORKLOADS[name][3], "n_cams": int(n_cams), "n_points": int(n_points), "n_obs": int(n_obs),
+            "l2": ("inputs larger than L2 (the job's Jacobian store is %.2f GB, its observations %.2f GB)" % (224.0 * n_obs / 1e9, 24.0 * n_obs / 1e9))
+                  if 224.0 * n_obs > 126e6 * max(1, world) else "smoke-sized workload: fits in L2, not a measurement configuration",
+            "parallelism": "dp%d: %s" % (world, "one problem, points sharded in contiguous ranges balanced by observation count, cameras replicated (strong scaling)"
+                                         if scaling == "strong" else "every rank its own points of one shared camera world (weak scaling)")}
+
+
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_run(name, steps, warmup, budget_s=270.0):
+    """The CPU arm: the oracle (the reference's algorithm restated in plain C++17) on the host cores, one LM iteration per step.
+
+    c3 / c3s: the SAME configuration as the GPU arm through the oracle's threaded sparse flow (per-point / per-frame passes on all
+    host threads, camera-pair blocks merged in thread order, skyline Cholesky of the block-banded system in place of the reference's
+    dense Householder QR, which alone needs 1.3e12 flop at n_f = 9993) -- faster than the single-threaded reference would be, so the
+    GPU/CPU ratio it yields is conservative.  c2 / tiny: the same configuration through the reference's own data flow restricted to the
+    non-zero blocks + Householder QR, one thread like the reference.  c5: a bounded sample (1000 cameras x 500k points) of the same
+    generator through the threaded flow.  Steps beyond `budget_s` of CPU time are dropped (and the count reported says so)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_lib as ol
     ol.build()
-    pr = make_scene(name, sample=True)
+    sample = name in CPU_SAMPLES
+    pr = make_scene(name, sample=sample)
     op = ol.Problem(pr.obs_cam, pr.obs_point, pr.obs_xy, pr.points, pr.cams, pr.K, False, pr.f0)
-    times, iters = [], []
-    for i in range(warmup + steps):
-        if i < warmup and i > 0:
-            continue  # one warm-up pass is enough to page the library and the scene in
-        r = ol.ba_solve(op, max_outer_iters=1, flow="sparse", solve="qr", acc="double")
-        if i >= warmup:
-            times.append(r.seconds); iters.append(max(1, r.outer_iters))
+    threaded = name in ("c3", "c3s", "c5")
+    kw = dict(flow="threaded", solve="chol") if threaded else dict(flow="sparse", solve="qr")
+    cores = cpu_threads() if threaded else 1
+    if threaded:
+        os.environ.setdefault("SRK_ORACLE_THREADS", str(cores))
+    times, done_warm, t_all = [], 0, time.perf_counter()
+    n_total = warmup + steps
+    i = 0
+    while i < n_total:
+        r = ol.ba_solve(op, max_outer_iters=1, acc="double", **kw)
+        if i < warmup:
+            done_warm += 1
+        else:
+            times.append(r.seconds)
+        i += 1
+        spent = time.perf_counter() - t_all
+        per = spent / i
+        if i < warmup and spent + (n_total - i) * per > budget_s:     # the plan does not fit the budget: stop warming, start timing
+            n_total -= warmup - i
+            warmup = i
+        if times and spent + per > budget_s:
+            break
     t = float(np.sum(times))
-    M, N, k = CPU_SAMPLES[name]
-    return {"value": pr.n_obs * len(times) / t, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": "ring scene %d cameras x %d points x %d observations (same generator and seed as the GPU workload), %d LM iteration(s), "
-                      "oracle sparse-equivalent flow + Householder QR, single thread like the reference" % (M, N, pr.n_obs, len(times)),
-            "seconds_per_iteration": t / len(times), "n_obs": pr.n_obs}
+    what = ("%d cameras x %d points x %d observations" % (pr.n_cams, pr.n_points, pr.n_obs))
+    how = ("oracle threaded sparse flow on %d host threads + skyline Cholesky (reference: one thread, dense Householder QR)" % cores) if threaded else \
+          "oracle sparse-equivalent flow + Householder QR, single thread like the reference"
+    return {"value": pr.n_obs * len(times) / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": ("%s: %s, %d LM iteration(s) timed, %s" % ("bounded sample of the same generator" if sample else "the full configuration of the GPU arm", what, len(times), how)),
+            "seconds_per_iteration": t / len(times), "n_obs": pr.n_obs, "steps_timed": len(times), "warmup_done": done_warm, "same_config": not sample, "shape": (pr.n_cams, pr.n_points, pr.n_obs),
+            "err_initial": r.err_initial, "err_after_step": float(r.err_trace[0]) if len(r.err_trace) else None}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3)); warmup = 1 if args.warmup > 0 else 0
-    cb = cpu_oracle_run(args.workload, steps, warmup)
-    out = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-           "ms_per_step": cb["seconds_per_iteration"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+    if args.workload == "c4":
+        return run_reference_ekf(args)
+    cb = cpu_oracle_run(args.workload, max(1, args.steps), max(0, args.warmup))
+    out = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps_timed"], "warmup": cb["warmup_done"],
+           "ms_per_step": cb["seconds_per_iteration"] * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "impl": "reference",
-           "config": {"workload": WORKLOADS[args.workload][3], "sample": cb["sample"]},
+           "config": job_config(args.workload, *cb["shape"], args.gpus, "strong") if cb["same_config"] else {"workload": WORKLOADS[args.workload][3], "sample": cb["sample"]},
+           "config_detail": {"cpu_arm": cb["sample"], "same_config_as_gpu_arm": cb["same_config"]},
            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+           "err_initial": cb["err_initial"], "err_after_step": cb["err_after_step"]}
     emit(out)
+
+
+def run_reference_ekf(args):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_lib as ol
+    from surikatoko_b200.ekf import synthetic_ekf_frame
+    ol.build()
+    sm = synthetic_ekf_frame(CPU_SAMPLES["c4"][1], 3, seed=1234)
+    secs = []
+    for _ in range(max(1, min(args.steps, 5))):
+        ok, _, _, sec = ol.ekf_update(sm["P"], sm["x"], sm["Hcam"], sm["Hpt"], sm["pt_off"], sm["z"], sm["h"], sm["meas_var"])
+        secs.append(sec)
+    v = len(secs) / float(np.sum(secs))
+    sample = "stacked update with %d salient points (n = %d, 2m = %d): the reference's dense H*P, LU inverse, K, P - K S K^T chain, one thread" % (sm["m"], sm["n"], 2 * sm["m"])
+    emit({"metric": "MonoSLAM EKF frames/sec (covariance predict + stacked update)", "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(secs), "warmup": 0,
+          "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+          "config": {"workload": WORKLOADS["c4"][3], "cpu_arm": sample, "same_config_as_gpu_arm": False},
+          "cpu_baseline": {"value": v, "unit": "frames/s", "cores": 1, "kind": "port", "sample": sample},
+          "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 def fp64_gemm_peak(torch, dev):
@@ -152,23 +229,23 @@ def fp64_gemm_peak(torch, dev):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
-def run_ours(args):
+def dist_env():
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def measure_ba(args, name, steps, warmup, scaling="strong", full=True):
+    """One BA workload on this job's GPUs -> the contract's dict on rank 0 (None elsewhere).  full=False: the short form used for the
+    `other_configs` block (no CPU leg, no multi-GPU extras)."""
     import torch
     import torch.distributed as dist
     import surikatoko_b200 as sb
 
-    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
-    torch.cuda.set_device(local)
+    world, rank, local = dist_env()
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    name = args.workload
-    M, N, k, desc = WORKLOADS[name]
-
-    prob = make_scene(name, rank=rank)
-    O = prob.n_obs
+    M, N_full, k, desc = WORKLOADS[name]
+    prob = make_scene(name, rank=rank, world=world, scaling=scaling)
+    M = prob.n_cams
+    O, N = prob.n_obs, prob.n_points
     # pinned host copies (the e2e leg copies from these)
     def pin(a):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -181,9 +258,14 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     eng = sb.Engine(local)
     eng.set_stream(stream.cuda_stream)
+    exchange = "none"
     if world > 1:
-        from surikatoko_b200.dist import attach_allreduce
-        attach_allreduce(eng, stream, dev)
+        # default: the library's own NCCL communicator (C++ host path, srk_ba_nccl_init); SRK_BENCH_ALLREDUCE=torch: torch.distributed callback
+        from surikatoko_b200.dist import attach_allreduce, attach_nccl
+        if os.environ.get("SRK_BENCH_ALLREDUCE", "nccl") == "torch":
+            attach_allreduce(eng, stream, dev); exchange = "torch.distributed all_reduce callback (NCCL)"
+        else:
+            attach_nccl(eng); exchange = "ncclAllReduce issued by the library on its stream (srk_ba_nccl_init)"
 
     solver = {"c5": sb.SOLVER_BLOCK_PCG}.get(name, sb.SOLVER_AUTO)
     opt1 = sb.BAOptions(max_outer_iters=1, solver=solver)
@@ -193,11 +275,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    parity = None
+    weak = None
     with torch.cuda.stream(stream):
         assert eng.bind(prob, opt1), "gauge normalisation failed on the synthetic scene"
         # ---------------- device-resident steps
         launches = 0
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             eng.reset(); rep = eng.run(opt1)
         barrier()
         eng.set_timing(True)
@@ -205,7 +289,7 @@ def run_ours(args):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         attempts = 0
-        for _ in range(args.steps):
+        for _ in range(steps):
             eng.reset(); rep = eng.run(opt1)
             launches += rep.gpu_launches + 1; attempts += rep.attempts_count
         e1.record(stream)
@@ -213,11 +297,15 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         clk = clocks.stop()
         timing = eng.get_timing()
+        pcg = eng.pcg_stats()
         eng.set_timing(False)
+        # ---------------- multi-GPU parity, outside the timed region: the sharded step against the unsharded one on rank 0's GPU
+        if world > 1 and full and scaling == "strong":
+            parity = multi_gpu_parity(torch, dist, sb, eng, opt1, name, rank, world, local, dev)
         # ---------------- end to end through srk_ba_solve with host buffers
         # every step is one srk_ba_solve call on its own pinned host copy of the scene state (the call refines points and poses in
         # place, so a step cannot reuse the previous step's buffers; preparing the copies is not part of a step)
-        e2e_steps = max(1, min(args.steps, 5))
+        e2e_steps = max(1, min(steps, 5))
         fresh = []
         for i in range(1 + e2e_steps):
             tp, vp = pin(pts0); tc, vc = pin(cams0); keep += [tp, tc]; fresh.append((vp, vc))
@@ -229,16 +317,30 @@ def run_ours(args):
         g1 = torch.cuda.Event(enable_timing=True); g1.record(stream)
         barrier()
         ms_e2e = max(g0.elapsed_time(g1), (time.perf_counter() - t0) * 1e3)
+        # ---------------- weak scaling as an extra key (every rank its own points of the same 1000-camera world)
+        if world > 1 and full and scaling == "strong":
+            wprob = make_scene(name, rank=rank, world=world, scaling="weak")
+            assert eng.bind(wprob, opt1)
+            for _ in range(3):
+                eng.reset(); eng.run(opt1)
+            barrier()
+            w0 = torch.cuda.Event(enable_timing=True); w1 = torch.cuda.Event(enable_timing=True)
+            wsteps = max(1, min(steps, 10))
+            w0.record(stream)
+            for _ in range(wsteps):
+                eng.reset(); eng.run(opt1)
+            w1.record(stream)
+            barrier()
+            weak = (w0.elapsed_time(w1), wsteps, float(wprob.n_obs))
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
-    tot_obs = torch.tensor([float(O)], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, weak[0] if weak else 0.0], device=dev, dtype=torch.float64)
+    tot = torch.tensor([float(O), weak[2] if weak else 0.0, float(N)], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(tot_obs, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = float(t[0]), float(t[1]); total_obs = float(tot_obs[0])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = float(t[0]), float(t[1]); total_obs = float(tot[0]); total_pts = float(tot[2])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        eng.close()
+        return None
 
     peaks = {}
     try:
@@ -248,12 +350,13 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     f64_peak = fp64_gemm_peak(torch, dev)
     nf = 10 * M - 7
-    # algorithmic bytes / flops per launch (DESIGN.md "Kernels")
+    # algorithmic bytes / flops per launch of THIS rank's kernels (DESIGN.md "Kernels")
     kk = O / max(N, 1)                                  # observations per point
     schur_flops = N * (300.0 * kk * (kk + 1) + 330.0 * kk + 60.0)   # block products F_i^T W_l over the pairs of a track, F, W = E^-1 F, rhs, E
     solve_flops, solve_note = nf ** 3 / 3.0 + 2.0 * nf * nf, "dense n_f^3/3"
     stats = None
-    if rep.solver_used == 1:
+    is_pcg = rep.solver_used != 1
+    if not is_pcg:
         try:
             stats = eng.solve_stats()
             # flops the factorisation executed (zero 64x64 tiles are skipped) + 2 x (forward + backward) substitutions over the non-zero tiles
@@ -265,11 +368,23 @@ def run_ours(args):
                     stats["parts"], stats["max_part_blocks"], stats["separator_blocks"])
         except Exception as ex:  # pragma: no cover
             solve_note += " (solve_stats unavailable: %s)" % ex
-    schur_bytes = 232.0 * O + 72.0 * N + 8.0 * nf * nf + 80.0 * M
-    # K2 is a DMMA contraction: its 3.6e10 flop take 1.0 ms at the FP64 peak, its 3.2 GB 0.5 ms at the HBM peak -> the FP64 tensor pipe bounds it
+    # stored entries of the reduced system: the non-zero 64x64 tiles of the dense layout / the 10x10 blocks of the block-sparse one
+    if is_pcg:
+        nnz_S = 100.0 * pcg["nnz_blocks"]
+    elif stats is not None and stats.get("parts", 0) > 0:
+        nnz_S = min(float(nf) * nf, 4096.0 * stats["nonzero_tiles"])
+    else:
+        nnz_S = float(nf) * nf
+    schur_bytes = 232.0 * O + 72.0 * N + 8.0 * nnz_S + 80.0 * M
+    # K2 is a DMMA contraction: its 3.6e10 flop take 1.0 ms at the FP64 peak, its bytes 0.5 ms at the HBM peak -> the FP64 tensor pipe bounds it
     alg = {"jacobian": ("hbm", 248.0 * O + 24.0 * N + 200.0 * M), "schur": ("tensor" if schur_flops / (f64_peak * 1e12) > schur_bytes / (hbm_peak * 1e9) else "hbm", None),
            "backsub": ("hbm", 232.0 * O + 72.0 * N + 80.0 * M + 24.0 * N), "residual": ("hbm", 24.0 * O + 24.0 * N + 200.0 * M),
            "frame_blocks": ("hbm", 20.0 * O + 24.0 * N + 200.0 * M + 880.0 * M), "solve": ("tensor", solve_flops)}
+    if is_pcg:   # executed work of the PCG solves: per iteration one block-sparse mat-vec (800 B per stored block, mirrored blocks re-read) + 5 vectors
+        n_solves = max(1, timing["solve"]["count"])
+        alg["solve"] = ("hbm", (pcg["iters"] / n_solves) * (800.0 * (2 * pcg["nnz_blocks"] - M) + 40.0 * 10 * M))
+        solve_note = "PCG: %.0f iterations per solve x (800 B x %d block reads + 40 B x %d unknowns); the system (%.2f GB) is L2-resident, so the HBM figure is an upper bound view" % (
+            pcg["iters"] / n_solves, 2 * pcg["nnz_blocks"] - M, 10 * M, 800.0 * pcg["nnz_blocks"] / 1e9)
     traffic = {}
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name, {})
@@ -285,20 +400,25 @@ def run_ours(args):
         if bound == "hbm":
             ach = work / (avg_ms * 1e-3) / 1e9
             kernels[fam] = {"bound": "hbm", "avg_ms": avg_ms, "launch_groups": tm["count"], "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": ach / hbm_peak, "share_of_step": tm["ms_total"] / ms, "traffic": traffic.get(fam)}
+                            "frac": ach / hbm_peak, "share_of_step": tm["ms_total"] / ms, "traffic": traffic.get(fam) if world == 1 else None}
         else:
             ach = work / (avg_ms * 1e-3) / 1e12
             kernels[fam] = {"bound": "tensor", "avg_ms": avg_ms, "launch_groups": tm["count"], "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s",
-                            "frac": ach / f64_peak, "share_of_step": tm["ms_total"] / ms, "traffic": traffic.get(fam)}
-    if "schur" in kernels:   # both views of K2: FP64 tensor pipe (37 kflop per point) and HBM (3.2 GB per launch)
+                            "frac": ach / f64_peak, "share_of_step": tm["ms_total"] / ms, "traffic": traffic.get(fam) if world == 1 else None}
+    if "schur" in kernels:   # both views of K2: FP64 tensor pipe (37 kflop per point) and HBM
         t = kernels["schur"]["avg_ms"] * 1e-3
         kernels["schur"]["fp64"] = {"achieved": schur_flops / t / 1e12, "peak": f64_peak, "unit": "TFLOP/s", "frac": schur_flops / t / 1e12 / f64_peak,
                                     "flops": schur_flops}
         kernels["schur"]["hbm"] = {"achieved": schur_bytes / t / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": schur_bytes / t / 1e9 / hbm_peak,
                                    "bytes": schur_bytes}
     if "solve" in kernels:
-        kernels["solve"]["flops"] = solve_flops; kernels["solve"]["flops_counted"] = solve_note
-        kernels["solve"]["dense_equivalent_tflops"] = (nf ** 3 / 3.0) / (kernels["solve"]["avg_ms"] * 1e-3) / 1e12
+        kernels["solve"]["work_counted"] = solve_note
+        if not is_pcg:
+            kernels["solve"]["flops"] = solve_flops
+            kernels["solve"]["dense_equivalent_tflops"] = (nf ** 3 / 3.0) / (kernels["solve"]["avg_ms"] * 1e-3) / 1e12
+        else:
+            kernels["solve"]["pcg"] = {"iters_per_solve": pcg["iters"] / max(1, timing["solve"]["count"]), "nnz_blocks": pcg["nnz_blocks"],
+                                       "rel_res_last": rep.pcg_rel_res_last}
         if stats is not None:
             kernels["solve"]["structure"] = stats
     for fam in ("update", "allreduce", "solve_factor", "solve_trsv"):
@@ -316,39 +436,124 @@ def run_ours(args):
                             "%.0f %% of peak" % (schur_flops, schur_flops / (f64_peak * 1e12) * 1e3, schur_bytes / 1e9, schur_bytes / (hbm_peak * 1e9) * 1e3,
                                                  kernels["schur"]["hbm"]["achieved"], 100.0 * kernels["schur"]["hbm"]["frac"]))
     if dominant == "solve":
-        roofline["note"] = ("the reduced camera system of this scene is block-banded: the factorisation is a chain of %d dependent 64-column steps over "
-                            "few tiles, latency-bound, not FP64-throughput-bound; flops counted = %s" % ((nf + 63) // 64, solve_note))
+        roofline["note"] = ("solve of the reduced camera system; work counted = %s" % solve_note)
     # the bandwidth-bound kernels the north star names, as one group: algorithmic bytes over summed time
-    stream = [f for f in ("jacobian", "residual", "backsub") if f in kernels]
-    if stream:
-        tot_b = sum(alg[f][1] * timing[f]["count"] for f in stream); tot_t = sum(timing[f]["ms_total"] for f in stream) * 1e-3
-        kernels["streaming_group"] = {"members": stream, "achieved": tot_b / tot_t / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": tot_b / tot_t / 1e9 / hbm_peak}
-
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        cpu = cpu_oracle_run(name, 1, 0)
+    sgrp = [f for f in ("jacobian", "residual", "backsub") if f in kernels]
+    if sgrp:
+        tot_b = sum(alg[f][1] * timing[f]["count"] for f in sgrp); tot_t = sum(timing[f]["ms_total"] for f in sgrp) * 1e-3
+        kernels["streaming_group"] = {"members": sgrp, "achieved": tot_b / tot_t / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": tot_b / tot_t / 1e9 / hbm_peak}
 
     h2d = 24 * O + 24 * N + 96 * M + 72 * M
     d2h = 24 * N + 96 * M
-    steps_per_s = args.steps / (ms * 1e-3)
-    out = {"metric": METRIC, "value": total_obs * steps_per_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "lm_iters_per_sec": steps_per_s, "attempts_per_step": attempts / args.steps,
-           "config": {"workload": desc, "per_rank": {"n_cams": M, "n_points": N, "n_obs": int(O)}, "solver": "dense_cholesky" if rep.solver_used == 1 else "block_pcg",
-                      "l2": "inputs larger than L2 (Jacobian store %.2f GB per rank)" % (224.0 * O / 1e9), "parallelism": "points sharded, dp%d" % world},
+    steps_per_s = steps / (ms * 1e-3)
+    out = {"metric": METRIC, "value": total_obs * steps_per_s, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms / steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "lm_iters_per_sec": steps_per_s, "attempts_per_step": attempts / steps,
+           "config": job_config(name, M, total_pts, total_obs, world, scaling),
+           "config_detail": {"rank0": {"n_points": int(N), "n_obs": int(O)}, "solver": "dense_cholesky" if not is_pcg else "block_pcg", "exchange": exchange},
            "clocks": clk,
            "e2e": {"value": total_obs * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+                   "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps, "bytes_are": "rank 0's copies per step"},
            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "fp64_gemm_peak_tflops": f64_peak,
            "err_initial": rep.err_initial, "err_after_step": rep.err_final}
-    if cpu is not None:
+    if parity is not None:
+        out["multi_gpu_parity"] = parity
+    if weak is not None:
+        wms = float(t[2]); wobs = float(tot[1])
+        out["weak_scaling"] = {"value": wobs * weak[1] / (wms * 1e-3), "unit": UNIT, "ms_per_step": wms / weak[1], "steps": weak[1],
+                               "per_rank": {"n_points": N_full, "n_obs": int(wobs / world)},
+                               "note": "every rank its own %d points of the same %d-camera world; compare with the N=1 value of the strong line" % (N_full, M)}
+    eng.close()
+    return out
+
+
+def multi_gpu_parity(torch, dist, sb, eng, opt1, name, rank, world, local, dev):
+    """One LM iteration of the sharded job against the same iteration of the WHOLE problem on one GPU (rank 0's), outside the timed
+    region: relative deviation of the error after the step and of the refined cameras; and whether all ranks hold bit-identical
+    cameras and errors (they take the accept / reject decisions from them)."""
+    eng.reset(); rep = eng.run(opt1)
+    _, cams = eng.debug_get_state()
+    sig = np.frombuffer(cams.tobytes() + np.array([rep.err_final, rep.err_initial]).tobytes(), dtype=np.uint8)
+    tsig = torch.from_numpy(sig.copy()).to(dev)
+    gathered = [torch.empty_like(tsig) for _ in range(world)]
+    dist.all_gather(gathered, tsig)
+    identical = all(bool(torch.equal(g, gathered[0])) for g in gathered)
+    out = None
+    if rank == 0:
+        whole = make_scene(name, rank=0, world=1)
+        e1 = sb.Engine(local)
+        try:
+            assert e1.bind(whole, opt1)
+            r1 = e1.run(opt1)
+            _, cams1 = e1.debug_get_state()
+        finally:
+            e1.close()
+        dev_err = abs(rep.err_final - r1.err_final) / abs(r1.err_final)
+        dev_cam = float(np.max(np.abs(cams - cams1)) / np.max(np.abs(cams1)))
+        out = {"max_rel_dev": max(dev_err, dev_cam), "err_after_step_rel_dev": dev_err, "cameras_rel_dev": dev_cam, "ranks_identical": identical,
+               "err_initial_equal": rep.err_initial == r1.err_initial or abs(rep.err_initial - r1.err_initial) <= 1e-12 * abs(r1.err_initial),
+               "attempts_equal": rep.attempts_count == r1.attempts_count,
+               "what": "one LM iteration: %d-rank sharded job vs the whole problem on one GPU (same engine, no exchange)" % world}
+    dist.barrier()
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world, rank, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name = args.workload
+    out = measure_ba(args, name, args.steps, args.warmup, scaling=args.scaling, full=True)
+    if world == 1 and not args.no_cpu and out is not None:
+        # the CPU arm next to it: ONE LM iteration of the same configuration on the host cores (bounded: ~10-30 s of CPU work)
+        cpu = cpu_oracle_run(name, 1, 0)
         out["cpu_baseline"] = {kk: cpu[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
-    emit(out)
+        if cpu.get("err_after_step") is not None and cpu["same_config"]:
+            out["cpu_baseline"]["err_after_step_rel_dev_vs_gpu"] = abs(cpu["err_after_step"] - out["err_after_step"]) / abs(cpu["err_after_step"])
+    # the other BASELINE.json configurations, each a short run, so that the one driver-visible line covers configs[1], [3], [4] too
+    if world == 1 and name == "c3" and not args.no_others:
+        others = {}
+        for oname in ("c2", "c5"):
+            try:
+                o = measure_ba(args, oname, 5 if oname == "c2" else 3, 3, full=False)
+                others[oname] = {"workload": o["config"]["workload"], "value": o["value"], "unit": o["unit"], "ms_per_step": o["ms_per_step"],
+                                 "attempts_per_step": o["attempts_per_step"], "solver": o["config_detail"]["solver"],
+                                 "e2e": {"value": o["e2e"]["value"], "ms_per_step": o["e2e"]["ms_per_step"]},
+                                 "roofline": {kq: o["roofline"][kq] for kq in ("kernel", "bound", "achieved", "peak", "unit", "frac")},
+                                 "kernels": {f: {kq: v[kq] for kq in ("avg_ms", "frac", "share_of_step", "bound") if kq in v} for f, v in o["kernels"].items()},
+                                 "err_initial": o["err_initial"], "err_after_step": o["err_after_step"], "gpu_launches": o["gpu_launches"]}
+                if "pcg" in o["kernels"].get("solve", {}):
+                    others[oname]["pcg"] = o["kernels"]["solve"]["pcg"]
+            except Exception as ex:  # pragma: no cover
+                others[oname] = {"error": repr(ex)}
+        try:
+            o = measure_ekf(args, 5, 3, with_cpu=False, with_ransac=False)
+            others["c4"] = {"workload": o["config"]["workload"], "value": o["value"], "unit": o["unit"], "ms_per_step": o["ms_per_step"],
+                            "e2e": {"value": o["e2e"]["value"], "ms_per_step": o["e2e"]["ms_per_step"]},
+                            "roofline": {kq: o["roofline"][kq] for kq in ("kernel", "bound", "achieved", "peak", "unit", "frac")},
+                            "kernels": {f: {kq: v[kq] for kq in ("avg_ms", "frac", "share_of_step") if kq in v} for f, v in o["kernels"].items()},
+                            "gpu_launches": o["gpu_launches"]}
+        except Exception as ex:  # pragma: no cover
+            others["c4"] = {"error": repr(ex)}
+        out["other_configs"] = others
+    if out is not None:
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_ekf(args):
+    out = measure_ekf(args, args.steps, args.warmup, with_cpu=not args.no_cpu, with_ransac=True)
+    if out is not None:
+        emit(out)
+
+
+def measure_ekf(args, steps, warmup, with_cpu=True, with_ransac=True):
     """configs[3]: one step = one MonoSLAM frame (covariance predict + stacked update of all 2000 observed points) on the resident state."""
     import torch
     from surikatoko_b200.ekf import EkfEngine, synthetic_ekf_frame
@@ -363,7 +568,7 @@ def run_ekf(args):
     args_u = (fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"])
     with torch.cuda.stream(stream):
         eng.set_state(fr["P"], fr["x"])
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             eng.predict(fr["F"], fr["GQGt"], fr["x"][:13]); eng.update(*args_u)
         torch.cuda.synchronize()
         eng.set_state(fr["P"], fr["x"])
@@ -372,7 +577,7 @@ def run_ekf(args):
         clocks = ClockSampler(local); clocks.start()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             eng.predict(fr["F"], fr["GQGt"], fr["x"][:13]); info = eng.update(*args_u)
         e1.record(stream); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -382,7 +587,7 @@ def run_ekf(args):
         # e2e: one-shot host form, P travels both ways
         P = torch.from_numpy(np.asfortranarray(fr["P"]).T.copy()).pin_memory().numpy().T   # Fortran-ordered view of pinned memory
         x = fr["x"].copy()
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(steps, 3))
         for i in range(1 + e2e_steps):
             P[:, :] = fr["P"]; x[:] = fr["x"]
             if i == 1:
@@ -391,21 +596,24 @@ def run_ekf(args):
         torch.cuda.synchronize()
         ms_e2e = (time.perf_counter() - t0) * 1e3
         # 1-point RANSAC hypothesis scoring on a frame in the reference's camera model: 2000 hypotheses x 2000 projections
-        from surikatoko_b200.ekf import synthetic_ransac_frame
-        rf = synthetic_ransac_frame(npts, 3, seed=77)
-        eng.set_state(rf["P"], rf["x"])
-        r_args = (rf["Hcam"], rf["Hpt"], rf["pt_off"], rf["z"], rf["meas_var"], rf["camera"], 0.3)
-        for _ in range(2):
-            r_best, r_sup, _ = eng.ransac_consensus(*r_args)
-        eng.set_timing(True)
-        t0r = time.perf_counter()
-        for _ in range(5):
-            eng.ransac_consensus(*r_args)
-        torch.cuda.synchronize()
-        ransac_call_ms = (time.perf_counter() - t0r) * 1e3 / 5
-        tm_r = eng.get_timing()["ransac"]; eng.set_timing(False)
+        tm_r = {"count": 0}
+        if with_ransac:
+            from surikatoko_b200.ekf import synthetic_ransac_frame
+            rf = synthetic_ransac_frame(npts, 3, seed=77)
+            eng.set_state(rf["P"], rf["x"])
+            r_args = (rf["Hcam"], rf["Hpt"], rf["pt_off"], rf["z"], rf["meas_var"], rf["camera"], 0.3)
+            for _ in range(2):
+                r_best, r_sup, _ = eng.ransac_consensus(*r_args)
+            eng.set_timing(True)
+            t0r = time.perf_counter()
+            for _ in range(5):
+                eng.ransac_consensus(*r_args)
+            torch.cuda.synchronize()
+            ransac_call_ms = (time.perf_counter() - t0r) * 1e3 / 5
+            tm_r = eng.get_timing()["ransac"]; eng.set_timing(False)
+    eng.close()
     if rank != 0:
-        return
+        return None
     f64_peak = fp64_gemm_peak(torch, dev)
     flops = {"chol": m2 ** 3 / 3.0, "trsm": float(n) * m2 * m2, "syrk": float(n) * n * m2}   # the algorithmic minimum of the chain
     kernels = {}
@@ -419,7 +627,7 @@ def run_ekf(args):
             kernels[fam].update({"bound": "tensor", "achieved": ach, "peak": f64_peak, "unit": "TFLOP/s", "frac": ach / f64_peak})
     dom = max((f for f in kernels if "frac" in kernels[f]), key=lambda f: kernels[f]["share_of_step"])
     cpu = None
-    if not args.no_cpu:
+    if with_cpu:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle_lib as ol
         ol.build()
@@ -428,8 +636,8 @@ def run_ekf(args):
         cpu = {"value": 1.0 / sec, "unit": "frames/s", "cores": 1, "kind": "port",
                "sample": "stacked update with %d salient points (n = %d, 2m = %d): the reference's dense H*P, LU inverse, K, P - K S K^T chain, one thread; "
                          "its cost grows ~cubically with the point count" % (sm["m"], sm["n"], 2 * sm["m"])}
-    out = {"metric": "MonoSLAM EKF frames/sec (covariance predict + stacked update)", "value": args.steps / (ms * 1e-3) * world, "unit": "frames/s", "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    out = {"metric": "MonoSLAM EKF frames/sec (covariance predict + stacked update)", "value": steps / (ms * 1e-3) * world, "unit": "frames/s", "n_gpus": world,
+           "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic",
            "config": {"workload": WORKLOADS["c4"][3], "n_state": n, "n_observed": fr["m"], "parallelism": "replicas only (a single filter is one dense chain)",
                       "l2": "covariance %.0f MB + P*H^T %.0f MB exceed L2" % (8.0 * n * n / 1e6, 8.0 * n * m2 / 1e6)},
@@ -450,7 +658,7 @@ def run_ekf(args):
                          "kernel_ms": k_ms, "call_ms_host_buffers": ransac_call_ms, "hypotheses_per_s": rf["m"] / (k_ms * 1e-3), "bound": "hbm",
                          "achieved": rbytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": rbytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                          "best": int(r_best), "support_of_best": int(r_sup.max())}
-        if not args.no_cpu:
+        if with_cpu:
             rs = synthetic_ransac_frame(300, 3, seed=77)
             t0c = time.perf_counter()
             ol.ekf_ransac(rs["P"], rs["x"], rs["Hcam"], rs["Hpt"], rs["pt_off"], rs["z"], rs["meas_var"], rs["camera"].as_array(), 0.3)
@@ -459,7 +667,7 @@ def run_ekf(args):
                                              "sample": "%d matched points (n = %d): per hypothesis an n x 2 gain and %d projections, as the reference does; cost ~ m * (n + m)" % (rs["m"], rs["n"], rs["m"])}
     if cpu is not None:
         out["cpu_baseline"] = cpu
-    emit(out)
+    return out
 
 
 RESULT = sys.stdout
@@ -549,6 +757,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other BASELINE.json configurations (other_configs)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"], help="N > 1: one problem sharded over the ranks (default) or every rank its own points")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

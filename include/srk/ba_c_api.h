@@ -138,6 +138,15 @@ SRK_API int srk_ba_fetch(void* h, srk_ba_problem* problem);                     
  * all cameras replicated; the engine reduces G, g_f, S, rhs and the error partials. */
 typedef int (*srk_allreduce_fn)(void* user, double* dev, int64_t count, void* stream);
 SRK_API int srk_ba_set_allreduce(void* h, srk_allreduce_fn fn, void* user, int rank, int world_size);
+/* The same exchange without a host callback (no Python in the loop): the library binds NCCL itself (dlopen of libnccl.so.2, so
+ * single-GPU users need no NCCL) and all-reduces on the handle's stream with ncclAllReduce(ncclDouble, ncclSum) -- SURVEY.md
+ * section 7 step 6 / 8e.  Create the 128-byte id on rank 0 (srk_nccl_unique_id), hand it to every rank over any channel (MPI,
+ * a file, torch.distributed), then every rank calls srk_ba_nccl_init (collective: it returns when all ranks have joined).
+ * srk_ba_set_nccl_comm adopts a communicator the host already owns (an ncclComm_t; it is not destroyed with the handle). */
+#define SRK_NCCL_UNIQUE_ID_BYTES 128
+SRK_API int srk_nccl_unique_id(unsigned char* id128);
+SRK_API int srk_ba_nccl_init(void* h, const unsigned char* id128, int rank, int world_size);
+SRK_API int srk_ba_set_nccl_comm(void* h, void* nccl_comm, int rank, int world_size);
 
 /* Parity hooks: one derivative pass (+ one two-phase solve at damping c when c >= 0) on the resident normalised state.
  * Any output may be null.  Layouts match oracle/srk_oracle_capi.cpp::srk_oracle_derivs_and_solve:
@@ -175,6 +184,9 @@ SRK_API int srk_ba_solve_stats(void* h, int64_t* n_f, int64_t* block_rows, int64
  * block columns) followed by a separator of separator_blocks block columns; ordered_n = n_f + padding to 64-column part boundaries.
  * SRK_SOLVE_ORDER=0 in the environment of srk_ba_create forces capture order. */
 SRK_API int srk_ba_solve_order(void* h, int64_t* ordered_n, int64_t* parts, int64_t* max_part_blocks, int64_t* separator_blocks);
+/* Block-sparse (PCG) path: stored 10x10 blocks of the reduced camera system (lower block triangle incl. the diagonal) and the PCG
+ * iterations executed since srk_ba_set_timing(h, 1) -- the work bench.py's roofline of that solve is computed from. */
+SRK_API int srk_ba_pcg_stats(void* h, int64_t* nnz_blocks, int64_t* iters_since_timing);
 
 #ifdef __cplusplus
 }

@@ -118,6 +118,7 @@ def read_bundle(path):
     return Problem(obs_cam, obs_point, obs_xy, points, cams, K, shared_K, f0)
 
 
+_FLOW = {"dense": 0, "sparse": 1, "threaded": 2}   # "threaded": sparse arithmetic over host threads + skyline Cholesky (the timed CPU arm at full size)
 _SOLVE = {"qr": 0, "chol": 1, "none": 2}   # "none": assemble S / rhs only (large systems; the corrections are then meaningless)
 
 
@@ -139,7 +140,7 @@ def ba_solve(pr, err_change=None, max_hessian_factor=None, unity_ind=1, unity_va
                                    C.c_int(err_change is not None), C.c_double(err_change or 0.0),
                                    C.c_int(max_hessian_factor is not None), C.c_double(max_hessian_factor or 0.0),
                                    C.c_int(unity_ind), C.c_double(unity_val), C.c_int(max_outer_iters),
-                                   C.c_int(0 if flow == "dense" else 1), C.c_int(_SOLVE[solve]),
+                                   C.c_int(_FLOW[flow]), C.c_int(_SOLVE[solve]),
                                    C.c_int(0 if acc == "double" else 1), C.byref(rep), _p(tr, C.c_double), C.c_int(cap),
                                    _p(att, C.c_double), C.c_int(cap))
     if rc != 0:
@@ -189,7 +190,7 @@ def derivs_and_solve(pr, c=None, unity_ind=1, flow="sparse", solve="qr", acc="do
         out.update(S=np.zeros((nf, nf)), rhs=np.zeros(nf), skipped=np.zeros(N, dtype=np.uint8), corrections=np.zeros(3 * N + 10 * M))
     rc = lib().srk_oracle_derivs_and_solve(*_prob_args(pr), _p(pr.points, C.c_double), _p(pr.cams, C.c_double), _p(pr.K, C.c_double),
                                            C.c_int(1 if pr.shared_K else 0), C.c_double(pr.f0), C.c_int(unity_ind),
-                                           C.c_double(-1.0 if c is None else c), C.c_int(0 if flow == "dense" else 1),
+                                           C.c_double(-1.0 if c is None else c), C.c_int(_FLOW[flow]),
                                            C.c_int(_SOLVE[solve]), C.c_int(0 if acc == "double" else 1),
                                            _p(out["gradE"], C.c_double), _p(out["E"], C.c_double), _p(out["G"], C.c_double),
                                            _p(out["F"], C.c_double), _p(out.get("S"), C.c_double), _p(out.get("rhs"), C.c_double),

@@ -16,11 +16,14 @@
 // `Acc` is the type in which the Schur complement is formed (double = faithful; long double = "exact" mode used
 // as the parity target, see DESIGN.md "Parity budget").
 #pragma once
+#include <array>
 #include <limits>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 #include "srk_oracle_geom.hpp"
+#include "srk_oracle_parallel.hpp"
 
 namespace srk_oracle {
 
@@ -34,7 +37,13 @@ struct DynMat {  // column-major dense matrix (Eigen default layout)
     F operator()(size_t r, size_t c) const { return d[c * rows + r]; }
 };
 
-enum class SchurFlow { DenseReference = 0, SparseEquivalent = 1 };
+// SparseThreaded: the SparseEquivalent arithmetic spread over host threads for the timed CPU arm of the full-size configurations
+// (bench.py --impl reference): derivative passes per point / per frame (bit-identical to the serial order), per-observation errors summed
+// serially in the reference's frame-major order (bit-identical), the Schur complement accumulated per thread in 10x10 camera-pair blocks
+// (lower block triangle) merged in thread order, a skyline Cholesky of the block-banded system instead of the reference's dense
+// Householder QR (which needs 1.3e12 flop at n_f = 9993), back substitution per point.  NOT the reference's single-threaded data flow:
+// it exists so that the CPU arm can run the SAME configuration as the GPU arm in minutes, and says so wherever it is reported.
+enum class SchurFlow { DenseReference = 0, SparseEquivalent = 1, SparseThreaded = 2 };
 enum class SolveImpl { HouseholderQR = 0, CholeskyRefined = 1, None = 2 };   // None: assemble S / rhs only (parity checks of large systems)
 enum StopReason { kStopNone = 0, kStopAbsErrThreshold = 1, kStopSmallErrChange = 2, kStopHessianOverflow = 3, kStopErrConverged = 4,
                   kStopNormalizationFailed = 5, kStopMaxIters = 6 };
@@ -252,6 +261,18 @@ public:
     F CurrentReprojError(size_t* seen = nullptr) const {
         if (schur_flow == SchurFlow::DenseReference)
             return ReprojError(f0_, *map_, *inverse_orient_cams_, *track_rep_, shared_K_, Ks_, seen);
+        if (schur_flow == SchurFlow::SparseThreaded) {   // per-observation terms in parallel, summed serially in the same frame-major order
+            std::vector<F> term(obs_.size());
+            ParallelFor(0, (int64_t)obs_.size(), 4096, [&](int64_t oi) {
+                const Obs& o = obs_[(size_t)oi];
+                term[(size_t)oi] = OneReprojErr(f0_, GetK(o.frame), (*inverse_orient_cams_)[o.frame], map_->GetSalientPoint(pnt_to_map_id_[o.pnt]), Point2<F>(o.x, o.y));
+            });
+            F acc = 0; size_t n = 0;
+            for (size_t frame_ind = 0; frame_ind < by_frame_.size(); ++frame_ind)
+                for (uint32_t oi : by_frame_[frame_ind]) { acc += term[oi]; n += 1; }
+            if (seen != nullptr) *seen = n;
+            return acc;
+        }
         // SparseEquivalent: same per-observation arithmetic, same frame-major / track-inner summation order.
         F err_sum = 0; size_t cnt = 0;
         for (size_t frame_ind = 0; frame_ind < by_frame_.size(); ++frame_ind) {
@@ -304,7 +325,7 @@ public:
         else Fblk_.assign(obs_.size() * 30, F(0));
         corrections_.assign(VarsCount(), F(0));
         size_t nf = NormalizedFrameVarsCount();
-        S_.resize(nf, nf);
+        if (schur_flow == SchurFlow::SparseThreaded) S_.resize(0, 0); else S_.resize(nf, nf);   // the threaded flow keeps S in skyline form
         rhs_.assign(nf, Acc(0));
         skipped_mask_.assign(N, 0);
     }
@@ -418,6 +439,21 @@ public:
                     });
                 }
             }
+        } else if (schur_flow == SchurFlow::SparseThreaded) {
+            std::fill(Fblk_.begin(), Fblk_.end(), F(0));
+            ParallelFor(0, (int64_t)pt_begin_.size() - 1, 1024, [&](int64_t pnt_ind) {      // a point's gradE / E entries are its own
+                const Vec3<F>& X = map_->GetSalientPoint(pnt_to_map_id_[(size_t)pnt_ind]);
+                for (size_t oi = pt_begin_[(size_t)pnt_ind]; oi < pt_begin_[(size_t)pnt_ind + 1]; ++oi)
+                    AccumulatePointPass((size_t)pnt_ind, obs_[oi].frame, X, Point2<F>(obs_[oi].x, obs_[oi].y));
+            });
+            ParallelFor(0, (int64_t)M, 1, [&](int64_t frame_ind) {                            // a frame's gradE / G entries are its own
+                for (uint32_t oi : by_frame_[(size_t)frame_ind]) {
+                    const Obs& o = obs_[oi];
+                    const Vec3<F>& X = map_->GetSalientPoint(pnt_to_map_id_[o.pnt]);
+                    F* blk = &Fblk_[(size_t)oi * 30];
+                    AccumulateFramePass((size_t)frame_ind, X, Point2<F>(o.x, o.y), [&](size_t pv, size_t fv, F sv) { blk[pv * 10 + fv] += sv; });
+                }
+            });
         } else {
             std::fill(Fblk_.begin(), Fblk_.end(), F(0));
             for (size_t pnt_ind = 0; pnt_ind + 1 < pt_begin_.size(); ++pnt_ind) {
@@ -508,8 +544,135 @@ public:
         }
     }
 
+    // SparseThreaded variant of the function below: same per-point arithmetic (damped block, |det| rule, A^T E^-1 A, A^T E^-1 g),
+    // accumulated per thread into the lower block triangle of camera-pair 10x10 blocks, merged in thread order into a skyline
+    // (row-profile) matrix, factored by a skyline Cholesky in double, no refinement.
+    bool EstimateCorrectionsThreaded(F hessian_factor, long* skipped_points) {
+        const size_t N = PointsCount(), M = FramesCount(), nf = NormalizedFrameVarsCount();
+        const int nt = OracleThreads();
+        typedef std::array<double, 100> Blk;
+        struct Local { std::unordered_map<uint64_t, Blk> blocks; std::unordered_map<uint32_t, std::array<double, 10>> rhs; long skipped = 0; };
+        std::vector<Local> loc((size_t)nt);
+        std::vector<double> einv(N * 9, 0.0);
+        ParallelFor(0, nt, 1, [&](int64_t t) {
+            Local& L = loc[(size_t)t];
+            const size_t p0 = N * (size_t)t / (size_t)nt, p1 = N * ((size_t)t + 1) / (size_t)nt;
+            std::vector<double> tmp;
+            for (size_t p = p0; p < p1; ++p) {
+                Mat33<Acc> Einv;
+                const bool ok = ScaledPointHessianInverse(p, hessian_factor, &Einv);
+                skipped_mask_[p] = ok ? 0 : 1;
+                if (!ok) { ++L.skipped; continue; }
+                for (int i = 0; i < 9; ++i) einv[p * 9 + i] = (double)Einv.a[i];
+                const size_t ob = pt_begin_[p], oe = pt_begin_[p + 1];
+                tmp.assign((oe - ob) * 30, 0.0);
+                for (size_t oi = ob; oi < oe; ++oi) {          // tmp_i = F_i^T E^-1   [10 x 3]
+                    const F* b = &Fblk_[oi * 30];
+                    double* ti = &tmp[(oi - ob) * 30];
+                    for (int a = 0; a < 10; ++a)
+                        for (int k = 0; k < 3; ++k) ti[a * 3 + k] = (b[a] * (double)Einv(0, k) + b[10 + a] * (double)Einv(1, k)) + b[20 + a] * (double)Einv(2, k);
+                }
+                const double g0 = gradE_[p * 3], g1 = gradE_[p * 3 + 1], g2 = gradE_[p * 3 + 2];
+                for (size_t oi = ob; oi < oe; ++oi) {
+                    const double* ti = &tmp[(oi - ob) * 30];
+                    auto& r = L.rhs[obs_[oi].frame];
+                    for (int a = 0; a < 10; ++a) r[(size_t)a] += (ti[a * 3] * g0 + ti[a * 3 + 1] * g1) + ti[a * 3 + 2] * g2;
+                    for (size_t oj = ob; oj <= oi; ++oj) {    // observations are frame-ascending inside a track: frame(oj) <= frame(oi)
+                        const F* bj = &Fblk_[oj * 30];
+                        Blk& blk = L.blocks[((uint64_t)obs_[oi].frame << 32) | obs_[oj].frame];
+                        for (int a = 0; a < 10; ++a)
+                            for (int b2 = 0; b2 < 10; ++b2) blk[(size_t)(a * 10 + b2)] += (ti[a * 3] * bj[b2] + ti[a * 3 + 1] * bj[10 + b2]) + ti[a * 3 + 2] * bj[20 + b2];
+                    }
+                }
+            }
+        });
+        long skipped = 0;
+        for (const Local& L : loc) skipped += L.skipped;
+        if (skipped_points != nullptr) *skipped_points = skipped;
+        // row profile of the reduced system from the union of the block structure (+ the diagonal blocks)
+        std::vector<int> first_cam(M);
+        for (size_t f = 0; f < M; ++f) first_cam[f] = (int)f;
+        for (const Local& L : loc) for (const auto& kv : L.blocks) { int i = (int)(kv.first >> 32), j = (int)(kv.first & 0xffffffffu); if (j < first_cam[(size_t)i]) first_cam[(size_t)i] = j; }
+        auto first_red = [&](size_t cam) { for (size_t v = 0; v < kV; ++v) { int r = ReducedIndex(cam * kV + v); if (r >= 0) return r; } return 0; };
+        std::vector<size_t> rowptr(nf + 1, 0);
+        std::vector<int> first(nf, 0);
+        for (size_t cam = 0; cam < M; ++cam)
+            for (size_t v = 0; v < kV; ++v) { int r = ReducedIndex(cam * kV + v); if (r >= 0) first[(size_t)r] = first_red((size_t)first_cam[cam]); }
+        for (size_t r = 0; r < nf; ++r) rowptr[r + 1] = rowptr[r] + (size_t)((int)r - first[r] + 1);
+        std::vector<double> A(rowptr[nf], 0.0);                      // row r holds columns first[r] .. r
+        auto at = [&](int r, int c) -> double& { return A[rowptr[(size_t)r] + (size_t)(c - first[(size_t)r])]; };
+        for (size_t cam = 0; cam < M; ++cam)                          // fill_matG (BA.cpp:1780-1823)
+            for (size_t v1 = 0; v1 < kV; ++v1) {
+                int r1 = ReducedIndex(cam * kV + v1); if (r1 < 0) continue;
+                for (size_t v2 = 0; v2 <= v1; ++v2) {
+                    int r2 = ReducedIndex(cam * kV + v2); if (r2 < 0) continue;
+                    F g = G_(cam * kV + v1, v2);
+                    if (v1 == v2) g *= F(1) + hessian_factor;
+                    at(r1, r2) = (double)g;
+                }
+            }
+        std::vector<double> b(nf, 0.0);
+        for (const Local& L : loc) {                                  // thread order: deterministic for a given thread count
+            for (const auto& kv : L.blocks) {
+                const size_t ci = (size_t)(kv.first >> 32), cj = (size_t)(kv.first & 0xffffffffu);
+                for (size_t a = 0; a < kV; ++a) {
+                    int r = ReducedIndex(ci * kV + a); if (r < 0) continue;
+                    for (size_t b2 = 0; b2 < kV; ++b2) {
+                        int c2 = ReducedIndex(cj * kV + b2); if (c2 < 0 || c2 > r) continue;
+                        at(r, c2) -= kv.second[a * 10 + b2];
+                    }
+                }
+            }
+            for (const auto& kv : L.rhs) for (size_t a = 0; a < kV; ++a) { int r = ReducedIndex((size_t)kv.first * kV + a); if (r >= 0) b[(size_t)r] += kv.second[a]; }
+        }
+        for (size_t v = 0; v < kV * M; ++v) { int r = ReducedIndex(v); if (r >= 0) b[(size_t)r] -= (double)gradE_[N * 3 + v]; }
+        for (size_t i = 0; i < nf; ++i) rhs_[i] = Acc(b[i]);
+        // skyline Cholesky, row by row
+        for (int i = 0; i < (int)nf; ++i) {
+            double* li = &A[rowptr[(size_t)i]]; const int fi = first[(size_t)i];
+            for (int j = fi; j <= i; ++j) {
+                const double* lj = &A[rowptr[(size_t)j]]; const int fj = first[(size_t)j];
+                const int k0 = fi > fj ? fi : fj;
+                double sacc = li[j - fi];
+                for (int k = k0; k < j; ++k) sacc -= li[k - fi] * lj[k - fj];
+                if (j < i) li[j - fi] = sacc / lj[j - fj];
+                else { if (!(sacc > 0)) return false; li[j - fi] = std::sqrt(sacc); }
+            }
+        }
+        std::vector<double> y(b);
+        for (int i = 0; i < (int)nf; ++i) { const double* li = &A[rowptr[(size_t)i]]; const int fi = first[(size_t)i]; double sacc = y[(size_t)i]; for (int k = fi; k < i; ++k) sacc -= li[k - fi] * y[(size_t)k]; y[(size_t)i] = sacc / li[i - fi]; }
+        for (int i = (int)nf - 1; i >= 0; --i) { const double* li = &A[rowptr[(size_t)i]]; const int fi = first[(size_t)i]; const double xi = y[(size_t)i] / li[i - fi]; y[(size_t)i] = xi; for (int k = fi; k < i; ++k) y[(size_t)k] -= li[k - fi] * xi; }
+        for (double v : y) if (!std::isfinite(v)) return false;
+        // back substitution (BA.cpp:1919-1960), per point
+        std::vector<F> normalized(NormalizedVarsCount(), F(0));
+        std::vector<unsigned char> bad((size_t)nt, 0);
+        ParallelFor(0, nt, 1, [&](int64_t t) {
+            const size_t p0 = N * (size_t)t / (size_t)nt, p1 = N * ((size_t)t + 1) / (size_t)nt;
+            for (size_t p = p0; p < p1; ++p) {
+                if (skipped_mask_[p]) continue;
+                double tt[3] = {0, 0, 0};
+                for (size_t oi = pt_begin_[p]; oi < pt_begin_[p + 1]; ++oi) {
+                    const F* blk = &Fblk_[oi * 30];
+                    for (size_t fv = 0; fv < kV; ++fv) { int r = ReducedIndex(obs_[oi].frame * kV + fv); if (r < 0) continue; for (int k = 0; k < 3; ++k) tt[k] += blk[(size_t)k * 10 + fv] * y[(size_t)r]; }
+                }
+                for (int k = 0; k < 3; ++k) tt[k] += gradE_[p * 3 + (size_t)k];
+                const double* ei = &einv[p * 9];
+                for (int r = 0; r < 3; ++r) {   // Mat33 is column-major: (r, c) -> a[c * 3 + r]
+                    double sacc = (ei[0 * 3 + r] * tt[0] + ei[1 * 3 + r] * tt[1]) + ei[2 * 3 + r] * tt[2];
+                    normalized[p * 3 + (size_t)r] = F(-sacc);
+                    if (!std::isfinite(sacc)) bad[(size_t)t] = 1;
+                }
+            }
+        });
+        for (unsigned char f : bad) if (f) return false;
+        for (size_t i = 0; i < nf; ++i) normalized[N * 3 + i] = F(y[i]);
+        FillCorrectionsGapsFromNormalized(normalized);
+        return true;
+    }
+
     // BA.cpp:1771-1995
     bool EstimateCorrectionsDecomposedInTwoPhases(F hessian_factor, long* skipped_points = nullptr) {
+        if (schur_flow == SchurFlow::SparseThreaded) return EstimateCorrectionsThreaded(hessian_factor, skipped_points);
         size_t N = PointsCount();
         size_t nf = NormalizedFrameVarsCount();
         FillMatG(hessian_factor);

@@ -57,7 +57,7 @@ void Collapse(const Mirrors& m, double* points, double* cams) {
 
 template <class BA>
 void Configure(BA& ba, int flow, int solve_impl, int unity_ind, double unity_val, int max_outer_iters) {
-    ba.schur_flow = flow == 0 ? SchurFlow::DenseReference : SchurFlow::SparseEquivalent;
+    ba.schur_flow = flow == 0 ? SchurFlow::DenseReference : flow == 2 ? SchurFlow::SparseThreaded : SchurFlow::SparseEquivalent;
     ba.solve_impl = solve_impl == 0 ? SolveImpl::HouseholderQR : solve_impl == 2 ? SolveImpl::None : SolveImpl::CholeskyRefined;
     if (solve_impl >= 10) { ba.chol_in_double = true; ba.refine_steps = solve_impl - 10; }  // 10+k: double LL^T with k refinement steps
     ba.unity_t1_comp_ind_ = (size_t)unity_ind;

@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [_nvcc(), "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -77,6 +77,10 @@ def load_library():
     L.srk_ba_get_timing.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.srk_ba_solve_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.srk_ba_solve_order.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.srk_nccl_unique_id.argtypes = [C.c_void_p]
+    L.srk_ba_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.srk_ba_set_nccl_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.srk_ba_pcg_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.srk_ba_default_options.argtypes = [C.POINTER(_Options)]
     L.srk_ba_default_options.restype = None
     _lib = L
@@ -91,6 +95,13 @@ def _check(rc):
 
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def nccl_unique_id():
+    """128-byte ncclUniqueId (srk_nccl_unique_id); create on rank 0 and hand to every rank."""
+    buf = (C.c_ubyte * 128)()
+    _check(load_library().srk_nccl_unique_id(C.cast(buf, C.c_void_p)))
+    return bytes(buf)
 
 
 class BAProblem:
@@ -201,6 +212,12 @@ class Engine:
         self._cb = ALLREDUCE_FN(_tramp)
         _check(self._lib.srk_ba_set_allreduce(self._h, self._cb, None, rank, world))
 
+    def nccl_init(self, unique_id, rank, world):
+        """The library's own NCCL exchange (srk_ba_nccl_init): no Python callback per all-reduce.  unique_id: 128 bytes from nccl_unique_id()
+        on rank 0, handed to every rank; collective."""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        _check(self._lib.srk_ba_nccl_init(self._h, C.cast(buf, C.c_void_p), rank, world))
+
     def _new_report(self):
         rep = _Report()
         tr = np.zeros(self._trace_cap)
@@ -281,6 +298,12 @@ class Engine:
         _check(self._lib.srk_ba_solve_order(self._h, C.byref(on), C.byref(parts), C.byref(mp), C.byref(sb)))
         return dict(n_f=nf.value, block_rows=nb.value, nonzero_tiles=nz.value, factor_flops=fl.value, ordered_n=on.value, parts=parts.value,
                     max_part_blocks=mp.value, separator_blocks=sb.value)
+
+    def pcg_stats(self):
+        """Stored 10x10 blocks of the block-sparse reduced system and the PCG iterations executed since set_timing(True)."""
+        nb, it = C.c_int64(), C.c_int64()
+        _check(self._lib.srk_ba_pcg_stats(self._h, C.byref(nb), C.byref(it)))
+        return dict(nnz_blocks=nb.value, iters=it.value)
 
     def set_timing(self, enabled):
         _check(self._lib.srk_ba_set_timing(self._h, 1 if enabled else 0))

@@ -1132,9 +1132,9 @@ void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, c
                        unsigned long long* plan_keys, unsigned plan_mask, int* plan_overflow) {
     if (N <= 0) return;
     constexpr int CMAX = 12;
-    static bool attr = false;
+    static PerDeviceOnce once;
     const size_t smem = schur_tile_smem<CMAX>();
-    if (!attr) { cudaFuncSetAttribute(k_schur_tile<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    if (once.first()) cudaFuncSetAttribute(k_schur_tile<CMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_schur_tile<CMAX><<<cdiv(N, tile_points), SchurTileCfg<CMAX>::kThreads, smem, st>>>(N, O, tile_points, pt_begin, obs_cam, J, c, sink, pinv, skipped,
                                                                                       deferred, plan_only, plan_keys, plan_mask, plan_overflow);
 }

@@ -14,6 +14,8 @@
 //                     tiles per warp.  4x less trailing-matrix traffic than a 64-wide right-looking sweep.
 //   k_trsv_coop     : forward / backward substitution as ONE cooperative kernel: per 64-block a GEMV with the stored
 //                     L_kk^-1, a grid-wide panel GEMV for the rows below / above, one grid.sync per block.
+#include <mutex>
+#include <unordered_map>
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdio.h>
@@ -1296,10 +1298,15 @@ static int g_coop_blocks = 0;
 static int g_potrf_rowops = 0;
 static int g_sms = 148;
 static void launch_syrk(cudaStream_t st, int n, double* A, int64_t ld, int kcol0, int K, int origin, int col_end, const unsigned char* F, int nblk);
-static int g_epoch = 0;
+// substitution epoch of a factor: the flags of k_trsv_flags live in the factor's own workspace, so the counter is kept per workspace
+// (handles that alternate, or run on different host threads, do not see each other's epochs)
+static std::mutex g_epoch_mu;
+static std::unordered_map<const void*, int> g_epochs;
+static void epoch_reset(const void* ws) { std::lock_guard<std::mutex> g(g_epoch_mu); if (g_epochs.size() > 4096) g_epochs.clear(); g_epochs[ws] = 0; }
+static int epoch_next(const void* ws) { std::lock_guard<std::mutex> g(g_epoch_mu); return ++g_epochs[ws]; }
 static void set_attrs_once() {
-    static bool attr_set = false;
-    if (attr_set) return;
+    static PerDeviceOnce once;
+    if (!once.first()) return;
     cudaFuncSetAttribute(k_panel_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSolveSmem);
     cudaFuncSetAttribute(k_potrf64_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kPotrfScratchDoubles));
     { const char* e = getenv("SRK_POTRF"); g_potrf_rowops = (e != nullptr && e[0] == 'r') ? 1 : 0; }
@@ -1312,7 +1319,6 @@ static void set_attrs_once() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_trsv_flags, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * 2 * kTrsvOwn * NB * NB + kTrsvFCacheMax));
     g_coop_blocks = sms * (per_sm < 1 ? 1 : 1);   // one CTA per SM: fewer spinners, same bandwidth
-    attr_set = true;
 }
 
 // Workspace layout (doubles): [dinv: nblk*64*64][ybuf: nblk*64][flags: nblk ints, padded][F: nblk*nblk bytes, padded][op lists: 2 x 7*nblk ints]
@@ -1377,7 +1383,7 @@ static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, dou
 // The launch sequence of a factorisation is static for given (n, buffers): it is captured once into a CUDA graph and
 // replayed, which removes ~800 host launch calls per solve from the critical path.
 struct FactorGraph { int n = 0; double* A = nullptr; int64_t ld = 0; double* ws = nullptr; int* info = nullptr; cudaGraphExec_t exec = nullptr; int64_t launches = 0; };
-static FactorGraph g_fg;
+static thread_local FactorGraph g_fg;   // per host thread: a handle is driven by one thread at a time (ba_c_api.h threading contract)
 
 // Sparse-factor path: tile pattern of the input, then (when it is sparse enough) the single-cluster kernel.  Returns the number of
 // launches, or 0 when the matrix is not sparse and the launch-per-operation path has to run.
@@ -1388,10 +1394,9 @@ static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, do
     static int force = -1;    // SRK_CHOL_PATH=dense disables the sparse path, =band forces it (development aid)
     if (force < 0) { const char* e = getenv("SRK_CHOL_PATH"); force = e == nullptr ? 0 : (e[0] == 'd' ? 1 : (e[0] == 'b' ? 2 : 0)); }
     if (force == 1) return 0;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(k_band_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BandSmem)) != cudaSuccess) { cudaGetLastError(); return 0; }
-        attr = true;
+    static PerDeviceOnce once;
+    if (once.first()) {
+        if (cudaFuncSetAttribute(k_band_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BandSmem)) != cudaSuccess) { cudaGetLastError(); once.forget(); return 0; }
     }
     unsigned char* F = ws_F(ws, n);
     int* cnt = ws_nzt(ws, n);
@@ -1437,7 +1442,7 @@ bool dense_cholesky_pattern_ok(int n, int pattern_count, bool partitioned) {
 int64_t dense_cholesky_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part, const unsigned char* pattern_dev,
                               int pattern_count) {
     set_attrs_once();
-    g_epoch = 0;
+    epoch_reset(ws);
     static int prof_env = -1;
     if (prof_env < 0) { const char* e = getenv("SRK_CHOL_PROFILE"); prof_env = (e != nullptr && e[0] == '1') ? 1 : 0; }
     g_prof = prof_env == 1;
@@ -1489,17 +1494,18 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
     double* ybuf = ws_ybuf(ws, n);
     int* flags = ws_flags(ws, n);
     const unsigned char* F = ws_F(ws, n);
-    int epoch = ++g_epoch;
+    int epoch = epoch_next(ws);
     const int* nzt = ws_nzt(ws, n);
     if (n <= kTrsvSparseMaxN) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(k_trsv_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTrsvSparseMaxN + sizeof(int) * (kTrsvSparseFill + 1) * kTrsvSparseMaxBlk)); attr = true; }
+        static PerDeviceOnce once;
+        if (once.first()) cudaFuncSetAttribute(k_trsv_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kTrsvSparseMaxN + sizeof(int) * (kTrsvSparseFill + 1) * kTrsvSparseMaxBlk));
         static int use_cluster = -1;
         if (use_cluster < 0) {
             const char* e = getenv("SRK_TRSV_CLUSTER");
             use_cluster = (e != nullptr && e[0] == '0') ? 0 : 1;
-            if (use_cluster && cudaFuncSetAttribute(k_trsv_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsvClSmem)) != cudaSuccess) { cudaGetLastError(); use_cluster = 0; }
         }
+        static PerDeviceOnce once_cl;
+        if (use_cluster && once_cl.first() && cudaFuncSetAttribute(k_trsv_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsvClSmem)) != cudaSuccess) { cudaGetLastError(); use_cluster = 0; }
         if (use_cluster) {
             const int* lst = ws_list(ws, n, backward);
             if (part != nullptr && part->nparts > 0) {
@@ -1669,9 +1675,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
 void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only,
                          int allow_split_k) {
     set_attrs_once();
-    static bool attr = false;
+    static PerDeviceOnce once;
     const size_t smem = sizeof(double) * (2 * STAGES * KC * (128 + 4));
-    if (!attr) { cudaFuncSetAttribute(k_gemm_nt_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    if (once.first()) cudaFuncSetAttribute(k_gemm_nt_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (m <= 0 || n <= 0 || K <= 0) return;
     const int tm = (m + 127) / 128, tn = (n + 127) / 128;
     const int tiles = lower_only ? tm * (tm + 1) / 2 : tm * tn;          // tiles that do work

@@ -6,6 +6,20 @@
 
 namespace srk {
 
+// cudaFuncSetAttribute (the > 48 KB dynamic shared-memory opt-in) is a PER-DEVICE property: a host that opens handles on several GPUs
+// in one process must set it once on each.  `static PerDeviceOnce once; if (once.first()) { ... }` replaces a process-wide flag.
+struct PerDeviceOnce {
+    unsigned long long seen[4] = {0, 0, 0, 0};   // 256 device ordinals
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 256) return true;
+        const unsigned long long bit = 1ull << (d & 63);
+        unsigned long long old = __atomic_fetch_or(&seen[d >> 6], bit, __ATOMIC_ACQ_REL);
+        return (old & bit) == 0;
+    }
+    void forget() { int d = 0; if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 256) __atomic_fetch_and(&seen[d >> 6], ~(1ull << (d & 63)), __ATOMIC_ACQ_REL); }
+};
+
 constexpr int kV = 10;           // frame variables [fx fy u0 v0 | Tx Ty Tz | Wx Wy Wz]   (BA.h:102-118)
 constexpr int kCamStride = 48;   // doubles per derived-camera record (384 B, 128-B aligned)
 

@@ -6,6 +6,8 @@
 // (BA.cpp:249-270).  All per-observation / per-point / per-camera arithmetic runs in the CUDA kernels of ba_kernels.cu,
 // chol_kernels.cu and pcg_kernels.cu; the host only owns buffers, launch order and the scalar control flow.
 // There is no CPU fallback: without a CUDA device srk_ba_create fails.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -154,12 +156,15 @@ struct Engine {
     srk_allreduce_fn ar = nullptr;
     void* ar_user = nullptr;
     int rank = 0, world = 1;
+    void* nccl_comm = nullptr;   // ncclComm_t when the library drives NCCL itself (srk_ba_nccl_init / srk_ba_set_nccl_comm)
+    bool nccl_owned = false;
 
     // accounting
     bool timing = false;
     FamilyTimer timers[F_COUNT];
     int64_t launches = 0;
     int32_t pcg_iters_last = 0;
+    int64_t pcg_iters_total = 0;     // since srk_ba_set_timing(h, 1)
     double pcg_rel_res_last = 0.0;
     int solver_used = 0;
     int64_t factor_failures = 0;     // attempts whose Cholesky factorisation met a non-positive pivot (retried with more damping)
@@ -192,6 +197,41 @@ void resolve_timers(Engine& e) {
         }
         t.pending.clear();
     }
+}
+
+// ---- NCCL through dlopen: the library has no link-time dependency on it (single-GPU hosts need none) -------------------------------
+struct NcclId { char internal[128]; };                                      // == ncclUniqueId (nccl.h: NCCL_UNIQUE_ID_BYTES 128)
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;                                    // ncclGetUniqueId(ncclUniqueId*)
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;         // ncclCommInitRank(ncclComm_t*, nranks, ncclUniqueId, rank)
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+    if (g_nccl.lib != nullptr) return true;
+    const char* names[] = {std::getenv("SRK_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) { if (nm != nullptr && nm[0] != 0 && (lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL)) != nullptr) break; }
+    if (lib == nullptr) { set_error("libnccl.so.2 not found (set SRK_NCCL_LIB to its path)"); return false; }
+    NcclApi a; a.lib = lib;
+    a.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    a.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    a.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy) { set_error("libnccl lacks the expected entry points"); return false; }
+    g_nccl = a;
+    return true;
+}
+int nccl_allreduce_cb(void* user, double* dev, int64_t count, void* stream) {
+    Engine* e = (Engine*)user;
+    if (e == nullptr || e->nccl_comm == nullptr) return 1;
+    const int rc = g_nccl.AllReduce(dev, dev, (size_t)count, /*ncclDouble*/ 8, /*ncclSum*/ 0, e->nccl_comm, (cudaStream_t)stream);
+    if (rc != 0) { set_error(std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return 1; }
+    return 0;
 }
 
 int do_allreduce(Engine& e, double* dev, int64_t count) {
@@ -714,6 +754,7 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
                                 e.ar, e.ar_user, &e.launches, &e.pcg_iters_last, &rel);
             if (rc != SRK_OK) { set_error("pcg solve failed: " + std::string(cudaGetErrorString(cudaGetLastError()))); return rc; }
             e.pcg_rel_res_last = rel;
+            e.pcg_iters_total += e.pcg_iters_last;
         }
         e.solver_used = SRK_SOLVER_BLOCK_PCG;
     }
@@ -974,6 +1015,7 @@ void srk_ba_destroy(void* h) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     srk::pcg_release(e->pcg);
+    if (e->nccl_comm != nullptr && e->nccl_owned && g_nccl.CommDestroy != nullptr) g_nccl.CommDestroy(e->nccl_comm);
     if (e->h_slots != nullptr) cudaFreeHost(e->h_slots);
     if (e->h_adj != nullptr) cudaFreeHost(e->h_adj);
     for (int f = 0; f < F_COUNT; ++f) {
@@ -999,6 +1041,42 @@ int srk_ba_set_allreduce(void* h, srk_allreduce_fn fn, void* user, int rank, int
     Engine* e = (Engine*)h;
     e->ar = fn; e->ar_user = user; e->rank = rank; e->world = world_size;
     e->bound = false;  // slot buffers are sized at bind time
+    return SRK_OK;
+}
+
+int srk_nccl_unique_id(unsigned char* id128) {
+    if (id128 == nullptr) { set_error("null id buffer"); return SRK_E_INVALID_ARG; }
+    if (!nccl_load()) return SRK_E_INVALID_ARG;
+    NcclId id; std::memset(&id, 0, sizeof(id));
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) { set_error(std::string("ncclGetUniqueId: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SRK_E_CUDA; }
+    std::memcpy(id128, id.internal, 128);
+    return SRK_OK;
+}
+
+int srk_ba_set_nccl_comm(void* h, void* nccl_comm, int rank, int world_size) {
+    if (h == nullptr || nccl_comm == nullptr) { set_error("null handle or communicator"); return SRK_E_INVALID_ARG; }
+    if (!nccl_load()) return SRK_E_INVALID_ARG;
+    Engine* e = (Engine*)h;
+    int rc = srk_ba_set_allreduce(h, nccl_allreduce_cb, e, rank, world_size);
+    if (rc != SRK_OK) return rc;
+    if (e->nccl_comm != nullptr && e->nccl_owned) g_nccl.CommDestroy(e->nccl_comm);
+    e->nccl_comm = nccl_comm; e->nccl_owned = false;
+    return SRK_OK;
+}
+
+int srk_ba_nccl_init(void* h, const unsigned char* id128, int rank, int world_size) {
+    if (h == nullptr || id128 == nullptr) { set_error("null handle or id"); return SRK_E_INVALID_ARG; }
+    if (!nccl_load()) return SRK_E_INVALID_ARG;
+    Engine* e = (Engine*)h;
+    SRK_CUDA(cudaSetDevice(e->device));
+    NcclId id; std::memcpy(id.internal, id128, 128);
+    void* comm = nullptr;
+    const int rc = g_nccl.CommInitRank(&comm, world_size, id, rank);
+    if (rc != 0 || comm == nullptr) { set_error(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); return SRK_E_CUDA; }
+    int rc2 = srk_ba_set_nccl_comm(h, comm, rank, world_size);
+    if (rc2 != SRK_OK) { g_nccl.CommDestroy(comm); return rc2; }
+    e->nccl_owned = true;
     return SRK_OK;
 }
 
@@ -1190,11 +1268,20 @@ int srk_ba_solve_order(void* h, int64_t* ordered_n, int64_t* parts, int64_t* max
     return SRK_OK;
 }
 
+int srk_ba_pcg_stats(void* h, int64_t* nnz_blocks, int64_t* iters_since_timing) {
+    if (h == nullptr) { set_error("null handle"); return SRK_E_INVALID_ARG; }
+    Engine& e = *(Engine*)h;
+    if (nnz_blocks != nullptr) *nnz_blocks = e.pcg.structure_valid ? e.pcg.nnzb : 0;
+    if (iters_since_timing != nullptr) *iters_since_timing = e.pcg_iters_total;
+    return SRK_OK;
+}
+
 int srk_ba_set_timing(void* h, int enabled) {
     if (h == nullptr) return SRK_E_INVALID_ARG;
     Engine& e = *(Engine*)h;
     resolve_timers(e);
     e.timing = enabled != 0;
+    if (enabled) e.pcg_iters_total = 0;
     for (int f = 0; f < F_COUNT; ++f) { e.timers[f].total_ms = 0.0; e.timers[f].last_ms = 0.0; e.timers[f].count = 0; }
     return SRK_OK;
 }

@@ -462,8 +462,8 @@ void launch_schur_plan(cudaStream_t st, int64_t N, int tile_points, const int64_
 void launch_schur_mma(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
                       const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred) {
     if (N <= 0) return;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_schur_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MmaSmem)); attr = true; }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k_schur_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MmaSmem));
     const unsigned grid = (unsigned)((N + tile_points - 1) / tile_points);
     k_schur_mma<<<grid, kMmaThreads, sizeof(MmaSmem), st>>>(N, O, tile_points, pt_begin, obs_cam, J, c, sink, pinv, skipped, deferred);
 }

@@ -29,3 +29,13 @@ def attach_allreduce(engine, stream, device, group=None):
 
     engine.set_allreduce(allreduce, rank, world)
     return views
+
+
+def attach_nccl(engine, group=None):
+    """The library's own NCCL exchange (srk_ba_nccl_init, C++ host path, no Python callback per all-reduce): torch.distributed only
+    carries the 128-byte ncclUniqueId from rank 0 to the other ranks once."""
+    from .capi import nccl_unique_id
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    engine.nccl_init(box[0], rank, world)
