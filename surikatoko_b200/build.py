@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIB_DIR, "libsrk_ba.so")
-SOURCES = ["engine.cu", "ba_kernels.cu", "schur_mma.cu", "prep_kernels.cu", "chol_kernels.cu", "pcg_kernels.cu", "aux_kernels.cu", "ekf_kernels.cu", "frontend.cu", "solve_order.cu", "bundle.cu"]
+SOURCES = ["engine.cu", "ba_kernels.cu", "schur_mma.cu", "schur_v3.cu", "prep_kernels.cu", "chol_kernels.cu", "pcg_kernels.cu", "aux_kernels.cu", "ekf_kernels.cu", "frontend.cu", "solve_order.cu", "bundle.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
               "--expt-relaxed-constexpr"]
 

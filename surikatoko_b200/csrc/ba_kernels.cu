@@ -315,12 +315,17 @@ constexpr int kSchurWarps = 4;
 __global__ void __launch_bounds__(kSchurWarps * 32) k_schur(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin,
                                                             const int32_t* __restrict__ obs_cam, const double* __restrict__ J, double c,
                                                             SchurSink sink, double* __restrict__ pinv, unsigned char* __restrict__ skipped,
-                                                            const unsigned char* __restrict__ only_flagged) {
+                                                            const unsigned char* __restrict__ only_flagged, const int* __restrict__ list,
+                                                            const int* __restrict__ list_count) {
     __shared__ double sF[kSchurWarps][kSchurCH][30];   // slot 0 only: F of the row chunk
     __shared__ double sW[kSchurWarps][2][kSchurCH][30];
     __shared__ int sCam[kSchurWarps][2][kSchurCH];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int64_t j = (int64_t)blockIdx.x * kSchurWarps + w;
+    if (list != nullptr) {   // exception list of the tile kernel (schur_v3.cu): a device-side count, normally zero
+        if (j >= (int64_t)*list_count) return;
+        j = list[j];
+    }
     if (j >= N) return;
     if (only_flagged != nullptr && only_flagged[j] == 0) return;
     const int64_t b = pt_begin[j], e = pt_begin[j + 1];
@@ -1125,7 +1130,11 @@ void launch_fill_reduced(cudaStream_t st, int M, const double* G, const double* 
 }
 void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
                   double* pinv, unsigned char* skipped, const unsigned char* only_flagged) {
-    if (N > 0) k_schur<<<cdiv(N, kSchurWarps), kSchurWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, sink, pinv, skipped, only_flagged);
+    if (N > 0) k_schur<<<cdiv(N, kSchurWarps), kSchurWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, sink, pinv, skipped, only_flagged, nullptr, nullptr);
+}
+void launch_schur_list(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
+                       double* pinv, unsigned char* skipped, const int* list, const int* list_count, int list_cap) {
+    if (N > 0 && list_cap > 0) k_schur<<<cdiv(list_cap, kSchurWarps), kSchurWarps * 32, 0, st>>>(N, O, pt_begin, obs_cam, J, c, sink, pinv, skipped, nullptr, list, list_count);
 }
 void launch_schur_tile(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c,
                        const SchurSink& sink, double* pinv, unsigned char* skipped, unsigned char* deferred, int plan_only,

@@ -119,6 +119,8 @@ struct Engine {
     Buf obs_cam, obs_pt, obs_xy, ox, oy, pt_begin, cam_cnt, cam_cursor, cam_begin, c_pt, c_x, c_y;
     Buf chunk_cams, chunk_cnt, chunk_pts, obs_slot, obs_pos;
     Buf rows_F, rows_W, rows_D;   // dense-rows form of K2 (schur_dense_rows)
+    Buf k2_slot, k2_mask, k2_tab, k2_ntab, k2_gi, k2_u, k2_exc;   // K2 third form (schur_v3.cu): bind-time tile tables, per-attempt point factors, exception list
+    static constexpr int kExcCap = 16384;
     bool schur_dense_rows = false;
     Buf tacc;                 // K2' per-point accumulators [3N]; zero between attempts (k_backsub_finish re-zeroes what it reads)
     bool tacc_zero = false;
@@ -146,7 +148,7 @@ struct Engine {
     int64_t n_deferred = 0;   // points the tiled Schur kernel leaves to the per-point kernel (structure only, known at bind time)
     int schur_tile_points = 256;
     int schur_tile_fixed = 0; // SRK_SCHUR_TILE: force the tile size (0 = choose at bind time)
-    int schur_impl = 0;       // 0 = DMMA tile kernel (schur_mma.cu), 1 = vector-FMA tile kernel (ba_kernels.cu)
+    int schur_impl = 0;       // 0 = single-operand DMMA tile kernel (schur_v3.cu), 2 = two-operand DMMA tile kernel (schur_mma.cu), 1 = vector-FMA tile kernel (ba_kernels.cu)
     srk::PcgWorkspace pcg;
     int residual_blocks = 0;
     double* h_slots = nullptr;  // pinned
@@ -380,6 +382,15 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
             }
             if (!chosen) { rcp = plan(256, &e.n_deferred); if (rcp != SRK_OK) return rcp; }   // restore the flags of the small tiling
         }
+    }
+    // tables of the tile kernel for the chosen tiling (table slot of every observation, slot mask of every point, camera table of every tile)
+    if (N > 0 && e.schur_impl == 0) {
+        const int64_t ntile = (N + e.schur_tile_points - 1) / e.schur_tile_points;
+        SRK_CUDA(e.k2_slot.ensure((size_t)(O > 0 ? O : 1))); SRK_CUDA(e.k2_mask.ensure(sizeof(unsigned short) * (size_t)N));
+        SRK_CUDA(e.k2_tab.ensure(sizeof(int) * 12 * (size_t)ntile)); SRK_CUDA(e.k2_ntab.ensure(sizeof(int) * (size_t)ntile));
+        srk::launch_schur_tables(ss, N, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.k2_tab.as<int>(), e.k2_ntab.as<int>(),
+                                 e.k2_slot.as<unsigned char>(), e.k2_mask.as<unsigned short>(), e.deferred.as<unsigned char>());
+        e.launches += 1;
     }
     // dense-rows K2 when most points are left to the per-point kernel and the rows fit comfortably (2 x 3N x 10M doubles)
     e.schur_dense_rows = e.schur_rows_enabled && N > 0 && e.n_deferred * 2 > N && e.nf <= 16384 &&
@@ -633,7 +644,21 @@ void schur_accumulate(Engine& e, const srk::SchurSink& sink, double c) {
         }
         cudaGetLastError();   // not enough memory for the rows: the per-point kernels below
     }
-    if (e.schur_impl == 0)
+    bool v3 = false;
+    if (e.schur_impl == 0 && e.N > 0 && e.k2_gi.ensure(sizeof(double) * 6 * (size_t)e.N) == cudaSuccess && e.k2_u.ensure(sizeof(double) * 3 * (size_t)e.N) == cudaSuccess &&
+        e.k2_exc.ensure(sizeof(int) * (Engine::kExcCap + 4)) == cudaSuccess) {
+        v3 = true;
+        int* exc_count = e.k2_exc.as<int>(); int* exc_list = exc_count + 4;
+        cudaMemsetAsync(exc_count, 0, sizeof(int), st);
+        srk::launch_point_factor(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.J.as<double>(), c, e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.k2_gi.as<double>(),
+                                 e.k2_u.as<double>(), exc_list, exc_count, Engine::kExcCap);
+        srk::launch_schur_v3(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_pt.as<int32_t>(), e.J.as<double>(), sink, e.k2_gi.as<double>(),
+                             e.k2_u.as<double>(), e.skipped.as<unsigned char>(), e.k2_tab.as<int>(), e.k2_ntab.as<int>(), e.k2_slot.as<unsigned char>(),
+                             e.k2_mask.as<unsigned short>());
+        srk::launch_schur_list(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink, e.pinv.as<double>(),
+                               e.skipped.as<unsigned char>(), exc_list, exc_count, 1024);
+        e.launches += 2;
+    } else if (e.schur_impl == 0 || e.schur_impl == 2)
         srk::launch_schur_mma(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_cam.as<int32_t>(), e.J.as<double>(), c, sink,
                               e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.deferred.as<unsigned char>());
     else   // SRK_SCHUR_IMPL=1: the vector-FMA tile kernel (kept as a cross-check of the DMMA path)
@@ -992,7 +1017,7 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     SRK_CUDA(cudaSetDevice(dev));
     Engine* e = new Engine();
     e->device = dev;
-    if (const char* v = std::getenv("SRK_SCHUR_IMPL")) e->schur_impl = std::atoi(v) == 1 ? 1 : 0;
+    if (const char* v = std::getenv("SRK_SCHUR_IMPL")) { const int q = std::atoi(v); e->schur_impl = (q == 1 || q == 2) ? q : 0; }
     if (const char* v = std::getenv("SRK_TILE_EXCHANGE")) e->tile_exchange = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SOLVE_ORDER")) e->solve_order_enabled = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SCHUR_ROWS")) e->schur_rows_enabled = std::atoi(v) != 0 ? 1 : 0;

@@ -22,6 +22,17 @@ void launch_fill_reduced(cudaStream_t st, int M, const double* G, const double* 
 struct SchurSink;   // common.cuh
 void launch_schur(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
                   double* pinv, unsigned char* skipped, const unsigned char* only_flagged);
+// the same kernel over a device-side list of points (count read on the device; grid sized for list_cap)
+void launch_schur_list(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const int32_t* obs_cam, const double* J, double c, const SchurSink& sink,
+                       double* pinv, unsigned char* skipped, const int* list, const int* list_count, int list_cap);
+// K2, third form (schur_v3.cu): per-point factor kernel + bind-time tile tables + single-operand DMMA tile kernel
+void launch_point_factor(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const double* J, double c, double* pinv, unsigned char* skipped,
+                         double* gi, double* uvec, int* exc_list, int* exc_count, int exc_cap);
+void launch_schur_tables(cudaStream_t st, int64_t N, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, int* tile_tab, int* tile_n,
+                         unsigned char* obs_slot, unsigned short* pt_mask, unsigned char* deferred);
+void launch_schur_v3(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_pt, const double* J,
+                     const SchurSink& sink, const double* gi, const double* uvec, const unsigned char* skipped, const int* tile_tab, const int* tile_n,
+                     const unsigned char* obs_slot, const unsigned short* pt_mask);
 // Tiled Schur accumulation (register-owned camera-pair blocks per tile of points); flags the points it leaves to launch_schur.
 // plan_only: structure pass -- deferred flags and (plan_keys != nullptr) the camera-pair hash of the block-sparse system.
 // DMMA formulation of the same accumulation (schur_mma.cu); same deferral rule as the plan pass of launch_schur_tile.

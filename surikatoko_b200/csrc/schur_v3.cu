@@ -1,0 +1,450 @@
+// suriko-b200 — K2, third form: the Schur complement of a tile of points as ONE symmetric rank-k update on the FP64 tensor pipe.
+//
+// Replaces the Schur loop of EstimateCorrectionsDecomposedInTwoPhases (BA.cpp:1859-1900):
+//     S[cam_i, cam_l] -= sum_j F_ji^T E_cj^-1 F_jl ,   rhs[cam_i] += sum_j F_ji^T E_cj^-1 g_pj
+// What ncu said about the second form (schur_mma.cu, profiles/r01_ncu_schur_hot_lines.txt): the FP64 pipe is shared by the consumers'
+// DMMAs and the producers' vector arithmetic; a producer DFMA queues behind 16-cycle DMMAs, so the ~256 FP64 instructions a producer
+// lane spent per batch (E reduction by shuffles, cofactor inverse, F and W = E^-1 F) made the PRODUCERS the bottleneck through pipe
+// arbitration: the consumers sat 30 % of their time at the batch barrier with the DMMA sub-pipe 50 % busy.  This form takes the work
+// off that pipe instead of scheduling around it:
+//   * k_point_factor (a small streaming kernel, once per attempt): per point E = 2 sum Jp^T Jp, g_p, the damped cofactor inverse with the
+//     |det| > 1e-12 rule (quirk Q5, BA.cpp:1873-1881) -> pinv / skipped for K2' exactly as before, plus the Cholesky factor of the damped
+//     block E_c = L L^T as Gi = L^-1 (6 doubles) and u = Gi g_p.  With V_j = Gi_j F_j:   F^T E_c^-1 F = V^T V,   F^T E_c^-1 g_p = V^T u,
+//     so the tile contraction needs ONE operand (half the shared memory, half the stores) and the producers no reductions at all.
+//   * bind-time tables (k_schur_tables; the observation order never changes): the sorted camera table of every tile, the table slot of
+//     every observation (1 byte), the slot mask of every point -- no per-launch hash / sort / search.
+//   * k_schur_v3: 8 producer warps, one LANE PER OBSERVATION (every lane of every load carries data): Q = Gi (2 Jp^T) (3x2), V = Q Jc
+//     (3x10: 72 FP64 instructions per lane instead of ~256), written to a 4-deep ring of [48 x 124] operand stages; unseen slots are
+//     zero-filled from the point masks.  8 consumer warps run D += V^T V over the lower triangle of 8x8 fragments with mma.sync.m8n8k4.f64,
+//     super-blocks dealt so that the four SM sub-partitions carry 27 / 27 / 27 / 24 + rhs fragments (30 / 30 / 30 / 15 before).
+//     Producers and consumers meet through named barriers per ring stage (bar.arrive / bar.sync: full[s], empty[s]) -- the producers run
+//     up to three batches ahead, so a slow batch (a DRAM round trip) no longer stalls the tensor pipe.
+// A point whose damped block passes the |det| rule but is not numerically positive definite (never for a sum of squares with damping
+// unless rounding dominates) has no real factor: it contributes through the exception list to the per-point kernel (two operands).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace srk {
+
+constexpr int kV3Cams = 12;              // cameras per tile table (== the plan kernel's CMAX, schur_mma.cu kMmaCams)
+constexpr int kV3Rows = kV3Cams * 10;    // 120
+constexpr int kV3SLD = 124;              // row stride of an operand stage: 124 = 12 (mod 16) -> conflict-free fragment loads
+constexpr int kV3BP = 16;                // points per batch
+constexpr int kV3K = 3 * kV3BP;          // 48 contraction rows per batch
+constexpr int kV3Threads = 512;
+constexpr int kV3Stages = 4;
+constexpr int kV3Hash = 64;
+
+struct V3Smem {
+    double V[kV3Stages][kV3K * kV3SLD];
+    double U[kV3Stages][kV3K];
+    int gidx[kV3Rows];
+    int blk[kV3Cams * kV3Cams];
+    int tab[kV3Cams];
+};
+
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;\n" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void dmma884_v3(double& d0, double& d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Per-point blocks of one attempt.  Half-warp per point (lanes over its observations, strided for long tracks).
+__global__ void __launch_bounds__(256) k_point_factor(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin, const double* __restrict__ J, double c,
+                                                      double* __restrict__ pinv, unsigned char* __restrict__ skipped, double* __restrict__ gi,
+                                                      double* __restrict__ uvec, int* __restrict__ exc_list, int* __restrict__ exc_count, int exc_cap) {
+    const int hl = threadIdx.x & 15;
+    const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4;
+    const bool valid = j < N;
+    int64_t kb = 0; int k = 0;
+    if (valid) { kb = pt_begin[j]; k = (int)(pt_begin[j + 1] - kb); }
+    double a9[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a9[i] = 0.0;
+    for (int i = hl; i < k; i += 16) {
+        const int64_t o = kb + i;
+        const double rx = J[o], ry = J[O + o];
+        double jp[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) jp[q] = J[(int64_t)(2 + q) * O + o];
+        a9[0] += jp[0] * jp[0] + jp[1] * jp[1];
+        a9[1] += jp[0] * jp[2] + jp[1] * jp[3];
+        a9[2] += jp[0] * jp[4] + jp[1] * jp[5];
+        a9[3] += jp[2] * jp[2] + jp[3] * jp[3];
+        a9[4] += jp[2] * jp[4] + jp[3] * jp[5];
+        a9[5] += jp[4] * jp[4] + jp[5] * jp[5];
+        a9[6] += jp[0] * rx + jp[1] * ry;
+        a9[7] += jp[2] * rx + jp[3] * ry;
+        a9[8] += jp[4] * rx + jp[5] * ry;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double v = a9[i];
+#pragma unroll
+        for (int s2 = 8; s2 > 0; s2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s2);   // stays inside the half-warp
+        a9[i] = 2.0 * v;
+    }
+    if (!valid || hl != 0) return;
+    double inv[6];
+    const bool ok = point_block_inverse(a9, c, inv);
+    skipped[j] = ok ? 0 : 1;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) pinv[(int64_t)i * N + j] = ok ? inv[i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pinv[(int64_t)(6 + i) * N + j] = a9[6 + i];
+    // Cholesky of the damped block (same damped entries as point_block_inverse), Gi = L^-1
+    double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, u[3] = {0.0, 0.0, 0.0};   // g = {Gi00, Gi10, Gi11, Gi20, Gi21, Gi22}
+    if (ok) {
+        const double m00 = a9[0] * (1.0 + c), m11 = a9[3] * (1.0 + c), m22 = a9[5] * (1.0 + c), m01 = a9[1], m02 = a9[2], m12 = a9[4];
+        bool pd = m00 > 0.0;
+        const double l00 = sqrt(m00);
+        const double l10 = m01 / l00, l20 = m02 / l00;
+        const double d11 = m11 - l10 * l10;
+        pd = pd && d11 > 0.0;
+        const double l11 = sqrt(d11);
+        const double l21 = (m12 - l20 * l10) / l11;
+        const double d22 = m22 - l20 * l20 - l21 * l21;
+        pd = pd && d22 > 0.0;
+        const double l22 = sqrt(d22);
+        const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+        const double g10 = -l10 * i00 * i11, g21 = -l21 * i11 * i22;
+        const double g20 = -(l20 * i00 + l21 * g10) * i22;
+        pd = pd && isfinite(i00) && isfinite(i11) && isfinite(i22) && isfinite(g10) && isfinite(g20) && isfinite(g21);
+        if (pd) {
+            g[0] = i00; g[1] = g10; g[2] = i11; g[3] = g20; g[4] = g21; g[5] = i22;
+            u[0] = g[0] * a9[6];
+            u[1] = g[1] * a9[6] + g[2] * a9[7];
+            u[2] = g[3] * a9[6] + g[4] * a9[7] + g[5] * a9[8];
+        } else {   // invertible by the reference's rule but without a real factor: the two-operand per-point kernel takes it
+            const int idx = atomicAdd(exc_count, 1);
+            if (idx < exc_cap) exc_list[idx] = (int)j;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gi[(int64_t)i * N + j] = g[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) uvec[(int64_t)i * N + j] = u[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Bind-time tables of the tile kernel.  Same table construction and the same deferral rule as k_schur_plan (schur_mma.cu): the
+// kV3Cams smallest distinct camera ids of the tile, sorted; a point is deferred when it has more than 16 observations or sees a camera
+// outside the table.  Outputs: tile_tab [tiles x 12], tile_n [tiles], obs_slot [O] (0xFF for observations of deferred points),
+// pt_mask [N] (bit s = the point sees table slot s; 0 for deferred points), deferred [N] (rewritten with the same values).
+__global__ void __launch_bounds__(256) k_schur_tables(int64_t N, int tile_points, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam,
+                                                      int* __restrict__ tile_tab, int* __restrict__ tile_n, unsigned char* __restrict__ obs_slot,
+                                                      unsigned short* __restrict__ pt_mask, unsigned char* __restrict__ deferred) {
+    __shared__ int hash[kV3Hash];
+    __shared__ int tab[kV3Cams];
+    __shared__ int n_local;
+    const int tid = threadIdx.x;
+    const int64_t p0 = (int64_t)blockIdx.x * tile_points;
+    const int64_t p1 = min(N, p0 + (int64_t)tile_points);
+    if (p0 >= N) return;
+    for (int i = tid; i < kV3Hash; i += blockDim.x) hash[i] = -1;
+    if (tid < kV3Cams) tab[tid] = -1;
+    __syncthreads();
+    const int64_t ob = pt_begin[p0], oe = pt_begin[p1];
+    for (int64_t o = ob + tid; o < oe; o += blockDim.x) {
+        const int cam = obs_cam[o];
+        unsigned h = ((unsigned)cam * 2654435761u) >> 26;
+        for (int probe = 0; probe < kV3Hash; ++probe) {
+            const int prev = atomicCAS(&hash[h], -1, cam);
+            if (prev == -1 || prev == cam) break;
+            h = (h + 1) & (kV3Hash - 1);
+        }
+    }
+    __syncthreads();
+    if (tid < kV3Hash) {
+        const int cam = hash[tid];
+        int rank = 0, total = 0;
+        for (int i = 0; i < kV3Hash; ++i) { const int other = hash[i]; total += other >= 0; rank += (other >= 0 && other < cam); }
+        if (cam >= 0 && rank < kV3Cams) tab[rank] = cam;
+        if (tid == 0) n_local = total < kV3Cams ? total : kV3Cams;
+    }
+    __syncthreads();
+    const int nLocal = n_local;
+    if (tid < kV3Cams) tile_tab[(size_t)blockIdx.x * kV3Cams + tid] = tab[tid];
+    if (tid == 0) tile_n[blockIdx.x] = nLocal;
+    for (int64_t j = p0 + tid; j < p1; j += blockDim.x) {
+        const int64_t kb = pt_begin[j];
+        const int k = (int)(pt_begin[j + 1] - kb);
+        bool bad = k > 16;
+        unsigned mask = 0;
+        for (int i = 0; i < k && !bad; ++i) {
+            const int cam = obs_cam[kb + i];
+            int loc = -1;
+            for (int q = 0; q < nLocal; ++q) if (tab[q] == cam) loc = q;
+            if (loc < 0) bad = true; else mask |= 1u << loc;
+        }
+        deferred[j] = bad ? 1 : 0;
+        pt_mask[j] = bad ? (unsigned short)0 : (unsigned short)mask;
+        for (int i = 0; i < k; ++i) {
+            int loc = 0xFF;
+            if (!bad) { const int cam = obs_cam[kb + i]; for (int q = 0; q < nLocal; ++q) if (tab[q] == cam) loc = q; }
+            obs_slot[kb + i] = (unsigned char)loc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// One super-block (NI x NJ fragments of 8x8; DIAG: only the fragments on and below its diagonal) over one batch.
+template <int NI, int NJ, bool DIAG>
+__device__ __forceinline__ void v3_sb_batch(double (&acc)[3][3][2], const double* __restrict__ pa, const double* __restrict__ pb) {
+#pragma unroll 4
+    for (int ks = 0; ks < kV3K / 4; ++ks) {
+        const int off = ks * 4 * kV3SLD;
+        double af[NI], bf[NJ];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) af[i] = pa[off + 8 * i];
+        if (DIAG) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) bf[j] = af[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) bf[j] = pb[off + 8 * j];
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj)
+                if (!DIAG || jj <= i) dmma884_v3(acc[i][jj][0], acc[i][jj][1], af[i], bf[jj]);
+    }
+}
+__device__ __forceinline__ void v3_sb_dispatch(int code, double (&acc)[3][3][2], const double* pa, const double* pb) {
+    switch (code) {
+        case 0: v3_sb_batch<1, 1, false>(acc, pa, pb); break;
+        case 1: v3_sb_batch<1, 2, false>(acc, pa, pb); break;
+        case 2: v3_sb_batch<1, 3, false>(acc, pa, pb); break;
+        case 3: v3_sb_batch<2, 1, false>(acc, pa, pb); break;
+        case 4: v3_sb_batch<2, 2, false>(acc, pa, pb); break;
+        case 5: v3_sb_batch<2, 3, false>(acc, pa, pb); break;
+        case 6: v3_sb_batch<3, 1, false>(acc, pa, pb); break;
+        case 7: v3_sb_batch<3, 2, false>(acc, pa, pb); break;
+        case 8: v3_sb_batch<3, 3, false>(acc, pa, pb); break;
+        case 9: v3_sb_batch<1, 1, true>(acc, pa, pb); break;
+        case 10: v3_sb_batch<2, 2, true>(acc, pa, pb); break;
+        case 11: v3_sb_batch<3, 3, true>(acc, pa, pb); break;
+        default: break;
+    }
+}
+
+__global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O, int tile_points, const int64_t* __restrict__ pt_begin,
+                                                            const int32_t* __restrict__ obs_pt, const double* __restrict__ J, SchurSink sink,
+                                                            const double* __restrict__ gi, const double* __restrict__ uvec,
+                                                            const unsigned char* __restrict__ skipped, const int* __restrict__ tile_tab,
+                                                            const int* __restrict__ tile_n, const unsigned char* __restrict__ obs_slot,
+                                                            const unsigned short* __restrict__ pt_mask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V3Smem& sm = *reinterpret_cast<V3Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t p0 = (int64_t)blockIdx.x * tile_points;
+    const int64_t p1 = min(N, p0 + (int64_t)tile_points);
+    if (p0 >= N) return;
+    const int nbatch = (int)((p1 - p0 + kV3BP - 1) / kV3BP);
+    const int nLocal = tile_n[blockIdx.x];
+
+    if (w >= 8) {
+        // ================= producers: one lane per observation of the batch
+        const int ptid = tid - 256;
+        for (int b = 0; b < nbatch; ++b) {
+            const int s = b % kV3Stages;
+            if (b >= kV3Stages) bar_sync_named(1 + kV3Stages + s, kV3Threads);     // empty[s]: the consumers are done with batch b - stages
+            const int64_t pb0 = p0 + (int64_t)b * kV3BP;
+            const int64_t pb1 = min(p1, pb0 + kV3BP);
+            const int64_t ob = pt_begin[pb0], oe = pt_begin[pb1];
+            double* Vs = sm.V[s];
+            if (ptid < kV3BP * kV3Cams) {           // slots the point does not see (all of them for an absent / deferred point)
+                const int pl = ptid / kV3Cams, sl = ptid - pl * kV3Cams;
+                const int64_t j = pb0 + pl;
+                const unsigned mask = j < pb1 ? (unsigned)pt_mask[j] : 0u;
+                if (((mask >> sl) & 1u) == 0u) {
+                    double* r = Vs + (3 * pl) * kV3SLD + 10 * sl;
+#pragma unroll
+                    for (int v = 0; v < 3; ++v)
+#pragma unroll
+                        for (int a = 0; a < 10; a += 2) *reinterpret_cast<double2*>(r + v * kV3SLD + a) = make_double2(0.0, 0.0);
+                }
+            } else if (ptid < kV3BP * kV3Cams + kV3K) {   // u = Gi g_p of the batch's points (zero for absent / deferred / skipped ones)
+                const int e = ptid - kV3BP * kV3Cams;
+                const int pl = e / 3, v = e - 3 * pl;
+                const int64_t j = pb0 + pl;
+                double val = 0.0;
+                if (j < pb1 && pt_mask[j] != 0) val = uvec[(int64_t)v * N + j];
+                sm.U[s][e] = val;
+            }
+            for (int64_t o = ob + ptid; o < oe; o += 256) {
+                const int sl = obs_slot[o];
+                if (sl == 0xFF) continue;
+                const int64_t j = obs_pt[o];
+                const int pl = (int)(j - pb0);
+                double jp[6], jc[20], g[6];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+#pragma unroll
+                for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) g[i] = gi[(int64_t)i * N + j];
+                const bool live = skipped[j] == 0;
+                // Q = Gi (2 Jp^T): q[v][comp], Gi lower triangular {g00, g10, g11, g20, g21, g22}, jp[u*2 + comp]
+                double q[3][2];
+#pragma unroll
+                for (int cpt = 0; cpt < 2; ++cpt) {
+                    const double a0 = 2.0 * jp[0 + cpt], a1 = 2.0 * jp[2 + cpt], a2 = 2.0 * jp[4 + cpt];
+                    q[0][cpt] = g[0] * a0;
+                    q[1][cpt] = g[1] * a0 + g[2] * a1;
+                    q[2][cpt] = g[3] * a0 + g[4] * a1 + g[5] * a2;
+                }
+                double* r = Vs + (3 * pl) * kV3SLD + 10 * sl;
+#pragma unroll
+                for (int a = 0; a < 10; a += 2) {
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) {
+                        double x0 = q[v][0] * jc[a * 2] + q[v][1] * jc[a * 2 + 1];
+                        double x1 = q[v][0] * jc[a * 2 + 2] + q[v][1] * jc[a * 2 + 3];
+                        if (!live) { x0 = 0.0; x1 = 0.0; }   // BA.cpp:1877-1881: a non-invertible point block contributes nothing
+                        *reinterpret_cast<double2*>(r + v * kV3SLD + a) = make_double2(x0, x1);
+                    }
+                }
+            }
+            bar_arrive_named(1 + s, kV3Threads);                                   // full[s]
+        }
+        return;
+    }
+
+    // ================= consumers
+    const int g8 = lane >> 2, tg = lane & 3;
+    // super-block sb = I(I+1)/2 + Jc covers rows [24 I, 24 I + 24) x columns [24 Jc, 24 Jc + 24); a diagonal super-block computes the 6
+    // fragments on and below its diagonal; fragment rows / columns beyond the tile's last camera slot (10 * nLocal) are not computed.
+    // Dealing by SM sub-partition (warp w runs on sub-partition w % 4): with <= 11 cameras (14 fragment rows, 105 fragments) the pairs
+    // (w, w + 4) carry 15 + 12, 15 + 12, 15 + 12, 15 + 9 (+ the rhs GEMV on warp 7); with 12 cameras (120 fragments) 15 + 15, 15 + 18,
+    // 15 + 18, 15 + 9 (+ rhs).
+    int sbI[2] = {0, 0}, sbJ[2] = {0, 0}, code[2] = {-1, -1};
+    int nsb = 0;
+    {
+        constexpr int kSbOf[8][2] = {{1, 0}, {4, 2}, {6, 5}, {7, 9}, {3, 14}, {10, 11}, {12, 13}, {8, -1}};
+        const int lim = 10 * nLocal;
+        for (int q = 0; q < 2; ++q) {
+            const int sb = kSbOf[w][q];
+            if (sb < 0) break;
+            int I = 0;
+            while ((I + 1) * (I + 2) / 2 <= sb) ++I;
+            sbI[q] = I; sbJ[q] = sb - I * (I + 1) / 2;
+            nsb = q + 1;
+            int ni = (lim - 24 * sbI[q] + 7) / 8; ni = ni < 0 ? 0 : (ni > 3 ? 3 : ni);
+            int nj = (lim - 24 * sbJ[q] + 7) / 8; nj = nj < 0 ? 0 : (nj > 3 ? 3 : nj);
+            if (ni > 0 && nj > 0) code[q] = sbI[q] == sbJ[q] ? 9 + (ni - 1) : (ni - 1) * 3 + (nj - 1);
+        }
+    }
+    double acc[2][3][3][2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) { acc[q][i][jj][0] = 0.0; acc[q][i][jj][1] = 0.0; }
+    double racc[4] = {0.0, 0.0, 0.0, 0.0};   // warp 7: rhs entries m = lane + 32*q < 120
+
+    for (int b = 0; b < nbatch; ++b) {
+        const int s = b % kV3Stages;
+        bar_sync_named(1 + s, kV3Threads);                                         // full[s]
+        const double* V = sm.V[s];
+        v3_sb_dispatch(code[0], acc[0], V + tg * kV3SLD + 24 * sbI[0] + g8, V + tg * kV3SLD + 24 * sbJ[0] + g8);
+        if (nsb > 1) v3_sb_dispatch(code[1], acc[1], V + tg * kV3SLD + 24 * sbI[1] + g8, V + tg * kV3SLD + 24 * sbJ[1] + g8);
+        if (w == 7) {   // rhs += V^T u
+            const double* U = sm.U[s];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int m = lane + 32 * q;
+                if (m < kV3Rows) {
+                    double sacc = racc[q];
+#pragma unroll 8
+                    for (int kk = 0; kk < kV3K; ++kk) sacc += V[kk * kV3SLD + m] * U[kk];
+                    racc[q] = sacc;
+                }
+            }
+        }
+        if (b + kV3Stages < nbatch) bar_arrive_named(1 + kV3Stages + s, kV3Threads);   // empty[s]
+    }
+
+    // ---- flush: one red.global.add.f64 per touched entry per tile
+    if (tid < kV3Cams) sm.tab[tid] = tile_tab[(size_t)blockIdx.x * kV3Cams + tid];
+    bar_sync_named(9, 256);
+    for (int m = tid; m < kV3Rows; m += 256) {
+        const int slot = m / 10, a = m - 10 * slot;
+        sm.gidx[m] = slot < nLocal ? red_index(sm.tab[slot], a, sink.unity) : -1;
+    }
+    if (sink.blocks != nullptr) {
+        for (int e = tid; e < kV3Cams * kV3Cams; e += 256) {
+            const int si = e / kV3Cams, sl = e % kV3Cams;
+            sm.blk[e] = (si < nLocal && sl <= si) ? sink_block_id(sink, sm.tab[si], sm.tab[sl]) : -1;
+        }
+    }
+    bar_sync_named(9, 256);
+    const bool dense = sink.blocks == nullptr;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (q >= nsb) break;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const int row = 24 * sbI[q] + 8 * i + g8;
+            const int ri = sm.gidx[row], si = row / 10;
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double v = acc[q][i][jj][e];
+                    const int col = 24 * sbJ[q] + 8 * jj + 2 * tg + e;
+                    const int ci = sm.gidx[col], sl = col / 10;
+                    // lower block triangle; inside a diagonal block the lower triangle (row >= col) is computed once
+                    if (v == 0.0 || ri < 0 || ci < 0 || sl > si || (sl == si && col > row)) continue;
+                    if (dense) {
+                        atomicAdd(&sink.S[(size_t)ci * sink.ld + ri], -v);
+                    } else {
+                        const int blk = sm.blk[si * kV3Cams + sl];
+                        if (blk < 0) continue;
+                        const int a = row - 10 * si, bq = col - 10 * sl;
+                        atomicAdd(&sink.blocks[(size_t)blk * 100 + a * 10 + bq], -v);
+                        if (sl == si && a != bq) atomicAdd(&sink.blocks[(size_t)blk * 100 + bq * 10 + a], -v);   // stored diagonal blocks are full
+                    }
+                }
+        }
+    }
+    if (w == 7) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int m = lane + 32 * q;
+            if (m >= kV3Rows || racc[q] == 0.0) continue;
+            const int r = sm.gidx[m];
+            if (r < 0) continue;
+            const int slot = m / 10;
+            if (dense) atomicAdd(&sink.rhs[r], racc[q]);
+            else atomicAdd(&sink.rhs[(size_t)sm.tab[slot] * 10 + (m - 10 * slot)], racc[q]);
+        }
+    }
+}
+
+void launch_point_factor(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const double* J, double c, double* pinv, unsigned char* skipped,
+                         double* gi, double* uvec, int* exc_list, int* exc_count, int exc_cap) {
+    if (N <= 0) return;
+    k_point_factor<<<(unsigned)((N * 16 + 255) / 256), 256, 0, st>>>(N, O, pt_begin, J, c, pinv, skipped, gi, uvec, exc_list, exc_count, exc_cap);
+}
+
+void launch_schur_tables(cudaStream_t st, int64_t N, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, int* tile_tab, int* tile_n,
+                         unsigned char* obs_slot, unsigned short* pt_mask, unsigned char* deferred) {
+    if (N <= 0) return;
+    k_schur_tables<<<(unsigned)((N + tile_points - 1) / tile_points), 256, 0, st>>>(N, tile_points, pt_begin, obs_cam, tile_tab, tile_n, obs_slot, pt_mask, deferred);
+}
+
+void launch_schur_v3(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_pt, const double* J,
+                     const SchurSink& sink, const double* gi, const double* uvec, const unsigned char* skipped, const int* tile_tab, const int* tile_n,
+                     const unsigned char* obs_slot, const unsigned short* pt_mask) {
+    if (N <= 0) return;
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k_schur_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
+    const unsigned grid = (unsigned)((N + tile_points - 1) / tile_points);
+    k_schur_v3<<<grid, kV3Threads, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask);
+}
+
+}  // namespace srk
