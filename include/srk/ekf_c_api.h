@@ -68,6 +68,17 @@ SRK_API int srk_ekf_ransac_consensus_resident(void* h, int64_t m, const double* 
                                               double meas_var, const srk_ekf_camera* camera, double max_divergence_pix, int32_t* support, int32_t* best,
                                               unsigned char* best_inliers);
 
+/* Covariance growth for k new salient points on the resident state: the dense part of AllocateAndInitStateForNewSalientPoint
+ * (EKF.cpp:2322-2396; the reference calls conservativeResize -- a temporary and a full copy of P -- once per point):
+ *     x <- [x ; x_new],   P[new_i, old] = Jy_i P[0:7, old],   P[new_i, new_l] = Jy_i P[0:7, 0:7] Jy_l^T (+ Qnew_i when i == l)
+ * x_new [k*s]; Jy [k][s][7] row-major = d(new point) / d(camera position, quaternion) (sal_pnt_by_cam, EKF.cpp:2483-2512; for s = 3 times
+ * deriv_sal_pnt_xyz_by_spher, :2586-2592); Qnew [k][s][s] row-major = the part of the auto-covariance that does not come from P (pixel
+ * noise and initial inverse-distance variance, :2535-2539, conjugated likewise).  diag_only != 0: force_xyz_sal_pnt_pos_diagonal_uncert_
+ * (:2579-2584) -- zero cross covariance, auto-covariance = Qnew.  surikatoko_b200/ekf.py::new_salient_point forms x_new / Jy / Qnew from a
+ * corner pixel the way GetNewSphericalSalientPointState / ...Covar do (13 scalars of host code per point, like the kinematic model). */
+SRK_API int srk_ekf_add_points_resident(void* h, int64_t k, int32_t s, const double* x_new, const double* Jy, const double* Qnew, int32_t diag_only);
+SRK_API int srk_ekf_state_size(void* h, int64_t* n);
+
 /* One-shot forms with host buffers (upload, operate, download). */
 SRK_API int srk_ekf_update(void* h, int64_t n, int64_t m, double* P, double* x, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s,
                            const double* z, const double* h_pred, double meas_var);

@@ -347,6 +347,31 @@ def ekf_ransac(P, x, Hcam, Hpt, pt_off, z, meas_var, cam9, max_divergence_pix):
     return int(best), support, inl
 
 
+def ekf_new_point(cam9, cam13, corner_pix, inv_dist, inv_dist_std, meas_std_pix):
+    """GetNewSphericalSalientPointState + the small Jacobians of GetNewSphericalSalientPointCovar (EKF.cpp:2398-2527) and the XYZ conversion:
+    dict(spher[6], Jy6[6,7], Q6[6,6], xyz[3], Jy3[3,7], Q3[3,3], xyz_ok)."""
+    out = np.zeros(117)
+    c9 = np.ascontiguousarray(cam9, dtype=np.float64); c13 = np.ascontiguousarray(cam13, dtype=np.float64)
+    px = np.ascontiguousarray(corner_pix, dtype=np.float64)
+    ok = lib().srk_oracle_ekf_new_point(_p(c9, C.c_double), _p(c13, C.c_double), _p(px, C.c_double), C.c_double(inv_dist), C.c_double(inv_dist_std),
+                                        C.c_double(meas_std_pix), _p(out, C.c_double))
+    return dict(spher=out[0:6].copy(), Jy6=out[6:48].reshape(6, 7).copy(), Q6=out[48:84].reshape(6, 6).copy(), xyz=out[84:87].copy(),
+                Jy3=out[87:108].reshape(3, 7).copy(), Q3=out[108:117].reshape(3, 3).copy(), xyz_ok=bool(ok))
+
+
+def ekf_add_points(P, x, x_new, Jy, Qnew, diag_only=False):
+    """AllocateAndInitStateForNewSalientPoint (EKF.cpp:2322-2396), the points appended one after the other: (P_new, x_new_full)."""
+    Pn = np.asfortranarray(np.array(P, dtype=np.float64)); xn = np.ascontiguousarray(x, dtype=np.float64)
+    xa = np.ascontiguousarray(x_new, dtype=np.float64); k, s = xa.shape
+    Ja = np.ascontiguousarray(Jy, dtype=np.float64); Qa = np.ascontiguousarray(Qnew, dtype=np.float64)
+    n = xn.shape[0]; n2 = n + k * s
+    Pout = np.zeros((n2, n2), order="F"); xout = np.zeros(n2)
+    lib().srk_oracle_ekf_add_points(C.c_int64(n), Pn.ctypes.data_as(C.POINTER(C.c_double)), _p(xn, C.c_double), C.c_int64(k), C.c_int(s), _p(xa, C.c_double),
+                                    _p(Ja, C.c_double), _p(Qa, C.c_double), C.c_int(1 if diag_only else 0), Pout.ctypes.data_as(C.POINTER(C.c_double)),
+                                    _p(xout, C.c_double))
+    return Pout, xout
+
+
 def ekf_predict(P, F13, GQGt13, fix_symmetry=True):
     Pn = np.asfortranarray(np.array(P, dtype=np.float64))
     F = np.asfortranarray(np.array(F13, dtype=np.float64)); Q = np.asfortranarray(np.array(GQGt13, dtype=np.float64))

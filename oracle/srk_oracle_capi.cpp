@@ -11,6 +11,7 @@
 #include "srk_oracle_ekf.hpp"
 #include "srk_oracle_ekf_exact.hpp"
 #include "srk_oracle_ekf_ransac.hpp"
+#include "srk_oracle_ekf_newpoint.hpp"
 
 using namespace srk_oracle;
 
@@ -368,6 +369,32 @@ int srk_oracle_ekf_jacobians(int64_t n, int64_t m, const double* x, const int64_
     (void)n;
     EkfCamera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8] != 0.0 ? 1 : 0};
     for (int64_t i = 0; i < m; ++i) EkfMeasurementJacobian(cam, x, x + pt_off[i], s, Hcam + (size_t)(2 * i) * 13, Hpt + (size_t)(2 * i) * s, hd + 2 * i);
+    return 0;
+}
+// State / small Jacobians of a new salient point (EKF.cpp:2398-2527).  out55x = spher[6], Jy6[42], Q6[36], xyz[3], Jy3[21], Q3[9] in that order; returns xyz_ok.
+int srk_oracle_ekf_new_point(const double* cam9, const double* cam13, const double* corner_pix, double inv_dist, double inv_dist_std, double meas_std_pix, double* out117) {
+    EkfCamera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8] != 0.0 ? 1 : 0};
+    EkfNewPoint np;
+    EkfNewSalientPoint(cam, cam13, corner_pix, inv_dist, inv_dist_std, meas_std_pix, &np);
+    double* o = out117;
+    std::memcpy(o, np.spher, sizeof(np.spher)); o += 6;
+    std::memcpy(o, np.Jy6, sizeof(np.Jy6)); o += 42;
+    std::memcpy(o, np.Q6, sizeof(np.Q6)); o += 36;
+    std::memcpy(o, np.xyz, sizeof(np.xyz)); o += 3;
+    std::memcpy(o, np.Jy3, sizeof(np.Jy3)); o += 21;
+    std::memcpy(o, np.Q3, sizeof(np.Q3));
+    return np.xyz_ok;
+}
+// AllocateAndInitStateForNewSalientPoint (EKF.cpp:2322-2396), k points appended ONE AFTER THE OTHER as the reference does.
+// P [n x n] col-major in, Pout [(n + k s) x (n + k s)] col-major out, xout [n + k s].
+int srk_oracle_ekf_add_points(int64_t n, const double* P, const double* x, int64_t k, int s, const double* x_new, const double* Jy, const double* Qnew, int diag_only,
+                              double* Pout, double* xout) {
+    EkfMat Pm((size_t)n, (size_t)n);
+    std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);
+    std::vector<double> xs(x, x + n);
+    for (int64_t i = 0; i < k; ++i) EkfAddSalientPoint(&xs, &Pm, s, x_new + i * s, Jy + i * s * 7, Qnew + i * s * s, diag_only != 0);
+    std::memcpy(Pout, Pm.d.data(), sizeof(double) * Pm.d.size());
+    std::memcpy(xout, xs.data(), sizeof(double) * xs.size());
     return 0;
 }
 int srk_oracle_ekf_predict(int64_t n, double* P, const double* F13, const double* GQGt13, int fix_symmetry) {

@@ -222,15 +222,22 @@ __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __re
     __shared__ double xsl[3 * kResChunk];      // the chunk's points (a chunk of kResChunk observations spans at most as many point ids)
     double s = 0.0;
     const int64_t nchunks = (O + kResChunk - 1) / kResChunk;
-    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    // software pipeline over the CTA's chunks: the per-observation streams (slot, point id, pixel) of chunk i+1 are loaded into a second
+    // register set while chunk i is staged and evaluated, so that the long round trip of a chunk is hidden behind the previous chunk's
+    // arithmetic inside the CTA (before: load -> barrier -> arithmetic phases overlapped only across the resident CTAs of an SM)
+    int pt[kResRows], sl[kResRows]; double xs[kResRows], ys[kResRows];
+    auto load_obs = [&](int64_t ch, int (&p)[kResRows], int (&q)[kResRows], double (&a)[kResRows], double (&b)[kResRows]) {
         const int64_t base = ch * kResChunk + threadIdx.x;
-        int pt[kResRows], sl[kResRows]; double xs[kResRows], ys[kResRows];
 #pragma unroll
         for (int rr = 0; rr < kResRows; ++rr) {
             const int64_t o = base + 256 * rr;
-            const bool in = o < O;
-            sl[rr] = in ? (int)obs_slot[o] : -1; pt[rr] = in ? obs_pt[o] : 0; xs[rr] = in ? obs_xs[o] : 0.0; ys[rr] = in ? obs_ys[o] : 0.0;
+            const bool in = ch < nchunks && o < O;
+            q[rr] = in ? (int)obs_slot[o] : -1; p[rr] = in ? obs_pt[o] : 0; a[rr] = in ? obs_xs[o] : 0.0; b[rr] = in ? obs_ys[o] : 0.0;
         }
+    };
+    load_obs(blockIdx.x, pt, sl, xs, ys);
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const int64_t base = ch * kResChunk + threadIdx.x;
         const int n = chunk_cnt[ch] * kCamStride;
         const int2 pr = chunk_pts[ch];
         const bool staged = pr.y <= kResChunk;   // false only when point ids without observations stretch the range: gather from global then
@@ -244,6 +251,8 @@ __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __re
                 xsl[e] = X[pr.x + e]; xsl[kResChunk + e] = X[N + pr.x + e]; xsl[2 * kResChunk + e] = X[2 * N + pr.x + e];
             }
         }
+        int pt2[kResRows], sl2[kResRows]; double xs2[kResRows], ys2[kResRows];
+        load_obs(ch + gridDim.x, pt2, sl2, xs2, ys2);     // next chunk's streams: in flight during this chunk's arithmetic
         __syncthreads();
 #pragma unroll
         for (int rr = 0; rr < kResRows; ++rr) {
@@ -256,6 +265,8 @@ __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __re
             obs_residual(cd, X0r, X1r, X2r, xs[rr], ys[rr], rx, ry);
             s += rx * rx + ry * ry;
         }
+#pragma unroll
+        for (int rr = 0; rr < kResRows; ++rr) { pt[rr] = pt2[rr]; sl[rr] = sl2[rr]; xs[rr] = xs2[rr]; ys[rr] = ys2[rr]; }
     }
     __shared__ double red[8];
 #pragma unroll

@@ -524,6 +524,7 @@ struct Ekf {
     int64_t n = 0;
     DBuf P, x, PHt, S, ws, w, Hcam, Hpt, off, z, h, aux, tmp, neg, info, small;
     DBuf r_hyp, r_support, r_bits;   // 1-point RANSAC scoring: per-hypothesis vectors, support counts, inlier bit rows
+    DBuf Pgrow, xgrow, grow_in;      // covariance growth for new salient points: the grown copies (swapped in) and the small Jacobians
     int64_t launches = 0;
     bool timing = false;
     std::vector<cudaEvent_t> pend[E_COUNT];
@@ -764,6 +765,80 @@ int ransac_consensus(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, c
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Covariance growth for new salient points (AllocateAndInitStateForNewSalientPoint, EKF.cpp:2322-2396, with the P-dependent products of
+// GetNewSphericalSalientPointCovar :2528-2546 and the XYZ conversion :2586-2592), for k new points in one pass.  The reference resizes the
+// dense matrix once per point (conservativeResize: a temporary + a full copy each time); here the old block is copied once (a device
+// copy at HBM speed) and the k*s new rows / columns are filled by one kernel:
+//     P[new_i, old]   = Jy_i P[0:7, old]                      (bottom-left stripe, mirrored to the top right)
+//     P[new_i, new_l] = Jy_i P[0:7, 0:7] Jy_l^T  (+ Qnew_i when i == l)
+// which is what adding the points one after the other yields (P[0:7, new_l] = P[0:7, 0:7] Jy_l^T once point l exists).
+__global__ void __launch_bounds__(256) k_ekf_grow(int n, int n2, int k, int s, const double* __restrict__ Pold, double* __restrict__ Pnew,
+                                                  const double* __restrict__ Jy, const double* __restrict__ Q, int diag_only) {
+    const int r = n + blockIdx.y;                 // new row
+    const int kk = blockIdx.y / s, a = blockIdx.y - kk * s;
+    const double* jy = Jy + ((size_t)kk * s + a) * 7;
+    double j7[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) j7[q] = jy[q];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n2; c += gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (c < n) {
+            if (!diag_only) {
+#pragma unroll
+                for (int q = 0; q < 7; ++q) v += j7[q] * Pold[(size_t)c * n + q];
+            }
+            Pnew[(size_t)c * n2 + r] = v;
+            Pnew[(size_t)r * n2 + c] = v;
+        } else {
+            const int ll = (c - n) / s, b = (c - n) - ll * s;
+            if (c > r) continue;                  // the lower triangle of the new-new block; mirrored below
+            if (!diag_only) {
+                const double* jl = Jy + ((size_t)ll * s + b) * 7;
+                for (int t = 0; t < 7; ++t) {
+                    double w = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 7; ++q) w += j7[q] * Pold[(size_t)t * n + q];
+                    v += w * jl[t];
+                }
+            }
+            if (ll == kk) v += Q[((size_t)kk * s + a) * s + b];
+            Pnew[(size_t)c * n2 + r] = v;
+            Pnew[(size_t)r * n2 + c] = v;
+        }
+    }
+}
+
+int add_points_resident(Ekf& e, int64_t k, int s, const double* x_new, const double* Jy, const double* Qnew, int diag_only) {
+    if (e.n <= 0) { g_ekf_error = "srk_ekf_add_points_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
+    if (k <= 0 || (s != 3 && s != 6) || x_new == nullptr || Jy == nullptr || Qnew == nullptr) { g_ekf_error = "bad add-points arguments (s must be 3 or 6)"; return SRK_E_INVALID_ARG; }
+    const int64_t n = e.n, n2 = e.n + k * s;
+    if (n2 > 60000) { g_ekf_error = "state too large"; return SRK_E_TOO_LARGE; }
+    EKF_CUDA(cudaSetDevice(e.device));
+    cudaStream_t st = e.st;
+    EKF_CUDA(e.Pgrow.ensure(sizeof(double) * (size_t)n2 * n2 + 64)); EKF_CUDA(e.xgrow.ensure(sizeof(double) * (size_t)n2));
+    EKF_CUDA(e.small.ensure(sizeof(double) * (3 * kCam * kCam + kCam)));
+    EKF_CUDA(e.grow_in.ensure(sizeof(double) * (size_t)k * s * (7 + s)));
+    double* dJy = e.grow_in.as<double>(); double* dQ = dJy + (size_t)k * s * 7;
+    EKF_CUDA(cudaMemcpyAsync(dJy, Jy, sizeof(double) * (size_t)k * s * 7, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(dQ, Qnew, sizeof(double) * (size_t)k * s * s, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpy2DAsync(e.Pgrow.p, sizeof(double) * (size_t)n2, e.P.p, sizeof(double) * (size_t)n, sizeof(double) * (size_t)n, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.xgrow.p, e.x.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.xgrow.as<double>() + n, x_new, sizeof(double) * (size_t)k * s, cudaMemcpyHostToDevice, st));
+    {
+        EScope sc(e, E_STATE);
+        dim3 grid((unsigned)((n2 + 255) / 256 < 64 ? (n2 + 255) / 256 : 64), (unsigned)(k * s));
+        k_ekf_grow<<<grid, 256, 0, st>>>((int)n, (int)n2, (int)k, s, e.P.as<double>(), e.Pgrow.as<double>(), dJy, dQ, diag_only);
+        e.launches += 1;
+    }
+    EKF_CUDA(cudaStreamSynchronize(st));
+    EKF_CUDA(cudaGetLastError());
+    std::swap(e.P.p, e.Pgrow.p); std::swap(e.P.cap, e.Pgrow.cap);
+    std::swap(e.x.p, e.xgrow.p); std::swap(e.x.cap, e.xgrow.cap);
+    e.n = n2;
+    return SRK_OK;
+}
+
 extern "C" {
 
 int srk_ekf_create(void** h, int device) {
@@ -830,6 +905,15 @@ int srk_ekf_ransac_consensus_resident(void* h, int64_t m, const double* Hcam, co
                                       const srk_ekf_camera* camera, double max_divergence_pix, int32_t* support, int32_t* best, unsigned char* best_inliers) {
     if (h == nullptr) return SRK_E_INVALID_ARG;
     return ransac_consensus(*(Ekf*)h, m, Hcam, Hpt, pt_off, s, z, meas_var, camera, max_divergence_pix, support, best, best_inliers);
+}
+int srk_ekf_add_points_resident(void* h, int64_t k, int32_t s, const double* x_new, const double* Jy, const double* Qnew, int32_t diag_only) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    return add_points_resident(*(Ekf*)h, k, s, x_new, Jy, Qnew, diag_only);
+}
+int srk_ekf_state_size(void* h, int64_t* n) {
+    if (h == nullptr || n == nullptr) return SRK_E_INVALID_ARG;
+    *n = ((Ekf*)h)->n;
+    return SRK_OK;
 }
 int srk_ekf_update_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, const double* z, const double* h_pred,
                             double meas_var, int32_t* info) {

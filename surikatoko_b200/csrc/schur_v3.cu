@@ -38,6 +38,7 @@ constexpr int kV3Hash = 64;
 struct V3Smem {
     double V[kV3Stages][kV3K * kV3SLD];
     double U[kV3Stages][kV3K];
+    double G[kV3Stages][kV3BP * 6];      // Gi of the batch's points
     int gidx[kV3Rows];
     int blk[kV3Cams * kV3Cams];
     int tab[kV3Cams];
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256) k_point_factor(int64_t N, int64_t O, cons
 // ---------------------------------------------------------------------------------------------------------------------------------
 // Bind-time tables of the tile kernel.  Same table construction and the same deferral rule as k_schur_plan (schur_mma.cu): the
 // kV3Cams smallest distinct camera ids of the tile, sorted; a point is deferred when it has more than 16 observations or sees a camera
-// outside the table.  Outputs: tile_tab [tiles x 12], tile_n [tiles], obs_slot [O] (0xFF for observations of deferred points),
+// outside the table.  Outputs: tile_tab [tiles x 12], tile_n [tiles], obs_slot [O] (point-in-batch << 4 | table slot; slot 0xF for observations of deferred points),
 // pt_mask [N] (bit s = the point sees table slot s; 0 for deferred points), deferred [N] (rewritten with the same values).
 __global__ void __launch_bounds__(256) k_schur_tables(int64_t N, int tile_points, const int64_t* __restrict__ pt_begin, const int32_t* __restrict__ obs_cam,
                                                       int* __restrict__ tile_tab, int* __restrict__ tile_n, unsigned char* __restrict__ obs_slot,
@@ -180,10 +181,11 @@ __global__ void __launch_bounds__(256) k_schur_tables(int64_t N, int tile_points
         }
         deferred[j] = bad ? 1 : 0;
         pt_mask[j] = bad ? (unsigned short)0 : (unsigned short)mask;
+        const int pl = (int)((j - p0) % kV3BP);       // the point's position inside its batch of the tile (tiles start on batch boundaries)
         for (int i = 0; i < k; ++i) {
-            int loc = 0xFF;
+            int loc = 0xF;
             if (!bad) { const int cam = obs_cam[kb + i]; for (int q = 0; q < nLocal; ++q) if (tab[q] == cam) loc = q; }
-            obs_slot[kb + i] = (unsigned char)loc;
+            obs_slot[kb + i] = (unsigned char)((pl << 4) | loc);
         }
     }
 }
@@ -247,14 +249,44 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
 
     if (w >= 8) {
         // ================= producers: one lane per observation of the batch
+        // Every global address of a batch is known before the batch starts: the observation extents come one batch ahead, the per-point
+        // Gi / u / slot masks are addressed by the batch's first point id (staged to shared memory by helper lanes) and the position of an
+        // observation's point inside the batch travels in the slot byte -- ONE round trip per batch, no dependent loads.
         const int ptid = tid - 256;
+        int64_t ob = pt_begin[p0], oe = pt_begin[min(p1, p0 + (int64_t)kV3BP)];
         for (int b = 0; b < nbatch; ++b) {
             const int s = b % kV3Stages;
-            if (b >= kV3Stages) bar_sync_named(1 + kV3Stages + s, kV3Threads);     // empty[s]: the consumers are done with batch b - stages
             const int64_t pb0 = p0 + (int64_t)b * kV3BP;
             const int64_t pb1 = min(p1, pb0 + kV3BP);
-            const int64_t ob = pt_begin[pb0], oe = pt_begin[pb1];
+            int64_t ob_n = 0, oe_n = 0;
+            if (b + 1 < nbatch) { ob_n = oe; oe_n = pt_begin[min(p1, pb0 + 2 * (int64_t)kV3BP)]; }
+            if (b >= kV3Stages) bar_sync_named(1 + kV3Stages + s, kV3Threads);     // empty[s]: the consumers are done with batch b - stages
             double* Vs = sm.V[s];
+            // ---- this lane's observation (first pass): loads in flight before anything is waited for
+            int64_t o = ob + ptid;
+            bool have = o < oe;
+            int sb = 0xF;
+            double jp[6], jc[20];
+            if (have) {
+                sb = obs_slot[o];
+#pragma unroll
+                for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+#pragma unroll
+                for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
+            }
+            // ---- helper lanes: per-point data of the batch
+            if (ptid < kV3BP * 6) {
+                const int pl = ptid / 6, i = ptid - 6 * pl;
+                const int64_t j = pb0 + pl;
+                sm.G[s][ptid] = j < pb1 ? gi[(int64_t)i * N + j] : 0.0;
+            } else if (ptid < kV3BP * 6 + kV3K) {     // u = Gi g_p of the batch's points (zero for absent / deferred / skipped ones)
+                const int e = ptid - kV3BP * 6;
+                const int pl = e / 3, v = e - 3 * pl;
+                const int64_t j = pb0 + pl;
+                double val = 0.0;
+                if (j < pb1 && pt_mask[j] != 0) val = uvec[(int64_t)v * N + j];
+                sm.U[s][e] = val;
+            }
             if (ptid < kV3BP * kV3Cams) {           // slots the point does not see (all of them for an absent / deferred point)
                 const int pl = ptid / kV3Cams, sl = ptid - pl * kV3Cams;
                 const int64_t j = pb0 + pl;
@@ -266,49 +298,47 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
 #pragma unroll
                         for (int a = 0; a < 10; a += 2) *reinterpret_cast<double2*>(r + v * kV3SLD + a) = make_double2(0.0, 0.0);
                 }
-            } else if (ptid < kV3BP * kV3Cams + kV3K) {   // u = Gi g_p of the batch's points (zero for absent / deferred / skipped ones)
-                const int e = ptid - kV3BP * kV3Cams;
-                const int pl = e / 3, v = e - 3 * pl;
-                const int64_t j = pb0 + pl;
-                double val = 0.0;
-                if (j < pb1 && pt_mask[j] != 0) val = uvec[(int64_t)v * N + j];
-                sm.U[s][e] = val;
             }
-            for (int64_t o = ob + ptid; o < oe; o += 256) {
-                const int sl = obs_slot[o];
-                if (sl == 0xFF) continue;
-                const int64_t j = obs_pt[o];
-                const int pl = (int)(j - pb0);
-                double jp[6], jc[20], g[6];
+            bar_sync_named(10, 256);                 // producers only: G[s] is complete
+            for (;;) {
+                if (have && (sb & 0xF) != 0xF) {
+                    const int pl = sb >> 4, sl = sb & 0xF;
+                    const double* g = sm.G[s] + 6 * pl;   // {g00, g10, g11, g20, g21, g22}; all zero for a skipped point (BA.cpp:1877-1881: no contribution)
+                    // Q = Gi (2 Jp^T): q[v][comp], jp[u*2 + comp]
+                    double q[3][2];
 #pragma unroll
-                for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
-#pragma unroll
-                for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
-#pragma unroll
-                for (int i = 0; i < 6; ++i) g[i] = gi[(int64_t)i * N + j];
-                const bool live = skipped[j] == 0;
-                // Q = Gi (2 Jp^T): q[v][comp], Gi lower triangular {g00, g10, g11, g20, g21, g22}, jp[u*2 + comp]
-                double q[3][2];
-#pragma unroll
-                for (int cpt = 0; cpt < 2; ++cpt) {
-                    const double a0 = 2.0 * jp[0 + cpt], a1 = 2.0 * jp[2 + cpt], a2 = 2.0 * jp[4 + cpt];
-                    q[0][cpt] = g[0] * a0;
-                    q[1][cpt] = g[1] * a0 + g[2] * a1;
-                    q[2][cpt] = g[3] * a0 + g[4] * a1 + g[5] * a2;
-                }
-                double* r = Vs + (3 * pl) * kV3SLD + 10 * sl;
-#pragma unroll
-                for (int a = 0; a < 10; a += 2) {
-#pragma unroll
-                    for (int v = 0; v < 3; ++v) {
-                        double x0 = q[v][0] * jc[a * 2] + q[v][1] * jc[a * 2 + 1];
-                        double x1 = q[v][0] * jc[a * 2 + 2] + q[v][1] * jc[a * 2 + 3];
-                        if (!live) { x0 = 0.0; x1 = 0.0; }   // BA.cpp:1877-1881: a non-invertible point block contributes nothing
-                        *reinterpret_cast<double2*>(r + v * kV3SLD + a) = make_double2(x0, x1);
+                    for (int cpt = 0; cpt < 2; ++cpt) {
+                        const double a0 = 2.0 * jp[0 + cpt], a1 = 2.0 * jp[2 + cpt], a2 = 2.0 * jp[4 + cpt];
+                        q[0][cpt] = g[0] * a0;
+                        q[1][cpt] = g[1] * a0 + g[2] * a1;
+                        q[2][cpt] = g[3] * a0 + g[4] * a1 + g[5] * a2;
                     }
+                    const bool live = g[0] != 0.0;
+                    double* r = Vs + (3 * pl) * kV3SLD + 10 * sl;
+#pragma unroll
+                    for (int a = 0; a < 10; a += 2) {
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) {
+                            double x0 = q[v][0] * jc[a * 2] + q[v][1] * jc[a * 2 + 1];
+                            double x1 = q[v][0] * jc[a * 2 + 2] + q[v][1] * jc[a * 2 + 3];
+                            if (!live) { x0 = 0.0; x1 = 0.0; }
+                            *reinterpret_cast<double2*>(r + v * kV3SLD + a) = make_double2(x0, x1);
+                        }
+                    }
+                }
+                o += 256;                             // batches with more than 256 observations (deferred long tracks inside the range): further passes
+                if (!__any_sync(0xffffffffu, o < oe)) break;
+                have = o < oe;
+                if (have) {
+                    sb = obs_slot[o];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) jp[i] = J[(int64_t)(2 + i) * O + o];
+#pragma unroll
+                    for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
                 }
             }
             bar_arrive_named(1 + s, kV3Threads);                                   // full[s]
+            ob = ob_n; oe = oe_n;
         }
         return;
     }

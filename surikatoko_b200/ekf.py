@@ -27,6 +27,8 @@ def _lib():
         L.srk_ekf_ransac_consensus_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double,
                                                         C.c_void_p, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
         L.srk_ekf_measurement_jacobians_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.srk_ekf_add_points_resident.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.srk_ekf_state_size.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.srk_ekf_update.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_double]
         L.srk_ekf_predict.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -54,6 +56,54 @@ class EkfCamera(C.Structure):
 
     def as_array(self):
         return np.array([self.fx_pix, self.fy_pix, self.cx, self.cy, self.dx_mm, self.dy_mm, self.k1, self.k2, float(self.enable_distortion)])
+
+
+def new_salient_point(cam13, corner_pix, camera, inv_dist, inv_dist_std, meas_std_pix, s=3):
+    """State and small Jacobians of a new salient point seen at `corner_pix` from camera state `cam13` -- the host side of
+    AllocateAndInitStateForNewSalientPoint (EKF.cpp:2322-2396), 13 scalars of work per point like the kinematic model:
+    GetNewSphericalSalientPointState (:2398-2455: undistortion, A.58 back-projection, azimuth / elevation, constant initial inverse
+    distance), the Jacobians of GetNewSphericalSalientPointCovar (:2457-2527, A.67-A.79) and, for s = 3, ConvertXyzFromSphericalSalientPoint
+    (:405-416) with DerivSalPnt_xyz_by_spher (:3790-3828).  Returns (x_new [s], Jy [s, 7], Qnew [s, s]) for EkfEngine.add_points:
+    Jy = d(point) / d(camera position, quaternion), Qnew = the auto-covariance term that does not come from P (pixel noise through
+    sal_pnt_by_h_rho, initial inverse-distance variance)."""
+    cam13 = np.asarray(cam13, dtype=np.float64); q = cam13[3:7]
+    hd = np.asarray(corner_pix, dtype=np.float64)
+    cx, cy, dx, dy, k1, k2 = camera.cx, camera.cy, camera.dx_mm, camera.dy_mm, camera.k1, camera.k2
+    hu = hd.copy(); hu_by_hd = np.eye(2)
+    if camera.enable_distortion:
+        rd = np.sqrt((dx * (hd[0] - cx)) ** 2 + (dy * (hd[1] - cy)) ** 2)                       # A.24
+        stretch = 1 + k1 * rd ** 2 + k2 * rd ** 4
+        hu = np.array([cx + (hd[0] - cx) * stretch, cy + (hd[1] - cy) * stretch])
+        kk = k1 + 2 * k2 * rd ** 2
+        side = 2 * kk * (hd[1] - cy) * (hd[0] - cx)
+        hu_by_hd = np.array([[stretch + 2 * kk * (dx * (hd[0] - cx)) ** 2, side * dy ** 2],   # A.32, entries as the reference assigns them (:2674-2678)
+                             [side * dx ** 2, stretch + 2 * kk * (dy * (hd[1] - cy)) ** 2]])
+    hc = np.array([-(hu[0] - cx) / camera.fx_pix, -(hu[1] - cy) / camera.fy_pix, 1.0])          # A.58
+    R = _quat_to_R(q)
+    hw = R @ hc
+    theta = np.arctan2(hw[0], hw[2]); phi = np.arctan2(-hw[1], np.sqrt(hw[0] ** 2 + hw[2] ** 2))
+    dR = [np.array([[2 * q[0], -2 * q[3], 2 * q[2]], [2 * q[3], 2 * q[0], -2 * q[1]], [-2 * q[2], 2 * q[1], 2 * q[0]]]),     # A.46-A.49
+          np.array([[2 * q[1], 2 * q[2], 2 * q[3]], [2 * q[2], -2 * q[1], -2 * q[0]], [2 * q[3], 2 * q[0], -2 * q[1]]]),
+          np.array([[-2 * q[2], 2 * q[1], 2 * q[0]], [2 * q[1], 2 * q[2], 2 * q[3]], [-2 * q[0], 2 * q[3], -2 * q[2]]]),
+          np.array([[-2 * q[3], -2 * q[0], 2 * q[1]], [2 * q[0], -2 * q[3], 2 * q[2]], [2 * q[1], 2 * q[2], 2 * q[3]]])]
+    hw_by_q = np.stack([d @ hc for d in dR], axis=1)                                             # A.73
+    dxz2 = hw[0] ** 2 + hw[2] ** 2; d2 = dxz2 + hw[1] ** 2; dxz = np.sqrt(dxz2); sf = hw[1] / (d2 * dxz)
+    th_by_hw = np.array([hw[2] / dxz2, 0.0, -hw[0] / dxz2]); ph_by_hw = np.array([hw[0] * sf, -dxz / d2, hw[2] * sf])
+    Jy6 = np.zeros((6, 7)); Jy6[0:3, 0:3] = np.eye(3)
+    Jy6[3, 3:7] = th_by_hw @ hw_by_q; Jy6[4, 3:7] = ph_by_hw @ hw_by_q
+    hw_by_hd = R @ (np.array([[-1 / camera.fx_pix, 0.0], [0.0, -1 / camera.fy_pix], [0.0, 0.0]]) @ hu_by_hd)
+    A = np.zeros((6, 3)); A[3, 0:2] = th_by_hw @ hw_by_hd; A[4, 0:2] = ph_by_hw @ hw_by_hd; A[5, 2] = 1.0
+    Q6 = A @ np.diag([meas_std_pix ** 2, meas_std_pix ** 2, inv_dist_std ** 2]) @ A.T
+    spher = np.array([cam13[0], cam13[1], cam13[2], theta, phi, inv_dist])
+    if s == 6:
+        return spher, Jy6, Q6
+    ct, st, cp, sp = np.cos(theta), np.sin(theta), np.cos(phi), np.sin(phi)
+    dist, dist2 = 1 / inv_dist, 1 / inv_dist ** 2
+    xyz = cam13[0:3] + dist * np.array([cp * st, -sp, cp * ct])
+    D = np.array([[1, 0, 0, dist * cp * ct, -dist * sp * st, -dist2 * cp * st],
+                  [0, 1, 0, 0.0, -dist * cp, dist2 * sp],
+                  [0, 0, 1, -dist * cp * st, -dist * sp * ct, -dist2 * cp * ct]])
+    return xyz, D @ Jy6, D @ Q6 @ D.T
 
 
 def scenario01_camera(enable_distortion=True, k1=0.06, k2=0.01):
@@ -104,6 +154,17 @@ class EkfEngine:
         info = C.c_int32(0)
         _chk(self._L.srk_ekf_update_resident(self._h, off.shape[0], _p(Hc), _p(Hp), _p(off), Hp.shape[1], _p(zz), _p(hh), float(meas_var), C.byref(info)))
         return info.value
+
+    def add_points(self, x_new, Jy, Qnew, diag_only=False):
+        """Covariance growth for k new salient points on the resident state (srk_ekf_add_points_resident; AllocateAndInitStateForNewSalientPoint,
+        EKF.cpp:2322-2396): x_new [k, s], Jy [k, s, 7], Qnew [k, s, s] as new_salient_point() forms them.  Returns the new state size."""
+        xa = np.ascontiguousarray(x_new, dtype=np.float64); k, s = xa.shape
+        Ja = np.ascontiguousarray(Jy, dtype=np.float64).reshape(k, s, 7); Qa = np.ascontiguousarray(Qnew, dtype=np.float64).reshape(k, s, s)
+        _chk(self._L.srk_ekf_add_points_resident(self._h, k, s, _p(xa), _p(Ja), _p(Qa), 1 if diag_only else 0))
+        n = C.c_int64(0)
+        _chk(self._L.srk_ekf_state_size(self._h, C.byref(n)))
+        self.n = n.value
+        return self.n
 
     def measurement_jacobians(self, pt_off, s, camera):
         """Deriv_hd_by_cam_state_and_sal_pnt for every listed point at the resident state (EKF.cpp:3067-3159): (Hcam, Hpt, h_pred)."""

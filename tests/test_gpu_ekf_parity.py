@@ -142,3 +142,43 @@ def test_batched_measurement_jacobians_match_oracle(oracle, ekf, npts, s, dist, 
     assert ekf.update(Hc[rows], Hp[rows], fr["pt_off"][sel], fr["z"][rows], hd[rows], fr["meas_var"]) == 0
     P, x = ekf.get_state()
     assert relerr(x, x_ref) < TOL and relerr(P, P_ref) < TOL
+
+
+@pytest.mark.parametrize("s,k", [(3, 5), (6, 3)])
+def test_covariance_growth_for_new_points_matches_oracle(oracle, s, k):
+    """srk_ekf_add_points_resident (AllocateAndInitStateForNewSalientPoint, EKF.cpp:2322-2396) for k new points in one pass against the
+    oracle appending them one after the other; the small Jacobians come from new_salient_point (host side) on real corner pixels.  Then a
+    stacked update on the grown state (the new points are observed too) against the oracle's update of the oracle's grown state."""
+    from surikatoko_b200.ekf import EkfEngine, new_salient_point, scenario01_camera, synthetic_ransac_frame
+    fr = synthetic_ransac_frame(40, s, seed=21)
+    cam = fr["camera"]
+    rng = np.random.default_rng(9)
+    px = np.stack([rng.uniform(40, 280, k), rng.uniform(30, 210, k)], axis=1)
+    parts = [new_salient_point(fr["x"][:13], px[i], cam, 0.25, 0.3, 1.0, s=s) for i in range(k)]
+    xn = np.stack([p[0] for p in parts]); Jy = np.stack([p[1] for p in parts]); Q = np.stack([p[2] for p in parts])
+    P_ref, x_ref = oracle.ekf_add_points(fr["P"], fr["x"], xn, Jy, Q)
+    ekf = EkfEngine(0)
+    try:
+        ekf.set_state(fr["P"], fr["x"])
+        n2 = ekf.add_points(xn, Jy, Q)
+        assert n2 == fr["n"] + k * s
+        P, x = ekf.get_state()
+        assert relerr(P, P_ref) < 1e-14 and np.array_equal(x, x_ref) and np.array_equal(P, P.T)
+        assert np.array_equal(P[:fr["n"], :fr["n"]], fr["P"]), "the old block must be untouched"
+        # one frame later: all points, old and new, observed
+        off = np.concatenate([fr["pt_off"], fr["n"] + s * np.arange(k)])
+        Hc, Hp, hp = ekf.measurement_jacobians(off, s, cam)
+        z = hp + np.random.default_rng(3).normal(0, 0.5, hp.shape)
+        ok, P_u, x_u, _ = oracle.ekf_update(P_ref, x_ref, Hc, Hp, off, z, hp, 1.0)
+        assert ok
+        assert ekf.update(Hc, Hp, off, z, hp, 1.0) == 0
+        P2, x2 = ekf.get_state()
+        assert relerr(x2, x_u) < TOL and relerr(P2, P_u) < TOL
+        # diagonal-uncertainty variant (force_xyz_sal_pnt_pos_diagonal_uncert_, :2579-2584)
+        ekf.set_state(fr["P"], fr["x"])
+        ekf.add_points(xn, Jy, Q, diag_only=True)
+        Pd, _ = ekf.get_state()
+        Pd_ref, _ = oracle.ekf_add_points(fr["P"], fr["x"], xn, Jy, Q, diag_only=True)
+        assert np.array_equal(Pd, Pd_ref)
+    finally:
+        ekf.close()
