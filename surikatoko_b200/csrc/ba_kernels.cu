@@ -64,9 +64,10 @@ constexpr int kObsRows = 4;
 __global__ void __launch_bounds__(256) k_jacobian(int64_t O, const int32_t* __restrict__ obs_cam, const int32_t* __restrict__ obs_pt,
                                                   const double* __restrict__ obs_xs, const double* __restrict__ obs_ys,
                                                   const double* __restrict__ X, int64_t N, const double* __restrict__ camd,
-                                                  double* __restrict__ J) {
+                                                  double* __restrict__ J, double* __restrict__ Eacc) {
     __shared__ CamTable tab;
     const int64_t base = (int64_t)blockIdx.x * (256 * kObsRows) + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     cam_table_reset(tab);
     int cam[kObsRows], hp[kObsRows];
 #pragma unroll
@@ -80,19 +81,55 @@ __global__ void __launch_bounds__(256) k_jacobian(int64_t O, const int32_t* __re
 #pragma unroll
     for (int rr = 0; rr < kObsRows; ++rr) {
         const int64_t o = base + 256 * rr;
-        if (o >= O) continue;
-        const int pt = obs_pt[o];
-        const double xs = obs_xs[o], ys = obs_ys[o];
-        const double X0 = X[pt], X1 = X[N + pt], X2 = X[2 * N + pt];
-        const double* cd = cam_table_record(tab, hp[rr], cam[rr], camd);
-        double rx, ry, jp[6], jc[20];
-        obs_jacobian(cd, X0, X1, X2, xs, ys, rx, ry, jp, jc);
-        J[o] = rx;
-        J[O + o] = ry;
+        const bool valid = o < O;
+        int pt = -1;
+        double a9[9];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) J[(int64_t)(2 + i) * O + o] = jp[i];
+        for (int i = 0; i < 9; ++i) a9[i] = 0.0;
+        if (valid) {
+            pt = obs_pt[o];
+            const double xs = obs_xs[o], ys = obs_ys[o];
+            const double X0 = X[pt], X1 = X[N + pt], X2 = X[2 * N + pt];
+            const double* cd = cam_table_record(tab, hp[rr], cam[rr], camd);
+            double rx, ry, jp[6], jc[20];
+            obs_jacobian(cd, X0, X1, X2, xs, ys, rx, ry, jp, jc);
+            J[o] = rx;
+            J[O + o] = ry;
 #pragma unroll
-        for (int i = 0; i < 20; ++i) J[(int64_t)(8 + i) * O + o] = jc[i];
+            for (int i = 0; i < 6; ++i) J[(int64_t)(2 + i) * O + o] = jp[i];
+#pragma unroll
+            for (int i = 0; i < 20; ++i) J[(int64_t)(8 + i) * O + o] = jc[i];
+            if (Eacc != nullptr) {     // this observation's terms of E_j / 2 = sum Jp^T Jp and g_pj / 2 = sum Jp^T rho (BA.cpp:1184-1220)
+                a9[0] = jp[0] * jp[0] + jp[1] * jp[1];
+                a9[1] = jp[0] * jp[2] + jp[1] * jp[3];
+                a9[2] = jp[0] * jp[4] + jp[1] * jp[5];
+                a9[3] = jp[2] * jp[2] + jp[3] * jp[3];
+                a9[4] = jp[2] * jp[4] + jp[3] * jp[5];
+                a9[5] = jp[4] * jp[4] + jp[5] * jp[5];
+                a9[6] = jp[0] * rx + jp[1] * ry;
+                a9[7] = jp[2] * rx + jp[3] * ry;
+                a9[8] = jp[4] * rx + jp[5] * ry;
+            }
+        }
+        if (Eacc != nullptr) {
+            // Observations are point-major: the lanes of one point are contiguous.  Segmented inclusive scan over the warp (a lane adds
+            // the value d lanes below while that lane belongs to the same point), then the LAST lane of every segment adds the point's
+            // partial sum to Eacc with red.global.add.f64.  A point's observations meet in at most a few warps; the partial sums land on
+            // exact zeros and floating-point addition commutes, so the result does not depend on the order for up to two partials
+            // (tracks of at most 32 observations) -- the per-point blocks are consumed by k_point_finish (schur_v3.cu).
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int ptu = __shfl_up_sync(0xffffffffu, pt, d);
+                const bool take = lane >= d && ptu == pt;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) { const double v = __shfl_up_sync(0xffffffffu, a9[i], d); if (take) a9[i] += v; }
+            }
+            const int ptn = __shfl_down_sync(0xffffffffu, pt, 1);
+            if (valid && (lane == 31 || ptn != pt)) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) atomicAdd(&Eacc[(int64_t)i * N + pt], a9[i]);
+            }
+        }
     }
 }
 
@@ -222,22 +259,15 @@ __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __re
     __shared__ double xsl[3 * kResChunk];      // the chunk's points (a chunk of kResChunk observations spans at most as many point ids)
     double s = 0.0;
     const int64_t nchunks = (O + kResChunk - 1) / kResChunk;
-    // software pipeline over the CTA's chunks: the per-observation streams (slot, point id, pixel) of chunk i+1 are loaded into a second
-    // register set while chunk i is staged and evaluated, so that the long round trip of a chunk is hidden behind the previous chunk's
-    // arithmetic inside the CTA (before: load -> barrier -> arithmetic phases overlapped only across the resident CTAs of an SM)
-    int pt[kResRows], sl[kResRows]; double xs[kResRows], ys[kResRows];
-    auto load_obs = [&](int64_t ch, int (&p)[kResRows], int (&q)[kResRows], double (&a)[kResRows], double (&b)[kResRows]) {
+    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
         const int64_t base = ch * kResChunk + threadIdx.x;
+        int pt[kResRows], sl[kResRows]; double xs[kResRows], ys[kResRows];
 #pragma unroll
         for (int rr = 0; rr < kResRows; ++rr) {
             const int64_t o = base + 256 * rr;
-            const bool in = ch < nchunks && o < O;
-            q[rr] = in ? (int)obs_slot[o] : -1; p[rr] = in ? obs_pt[o] : 0; a[rr] = in ? obs_xs[o] : 0.0; b[rr] = in ? obs_ys[o] : 0.0;
+            const bool in = o < O;
+            sl[rr] = in ? (int)obs_slot[o] : -1; pt[rr] = in ? obs_pt[o] : 0; xs[rr] = in ? obs_xs[o] : 0.0; ys[rr] = in ? obs_ys[o] : 0.0;
         }
-    };
-    load_obs(blockIdx.x, pt, sl, xs, ys);
-    for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const int64_t base = ch * kResChunk + threadIdx.x;
         const int n = chunk_cnt[ch] * kCamStride;
         const int2 pr = chunk_pts[ch];
         const bool staged = pr.y <= kResChunk;   // false only when point ids without observations stretch the range: gather from global then
@@ -251,8 +281,6 @@ __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __re
                 xsl[e] = X[pr.x + e]; xsl[kResChunk + e] = X[N + pr.x + e]; xsl[2 * kResChunk + e] = X[2 * N + pr.x + e];
             }
         }
-        int pt2[kResRows], sl2[kResRows]; double xs2[kResRows], ys2[kResRows];
-        load_obs(ch + gridDim.x, pt2, sl2, xs2, ys2);     // next chunk's streams: in flight during this chunk's arithmetic
         __syncthreads();
 #pragma unroll
         for (int rr = 0; rr < kResRows; ++rr) {
@@ -265,8 +293,6 @@ __global__ void __launch_bounds__(256) k_residual(int64_t O, const int32_t* __re
             obs_residual(cd, X0r, X1r, X2r, xs[rr], ys[rr], rx, ry);
             s += rx * rx + ry * ry;
         }
-#pragma unroll
-        for (int rr = 0; rr < kResRows; ++rr) { pt[rr] = pt2[rr]; sl[rr] = sl2[rr]; xs[rr] = xs2[rr]; ys[rr] = ys2[rr]; }
     }
     __shared__ double red[8];
 #pragma unroll
@@ -1105,8 +1131,8 @@ void launch_cam_prep(cudaStream_t st, int M, const double* cams, const double* K
     k_cam_prep<<<cdiv(M, 128), 128, 0, st>>>(M, cams, K, shared_K, f0, camd);
 }
 void launch_jacobian(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
-                     const double* X, int64_t N, const double* camd, double* J) {
-    if (O > 0) k_jacobian<<<cdiv(O, 256 * kObsRows), 256, 0, st>>>(O, obs_cam, obs_pt, x, y, X, N, camd, J);
+                     const double* X, int64_t N, const double* camd, double* J, double* Eacc) {
+    if (O > 0) k_jacobian<<<cdiv(O, 256 * kObsRows), 256, 0, st>>>(O, obs_cam, obs_pt, x, y, X, N, camd, J, Eacc);
 }
 void launch_frame_blocks(cudaStream_t st, int M, const int64_t* cam_begin, const int32_t* c_pt, const double* c_x, const double* c_y,
                          const double* X, int64_t N, const double* camd, double* G, double* gf, int splits) {

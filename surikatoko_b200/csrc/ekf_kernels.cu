@@ -802,9 +802,9 @@ __global__ void __launch_bounds__(256) k_ekf_grow(int n, int n2, int k, int s, c
                     v += w * jl[t];
                 }
             }
-            if (ll == kk) v += Q[((size_t)kk * s + a) * s + b];
-            Pnew[(size_t)c * n2 + r] = v;
-            Pnew[(size_t)r * n2 + c] = v;
+            // the reference assigns the auto-covariance block entry by entry as computed (:2386, :2394): Qnew is not symmetrised
+            Pnew[(size_t)c * n2 + r] = ll == kk ? v + Q[((size_t)kk * s + a) * s + b] : v;     // P(r, c)
+            Pnew[(size_t)r * n2 + c] = ll == kk ? v + Q[((size_t)kk * s + b) * s + a] : v;     // P(c, r)
         }
     }
 }

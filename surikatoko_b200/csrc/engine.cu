@@ -119,8 +119,10 @@ struct Engine {
     Buf obs_cam, obs_pt, obs_xy, ox, oy, pt_begin, cam_cnt, cam_cursor, cam_begin, c_pt, c_x, c_y;
     Buf chunk_cams, chunk_cnt, chunk_pts, obs_slot, obs_pos;
     Buf rows_F, rows_W, rows_D;   // dense-rows form of K2 (schur_dense_rows)
-    Buf k2_slot, k2_mask, k2_tab, k2_ntab, k2_gi, k2_u, k2_exc;   // K2 third form (schur_v3.cu): bind-time tile tables, per-attempt point factors, exception list
+    Buf k2_slot, k2_mask, k2_tab, k2_ntab, k2_gi, k2_u, k2_exc, k2_eacc;   // K2 third form (schur_v3.cu): bind-time tile tables, per-attempt point factors, exception list
     static constexpr int kExcCap = 16384;
+    bool k2_eacc_valid = false;   // K1 left the per-point sums of this outer iteration in k2_eacc
+    int k2_fuse_k1 = 1;           // SRK_K2_FUSE_K1=0: k_point_factor re-reads rho / Jp instead (cross-check)
     bool schur_dense_rows = false;
     Buf tacc;                 // K2' per-point accumulators [3N]; zero between attempts (k_backsub_finish re-zeroes what it reads)
     bool tacc_zero = false;
@@ -502,8 +504,16 @@ int derivative_pass(Engine& e) {
     cudaStream_t st = e.stream;
     {
         Scope s(e, F_JACOBIAN);
+        // K2's third form consumes per-point sums of Jp^T Jp / Jp^T rho: K1 has every term in registers and leaves them in k2_eacc
+        double* eacc = nullptr;
+        e.k2_eacc_valid = false;
+        if (e.schur_impl == 0 && e.k2_fuse_k1 && !e.schur_dense_rows && e.N > 0 && e.k2_eacc.ensure(sizeof(double) * 9 * (size_t)e.N) == cudaSuccess) {
+            eacc = e.k2_eacc.as<double>();
+            SRK_CUDA(cudaMemsetAsync(eacc, 0, sizeof(double) * 9 * (size_t)e.N, st));
+            e.k2_eacc_valid = true;
+        }
         srk::launch_jacobian(st, e.O, e.obs_cam.as<int32_t>(), e.obs_pt.as<int32_t>(), e.ox.as<double>(), e.oy.as<double>(), e.X_cur, e.N, e.camd_cur,
-                             e.J.as<double>());
+                             e.J.as<double>(), eacc);
         e.launches += e.O > 0 ? 1 : 0;
     }
     {
@@ -650,8 +660,12 @@ void schur_accumulate(Engine& e, const srk::SchurSink& sink, double c) {
         v3 = true;
         int* exc_count = e.k2_exc.as<int>(); int* exc_list = exc_count + 4;
         cudaMemsetAsync(exc_count, 0, sizeof(int), st);
-        srk::launch_point_factor(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.J.as<double>(), c, e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.k2_gi.as<double>(),
-                                 e.k2_u.as<double>(), exc_list, exc_count, Engine::kExcCap);
+        if (e.k2_eacc_valid)
+            srk::launch_point_finish(st, e.N, e.k2_eacc.as<double>(), c, e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.k2_gi.as<double>(), e.k2_u.as<double>(),
+                                     exc_list, exc_count, Engine::kExcCap);
+        else
+            srk::launch_point_factor(st, e.N, e.O, e.pt_begin.as<int64_t>(), e.J.as<double>(), c, e.pinv.as<double>(), e.skipped.as<unsigned char>(), e.k2_gi.as<double>(),
+                                     e.k2_u.as<double>(), exc_list, exc_count, Engine::kExcCap);
         srk::launch_schur_v3(st, e.N, e.O, e.schur_tile_points, e.pt_begin.as<int64_t>(), e.obs_pt.as<int32_t>(), e.J.as<double>(), sink, e.k2_gi.as<double>(),
                              e.k2_u.as<double>(), e.skipped.as<unsigned char>(), e.k2_tab.as<int>(), e.k2_ntab.as<int>(), e.k2_slot.as<unsigned char>(),
                              e.k2_mask.as<unsigned short>());
@@ -1018,6 +1032,7 @@ int srk_ba_create(void** h, const int* device_ids, int n_devices) {
     Engine* e = new Engine();
     e->device = dev;
     if (const char* v = std::getenv("SRK_SCHUR_IMPL")) { const int q = std::atoi(v); e->schur_impl = (q == 1 || q == 2) ? q : 0; }
+    if (const char* v = std::getenv("SRK_K2_FUSE_K1")) e->k2_fuse_k1 = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_TILE_EXCHANGE")) e->tile_exchange = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SOLVE_ORDER")) e->solve_order_enabled = std::atoi(v) != 0 ? 1 : 0;
     if (const char* v = std::getenv("SRK_SCHUR_ROWS")) e->schur_rows_enabled = std::atoi(v) != 0 ? 1 : 0;

@@ -8,7 +8,7 @@ namespace srk {
 
 void launch_cam_prep(cudaStream_t st, int M, const double* cams, const double* K, int shared_K, double f0, double* camd);
 void launch_jacobian(cudaStream_t st, int64_t O, const int32_t* obs_cam, const int32_t* obs_pt, const double* x, const double* y,
-                     const double* X, int64_t N, const double* camd, double* J);
+                     const double* X, int64_t N, const double* camd, double* J, double* Eacc = nullptr /* [9N], zero on entry: per-point sums of Jp^T Jp (6) and Jp^T rho (3) */);
 void launch_frame_blocks(cudaStream_t st, int M, const int64_t* cam_begin, const int32_t* c_pt, const double* c_x, const double* c_y,
                          const double* X, int64_t N, const double* camd, double* G, double* gf, int splits);
 // bind-time structure pass of K1' (per-chunk camera lists + per-observation slots), see k_chunk_tables
@@ -28,6 +28,9 @@ void launch_schur_list(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_
 // K2, third form (schur_v3.cu): per-point factor kernel + bind-time tile tables + single-operand DMMA tile kernel
 void launch_point_factor(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const double* J, double c, double* pinv, unsigned char* skipped,
                          double* gi, double* uvec, int* exc_list, int* exc_count, int exc_cap);
+// the same from the per-point sums K1 left in Eacc (launch_jacobian): one thread per point, no pass over the observations
+void launch_point_finish(cudaStream_t st, int64_t N, const double* Eacc, double c, double* pinv, unsigned char* skipped, double* gi, double* uvec, int* exc_list,
+                         int* exc_count, int exc_cap);
 void launch_schur_tables(cudaStream_t st, int64_t N, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, int* tile_tab, int* tile_n,
                          unsigned char* obs_slot, unsigned short* pt_mask, unsigned char* deferred);
 void launch_schur_v3(cudaStream_t st, int64_t N, int64_t O, int tile_points, const int64_t* pt_begin, const int32_t* obs_pt, const double* J,

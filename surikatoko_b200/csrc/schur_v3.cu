@@ -50,43 +50,10 @@ __device__ __forceinline__ void dmma884_v3(double& d0, double& d1, double a, dou
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// ---------------------------------------------------------------------------------------------------------------------------------
-// Per-point blocks of one attempt.  Half-warp per point (lanes over its observations, strided for long tracks).
-__global__ void __launch_bounds__(256) k_point_factor(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin, const double* __restrict__ J, double c,
-                                                      double* __restrict__ pinv, unsigned char* __restrict__ skipped, double* __restrict__ gi,
-                                                      double* __restrict__ uvec, int* __restrict__ exc_list, int* __restrict__ exc_count, int exc_cap) {
-    const int hl = threadIdx.x & 15;
-    const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4;
-    const bool valid = j < N;
-    int64_t kb = 0; int k = 0;
-    if (valid) { kb = pt_begin[j]; k = (int)(pt_begin[j + 1] - kb); }
-    double a9[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) a9[i] = 0.0;
-    for (int i = hl; i < k; i += 16) {
-        const int64_t o = kb + i;
-        const double rx = J[o], ry = J[O + o];
-        double jp[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) jp[q] = J[(int64_t)(2 + q) * O + o];
-        a9[0] += jp[0] * jp[0] + jp[1] * jp[1];
-        a9[1] += jp[0] * jp[2] + jp[1] * jp[3];
-        a9[2] += jp[0] * jp[4] + jp[1] * jp[5];
-        a9[3] += jp[2] * jp[2] + jp[3] * jp[3];
-        a9[4] += jp[2] * jp[4] + jp[3] * jp[5];
-        a9[5] += jp[4] * jp[4] + jp[5] * jp[5];
-        a9[6] += jp[0] * rx + jp[1] * ry;
-        a9[7] += jp[2] * rx + jp[3] * ry;
-        a9[8] += jp[4] * rx + jp[5] * ry;
-    }
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        double v = a9[i];
-#pragma unroll
-        for (int s2 = 8; s2 > 0; s2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s2);   // stays inside the half-warp
-        a9[i] = 2.0 * v;
-    }
-    if (!valid || hl != 0) return;
+// a9 = {E00, E01, E02, E11, E12, E22, g_p0, g_p1, g_p2} of point j -> pinv / skipped (K2'), Gi, u (tile kernel), exception list
+__device__ __forceinline__ void point_factor_store(int64_t j, int64_t N, const double* a9, double c, double* __restrict__ pinv, unsigned char* __restrict__ skipped,
+                                                   double* __restrict__ gi, double* __restrict__ uvec, int* __restrict__ exc_list, int* __restrict__ exc_count,
+                                                   int exc_cap) {
     double inv[6];
     const bool ok = point_block_inverse(a9, c, inv);
     skipped[j] = ok ? 0 : 1;
@@ -126,6 +93,58 @@ __global__ void __launch_bounds__(256) k_point_factor(int64_t N, int64_t O, cons
     for (int i = 0; i < 6; ++i) gi[(int64_t)i * N + j] = g[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) uvec[(int64_t)i * N + j] = u[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Per-point blocks of one attempt.  Half-warp per point (lanes over its observations, strided for long tracks).
+__global__ void __launch_bounds__(256) k_point_factor(int64_t N, int64_t O, const int64_t* __restrict__ pt_begin, const double* __restrict__ J, double c,
+                                                      double* __restrict__ pinv, unsigned char* __restrict__ skipped, double* __restrict__ gi,
+                                                      double* __restrict__ uvec, int* __restrict__ exc_list, int* __restrict__ exc_count, int exc_cap) {
+    const int hl = threadIdx.x & 15;
+    const int64_t j = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 4;
+    const bool valid = j < N;
+    int64_t kb = 0; int k = 0;
+    if (valid) { kb = pt_begin[j]; k = (int)(pt_begin[j + 1] - kb); }
+    double a9[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a9[i] = 0.0;
+    for (int i = hl; i < k; i += 16) {
+        const int64_t o = kb + i;
+        const double rx = J[o], ry = J[O + o];
+        double jp[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) jp[q] = J[(int64_t)(2 + q) * O + o];
+        a9[0] += jp[0] * jp[0] + jp[1] * jp[1];
+        a9[1] += jp[0] * jp[2] + jp[1] * jp[3];
+        a9[2] += jp[0] * jp[4] + jp[1] * jp[5];
+        a9[3] += jp[2] * jp[2] + jp[3] * jp[3];
+        a9[4] += jp[2] * jp[4] + jp[3] * jp[5];
+        a9[5] += jp[4] * jp[4] + jp[5] * jp[5];
+        a9[6] += jp[0] * rx + jp[1] * ry;
+        a9[7] += jp[2] * rx + jp[3] * ry;
+        a9[8] += jp[4] * rx + jp[5] * ry;
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        double v = a9[i];
+#pragma unroll
+        for (int s2 = 8; s2 > 0; s2 >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s2);   // stays inside the half-warp
+        a9[i] = 2.0 * v;
+    }
+    if (!valid || hl != 0) return;
+    point_factor_store(j, N, a9, c, pinv, skipped, gi, uvec, exc_list, exc_count, exc_cap);
+}
+
+// The same from the per-point sums K1 accumulated (k_jacobian, Eacc [9N]: sum Jp^T Jp (6), sum Jp^T rho (3)): one thread per point.
+__global__ void __launch_bounds__(256) k_point_finish(int64_t N, const double* __restrict__ Eacc, double c, double* __restrict__ pinv,
+                                                      unsigned char* __restrict__ skipped, double* __restrict__ gi, double* __restrict__ uvec,
+                                                      int* __restrict__ exc_list, int* __restrict__ exc_count, int exc_cap) {
+    const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (j >= N) return;
+    double a9[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a9[i] = 2.0 * Eacc[(int64_t)i * N + j];
+    point_factor_store(j, N, a9, c, pinv, skipped, gi, uvec, exc_list, exc_count, exc_cap);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
@@ -459,6 +478,12 @@ void launch_point_factor(cudaStream_t st, int64_t N, int64_t O, const int64_t* p
                          double* gi, double* uvec, int* exc_list, int* exc_count, int exc_cap) {
     if (N <= 0) return;
     k_point_factor<<<(unsigned)((N * 16 + 255) / 256), 256, 0, st>>>(N, O, pt_begin, J, c, pinv, skipped, gi, uvec, exc_list, exc_count, exc_cap);
+}
+
+void launch_point_finish(cudaStream_t st, int64_t N, const double* Eacc, double c, double* pinv, unsigned char* skipped, double* gi, double* uvec, int* exc_list,
+                         int* exc_count, int exc_cap) {
+    if (N <= 0) return;
+    k_point_finish<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(N, Eacc, c, pinv, skipped, gi, uvec, exc_list, exc_count, exc_cap);
 }
 
 void launch_schur_tables(cudaStream_t st, int64_t N, int tile_points, const int64_t* pt_begin, const int32_t* obs_cam, int* tile_tab, int* tile_n,

@@ -163,7 +163,8 @@ def test_covariance_growth_for_new_points_matches_oracle(oracle, s, k):
         n2 = ekf.add_points(xn, Jy, Q)
         assert n2 == fr["n"] + k * s
         P, x = ekf.get_state()
-        assert relerr(P, P_ref) < 1e-14 and np.array_equal(x, x_ref) and np.array_equal(P, P.T)
+        assert relerr(P, P_ref) < 1e-14 and np.array_equal(x, x_ref) and relerr(P, P.T) < 1e-15
+        assert np.array_equal(P[fr["n"]:, :fr["n"]], P[:fr["n"], fr["n"]:].T)
         assert np.array_equal(P[:fr["n"], :fr["n"]], fr["P"]), "the old block must be untouched"
         # one frame later: all points, old and new, observed
         off = np.concatenate([fr["pt_off"], fr["n"] + s * np.arange(k)])
