@@ -32,7 +32,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".inc"))]
     headers += [os.path.join(_HERE, "..", "include", "srk", f) for f in os.listdir(os.path.join(_HERE, "..", "include", "srk"))]
     objs = []
     procs = []

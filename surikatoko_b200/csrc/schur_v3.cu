@@ -21,6 +21,7 @@
 //     up to three batches ahead, so a slow batch (a DRAM round trip) no longer stalls the tensor pipe.
 // A point whose damped block passes the |det| rule but is not numerically positive definite (never for a sum of squares with damping
 // unless rounding dominates) has no real factor: it contributes through the exception list to the per-point kernel (two operands).
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -210,53 +211,14 @@ __global__ void __launch_bounds__(256) k_schur_tables(int64_t N, int tile_points
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------
-// One super-block (NI x NJ fragments of 8x8; DIAG: only the fragments on and below its diagonal) over one batch.
-template <int NI, int NJ, bool DIAG>
-__device__ __forceinline__ void v3_sb_batch(double (&acc)[3][3][2], const double* __restrict__ pa, const double* __restrict__ pb) {
-#pragma unroll 4
-    for (int ks = 0; ks < kV3K / 4; ++ks) {
-        const int off = ks * 4 * kV3SLD;
-        double af[NI], bf[NJ];
-#pragma unroll
-        for (int i = 0; i < NI; ++i) af[i] = pa[off + 8 * i];
-        if (DIAG) {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) bf[j] = af[j];
-        } else {
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) bf[j] = pb[off + 8 * j];
-        }
-#pragma unroll
-        for (int i = 0; i < NI; ++i)
-#pragma unroll
-            for (int jj = 0; jj < NJ; ++jj)
-                if (!DIAG || jj <= i) dmma884_v3(acc[i][jj][0], acc[i][jj][1], af[i], bf[jj]);
-    }
-}
-__device__ __forceinline__ void v3_sb_dispatch(int code, double (&acc)[3][3][2], const double* pa, const double* pb) {
-    switch (code) {
-        case 0: v3_sb_batch<1, 1, false>(acc, pa, pb); break;
-        case 1: v3_sb_batch<1, 2, false>(acc, pa, pb); break;
-        case 2: v3_sb_batch<1, 3, false>(acc, pa, pb); break;
-        case 3: v3_sb_batch<2, 1, false>(acc, pa, pb); break;
-        case 4: v3_sb_batch<2, 2, false>(acc, pa, pb); break;
-        case 5: v3_sb_batch<2, 3, false>(acc, pa, pb); break;
-        case 6: v3_sb_batch<3, 1, false>(acc, pa, pb); break;
-        case 7: v3_sb_batch<3, 2, false>(acc, pa, pb); break;
-        case 8: v3_sb_batch<3, 3, false>(acc, pa, pb); break;
-        case 9: v3_sb_batch<1, 1, true>(acc, pa, pb); break;
-        case 10: v3_sb_batch<2, 2, true>(acc, pa, pb); break;
-        case 11: v3_sb_batch<3, 3, true>(acc, pa, pb); break;
-        default: break;
-    }
-}
+#include "schur_v3_consume.inc"
 
 __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O, int tile_points, const int64_t* __restrict__ pt_begin,
                                                             const int32_t* __restrict__ obs_pt, const double* __restrict__ J, SchurSink sink,
                                                             const double* __restrict__ gi, const double* __restrict__ uvec,
                                                             const unsigned char* __restrict__ skipped, const int* __restrict__ tile_tab,
                                                             const int* __restrict__ tile_n, const unsigned char* __restrict__ obs_slot,
-                                                            const unsigned short* __restrict__ pt_mask) {
+                                                            const unsigned short* __restrict__ pt_mask, int dbg_mode) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     V3Smem& sm = *reinterpret_cast<V3Smem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -266,6 +228,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
     const int nbatch = (int)((p1 - p0 + kV3BP - 1) / kV3BP);
     const int nLocal = tile_n[blockIdx.x];
 
+    // dbg_mode (timing experiments only, results are garbage): 1 = consumers alone (no producers, no barriers), 2 = producers alone
+    if (dbg_mode == 1 && w >= 8) return;
+    if (dbg_mode == 2 && w < 8) return;
     if (w >= 8) {
         // ================= producers: one lane per observation of the batch
         // Every global address of a batch is known before the batch starts: the observation extents come one batch ahead, the per-point
@@ -279,7 +244,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
             const int64_t pb1 = min(p1, pb0 + kV3BP);
             int64_t ob_n = 0, oe_n = 0;
             if (b + 1 < nbatch) { ob_n = oe; oe_n = pt_begin[min(p1, pb0 + 2 * (int64_t)kV3BP)]; }
-            if (b >= kV3Stages) bar_sync_named(1 + kV3Stages + s, kV3Threads);     // empty[s]: the consumers are done with batch b - stages
+            if (b >= kV3Stages && dbg_mode == 0) bar_sync_named(1 + kV3Stages + s, kV3Threads);     // empty[s]: the consumers are done with batch b - stages
             double* Vs = sm.V[s];
             // ---- this lane's observation (first pass): loads in flight before anything is waited for
             int64_t o = ob + ptid;
@@ -356,51 +321,29 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
                     for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
                 }
             }
-            bar_arrive_named(1 + s, kV3Threads);                                   // full[s]
+            if (dbg_mode == 0) bar_arrive_named(1 + s, kV3Threads);                // full[s]
             ob = ob_n; oe = oe_n;
         }
         return;
     }
 
     // ================= consumers
+    // Fragment lists per (warp, R) and the straight-line DMMA code that walks them: schur_v3_consume.inc (tools/gen_schur_v3_consume.py).
+    // R = fragment rows of the tile's lower triangle; every warp walks both of its pieces in ONE k-loop (15 DMMAs back to back per k-step
+    // at R = 15, operand fragments loaded once per k-step); 30 fragments per SM sub-partition at R = 15, 28 / 28 / 28 / 21 + rhs at R = 14.
     const int g8 = lane >> 2, tg = lane & 3;
-    // super-block sb = I(I+1)/2 + Jc covers rows [24 I, 24 I + 24) x columns [24 Jc, 24 Jc + 24); a diagonal super-block computes the 6
-    // fragments on and below its diagonal; fragment rows / columns beyond the tile's last camera slot (10 * nLocal) are not computed.
-    // Dealing by SM sub-partition (warp w runs on sub-partition w % 4): with <= 11 cameras (14 fragment rows, 105 fragments) the pairs
-    // (w, w + 4) carry 15 + 12, 15 + 12, 15 + 12, 15 + 9 (+ the rhs GEMV on warp 7); with 12 cameras (120 fragments) 15 + 15, 15 + 18,
-    // 15 + 18, 15 + 9 (+ rhs).
-    int sbI[2] = {0, 0}, sbJ[2] = {0, 0}, code[2] = {-1, -1};
-    int nsb = 0;
-    {
-        constexpr int kSbOf[8][2] = {{1, 0}, {4, 2}, {6, 5}, {7, 9}, {3, 14}, {10, 11}, {12, 13}, {8, -1}};
-        const int lim = 10 * nLocal;
-        for (int q = 0; q < 2; ++q) {
-            const int sb = kSbOf[w][q];
-            if (sb < 0) break;
-            int I = 0;
-            while ((I + 1) * (I + 2) / 2 <= sb) ++I;
-            sbI[q] = I; sbJ[q] = sb - I * (I + 1) / 2;
-            nsb = q + 1;
-            int ni = (lim - 24 * sbI[q] + 7) / 8; ni = ni < 0 ? 0 : (ni > 3 ? 3 : ni);
-            int nj = (lim - 24 * sbJ[q] + 7) / 8; nj = nj < 0 ? 0 : (nj > 3 ? 3 : nj);
-            if (ni > 0 && nj > 0) code[q] = sbI[q] == sbJ[q] ? 9 + (ni - 1) : (ni - 1) * 3 + (nj - 1);
-        }
-    }
-    double acc[2][3][3][2];
+    int R = (10 * nLocal + 7) / 8;
+    R = R < 1 ? 1 : (R > 15 ? 15 : R);
+    double acc[15][2];
 #pragma unroll
-    for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) { acc[q][i][jj][0] = 0.0; acc[q][i][jj][1] = 0.0; }
+    for (int f = 0; f < 15; ++f) { acc[f][0] = 0.0; acc[f][1] = 0.0; }
     double racc[4] = {0.0, 0.0, 0.0, 0.0};   // warp 7: rhs entries m = lane + 32*q < 120
 
     for (int b = 0; b < nbatch; ++b) {
         const int s = b % kV3Stages;
-        bar_sync_named(1 + s, kV3Threads);                                         // full[s]
+        if (dbg_mode == 0) bar_sync_named(1 + s, kV3Threads);                      // full[s]
         const double* V = sm.V[s];
-        v3_sb_dispatch(code[0], acc[0], V + tg * kV3SLD + 24 * sbI[0] + g8, V + tg * kV3SLD + 24 * sbJ[0] + g8);
-        if (nsb > 1) v3_sb_dispatch(code[1], acc[1], V + tg * kV3SLD + 24 * sbI[1] + g8, V + tg * kV3SLD + 24 * sbJ[1] + g8);
+        v3_consume_generated(w, R, acc, V + tg * kV3SLD + g8);
         if (w == 7) {   // rhs += V^T u
             const double* U = sm.U[s];
 #pragma unroll
@@ -414,7 +357,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
                 }
             }
         }
-        if (b + kV3Stages < nbatch) bar_arrive_named(1 + kV3Stages + s, kV3Threads);   // empty[s]
+        if (b + kV3Stages < nbatch && dbg_mode == 0) bar_arrive_named(1 + kV3Stages + s, kV3Threads);   // empty[s]
     }
 
     // ---- flush: one red.global.add.f64 per touched entry per tile
@@ -432,32 +375,31 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
     }
     bar_sync_named(9, 256);
     const bool dense = sink.blocks == nullptr;
+    const int nfr = kV3NFrag[R - kV3GenRMin][w];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        if (q >= nsb) break;
+    for (int f = 0; f < 15; ++f) {
+        if (f >= nfr) break;
+        const int rc = kV3FragRC[R - kV3GenRMin][w][f];
+        const int row = 8 * (rc >> 4) + g8;
+        if (row >= kV3Rows) continue;
+        const int ri = sm.gidx[row], si = row / 10;
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int row = 24 * sbI[q] + 8 * i + g8;
-            const int ri = sm.gidx[row], si = row / 10;
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const double v = acc[q][i][jj][e];
-                    const int col = 24 * sbJ[q] + 8 * jj + 2 * tg + e;
-                    const int ci = sm.gidx[col], sl = col / 10;
-                    // lower block triangle; inside a diagonal block the lower triangle (row >= col) is computed once
-                    if (v == 0.0 || ri < 0 || ci < 0 || sl > si || (sl == si && col > row)) continue;
-                    if (dense) {
-                        atomicAdd(&sink.S[(size_t)ci * sink.ld + ri], -v);
-                    } else {
-                        const int blk = sm.blk[si * kV3Cams + sl];
-                        if (blk < 0) continue;
-                        const int a = row - 10 * si, bq = col - 10 * sl;
-                        atomicAdd(&sink.blocks[(size_t)blk * 100 + a * 10 + bq], -v);
-                        if (sl == si && a != bq) atomicAdd(&sink.blocks[(size_t)blk * 100 + bq * 10 + a], -v);   // stored diagonal blocks are full
-                    }
-                }
+        for (int e = 0; e < 2; ++e) {
+            const double v = acc[f][e];
+            const int col = 8 * (rc & 15) + 2 * tg + e;
+            if (col >= kV3Rows) continue;
+            const int ci = sm.gidx[col], sl = col / 10;
+            // lower block triangle; inside a diagonal block the lower triangle (row >= col) is computed once
+            if (v == 0.0 || ri < 0 || ci < 0 || sl > si || (sl == si && col > row)) continue;
+            if (dense) {
+                atomicAdd(&sink.S[(size_t)ci * sink.ld + ri], -v);
+            } else {
+                const int blk = sm.blk[si * kV3Cams + sl];
+                if (blk < 0) continue;
+                const int a = row - 10 * si, bq = col - 10 * sl;
+                atomicAdd(&sink.blocks[(size_t)blk * 100 + a * 10 + bq], -v);
+                if (sl == si && a != bq) atomicAdd(&sink.blocks[(size_t)blk * 100 + bq * 10 + a], -v);   // stored diagonal blocks are full
+            }
         }
     }
     if (w == 7) {
@@ -499,7 +441,9 @@ void launch_schur_v3(cudaStream_t st, int64_t N, int64_t O, int tile_points, con
     static PerDeviceOnce once;
     if (once.first()) cudaFuncSetAttribute(k_schur_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
     const unsigned grid = (unsigned)((N + tile_points - 1) / tile_points);
-    k_schur_v3<<<grid, kV3Threads, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask);
+    static int dbg_mode = -1;
+    if (dbg_mode < 0) { const char* e = getenv("SRK_V3_DEBUG"); dbg_mode = e != nullptr ? atoi(e) : 0; }
+    k_schur_v3<<<grid, kV3Threads, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
 }
 
 }  // namespace srk
