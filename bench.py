@@ -333,11 +333,11 @@ def measure_ba(args, name, steps, warmup, scaling="strong", full=True):
             barrier()
             weak = (w0.elapsed_time(w1), wsteps, float(wprob.n_obs))
 
-    t = torch.tensor([ms, ms_e2e, weak[0] if weak else 0.0], device=dev, dtype=torch.float64)
+    tmax = torch.tensor([ms, ms_e2e, weak[0] if weak else 0.0], device=dev, dtype=torch.float64)
     tot = torch.tensor([float(O), weak[2] if weak else 0.0, float(N)], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = float(t[0]), float(t[1]); total_obs = float(tot[0]); total_pts = float(tot[2])
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = float(tmax[0]), float(tmax[1]); total_obs = float(tot[0]); total_pts = float(tot[2])
     if rank != 0:
         eng.close()
         return None
@@ -459,7 +459,7 @@ def measure_ba(args, name, steps, warmup, scaling="strong", full=True):
     if parity is not None:
         out["multi_gpu_parity"] = parity
     if weak is not None:
-        wms = float(t[2]); wobs = float(tot[1])
+        wms = float(tmax[2]); wobs = float(tot[1])
         out["weak_scaling"] = {"value": wobs * weak[1] / (wms * 1e-3), "unit": UNIT, "ms_per_step": wms / weak[1], "steps": weak[1],
                                "per_rank": {"n_points": N_full, "n_obs": int(wobs / world)},
                                "note": "every rank its own %d points of the same %d-camera world; compare with the N=1 value of the strong line" % (N_full, M)}
