@@ -68,6 +68,13 @@ SRK_API int srk_ekf_ransac_consensus_resident(void* h, int64_t m, const double* 
                                               double meas_var, const srk_ekf_camera* camera, double max_divergence_pix, int32_t* support, int32_t* best,
                                               unsigned char* best_inliers);
 
+/* Projected 2-D covariance of every listed point at the resident state, J P_in J^T over the camera position / quaternion and the point's own
+ * variables (GetSalientPointProjected2DPosWithUncertainty, EKF.cpp:3901-4025; no measurement noise is added there).  cov [m][4] row-major,
+ * symmetrised like FixAlmostSymmetricMat.  The second stage of the 1-point RANSAC update (EKF.cpp:1466-1498) is this + a chi^2 test; the whole
+ * update -- consensus, stacked update of the low-innovation inliers, rescue, second stacked update -- is `surikatoko_b200/ekf.py::
+ * one_point_ransac_update` on top of the resident entry points (ProcessFrame_OnePointRansacUpdateCore :1393-1513 is host control flow). */
+SRK_API int srk_ekf_projected_covariances_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, double* cov);
+
 /* Covariance growth for k new salient points on the resident state: the dense part of AllocateAndInitStateForNewSalientPoint
  * (EKF.cpp:2322-2396; the reference calls conservativeResize -- a temporary and a full copy of P -- once per point):
  *     x <- [x ; x_new],   P[new_i, old] = Jy_i P[0:7, old],   P[new_i, new_l] = Jy_i P[0:7, 0:7] Jy_l^T (+ Qnew_i when i == l)

@@ -347,6 +347,19 @@ def ekf_ransac(P, x, Hcam, Hpt, pt_off, z, meas_var, cam9, max_divergence_pix):
     return int(best), support, inl
 
 
+def ekf_ransac_update(P, x, pt_off, s, z, meas_var, cam9, max_divergence_pix, chi2_thr=float(np.float32(9.21034))):
+    """ProcessFrame_OnePointRansacUpdateCore (EKF.cpp:1393-1513): (P_new, x_new, low mask, high mask)."""
+    Pn = np.asfortranarray(np.array(P, dtype=np.float64)); xn = np.array(x, dtype=np.float64)
+    off = np.ascontiguousarray(pt_off, dtype=np.int64); zz = np.ascontiguousarray(z, dtype=np.float64)
+    c9 = np.ascontiguousarray(cam9, dtype=np.float64)
+    m = off.shape[0]
+    low = np.zeros(m, dtype=np.uint8); high = np.zeros(m, dtype=np.uint8); counts = np.zeros(2, dtype=np.int64)
+    lib().srk_oracle_ekf_ransac_update(C.c_int64(xn.shape[0]), C.c_int64(m), Pn.ctypes.data_as(C.POINTER(C.c_double)), _p(xn, C.c_double), _p(off, C.c_int64),
+                                       C.c_int(s), _p(zz, C.c_double), C.c_double(meas_var), _p(c9, C.c_double), C.c_double(max_divergence_pix), C.c_double(chi2_thr),
+                                       _p(low, C.c_ubyte), _p(high, C.c_ubyte), _p(counts, C.c_int64))
+    return np.array(Pn), xn, low.astype(bool), high.astype(bool)
+
+
 def ekf_new_point(cam9, cam13, corner_pix, inv_dist, inv_dist_std, meas_std_pix):
     """GetNewSphericalSalientPointState + the small Jacobians of GetNewSphericalSalientPointCovar (EKF.cpp:2398-2527) and the XYZ conversion:
     dict(spher[6], Jy6[6,7], Q6[6,6], xyz[3], Jy3[3,7], Q3[3,3], xyz_ok)."""

@@ -12,6 +12,7 @@
 #include "srk_oracle_ekf_exact.hpp"
 #include "srk_oracle_ekf_ransac.hpp"
 #include "srk_oracle_ekf_newpoint.hpp"
+#include "srk_oracle_ekf_ransac_update.hpp"
 
 using namespace srk_oracle;
 
@@ -369,6 +370,18 @@ int srk_oracle_ekf_jacobians(int64_t n, int64_t m, const double* x, const int64_
     (void)n;
     EkfCamera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8] != 0.0 ? 1 : 0};
     for (int64_t i = 0; i < m; ++i) EkfMeasurementJacobian(cam, x, x + pt_off[i], s, Hcam + (size_t)(2 * i) * 13, Hpt + (size_t)(2 * i) * s, hd + 2 * i);
+    return 0;
+}
+// ProcessFrame_OnePointRansacUpdateCore (EKF.cpp:1393-1513) on copies: P [n x n] col-major and x [n] in / out, low[m] / high[m] masks, counts[2].
+int srk_oracle_ekf_ransac_update(int64_t n, int64_t m, double* P, double* x, const int64_t* pt_off, int s, const double* z, double meas_var, const double* cam9,
+                                 double max_divergence_pix, double chi2_thr, unsigned char* low, unsigned char* high, int64_t* counts) {
+    EkfCamera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8] != 0.0 ? 1 : 0};
+    EkfMat Pm((size_t)n, (size_t)n);
+    std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);
+    std::vector<double> xs(x, x + n);
+    EkfOnePointRansacUpdate(&xs, &Pm, m, pt_off, s, z, meas_var, cam, max_divergence_pix, chi2_thr, low, high, counts);
+    std::memcpy(P, Pm.d.data(), sizeof(double) * (size_t)n * (size_t)n);
+    std::memcpy(x, xs.data(), sizeof(double) * (size_t)n);
     return 0;
 }
 // State / small Jacobians of a new salient point (EKF.cpp:2398-2527).  out55x = spher[6], Jy6[42], Q6[36], xyz[3], Jy3[21], Q3[9] in that order; returns xyz_ok.

@@ -809,6 +809,64 @@ __global__ void __launch_bounds__(256) k_ekf_grow(int n, int n2, int k, int s, c
     }
 }
 
+// Projected 2-D covariance of every listed point at the resident state: covar2D = J P_in J^T with J = [d hd / d (camera position, quaternion)
+// | d hd / d point] and P_in the matching blocks of P (GetSalientPointProjected2DPosWithUncertainty, EKF.cpp:3901-4025, the batched form the
+// second stage of the 1-point RANSAC update needs, :1483).  One thread per point; cov [m][4] row-major, symmetrised as FixAlmostSymmetricMat does.
+template <int S>
+__global__ void __launch_bounds__(128) k_ekf_proj_cov(int m, int n, const double* __restrict__ P, const double* __restrict__ Hcam, const double* __restrict__ Hpt,
+                                                      const int64_t* __restrict__ off, double* __restrict__ cov) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    constexpr int D = 7 + S;
+    const size_t o = (size_t)off[i];
+    double J[2][D];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) J[k][c] = Hcam[(size_t)(2 * i + k) * kCam + c];
+#pragma unroll
+        for (int c = 0; c < S; ++c) J[k][7 + c] = Hpt[(size_t)(2 * i + k) * S + c];
+    }
+    double c2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for (int a = 0; a < D; ++a) {
+        const size_t ra = a < 7 ? (size_t)a : o + (size_t)(a - 7);
+        double t0 = 0.0, t1 = 0.0;      // (P_in J^T)[a][0..1]
+        for (int b = 0; b < D; ++b) {
+            const size_t cb = b < 7 ? (size_t)b : o + (size_t)(b - 7);
+            const double p = P[cb * (size_t)n + ra];
+            t0 += p * J[0][b]; t1 += p * J[1][b];
+        }
+        c2[0][0] += J[0][a] * t0; c2[0][1] += J[0][a] * t1; c2[1][0] += J[1][a] * t0; c2[1][1] += J[1][a] * t1;
+    }
+    const double offd = (c2[0][1] + c2[1][0]) / 2;
+    cov[4 * (size_t)i] = c2[0][0]; cov[4 * (size_t)i + 1] = offd; cov[4 * (size_t)i + 2] = offd; cov[4 * (size_t)i + 3] = c2[1][1];
+}
+
+int projected_covariances(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int s, double* cov) {
+    if (e.n <= 0) { g_ekf_error = "srk_ekf_projected_covariances_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
+    if (m <= 0 || Hcam == nullptr || Hpt == nullptr || pt_off == nullptr || cov == nullptr || (s != 3 && s != 6)) { g_ekf_error = "bad arguments (s must be 3 or 6)"; return SRK_E_INVALID_ARG; }
+    for (int64_t i = 0; i < m; ++i) if (pt_off[i] < kCam || pt_off[i] + s > e.n) { g_ekf_error = "salient point offset out of range"; return SRK_E_INVALID_ARG; }
+    EKF_CUDA(cudaSetDevice(e.device));
+    const int mi = (int)m, m2 = (int)(2 * m);
+    cudaStream_t st = e.st;
+    EKF_CUDA(e.Hcam.ensure(sizeof(double) * (size_t)m2 * kCam)); EKF_CUDA(e.Hpt.ensure(sizeof(double) * (size_t)m2 * s));
+    EKF_CUDA(e.off.ensure(sizeof(int64_t) * (size_t)m)); EKF_CUDA(e.small.ensure(sizeof(double) * (3 * kCam * kCam + kCam)));
+    EKF_CUDA(e.tmp.ensure(sizeof(double) * 4 * (size_t)(m > e.n ? m : e.n)));
+    EKF_CUDA(cudaMemcpyAsync(e.Hcam.p, Hcam, sizeof(double) * (size_t)m2 * kCam, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.Hpt.p, Hpt, sizeof(double) * (size_t)m2 * s, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.off.p, pt_off, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, st));
+    {
+        EScope sc(e, E_RANSAC);
+        if (s == 3) k_ekf_proj_cov<3><<<(mi + 127) / 128, 128, 0, st>>>(mi, (int)e.n, e.P.as<double>(), e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(), e.tmp.as<double>());
+        else k_ekf_proj_cov<6><<<(mi + 127) / 128, 128, 0, st>>>(mi, (int)e.n, e.P.as<double>(), e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(), e.tmp.as<double>());
+        e.launches += 1;
+    }
+    EKF_CUDA(cudaMemcpyAsync(cov, e.tmp.p, sizeof(double) * 4 * (size_t)m, cudaMemcpyDeviceToHost, st));
+    EKF_CUDA(cudaStreamSynchronize(st));
+    EKF_CUDA(cudaGetLastError());
+    return SRK_OK;
+}
+
 int add_points_resident(Ekf& e, int64_t k, int s, const double* x_new, const double* Jy, const double* Qnew, int diag_only) {
     if (e.n <= 0) { g_ekf_error = "srk_ekf_add_points_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
     if (k <= 0 || (s != 3 && s != 6) || x_new == nullptr || Jy == nullptr || Qnew == nullptr) { g_ekf_error = "bad add-points arguments (s must be 3 or 6)"; return SRK_E_INVALID_ARG; }
@@ -909,6 +967,10 @@ int srk_ekf_ransac_consensus_resident(void* h, int64_t m, const double* Hcam, co
 int srk_ekf_add_points_resident(void* h, int64_t k, int32_t s, const double* x_new, const double* Jy, const double* Qnew, int32_t diag_only) {
     if (h == nullptr) return SRK_E_INVALID_ARG;
     return add_points_resident(*(Ekf*)h, k, s, x_new, Jy, Qnew, diag_only);
+}
+int srk_ekf_projected_covariances_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, double* cov) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    return projected_covariances(*(Ekf*)h, m, Hcam, Hpt, pt_off, s, cov);
 }
 int srk_ekf_state_size(void* h, int64_t* n) {
     if (h == nullptr || n == nullptr) return SRK_E_INVALID_ARG;

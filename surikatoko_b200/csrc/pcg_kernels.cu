@@ -1,6 +1,8 @@
 // suriko-b200 — K3b: block-sparse reduced camera system + block-Jacobi PCG (see pcg.h).
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "kernels.h"
 #include "pcg.h"
 #include "prep.h"
@@ -276,6 +278,98 @@ __global__ void __launch_bounds__(kPcgThreads) k_pcg_direction(int M, int nparts
     }
 }
 
+// ---- the whole PCG loop as ONE persistent cooperative kernel (single GPU) ---------------------------------------------------------
+// The launch-per-phase form above spends most of an iteration between kernels: three dependent grid-wide launches of ~10 us of work each
+// (configs[4]: 57 us per iteration for a system that is L2 resident).  Here one co-resident grid walks the iterations itself with three
+// grid barriers per iteration; every CTA re-reduces the per-CTA partials in the same fixed order, so all CTAs see bit-identical scalars,
+// take the convergence decision in lock-step without a flag, and the iteration stays deterministic (for a given grid).  A warp owns
+// three cameras at a time (10 lanes each) in every phase; z = Minv r exchanges r through shuffles.
+// scal[0..3] = {rz, bb, rr, -} from k_pcg_init / k_pcg_init_scal; out[0] = iterations, out[1] = rr, out[2] = bb.
+constexpr int kPcgPersistThreads = 256;
+__global__ void __launch_bounds__(kPcgPersistThreads) k_pcg_persistent(int M, const int64_t* __restrict__ row_ptr, const int* __restrict__ row_ent,
+                                                                       const double* __restrict__ blocks, const double* __restrict__ Minv, double* __restrict__ x,
+                                                                       double* __restrict__ r, double* __restrict__ z, double* __restrict__ p, double* __restrict__ y,
+                                                                       double* __restrict__ part_dot, double* __restrict__ part_vec, const double* __restrict__ scal,
+                                                                       int max_iters, double tol2, double* __restrict__ out) {
+    namespace cgx = cooperative_groups;
+    cgx::grid_group grid = cgx::this_grid();
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, GW = (gridDim.x * blockDim.x) >> 5;
+    const int sub = lane / 10, a = lane - 10 * sub;
+    const int ntrip = (M + 2) / 3;
+    const int G = (int)gridDim.x;
+    double rz = scal[0];
+    const double bb = scal[1];
+    double rr = scal[2];
+    int it = 0;
+    if (!(bb > 0.0)) max_iters = 0;
+    for (; it < max_iters; ++it) {
+        // ---- y = S p, partial of p.y
+        double dot = 0.0;
+        for (int t = gw; t < ntrip; t += GW) {
+            const int cam = 3 * t + sub;
+            if (sub < 3 && cam < M) {
+                double acc = 0.0;
+                for (int64_t e = row_ptr[cam]; e < row_ptr[cam + 1]; ++e) {
+                    const int ent = row_ent[2 * e], col = row_ent[2 * e + 1];
+                    const double* B = blocks + (size_t)(ent & 0x3fffffff) * 100;
+                    const double* vc = p + (size_t)col * 10;
+                    if (ent & (1 << 30)) {
+#pragma unroll
+                        for (int b = 0; b < 10; ++b) acc += B[b * 10 + a] * vc[b];
+                    } else {
+#pragma unroll
+                        for (int b = 0; b < 10; ++b) acc += B[a * 10 + b] * vc[b];
+                    }
+                }
+                y[(size_t)cam * 10 + a] = acc;
+                dot += p[(size_t)cam * 10 + a] * acc;
+            }
+        }
+        dot = cta_sum_fixed(dot, red);
+        if (threadIdx.x == 0) part_dot[blockIdx.x] = dot;
+        grid.sync();
+        // ---- alpha; x += alpha p; r -= alpha y; z = Minv r; partials of r.z and r.r
+        const double pAp = reduce_partials(part_dot, G, 1, 0, red);
+        const double alpha = (pAp != 0.0) ? rz / pAp : 0.0;
+        double rzn = 0.0, rrn = 0.0;
+        for (int t = gw; t < ntrip; t += GW) {
+            const int cam = 3 * t + sub;
+            const bool in = sub < 3 && cam < M;
+            double ri = 0.0;
+            if (in) {
+                const size_t i = (size_t)cam * 10 + a;
+                x[i] += alpha * p[i];
+                ri = r[i] - alpha * y[i];
+                r[i] = ri;
+            }
+            double zi = 0.0;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                const double rk = __shfl_sync(0xffffffffu, ri, (sub < 3 ? sub : 0) * 10 + k);
+                if (in) zi += Minv[(size_t)cam * 100 + a * 10 + k] * rk;
+            }
+            if (in) { z[(size_t)cam * 10 + a] = zi; rzn += ri * zi; rrn += ri * ri; }
+        }
+        rzn = cta_sum_fixed(rzn, red); rrn = cta_sum_fixed(rrn, red);
+        if (threadIdx.x == 0) { part_vec[2 * blockIdx.x] = rzn; part_vec[2 * blockIdx.x + 1] = rrn; }
+        grid.sync();
+        // ---- beta; p = z + beta p; convergence (every CTA holds the same scalars)
+        const double rz_new = reduce_partials(part_vec, G, 2, 0, red);
+        rr = reduce_partials(part_vec, G, 2, 1, red);
+        const double beta = (rz != 0.0) ? rz_new / rz : 0.0;
+        for (int t = gw; t < ntrip; t += GW) {
+            const int cam = 3 * t + sub;
+            if (sub < 3 && cam < M) { const size_t i = (size_t)cam * 10 + a; p[i] = z[i] + beta * p[i]; }
+        }
+        rz = rz_new;
+        grid.sync();
+        if (!(rr == rr) || rr <= tol2 * bb) { ++it; break; }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out[0] = (double)it; out[1] = rr; out[2] = bb; }
+}
+
 // parity hook: scatter the block-sparse system into the dense gauge-reduced layout
 __global__ void k_bsr_to_dense(int nnzb, const int* __restrict__ blk_cams, const double* __restrict__ blocks, int unity, double* __restrict__ S, int64_t ld) {
     const int id = blockIdx.x, t = threadIdx.x;
@@ -374,7 +468,7 @@ int pcg_solve(PcgWorkspace& ws, cudaStream_t st, int M, double* x, int max_iters
     const int g_dot = 296;                                                 // CTAs of the separate dot product (multi-GPU)
     const int g_init = g_vec < 1184 ? g_vec : 1184;
     {
-        const size_t need = (size_t)(g_spmv > g_dot ? g_spmv : g_dot) + 3 * (size_t)g_vec + 2 * (size_t)g_init + 16;
+        const size_t need = (size_t)(g_spmv > g_dot ? g_spmv : g_dot) + 3 * (size_t)g_vec + 2 * (size_t)g_init + 16 + 3 * 1024 + 8;   // + the persistent kernel's per-CTA partials
         PCG_CUDA(ensure(ws.partials, ws.partials_cap, need));
     }
     double* part_dot = ws.partials;
@@ -387,6 +481,38 @@ int pcg_solve(PcgWorkspace& ws, cudaStream_t st, int M, double* x, int max_iters
     int it = 0;
     double rel = 1.0;
     const double tol2 = rel_tol * rel_tol;
+    static int persist = -1;   // SRK_PCG_PERSISTENT=0: the launch-per-phase loop on one GPU too (cross-check)
+    if (persist < 0) { const char* e = getenv("SRK_PCG_PERSISTENT"); persist = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    if (!multi && persist) {
+        int dev = 0, sms = 148, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pcg_persistent, kPcgPersistThreads, 0) == cudaSuccess && occ >= 1) {
+            const int per_sm = occ < 4 ? occ : 4;
+            int G = sms * per_sm;
+            if (G > 1024) G = 1024;
+            double* pd = ws.partials + (g_spmv > g_dot ? g_spmv : g_dot) + 3 * (size_t)g_vec + 2 * (size_t)g_init + 16;
+            double* pv = pd + G;
+            double* outp = ws.scal + 8;      // parity-1 slot of the scalar block: free on this path
+            int Mi = M, mi = max_iters; double t2 = tol2;
+            const int64_t* rp = ws.row_ptr; const int* re = ws.row_ent; const double* bl = ws.blocks; const double* mv = ws.diag; const double* sc = ws.scal;
+            double *xx = x, *rr_ = ws.r, *zz = ws.z, *pp = ws.p, *yy = ws.y;
+            void* args[] = {&Mi, &rp, &re, &bl, &mv, &xx, &rr_, &zz, &pp, &yy, &pd, &pv, &sc, &mi, &t2, &outp};
+            if (cudaLaunchCooperativeKernel((void*)k_pcg_persistent, dim3(G), dim3(kPcgPersistThreads), args, 0, st) == cudaSuccess) {
+                *launches += 1;
+                PCG_CUDA(cudaMemcpyAsync(ws.h_scal, outp, sizeof(double) * 3, cudaMemcpyDeviceToHost, st));
+                PCG_CUDA(cudaStreamSynchronize(st));
+                it = (int)ws.h_scal[0];
+                const double rrv = ws.h_scal[1], bbv = ws.h_scal[2];
+                rel = bbv > 0.0 ? sqrt(rrv / bbv) : 0.0;
+                *iters_out = it;
+                if (rel_res_out != nullptr) *rel_res_out = rel;
+                PCG_CUDA(cudaGetLastError());
+                return SRK_OK;
+            }
+            cudaGetLastError();   // cooperative launch refused: the loop below
+        }
+    }
     while (it < max_iters) {
         const int batch = (max_iters - it) < check_every ? (max_iters - it) : check_every;
         for (int k = 0; k < batch; ++k) {

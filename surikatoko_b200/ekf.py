@@ -28,6 +28,7 @@ def _lib():
                                                         C.c_void_p, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
         L.srk_ekf_measurement_jacobians_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.srk_ekf_add_points_resident.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        L.srk_ekf_projected_covariances_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.srk_ekf_state_size.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.srk_ekf_update.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_double]
@@ -56,6 +57,45 @@ class EkfCamera(C.Structure):
 
     def as_array(self):
         return np.array([self.fx_pix, self.fy_pix, self.cx, self.cy, self.dx_mm, self.dy_mm, self.k1, self.k2, float(self.enable_distortion)])
+
+
+CHI2_99_DOF2 = float(np.float32(9.21034))     # the reference's float literal (EKF.cpp:1495)
+
+
+def one_point_ransac_update(engine, pt_off, s, z, camera, meas_var, max_divergence_pix, chi2_thr=CHI2_99_DOF2):
+    """ProcessFrame_OnePointRansacUpdateCore (EKF.cpp:1393-1513), the update the shipped flagfile selects (--monoslam_update_impl=4), as host
+    control flow over the resident entry points.  Stage 1: measurement Jacobians at the predicted state, 1-point RANSAC consensus
+    (OnePointRansac_GetConsensusMatches :1271-1391), stacked update with the low-innovation inliers (:1445-1446).  Stage 2: every other
+    matched point whose corner lies inside the chi^2 ellipse of its projection under the UPDATED state (:1466-1498) is rescued and enters a
+    second stacked update (:1507-1508).  Returns (low mask, high mask)."""
+    off = np.ascontiguousarray(pt_off, dtype=np.int64); z = np.ascontiguousarray(z, dtype=np.float64)
+    m = off.shape[0]
+    rows = lambda mask: np.repeat(mask, 2)
+    Hc, Hp, hp = engine.measurement_jacobians(off, s, camera)
+    best, _, inl = engine.ransac_consensus(Hc, Hp, off, z, meas_var, camera, max_divergence_pix)
+    low = inl.astype(bool) if best >= 0 else np.zeros(m, dtype=bool)
+    high = np.zeros(m, dtype=bool)
+    if low.any():
+        engine.update(Hc[rows(low)], Hp[rows(low)], off[low], z[rows(low)], hp[rows(low)], meas_var)
+    rest = np.flatnonzero(~low)
+    if rest.size == 0:
+        return low, high
+    Hc2, Hp2, hp2 = engine.measurement_jacobians(off[rest], s, camera)
+    cov = engine.projected_covariances(Hc2, Hp2, off[rest])
+    d = (z.reshape(-1, 2)[rest] - hp2.reshape(-1, 2))
+    tr = cov[:, 0, 0] + cov[:, 1, 1]; df = cov[:, 0, 0] - cov[:, 1, 1]
+    lo = tr / 2 - np.sqrt(df * df / 4 + cov[:, 0, 1] * cov[:, 0, 1])
+    ellipse_ok = ~((lo < 0) & ~(np.abs(0.0 - lo) <= (1.0e-8 + 1.0e-5 * np.abs(np.maximum(0.0, lo)))))     # CheckEllipseIsExtractableFrom2DCovarMat
+    det = cov[:, 0, 0] * cov[:, 1, 1] - cov[:, 0, 1] * cov[:, 1, 0]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        i00, i01, i10, i11 = cov[:, 1, 1] / det, -cov[:, 0, 1] / det, -cov[:, 1, 0] / det, cov[:, 0, 0] / det
+        dist = d[:, 0] * (i00 * d[:, 0] + i01 * d[:, 1]) + d[:, 1] * (i10 * d[:, 0] + i11 * d[:, 1])
+    take = ellipse_ok & (dist < chi2_thr)
+    high[rest[take]] = True
+    if take.any():
+        t2 = rows(take)
+        engine.update(Hc2[t2], Hp2[t2], off[rest[take]], z[rows(high)], hp2[t2], meas_var)
+    return low, high
 
 
 def new_salient_point(cam13, corner_pix, camera, inv_dist, inv_dist_std, meas_std_pix, s=3):
@@ -165,6 +205,14 @@ class EkfEngine:
         _chk(self._L.srk_ekf_state_size(self._h, C.byref(n)))
         self.n = n.value
         return self.n
+
+    def projected_covariances(self, Hcam, Hpt, pt_off):
+        """J P_in J^T per listed point at the resident state (GetSalientPointProjected2DPosWithUncertainty, EKF.cpp:3901-4025): [m, 2, 2]."""
+        Hc = np.ascontiguousarray(Hcam, dtype=np.float64); Hp = np.ascontiguousarray(Hpt, dtype=np.float64)
+        off = np.ascontiguousarray(pt_off, dtype=np.int64)
+        cov = np.zeros((off.shape[0], 2, 2))
+        _chk(self._L.srk_ekf_projected_covariances_resident(self._h, off.shape[0], _p(Hc), _p(Hp), _p(off), Hp.shape[1], _p(cov)))
+        return cov
 
     def measurement_jacobians(self, pt_off, s, camera):
         """Deriv_hd_by_cam_state_and_sal_pnt for every listed point at the resident state (EKF.cpp:3067-3159): (Hcam, Hpt, h_pred)."""

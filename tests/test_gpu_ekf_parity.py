@@ -183,3 +183,24 @@ def test_covariance_growth_for_new_points_matches_oracle(oracle, s, k):
         assert np.array_equal(Pd, Pd_ref)
     finally:
         ekf.close()
+
+
+@pytest.mark.parametrize("s,npts", [(3, 80), (6, 50), (3, 300)])
+def test_two_stage_one_point_ransac_update_matches_oracle(oracle, s, npts):
+    """ProcessFrame_OnePointRansacUpdateCore (EKF.cpp:1393-1513), the update of the shipped flagfile (impl 4): consensus -> stacked update of the
+    low-innovation inliers -> chi^2 rescue under the updated state (batched projected covariances on the device) -> second stacked update.
+    Both masks are integers and must agree exactly; the final state within the EKF tolerance."""
+    from surikatoko_b200.ekf import EkfEngine, one_point_ransac_update, synthetic_ransac_frame
+    fr = synthetic_ransac_frame(npts, s, seed=31 + npts, outlier_frac=0.25, pix_sigma=0.3)
+    P_ref, x_ref, low_ref, high_ref = oracle.ekf_ransac_update(fr["P"], fr["x"], fr["pt_off"], s, fr["z"], fr["meas_var"], fr["camera"].as_array(), 0.6)
+    ekf = EkfEngine(0)
+    try:
+        ekf.set_state(fr["P"], fr["x"])
+        low, high = one_point_ransac_update(ekf, fr["pt_off"], s, fr["z"], fr["camera"], fr["meas_var"], 0.6)
+        P, x = ekf.get_state()
+    finally:
+        ekf.close()
+    print("RANSAC update: %d matched, %d low-innovation inliers, %d rescued, %d spurious" % (npts, low.sum(), high.sum(), npts - low.sum() - high.sum()))
+    assert np.array_equal(low, low_ref) and np.array_equal(high, high_ref)
+    assert low.sum() > 0 and (low | high).sum() < npts, "the frame must exercise both stages and leave spurious matches out"
+    assert relerr(x, x_ref) < TOL and relerr(P, P_ref) < TOL
