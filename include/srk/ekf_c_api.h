@@ -75,6 +75,13 @@ SRK_API int srk_ekf_ransac_consensus_resident(void* h, int64_t m, const double* 
  * one_point_ransac_update` on top of the resident entry points (ProcessFrame_OnePointRansacUpdateCore :1393-1513 is host control flow). */
 SRK_API int srk_ekf_projected_covariances_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, double* cov);
 
+/* The per-observation update variants on the resident state: ProcessFrame_OneObservationPerUpdate (EKF.cpp:1153-1269; per_component = 0) and
+ * ProcessFrame_OneComponentOfOneObservationPerUpdate (:1525-1650; per_component = 1).  The measurement Jacobian of every point is re-derived on
+ * the device at the latest state, so the call is a dependent chain of m (2m) rank-2 (rank-1) updates of the whole covariance: 16 n^2 bytes of
+ * HBM traffic each -- use the stacked update for throughput; this is the reference's alternative semantics (relinearisation per observation). */
+SRK_API int srk_ekf_sequential_update_resident(void* h, int64_t m, const int64_t* pt_off, int32_t s, const double* z, const srk_ekf_camera* camera, double meas_var,
+                                               int32_t per_component);
+
 /* Covariance growth for k new salient points on the resident state: the dense part of AllocateAndInitStateForNewSalientPoint
  * (EKF.cpp:2322-2396; the reference calls conservativeResize -- a temporary and a full copy of P -- once per point):
  *     x <- [x ; x_new],   P[new_i, old] = Jy_i P[0:7, old],   P[new_i, new_l] = Jy_i P[0:7, 0:7] Jy_l^T (+ Qnew_i when i == l)

@@ -347,6 +347,15 @@ def ekf_ransac(P, x, Hcam, Hpt, pt_off, z, meas_var, cam9, max_divergence_pix):
     return int(best), support, inl
 
 
+def ekf_sequential_update(P, x, pt_off, s, z, meas_var, cam9, per_component=False):
+    """ProcessFrame_OneObservationPerUpdate (EKF.cpp:1153-1269) or, per_component, ...OneComponentOfOneObservationPerUpdate (:1525-1650)."""
+    Pn = np.asfortranarray(np.array(P, dtype=np.float64)); xn = np.array(x, dtype=np.float64)
+    off = np.ascontiguousarray(pt_off, dtype=np.int64); zz = np.ascontiguousarray(z, dtype=np.float64); c9 = np.ascontiguousarray(cam9, dtype=np.float64)
+    lib().srk_oracle_ekf_sequential_update(C.c_int64(xn.shape[0]), C.c_int64(off.shape[0]), Pn.ctypes.data_as(C.POINTER(C.c_double)), _p(xn, C.c_double),
+                                           _p(off, C.c_int64), C.c_int(s), _p(zz, C.c_double), C.c_double(meas_var), _p(c9, C.c_double), C.c_int(1 if per_component else 0))
+    return np.array(Pn), xn
+
+
 def ekf_ransac_update(P, x, pt_off, s, z, meas_var, cam9, max_divergence_pix, chi2_thr=float(np.float32(9.21034))):
     """ProcessFrame_OnePointRansacUpdateCore (EKF.cpp:1393-1513): (P_new, x_new, low mask, high mask)."""
     Pn = np.asfortranarray(np.array(P, dtype=np.float64)); xn = np.array(x, dtype=np.float64)

@@ -13,6 +13,7 @@
 #include "srk_oracle_ekf_ransac.hpp"
 #include "srk_oracle_ekf_newpoint.hpp"
 #include "srk_oracle_ekf_ransac_update.hpp"
+#include "srk_oracle_ekf_sequential.hpp"
 
 using namespace srk_oracle;
 
@@ -370,6 +371,18 @@ int srk_oracle_ekf_jacobians(int64_t n, int64_t m, const double* x, const int64_
     (void)n;
     EkfCamera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8] != 0.0 ? 1 : 0};
     for (int64_t i = 0; i < m; ++i) EkfMeasurementJacobian(cam, x, x + pt_off[i], s, Hcam + (size_t)(2 * i) * 13, Hpt + (size_t)(2 * i) * s, hd + 2 * i);
+    return 0;
+}
+// ProcessFrame_OneObservationPerUpdate (EKF.cpp:1153-1269) / ...OneComponentOfOneObservationPerUpdate (:1525-1650) on copies.
+int srk_oracle_ekf_sequential_update(int64_t n, int64_t m, double* P, double* x, const int64_t* pt_off, int s, const double* z, double meas_var, const double* cam9,
+                                     int per_component) {
+    EkfCamera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8] != 0.0 ? 1 : 0};
+    EkfMat Pm((size_t)n, (size_t)n);
+    std::memcpy(Pm.d.data(), P, sizeof(double) * (size_t)n * (size_t)n);
+    std::vector<double> xs(x, x + n);
+    EkfSequentialUpdate(&xs, &Pm, m, pt_off, s, z, meas_var, cam, per_component != 0);
+    std::memcpy(P, Pm.d.data(), sizeof(double) * (size_t)n * (size_t)n);
+    std::memcpy(x, xs.data(), sizeof(double) * (size_t)n);
     return 0;
 }
 // ProcessFrame_OnePointRansacUpdateCore (EKF.cpp:1393-1513) on copies: P [n x n] col-major and x [n] in / out, low[m] / high[m] masks, counts[2].

@@ -524,6 +524,7 @@ struct Ekf {
     int64_t n = 0;
     DBuf P, x, PHt, S, ws, w, Hcam, Hpt, off, z, h, aux, tmp, neg, info, small;
     DBuf r_hyp, r_support, r_bits;   // 1-point RANSAC scoring: per-hypothesis vectors, support counts, inlier bit rows
+    DBuf seq;                        // per-observation update: Jacobian of the point, K, K S
     DBuf Pgrow, xgrow, grow_in;      // covariance growth for new salient points: the grown copies (swapped in) and the small Jacobians
     int64_t launches = 0;
     bool timing = false;
@@ -867,6 +868,113 @@ int projected_covariances(Ekf& e, int64_t m, const double* Hcam, const double* H
     return SRK_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Per-observation update variants: ProcessFrame_OneObservationPerUpdate (EKF.cpp:1153-1269; 2x2 innovation per observed point) and
+// ProcessFrame_OneComponentOfOneObservationPerUpdate (:1525-1650; scalar innovation per pixel component).  Every update re-derives the
+// measurement Jacobian at the LATEST state, so the m (or 2m) updates form a dependent chain of rank-2 (rank-1) updates of the whole P:
+// per update one launch for the Jacobian of the point, one for the innovation covariance + gain + state, one for P -= (K S) K^T (the HBM-bound
+// one: 16 n^2 bytes), three for the quaternion normalisation.  FixSymmetricMat (:4308) is folded into the covariance kernel: the entry written
+// is P(r, c) - (KS_r . K_c + KS_c . K_r) / 2.
+// scratch (doubles): [0..25] Hx, [26..37] Hy, [38..39] hd  (written by k_ekf_jacobians with m = 1), then K [2n], KS [2n].
+template <int S>
+__global__ void __launch_bounds__(256) k_ekf_seq_gain(int n, const double* __restrict__ P, const double* __restrict__ jac, int64_t off, const double* __restrict__ z2,
+                                                      double meas_var, int comp /* -1: both components, 0 / 1: one */, double* __restrict__ x,
+                                                      double* __restrict__ K, double* __restrict__ KS) {
+    __shared__ double sH[2][kCam + S];
+    __shared__ double sS[2][2], sSi[2][2], sDelta[2];
+    const int tid = threadIdx.x;
+    const int k0 = comp < 0 ? 0 : comp, d = comp < 0 ? 2 : 1;
+    if (tid < 2 * (kCam + S)) {
+        const int k = tid / (kCam + S), c = tid - k * (kCam + S);
+        sH[k][c] = c < kCam ? jac[k * kCam + c] : jac[26 + k * S + (c - kCam)];
+    }
+    __syncthreads();
+    if (tid < d * d) {   // S = H P_in H^T + R over the camera (13) and the point (S) variables (:1208-1216, :1591-1597)
+        const int a = k0 + tid / d, b = k0 + tid % d;
+        double acc = 0.0;
+        for (int i = 0; i < kCam + S; ++i) {
+            const size_t ri = i < kCam ? (size_t)i : (size_t)off + (size_t)(i - kCam);
+            double t = 0.0;
+            for (int j = 0; j < kCam + S; ++j) {
+                const size_t cj = j < kCam ? (size_t)j : (size_t)off + (size_t)(j - kCam);
+                t += P[cj * (size_t)n + ri] * sH[b][j];
+            }
+            acc += sH[a][i] * t;
+        }
+        sS[tid / d][tid % d] = acc + (a == b ? meas_var : 0.0);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (d == 2) { const double det = sS[0][0] * sS[1][1] - sS[0][1] * sS[1][0]; sSi[0][0] = sS[1][1] / det; sSi[0][1] = -sS[0][1] / det; sSi[1][0] = -sS[1][0] / det; sSi[1][1] = sS[0][0] / det; }
+        else { sSi[0][0] = 1.0 / sS[0][0]; sSi[0][1] = sSi[1][0] = sSi[1][1] = 0.0; sS[0][1] = sS[1][0] = sS[1][1] = 0.0; }
+        for (int a = 0; a < 2; ++a) sDelta[a] = a < d ? z2[k0 + a] - jac[38 + k0 + a] : 0.0;
+    }
+    __syncthreads();
+    const int r = blockIdx.x * blockDim.x + tid;
+    if (r >= n) return;
+    double ph[2] = {0.0, 0.0};
+    for (int a = 0; a < d; ++a) {
+        double v = 0.0;
+#pragma unroll
+        for (int c = 0; c < kCam; ++c) v += P[(size_t)c * n + r] * sH[k0 + a][c];
+#pragma unroll
+        for (int c = 0; c < S; ++c) v += P[((size_t)off + c) * n + r] * sH[k0 + a][kCam + c];
+        ph[a] = v;
+    }
+    double kk[2] = {0.0, 0.0}, ks[2] = {0.0, 0.0};
+    for (int a = 0; a < d; ++a) kk[a] = ph[0] * sSi[0][a] + (d == 2 ? ph[1] * sSi[1][a] : 0.0);
+    for (int a = 0; a < d; ++a) ks[a] = kk[0] * sS[0][a] + (d == 2 ? kk[1] * sS[1][a] : 0.0);
+    x[r] += kk[0] * sDelta[0] + kk[1] * sDelta[1];
+    K[2 * (size_t)r] = kk[0]; K[2 * (size_t)r + 1] = kk[1];
+    KS[2 * (size_t)r] = ks[0]; KS[2 * (size_t)r + 1] = ks[1];
+}
+__global__ void __launch_bounds__(256) k_ekf_seq_cov(int n, double* __restrict__ P, const double* __restrict__ K, const double* __restrict__ KS) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+    if (r >= n) return;
+    const double kr0 = K[2 * (size_t)r], kr1 = K[2 * (size_t)r + 1], sr0 = KS[2 * (size_t)r], sr1 = KS[2 * (size_t)r + 1];
+    const double kc0 = K[2 * (size_t)c], kc1 = K[2 * (size_t)c + 1], sc0 = KS[2 * (size_t)c], sc1 = KS[2 * (size_t)c + 1];
+    // P is symmetric on entry: (P - D) symmetrised = P - (D + D^T) / 2 with D(r, c) = KS_r . K_c
+    P[(size_t)c * n + r] -= 0.5 * ((sr0 * kc0 + sr1 * kc1) + (sc0 * kr0 + sc1 * kr1));
+}
+
+int sequential_update(Ekf& e, int64_t m, const int64_t* pt_off, int s, const double* z, const srk_ekf_camera* cp, double meas_var, int per_component) {
+    if (e.n <= 0) { g_ekf_error = "srk_ekf_sequential_update_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
+    if (m <= 0 || pt_off == nullptr || z == nullptr || cp == nullptr || (s != 3 && s != 6)) { g_ekf_error = "bad arguments (s must be 3 or 6)"; return SRK_E_INVALID_ARG; }
+    for (int64_t i = 0; i < m; ++i) if (pt_off[i] < kCam || pt_off[i] + s > e.n) { g_ekf_error = "salient point offset out of range"; return SRK_E_INVALID_ARG; }
+    EKF_CUDA(cudaSetDevice(e.device));
+    const int n = (int)e.n;
+    cudaStream_t st = e.st;
+    EKF_CUDA(e.off.ensure(sizeof(int64_t) * (size_t)m)); EKF_CUDA(e.z.ensure(sizeof(double) * 2 * (size_t)m));
+    EKF_CUDA(e.seq.ensure(sizeof(double) * (64 + 4 * (size_t)n)));
+    EKF_CUDA(e.aux.ensure(sizeof(double) * 32)); EKF_CUDA(e.tmp.ensure(sizeof(double) * 4 * (size_t)n));
+    EKF_CUDA(cudaMemcpyAsync(e.off.p, pt_off, sizeof(int64_t) * (size_t)m, cudaMemcpyHostToDevice, st));
+    EKF_CUDA(cudaMemcpyAsync(e.z.p, z, sizeof(double) * 2 * (size_t)m, cudaMemcpyHostToDevice, st));
+    EkfCam cam{cp->fx_pix, cp->fy_pix, cp->cx, cp->cy, cp->dx_mm, cp->dy_mm, cp->k1, cp->k2, cp->enable_distortion != 0 ? 1 : 0};
+    double* jac = e.seq.as<double>(); double* K = jac + 64; double* KS = K + 2 * (size_t)n;
+    EScope sc(e, E_STATE);
+    for (int64_t i = 0; i < m; ++i) {
+        const int passes = per_component ? 2 : 1;
+        for (int pass = 0; pass < passes; ++pass) {
+            const int comp = per_component ? pass : -1;
+            if (s == 3) {
+                k_ekf_jacobians<3><<<1, 128, 0, st>>>(1, e.x.as<double>(), e.off.as<int64_t>() + i, cam, jac, jac + 26, jac + 38);
+                k_ekf_seq_gain<3><<<(n + 255) / 256, 256, 0, st>>>(n, e.P.as<double>(), jac, pt_off[i], e.z.as<double>() + 2 * i, meas_var, comp, e.x.as<double>(), K, KS);
+            } else {
+                k_ekf_jacobians<6><<<1, 128, 0, st>>>(1, e.x.as<double>(), e.off.as<int64_t>() + i, cam, jac, jac + 26, jac + 38);
+                k_ekf_seq_gain<6><<<(n + 255) / 256, 256, 0, st>>>(n, e.P.as<double>(), jac, pt_off[i], e.z.as<double>() + 2 * i, meas_var, comp, e.x.as<double>(), K, KS);
+            }
+            k_ekf_seq_cov<<<dim3((n + 255) / 256, n), 256, 0, st>>>(n, e.P.as<double>(), K, KS);
+            k_ekf_quat_prepare<<<1, 32, 0, st>>>(e.x.as<double>(), e.aux.as<double>());
+            k_ekf_quat_columns<<<(n + 255) / 256, 256, 0, st>>>(n, e.P.as<double>(), e.aux.as<double>(), e.tmp.as<double>());
+            k_ekf_quat_write<<<(n + 255) / 256, 256, 0, st>>>(n, e.P.as<double>(), e.aux.as<double>(), e.tmp.as<double>());
+            e.launches += 6;
+        }
+    }
+    EKF_CUDA(cudaStreamSynchronize(st));
+    EKF_CUDA(cudaGetLastError());
+    return SRK_OK;
+}
+
 int add_points_resident(Ekf& e, int64_t k, int s, const double* x_new, const double* Jy, const double* Qnew, int diag_only) {
     if (e.n <= 0) { g_ekf_error = "srk_ekf_add_points_resident before srk_ekf_set_state"; return SRK_E_NOT_BOUND; }
     if (k <= 0 || (s != 3 && s != 6) || x_new == nullptr || Jy == nullptr || Qnew == nullptr) { g_ekf_error = "bad add-points arguments (s must be 3 or 6)"; return SRK_E_INVALID_ARG; }
@@ -971,6 +1079,11 @@ int srk_ekf_add_points_resident(void* h, int64_t k, int32_t s, const double* x_n
 int srk_ekf_projected_covariances_resident(void* h, int64_t m, const double* Hcam, const double* Hpt, const int64_t* pt_off, int32_t s, double* cov) {
     if (h == nullptr) return SRK_E_INVALID_ARG;
     return projected_covariances(*(Ekf*)h, m, Hcam, Hpt, pt_off, s, cov);
+}
+int srk_ekf_sequential_update_resident(void* h, int64_t m, const int64_t* pt_off, int32_t s, const double* z, const srk_ekf_camera* camera, double meas_var,
+                                       int32_t per_component) {
+    if (h == nullptr) return SRK_E_INVALID_ARG;
+    return sequential_update(*(Ekf*)h, m, pt_off, s, z, camera, meas_var, per_component);
 }
 int srk_ekf_state_size(void* h, int64_t* n) {
     if (h == nullptr || n == nullptr) return SRK_E_INVALID_ARG;

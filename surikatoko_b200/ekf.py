@@ -29,6 +29,7 @@ def _lib():
         L.srk_ekf_measurement_jacobians_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.srk_ekf_add_points_resident.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         L.srk_ekf_projected_covariances_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.srk_ekf_sequential_update_resident.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double, C.c_int32]
         L.srk_ekf_state_size.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.srk_ekf_update.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                      C.c_void_p, C.c_double]
@@ -205,6 +206,11 @@ class EkfEngine:
         _chk(self._L.srk_ekf_state_size(self._h, C.byref(n)))
         self.n = n.value
         return self.n
+
+    def sequential_update(self, pt_off, s, z, camera, meas_var, per_component=False):
+        """ProcessFrame_OneObservationPerUpdate (EKF.cpp:1153-1269) / per_component: ...OneComponentOfOneObservationPerUpdate (:1525-1650)."""
+        off = np.ascontiguousarray(pt_off, dtype=np.int64); zz = np.ascontiguousarray(z, dtype=np.float64)
+        _chk(self._L.srk_ekf_sequential_update_resident(self._h, off.shape[0], _p(off), s, _p(zz), C.addressof(camera), float(meas_var), 1 if per_component else 0))
 
     def projected_covariances(self, Hcam, Hpt, pt_off):
         """J P_in J^T per listed point at the resident state (GetSalientPointProjected2DPosWithUncertainty, EKF.cpp:3901-4025): [m, 2, 2]."""

@@ -204,3 +204,24 @@ def test_two_stage_one_point_ransac_update_matches_oracle(oracle, s, npts):
     assert np.array_equal(low, low_ref) and np.array_equal(high, high_ref)
     assert low.sum() > 0 and (low | high).sum() < npts, "the frame must exercise both stages and leave spurious matches out"
     assert relerr(x, x_ref) < TOL and relerr(P, P_ref) < TOL
+
+
+@pytest.mark.parametrize("s,per_component", [(3, False), (3, True), (6, False), (6, True)])
+def test_per_observation_update_variants_match_oracle(oracle, s, per_component):
+    """ProcessFrame_OneObservationPerUpdate (EKF.cpp:1153-1269) and ...OneComponentOfOneObservationPerUpdate (:1525-1650): a dependent chain of
+    rank-2 / rank-1 updates with the Jacobian re-derived on the device at the latest state, against the oracle's restatement."""
+    from surikatoko_b200.ekf import EkfEngine, synthetic_ransac_frame
+    fr = synthetic_ransac_frame(36, s, seed=17, outlier_frac=0.0, pix_sigma=0.3)
+    P_ref, x_ref = oracle.ekf_sequential_update(fr["P"], fr["x"], fr["pt_off"], s, fr["z"], fr["meas_var"], fr["camera"].as_array(), per_component=per_component)
+    ekf = EkfEngine(0)
+    try:
+        ekf.set_state(fr["P"], fr["x"])
+        ekf.sequential_update(fr["pt_off"], s, fr["z"], fr["camera"], fr["meas_var"], per_component=per_component)
+        P, x = ekf.get_state()
+    finally:
+        ekf.close()
+    dx, dP = relerr(x, x_ref), relerr(P, P_ref)
+    print("PARITY ekf sequential (s=%d, per_component=%s): state %.2e covariance %.2e" % (s, per_component, dx, dP))
+    assert dx < TOL and dP < TOL
+    assert relerr(P, P.T) < 1e-15
+    assert relerr(x, fr["x"]) > 1e-6, "the update must move the state"
