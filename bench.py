@@ -532,12 +532,17 @@ def run_ours(args):
             except Exception as ex:  # pragma: no cover
                 others[oname] = {"error": repr(ex)}
         try:
-            o = measure_ekf(args, 5, 3, with_cpu=False, with_ransac=False)
+            o = measure_ekf(args, 5, 3, with_cpu=False, with_ransac=True)
             others["c4"] = {"workload": o["config"]["workload"], "value": o["value"], "unit": o["unit"], "ms_per_step": o["ms_per_step"],
                             "e2e": {"value": o["e2e"]["value"], "ms_per_step": o["e2e"]["ms_per_step"]},
                             "roofline": {kq: o["roofline"][kq] for kq in ("kernel", "bound", "achieved", "peak", "unit", "frac")},
                             "kernels": {f: {kq: v[kq] for kq in ("avg_ms", "frac", "share_of_step") if kq in v} for f, v in o["kernels"].items()},
                             "gpu_launches": o["gpu_launches"]}
+            for extra_key in ("ransac_update_impl4", "six_d"):
+                if extra_key in o:
+                    others["c4"][extra_key] = o[extra_key]
+            if "ransac" in o:
+                others["c4"]["ransac_scoring"] = {kq: o["ransac"][kq] for kq in ("kernel_ms", "hypotheses_per_s", "frac") if kq in o["ransac"]}
         except Exception as ex:  # pragma: no cover
             others["c4"] = {"error": repr(ex)}
         out["other_configs"] = others
