@@ -292,3 +292,34 @@ def test_ekf_predict_oracle_matches_block_formula(oracle):
     P1[:13, :13] = F @ P[:13, :13] @ F.T + fr["GQGt"].astype(ld)
     P1[:13, 13:] = F @ P[:13, 13:]; P1[13:, :13] = P1[:13, 13:].T
     assert relerr(P_o, P1.astype(np.float64)) < 1e-14
+
+
+def test_threaded_sparse_flow_matches_the_serial_oracle(oracle):
+    """The timed CPU arm of the full-size configurations (bench.py --impl reference): per-point / per-frame passes on host threads, camera-pair
+    blocks merged in thread order, skyline Cholesky.  Same accept / skip decisions and the same trajectory as the serial sparse flow with the
+    refined Cholesky; the initial error is bit-identical (per-observation terms in parallel, summed serially in the reference's order)."""
+    from surikatoko_b200 import scenes
+    for scene in (scenes.ring_scene(40, 3000, 8, seed=7), scenes.ring_scene(80, 2000, 6, seed=9)):
+        pr = oracle.Problem(scene.obs_cam, scene.obs_point, scene.obs_xy, scene.points, scene.cams, scene.K, False, scene.f0)
+        a = oracle.ba_solve(pr, max_outer_iters=2, flow="sparse", solve="chol", acc="double")
+        b = oracle.ba_solve(pr, max_outer_iters=2, flow="threaded", solve="chol", acc="double")
+        assert a.err_initial == b.err_initial
+        assert np.array_equal(a.attempts[:, 2], b.attempts[:, 2]) and np.array_equal(a.attempts[:, 3], b.attempts[:, 3])
+        assert np.max(np.abs(a.err_trace - b.err_trace) / a.err_trace) < 1e-9
+
+
+def test_sequential_ekf_updates_agree_with_the_stacked_update_to_first_order(oracle):
+    """One observation per update (EKF.cpp:1153-1269) and one component per update (:1525-1650) relinearise between observations; for small
+    innovations all three update variants describe the same posterior to first order -- a sanity bound on the two restatements."""
+    from surikatoko_b200.ekf import synthetic_ransac_frame
+    fr = synthetic_ransac_frame(24, 3, seed=5, outlier_frac=0.0, pix_sigma=0.05)
+    cam9 = fr["camera"].as_array()
+    Hc, Hp, hp = oracle.ekf_jacobians(fr["x"], fr["pt_off"], 3, cam9)
+    ok, Ps, xs, _ = oracle.ekf_update(fr["P"], fr["x"], Hc, Hp, fr["pt_off"], fr["z"], hp, fr["meas_var"])
+    P1, x1 = oracle.ekf_sequential_update(fr["P"], fr["x"], fr["pt_off"], 3, fr["z"], fr["meas_var"], cam9)
+    P2, x2 = oracle.ekf_sequential_update(fr["P"], fr["x"], fr["pt_off"], 3, fr["z"], fr["meas_var"], cam9, per_component=True)
+    assert ok
+    step = np.max(np.abs(xs - fr["x"]))
+    assert np.max(np.abs(x1 - xs)) < 0.05 * step and np.max(np.abs(x2 - xs)) < 0.05 * step
+    assert relerr(P1, Ps) < 0.02 and relerr(P2, Ps) < 0.02
+    assert relerr(P1, P1.T) < 1e-15 and np.all(np.diag(P1) > 0)
