@@ -794,6 +794,15 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
             if (rc != SRK_OK) { set_error("pcg solve failed: " + std::string(cudaGetErrorString(cudaGetLastError()))); return rc; }
             e.pcg_rel_res_last = rel;
             e.pcg_iters_total += e.pcg_iters_last;
+            // The reference solves the reduced system exactly (BA.cpp:1911).  An iterative solve that stopped far from its tolerance (iteration
+            // cap, breakdown) must not pass for one: like a failed factorisation it counts as a failed attempt and is retried with more
+            // damping (flags[2] is the factorisation-info slot fetch_attempt_scalars reports).  Every rank sees the same residual.
+            const double tol = (opt != nullptr && opt->pcg_rel_tol > 0.0) ? opt->pcg_rel_tol : 1e-13;
+            if (!(rel <= 1e4 * tol) && !(rel <= 1e-8)) {
+                const int one = 1;
+                SRK_CUDA(cudaMemcpyAsync(e.flags.as<int>() + 2, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+                SRK_CUDA(cudaStreamSynchronize(st));
+            }
         }
         e.solver_used = SRK_SOLVER_BLOCK_PCG;
     }

@@ -104,3 +104,23 @@ def test_ekf_update_refuses_a_non_positive_definite_innovation_covariance():
         assert ekf.update(fr["Hcam"], fr["Hpt"], fr["pt_off"], fr["z"], fr["h"], fr["meas_var"]) == 0   # and the handle stays usable
     finally:
         ekf.close()
+
+
+def test_unconverged_pcg_solve_is_a_failed_attempt_not_a_silent_success():
+    """the reference solves the reduced system exactly (BA.cpp:1911); a PCG solve that stops at its iteration cap far from the
+    tolerance must not pass for one.  With 2 iterations allowed every attempt is refused (counted like a failed factorisation, retried with
+    ten times the damping) until max_hessian_factor ends the run the way the reference's loop does (:845-848); the last relative residual is
+    reported."""
+    import surikatoko_b200 as sb
+    from surikatoko_b200 import scenes
+    prob = scenes.ring_scene(40, 3000, 8, seed=7)
+    eng = sb.Engine(0)
+    try:
+        rep = eng.solve(prob.copy(), sb.BAOptions(err_change=1e-10, max_outer_iters=2, solver=sb.SOLVER_BLOCK_PCG, pcg_max_iters=2, max_hessian_factor=1e-1))
+        assert rep.factor_failures >= 1 and rep.pcg_rel_res_last > 1e-8
+        assert rep.stop_reason == "hessian overflow" and not rep.converged
+        assert np.all(np.isinf(rep.attempts[:, 1])) and np.all(rep.attempts[:, 2] == 0)
+        ok = eng.solve(prob.copy(), sb.BAOptions(err_change=1e-10, max_outer_iters=2, solver=sb.SOLVER_BLOCK_PCG))
+        assert ok.factor_failures == 0 and ok.pcg_rel_res_last <= 1e-9 and ok.err_trace[-1] < ok.err_initial
+    finally:
+        eng.close()
