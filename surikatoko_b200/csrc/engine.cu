@@ -368,13 +368,10 @@ int bind_impl(Engine& e, const srk_ba_problem* p, const srk_ba_options* opt, boo
         if (e.schur_tile_fixed > 0) {
             if (e.schur_tile_fixed != 256) { rcp = plan(e.schur_tile_fixed, &e.n_deferred); if (rcp != SRK_OK) return rcp; e.schur_tile_points = e.schur_tile_fixed; }
         } else if (N >= 148 * 4 * 1024) {   // enough tiles to keep every SM busy for several waves
-            // among the tile sizes that fill the 148 SMs evenly: the fuller the last wave of CTAs, the earlier the candidate is tried
-            // (configs[2]: 768 points -> 1303 tiles = 8.8 waves, 1024 -> 977 tiles = 6.6 waves; measured 2.21 vs 2.30 ms)
-            int cands[3] = {1024, 768, 512};
-            {
-                auto fill = [&](int t) { const double tiles = (double)((N + t - 1) / t); return tiles / (std::ceil(tiles / 148.0) * 148.0); };
-                std::sort(cands, cands + 3, [&](int a, int b) { const double fa = fill(a), fb = fill(b); return fa != fb ? fa > fb : a > b; });
-            }
+            // measured with the third form of K2 at configs[2] (K2 family, ms): 128 points 1.89, 256 1.78, 384 1.77, 512 1.80, 640 1.82, 768 1.82,
+            // 1024 1.96, 1536 2.28 -- smaller tiles touch fewer cameras (fewer fragment rows: 105 -> 91 DMMAs per k-step at 10 cameras) and
+            // the per-tile table work is gone (bind-time tables), larger ones amortise the flush of the accumulators
+            int cands[3] = {384, 512, 768};
             bool chosen = false;
             for (int t : cands) {
                 int64_t nd = 0;
