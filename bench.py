@@ -364,8 +364,10 @@ def measure_ba(args, name, steps, warmup, scaling="strong", full=True):
             solve_note = "executed flops over the %d non-zero 64x64 tiles of L (%d block rows; a dense factor would have %d)" % (
                 stats["nonzero_tiles"], stats["block_rows"], stats["block_rows"] * (stats["block_rows"] + 1) // 2)
             if stats.get("parts", 0) > 0:
-                solve_note += "; nested-dissection order: %d parts factored concurrently (longest %d block columns) + separator of %d" % (
-                    stats["parts"], stats["max_part_blocks"], stats["separator_blocks"])
+                solve_note += "; nested-dissection order: %d parts factored concurrently (longest %d block columns)" % (stats["parts"], stats["max_part_blocks"])
+                if stats.get("mid_separators", 0) > 0:
+                    solve_note += " + %d second-level separators (longest %d)" % (stats["mid_separators"], stats["max_mid_blocks"])
+                solve_note += " + separator of %d" % stats["separator_blocks"]
         except Exception as ex:  # pragma: no cover
             solve_note += " (solve_stats unavailable: %s)" % ex
     # stored entries of the reduced system: the non-zero 64x64 tiles of the dense layout / the 10x10 blocks of the block-sparse one

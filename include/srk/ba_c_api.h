@@ -167,6 +167,9 @@ SRK_API int srk_ba_debug_get_state(void* h, double* points, double* cams);
  * part_k0 / part_k1 [32] = 64-column block ranges of the parts, *ksep = first block column of the separator. */
 SRK_API int srk_ba_debug_build_order(int32_t n_groups, const int32_t* group_size, const unsigned char* adj, int32_t* pos, int64_t* ordered_n, int32_t* part_k0,
                                      int32_t* part_k1, int32_t* ksep);
+/* Same inputs: the second level.  Returns the number of second-level separators; mid_k0 / mid_k1 [16] = their block ranges, all inside
+ * [ksep, *msep); *msep = first block column of the top separator.  A second-level separator couples exactly two leaves. */
+SRK_API int srk_ba_debug_order_levels(int32_t n_groups, const int32_t* group_size, const unsigned char* adj, int32_t* mid_k0, int32_t* mid_k1, int32_t* msep);
 /* ApplyCorrections (BA.cpp:1997-2063) of `corrections` to the resident state, then ReprojError. */
 SRK_API int srk_ba_debug_apply(void* h, const double* corrections, double* err_new);
 
@@ -184,6 +187,10 @@ SRK_API int srk_ba_solve_stats(void* h, int64_t* n_f, int64_t* block_rows, int64
  * block columns) followed by a separator of separator_blocks block columns; ordered_n = n_f + padding to 64-column part boundaries.
  * SRK_SOLVE_ORDER=0 in the environment of srk_ba_create forces capture order. */
 SRK_API int srk_ba_solve_order(void* h, int64_t* ordered_n, int64_t* parts, int64_t* max_part_blocks, int64_t* separator_blocks);
+/* Second level of the dissection: when mid_separators > 0 the parts above are LEAVES, pairs of which are coupled through a second-level
+ * separator (the longest is max_mid_blocks block columns); the dependent chain of the factorisation is then
+ * max_part_blocks + max_mid_blocks + separator_blocks block columns.  SRK_SOLVE_LEVELS=1 keeps the one-level order. */
+SRK_API int srk_ba_solve_levels(void* h, int64_t* mid_separators, int64_t* max_mid_blocks);
 /* Block-sparse (PCG) path: stored 10x10 blocks of the reduced camera system (lower block triangle incl. the diagonal) and the PCG
  * iterations executed since srk_ba_set_timing(h, 1) -- the work bench.py's roofline of that solve is computed from. */
 SRK_API int srk_ba_pcg_stats(void* h, int64_t* nnz_blocks, int64_t* iters_since_timing);

@@ -77,6 +77,7 @@ def load_library():
     L.srk_ba_get_timing.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.srk_ba_solve_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
     L.srk_ba_solve_order.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.srk_ba_solve_levels.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.srk_nccl_unique_id.argtypes = [C.c_void_p]
     L.srk_ba_nccl_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.srk_ba_set_nccl_comm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -296,8 +297,10 @@ class Engine:
         _check(self._lib.srk_ba_solve_stats(self._h, C.byref(nf), C.byref(nb), C.byref(nz), C.byref(fl)))
         on, parts, mp, sb = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         _check(self._lib.srk_ba_solve_order(self._h, C.byref(on), C.byref(parts), C.byref(mp), C.byref(sb)))
+        mids, mm = C.c_int64(), C.c_int64()
+        _check(self._lib.srk_ba_solve_levels(self._h, C.byref(mids), C.byref(mm)))
         return dict(n_f=nf.value, block_rows=nb.value, nonzero_tiles=nz.value, factor_flops=fl.value, ordered_n=on.value, parts=parts.value,
-                    max_part_blocks=mp.value, separator_blocks=sb.value)
+                    max_part_blocks=mp.value, separator_blocks=sb.value, mid_separators=mids.value, max_mid_blocks=mm.value)
 
     def pcg_stats(self):
         """Stored 10x10 blocks of the block-sparse reduced system and the PCG iterations executed since set_timing(True)."""

@@ -1387,6 +1387,14 @@ static thread_local FactorGraph g_fg;   // per host thread: a handle is driven b
 
 // Sparse-factor path: tile pattern of the input, then (when it is sparse enough) the single-cluster kernel.  Returns the number of
 // launches, or 0 when the matrix is not sparse and the launch-per-operation path has to run.
+constexpr size_t kBandSmemRequest = sizeof(BandSmem) > 120 * 1024 ? sizeof(BandSmem) : 120 * 1024;
+// the second level of a two-level partition seen as a one-level one: parts = the second-level separators, separator = the top one
+static CholPartition mid_level(const CholPartition& p) {
+    CholPartition m;
+    m.nparts = p.nmids; m.ksep = p.msep;
+    for (int i = 0; i < p.nmids; ++i) { m.k0[i] = p.m0[i]; m.k1[i] = p.m1[i]; }
+    return m;
+}
 static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev, const CholPartition* part, const unsigned char* pattern_dev,
                                int pattern_count) {
     const int nblk = chol_nblk(n);
@@ -1396,8 +1404,13 @@ static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, do
     if (force == 1) return 0;
     static PerDeviceOnce once;
     if (once.first()) {
-        if (cudaFuncSetAttribute(k_band_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BandSmem)) != cudaSuccess) { cudaGetLastError(); once.forget(); return 0; }
+        if (cudaFuncSetAttribute(k_band_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandSmemRequest) != cudaSuccess) { cudaGetLastError(); once.forget(); return 0; }
     }
+    // The kernel is a latency chain: two CTAs of different clusters on one SM would take turns on every step.  Asking for more than half
+    // of the SM's shared memory keeps it at one CTA per SM (SRK_BAND_SMEM_PAD=0: the bare request, development aid).
+    static int pad = -1;
+    if (pad < 0) { const char* e = getenv("SRK_BAND_SMEM_PAD"); pad = (e != nullptr && e[0] == '0') ? 0 : 1; }
+    const size_t band_smem = pad ? kBandSmemRequest : sizeof(BandSmem);
     unsigned char* F = ws_F(ws, n);
     int* cnt = ws_nzt(ws, n);
     cudaMemsetAsync(info_dev, 0, sizeof(int), st);
@@ -1416,12 +1429,19 @@ static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, do
     const int max_fill = (part != nullptr && part->nparts > 0) ? 2 * kBandMaxFill : kBandMaxFill;   // a partitioned pattern carries the separator rows as well
     if (h < 0 || (force != 2 && h > max_fill * nblk)) return 0;
     if (part != nullptr && part->nparts > 0) {
-        k_band_chol<<<kBandCluster * part->nparts, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 0);
-        k_band_chol<<<kBandCluster, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 1);
+        k_band_chol<<<kBandCluster * part->nparts, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 0);
+        CholPartition top = *part;
+        if (part->nmids > 0) {      // second-level separators: the same kernel with their ranges as the parts and the top separator as the shared block
+            const CholPartition mids = mid_level(*part);
+            k_band_chol<<<kBandCluster * mids.nparts, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, mids, 0);
+            top.ksep = part->msep;
+            nl += 1;
+        }
+        k_band_chol<<<kBandCluster, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, top, 1);
         nl += 2;
     } else {
-        CholPartition whole; whole.nparts = 0; whole.ksep = 0;
-        k_band_chol<<<kBandCluster, 256, sizeof(BandSmem), st>>>(n, A, ld, ws, info_dev, F, nblk, whole, 1);
+        CholPartition whole;
+        k_band_chol<<<kBandCluster, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, whole, 1);
         nl += 1;
     }
     if (cudaGetLastError() != cudaSuccess) return 0;
@@ -1509,11 +1529,21 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
         if (use_cluster) {
             const int* lst = ws_list(ws, n, backward);
             if (part != nullptr && part->nparts > 0) {
-                if (!backward) k_trsv_cluster<<<kBandCluster * part->nparts, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, *part, 0);
-                k_trsv_cluster<<<kBandCluster, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, *part, 1);
-                if (backward) k_trsv_cluster<<<kBandCluster * part->nparts, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, *part, 0);
+                // forward: leaves, second-level separators, top;  backward: the reverse (solved blocks of the later levels are plain multipliers)
+                CholPartition top = *part, mids;
+                const bool two = part->nmids > 0;
+                if (two) { mids = mid_level(*part); top.ksep = part->msep; }
+                if (!backward) {
+                    k_trsv_cluster<<<kBandCluster * part->nparts, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, *part, 0);
+                    if (two) k_trsv_cluster<<<kBandCluster * mids.nparts, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, mids, 0);
+                }
+                k_trsv_cluster<<<kBandCluster, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, top, 1);
+                if (backward) {
+                    if (two) k_trsv_cluster<<<kBandCluster * mids.nparts, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, mids, 0);
+                    k_trsv_cluster<<<kBandCluster * part->nparts, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, *part, 0);
+                }
             } else {
-                CholPartition whole; whole.nparts = 0; whole.ksep = 0;
+                CholPartition whole;
                 k_trsv_cluster<<<kBandCluster, 256, sizeof(TrsvClSmem), st>>>(n, L, ld, dinv, b, nzt, lst, backward, whole, 1);
             }
         }
@@ -1525,13 +1555,13 @@ static int64_t trsv(cudaStream_t st, int n, const double* L, int64_t ld, double*
             printf("  trsv: nblk=%d non-zero tiles=%d ops=%d sparse path=%d\n", nblk, h[0], h[1], (int)trsv_use_sparse(n, nblk, h[0]));
         }
     }
-    if (sparse_certain && n <= kTrsvSparseMaxN && !g_prof) return 1 + ((part != nullptr && part->nparts > 0) ? 1 : 0);   // the caller knows the tile count: no need to launch the dense kernel just to see it return
+    if (sparse_certain && n <= kTrsvSparseMaxN && !g_prof) return 1 + ((part != nullptr && part->nparts > 0) ? (part->nmids > 0 ? 2 : 1) : 0);   // the caller knows the tile count: no need to launch the dense kernel just to see it return
     int cacheF = nblk * nblk <= kTrsvFCacheMax ? 1 : 0;
     size_t smem = sizeof(double) * 2 * kTrsvOwn * NB * NB + (cacheF ? (size_t)((nblk * nblk + 15) & ~15) : 0);
     void* args[] = {(void*)&n, (void*)&L, (void*)&ld, (void*)&dinv, (void*)&b, (void*)&ybuf, (void*)&flags, (void*)&F, (void*)&epoch, (void*)&backward,
                     (void*)&cacheF, (void*)&nzt};
     cudaLaunchCooperativeKernel((void*)k_trsv_flags, dim3(blocks), dim3(256), args, smem, st);
-    return 2 + ((part != nullptr && part->nparts > 0 && n <= kTrsvSparseMaxN) ? 1 : 0);
+    return 2 + ((part != nullptr && part->nparts > 0 && n <= kTrsvSparseMaxN) ? (part->nmids > 0 ? 2 : 1) : 0);
 }
 // Structure of the last factor held in `ws`: non-zero 64x64 tiles of L and the flops the factorisation actually executed
 // (potrf 64^3/3 per diagonal block, 64^3 per off-diagonal tile for the right solve, 2*64^3 per pair of non-zero tiles of a

@@ -1314,6 +1314,26 @@ int srk_ba_solve_order(void* h, int64_t* ordered_n, int64_t* parts, int64_t* max
     return SRK_OK;
 }
 
+int srk_ba_solve_levels(void* h, int64_t* mid_separators, int64_t* max_mid_blocks) {
+    if (h == nullptr) { set_error("null handle"); return SRK_E_INVALID_ARG; }
+    Engine& e = *(Engine*)h;
+    if (!e.bound) { set_error("no problem bound"); return SRK_E_NOT_BOUND; }
+    const bool on = e.order_ready && e.order.active;
+    if (mid_separators != nullptr) *mid_separators = on ? e.order.part.nmids : 0;
+    if (max_mid_blocks != nullptr) *max_mid_blocks = on ? e.order.max_mid_blocks : 0;
+    return SRK_OK;
+}
+
+int srk_ba_debug_order_levels(int32_t n_groups, const int32_t* group_size, const unsigned char* adj, int32_t* mid_k0, int32_t* mid_k1, int32_t* msep) {
+    if (n_groups <= 0 || group_size == nullptr || adj == nullptr) { set_error("null argument"); return SRK_E_INVALID_ARG; }
+    std::vector<int> gs(group_size, group_size + n_groups);
+    const srk::SolveOrder o = srk::build_solve_order(n_groups, gs.data(), adj);
+    if (!o.active) { if (msep != nullptr) *msep = 0; return 0; }
+    for (int p = 0; p < o.part.nmids; ++p) { if (mid_k0 != nullptr) mid_k0[p] = o.part.m0[p]; if (mid_k1 != nullptr) mid_k1[p] = o.part.m1[p]; }
+    if (msep != nullptr) *msep = o.part.msep;
+    return o.part.nmids;
+}
+
 int srk_ba_pcg_stats(void* h, int64_t* nnz_blocks, int64_t* iters_since_timing) {
     if (h == nullptr) { set_error("null handle"); return SRK_E_INVALID_ARG; }
     Engine& e = *(Engine*)h;

@@ -82,7 +82,14 @@ void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda,
 // Optional scheduling hint for block-sparse systems ordered by nested dissection (solve_order.h): the block columns (64 wide) of
 // part p are [k0[p], k1[p]); no non-zero tile couples two different parts; [ksep, nblk) is the separator block, ordered last.
 // The parts are then factored / substituted by one thread-block cluster each, concurrently, the separator afterwards.
-struct CholPartition { static constexpr int kMaxParts = 32; int nparts; int ksep; int k0[kMaxParts]; int k1[kMaxParts]; };
+// Two-level dissection (nmids > 0): the parts are the LEAVES, [ksep, msep) holds the second-level separators -- block columns
+// [m0[i], m1[i]) of separator i, which couples two leaves to each other; different second-level separators do not touch -- and
+// [msep, nblk) is the top separator.  Order of work: leaves (concurrently), second-level separators (concurrently), top.
+struct CholPartition {
+    static constexpr int kMaxParts = 32;
+    int nparts = 0; int ksep = 0; int k0[kMaxParts]; int k1[kMaxParts];
+    int nmids = 0; int msep = 0; int m0[kMaxParts / 2]; int m1[kMaxParts / 2];
+};
 // pattern_dev (optional, device, nblk x nblk bytes, [c*nblk + r] = 1 for a strictly lower tile that may hold a non-zero) + its count:
 // the caller's knowledge of the tile structure replaces the pattern pass over A and its host round trip.  A must then be zero in
 // every tile outside the pattern that the factorisation fills (SolveOrder::l_all_tiles).

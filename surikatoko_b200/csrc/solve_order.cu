@@ -7,13 +7,21 @@
 #include <numeric>
 #include <queue>
 #include <cstring>
+#include <cstdlib>
 
 namespace srk {
 
 namespace {
 
 constexpr int kTile = 64;
-constexpr int kMaxConcurrentParts = 16;     // clusters of 8 CTAs that are co-resident on 148 SMs
+// clusters of 8 CTAs that are co-resident on 148 SMs at one CTA per SM: cudaOccupancyMaxActiveClusters says 15 on B200 (a cluster stays
+// inside a GPC, and the GPCs have 16 to 20 SMs); a 16th part would run as a second wave.  SRK_SOLVE_MAX_PARTS overrides (development aid)
+static int max_concurrent_parts() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SRK_SOLVE_MAX_PARTS"); v = e != nullptr ? atoi(e) : 15; if (v < 2) v = 2; if (v > CholPartition::kMaxParts) v = CholPartition::kMaxParts; }
+    return v;
+}
+#define kMaxConcurrentParts max_concurrent_parts()
 
 struct Graph {
     int G;
@@ -58,7 +66,7 @@ struct Candidate {
     int nbins = 0, sep_tiles = 0, max_bin_tiles = 0, nsep_levels = 0;
 };
 
-Candidate evaluate(const Graph& g, const int* gsize, const std::vector<int>& level, int nlevels, const std::vector<char>& sep_level) {
+Candidate evaluate(const Graph& g, const int* gsize, const std::vector<int>& level, int nlevels, const std::vector<char>& sep_level, int max_bins) {
     Candidate c;
     c.is_sep_level = sep_level;
     c.comp.assign(g.G, -1);
@@ -81,8 +89,8 @@ Candidate evaluate(const Graph& g, const int* gsize, const std::vector<int>& lev
     }
     for (char s : sep_level) c.nsep_levels += s ? 1 : 0;
     if (ncomp < 2) return c;
-    // longest-processing-time packing of the components into at most kMaxConcurrentParts bins
-    const int nbins = std::min(ncomp, kMaxConcurrentParts);
+    // longest-processing-time packing of the components into at most max_bins bins
+    const int nbins = std::min(ncomp, max_bins);
     std::vector<int> order(ncomp);
     std::iota(order.begin(), order.end(), 0);
     std::sort(order.begin(), order.end(), [&](int a, int b) { return comp_vars[a] != comp_vars[b] ? comp_vars[a] > comp_vars[b] : a < b; });
@@ -149,7 +157,74 @@ SolveOrder build_solve_order(int G, const int* gsize, const unsigned char* adj) 
     }
     // candidates: q whole levels as separators, spaced evenly in unknowns (scheme 0) or with half-width end gaps (scheme 1: on a ring
     // the end gaps are one component each, the inner gaps split into two)
-    Candidate best;
+    // One-level candidates fill up to kMaxConcurrentParts bins; two-level candidates half as many, because every bin becomes two leaves.
+    static int two_level = -1;      // SRK_SOLVE_LEVELS=1 keeps the one-level order (development aid)
+    if (two_level < 0) { const char* e = getenv("SRK_SOLVE_LEVELS"); two_level = (e != nullptr && e[0] == '1') ? 0 : 1; }
+    std::vector<int> by_level(G);
+    std::iota(by_level.begin(), by_level.end(), 0);
+    std::stable_sort(by_level.begin(), by_level.end(), [&](int a, int b) { return level[a] < level[b]; });
+    struct Piece { std::vector<int> groups; int vars = 0; };
+    struct Plan { std::vector<Piece> leaves, mids; int chain = 0; bool cut = false; };
+    // second level: a bin that holds ONE component is cut at the BFS level that halves its unknowns.  Edges join neighbouring levels
+    // only, so the level separates what lies below it from what lies above: two leaves and a second-level separator that only those
+    // two leaves (and the top separator) touch.  The chain of a bin of b tiles shrinks from b to ~b/2 + (tiles of one level).
+    auto plan_of = [&](const Candidate& c, bool allow_cut) {
+        Plan pl;
+        const int ncomp = (int)c.bin_of_comp.size();
+        std::vector<std::vector<int>> bin_groups(c.nbins);
+        std::vector<int> bin_ncomp(c.nbins, 0), bin_vars(c.nbins, 0);
+        for (int b = 0; b < c.nbins; ++b)
+            for (int ci = 0; ci < ncomp; ++ci) {
+                if (c.bin_of_comp[ci] != b) continue;
+                ++bin_ncomp[b];
+                for (int u : by_level) if (c.comp[u] == ci) { bin_groups[b].push_back(u); bin_vars[b] += gsize[u]; }
+            }
+        auto tiles = [](int v) { return (v + kTile - 1) / kTile; };
+        std::vector<int> cut_level(c.nbins, -1), cut_chain(c.nbins, 0);
+        int nleaves = c.nbins, chain_before = 0, chain_after = 0;
+        std::vector<int> cand(c.nbins);
+        std::iota(cand.begin(), cand.end(), 0);
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return bin_vars[a] > bin_vars[b]; });
+        for (int b : cand) {
+            cut_chain[b] = tiles(bin_vars[b]);
+            if (!allow_cut || nleaves + 1 > kMaxConcurrentParts || bin_ncomp[b] != 1 || bin_groups[b].empty()) continue;
+            const int lo = level[bin_groups[b].front()], hi = level[bin_groups[b].back()];
+            if (hi - lo < 2) continue;
+            std::vector<int> w(hi - lo + 1, 0);
+            for (int u : bin_groups[b]) w[level[u] - lo] += gsize[u];
+            int best_l = -1, best_worst = 0x7fffffff, below = w[0];
+            for (int l = lo + 1; l < hi; ++l) {
+                const int above = bin_vars[b] - below - w[l - lo];
+                const int worst = std::max(below, above);
+                if (below > 0 && above > 0 && worst < best_worst) { best_worst = worst; best_l = l; }
+                below += w[l - lo];
+            }
+            if (best_l < 0) continue;
+            const int cut_tiles = tiles(best_worst) + tiles(w[best_l - lo]);
+            if (cut_tiles + 2 > tiles(bin_vars[b])) continue;             // nothing to gain
+            cut_level[b] = best_l;
+            cut_chain[b] = cut_tiles;
+            ++nleaves;
+        }
+        // the chain is the longest bin: cuts pay only when they shorten THAT by two steps or more, and only bins longer than the new
+        // longest one need cutting (every cut costs padding)
+        for (int b = 0; b < c.nbins; ++b) { chain_before = std::max(chain_before, tiles(bin_vars[b])); chain_after = std::max(chain_after, cut_chain[b]); }
+        for (int b = 0; b < c.nbins; ++b)
+            if (chain_after + 2 > chain_before || tiles(bin_vars[b]) <= chain_after) cut_level[b] = -1;
+        pl.chain = chain_after + 2 > chain_before ? chain_before : chain_after;
+        for (int b = 0; b < c.nbins; ++b) {
+            if (cut_level[b] < 0) { Piece p; p.groups = bin_groups[b]; p.vars = bin_vars[b]; pl.leaves.push_back(std::move(p)); continue; }
+            Piece lo_p, hi_p, mid_p;
+            for (int u : bin_groups[b]) {
+                Piece& dst = level[u] < cut_level[b] ? lo_p : (level[u] == cut_level[b] ? mid_p : hi_p);
+                dst.groups.push_back(u); dst.vars += gsize[u];
+            }
+            pl.leaves.push_back(std::move(lo_p)); pl.leaves.push_back(std::move(hi_p)); pl.mids.push_back(std::move(mid_p));
+            pl.cut = true;
+        }
+        return pl;
+    };
+    Candidate best, best2;
     const int qmax = std::min(24, (nlevels - 1) / 2);
     for (int q = 1; q <= qmax; ++q) {
         for (int scheme = 0; scheme < 2; ++scheme) {
@@ -164,40 +239,60 @@ SolveOrder build_solve_order(int G, const int* gsize, const unsigned char* adj) 
                 if (!sep[l]) { sep[l] = 1; ++placed; }
             }
             if (placed == 0) continue;
-            Candidate c = evaluate(g, gsize, level, nlevels, sep);
+            Candidate c = evaluate(g, gsize, level, nlevels, sep, kMaxConcurrentParts);
             if (c.cost < best.cost) best = std::move(c);
+            if (two_level) {
+                Candidate c2 = evaluate(g, gsize, level, nlevels, sep, kMaxConcurrentParts / 2);
+                if (c2.nbins >= 2) {        // estimate: every bin halves, plus a second-level separator of about two tiles
+                    c2.cost = (double)((c2.max_bin_tiles + 1) / 2 + 2) + dense_chain_cost(c2.sep_tiles);
+                    if (c2.cost < best2.cost) best2 = std::move(c2);
+                }
+            }
         }
     }
+    Plan plan;
+    bool have_plan = false;
+    if (two_level && best2.nbins >= 2) {        // the estimate has to survive the real cut
+        Plan p2 = plan_of(best2, true);
+        const double cost2 = (double)p2.chain + dense_chain_cost(best2.sep_tiles);
+        if (p2.cut && cost2 + 1.0 < best.cost) { best = std::move(best2); best.cost = cost2; plan = std::move(p2); have_plan = true; }
+    }
     if (!(best.cost < 0.75 * (double)nblk0) || best.nbins < 2) return o;
+    if (!have_plan) plan = plan_of(best, false);
+    const std::vector<Piece>& leaves = plan.leaves;
+    const std::vector<Piece>& mids = plan.mids;
 
-    // positions: bins in order, inside a bin components in id order, inside a component groups by (level, index); separator last
+    // positions: leaves in order (inside a leaf components in id order, inside a component groups by (level, index)), then the
+    // second-level separators, the top separator last; every piece starts on a 64-column boundary
     std::vector<int> gstart(G + 1, 0);
     for (int u = 0; u < G; ++u) gstart[u + 1] = gstart[u] + gsize[u];
     o.pos.assign(n, -1);
     int cursor = 0;
     auto place = [&](int u) { for (int a = 0; a < gsize[u]; ++a) o.pos[gstart[u] + a] = cursor++; };
-    std::vector<int> by_level(G);
-    std::iota(by_level.begin(), by_level.end(), 0);
-    std::stable_sort(by_level.begin(), by_level.end(), [&](int a, int b) { return level[a] < level[b]; });
-    const int ncomp = (int)best.bin_of_comp.size();
     o.part.nparts = 0;
-    for (int b = 0; b < best.nbins; ++b) {
+    for (const Piece& p : leaves) {
         const int k0 = cursor / kTile;
-        for (int ci = 0; ci < ncomp; ++ci) {
-            if (best.bin_of_comp[ci] != b) continue;
-            for (int u : by_level) if (best.comp[u] == ci) place(u);
-        }
+        for (int u : p.groups) place(u);
         cursor = (cursor + kTile - 1) / kTile * kTile;
         const int k1 = cursor / kTile;
         if (k1 > k0) { o.part.k0[o.part.nparts] = k0; o.part.k1[o.part.nparts] = k1; ++o.part.nparts; o.max_part_blocks = std::max(o.max_part_blocks, k1 - k0); }
     }
     o.part.ksep = cursor / kTile;
+    o.part.nmids = 0;
+    for (const Piece& p : mids) {
+        const int k0 = cursor / kTile;
+        for (int u : p.groups) place(u);
+        cursor = (cursor + kTile - 1) / kTile * kTile;
+        const int k1 = cursor / kTile;
+        if (k1 > k0) { o.part.m0[o.part.nmids] = k0; o.part.m1[o.part.nmids] = k1; ++o.part.nmids; o.max_mid_blocks = std::max(o.max_mid_blocks, k1 - k0); }
+    }
+    o.part.msep = cursor / kTile;
     for (int u : by_level) if (best.comp[u] < 0) place(u);
     o.np = cursor;
     o.src.assign(o.np, -1);
     for (int i = 0; i < n; ++i) o.src[o.pos[i]] = i;
     o.sep_levels = best.nsep_levels;
-    o.sep_blocks = (o.np + kTile - 1) / kTile - o.part.ksep;
+    o.sep_blocks = (o.np + kTile - 1) / kTile - o.part.msep;
     o.active = o.part.nparts >= 2;
     if (!o.active) return o;
 

@@ -23,7 +23,7 @@ struct SolveOrder {
     std::vector<int> pos;       // [n]  natural index -> ordered index
     std::vector<int> src;       // [np] ordered index -> natural index, -1 = padding
     CholPartition part{};       // block-column ranges of the parts and of the separator
-    int levels = 0, sep_levels = 0, sep_blocks = 0, max_part_blocks = 0;   // diagnostics
+    int levels = 0, sep_levels = 0, sep_blocks = 0, max_part_blocks = 0, max_mid_blocks = 0;   // diagnostics (blocks of the top separator, the longest leaf, the longest second-level separator)
     // 64x64 tile structure (from the same graph, so a superset of whatever the damping / skip rule leaves non-zero), which lets
     // every pass over the system touch its ~4 % non-zero tiles instead of n^2 entries.  Tiles are packed (row << 16) | col, row >= col.
     std::vector<int> s_tiles;            // natural-order system: lower tiles that can hold a non-zero

@@ -20,7 +20,12 @@ def build_order(adj, group_size=None):
     on = C.c_int64(); ksep = C.c_int32()
     nparts = L.srk_ba_debug_build_order(G, gs.ctypes.data, a.ctypes.data, pos.ctypes.data, C.byref(on), k0.ctypes.data, k1.ctypes.data, C.byref(ksep))
     assert nparts >= 0
-    return dict(nparts=nparts, pos=pos, ordered_n=on.value, k0=k0[:nparts], k1=k1[:nparts], ksep=ksep.value, gs=gs)
+    L.srk_ba_debug_order_levels.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+    m0 = np.zeros(16, dtype=np.int32); m1 = np.zeros(16, dtype=np.int32); msep = C.c_int32()
+    nmids = L.srk_ba_debug_order_levels(G, gs.ctypes.data, a.ctypes.data, m0.ctypes.data, m1.ctypes.data, C.byref(msep))
+    assert nmids >= 0
+    return dict(nparts=nparts, pos=pos, ordered_n=on.value, k0=k0[:nparts], k1=k1[:nparts], ksep=ksep.value, gs=gs,
+                nmids=nmids, m0=m0[:nmids], m1=m1[:nmids], msep=msep.value if nparts > 0 else 0)
 
 
 def check_valid(adj, o):
@@ -45,6 +50,23 @@ def check_valid(adj, o):
     a_idx, b_idx = np.nonzero(adj)
     pa, pb = part_of_group[a_idx], part_of_group[b_idx]
     assert not np.any((pa >= 0) & (pb >= 0) & (pa != pb)), "two different parts are coupled"
+    # second level: the separators lie in [ksep, msep), do not overlap, are not coupled to each other, and each touches at most two leaves
+    assert o["ksep"] <= o["msep"] <= (o["ordered_n"] + 63) // 64
+    mid_of_tile = np.full_like(part_of_tile, -1)
+    for m, (a, b) in enumerate(zip(o["m0"], o["m1"])):
+        assert o["ksep"] <= a < b <= o["msep"]
+        assert np.all(mid_of_tile[a:b] == -1)
+        mid_of_tile[a:b] = m
+    assert np.all(mid_of_tile[o["ksep"]:o["msep"]] >= 0)
+    if o["nmids"] == 0:
+        assert o["msep"] == o["ksep"]
+        return
+    mid_of_group = np.array([mid_of_tile[tile[start[g]]] for g in range(len(gs))])
+    ma, mb = mid_of_group[a_idx], mid_of_group[b_idx]
+    assert not np.any((ma >= 0) & (mb >= 0) & (ma != mb)), "two second-level separators are coupled"
+    for m in range(o["nmids"]):
+        touched = set(pb[(ma == m) & (pb >= 0)].tolist()) | set(pa[(mb == m) & (pa >= 0)].tolist())
+        assert len(touched) <= 2, "a second-level separator couples more than two leaves"
 
 
 def ring_graph(M, w, closed=True):
@@ -67,8 +89,9 @@ def test_ring_and_chain_graphs_are_split_into_independent_parts(M, w, closed):
     check_valid(adj, o)
     assert o["nparts"] >= 4
     nblk0 = (int(o["gs"].sum()) + 63) // 64
-    longest = int(np.max(o["k1"] - o["k0"])); sep = (o["ordered_n"] + 63) // 64 - o["ksep"]
-    assert longest + sep < 0.5 * nblk0, "the dependent chain must be much shorter than in capture order"
+    longest = int(np.max(o["k1"] - o["k0"])); sep = (o["ordered_n"] + 63) // 64 - o["msep"]
+    longest_mid = int(np.max(o["m1"] - o["m0"])) if o["nmids"] else 0
+    assert longest + longest_mid + sep < 0.5 * nblk0, "the dependent chain must be much shorter than in capture order"
     assert o["ordered_n"] < 1.15 * int(o["gs"].sum())                                        # padding stays small
 
 
