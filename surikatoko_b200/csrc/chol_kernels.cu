@@ -1618,31 +1618,46 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
     const int nk = (K + KC - 1) / KC;
     const int wr = (warp & 3) * 32, wc = (warp >> 2) * 64;
     const int g = lane >> 2, tg = lane & 3;
-    for (int t = blockIdx.x; t < tm * tn; t += gridDim.x) {
-        const int ti = t % tm, tj = t / tm;
-        const int i0 = ti * TILE, j0 = tj * TILE;
-        if (lower_only && i0 + TILE - 1 < j0) continue;
-        auto load_chunk = [&](int stage, int kc) {
+    // Work list.  lower_only: ONLY the tiles that touch the lower triangle, numbered down the block columns -- striding over the full
+    // tm x tn grid and skipping the upper ones left the CTAs with 6 to 10 tiles each (ncu: the DMMA pipe 84 % busy while an SM was
+    // active, 71 % of the elapsed time).  Every tile of the list costs the same, so a plain round-robin is balanced to one tile.
+    const int tc = tn < tm ? tn : tm;          // block columns that reach the lower triangle
+    const int ntiles = lower_only ? tc * tm - tc * (tc - 1) / 2 : tm * tn;
+    auto tile_of = [&](int t, int& ti, int& tj) {
+        if (!lower_only) { ti = t % tm; tj = t / tm; return; }
+        int c = 0, rem = t;                       // block column c holds rows c .. tm-1
+        while (c < tn && rem >= tm - c) { rem -= (tm - c > 0 ? tm - c : 0); ++c; }
+        ti = c + rem; tj = c;
+    };
+    auto load_chunk = [&](int i0, int j0, int stage, int kc) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int v = tid + 256 * q;
-                const int k = v >> 6, rp = (v & 63) * 2;
-                const int kk = kc * KC + k;
-                {
-                    const int row = i0 + rp;
-                    int bytes = (kk < K) ? (m - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
-                    cp_async16(sA + (stage * KC + k) * SLD + rp, A + (bytes > 0 ? (size_t)kk * lda + row : 0), bytes);
-                }
-                {
-                    const int row = j0 + rp;
-                    int bytes = (kk < K) ? (n - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
-                    cp_async16(sB + (stage * KC + k) * SLD + rp, B + (bytes > 0 ? (size_t)kk * ldb + row : 0), bytes);
-                }
+        for (int q = 0; q < 4; ++q) {
+            const int v = tid + 256 * q;
+            const int k = v >> 6, rp = (v & 63) * 2;
+            const int kk = kc * KC + k;
+            {
+                const int row = i0 + rp;
+                int bytes = (kk < K) ? (m - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+                cp_async16(sA + (stage * KC + k) * SLD + rp, A + (bytes > 0 ? (size_t)kk * lda + row : 0), bytes);
             }
-        };
-        load_chunk(0, 0); cp_async_commit();
-        if (nk > 1) load_chunk(1, 1);
-        cp_async_commit();
+            {
+                const int row = j0 + rp;
+                int bytes = (kk < K) ? (n - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+                cp_async16(sB + (stage * KC + k) * SLD + rp, B + (bytes > 0 ? (size_t)kk * ldb + row : 0), bytes);
+            }
+        }
+    };
+    // the first two chunks of a tile are requested BEFORE the epilogue of the tile before it: its read-modify-write of C then overlaps them
+    bool primed = false;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int ti, tj;
+        tile_of(t, ti, tj);
+        const int i0 = ti * TILE, j0 = tj * TILE;
+        if (!primed) {
+            load_chunk(i0, j0, 0, 0); cp_async_commit();
+            if (nk > 1) load_chunk(i0, j0, 1, 1);
+            cp_async_commit();
+        }
         double acc[4][NJ][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -1651,7 +1666,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
         for (int kc = 0; kc < nk; ++kc) {
             cp_async_wait<1>();
             __syncthreads();
-            if (kc + 2 < nk) load_chunk((kc + 2) % STAGES, kc + 2);
+            if (kc + 2 < nk) load_chunk(i0, j0, (kc + 2) % STAGES, kc + 2);
             cp_async_commit();
             const double* cA = sA + (kc % STAGES) * KC * SLD;
             const double* cB = sB + (kc % STAGES) * KC * SLD;
@@ -1672,6 +1687,15 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
         }
         cp_async_wait<0>();
         __syncthreads();
+        primed = false;
+        if (t + (int)gridDim.x < ntiles) {      // every stage is free now: request the next tile's first two chunks, then do the epilogue
+            int ni, nj;
+            tile_of(t + (int)gridDim.x, ni, nj);
+            load_chunk(ni * TILE, nj * TILE, 0, 0); cp_async_commit();
+            if (nk > 1) load_chunk(ni * TILE, nj * TILE, 1, 1);
+            cp_async_commit();
+            primed = true;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -1713,7 +1737,7 @@ void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, 
     const int tiles = lower_only ? tm * (tm + 1) / 2 : tm * tn;          // tiles that do work
     int ksplit = 1;
     if (allow_split_k && tiles < g_sms / 2 && K >= 4096) { ksplit = (2 * g_sms + tiles - 1) / tiles; const int maxs = K / 1024; if (ksplit > maxs) ksplit = maxs; if (ksplit < 1) ksplit = 1; }
-    const int gx = tm * tn < g_sms ? tm * tn : g_sms;
+    const int gx = tiles < g_sms ? tiles : g_sms;
     k_gemm_nt_dmma<<<dim3(gx, ksplit), 256, smem, st>>>(m, n, K, A, lda, B, ldb, C, ldc, lower_only, ksplit);
 }
 

@@ -66,49 +66,58 @@ struct Candidate {
     int nbins = 0, sep_tiles = 0, max_bin_tiles = 0, nsep_levels = 0;
 };
 
-Candidate evaluate(const Graph& g, const int* gsize, const std::vector<int>& level, int nlevels, const std::vector<char>& sep_level, int max_bins) {
-    Candidate c;
-    c.is_sep_level = sep_level;
-    c.comp.assign(g.G, -1);
-    int ncomp = 0;
+// connected components of the groups outside the separator levels
+struct Components {
+    std::vector<int> comp;                  // component id per group (-1 = separator)
     std::vector<int> comp_vars;
-    int sep_vars = 0;
+    int sep_vars = 0, nsep_levels = 0;
+};
+void find_components(const Graph& g, const int* gsize, const std::vector<int>& level, const std::vector<char>& sep_level, Components& c, std::vector<int>& queue) {
+    c.comp.assign(g.G, -1);
+    c.comp_vars.clear();
+    c.sep_vars = 0; c.nsep_levels = 0;
+    queue.resize(g.G);
+    int ncomp = 0;
     for (int u = 0; u < g.G; ++u) {
-        if (sep_level[level[u]]) { sep_vars += gsize[u]; continue; }
+        if (sep_level[level[u]]) { c.sep_vars += gsize[u]; continue; }
         if (c.comp[u] >= 0) continue;
-        std::queue<int> q;
-        c.comp[u] = ncomp; q.push(u);
-        int vars = 0;
-        while (!q.empty()) {
-            const int a = q.front(); q.pop();
+        int head = 0, tail = 0, vars = 0;
+        c.comp[u] = ncomp; queue[tail++] = u;
+        while (head < tail) {
+            const int a = queue[head++];
             vars += gsize[a];
-            for (int b : g.nb[a]) if (!sep_level[level[b]] && c.comp[b] < 0) { c.comp[b] = ncomp; q.push(b); }
+            for (int b : g.nb[a]) if (c.comp[b] < 0 && !sep_level[level[b]]) { c.comp[b] = ncomp; queue[tail++] = b; }
         }
-        comp_vars.push_back(vars);
+        c.comp_vars.push_back(vars);
         ++ncomp;
     }
-    for (char s : sep_level) c.nsep_levels += s ? 1 : 0;
+    for (char sl : sep_level) c.nsep_levels += sl ? 1 : 0;
+}
+// longest-processing-time packing of the components into at most max_bins bins, and the chain-length cost of the result
+// (comp / is_sep_level are filled in by the caller for a candidate that wins: they are copies)
+Candidate pack_components(const Components& cs, int max_bins) {
+    Candidate c;
+    const int ncomp = (int)cs.comp_vars.size();
+    c.nsep_levels = cs.nsep_levels;
     if (ncomp < 2) return c;
-    // longest-processing-time packing of the components into at most max_bins bins
     const int nbins = std::min(ncomp, max_bins);
     std::vector<int> order(ncomp);
     std::iota(order.begin(), order.end(), 0);
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return comp_vars[a] != comp_vars[b] ? comp_vars[a] > comp_vars[b] : a < b; });
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return cs.comp_vars[a] != cs.comp_vars[b] ? cs.comp_vars[a] > cs.comp_vars[b] : a < b; });
     std::vector<int> bin_vars(nbins, 0);
     c.bin_of_comp.assign(ncomp, 0);
     for (int ci : order) {
         int best = 0;
         for (int b = 1; b < nbins; ++b) if (bin_vars[b] < bin_vars[best]) best = b;
         c.bin_of_comp[ci] = best;
-        bin_vars[best] += comp_vars[ci];
+        bin_vars[best] += cs.comp_vars[ci];
     }
     c.nbins = nbins;
     int maxb = 0;
     for (int b = 0; b < nbins; ++b) maxb = std::max(maxb, (bin_vars[b] + kTile - 1) / kTile);
     c.max_bin_tiles = maxb;
-    c.sep_tiles = (sep_vars + kTile - 1) / kTile;
+    c.sep_tiles = (cs.sep_vars + kTile - 1) / kTile;
     c.cost = (double)maxb + dense_chain_cost(c.sep_tiles);
-    (void)nlevels;
     return c;
 }
 
@@ -225,6 +234,8 @@ SolveOrder build_solve_order(int G, const int* gsize, const unsigned char* adj) 
         return pl;
     };
     Candidate best, best2;
+    Components comps;
+    std::vector<int> queue;
     const int qmax = std::min(24, (nlevels - 1) / 2);
     for (int q = 1; q <= qmax; ++q) {
         for (int scheme = 0; scheme < 2; ++scheme) {
@@ -239,13 +250,15 @@ SolveOrder build_solve_order(int G, const int* gsize, const unsigned char* adj) 
                 if (!sep[l]) { sep[l] = 1; ++placed; }
             }
             if (placed == 0) continue;
-            Candidate c = evaluate(g, gsize, level, nlevels, sep, kMaxConcurrentParts);
-            if (c.cost < best.cost) best = std::move(c);
+            find_components(g, gsize, level, sep, comps, queue);
+            if (comps.comp_vars.size() < 2) continue;
+            Candidate c = pack_components(comps, kMaxConcurrentParts);
+            if (c.cost < best.cost) { best = std::move(c); best.comp = comps.comp; best.is_sep_level = sep; }
             if (two_level) {
-                Candidate c2 = evaluate(g, gsize, level, nlevels, sep, kMaxConcurrentParts / 2);
+                Candidate c2 = pack_components(comps, kMaxConcurrentParts / 2);
                 if (c2.nbins >= 2) {        // estimate: every bin halves, plus a second-level separator of about two tiles
                     c2.cost = (double)((c2.max_bin_tiles + 1) / 2 + 2) + dense_chain_cost(c2.sep_tiles);
-                    if (c2.cost < best2.cost) best2 = std::move(c2);
+                    if (c2.cost < best2.cost) { best2 = std::move(c2); best2.comp = comps.comp; best2.is_sep_level = sep; }
                 }
             }
         }
