@@ -109,7 +109,8 @@ __device__ long long g_potrf_prof[8];
 constexpr int kPotrfLDT = 65;
 constexpr size_t kPotrfScratchDoubles = 2 * NB * kPotrfLDT;
 template <bool CG>
-__device__ __noinline__ void potrf64_blk_dev(int n, int k0, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk, double* scratch, long long* prof = nullptr) {
+__device__ __noinline__ void potrf64_blk_dev(int n, int k0, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk, double* scratch, long long* prof = nullptr,
+                                             int info_base = 0) {
     long long tp_ = clock64();
 #define POTRF_T(slot) do { if (prof != nullptr && threadIdx.x == 0) { const long long now_ = clock64(); prof[slot] += now_ - tp_; tp_ = now_; } } while (0)
     constexpr int LDT = kPotrfLDT;
@@ -152,7 +153,7 @@ __device__ __noinline__ void potrf64_blk_dev(int n, int k0, double* A, int64_t l
                 if (lane < 16) cb[r] = a[j];                       // scaled a(r, j); rows r < j hold stale upper entries nobody reads
                 __syncwarp();
                 const double d = cb[j];
-                if (lane == 0 && !(d > 0.0) && j0 + j < nb) atomicCAS(info, 0, k0 + j0 + j + 1);
+                if (lane == 0 && !(d > 0.0) && j0 + j < nb) atomicCAS(info, 0, info_base + k0 + j0 + j + 1);
                 const double p2 = __hiloint2double((2046 - ((__double2hiint(d) >> 20) & 0x7ff)) << 20, 0);   // 2^-e
                 const double dm = d * p2;                          // in [1, 2)
                 const double lr = a[j] * p2;
@@ -614,6 +615,7 @@ struct BandSmem {
     int rows[kMaxRowBlocks];
     int m;
 };
+constexpr size_t kBandSmemRequest = sizeof(BandSmem) > 120 * 1024 ? sizeof(BandSmem) : 120 * 1024;
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
@@ -737,7 +739,7 @@ __device__ long long g_band_prof[16];
 // An unpartitioned factorisation is phase 1 with ksep = 0.
 using BandParts = CholPartition;
 __global__ void __cluster_dims__(kBandCluster, 1, 1) __launch_bounds__(256, 1)
-k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk, const BandParts bp, int phase) {
+k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk, const BandParts bp, int phase, int info_base) {
     extern __shared__ __align__(16) unsigned char band_raw[];
     BandSmem& sm = *reinterpret_cast<BandSmem*>(band_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -752,7 +754,7 @@ k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char
     auto update_pair = [&](int ra, int rb, int k) { band_tile_op(sm, n, A, ld, dinv, F, nblk, 1, ra, rb, k, rb >= shared_from); };
 
     static_assert(2 * NB * kBandTS >= (int)kPotrfScratchDoubles, "potrf scratch must fit the two operand tiles");
-    if (rank == 0) potrf64_blk_dev<true>(n, kbeg * NB, A, ld, dinv + (size_t)kbeg * NB * NB, info, F, nblk, sm.A);
+    if (rank == 0) potrf64_blk_dev<true>(n, kbeg * NB, A, ld, dinv + (size_t)kbeg * NB * NB, info, F, nblk, sm.A, nullptr, info_base);
     long long t_prev = clock64();
     for (int k = kbeg; k < kend; ++k) {
         cluster_sync_all();                                   // A: potrf(k) and the updates of step k-1 are visible
@@ -782,7 +784,7 @@ k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char
             if (next_in_list) update_pair(k + 1, k + 1, k);
             __syncthreads();
             BAND_T(4);
-            if (k + 1 < kend) potrf64_blk_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk, sm.A, g_potrf_prof);
+            if (k + 1 < kend) potrf64_blk_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk, sm.A, g_potrf_prof, info_base);
             BAND_T(5);
         } else {
             for (int p = (next_in_list ? 1 : 0) + (rank - 1); p < npairs; p += kBandCluster - 1) {
@@ -1292,6 +1294,124 @@ __global__ void k_axpy1(int n, const double* __restrict__ d, double* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Strip triangular solve  X <- X * L^-T  for a panel of W <= 64*NBLK columns: X is (rows x W), L the W x W lower-triangular factor of
+// the panel's diagonal block, dinv the stored inverses of its 64x64 diagonal blocks.  The launch-per-operation form of this (a 64-wide
+// right solve, then a K = 64 product for the rest of the panel, per block column) is a chain of 2*W/64 launches of ~20 us each that
+// do ~9 us of arithmetic.  Here ONE CTA owns a strip of 48 rows and walks the whole panel: the strip lives in the accumulator
+// registers (warp w holds columns 8w..8w+7 of every 64-column block, 6 row fragments: 96 doubles per thread), the solved block
+// column goes through shared memory as the A operand of the products that follow, and the tiles of L and the diagonal inverses stream
+// through a three-slot cp.async ring in the order they are needed:  D_0, L_10 .. L_(n-1)0, D_1, L_21 ..   48 rows x 126 CTAs cover the
+// 6013 rows of the EKF gain with one wave on 148 SMs.
+constexpr int kStripRF = 6;
+constexpr int kStripRows = 8 * kStripRF;
+constexpr int kStripXS = kStripRows + 4;       // [k][row] stride, 52 = 4 (mod 16): conflict-free fragment loads
+struct StripSmem {
+    double ring[3][NB * kBandTS];              // tiles of L / diagonal inverses, [k][column]
+    double xin[NB * kStripXS];                 // the current block column before its diagonal solve, [k][row]
+    double xout[NB * kStripXS];                // ... and solved
+};
+template <int NBLK>
+__global__ void __launch_bounds__(256, 1) k_strip_trsm(int rows, int W, double* __restrict__ X, int64_t ldx, const double* __restrict__ L, int64_t ldl,
+                                                       const double* __restrict__ dinv) {
+    extern __shared__ __align__(16) unsigned char strip_raw[];
+    StripSmem& sm = *reinterpret_cast<StripSmem*>(strip_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tg = lane & 3;
+    const int r0 = blockIdx.x * kStripRows;
+    const int nblk = (W + NB - 1) / NB;
+    // tile stream: (j, jp) with jp == j the diagonal inverse of block j, jp > j the tile L(jp, j)
+    int ij = 0, ijp = 0;
+    auto issue_next = [&](int slot) {
+        if (ij < nblk) {
+            double* dst = sm.ring[slot];
+            const double* src; int64_t stride; int lim;
+            if (ijp == ij) { src = dinv + (size_t)ij * NB * NB; stride = NB; lim = NB; }
+            else { src = L + (size_t)(ij * NB) * ldl + ijp * NB; stride = ldl; lim = W - ijp * NB; }      // rows of L past W: zero
+            const int cp = (tid & 31) * 2;
+            int bytes = (lim - cp) * 8; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int k = (tid >> 5) + 8 * it;
+                cp_async16(dst + k * kBandTS + cp, bytes > 0 ? src + (size_t)k * stride + cp : src, bytes);
+            }
+            if (++ijp >= nblk) { ++ij; ijp = ij; }
+        }
+        cp_async_commit();
+    };
+    double acc[kStripRF][NBLK][2];
+#pragma unroll
+    for (int jb = 0; jb < NBLK; ++jb)
+#pragma unroll
+        for (int i = 0; i < kStripRF; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = r0 + 8 * i + g, col = jb * NB + 8 * warp + 2 * tg + e;
+                acc[i][jb][e] = (row < rows && col < W) ? X[(size_t)col * ldx + row] : 0.0;
+            }
+    issue_next(0);
+    issue_next(1);
+    int t = 0;
+#pragma unroll
+    for (int j = 0; j < NBLK; ++j) {
+        if (j >= nblk) break;
+        // block column j leaves the registers: operand of its own diagonal solve
+#pragma unroll
+        for (int i = 0; i < kStripRF; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) { sm.xin[(8 * warp + 2 * tg + e) * kStripXS + 8 * i + g] = acc[i][j][e]; acc[i][j][e] = 0.0; }
+        cp_async_wait<1>();
+        __syncthreads();                               // tile t (= D_j) has landed, xin is complete, every warp is done with tile t-1
+        issue_next((t + 2) % 3);
+        {
+            const double* D = sm.ring[t % 3];
+#pragma unroll 2
+            for (int ks = 0; ks < NB; ks += 4) {       // X_j(r, c) = sum_k xin(r, k) Linv(c, k)
+                const double bf = D[(ks + tg) * kBandTS + 8 * warp + g];
+#pragma unroll
+                for (int i = 0; i < kStripRF; ++i) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], sm.xin[(ks + tg) * kStripXS + 8 * i + g], bf);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kStripRF; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int row = r0 + 8 * i + g, col = j * NB + 8 * warp + 2 * tg + e;
+                sm.xout[(8 * warp + 2 * tg + e) * kStripXS + 8 * i + g] = -acc[i][j][e];      // negated: the products below subtract
+                if (row < rows && col < W) X[(size_t)col * ldx + row] = acc[i][j][e];
+            }
+        ++t;
+        __syncthreads();
+#pragma unroll
+        for (int jp = j + 1; jp < NBLK; ++jp) {
+            if (jp >= nblk) break;
+            cp_async_wait<1>();
+            __syncthreads();
+            issue_next((t + 2) % 3);
+            const double* T = sm.ring[t % 3];
+#pragma unroll 2
+            for (int ks = 0; ks < NB; ks += 4) {       // X_jp(r, c) -= sum_k X_j(r, k) L(jp*64 + c, j*64 + k)
+                const double bf = T[(ks + tg) * kBandTS + 8 * warp + g];
+#pragma unroll
+                for (int i = 0; i < kStripRF; ++i) dmma_m8n8k4(acc[i][jp][0], acc[i][jp][1], sm.xout[(ks + tg) * kStripXS + 8 * i + g], bf);
+            }
+            ++t;
+        }
+    }
+    cp_async_wait<0>();
+}
+void launch_strip_trsm(cudaStream_t st, int rows, int W, double* X, int64_t ldx, const double* L, int64_t ldl, const double* dinv) {
+    if (rows <= 0 || W <= 0) return;
+    static PerDeviceOnce once;
+    if (once.first()) {
+        cudaFuncSetAttribute(k_strip_trsm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StripSmem));
+        cudaFuncSetAttribute(k_strip_trsm<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StripSmem));
+    }
+    const int grid = (rows + kStripRows - 1) / kStripRows;
+    if (W <= 4 * NB) k_strip_trsm<4><<<grid, 256, sizeof(StripSmem), st>>>(rows, W, X, ldx, L, ldl, dinv);
+    else k_strip_trsm<8><<<grid, 256, sizeof(StripSmem), st>>>(rows, W, X, ldx, L, ldl, dinv);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 constexpr size_t kPanelSolveSmem = sizeof(double) * (NB * NB + NB * PS_ROWS);
 
 static int g_coop_blocks = 0;
@@ -1321,16 +1441,21 @@ static void set_attrs_once() {
     g_coop_blocks = sms * (per_sm < 1 ? 1 : 1);   // one CTA per SM: fewer spinners, same bandwidth
 }
 
-// Workspace layout (doubles): [dinv: nblk*64*64][ybuf: nblk*64][flags: nblk ints, padded][F: nblk*nblk bytes, padded][op lists: 2 x 7*nblk ints]
+// Workspace layout (doubles): [dinv: nblk*64*64][ybuf: nblk*64][flags: nblk ints, padded][F: nblk*nblk bytes, padded][op lists: 2 x 7*nblk ints][tile pattern of one panel's diagonal block: 64 bytes]
+constexpr size_t kFPanelBytes = 64;     // (PB / NB)^2 = 16 used
 static inline int chol_nblk(int n) { return (n + NB - 1) / NB; }
 size_t dense_cholesky_dinv_doubles(int n) {
     const size_t nblk = (size_t)chol_nblk(n);
-    return nblk * NB * NB + nblk * NB + (nblk + 1) / 2 + 8 + (nblk * nblk + 7) / 8 + 8 + (size_t)(kTrsvSparseFill + 1) * nblk + 8;   // the +8 after the flags also holds the tile / op counters
+    return nblk * NB * NB + nblk * NB + (nblk + 1) / 2 + 8 + (nblk * nblk + 7) / 8 + 8 + (size_t)(kTrsvSparseFill + 1) * nblk + 8 + kFPanelBytes / 8;   // the +8 after the flags also holds the tile / op counters
 }
 static inline double* ws_ybuf(double* ws, int n) { return ws + (size_t)chol_nblk(n) * NB * NB; }
 static inline int* ws_flags(double* ws, int n) { return (int*)(ws_ybuf(ws, n) + (size_t)chol_nblk(n) * NB); }
 static inline int* ws_nzt(double* ws, int n) { return ws_flags(ws, n) + chol_nblk(n) + 1; }
 static inline unsigned char* ws_F(double* ws, int n) { return (unsigned char*)(ws_ybuf(ws, n) + (size_t)chol_nblk(n) * NB + (chol_nblk(n) + 1) / 2 + 8); }
+static inline unsigned char* ws_fpanel(double* ws, int n) {
+    const size_t nblk = (size_t)chol_nblk(n);
+    return (unsigned char*)(ws_ybuf(ws, n) + nblk * NB + (nblk + 1) / 2 + 8 + (nblk * nblk + 7) / 8 + 8 + ((kTrsvSparseFill + 1) * nblk * 2 + 1) / 2 + 8);
+}
 static inline int* ws_list(double* ws, int n, int backward) {
     const size_t nblk = (size_t)chol_nblk(n);
     int* base = (int*)(ws_ybuf(ws, n) + nblk * NB + (nblk + 1) / 2 + 8 + (nblk * nblk + 7) / 8 + 8);
@@ -1352,7 +1477,42 @@ void dense_cholesky_profile_report() {
     for (int i = 0; i < 4; ++i) { g_prof_ms[i] = 0; g_prof_n[i] = 0; }
 }
 
+static bool ensure_band_attr();
+// Panel-wise dense factorisation (default): per 256-column panel THREE dependent steps instead of 4 x (potrf, right solve, in-panel
+// update) + trailing update --
+//   A  the 256 x 256 diagonal block is factored by one cluster (k_band_chol on the block as a 4-tile dense system: potrf look-ahead,
+//      tile solves and updates spread over 8 CTAs, no launch in between);
+//   B  the rows below are solved against it in one launch (k_strip_trsm, 48-row strips that walk the whole panel);
+//   C  trailing update with K = 256 (k_syrk_dmma).
+// Every tile of a dense factor is non-zero: F is set to ones (the substitutions and k_syrk_dmma read it).
+static int64_t enqueue_factor_panels(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
+    int64_t launches = 0;
+    const int nblk = chol_nblk(n);
+    unsigned char* F = ws_F(ws, n);
+    unsigned char* Fp = ws_fpanel(ws, n);
+    cudaMemsetAsync(info_dev, 0, sizeof(int), st);
+    cudaMemsetAsync(ws_flags(ws, n), 0, sizeof(int) * nblk, st);
+    cudaMemsetAsync(F, 1, (size_t)nblk * nblk, st);
+    cudaMemsetAsync(Fp, 1, kFPanelBytes, st);
+    CholPartition whole;
+    for (int p0 = 0; p0 < n; p0 += PB) {
+        const int pend = min(n, p0 + PB), W = pend - p0;
+        double* di = ws + (size_t)(p0 / NB) * NB * NB;
+        double* App = A + (size_t)p0 * ld + p0;
+        k_band_chol<<<kBandCluster, 256, kBandSmemRequest, st>>>(W, App, ld, di, info_dev, Fp, chol_nblk(W), whole, 1, p0); ++launches;
+        if (pend < n) {
+            launch_strip_trsm(st, n - pend, W, A + (size_t)p0 * ld + pend, ld, App, ld, di); ++launches;
+            launch_syrk(st, n, A, ld, p0, W, pend, n, F, nblk); launches += 2;
+        }
+    }
+    k_build_trsv_lists<<<1, 1024, 0, st>>>(n, nblk, F, ws_nzt(ws, n), ws_list(ws, n, 0), ws_list(ws, n, 1)); ++launches;
+    return launches;
+}
+
 static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
+    static int panels = -1;      // SRK_CHOL_DENSE=steps: the launch-per-64-columns form (development aid; also the profiled one)
+    if (panels < 0) { const char* e = getenv("SRK_CHOL_DENSE"); panels = (e != nullptr && e[0] == 's') ? 0 : 1; }
+    if (panels && !g_prof && n >= 2 * NB && ((uintptr_t)A & 15) == 0 && (ld & 1) == 0 && ensure_band_attr()) return enqueue_factor_panels(st, n, A, ld, ws, info_dev);
     int64_t launches = 0;
     const int nblk = chol_nblk(n);
     unsigned char* F = ws_F(ws, n);
@@ -1387,7 +1547,13 @@ static thread_local FactorGraph g_fg;   // per host thread: a handle is driven b
 
 // Sparse-factor path: tile pattern of the input, then (when it is sparse enough) the single-cluster kernel.  Returns the number of
 // launches, or 0 when the matrix is not sparse and the launch-per-operation path has to run.
-constexpr size_t kBandSmemRequest = sizeof(BandSmem) > 120 * 1024 ? sizeof(BandSmem) : 120 * 1024;
+static bool ensure_band_attr() {
+    static PerDeviceOnce once;
+    if (once.first()) {
+        if (cudaFuncSetAttribute(k_band_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandSmemRequest) != cudaSuccess) { cudaGetLastError(); once.forget(); return false; }
+    }
+    return true;
+}
 // the second level of a two-level partition seen as a one-level one: parts = the second-level separators, separator = the top one
 static CholPartition mid_level(const CholPartition& p) {
     CholPartition m;
@@ -1402,10 +1568,7 @@ static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, do
     static int force = -1;    // SRK_CHOL_PATH=dense disables the sparse path, =band forces it (development aid)
     if (force < 0) { const char* e = getenv("SRK_CHOL_PATH"); force = e == nullptr ? 0 : (e[0] == 'd' ? 1 : (e[0] == 'b' ? 2 : 0)); }
     if (force == 1) return 0;
-    static PerDeviceOnce once;
-    if (once.first()) {
-        if (cudaFuncSetAttribute(k_band_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBandSmemRequest) != cudaSuccess) { cudaGetLastError(); once.forget(); return 0; }
-    }
+    if (!ensure_band_attr()) return 0;
     // The kernel is a latency chain: two CTAs of different clusters on one SM would take turns on every step.  Asking for more than half
     // of the SM's shared memory keeps it at one CTA per SM (SRK_BAND_SMEM_PAD=0: the bare request, development aid).
     static int pad = -1;
@@ -1429,19 +1592,19 @@ static int64_t try_band_factor(cudaStream_t st, int n, double* A, int64_t ld, do
     const int max_fill = (part != nullptr && part->nparts > 0) ? 2 * kBandMaxFill : kBandMaxFill;   // a partitioned pattern carries the separator rows as well
     if (h < 0 || (force != 2 && h > max_fill * nblk)) return 0;
     if (part != nullptr && part->nparts > 0) {
-        k_band_chol<<<kBandCluster * part->nparts, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 0);
+        k_band_chol<<<kBandCluster * part->nparts, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, *part, 0, 0);
         CholPartition top = *part;
         if (part->nmids > 0) {      // second-level separators: the same kernel with their ranges as the parts and the top separator as the shared block
             const CholPartition mids = mid_level(*part);
-            k_band_chol<<<kBandCluster * mids.nparts, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, mids, 0);
+            k_band_chol<<<kBandCluster * mids.nparts, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, mids, 0, 0);
             top.ksep = part->msep;
             nl += 1;
         }
-        k_band_chol<<<kBandCluster, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, top, 1);
+        k_band_chol<<<kBandCluster, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, top, 1, 0);
         nl += 2;
     } else {
         CholPartition whole;
-        k_band_chol<<<kBandCluster, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, whole, 1);
+        k_band_chol<<<kBandCluster, 256, band_smem, st>>>(n, A, ld, ws, info_dev, F, nblk, whole, 1, 0);
         nl += 1;
     }
     if (cudaGetLastError() != cudaSuccess) return 0;

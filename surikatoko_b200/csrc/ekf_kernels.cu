@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/srk/ekf_c_api.h"
@@ -612,10 +613,18 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
         // right of the panel with K = 256: a K = 64 update of the whole trailing matrix per block column re-reads and re-writes PHt
         // m2 / 64 times (12 GB at n = 6013, 2m = 4000 -- memory-bound at 14 TFLOP/s); with the panel the trailing traffic drops fourfold.
         EScope sc(e, E_TRSM);
-        constexpr int kPanel = 512;
+        // inside a panel: ONE launch (48-row strips that walk the whole panel, chol_kernels.cu k_strip_trsm) instead of a right solve + a
+        // K = 64 product per block column.  SRK_EKF_TRSM_PANEL: panel width (256 / 512), 0 = the launch-per-block-column form (development aid)
+        static int panel_env = -1;
+        if (panel_env < 0) { const char* pe = getenv("SRK_EKF_TRSM_PANEL"); panel_env = pe != nullptr ? atoi(pe) : 512; if (panel_env != 0 && panel_env != 256 && panel_env != 512) panel_env = 512; }
+        const int kPanel = panel_env == 0 ? 512 : panel_env;
         for (int p0 = 0; p0 < m2; p0 += kPanel) {
             const int pend = m2 < p0 + kPanel ? m2 : p0 + kPanel;
-            for (int k0 = p0; k0 < pend; k0 += 64) {
+            if (panel_env != 0) {
+                srk::launch_strip_trsm(st, n, pend - p0, PHt + (size_t)p0 * ldz, ldz, S + (size_t)p0 * lds + p0, lds, srk::dense_cholesky_dinv_block(ws, p0 / 64));
+                e.launches += 1;
+            }
+            for (int k0 = p0; k0 < pend && panel_env == 0; k0 += 64) {
                 srk::launch_block_right_solve(st, n, PHt + (size_t)k0 * ldz, ldz, srk::dense_cholesky_dinv_block(ws, k0 / 64), m2 - k0);   // the last block may be ragged
                 e.launches += 1;
                 const int rest = pend - (k0 + 64);

@@ -76,6 +76,9 @@ inline const double* dense_cholesky_dinv_block(const double* ws, int kb) { retur
 // allow_split_k: few output tiles and a long contraction -> the K range is split over blockIdx.y and the slices are added atomically
 void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only,
                          int allow_split_k = 0);
+// X (rows x W, W <= 512) <- X * L^-T with L the W x W lower-triangular factor at L (ldl) and dinv the stored inverses of its 64x64 diagonal
+// blocks (dense_cholesky_dinv_block of the first one): the whole panel in one launch, 48-row strips.  X, L 16-byte aligned, ldx, ldl even.
+void launch_strip_trsm(cudaStream_t st, int rows, int W, double* X, int64_t ldx, const double* L, int64_t ldl, const double* dinv);
 // X (rows x 64 at A, lda) <- X * Linv^T with Linv a column-major 64x64 lower-triangular inverse (right-side triangular solve of one block column)
 // ncols: how many of the 64 columns exist (the caller's matrix may end inside the last block)
 void launch_block_right_solve(cudaStream_t st, int rows, double* A, int64_t lda, const double* dinv_block, int ncols = 64);

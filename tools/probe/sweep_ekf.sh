@@ -1,0 +1,14 @@
+#!/bin/bash
+# development aid: EKF frame time (configs[3]) against the factorisation / TRSM switches
+run() {
+  env "$@" timeout 200 python bench.py --workload c4 --steps 5 --warmup 3 --no-others --no-cpu 2>/tmp/sweep.err > /tmp/sweep.json || tail -3 /tmp/sweep.err
+  python - "$*" <<'P'
+import json, sys
+b = json.loads(open("/tmp/sweep.json").read().strip().splitlines()[-1]); k = b["kernels"]
+print(sys.argv[1], round(b["ms_per_step"], 3), {n: round(v["avg_ms"], 3) for n, v in k.items() if "avg_ms" in v})
+P
+}
+run SRK_X=0
+run SRK_EKF_TRSM_PANEL=512
+run SRK_EKF_TRSM_PANEL=0
+run SRK_CHOL_DENSE=steps
