@@ -1762,11 +1762,12 @@ int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t
 // read in [k][row] order straight from the column-major matrices, 128x128 tiles, persistent CTAs over the tile list.
 // ksplit > 1: blockIdx.y owns the K slice [y * Kper, (y + 1) * Kper) and ADDS its product atomically (a short-and-wide product -- few
 // output tiles, long contraction -- would otherwise keep only a handful of SMs busy)
+constexpr int kGemmKC = 16;      // K chunk per stage of the general product (32 halves the barriers but measured no faster: SYRK 5.04 -> 4.99 ms, TRSM 4.28 -> 4.35)
 __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot, const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
                                                          double* __restrict__ C, int64_t ldc, int lower_only, int ksplit) {
-    constexpr int TILE = 128, SLD = TILE + 4, NJ = 8;
+    constexpr int TILE = 128, SLD = TILE + 4, NJ = 8, KC = kGemmKC;
     if (ksplit > 1) {
-        const int Kper = (((Ktot + ksplit - 1) / ksplit) + KC - 1) / KC * KC;
+        const int Kper = (((Ktot + ksplit - 1) / ksplit) + kGemmKC - 1) / kGemmKC * kGemmKC;
         const int kb = (int)blockIdx.y * Kper;
         if (kb >= Ktot) return;
         A += (size_t)kb * lda; B += (size_t)kb * ldb;
@@ -1794,7 +1795,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
     };
     auto load_chunk = [&](int i0, int j0, int stage, int kc) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < KC / 4; ++q) {
             const int v = tid + 256 * q;
             const int k = v >> 6, rp = (v & 63) * 2;
             const int kk = kc * KC + k;
@@ -1893,7 +1894,7 @@ void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, 
                          int allow_split_k) {
     set_attrs_once();
     static PerDeviceOnce once;
-    const size_t smem = sizeof(double) * (2 * STAGES * KC * (128 + 4));
+    const size_t smem = sizeof(double) * (2 * STAGES * kGemmKC * (128 + 4));
     if (once.first()) cudaFuncSetAttribute(k_gemm_nt_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (m <= 0 || n <= 0 || K <= 0) return;
     const int tm = (m + 127) / 128, tn = (n + 127) / 128;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# development aid: EKF frame time (configs[3]) against the factorisation / TRSM switches
+# development aid: EKF frame time (configs[3]) against the factorisation / TRSM switches given as arguments (VAR=value ...)
 run() {
   env "$@" timeout 200 python bench.py --workload c4 --steps 5 --warmup 3 --no-others --no-cpu 2>/tmp/sweep.err > /tmp/sweep.json || tail -3 /tmp/sweep.err
   python - "$*" <<'P'
@@ -9,6 +9,4 @@ print(sys.argv[1], round(b["ms_per_step"], 3), {n: round(v["avg_ms"], 3) for n, 
 P
 }
 run SRK_X=0
-run SRK_EKF_TRSM_PANEL=512
-run SRK_EKF_TRSM_PANEL=0
-run SRK_CHOL_DENSE=steps
+for v in "$@"; do run $v; done
