@@ -653,7 +653,8 @@ def measure_ekf(args, steps, warmup, with_cpu=True, with_ransac=True):
     if rank != 0:
         return None
     f64_peak = fp64_gemm_peak(torch, dev)
-    flops = {"chol": m2 ** 3 / 3.0, "trsm": float(n) * m2 * m2, "syrk": float(n) * n * m2}   # the algorithmic minimum of the chain
+    flops = {"chol": m2 ** 3 / 3.0, "trsm": float(n) * m2 * m2, "syrk": float(n) * n * m2,    # the algorithmic minimum of the chain
+             "chol_trsm": m2 ** 3 / 3.0 + float(n) * m2 * m2}                                 # factorisation and gain TRSM side by side on two streams
     kernels = {}
     for fam, t in tm.items():
         if not t["count"]:

@@ -1509,6 +1509,54 @@ static int64_t enqueue_factor_panels(cudaStream_t st, int n, double* A, int64_t 
     return launches;
 }
 
+// Factorisation of the m x m matrix S on the stream `hi` with the triangular solve Z <- Z * L^-T (Z: rows x m) following it panel by panel on
+// the stream `lo` (EKF: S = innovation covariance, Z = P H^T).  The factorisation is a latency chain that leaves most SMs idle (one cluster
+// for the diagonal block, <= 78 CTAs for the strip solve), the solve is throughput work on every SM and needs of L only the panels that are
+// already final: run one after the other they cost 3.4 + 4.3 ms at m = 4000, rows = 6013.  `hi` should have a higher priority than `lo`; the
+// products of the solve are launched one CTA per tile so that the chain's kernels get SMs at tile granularity.  ev: >= m / 256 + 2 events.
+// On return `lo` has waited for everything enqueued on `hi`.
+int64_t dense_cholesky_factor_trsm(cudaStream_t hi, cudaStream_t lo, int m, double* S, int64_t lds, double* ws, int* info_dev, int rows, double* Z, int64_t ldz,
+                                   cudaEvent_t* ev, int nev) {
+    set_attrs_once();
+    epoch_reset(ws);
+    const int npanel = (m + PB - 1) / PB;
+    if (nev < npanel + 2 || !ensure_band_attr() || ((uintptr_t)S & 15) != 0 || (lds & 1) != 0) return -1;
+    int64_t launches = 0;
+    const int nblk = chol_nblk(m);
+    unsigned char* F = ws_F(ws, m);
+    unsigned char* Fp = ws_fpanel(ws, m);
+    cudaEventRecord(ev[npanel], lo);                       // S and Z are produced on `lo`
+    cudaStreamWaitEvent(hi, ev[npanel], 0);
+    cudaMemsetAsync(info_dev, 0, sizeof(int), hi);
+    cudaMemsetAsync(ws_flags(ws, m), 0, sizeof(int) * nblk, hi);
+    cudaMemsetAsync(F, 1, (size_t)nblk * nblk, hi);
+    cudaMemsetAsync(Fp, 1, kFPanelBytes, hi);
+    CholPartition whole;
+    constexpr int kZPanel = 2 * PB;                        // the solve walks 512-column panels = two panels of the factorisation
+    for (int p0 = 0, p = 0; p0 < m; p0 += PB, ++p) {
+        const int pend = min(m, p0 + PB), W = pend - p0;
+        double* di = ws + (size_t)(p0 / NB) * NB * NB;
+        double* App = S + (size_t)p0 * lds + p0;
+        k_band_chol<<<kBandCluster, 256, kBandSmemRequest, hi>>>(W, App, lds, di, info_dev, Fp, chol_nblk(W), whole, 1, p0); ++launches;
+        if (pend < m) { launch_strip_trsm(hi, m - pend, W, S + (size_t)p0 * lds + pend, lds, App, lds, di); ++launches; }
+        cudaEventRecord(ev[p], hi);                        // columns [p0, pend) of L are final
+        if (pend < m) { launch_syrk(hi, m, S, lds, p0, W, pend, m, F, nblk); launches += 2; }
+        if ((p & 1) == 1 || pend == m) {
+            const int q0 = (p0 / kZPanel) * kZPanel;
+            cudaStreamWaitEvent(lo, ev[p], 0);
+            launch_strip_trsm(lo, rows, pend - q0, Z + (size_t)q0 * ldz, ldz, S + (size_t)q0 * lds + q0, lds, ws + (size_t)(q0 / NB) * NB * NB); ++launches;
+            if (pend < m) {
+                launch_gemm_nt_dmma(lo, rows, m - pend, pend - q0, Z + (size_t)q0 * ldz, ldz, S + (size_t)q0 * lds + pend, lds, Z + (size_t)pend * ldz, ldz, 0, 0, 1);
+                ++launches;
+            }
+        }
+    }
+    k_build_trsv_lists<<<1, 1024, 0, hi>>>(m, nblk, F, ws_nzt(ws, m), ws_list(ws, m, 0), ws_list(ws, m, 1)); ++launches;
+    cudaEventRecord(ev[npanel + 1], hi);
+    cudaStreamWaitEvent(lo, ev[npanel + 1], 0);
+    return launches;
+}
+
 static int64_t enqueue_factor(cudaStream_t st, int n, double* A, int64_t ld, double* ws, int* info_dev) {
     static int panels = -1;      // SRK_CHOL_DENSE=steps: the launch-per-64-columns form (development aid; also the profiled one)
     if (panels < 0) { const char* e = getenv("SRK_CHOL_DENSE"); panels = (e != nullptr && e[0] == 's') ? 0 : 1; }
@@ -1891,7 +1939,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
 }
 // the operands need 16-byte aligned columns: lda, ldb even and base pointers 16-byte aligned (the callers guarantee it)
 void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only,
-                         int allow_split_k) {
+                         int allow_split_k, int cta_per_tile) {
     set_attrs_once();
     static PerDeviceOnce once;
     const size_t smem = sizeof(double) * (2 * STAGES * kGemmKC * (128 + 4));
@@ -1901,7 +1949,9 @@ void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, 
     const int tiles = lower_only ? tm * (tm + 1) / 2 : tm * tn;          // tiles that do work
     int ksplit = 1;
     if (allow_split_k && tiles < g_sms / 2 && K >= 4096) { ksplit = (2 * g_sms + tiles - 1) / tiles; const int maxs = K / 1024; if (ksplit > maxs) ksplit = maxs; if (ksplit < 1) ksplit = 1; }
-    const int gx = tiles < g_sms ? tiles : g_sms;
+    // cta_per_tile: one CTA per tile instead of persistent CTAs -- an SM is handed back after every tile, so the kernels of a
+    // higher-priority stream (the factorisation chain that runs beside the EKF gain) get in at tile granularity
+    const int gx = (cta_per_tile || tiles < g_sms) ? tiles : g_sms;
     k_gemm_nt_dmma<<<dim3(gx, ksplit), 256, smem, st>>>(m, n, K, A, lda, B, ldb, C, ldc, lower_only, ksplit);
 }
 

@@ -516,12 +516,14 @@ struct DBuf {
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
-const char* kEkfFam[] = {"pht", "innov", "chol", "trsm", "syrk", "state", "predict", "ransac"};
-enum { E_PHT = 0, E_INNOV, E_CHOL, E_TRSM, E_SYRK, E_STATE, E_PREDICT, E_RANSAC, E_COUNT };
+const char* kEkfFam[] = {"pht", "innov", "chol", "trsm", "syrk", "state", "predict", "ransac", "chol_trsm"};
+enum { E_PHT = 0, E_INNOV, E_CHOL, E_TRSM, E_SYRK, E_STATE, E_PREDICT, E_RANSAC, E_CHOL_TRSM, E_COUNT };
 
 struct Ekf {
     int device = 0;
     cudaStream_t own = nullptr, st = nullptr;
+    cudaStream_t hi = nullptr;       // high-priority stream of the factorisation chain while the gain TRSM runs beside it (update_resident)
+    std::vector<cudaEvent_t> evs;
     int64_t n = 0;
     DBuf P, x, PHt, S, ws, w, Hcam, Hpt, off, z, h, aux, tmp, neg, info, small;
     DBuf r_hyp, r_support, r_bits;   // 1-point RANSAC scoring: per-hypothesis vectors, support counts, inlier bit rows
@@ -530,8 +532,8 @@ struct Ekf {
     int64_t launches = 0;
     bool timing = false;
     std::vector<cudaEvent_t> pend[E_COUNT];
-    double total[E_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int64_t count[E_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double total[E_COUNT] = {};
+    int64_t count[E_COUNT] = {};
 };
 struct EScope {
     Ekf& e; int f; cudaEvent_t b = nullptr;
@@ -593,7 +595,33 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
         else k_ekf_innov<6><<<grid, 256, 0, st>>>(n, m2, PHt, e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(), meas_var, S, lds, ldz);
         e.launches += 1;
     }
+    // Factorisation of S and the gain TRSM Z = PHt * L^-T side by side (chol_kernels.cu dense_cholesky_factor_trsm): the factorisation is a
+    // latency chain on a handful of SMs, the TRSM needs of L only the panels that are already final.  Z overwrites PHt, which is scratch,
+    // so the positive-definiteness check below may come after it.  SRK_EKF_OVERLAP=0: one after the other (development aid).
+    bool overlapped = false;
     {
+        static int overlap_env = -1;
+        if (overlap_env < 0) { const char* oe = getenv("SRK_EKF_OVERLAP"); overlap_env = (oe != nullptr && oe[0] == '0') ? 0 : 1; }
+        if (overlap_env && m2 >= 1024) {
+            if (e.hi == nullptr) {
+                int least = 0, greatest = 0;
+                cudaDeviceGetStreamPriorityRange(&least, &greatest);
+                if (cudaStreamCreateWithPriority(&e.hi, cudaStreamNonBlocking, greatest) != cudaSuccess) { cudaGetLastError(); e.hi = nullptr; }
+            }
+            const size_t need = (size_t)m2 / 256 + 4;
+            while (e.hi != nullptr && e.evs.size() < need) {
+                cudaEvent_t ev = nullptr;
+                if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); break; }
+                e.evs.push_back(ev);
+            }
+            if (e.hi != nullptr && e.evs.size() >= need) {
+                EScope sc(e, E_CHOL_TRSM);
+                const int64_t nl = srk::dense_cholesky_factor_trsm(e.hi, st, m2, S, lds, ws, e.info.as<int>(), n, PHt, ldz, e.evs.data(), (int)e.evs.size());
+                if (nl >= 0) { e.launches += nl; overlapped = true; }
+            }
+        }
+    }
+    if (!overlapped) {
         EScope sc(e, E_CHOL);
         e.launches += srk::dense_cholesky_factor(st, m2, S, lds, ws, e.info.as<int>());
     }
@@ -609,7 +637,7 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
             return SRK_E_NOT_POSDEF;
         }
     }
-    {   // Z = PHt * L^-T; Z overwrites PHt.  Right-looking over 64-column blocks INSIDE a 256-column panel, then ONE update of everything
+    if (!overlapped) {   // Z = PHt * L^-T; Z overwrites PHt.  Right-looking over 64-column blocks INSIDE a 256-column panel, then ONE update of everything
         // right of the panel with K = 256: a K = 64 update of the whole trailing matrix per block column re-reads and re-writes PHt
         // m2 / 64 times (12 GB at n = 6013, 2m = 4000 -- memory-bound at 14 TFLOP/s); with the panel the trailing traffic drops fourfold.
         EScope sc(e, E_TRSM);
@@ -1037,6 +1065,8 @@ void srk_ekf_destroy(void* h) {
     Ekf* e = (Ekf*)h;
     cudaSetDevice(e->device);
     ekf_resolve(*e);
+    if (e->hi != nullptr) cudaStreamDestroy(e->hi);
+    for (cudaEvent_t ev : e->evs) cudaEventDestroy(ev);
     if (e->own != nullptr) cudaStreamDestroy(e->own);
     delete e;
 }

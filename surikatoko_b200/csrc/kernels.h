@@ -75,7 +75,12 @@ inline const double* dense_cholesky_dinv_block(const double* ws, int kb) { retur
 // C (m x n, ldc) -= A (m x K, lda) * B (n x K, ldb)^T, all column-major, DMMA 128x128 tiles; lower_only: only tiles / entries with row >= col.
 // allow_split_k: few output tiles and a long contraction -> the K range is split over blockIdx.y and the slices are added atomically
 void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int lower_only,
-                         int allow_split_k = 0);
+                         int allow_split_k = 0, int cta_per_tile = 0);
+// Factor S (m x m, lower, as dense_cholesky_factor) on stream `hi` while Z (rows x m) <- Z * L^-T follows panel by panel on stream `lo`;
+// `lo` must be the stream that produced S and Z, and has waited for all of `hi` on return.  ev: at least m / 256 + 3 events owned by the
+// caller.  Returns the number of launches, -1 when the arguments do not fit (the caller then runs the two steps one after the other).
+int64_t dense_cholesky_factor_trsm(cudaStream_t hi, cudaStream_t lo, int m, double* S, int64_t lds, double* ws, int* info_dev, int rows, double* Z, int64_t ldz,
+                                   cudaEvent_t* ev, int nev);
 // X (rows x W, W <= 512) <- X * L^-T with L the W x W lower-triangular factor at L (ldl) and dinv the stored inverses of its 64x64 diagonal
 // blocks (dense_cholesky_dinv_block of the first one): the whole panel in one launch, 48-row strips.  X, L 16-byte aligned, ldx, ldl even.
 void launch_strip_trsm(cudaStream_t st, int rows, int W, double* X, int64_t ldx, const double* L, int64_t ldl, const double* dinv);

@@ -10,7 +10,7 @@ import numpy as np
 from .capi import SrkError, load_library
 
 CAM = 13
-EKF_FAMILIES = ("pht", "innov", "chol", "trsm", "syrk", "state", "predict", "ransac")
+EKF_FAMILIES = ("pht", "innov", "chol", "trsm", "syrk", "state", "predict", "ransac", "chol_trsm")
 
 
 def _lib():
