@@ -72,7 +72,7 @@ def test_config2_thousand_camera_system_matches_sparse_oracle(oracle, engine):
     assert engine.bind(to_problem(pr))
     got = engine.debug_derivs_and_solve(c=c)
     st = engine.solve_stats()
-    assert st["n_f"] == 9993 and st["parts"] >= 2
+    assert st["n_f"] == 9993 and st["parts"] >= 2 and st["mid_separators"] >= 2      # the two-level nested-dissection order is on this path
     for k in ("gradE", "E", "G", "F"):
         assert relerr(got[k], ref[k]) < 1e-11, k
     assert np.array_equal(got["skipped"], ref["skipped"])
