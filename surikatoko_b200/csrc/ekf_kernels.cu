@@ -69,9 +69,15 @@ __global__ void __launch_bounds__(256) k_ekf_innov(int n, int m2, const double* 
     if (i == j) acc += meas_var;
     Sm[(size_t)j * lds + i] = acc;
 }
-__global__ void k_ekf_innovation_vec(int m2, const double* __restrict__ z, const double* __restrict__ h, double* __restrict__ w) {
+// w = z - h, written as ROW n of P H^T (element i at w[i * ldw]): the gain TRSM Z = [P H^T; w^T] L^-T then leaves L^-1 w in that row, and the
+// forward substitution of the state update (a latency chain of 2m / 64 blocks, 0.35 ms at 2m = 4000) is not needed
+__global__ void k_ekf_innovation_vec(int m2, const double* __restrict__ z, const double* __restrict__ h, double* __restrict__ w, int64_t ldw) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < m2) w[i] = z[i] - h[i];
+    if (i < m2) w[(size_t)i * ldw] = z[i] - h[i];
+}
+__global__ void k_ekf_take_row(int m2, const double* __restrict__ row, int64_t ld, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m2) out[i] = row[(size_t)i * ld];
 }
 // x += Z w  (Z: n x m2 column-major); one warp per 32 rows, columns strided over the CTA's warps, fixed combination order
 __global__ void __launch_bounds__(256) k_ekf_state(int n, int m2, const double* __restrict__ Z, int64_t ldz, const double* __restrict__ w, double* __restrict__ x) {
@@ -566,7 +572,8 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
     EKF_CUDA(cudaSetDevice(e.device));
     const int n = (int)e.n, m2 = (int)(2 * m);
     const int64_t lds = ((int64_t)m2 + 7) & ~(int64_t)7;
-    const int64_t ldz = ((int64_t)n + 7) & ~(int64_t)7;   // 16-byte aligned columns for the cp.async operand loads
+    const int nz = n + 1;                                  // rows of the TRSM: P H^T and, as row n, the innovation z - h
+    const int64_t ldz = ((int64_t)nz + 7) & ~(int64_t)7;  // 16-byte aligned columns for the cp.async operand loads
     cudaStream_t st = e.st;
     EKF_CUDA(e.PHt.ensure(sizeof(double) * (size_t)ldz * m2 + 64)); EKF_CUDA(e.S.ensure(sizeof(double) * (size_t)lds * m2));
     EKF_CUDA(e.ws.ensure(sizeof(double) * srk::dense_cholesky_dinv_doubles(m2))); EKF_CUDA(e.w.ensure(sizeof(double) * (size_t)lds));
@@ -595,6 +602,8 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
         else k_ekf_innov<6><<<grid, 256, 0, st>>>(n, m2, PHt, e.Hcam.as<double>(), e.Hpt.as<double>(), e.off.as<int64_t>(), meas_var, S, lds, ldz);
         e.launches += 1;
     }
+    k_ekf_innovation_vec<<<(m2 + 255) / 256, 256, 0, st>>>(m2, e.z.as<double>(), e.h.as<double>(), PHt + n, ldz);
+    e.launches += 1;
     // Factorisation of S and the gain TRSM Z = PHt * L^-T side by side (chol_kernels.cu dense_cholesky_factor_trsm): the factorisation is a
     // latency chain on a handful of SMs, the TRSM needs of L only the panels that are already final.  Z overwrites PHt, which is scratch,
     // so the positive-definiteness check below may come after it.  SRK_EKF_OVERLAP=0: one after the other (development aid).
@@ -616,7 +625,7 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
             }
             if (e.hi != nullptr && e.evs.size() >= need) {
                 EScope sc(e, E_CHOL_TRSM);
-                const int64_t nl = srk::dense_cholesky_factor_trsm(e.hi, st, m2, S, lds, ws, e.info.as<int>(), n, PHt, ldz, e.evs.data(), (int)e.evs.size());
+                const int64_t nl = srk::dense_cholesky_factor_trsm(e.hi, st, m2, S, lds, ws, e.info.as<int>(), nz, PHt, ldz, e.evs.data(), (int)e.evs.size());
                 if (nl >= 0) { e.launches += nl; overlapped = true; }
             }
         }
@@ -649,29 +658,28 @@ int update_resident(Ekf& e, int64_t m, const double* Hcam, const double* Hpt, co
         for (int p0 = 0; p0 < m2; p0 += kPanel) {
             const int pend = m2 < p0 + kPanel ? m2 : p0 + kPanel;
             if (panel_env != 0) {
-                srk::launch_strip_trsm(st, n, pend - p0, PHt + (size_t)p0 * ldz, ldz, S + (size_t)p0 * lds + p0, lds, srk::dense_cholesky_dinv_block(ws, p0 / 64));
+                srk::launch_strip_trsm(st, nz, pend - p0, PHt + (size_t)p0 * ldz, ldz, S + (size_t)p0 * lds + p0, lds, srk::dense_cholesky_dinv_block(ws, p0 / 64));
                 e.launches += 1;
             }
             for (int k0 = p0; k0 < pend && panel_env == 0; k0 += 64) {
-                srk::launch_block_right_solve(st, n, PHt + (size_t)k0 * ldz, ldz, srk::dense_cholesky_dinv_block(ws, k0 / 64), m2 - k0);   // the last block may be ragged
+                srk::launch_block_right_solve(st, nz, PHt + (size_t)k0 * ldz, ldz, srk::dense_cholesky_dinv_block(ws, k0 / 64), m2 - k0);   // the last block may be ragged
                 e.launches += 1;
                 const int rest = pend - (k0 + 64);
                 if (rest > 0) {   // the other blocks of the panel: PHt[:, k0+64:pend] -= Z_k (n x 64) * L[k0+64:pend, k0:k0+64]^T
-                    srk::launch_gemm_nt_dmma(st, n, rest, 64, PHt + (size_t)k0 * ldz, ldz, S + (size_t)k0 * lds + k0 + 64, lds, PHt + (size_t)(k0 + 64) * ldz, ldz, 0);
+                    srk::launch_gemm_nt_dmma(st, nz, rest, 64, PHt + (size_t)k0 * ldz, ldz, S + (size_t)k0 * lds + k0 + 64, lds, PHt + (size_t)(k0 + 64) * ldz, ldz, 0);
                     e.launches += 1;
                 }
             }
             if (pend < m2) {      // PHt[:, pend:] -= Z_panel (n x 256) * L[pend:, p0:pend]^T
-                srk::launch_gemm_nt_dmma(st, n, m2 - pend, pend - p0, PHt + (size_t)p0 * ldz, ldz, S + (size_t)p0 * lds + pend, lds, PHt + (size_t)pend * ldz, ldz, 0);
+                srk::launch_gemm_nt_dmma(st, nz, m2 - pend, pend - p0, PHt + (size_t)p0 * ldz, ldz, S + (size_t)p0 * lds + pend, lds, PHt + (size_t)pend * ldz, ldz, 0);
                 e.launches += 1;
             }
         }
     }
     {
         EScope sc(e, E_STATE);
-        k_ekf_innovation_vec<<<(m2 + 255) / 256, 256, 0, st>>>(m2, e.z.as<double>(), e.h.as<double>(), e.w.as<double>());
+        k_ekf_take_row<<<(m2 + 255) / 256, 256, 0, st>>>(m2, PHt + n, ldz, e.w.as<double>());      // L^-1 (z - h), carried through the TRSM as row n
         e.launches += 1;
-        e.launches += srk::dense_cholesky_forward(st, m2, S, lds, ws, e.w.as<double>());
         k_ekf_state<<<(n + 31) / 32, 256, 0, st>>>(n, m2, PHt, ldz, e.w.as<double>(), e.x.as<double>());
         e.launches += 1;
     }
