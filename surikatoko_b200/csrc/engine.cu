@@ -52,7 +52,8 @@ struct Buf {
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         // development aid: SRK_POISON=1 fills fresh buffers with NaN patterns, so that a read of memory nobody wrote shows up at once
-        if (e == cudaSuccess && std::getenv("SRK_POISON") != nullptr) cudaMemset(p, 0xFF, want);
+        // (the fill runs on the legacy default stream, which the engine's non-blocking streams do not wait for: finish it before anybody writes the buffer)
+        if (e == cudaSuccess && std::getenv("SRK_POISON") != nullptr) { cudaMemset(p, 0xFF, want); cudaDeviceSynchronize(); }
         return e;
     }
     void release() { if (p != nullptr) cudaFree(p); p = nullptr; cap = 0; }
