@@ -105,6 +105,7 @@ struct Engine {
     cudaStream_t own_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // structure pass of a bind, concurrent with the H2D copies on `stream`
     cudaEvent_t ev_idx = nullptr;
+    bool G_partial = false;               // multi-GPU dense path: Ggf holds this rank's partial sums (they travel inside S)
     cudaStream_t stream = nullptr;
 
     bool bound = false, norm_failed = false, normalized = false;
@@ -498,8 +499,9 @@ int fetch_attempt_scalars(Engine& e, bool with_flags, double* err, bool* nonfini
 }
 
 // ComputeCloseFormReprErrorDerivatives (BA.cpp:1140-1448) on the current state.
-int derivative_pass(Engine& e) {
+int derivative_pass(Engine& e, bool keep_partial_G = false) {
     cudaStream_t st = e.stream;
+    e.G_partial = false;
     {
         Scope s(e, F_JACOBIAN);
         // K2's third form consumes per-point sums of Jp^T Jp / Jp^T rho: K1 has every term in registers and leaves them in k2_eacc
@@ -525,6 +527,9 @@ int derivative_pass(Engine& e) {
                                  e.Ggf.as<double>(), e.Ggf.as<double>() + 100 * (size_t)e.M, splits);
         e.launches += 1;
     }
+    // Dense path of a multi-GPU run: G and g_f enter the reduced system linearly (damping multiplies the diagonal of the SUM), so every rank
+    // adds its own partial blocks to its partial S and the one all-reduce of S carries them: one latency-bound collective less per iteration.
+    if (keep_partial_G && e.world > 1) { e.G_partial = true; return SRK_OK; }
     return do_allreduce(e, e.Ggf.as<double>(), 110 * (int64_t)e.M);
 }
 
@@ -706,7 +711,7 @@ int attempt(Engine& e, int solver, const srk_ba_options* opt, double c, double* 
                 SRK_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * ((size_t)ld * nf + ld), st));
                 e.S_clean = e.order.active && e.order_tiles;
             }
-            if (e.rank == 0) { srk::launch_fill_reduced(st, M, G, gf, c, e.unity, S, ld, rhs); e.launches += 1; }
+            if (e.rank == 0 || e.G_partial) { srk::launch_fill_reduced(st, M, G, gf, c, e.unity, S, ld, rhs); e.launches += 1; }
             srk::SchurSink sink{S, ld, rhs, e.unity, nullptr, nullptr, 0, nullptr};
             schur_accumulate(e, sink, c);
         }
@@ -903,7 +908,7 @@ int run_impl(Engine& e, const srk_ba_options* opt, srk_ba_report* rep) {
             finish(0, SRK_STOP_MAX_ITERS, it - 1, attempts, err_initial, err_value, hessian_factor, seen);
             return SRK_OK;
         }
-        rc = derivative_pass(e);  // once per outer iteration (quirk Q7)
+        rc = derivative_pass(e, solver == SRK_SOLVER_DENSE_CHOLESKY);  // once per outer iteration (quirk Q7)
         if (rc != SRK_OK) return rc;
         enum { Success, FailedHessianOverflow, FailedButConverged } result;
         double err_new = std::nan("");
