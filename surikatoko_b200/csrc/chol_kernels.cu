@@ -1810,12 +1810,16 @@ int64_t dense_cholesky_backward(cudaStream_t st, int n, const double* L, int64_t
 // read in [k][row] order straight from the column-major matrices, 128x128 tiles, persistent CTAs over the tile list.
 // ksplit > 1: blockIdx.y owns the K slice [y * Kper, (y + 1) * Kper) and ADDS its product atomically (a short-and-wide product -- few
 // output tiles, long contraction -- would otherwise keep only a handful of SMs busy)
+constexpr int kGemmKC64 = 12;     // K chunk of the 64-row variant
 constexpr int kGemmKC = 16;      // K chunk per stage of the general product (32 halves the barriers but measured no faster: SYRK 5.04 -> 4.99 ms, TRSM 4.28 -> 4.35)
-__global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot, const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
-                                                         double* __restrict__ C, int64_t ldc, int lower_only, int ksplit) {
-    constexpr int TILE = 128, SLD = TILE + 4, NJ = 8, KC = kGemmKC;
+// TM = rows of a CTA tile: 128 (8 warps, one CTA per SM) or 64 (4 warps of the same 32 x 64 warp tile, <= 168 registers: THREE CTAs per SM whose
+// barriers and epilogues are out of step with each other -- the shape cuBLAS's own DGEMM on this GPU uses, cutlass d884gemm 64x128_16x3).
+template <int TM>
+__global__ void __launch_bounds__(TM * 2, TM == 64 ? 3 : 1) k_gemm_nt_dmma(int m, int n, int Ktot, const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                                                                           double* __restrict__ C, int64_t ldc, int lower_only, int ksplit) {
+    constexpr int TN = 128, SLDA = TM + 4, SLDB = TN + 4, NJ = 8, KC = TM == 64 ? kGemmKC64 : kGemmKC, NT = TM * 2;   // 64-row tiles: 3 x 19 KB of shared memory per CTA, three CTAs per SM
     if (ksplit > 1) {
-        const int Kper = (((Ktot + ksplit - 1) / ksplit) + kGemmKC - 1) / kGemmKC * kGemmKC;
+        const int Kper = (((Ktot + ksplit - 1) / ksplit) + 47) / 48 * 48;      // a multiple of both K chunk sizes
         const int kb = (int)blockIdx.y * Kper;
         if (kb >= Ktot) return;
         A += (size_t)kb * lda; B += (size_t)kb * ldb;
@@ -1824,39 +1828,43 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
     const int K = Ktot;
     extern __shared__ double sm[];
     double* sA = sm;
-    double* sB = sm + STAGES * KC * SLD;
+    double* sB = sm + STAGES * KC * SLDA;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tm = (m + TILE - 1) / TILE, tn = (n + TILE - 1) / TILE;
+    const int tm = (m + TM - 1) / TM, tn = (n + TN - 1) / TN;
     const int nk = (K + KC - 1) / KC;
-    const int wr = (warp & 3) * 32, wc = (warp >> 2) * 64;
+    const int wr = (warp % (TM / 32)) * 32, wc = (warp / (TM / 32)) * 64;
     const int g = lane >> 2, tg = lane & 3;
     // Work list.  lower_only: ONLY the tiles that touch the lower triangle, numbered down the block columns -- striding over the full
     // tm x tn grid and skipping the upper ones left the CTAs with 6 to 10 tiles each (ncu: the DMMA pipe 84 % busy while an SM was
     // active, 71 % of the elapsed time).  Every tile of the list costs the same, so a plain round-robin is balanced to one tile.
-    const int tc = tn < tm ? tn : tm;          // block columns that reach the lower triangle
-    const int ntiles = lower_only ? tc * tm - tc * (tc - 1) / 2 : tm * tn;
+    // block column c of the tile grid reaches the lower triangle from tile row (c * TN) / TM on
+    auto first_row = [&](int c) { const int f = (c * TN) / TM; return f < tm ? f : tm; };
+    int ntiles = tm * tn;
+    if (lower_only) { ntiles = 0; for (int c = 0; c < tn; ++c) ntiles += tm - first_row(c); }
     auto tile_of = [&](int t, int& ti, int& tj) {
         if (!lower_only) { ti = t % tm; tj = t / tm; return; }
-        int c = 0, rem = t;                       // block column c holds rows c .. tm-1
-        while (c < tn && rem >= tm - c) { rem -= (tm - c > 0 ? tm - c : 0); ++c; }
-        ti = c + rem; tj = c;
+        int c = 0, rem = t;
+        while (c < tn - 1 && rem >= tm - first_row(c)) { rem -= tm - first_row(c); ++c; }
+        ti = first_row(c) + rem; tj = c;
     };
     auto load_chunk = [&](int i0, int j0, int stage, int kc) {
 #pragma unroll
-        for (int q = 0; q < KC / 4; ++q) {
-            const int v = tid + 256 * q;
-            const int k = v >> 6, rp = (v & 63) * 2;
+        for (int q = 0; q < KC * (TM / 2) / NT; ++q) {          // A: KC x TM doubles
+            const int v = tid + NT * q;
+            const int k = v / (TM / 2), rp = (v % (TM / 2)) * 2;
             const int kk = kc * KC + k;
-            {
-                const int row = i0 + rp;
-                int bytes = (kk < K) ? (m - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
-                cp_async16(sA + (stage * KC + k) * SLD + rp, A + (bytes > 0 ? (size_t)kk * lda + row : 0), bytes);
-            }
-            {
-                const int row = j0 + rp;
-                int bytes = (kk < K) ? (n - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
-                cp_async16(sB + (stage * KC + k) * SLD + rp, B + (bytes > 0 ? (size_t)kk * ldb + row : 0), bytes);
-            }
+            const int row = i0 + rp;
+            int bytes = (kk < K) ? (m - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+            cp_async16(sA + (stage * KC + k) * SLDA + rp, A + (bytes > 0 ? (size_t)kk * lda + row : 0), bytes);
+        }
+#pragma unroll
+        for (int q = 0; q < KC * (TN / 2) / NT; ++q) {          // B: KC x TN doubles
+            const int v = tid + NT * q;
+            const int k = v / (TN / 2), rp = (v % (TN / 2)) * 2;
+            const int kk = kc * KC + k;
+            const int row = j0 + rp;
+            int bytes = (kk < K) ? (n - row) * 8 : 0; bytes = bytes > 16 ? 16 : (bytes < 0 ? 0 : bytes);
+            cp_async16(sB + (stage * KC + k) * SLDB + rp, B + (bytes > 0 ? (size_t)kk * ldb + row : 0), bytes);
         }
     };
     // the first two chunks of a tile are requested BEFORE the epilogue of the tile before it: its read-modify-write of C then overlaps them
@@ -1864,7 +1872,7 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int ti, tj;
         tile_of(t, ti, tj);
-        const int i0 = ti * TILE, j0 = tj * TILE;
+        const int i0 = ti * TM, j0 = tj * TN;
         if (!primed) {
             load_chunk(i0, j0, 0, 0); cp_async_commit();
             if (nk > 1) load_chunk(i0, j0, 1, 1);
@@ -1880,13 +1888,13 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
             __syncthreads();
             if (kc + 2 < nk) load_chunk(i0, j0, (kc + 2) % STAGES, kc + 2);
             cp_async_commit();
-            const double* cA = sA + (kc % STAGES) * KC * SLD;
-            const double* cB = sB + (kc % STAGES) * KC * SLD;
+            const double* cA = sA + (kc % STAGES) * KC * SLDA;
+            const double* cB = sB + (kc % STAGES) * KC * SLDB;
 #pragma unroll
             for (int ks = 0; ks < KC; ks += 4) {
                 double af[4], bf[NJ];
-                const double* pa = cA + (ks + tg) * SLD + wr + g;
-                const double* pb = cB + (ks + tg) * SLD + wc + g;
+                const double* pa = cA + (ks + tg) * SLDA + wr + g;
+                const double* pb = cB + (ks + tg) * SLDB + wc + g;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) af[i] = pa[i * 8];
 #pragma unroll
@@ -1903,8 +1911,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt_dmma(int m, int n, int Ktot,
         if (t + (int)gridDim.x < ntiles) {      // every stage is free now: request the next tile's first two chunks, then do the epilogue
             int ni, nj;
             tile_of(t + (int)gridDim.x, ni, nj);
-            load_chunk(ni * TILE, nj * TILE, 0, 0); cp_async_commit();
-            if (nk > 1) load_chunk(ni * TILE, nj * TILE, 1, 1);
+            load_chunk(ni * TM, nj * TN, 0, 0); cp_async_commit();
+            if (nk > 1) load_chunk(ni * TM, nj * TN, 1, 1);
             cp_async_commit();
             primed = true;
         }
@@ -1942,17 +1950,27 @@ void launch_gemm_nt_dmma(cudaStream_t st, int m, int n, int K, const double* A, 
                          int allow_split_k, int cta_per_tile) {
     set_attrs_once();
     static PerDeviceOnce once;
-    const size_t smem = sizeof(double) * (2 * STAGES * kGemmKC * (128 + 4));
-    if (once.first()) cudaFuncSetAttribute(k_gemm_nt_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem128 = sizeof(double) * (STAGES * kGemmKC * ((128 + 4) + (128 + 4)));
+    const size_t smem64 = sizeof(double) * (STAGES * kGemmKC64 * ((64 + 4) + (128 + 4)));
+    if (once.first()) {
+        cudaFuncSetAttribute(k_gemm_nt_dmma<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem128);
+        cudaFuncSetAttribute(k_gemm_nt_dmma<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem64);
+    }
     if (m <= 0 || n <= 0 || K <= 0) return;
-    const int tm = (m + 127) / 128, tn = (n + 127) / 128;
-    const int tiles = lower_only ? tm * (tm + 1) / 2 : tm * tn;          // tiles that do work
+    static int tile_env = -1;        // SRK_GEMM_TILE=64: 64 x 128 CTA tiles, three CTAs per SM (measured: SYRK 5.20 ms against 5.09 ms with 128 x 128)
+    if (tile_env < 0) { const char* e = getenv("SRK_GEMM_TILE"); tile_env = (e != nullptr && atoi(e) == 64) ? 64 : 128; }
+    const int TM = tile_env;
+    const int tm = (m + TM - 1) / TM, tn = (n + 127) / 128;
+    int tiles = tm * tn;                                                  // tiles that do work
+    if (lower_only) { tiles = 0; for (int c = 0; c < tn; ++c) { int f = (c * 128) / TM; if (f > tm) f = tm; tiles += tm - f; } }
     int ksplit = 1;
     if (allow_split_k && tiles < g_sms / 2 && K >= 4096) { ksplit = (2 * g_sms + tiles - 1) / tiles; const int maxs = K / 1024; if (ksplit > maxs) ksplit = maxs; if (ksplit < 1) ksplit = 1; }
     // cta_per_tile: one CTA per tile instead of persistent CTAs -- an SM is handed back after every tile, so the kernels of a
     // higher-priority stream (the factorisation chain that runs beside the EKF gain) get in at tile granularity
-    const int gx = (cta_per_tile || tiles < g_sms) ? tiles : g_sms;
-    k_gemm_nt_dmma<<<dim3(gx, ksplit), 256, smem, st>>>(m, n, K, A, lda, B, ldb, C, ldc, lower_only, ksplit);
+    const int resident = TM == 64 ? 3 * g_sms : g_sms;
+    const int gx = (cta_per_tile || tiles < resident) ? tiles : resident;
+    if (TM == 64) k_gemm_nt_dmma<64><<<dim3(gx, ksplit), 128, smem64, st>>>(m, n, K, A, lda, B, ldb, C, ldc, lower_only, ksplit);
+    else k_gemm_nt_dmma<128><<<dim3(gx, ksplit), 256, smem128, st>>>(m, n, K, A, lda, B, ldb, C, ldc, lower_only, ksplit);
 }
 
 // X <- X * Linv^T on an (rows x 64) block column: X(r,c) = sum_{q<=c} X(r,q) * Linv(c,q).
