@@ -212,8 +212,12 @@ __global__ void __launch_bounds__(256) k_schur_tables(int64_t N, int tile_points
 
 // ---------------------------------------------------------------------------------------------------------------------------------
 #include "schur_v3_consume.inc"
+#include "schur_v3_consume4.inc"
 
-__global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O, int tile_points, const int64_t* __restrict__ pt_begin,
+// CW = consumer warps: 8 (two per SM sub-partition, 15 accumulator fragments each; the rhs GEMV on consumer warp 7) or 4 (ONE per sub-partition
+// with 30 fragments: 30 independent DMMAs per k-step and operand load, the rhs GEMV with the producers).  Eight producer warps either way.
+template <int CW>
+__global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_t O, int tile_points, const int64_t* __restrict__ pt_begin,
                                                             const int32_t* __restrict__ obs_pt, const double* __restrict__ J, SchurSink sink,
                                                             const double* __restrict__ gi, const double* __restrict__ uvec,
                                                             const unsigned char* __restrict__ skipped, const int* __restrict__ tile_tab,
@@ -227,16 +231,33 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
     if (p0 >= N) return;
     const int nbatch = (int)((p1 - p0 + kV3BP - 1) / kV3BP);
     const int nLocal = tile_n[blockIdx.x];
+    constexpr int NT = 32 * (CW + 8);
+    if (CW == 4) {      // the flush tables up front: the producers flush the rhs themselves
+        if (tid < kV3Cams) sm.tab[tid] = tile_tab[(size_t)blockIdx.x * kV3Cams + tid];
+        __syncthreads();
+        for (int m = tid; m < kV3Rows; m += NT) {
+            const int slot = m / 10, a = m - 10 * slot;
+            sm.gidx[m] = slot < nLocal ? red_index(sm.tab[slot], a, sink.unity) : -1;
+        }
+        if (sink.blocks != nullptr) {
+            for (int e = tid; e < kV3Cams * kV3Cams; e += NT) {
+                const int si = e / kV3Cams, sl = e % kV3Cams;
+                sm.blk[e] = (si < nLocal && sl <= si) ? sink_block_id(sink, sm.tab[si], sm.tab[sl]) : -1;
+            }
+        }
+        __syncthreads();
+    }
 
     // dbg_mode (timing experiments only, results are garbage): 1 = consumers alone (no producers, no barriers), 2 = producers alone
-    if (dbg_mode == 1 && w >= 8) return;
-    if (dbg_mode == 2 && w < 8) return;
-    if (w >= 8) {
+    if (dbg_mode == 1 && w >= CW) return;
+    if (dbg_mode == 2 && w < CW) return;
+    if (w >= CW) {
         // ================= producers: one lane per observation of the batch
         // Every global address of a batch is known before the batch starts: the observation extents come one batch ahead, the per-point
         // Gi / u / slot masks are addressed by the batch's first point id (staged to shared memory by helper lanes) and the position of an
         // observation's point inside the batch travels in the slot byte -- ONE round trip per batch, no dependent loads.
-        const int ptid = tid - 256;
+        const int ptid = tid - 32 * CW;
+        double rhs_acc = 0.0;                         // CW == 4: threads 0..239 own (column m, half of the batch's rows) of rhs += V^T u
         int64_t ob = pt_begin[p0], oe = pt_begin[min(p1, p0 + (int64_t)kV3BP)];
         for (int b = 0; b < nbatch; ++b) {
             const int s = b % kV3Stages;
@@ -244,7 +265,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
             const int64_t pb1 = min(p1, pb0 + kV3BP);
             int64_t ob_n = 0, oe_n = 0;
             if (b + 1 < nbatch) { ob_n = oe; oe_n = pt_begin[min(p1, pb0 + 2 * (int64_t)kV3BP)]; }
-            if (b >= kV3Stages && dbg_mode == 0) bar_sync_named(1 + kV3Stages + s, kV3Threads);     // empty[s]: the consumers are done with batch b - stages
+            if (b >= kV3Stages && dbg_mode == 0) bar_sync_named(1 + kV3Stages + s, NT);     // empty[s]: the consumers are done with batch b - stages
             double* Vs = sm.V[s];
             // ---- this lane's observation (first pass): loads in flight before anything is waited for
             int64_t o = ob + ptid;
@@ -321,8 +342,26 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
                     for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
                 }
             }
-            if (dbg_mode == 0) bar_arrive_named(1 + s, kV3Threads);                // full[s]
+            if (CW == 4) bar_sync_named(10, 256);                                   // every producer's rows of V[s] are written (the rhs below reads them)
+            if (dbg_mode == 0) bar_arrive_named(1 + s, NT);                // full[s]
+            if (CW == 4 && ptid < 2 * kV3Rows) {   // rhs += V^T u: the stage is only rewritten by the producers themselves, a ring turn later
+                const int m = ptid % kV3Rows, k0 = (ptid / kV3Rows) * (kV3K / 2);
+                const double* U = sm.U[s];
+                double sacc = rhs_acc;
+#pragma unroll 8
+                for (int kk = k0; kk < k0 + kV3K / 2; ++kk) sacc += Vs[kk * kV3SLD + m] * U[kk];
+                rhs_acc = sacc;
+            }
             ob = ob_n; oe = oe_n;
+        }
+        if (CW == 4 && ptid < 2 * kV3Rows && rhs_acc != 0.0) {
+            const int m = ptid % kV3Rows;
+            const int r = sm.gidx[m];
+            if (r >= 0) {
+                const int slot = m / 10;
+                if (sink.blocks == nullptr) atomicAdd(&sink.rhs[r], rhs_acc);
+                else atomicAdd(&sink.rhs[(size_t)sm.tab[slot] * 10 + (m - 10 * slot)], rhs_acc);
+            }
         }
         return;
     }
@@ -334,6 +373,45 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
     const int g8 = lane >> 2, tg = lane & 3;
     int R = (10 * nLocal + 7) / 8;
     R = R < 1 ? 1 : (R > 15 ? 15 : R);
+    if constexpr (CW == 4) {
+        double acc[kV4NFMax][2];
+#pragma unroll
+        for (int f = 0; f < kV4NFMax; ++f) { acc[f][0] = 0.0; acc[f][1] = 0.0; }
+        for (int b = 0; b < nbatch; ++b) {
+            const int s = b % kV3Stages;
+            if (dbg_mode == 0) bar_sync_named(1 + s, NT);                          // full[s]
+            v4_consume_generated(w, R, acc, sm.V[s] + tg * kV3SLD + g8);
+            if (b + kV3Stages < nbatch && dbg_mode == 0) bar_arrive_named(1 + kV3Stages + s, NT);   // empty[s]
+        }
+        const bool dense = sink.blocks == nullptr;
+        const int nfr = kV4NFrag[R - kV3GenRMin][w];
+#pragma unroll
+        for (int f = 0; f < kV4NFMax; ++f) {
+            if (f >= nfr) break;
+            const int rc = kV4FragRC[R - kV3GenRMin][w][f];
+            const int row = 8 * (rc >> 4) + g8;
+            if (row >= kV3Rows) continue;
+            const int ri = sm.gidx[row], si = row / 10;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double v = acc[f][e];
+                const int col = 8 * (rc & 15) + 2 * tg + e;
+                if (col >= kV3Rows) continue;
+                const int ci = sm.gidx[col], sl = col / 10;
+                if (v == 0.0 || ri < 0 || ci < 0 || sl > si || (sl == si && col > row)) continue;
+                if (dense) {
+                    atomicAdd(&sink.S[(size_t)ci * sink.ld + ri], -v);
+                } else {
+                    const int blk = sm.blk[si * kV3Cams + sl];
+                    if (blk < 0) continue;
+                    const int a = row - 10 * si, bq = col - 10 * sl;
+                    atomicAdd(&sink.blocks[(size_t)blk * 100 + a * 10 + bq], -v);
+                    if (sl == si && a != bq) atomicAdd(&sink.blocks[(size_t)blk * 100 + bq * 10 + a], -v);
+                }
+            }
+        }
+        return;
+    } else {
     double acc[15][2];
 #pragma unroll
     for (int f = 0; f < 15; ++f) { acc[f][0] = 0.0; acc[f][1] = 0.0; }
@@ -341,7 +419,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
 
     for (int b = 0; b < nbatch; ++b) {
         const int s = b % kV3Stages;
-        if (dbg_mode == 0) bar_sync_named(1 + s, kV3Threads);                      // full[s]
+        if (dbg_mode == 0) bar_sync_named(1 + s, NT);                      // full[s]
         const double* V = sm.V[s];
         v3_consume_generated(w, R, acc, V + tg * kV3SLD + g8);
         if (w == 7) {   // rhs += V^T u
@@ -357,7 +435,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
                 }
             }
         }
-        if (b + kV3Stages < nbatch && dbg_mode == 0) bar_arrive_named(1 + kV3Stages + s, kV3Threads);   // empty[s]
+        if (b + kV3Stages < nbatch && dbg_mode == 0) bar_arrive_named(1 + kV3Stages + s, NT);   // empty[s]
     }
 
     // ---- flush: one red.global.add.f64 per touched entry per tile
@@ -414,6 +492,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) k_schur_v3(int64_t N, int64_t O
             else atomicAdd(&sink.rhs[(size_t)sm.tab[slot] * 10 + (m - 10 * slot)], racc[q]);
         }
     }
+
+    }
 }
 
 void launch_point_factor(cudaStream_t st, int64_t N, int64_t O, const int64_t* pt_begin, const double* J, double c, double* pinv, unsigned char* skipped,
@@ -439,11 +519,17 @@ void launch_schur_v3(cudaStream_t st, int64_t N, int64_t O, int tile_points, con
                      const unsigned char* obs_slot, const unsigned short* pt_mask) {
     if (N <= 0) return;
     static PerDeviceOnce once;
-    if (once.first()) cudaFuncSetAttribute(k_schur_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
+    if (once.first()) {
+        cudaFuncSetAttribute(k_schur_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
+        cudaFuncSetAttribute(k_schur_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
+    }
+    static int cons = -1;        // consumer warps: 4 = one per SM sub-partition with 30 fragments each (default: K2 1.77 -> 1.70 ms), SRK_V3_CONS=8 = two with 15 each
+    if (cons < 0) { const char* e = getenv("SRK_V3_CONS"); cons = (e != nullptr && atoi(e) == 8) ? 8 : 4; }
     const unsigned grid = (unsigned)((N + tile_points - 1) / tile_points);
     static int dbg_mode = -1;
     if (dbg_mode < 0) { const char* e = getenv("SRK_V3_DEBUG"); dbg_mode = e != nullptr ? atoi(e) : 0; }
-    k_schur_v3<<<grid, kV3Threads, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
+    if (cons == 4) k_schur_v3<4><<<grid, 32 * 12, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
+    else k_schur_v3<8><<<grid, kV3Threads, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
 }
 
 }  // namespace srk
