@@ -215,8 +215,11 @@ __global__ void __launch_bounds__(256) k_schur_tables(int64_t N, int tile_points
 #include "schur_v3_consume4.inc"
 
 // CW = consumer warps: 8 (two per SM sub-partition, 15 accumulator fragments each; the rhs GEMV on consumer warp 7) or 4 (ONE per sub-partition
-// with 30 fragments: 30 independent DMMAs per k-step and operand load, the rhs GEMV with the producers).  Eight producer warps either way.
-template <int CW>
+// with 30 fragments: 30 independent DMMAs per k-step and operand load).  Eight producer warps either way.
+// RP: the rhs GEMV (rhs += V^T u, vector FP64) runs with the producers instead of on the last consumer warp.  tools/probe/dmma_micro.cu: ONE
+// warp per sub-partition issues a DMMA every ~25 cycles (62 % of the pipe), TWO saturate it -- so every cycle a consumer warp spends on anything
+// but DMMAs (the GEMV took ~20 % of warp 7's time) idles its sub-partition's pipe, and all consumers wait for the slowest at the batch barrier.
+template <int CW, bool RP>
 __global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_t O, int tile_points, const int64_t* __restrict__ pt_begin,
                                                             const int32_t* __restrict__ obs_pt, const double* __restrict__ J, SchurSink sink,
                                                             const double* __restrict__ gi, const double* __restrict__ uvec,
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_
     const int nbatch = (int)((p1 - p0 + kV3BP - 1) / kV3BP);
     const int nLocal = tile_n[blockIdx.x];
     constexpr int NT = 32 * (CW + 8);
-    if (CW == 4) {      // the flush tables up front: the producers flush the rhs themselves
+    if (RP) {           // the flush tables up front: the producers flush the rhs themselves
         if (tid < kV3Cams) sm.tab[tid] = tile_tab[(size_t)blockIdx.x * kV3Cams + tid];
         __syncthreads();
         for (int m = tid; m < kV3Rows; m += NT) {
@@ -257,7 +260,17 @@ __global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_
         // Gi / u / slot masks are addressed by the batch's first point id (staged to shared memory by helper lanes) and the position of an
         // observation's point inside the batch travels in the slot byte -- ONE round trip per batch, no dependent loads.
         const int ptid = tid - 32 * CW;
-        double rhs_acc = 0.0;                         // CW == 4: threads 0..239 own (column m, half of the batch's rows) of rhs += V^T u
+        double rhs_acc = 0.0;                         // RP: threads 0..239 own (column m, half of the batch's rows) of rhs += V^T u
+        auto rhs_of_stage = [&](int st2) {
+            if (ptid >= 2 * kV3Rows) return;
+            const int m = ptid % kV3Rows, k0 = (ptid / kV3Rows) * (kV3K / 2);
+            const double* Vq = sm.V[st2];
+            const double* U = sm.U[st2];
+            double sacc = rhs_acc;
+#pragma unroll 8
+            for (int kk = k0; kk < k0 + kV3K / 2; ++kk) sacc += Vq[kk * kV3SLD + m] * U[kk];
+            rhs_acc = sacc;
+        };
         int64_t ob = pt_begin[p0], oe = pt_begin[min(p1, p0 + (int64_t)kV3BP)];
         for (int b = 0; b < nbatch; ++b) {
             const int s = b % kV3Stages;
@@ -279,6 +292,9 @@ __global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_
 #pragma unroll
                 for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
             }
+            // ---- rhs += V^T u of the batch BEFORE this one, while this batch's loads are in flight (the stage is only rewritten by the
+            // producers themselves, a ring turn later)
+            if (RP && b > 0) rhs_of_stage((b - 1) % kV3Stages);
             // ---- helper lanes: per-point data of the batch
             if (ptid < kV3BP * 6) {
                 const int pl = ptid / 6, i = ptid - 6 * pl;
@@ -342,19 +358,12 @@ __global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_
                     for (int i = 0; i < 20; ++i) jc[i] = J[(int64_t)(8 + i) * O + o];
                 }
             }
-            if (CW == 4) bar_sync_named(10, 256);                                   // every producer's rows of V[s] are written (the rhs below reads them)
+            if (RP) bar_sync_named(10, 256);                                        // every producer's rows of V[s] are written (the rhs below reads them)
             if (dbg_mode == 0) bar_arrive_named(1 + s, NT);                // full[s]
-            if (CW == 4 && ptid < 2 * kV3Rows) {   // rhs += V^T u: the stage is only rewritten by the producers themselves, a ring turn later
-                const int m = ptid % kV3Rows, k0 = (ptid / kV3Rows) * (kV3K / 2);
-                const double* U = sm.U[s];
-                double sacc = rhs_acc;
-#pragma unroll 8
-                for (int kk = k0; kk < k0 + kV3K / 2; ++kk) sacc += Vs[kk * kV3SLD + m] * U[kk];
-                rhs_acc = sacc;
-            }
             ob = ob_n; oe = oe_n;
         }
-        if (CW == 4 && ptid < 2 * kV3Rows && rhs_acc != 0.0) {
+        if (RP) rhs_of_stage((nbatch - 1) % kV3Stages);
+        if (RP && ptid < 2 * kV3Rows && rhs_acc != 0.0) {
             const int m = ptid % kV3Rows;
             const int r = sm.gidx[m];
             if (r >= 0) {
@@ -422,7 +431,7 @@ __global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_
         if (dbg_mode == 0) bar_sync_named(1 + s, NT);                      // full[s]
         const double* V = sm.V[s];
         v3_consume_generated(w, R, acc, V + tg * kV3SLD + g8);
-        if (w == 7) {   // rhs += V^T u
+        if (!RP && w == 7) {   // rhs += V^T u
             const double* U = sm.U[s];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -439,19 +448,21 @@ __global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_
     }
 
     // ---- flush: one red.global.add.f64 per touched entry per tile
-    if (tid < kV3Cams) sm.tab[tid] = tile_tab[(size_t)blockIdx.x * kV3Cams + tid];
-    bar_sync_named(9, 256);
-    for (int m = tid; m < kV3Rows; m += 256) {
-        const int slot = m / 10, a = m - 10 * slot;
-        sm.gidx[m] = slot < nLocal ? red_index(sm.tab[slot], a, sink.unity) : -1;
-    }
-    if (sink.blocks != nullptr) {
-        for (int e = tid; e < kV3Cams * kV3Cams; e += 256) {
-            const int si = e / kV3Cams, sl = e % kV3Cams;
-            sm.blk[e] = (si < nLocal && sl <= si) ? sink_block_id(sink, sm.tab[si], sm.tab[sl]) : -1;
+    if (!RP) {
+        if (tid < kV3Cams) sm.tab[tid] = tile_tab[(size_t)blockIdx.x * kV3Cams + tid];
+        bar_sync_named(9, 256);
+        for (int m = tid; m < kV3Rows; m += 256) {
+            const int slot = m / 10, a = m - 10 * slot;
+            sm.gidx[m] = slot < nLocal ? red_index(sm.tab[slot], a, sink.unity) : -1;
         }
+        if (sink.blocks != nullptr) {
+            for (int e = tid; e < kV3Cams * kV3Cams; e += 256) {
+                const int si = e / kV3Cams, sl = e % kV3Cams;
+                sm.blk[e] = (si < nLocal && sl <= si) ? sink_block_id(sink, sm.tab[si], sm.tab[sl]) : -1;
+            }
+        }
+        bar_sync_named(9, 256);
     }
-    bar_sync_named(9, 256);
     const bool dense = sink.blocks == nullptr;
     const int nfr = kV3NFrag[R - kV3GenRMin][w];
 #pragma unroll
@@ -480,7 +491,7 @@ __global__ void __launch_bounds__(32 * (CW + 8), 1) k_schur_v3(int64_t N, int64_
             }
         }
     }
-    if (w == 7) {
+    if (!RP && w == 7) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int m = lane + 32 * q;
@@ -520,16 +531,18 @@ void launch_schur_v3(cudaStream_t st, int64_t N, int64_t O, int tile_points, con
     if (N <= 0) return;
     static PerDeviceOnce once;
     if (once.first()) {
-        cudaFuncSetAttribute(k_schur_v3<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
-        cudaFuncSetAttribute(k_schur_v3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
+        cudaFuncSetAttribute(k_schur_v3<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
+        cudaFuncSetAttribute(k_schur_v3<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
+        cudaFuncSetAttribute(k_schur_v3<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(V3Smem));
     }
     static int cons = -1;        // consumer warps: 4 = one per SM sub-partition with 30 fragments each (default: K2 1.77 -> 1.70 ms), SRK_V3_CONS=8 = two with 15 each
-    if (cons < 0) { const char* e = getenv("SRK_V3_CONS"); cons = (e != nullptr && atoi(e) == 8) ? 8 : 4; }
+    if (cons < 0) { const char* e = getenv("SRK_V3_CONS"); cons = e != nullptr ? atoi(e) : 4; if (cons != 8 && cons != 80) cons = 4; }   // 8: two per sub-partition, rhs with the producers; 80: ... rhs on consumer warp 7 (round 2's first form)
     const unsigned grid = (unsigned)((N + tile_points - 1) / tile_points);
     static int dbg_mode = -1;
     if (dbg_mode < 0) { const char* e = getenv("SRK_V3_DEBUG"); dbg_mode = e != nullptr ? atoi(e) : 0; }
-    if (cons == 4) k_schur_v3<4><<<grid, 32 * 12, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
-    else k_schur_v3<8><<<grid, kV3Threads, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
+    if (cons == 4) k_schur_v3<4, true><<<grid, 32 * 12, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
+    else if (cons == 8) k_schur_v3<8, true><<<grid, kV3Threads, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
+    else k_schur_v3<8, false><<<grid, kV3Threads, sizeof(V3Smem), st>>>(N, O, tile_points, pt_begin, obs_pt, J, sink, gi, uvec, skipped, tile_tab, tile_n, obs_slot, pt_mask, dbg_mode);
 }
 
 }  // namespace srk
