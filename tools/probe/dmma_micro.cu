@@ -64,6 +64,10 @@ int main() {
     run<15, 8, 2>("rolling reloads", 8);
     run<32, 12, 0>("registers only", 8);
     run<32, 12, 1>("operands reloaded at the top (SYRK shape)", 8);
+    run<8, 6, 1>("2x4 piece: 8 fragments, 6 operands, reload at top", 16);
+    run<8, 6, 2>("2x4 piece: 8 fragments, 6 operands, rolling", 16);
+    run<8, 6, 1>("2x4 piece: 8 fragments, 6 operands, reload at top", 12);
+    run<10, 7, 1>("10 fragments, 7 operands, reload at top", 12);
     run<15, 8, 0>("registers only", 16);
     run<15, 8, 1>("operands reloaded at the top of a k-step", 16);
     return 0;
