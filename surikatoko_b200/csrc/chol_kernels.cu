@@ -110,7 +110,7 @@ constexpr int kPotrfLDT = 65;
 constexpr size_t kPotrfScratchDoubles = 2 * NB * kPotrfLDT;
 template <bool CG>
 __device__ __noinline__ void potrf64_blk_dev(int n, int k0, double* A, int64_t ld, double* dinv, int* info, unsigned char* F, int nblk, double* scratch, long long* prof = nullptr,
-                                             int info_base = 0) {
+                                             int info_base = 0, bool preloaded = false) {
     long long tp_ = clock64();
 #define POTRF_T(slot) do { if (prof != nullptr && threadIdx.x == 0) { const long long now_ = clock64(); prof[slot] += now_ - tp_; tp_ = now_; } } while (0)
     constexpr int LDT = kPotrfLDT;
@@ -121,13 +121,15 @@ __device__ __noinline__ void potrf64_blk_dev(int n, int k0, double* A, int64_t l
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nb = min(NB, n - k0);
     __syncthreads();                     // the scratch region may still be read as operand tiles by the caller
+    if (!preloaded) {                    // preloaded: the caller has left the tile in T and zeros in M (band_diag_update_into_scratch)
 #pragma unroll
-    for (int e = tid; e < NB * NB; e += 256) {
-        const int c = e >> 6, r = e & 63;
-        double v = (r == c) ? 1.0 : 0.0;
-        if (r < nb && c < nb && r >= c) { const double* src = A + (size_t)(k0 + c) * ld + k0 + r; v = CG ? __ldcg(src) : *src; }
-        T[r * LDT + c] = v;
-        M[r * LDT + c] = 0.0;
+        for (int e = tid; e < NB * NB; e += 256) {
+            const int c = e >> 6, r = e & 63;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < nb && c < nb && r >= c) { const double* src = A + (size_t)(k0 + c) * ld + k0 + r; v = CG ? __ldcg(src) : *src; }
+            T[r * LDT + c] = v;
+            M[r * LDT + c] = 0.0;
+        }
     }
     if (tid == 0) F[(size_t)(k0 / NB) * nblk + k0 / NB] = 1;
     __syncthreads();
@@ -730,6 +732,48 @@ __device__ __noinline__ void band_tile_op(BandSmem& sm, int n, double* A, int64_
     if (mode == 1 && tid == 0 && ra != rb) F[(size_t)rb * nblk + ra] = 1;   // fill (or already non-zero)
 }
 
+// The update of the NEXT diagonal tile, A(k1,k1) - X(k1,k) X(k1,k)^T, left directly in the scratch layout of potrf64_blk_dev (T = the tile, lower
+// triangle, identity outside the matrix; M = 0) instead of going back to global memory and being read again by the factorisation that follows at
+// once on the same CTA: one operand load instead of two, no store + reload round trip through L2 on the chain.
+__device__ __noinline__ void band_diag_update_into_scratch(BandSmem& sm, int n, const double* A, int64_t ld, int k1, int k, double* scratch) {
+    constexpr int LDT = kPotrfLDT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wr = (warp & 1) * 32, wc = (warp >> 1) * 16, g = lane >> 2, tg = lane & 3;
+    __syncthreads();
+    band_load_tile(sm.A, A, ld, k1 * NB, k * NB, n);
+    cp_async_commit();
+    const int nb = min(NB, n - k1 * NB);
+    double cur[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = wr + 8 * i + g, c = wc + 8 * j + 2 * tg + e;
+                cur[i][j][e] = (r < nb && c < nb && r >= c) ? __ldcg(A + (size_t)(k1 * NB + c) * ld + k1 * NB + r) : 0.0;
+            }
+    cp_async_wait<0>();
+    __syncthreads();
+    double acc[4][2][2];
+    band_tile_nt(sm.A, sm.A, acc);
+    __syncthreads();                     // every warp is done with the operand tile: the scratch layout overwrites it
+    double* T = scratch;
+    double* M = scratch + NB * LDT;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = wr + 8 * i + g, c = wc + 8 * j + 2 * tg + e;
+                double v = (r == c) ? 1.0 : 0.0;
+                if (r < nb && c < nb && r >= c) v = cur[i][j][e] - acc[i][j][e];
+                T[r * LDT + c] = v;
+                M[r * LDT + c] = 0.0;
+            }
+}
+
 // development aid: clock64() per phase, CTA 0 (slots 0..5: wait A, list, solve, wait B, diag update, potrf) and CTA 1 (8..11: wait A, solve, wait B, updates)
 __device__ long long g_band_prof[16];
 #define BAND_T(slot) do { if (tid == 0 && rank <= 1 && blockIdx.x < kBandCluster) { const long long now_ = clock64(); g_band_prof[rank * 8 + (slot)] += now_ - t_prev; t_prev = now_; } } while (0)
@@ -781,10 +825,13 @@ k_band_chol(int n, double* A, int64_t ld, double* dinv, int* info, unsigned char
         const bool next_in_list = m > 0 && sm.rows[0] == k + 1;
         const int npairs = m * (m + 1) / 2;
         if (rank == 0) {
-            if (next_in_list) update_pair(k + 1, k + 1, k);
+            // the next diagonal tile belongs to this cluster alone when it lies inside its own range: its update can stay on the CTA
+            const bool fuse = next_in_list && k + 1 < kend && k + 1 < shared_from;
+            if (fuse) band_diag_update_into_scratch(sm, n, A, ld, k + 1, k, sm.A);
+            else if (next_in_list) update_pair(k + 1, k + 1, k);
             __syncthreads();
             BAND_T(4);
-            if (k + 1 < kend) potrf64_blk_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk, sm.A, g_potrf_prof, info_base);
+            if (k + 1 < kend) potrf64_blk_dev<true>(n, (k + 1) * NB, A, ld, dinv + (size_t)(k + 1) * NB * NB, info, F, nblk, sm.A, g_potrf_prof, info_base, fuse);
             BAND_T(5);
         } else {
             for (int p = (next_in_list ? 1 : 0) + (rank - 1); p < npairs; p += kBandCluster - 1) {
